@@ -1,0 +1,246 @@
+/*
+ * rabacus_b200.h -- C ABI of librabacus_b200.so
+ *
+ * A B200-native (sm_100a, FP64 CUDA) replacement for the hot path behind
+ * galtay/rabacus' f2py module `rabacus_fc`: ray-traced HI/HeI/HeII column
+ * densities, the angle x frequency integrals giving photo-ionisation / heating
+ * rates per cell, and the per-cell ionisation / temperature equilibrium solve,
+ * iterated to convergence.  Every entry point cites the reference interface it
+ * replaces (paths relative to the reference root, v0.9.5).  INTEGRATION.md
+ * shows the Python binding a Rabacus maintainer would add.
+ *
+ * Conventions
+ *  - plain C: pointers and sizes only; all arrays 1-D contiguous float64, cgs.
+ *  - "host" entry points take HOST pointers (numpy buffers) and do their own
+ *    host<->device copies; the rb_plan_* API keeps a batch of problems resident
+ *    in HBM and exposes the sweep stages for multi-GPU cell sharding.
+ *  - return value 0 = success; otherwise one of RB_ERR_* (the reference calls
+ *    Fortran `stop`, i.e. kills the process: sphere_bgnd.f90:198-201,284-287;
+ *    ion_solver.f90:536-546,804-809,852-856,369-372; geometry.f90:138-142).
+ *    rb_strerror() gives the message.
+ *  - there is no CPU fallback: without a CUDA device every compute entry
+ *    returns RB_ERR_CUDA.
+ */
+#ifndef RABACUS_B200_H
+#define RABACUS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_OK 0
+#define RB_ERR_EDGES_NOT_MONOTONIC 1
+#define RB_ERR_MAX_ITER_OUTER 2
+#define RB_ERR_MAX_ITER_PCE 3
+#define RB_ERR_MAX_ITER_PCTE 4
+#define RB_ERR_T_NOT_BRACKETED 5
+#define RB_ERR_NAN 6
+#define RB_ERR_RAY_GEOMETRY 7
+#define RB_ERR_BAD_ARG 8
+#define RB_ERR_UNSUPPORTED 9 /* rec_meth != fixed: SURVEY 8(f) "next" */
+#define RB_ERR_CUDA 10
+#define RB_ERR_NOMEM 11
+
+/* geometry / driver selector for plans */
+#define RB_GEOM_SPHERE_BGND 0      /* rabacus/f2py/sphere_bgnd.f90 */
+#define RB_GEOM_SPHERE_STROMGREN 1 /* rabacus/f2py/sphere_stromgren.f90 */
+#define RB_GEOM_SLAB_PLANE_1 2     /* rabacus/f2py/slab_plane.f90 sweep_1 */
+#define RB_GEOM_SLAB_PLANE_2 3     /* rabacus/f2py/slab_plane.f90 sweep_2 */
+#define RB_GEOM_SLAB_BGND 4        /* rabacus/f2py/slab_bgnd.f90 */
+
+/* What a solve reports back across the boundary (the reference documents an
+ * `itr` attribute, sphere_bgnd.py:118, but never returns it). */
+typedef struct rb_info {
+  int iters;          /* sweeps performed (max over the batch) */
+  int n_launches;     /* CUDA kernels launched by this call */
+  double resid;       /* last max |ne_new/ne_old - 1| (NaN if not computed) */
+  double ms_total;    /* wall time of the call, host clock, incl. copies */
+  double ms_device;   /* device time of the iteration loop (CUDA events) */
+  double ms_columns;  /* summed device time of the column (ray / scan) kernel */
+  double ms_nu;       /* summed device time of the frequency-integral kernel */
+  double ms_cell;     /* summed device time of the cell-solver kernel */
+  long long evals;    /* cell*ray*frequency evaluations performed */
+} rb_info;
+
+const char *rb_strerror(int code);
+/* number of visible CUDA devices (0 if none / no driver) */
+int rb_device_count(void);
+const char *rb_version(void);
+
+/* ------------------------------------------------------------------------
+ * Host-pointer entry points == the f2py boundary.
+ *
+ * rb_sphere_bgnd_solve  <-  rabacus_fc.sphere_bgnd.sphere_bgnd_solve
+ *   (rabacus/f2py/sphere_bgnd.py:216-244 ; sphere_bgnd.f90:107-155).
+ *   Edges[Nl+1], nH/nHe/T[Nl] are intent(inout): T carries the equilibrium
+ *   temperature on return when i_find_Teq == 1.  The 17 outputs are [Nl].
+ *   SURVEY Q1 (the 1/2 (old + sum) recurrence of the mu quadrature) is
+ *   reproduced.  Sweep order is Jacobi (DESIGN.md "Sweep order").
+ * ---------------------------------------------------------------------- */
+int rb_sphere_bgnd_solve(
+    double *Edges, double *nH, double *nHe, double *T, int Nmu,
+    const double *E_eV, const double *shape, int i_rec_meth, double fixed_fcA,
+    int i_photo_fit, int i_rate_fit, int i_find_Teq, int i_thin,
+    double em_H1_fac, double em_He1_fac, double em_He2_fac, double z, double Hz,
+    double tol, int Nl, int Nnu, double *xH1, double *xH2, double *xHe1,
+    double *xHe2, double *xHe3, double *H1i_src, double *He1i_src,
+    double *He2i_src, double *H1i_rec, double *He1i_rec, double *He2i_rec,
+    double *H1h_src, double *He1h_src, double *He2h_src, double *H1h_rec,
+    double *He1h_rec, double *He2h_rec, rb_info *info);
+
+/* rb_sphere_stromgren_solve <- rabacus_fc.sphere_stromgren.sphere_stromgren_solve
+ *   (rabacus/f2py/sphere_stromgren.py:215-241 ; sphere_stromgren.f90:111-158) */
+int rb_sphere_stromgren_solve(
+    double *Edges, double *nH, double *nHe, double *T, int Nmu,
+    const double *E_eV, const double *shape, int i_rec_meth, double fixed_fcA,
+    int i_photo_fit, int i_rate_fit, int i_find_Teq, int i_thin,
+    double em_H1_fac, double em_He1_fac, double em_He2_fac, double z, double Hz,
+    double tol, int Nl, int Nnu, double *xH1, double *xH2, double *xHe1,
+    double *xHe2, double *xHe3, double *H1i_src, double *He1i_src,
+    double *He2i_src, double *H1i_rec, double *He1i_rec, double *He2i_rec,
+    double *H1h_src, double *He1h_src, double *He2h_src, double *H1h_rec,
+    double *He1h_rec, double *He2h_rec, rb_info *info);
+
+/* rb_slab_bgnd_solve <- rabacus_fc.slab_bgnd.slab_bgnd_solve
+ *   (rabacus/f2py/slab_bgnd.py:198-220 ; slab_bgnd.f90:97-129); only T is inout */
+int rb_slab_bgnd_solve(
+    const double *Edges, const double *nH, const double *nHe, double *T,
+    const double *E_eV, const double *shape, int i_rec_meth, double fixed_fcA,
+    int i_photo_fit, int i_rate_fit, int i_find_Teq, int i_thin, double z,
+    double Hz, double tol, int Nl, int Nnu, double *xH1, double *xH2,
+    double *xHe1, double *xHe2, double *xHe3, double *H1i_src, double *He1i_src,
+    double *He2i_src, double *H1i_rec, double *He1i_rec, double *He2i_rec,
+    double *H1h_src, double *He1h_src, double *He2h_src, double *H1h_rec,
+    double *He1h_rec, double *He2h_rec, rb_info *info);
+
+/* rb_slab_plane_solve <- rabacus_fc.slab_plane.slab_plane_solve
+ *   (rabacus/f2py/slab_plane.py:178-200,419-441 ; slab_plane.f90:105-137) */
+int rb_slab_plane_solve(
+    const double *Edges, const double *nH, const double *nHe, double *T,
+    const double *E_eV, const double *shape, int i_2side, int i_rec_meth,
+    double fixed_fcA, int i_photo_fit, int i_rate_fit, int i_find_Teq,
+    int i_thin, double z, double Hz, double tol, int Nl, int Nnu, double *xH1,
+    double *xH2, double *xHe1, double *xHe2, double *xHe3, double *H1i_src,
+    double *He1i_src, double *He2i_src, double *H1i_rec, double *He1i_rec,
+    double *He2i_rec, double *H1h_src, double *He1h_src, double *He2h_src,
+    double *H1h_rec, double *He1h_rec, double *He2h_rec, rb_info *info);
+
+/* rb_set_column_vs_impact <- rabacus_fc.sphere_base.set_column_vs_impact
+ *   (rabacus/f2py/sphere_base.py:182-193 ; sphere_base.f90:1115-1205) */
+int rb_set_column_vs_impact(const double *xH1, const double *xH2,
+                            const double *xHe1, const double *xHe2,
+                            const double *xHe3, const double *Edges,
+                            const double *nH, const double *nHe,
+                            const double *T, int Nl, double *NH, double *NHe,
+                            double *NH1, double *NHe1, double *NHe2);
+
+/* Single-zone batch API <- rabacus_fc.ion_solver.solve_{ce,pce,pcte}_{s,v},
+ *   rabacus_fc.chem_cool_rates.get_{kchem,kcool}_{s,v}
+ *   (rabacus/f2py/ion_solver.py:150-159,371-380,633-643 ;
+ *    rabacus/f2py/chem_cool_rates.py:104-106,332-334).
+ *   `lockstep` != 0 selects the `_v` semantics (all zones iterate until all
+ *   converge, ion_solver.f90:620,988); 0 runs the scalar solver per zone. */
+int rb_get_kchem(const double *T, const double *fcA_H2, const double *fcA_He2,
+                 const double *fcA_He3, int irate, int nn, double *reH2,
+                 double *reHe2, double *reHe3, double *ciH1, double *ciHe1,
+                 double *ciHe2);
+int rb_get_kcool(const double *T, const double *fcA_H2, const double *fcA_He2,
+                 const double *fcA_He3, int irate, int nn, double *recH2,
+                 double *recHe2, double *recHe3, double *cicH1, double *cicHe1,
+                 double *cicHe2, double *cecH1, double *cecHe2, double *bremss,
+                 double *compton);
+int rb_solve_ce(const double *reH2, const double *reHe2, const double *reHe3,
+                const double *ciH1, const double *ciHe1, const double *ciHe2,
+                int nn, double *xH1, double *xH2, double *xHe1, double *xHe2,
+                double *xHe3);
+int rb_solve_pce(const double *nH, const double *nHe, const double *reH2,
+                 const double *reHe2, const double *reHe3, const double *ciH1,
+                 const double *ciHe1, const double *ciHe2, const double *H1i,
+                 const double *He1i, const double *He2i, double tol, int nn,
+                 int lockstep, double *xH1, double *xH2, double *xHe1,
+                 double *xHe2, double *xHe3);
+int rb_solve_pcte(const double *nH, const double *nHe, const double *H1i,
+                  const double *He1i, const double *He2i, const double *H1h,
+                  const double *He1h, const double *He2h, double z, double Hz,
+                  const double *fcA_H2, const double *fcA_He2,
+                  const double *fcA_He3, int irate, double tol, int nn,
+                  int lockstep, double *xH1, double *xH2, double *xHe1,
+                  double *xHe2, double *xHe3, double *T);
+
+/* Verner 96 cross sections  <- rabacus_fc.photo_xsections.return_sigma_*
+ *   (rabacus/f2py/photo_xsections.f90:100-180); species 0=H1, 1=He1, 2=He2.
+ *   Host-side helper (no GPU needed). */
+int rb_photo_sigma(int species, const double *E_eV, int nn, double *sigma);
+double rb_photo_Eth(int species);
+/* Gauss-Legendre rule used for the polar angles
+ *   <- p_quadrature_rule (rabacus/f2py/legendre_polynomial.f90:815-864).
+ *   Host-side helper (no GPU needed). */
+int rb_gauss_legendre(int n, double *x, double *w);
+
+/* ------------------------------------------------------------------------
+ * Device-resident plan API: a batch of `n_problems` independent problems of
+ * identical shape (Nl, Nnu, Nmu) and solver flags, resident in HBM.  Used by
+ * bench.py, by the parameter-sweep driver (problems sharded over
+ * GPUs, no communication) and by the cell-sharded multi-GPU driver (each rank
+ * sweeps cells {cell_start + j*cell_stride}, the host all-gathers the state
+ * fields through torch.distributed/NCCL between rb_plan_sweep_local and
+ * rb_plan_finish_sweep).
+ * ---------------------------------------------------------------------- */
+typedef struct rb_plan rb_plan;
+
+typedef struct rb_plan_desc {
+  int geometry;   /* RB_GEOM_* */
+  int n_problems; /* batch size B */
+  int Nl, Nnu, Nmu;
+  int i_find_Teq;
+  double fixed_fcA;
+  double tol;
+  int device;     /* CUDA device ordinal, -1 = current */
+  int max_sweeps; /* 0: reference limits; >0: stop every problem after this many */
+} rb_plan_desc;
+
+int rb_plan_create(rb_plan **plan, const rb_plan_desc *desc);
+void rb_plan_destroy(rb_plan *plan);
+/* stage one problem's inputs (host pointers, copied into pinned staging) */
+int rb_plan_set_problem(rb_plan *plan, int b, const double *Edges,
+                        const double *nH, const double *nHe, const double *T,
+                        const double *E_eV, const double *shape, double z,
+                        double Hz);
+/* H2D copy of everything staged; resets iteration state */
+int rb_plan_upload(rb_plan *plan);
+/* optically-thin initial state (sphere_bgnd.f90:379-499 and twins) */
+int rb_plan_thin(rb_plan *plan);
+/* one Jacobi sweep over the local cells il = cell_start + j*cell_stride:
+ * columns -> frequency/angle integrals -> cell solve.  Does NOT test
+ * convergence. */
+int rb_plan_sweep_local(rb_plan *plan, int cell_start, int cell_stride);
+/* convergence test on n_e over all cells + iteration bookkeeping
+ * (sphere_bgnd.f90:284-296); returns the number of still-active problems */
+int rb_plan_finish_sweep(rb_plan *plan, int *n_active);
+/* thin state + sweeps to convergence on one GPU */
+int rb_plan_solve(rb_plan *plan, rb_info *info);
+/* D2H of one problem's results (un-reversed to the input order) */
+int rb_plan_get_problem(rb_plan *plan, int b, double *T, double *xH1,
+                        double *xH2, double *xHe1, double *xHe2, double *xHe3,
+                        double *H1i_src, double *He1i_src, double *He2i_src,
+                        double *H1h_src, double *He1h_src, double *He2h_src,
+                        int *iters);
+/* device pointers for torch / NCCL interop: fields are [n_problems*Nl] float64.
+ * 0..4 = xH1,xH2,xHe1,xHe2,xHe3 ; 5 = T ; 6..11 = H1i,He1i,He2i,H1h,He1h,He2h src */
+void *rb_plan_field_ptr(rb_plan *plan, int field);
+/* the CUDA stream (cudaStream_t) all plan work is enqueued on */
+void *rb_plan_stream(rb_plan *plan);
+int rb_plan_sync(rb_plan *plan);
+long long rb_plan_evals_per_sweep(const rb_plan *plan);
+int rb_plan_last_info(const rb_plan *plan, rb_info *info);
+
+/* FP64 pipe micro-benchmarks used as roofline denominators (bench.py):
+ * kind 0 = DFMA, 1 = exp, 2 = sqrt, 3 = pow.  Returns operations / second. */
+int rb_microbench(int kind, int device, double *ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

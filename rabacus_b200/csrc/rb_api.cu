@@ -1,0 +1,966 @@
+// rb_api.cu -- host side of librabacus_b200.so: plans, staging, iteration
+// control and the extern "C" boundary declared in include/rabacus_b200.h.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "rb_kernels.cuh"
+
+using namespace rb;
+
+#define CK(call)                                   \
+  do {                                             \
+    cudaError_t e_ = (call);                       \
+    if (e_ != cudaSuccess) {                       \
+      rb_set_cuda_error(e_, __FILE__, __LINE__);   \
+      return RB_ERR_CUDA;                          \
+    }                                              \
+  } while (0)
+
+static thread_local char g_cuda_msg[256] = "";
+static void rb_set_cuda_error(cudaError_t e, const char *file, int line) {
+  snprintf(g_cuda_msg, sizeof(g_cuda_msg), "CUDA error: %s (%s:%d)", cudaGetErrorString(e),
+           file, line);
+}
+
+extern "C" const char *rb_strerror(int code) {
+  switch (code) {
+    case RB_OK: return "ok";
+    case RB_ERR_EDGES_NOT_MONOTONIC: return "Edges not monotonic";
+    case RB_ERR_MAX_ITER_OUTER: return "MAX_ITER reached in the sweep loop";
+    case RB_ERR_MAX_ITER_PCE: return "solve_pce: iter > MAX_ITER";
+    case RB_ERR_MAX_ITER_PCTE: return "solve_pcte: iter > MAX_ITER";
+    case RB_ERR_T_NOT_BRACKETED: return "Teq not bracketed";
+    case RB_ERR_NAN: return "NaN in solve_ce";
+    case RB_ERR_RAY_GEOMETRY: return "ray geometry undefined (no shell edge <= impact parameter)";
+    case RB_ERR_BAD_ARG: return "bad argument";
+    case RB_ERR_UNSUPPORTED: return "option not supported by the CUDA path (only rec_meth='fixed', verner, hg97)";
+    case RB_ERR_CUDA: return g_cuda_msg[0] ? g_cuda_msg : "CUDA error / no CUDA device";
+    case RB_ERR_NOMEM: return "out of memory";
+  }
+  return "unknown error";
+}
+
+extern "C" const char *rb_version(void) { return "rabacus_b200 0.1 (sm_100a, fp64)"; }
+
+extern "C" int rb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------
+// host helpers: cross sections, Gauss-Legendre nodes, spectral tables
+// ---------------------------------------------------------------------------
+extern "C" int rb_photo_sigma(int species, const double *E_eV, int nn, double *sigma) {
+  if (species < 0 || species > 2 || nn < 0) return RB_ERR_BAD_ARG;
+  for (int i = 0; i < nn; ++i) sigma[i] = v96_sigma(species, E_eV[i]);
+  return RB_OK;
+}
+extern "C" double rb_photo_Eth(int species) { return v96_row(species).Eth; }
+
+// Gauss-Legendre nodes and weights from the Jacobi matrix of the Legendre
+// recurrence (Golub & Welsch), diagonalised with the implicit QL algorithm --
+// the same method as the reference (legendre_polynomial.f90:6-207,815-864), so
+// nodes agree to rounding.  0-based arrays.
+extern "C" int rb_gauss_legendre(int n, double *x, double *w) {
+  if (n < 1) return RB_ERR_BAD_ARG;
+  std::vector<double> d(n, 0.0), e(n + 1, 0.0), z(n, 0.0);
+  for (int i = 1; i <= n; ++i) e[i - 1] = sqrt((double)(i * i) / (double)(4 * i * i - 1));
+  z[0] = sqrt(2.0);
+  const double eps = 2.220446049250313e-16;
+  if (n > 1) {
+    e[n - 1] = 0.0;
+    for (int l = 0; l < n; ++l) {
+      int iter = 0;
+      for (;;) {
+        int m = l;
+        for (; m < n - 1; ++m)
+          if (fabs(e[m]) <= eps * (fabs(d[m]) + fabs(d[m + 1]))) break;
+        double p = d[l];
+        if (m == l) break;
+        if (iter++ >= 30) return RB_ERR_BAD_ARG;
+        double g = (d[l + 1] - p) / (2.0 * e[l]);
+        double r = sqrt(g * g + 1.0);
+        g = d[m] - p + e[l] / (g + copysign(r, g));
+        double s = 1.0, c = 1.0;
+        p = 0.0;
+        for (int i = m - 1; i >= l; --i) {
+          double f = s * e[i];
+          const double bb = c * e[i];
+          if (fabs(g) <= fabs(f)) {
+            c = g / f;
+            r = sqrt(c * c + 1.0);
+            e[i + 1] = f * r;
+            s = 1.0 / r;
+            c = c * s;
+          } else {
+            s = f / g;
+            r = sqrt(s * s + 1.0);
+            e[i + 1] = g * r;
+            c = 1.0 / r;
+            s = s * c;
+          }
+          g = d[i + 1] - p;
+          r = (d[i] - g) * s + 2.0 * c * bb;
+          p = s * r;
+          d[i + 1] = g + p;
+          g = c * r - bb;
+          f = z[i + 1];
+          z[i + 1] = s * z[i] + c * f;
+          z[i] = c * z[i] - s * f;
+        }
+        d[l] = d[l] - p;
+        e[l] = g;
+        e[m] = 0.0;
+      }
+    }
+    for (int i = 0; i < n - 1; ++i) {  // ascending selection sort, as the reference
+      int k = i;
+      double p = d[i];
+      for (int j = i + 1; j < n; ++j)
+        if (d[j] < p) { k = j; p = d[j]; }
+      if (k != i) {
+        d[k] = d[i]; d[i] = p;
+        const double t = z[i]; z[i] = z[k]; z[k] = t;
+      }
+    }
+  }
+  for (int i = 0; i < n; ++i) { x[i] = d[i]; w[i] = z[i] * z[i]; }
+  return RB_OK;
+}
+
+static int source_kind(int geom) {  // 0 background, 1 point, 2 plane
+  switch (geom) {
+    case RB_GEOM_SPHERE_BGND: case RB_GEOM_SLAB_BGND: return 0;
+    case RB_GEOM_SPHERE_STROMGREN: return 1;
+    default: return 2;
+  }
+}
+
+// Per-frequency table for one problem: [Nnu][9] = sigma_X/sigma_X,th (3),
+// W_ion,X (3), W_heat,X (3), plus thin[6] = sum_k W.
+//   y_ion,X(k)  = base_k * sigma_X(k)                  (source_background.f90:306-307)
+//   y_heat,X(k) = y_ion,X(k) * (E_k - E_th,X) * eV_2_erg   (:350)
+//   base_k = 4 pi I_k/(E_k h) | F_k/(E_k h) | L_k/(E_k h)   (s_bgnd:306, s_plane:296, s_point:348;
+//            the point source's 1/(4 pi r^2) is applied per cell in the kernel)
+//   trapezoid (utils.f90:19-20) folded into weights: W_k = y_k * (dE_{k-1}+dE_k)/2.
+// Nnu == 1 (monochromatic): rate = Fn*sigma*a, heat = Fn*sigma*(E-Eth)*eV_2_erg*a
+//   with Fn = 4 pi I/E*erg_2_eV | F/E*erg_2_eV | L/E*erg_2_eV
+//   (source_background.f90:111-112,195-197,231-233).
+static void build_spec_table(int geom, const double *E, const double *shape, int Nnu,
+                             const double sigma_th[3], double *tab, double *thin) {
+  const int kind = source_kind(geom);
+  const double four_pi = 4.0 * RB_PI;
+  for (int q = 0; q < 6; ++q) thin[q] = 0.0;
+  for (int k = 0; k < Nnu; ++k) {
+    double *row = tab + (size_t)k * kSpecStride;
+    double wk, base;
+    if (Nnu == 1) {
+      wk = 1.0;
+      base = (kind == 0 ? four_pi * shape[0] : shape[0]) / E[0] * RB_ERG_2_EV;
+    } else {
+      const double dlo = (k > 0) ? (E[k] - E[k - 1]) : 0.0;
+      const double dhi = (k < Nnu - 1) ? (E[k + 1] - E[k]) : 0.0;
+      wk = 0.5 * (dlo + dhi);
+      base = (kind == 0 ? four_pi * shape[k] : shape[k]) / (E[k] * RB_H_ERG_S);
+    }
+    for (int X = 0; X < 3; ++X) {
+      const double sig = v96_sigma(X, E[k]);
+      const double Eth = v96_row(X).Eth;
+      row[X] = sig / sigma_th[X];                       // sphere_bgnd.f90:669-671
+      const double yi = base * sig;
+      const double yh = yi * (E[k] - Eth) * RB_EV_2_ERG;
+      row[3 + X] = yi * wk;
+      row[6 + X] = yh * wk;
+      thin[X] += row[3 + X];
+      thin[3 + X] += row[6 + X];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------
+struct rb_plan {
+  rb_plan_desc d;
+  int Ndir;
+  double sigma_th[3];
+  cudaStream_t stream = nullptr;
+  // device buffers
+  double *dEdges = nullptr, *dnH = nullptr, *dnHe = nullptr, *dT = nullptr;
+  double *dx = nullptr;     // 5*B*Nl
+  double *dsrc = nullptr;   // 6*B*Nl
+  double *dconv = nullptr;
+  double4 *dpack = nullptr;
+  double *dspec = nullptr, *dthin = nullptr, *dmu = nullptr, *dcol = nullptr, *dzHz = nullptr;
+  int *dflags = nullptr;    // active, notconv, iters, err : 4*B, then nactive
+  unsigned long long *dresid = nullptr;
+  // pinned host staging
+  double *hEdges = nullptr, *hnH = nullptr, *hnHe = nullptr, *hT = nullptr, *hspec = nullptr,
+         *hthin = nullptr, *hzHz = nullptr, *hout = nullptr;
+  int *hflags = nullptr;
+  std::vector<char> reversed;
+  std::vector<double> mu, wmu;
+  cudaEvent_t ev[8];
+  bool ev_ok = false;
+  rb_info info;
+  PlanDev P;
+};
+
+static size_t cells(const rb_plan *p) { return (size_t)p->d.n_problems * p->d.Nl; }
+
+extern "C" void rb_plan_destroy(rb_plan *p) {
+  if (!p) return;
+  cudaFree(p->dEdges); cudaFree(p->dnH); cudaFree(p->dnHe); cudaFree(p->dT);
+  cudaFree(p->dx); cudaFree(p->dsrc); cudaFree(p->dconv); cudaFree(p->dpack);
+  cudaFree(p->dspec); cudaFree(p->dthin); cudaFree(p->dmu); cudaFree(p->dcol);
+  cudaFree(p->dzHz); cudaFree(p->dflags); cudaFree(p->dresid);
+  cudaFreeHost(p->hEdges); cudaFreeHost(p->hnH); cudaFreeHost(p->hnHe); cudaFreeHost(p->hT);
+  cudaFreeHost(p->hspec); cudaFreeHost(p->hthin); cudaFreeHost(p->hzHz);
+  cudaFreeHost(p->hout); cudaFreeHost(p->hflags);
+  if (p->ev_ok) for (auto &e : p->ev) cudaEventDestroy(e);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  cudaGetLastError();
+  delete p;
+}
+
+extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
+  if (!out || !desc) return RB_ERR_BAD_ARG;
+  *out = nullptr;
+  const rb_plan_desc &d = *desc;
+  if (d.geometry < 0 || d.geometry > RB_GEOM_SLAB_BGND || d.n_problems < 1 || d.Nl < 1 ||
+      d.Nnu < 1 || !(d.tol > 0.0))
+    return RB_ERR_BAD_ARG;
+  if (d.geometry == RB_GEOM_SPHERE_BGND && d.Nmu < 1) return RB_ERR_BAD_ARG;
+  if (d.Nl > 512 * 16) return RB_ERR_UNSUPPORTED;  // lock-step thin-state kernel limit
+  if (rb_device_count() < 1) {
+    snprintf(g_cuda_msg, sizeof(g_cuda_msg), "no CUDA device visible (there is no CPU fallback)");
+    return RB_ERR_CUDA;
+  }
+  if (d.device >= 0) CK(cudaSetDevice(d.device));
+  rb_plan *p = new rb_plan();
+  p->d = d;
+  switch (d.geometry) {
+    case RB_GEOM_SPHERE_BGND: p->Ndir = d.Nmu; break;
+    case RB_GEOM_SLAB_PLANE_2: case RB_GEOM_SLAB_BGND: p->Ndir = 2; break;
+    default: p->Ndir = 1;
+  }
+  for (int X = 0; X < 3; ++X) p->sigma_th[X] = v96_sigma(X, v96_row(X).Eth);
+  const size_t B = d.n_problems, Nl = d.Nl, Nnu = d.Nnu, NC = B * Nl;
+#define ALLOC(ptr, n)                                                          \
+  do {                                                                         \
+    if (cudaMalloc((void **)&(ptr), (n)) != cudaSuccess) {                     \
+      cudaGetLastError();                                                      \
+      rb_plan_destroy(p);                                                      \
+      return RB_ERR_NOMEM;                                                     \
+    }                                                                          \
+  } while (0)
+#define HALLOC(ptr, n)                                                         \
+  do {                                                                         \
+    if (cudaMallocHost((void **)&(ptr), (n)) != cudaSuccess) {                 \
+      cudaGetLastError();                                                      \
+      rb_plan_destroy(p);                                                      \
+      return RB_ERR_NOMEM;                                                     \
+    }                                                                          \
+  } while (0)
+  ALLOC(p->dEdges, B * (Nl + 1) * 8); ALLOC(p->dnH, NC * 8); ALLOC(p->dnHe, NC * 8);
+  ALLOC(p->dT, NC * 8); ALLOC(p->dx, 5 * NC * 8); ALLOC(p->dsrc, 6 * NC * 8);
+  ALLOC(p->dconv, NC * 8); ALLOC(p->dpack, B * (Nl + 1) * sizeof(double4));
+  ALLOC(p->dspec, B * Nnu * kSpecStride * 8); ALLOC(p->dthin, B * 6 * 8);
+  ALLOC(p->dmu, 2 * (size_t)std::max(1, d.Nmu) * 8);
+  ALLOC(p->dcol, NC * (size_t)p->Ndir * 3 * 8); ALLOC(p->dzHz, B * 2 * 8);
+  ALLOC(p->dflags, (4 * B + 4) * sizeof(int)); ALLOC(p->dresid, B * 8);
+  HALLOC(p->hEdges, B * (Nl + 1) * 8); HALLOC(p->hnH, NC * 8); HALLOC(p->hnHe, NC * 8);
+  HALLOC(p->hT, NC * 8); HALLOC(p->hspec, B * Nnu * kSpecStride * 8);
+  HALLOC(p->hthin, B * 6 * 8); HALLOC(p->hzHz, B * 2 * 8); HALLOC(p->hout, 12 * NC * 8);
+  HALLOC(p->hflags, (4 * B + 4) * sizeof(int));
+#undef ALLOC
+#undef HALLOC
+  p->reversed.assign(B, 0);
+  if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    rb_plan_destroy(p);
+    return RB_ERR_CUDA;
+  }
+  for (auto &e : p->ev) cudaEventCreate(&e);
+  p->ev_ok = true;
+  if (d.geometry == RB_GEOM_SPHERE_BGND) {
+    p->mu.resize(d.Nmu); p->wmu.resize(d.Nmu);
+    rb_gauss_legendre(d.Nmu, p->mu.data(), p->wmu.data());  // sphere_bgnd.f90:743
+    cudaMemcpy(p->dmu, p->mu.data(), d.Nmu * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(p->dmu + d.Nmu, p->wmu.data(), d.Nmu * 8, cudaMemcpyHostToDevice);
+  }
+  memset(&p->info, 0, sizeof(p->info));
+  PlanDev &P = p->P;
+  P.B = d.n_problems; P.Nl = d.Nl; P.Nnu = d.Nnu; P.Nmu = d.Nmu; P.Ndir = p->Ndir;
+  P.geom = d.geometry; P.find_Teq = d.i_find_Teq; P.max_sweeps = d.max_sweeps;
+  P.fcA = d.fixed_fcA; P.tol = d.tol; P.tol_inner = d.tol * RB_TOL_FRAC;
+  for (int X = 0; X < 3; ++X) P.sigma_th[X] = p->sigma_th[X];
+  P.Edges = p->dEdges; P.nH = p->dnH; P.nHe = p->dnHe; P.T = p->dT;
+  for (int i = 0; i < 5; ++i) P.x[i] = p->dx + i * NC;
+  for (int i = 0; i < 6; ++i) P.src[i] = p->dsrc + i * NC;
+  P.conv_old = p->dconv; P.pack = p->dpack; P.spec = p->dspec; P.thin = p->dthin;
+  P.mu = p->dmu; P.wmu = p->dmu + std::max(1, d.Nmu); P.col = p->dcol; P.zHz = p->dzHz;
+  if (d.geometry == RB_GEOM_SPHERE_BGND) P.wmu = p->dmu + d.Nmu;
+  P.active = p->dflags; P.notconv = p->dflags + B; P.iters = p->dflags + 2 * B;
+  P.err = p->dflags + 3 * B; P.nactive = p->dflags + 4 * B; P.resid_bits = p->dresid;
+  *out = p;
+  return RB_OK;
+}
+
+static bool mono_inc(const double *a, int n) {  // sphere_base.f90:1493-1509
+  for (int i = 1; i < n; ++i) if (a[i] < a[i - 1]) return false;
+  return true;
+}
+static bool mono_dec(const double *a, int n) {  // sphere_base.f90:1467-1483
+  for (int i = 1; i < n; ++i) if (a[i] > a[i - 1]) return false;
+  return true;
+}
+
+extern "C" int rb_plan_set_problem(rb_plan *p, int b, const double *Edges, const double *nH,
+                                   const double *nHe, const double *T, const double *E_eV,
+                                   const double *shape, double z, double Hz) {
+  if (!p || b < 0 || b >= p->d.n_problems) return RB_ERR_BAD_ARG;
+  const int Nl = p->d.Nl, Nnu = p->d.Nnu, g = p->d.geometry;
+  // orientation: SphereBgnd wants decreasing Edges (sphere_bgnd.f90:182-202),
+  // SphereStromgren increasing (sphere_stromgren.f90:186-204); slabs as given.
+  bool rev = false;
+  if (g == RB_GEOM_SPHERE_BGND) {
+    if (mono_inc(Edges, Nl + 1)) rev = true;
+    else if (!mono_dec(Edges, Nl + 1)) return RB_ERR_EDGES_NOT_MONOTONIC;
+  } else if (g == RB_GEOM_SPHERE_STROMGREN) {
+    if (mono_dec(Edges, Nl + 1)) rev = true;
+    else if (!mono_inc(Edges, Nl + 1)) return RB_ERR_EDGES_NOT_MONOTONIC;
+  }
+  p->reversed[b] = rev;
+  double *hE = p->hEdges + (size_t)b * (Nl + 1);
+  double *hH = p->hnH + (size_t)b * Nl, *hHe = p->hnHe + (size_t)b * Nl,
+         *hT = p->hT + (size_t)b * Nl;
+  for (int i = 0; i <= Nl; ++i) hE[i] = Edges[rev ? Nl - i : i];
+  for (int i = 0; i < Nl; ++i) {
+    const int s = rev ? Nl - 1 - i : i;
+    hH[i] = nH[s]; hHe[i] = nHe[s]; hT[i] = T[s];
+  }
+  build_spec_table(g, E_eV, shape, Nnu, p->sigma_th,
+                   p->hspec + (size_t)b * Nnu * kSpecStride, p->hthin + (size_t)b * 6);
+  p->hzHz[2 * b] = z;
+  p->hzHz[2 * b + 1] = Hz;
+  return RB_OK;
+}
+
+extern "C" int rb_plan_upload(rb_plan *p) {
+  if (!p) return RB_ERR_BAD_ARG;
+  const size_t B = p->d.n_problems, Nl = p->d.Nl, Nnu = p->d.Nnu, NC = B * Nl;
+  cudaStream_t s = p->stream;
+  CK(cudaMemcpyAsync(p->dEdges, p->hEdges, B * (Nl + 1) * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->dnH, p->hnH, NC * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->dnHe, p->hnHe, NC * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->dT, p->hT, NC * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->dspec, p->hspec, B * Nnu * kSpecStride * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->dthin, p->hthin, B * 6 * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->dzHz, p->hzHz, B * 2 * 8, cudaMemcpyHostToDevice, s));
+  for (size_t b = 0; b < B; ++b) {
+    p->hflags[b] = 1; p->hflags[B + b] = 0; p->hflags[2 * B + b] = 0; p->hflags[3 * B + b] = 0;
+  }
+  p->hflags[4 * B] = (int)B;
+  CK(cudaMemcpyAsync(p->dflags, p->hflags, (4 * B + 4) * sizeof(int), cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(p->dresid, 0, B * 8, s));
+  memset(&p->info, 0, sizeof(p->info));
+  p->info.resid = NAN;
+  return RB_OK;
+}
+
+extern "C" int rb_plan_thin(rb_plan *p) {
+  if (!p) return RB_ERR_BAD_ARG;
+  const int Nl = p->d.Nl, B = p->d.n_problems;
+  int cpt = 1;
+  while (cpt * 512 < Nl) cpt *= 4;
+  int threads = (Nl + cpt - 1) / cpt;
+  threads = ((threads + 31) / 32) * 32;
+  switch (cpt) {
+    case 1: k_thin_state<1><<<B, threads, 0, p->stream>>>(p->P); break;
+    case 4: k_thin_state<4><<<B, threads, 0, p->stream>>>(p->P); break;
+    case 16: k_thin_state<16><<<B, threads, 0, p->stream>>>(p->P); break;
+    default: return RB_ERR_UNSUPPORTED;
+  }
+  p->info.n_launches += 1;
+  CK(cudaGetLastError());
+  return RB_OK;
+}
+
+static int group_size(int ndir) {
+  int gs = 8;
+  while (gs < ndir && gs < 128) gs *= 2;
+  return gs;
+}
+
+extern "C" int rb_plan_sweep_local(rb_plan *p, int cell_start, int cell_stride) {
+  if (!p || cell_start < 0 || cell_stride < 1) return RB_ERR_BAD_ARG;
+  const int Nl = p->d.Nl, B = p->d.n_problems, g = p->d.geometry;
+  const bool two = (g == RB_GEOM_SLAB_PLANE_2 || g == RB_GEOM_SLAB_BGND);
+  const int ncell = two ? Nl / 2 : Nl;  // slab_bgnd.f90:686 (Nl2 = Nl/2)
+  const int n_local = (cell_start < ncell) ? (ncell - cell_start + cell_stride - 1) / cell_stride : 0;
+  cudaStream_t s = p->stream;
+  cudaEventRecord(p->ev[0], s);
+  if (g == RB_GEOM_SPHERE_BGND) {
+    dim3 gp((Nl + 1 + 255) / 256, B);
+    k_pack_shells<<<gp, 256, 0, s>>>(p->P);
+    if (n_local > 0) {
+      dim3 gc((n_local + 127) / 128, (p->d.Nmu + 1) / 2, B);
+      k_sphere_columns<128><<<gc, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local);
+    }
+    p->info.n_launches += 2;
+  } else {
+    k_column_taus<512><<<B, 512, 0, s>>>(p->P);
+    p->info.n_launches += 1;
+  }
+  cudaEventRecord(p->ev[1], s);
+  if (n_local > 0) {
+    const int gs = group_size(p->Ndir);
+    const int cpb = 128 / gs;
+    dim3 gn((n_local + cpb - 1) / cpb, B);
+    const size_t smem = (size_t)p->d.Nnu * kSpecStride * sizeof(double);
+    if (g == RB_GEOM_SLAB_BGND) {
+      if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(k_nu_rates<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_nu_rates<1><<<gn, 128, smem, s>>>(p->P, cell_start, cell_stride, n_local, gs);
+    } else {
+      if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(k_nu_rates<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_nu_rates<0><<<gn, 128, smem, s>>>(p->P, cell_start, cell_stride, n_local, gs);
+    }
+    cudaEventRecord(p->ev[2], s);
+    dim3 gs3((n_local + 127) / 128, B);
+    k_cell_solve<<<gs3, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local);
+    p->info.n_launches += 2;
+  } else {
+    cudaEventRecord(p->ev[2], s);
+  }
+  cudaEventRecord(p->ev[3], s);
+  CK(cudaGetLastError());
+  return RB_OK;
+}
+
+extern "C" int rb_plan_finish_sweep(rb_plan *p, int *n_active) {
+  if (!p) return RB_ERR_BAD_ARG;
+  const int Nl = p->d.Nl, B = p->d.n_problems;
+  cudaStream_t s = p->stream;
+  k_reset_resid<<<(B + 255) / 256, 256, 0, s>>>(p->P);
+  dim3 gc((Nl + 255) / 256, B);
+  k_convergence<<<gc, 256, 0, s>>>(p->P);
+  k_finish_sweep<<<1, 256, 0, s>>>(p->P);
+  p->info.n_launches += 3;
+  CK(cudaMemcpyAsync(p->hflags + 4 * B, p->dflags + 4 * B, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  // accumulate per-stage device times of the sweep just finished
+  float ms;
+  if (cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]) == cudaSuccess) p->info.ms_columns += ms;
+  if (cudaEventElapsedTime(&ms, p->ev[1], p->ev[2]) == cudaSuccess) p->info.ms_nu += ms;
+  if (cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]) == cudaSuccess) p->info.ms_cell += ms;
+  cudaGetLastError();
+  p->info.iters += 1;
+  if (n_active) *n_active = p->hflags[4 * B];
+  return RB_OK;
+}
+
+extern "C" long long rb_plan_evals_per_sweep(const rb_plan *p) {
+  if (!p) return 0;
+  const int g = p->d.geometry;
+  const bool two = (g == RB_GEOM_SLAB_PLANE_2 || g == RB_GEOM_SLAB_BGND);
+  const long long ncell = two ? p->d.Nl / 2 : p->d.Nl;
+  return ncell * (long long)p->Ndir * p->d.Nnu;  // per problem
+}
+
+static int plan_check_errors(rb_plan *p) {
+  const size_t B = p->d.n_problems;
+  CK(cudaMemcpyAsync(p->hflags, p->dflags, (4 * B + 4) * sizeof(int), cudaMemcpyDeviceToHost,
+                     p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  int rc = 0;
+  for (size_t b = 0; b < B; ++b) rc = std::max(rc, p->hflags[3 * B + b]);
+  return rc;
+}
+
+extern "C" int rb_plan_solve(rb_plan *p, rb_info *info) {
+  if (!p) return RB_ERR_BAD_ARG;
+  const auto t0 = std::chrono::steady_clock::now();
+  const size_t B = p->d.n_problems;
+  cudaEventRecord(p->ev[4], p->stream);
+  int rc = rb_plan_thin(p);
+  if (rc) return rc;
+  rc = plan_check_errors(p);
+  if (rc) return rc;
+  long long evals = 0;
+  int n_active = (int)B;
+  while (n_active > 0) {
+    rc = rb_plan_sweep_local(p, 0, 1);
+    if (rc) return rc;
+    evals += rb_plan_evals_per_sweep(p) * n_active;
+    rc = rb_plan_finish_sweep(p, &n_active);
+    if (rc) return rc;
+  }
+  cudaEventRecord(p->ev[5], p->stream);
+  rc = plan_check_errors(p);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, p->ev[4], p->ev[5]);
+  p->info.ms_device = ms;
+  p->info.evals = evals;
+  int itmax = 0;
+  for (size_t b = 0; b < B; ++b) itmax = std::max(itmax, p->hflags[2 * B + b]);
+  p->info.iters = itmax;
+  {
+    std::vector<unsigned long long> r(B);
+    cudaMemcpy(r.data(), p->dresid, B * 8, cudaMemcpyDeviceToHost);
+    double mx = 0.0;
+    for (size_t b = 0; b < B; ++b) {
+      double v;
+      memcpy(&v, &r[b], 8);
+      mx = std::max(mx, v);
+    }
+    p->info.resid = mx;
+  }
+  p->info.ms_total =
+      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (info) *info = p->info;
+  return rc;
+}
+
+extern "C" int rb_plan_last_info(const rb_plan *p, rb_info *info) {
+  if (!p || !info) return RB_ERR_BAD_ARG;
+  *info = p->info;
+  return RB_OK;
+}
+
+extern "C" int rb_plan_get_problem(rb_plan *p, int b, double *T, double *xH1, double *xH2,
+                                   double *xHe1, double *xHe2, double *xHe3, double *H1i,
+                                   double *He1i, double *He2i, double *H1h, double *He1h,
+                                   double *He2h, int *iters) {
+  if (!p || b < 0 || b >= p->d.n_problems) return RB_ERR_BAD_ARG;
+  const size_t B = p->d.n_problems, Nl = p->d.Nl, NC = B * Nl;
+  double *h = p->hout;  // 12 fields of Nl
+  cudaStream_t s = p->stream;
+  for (int f = 0; f < 5; ++f)
+    CK(cudaMemcpyAsync(h + f * Nl, p->dx + f * NC + b * Nl, Nl * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h + 5 * Nl, p->dT + b * Nl, Nl * 8, cudaMemcpyDeviceToHost, s));
+  for (int f = 0; f < 6; ++f)
+    CK(cudaMemcpyAsync(h + (6 + f) * Nl, p->dsrc + f * NC + b * Nl, Nl * 8,
+                       cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(p->hflags + 2 * B + b, p->dflags + 2 * B + b, sizeof(int),
+                     cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  double *outs[12] = {xH1, xH2, xHe1, xHe2, xHe3, T, H1i, He1i, He2i, H1h, He1h, He2h};
+  const bool rev = p->reversed[b];
+  for (int f = 0; f < 12; ++f) {
+    if (!outs[f]) continue;
+    for (size_t i = 0; i < Nl; ++i) outs[f][i] = h[f * Nl + (rev ? Nl - 1 - i : i)];
+  }
+  if (iters) *iters = p->hflags[2 * B + b];
+  return RB_OK;
+}
+
+extern "C" void *rb_plan_field_ptr(rb_plan *p, int field) {
+  if (!p || field < 0 || field > 11) return nullptr;
+  const size_t NC = cells(p);
+  if (field < 5) return p->dx + field * NC;
+  if (field == 5) return p->dT;
+  return p->dsrc + (field - 6) * NC;
+}
+extern "C" void *rb_plan_stream(rb_plan *p) { return p ? (void *)p->stream : nullptr; }
+extern "C" int rb_plan_sync(rb_plan *p) {
+  if (!p) return RB_ERR_BAD_ARG;
+  CK(cudaStreamSynchronize(p->stream));
+  return RB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host-pointer entry points (the f2py boundary)
+// ---------------------------------------------------------------------------
+static int check_fits(int i_rec_meth, int i_photo_fit, int i_rate_fit) {
+  if (i_rec_meth < 1 || i_rec_meth > 4) return RB_ERR_BAD_ARG;
+  if (i_rec_meth != 1 || i_photo_fit != 1 || i_rate_fit != 1) return RB_ERR_UNSUPPORTED;
+  return RB_OK;
+}
+
+static int solve_one(int geom, const double *Edges, const double *nH, const double *nHe,
+                     double *T, int Nmu, const double *E_eV, const double *shape,
+                     double fixed_fcA, int i_find_Teq, int i_thin, double z, double Hz,
+                     double tol, int Nl, int Nnu, double *outs[17], rb_info *info) {
+  const auto t0 = std::chrono::steady_clock::now();
+  rb_plan_desc d;
+  memset(&d, 0, sizeof(d));
+  d.geometry = geom; d.n_problems = 1; d.Nl = Nl; d.Nnu = Nnu; d.Nmu = Nmu;
+  d.i_find_Teq = i_find_Teq; d.fixed_fcA = fixed_fcA; d.tol = tol; d.device = -1;
+  rb_plan *p = nullptr;
+  int rc = rb_plan_create(&p, &d);
+  if (rc) return rc;
+  rc = rb_plan_set_problem(p, 0, Edges, nH, nHe, T, E_eV, shape, z, Hz);
+  if (!rc) rc = rb_plan_upload(p);
+  if (!rc) {
+    if (i_thin == 1) {
+      rc = rb_plan_thin(p);
+      if (!rc) rc = plan_check_errors(p);
+    } else {
+      rc = rb_plan_solve(p, nullptr);
+    }
+  }
+  if (!rc) {
+    // T is intent(inout): with find_Teq it returns the equilibrium temperature;
+    // the two-sided slabs mirror T unconditionally.
+    rc = rb_plan_get_problem(p, 0, T, outs[0], outs[1], outs[2], outs[3], outs[4], outs[5],
+                             outs[6], outs[7], outs[11], outs[12], outs[13], nullptr);
+    const int rec_idx[6] = {8, 9, 10, 14, 15, 16};  // *_rec outputs are zero for rec_meth=fixed
+    for (int q = 0; q < 6; ++q)
+      if (outs[rec_idx[q]]) memset(outs[rec_idx[q]], 0, sizeof(double) * (size_t)Nl);
+  }
+  if (info) {
+    *info = p->info;
+    info->ms_total =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+  rb_plan_destroy(p);
+  return rc;
+}
+
+#define PACK17                                                                          \
+  double *outs[17] = {xH1,     xH2,      xHe1,     xHe2,    xHe3,     H1i_src,          \
+                      He1i_src, He2i_src, H1i_rec, He1i_rec, He2i_rec, H1h_src,         \
+                      He1h_src, He2h_src, H1h_rec, He1h_rec, He2h_rec}
+
+extern "C" int rb_sphere_bgnd_solve(
+    double *Edges, double *nH, double *nHe, double *T, int Nmu, const double *E_eV,
+    const double *shape, int i_rec_meth, double fixed_fcA, int i_photo_fit, int i_rate_fit,
+    int i_find_Teq, int i_thin, double em_H1_fac, double em_He1_fac, double em_He2_fac,
+    double z, double Hz, double tol, int Nl, int Nnu, double *xH1, double *xH2, double *xHe1,
+    double *xHe2, double *xHe3, double *H1i_src, double *He1i_src, double *He2i_src,
+    double *H1i_rec, double *He1i_rec, double *He2i_rec, double *H1h_src, double *He1h_src,
+    double *He2h_src, double *H1h_rec, double *He1h_rec, double *He2h_rec, rb_info *info) {
+  (void)em_H1_fac; (void)em_He1_fac; (void)em_He2_fac;
+  int rc = check_fits(i_rec_meth, i_photo_fit, i_rate_fit);
+  if (rc) return rc;
+  PACK17;
+  return solve_one(RB_GEOM_SPHERE_BGND, Edges, nH, nHe, T, Nmu, E_eV, shape, fixed_fcA,
+                   i_find_Teq, i_thin, z, Hz, tol, Nl, Nnu, outs, info);
+}
+
+extern "C" int rb_sphere_stromgren_solve(
+    double *Edges, double *nH, double *nHe, double *T, int Nmu, const double *E_eV,
+    const double *shape, int i_rec_meth, double fixed_fcA, int i_photo_fit, int i_rate_fit,
+    int i_find_Teq, int i_thin, double em_H1_fac, double em_He1_fac, double em_He2_fac,
+    double z, double Hz, double tol, int Nl, int Nnu, double *xH1, double *xH2, double *xHe1,
+    double *xHe2, double *xHe3, double *H1i_src, double *He1i_src, double *He2i_src,
+    double *H1i_rec, double *He1i_rec, double *He2i_rec, double *H1h_src, double *He1h_src,
+    double *He2h_src, double *H1h_rec, double *He1h_rec, double *He2h_rec, rb_info *info) {
+  (void)em_H1_fac; (void)em_He1_fac; (void)em_He2_fac;
+  int rc = check_fits(i_rec_meth, i_photo_fit, i_rate_fit);
+  if (rc) return rc;
+  PACK17;
+  return solve_one(RB_GEOM_SPHERE_STROMGREN, Edges, nH, nHe, T, Nmu, E_eV, shape, fixed_fcA,
+                   i_find_Teq, i_thin, z, Hz, tol, Nl, Nnu, outs, info);
+}
+
+extern "C" int rb_slab_bgnd_solve(
+    const double *Edges, const double *nH, const double *nHe, double *T, const double *E_eV,
+    const double *shape, int i_rec_meth, double fixed_fcA, int i_photo_fit, int i_rate_fit,
+    int i_find_Teq, int i_thin, double z, double Hz, double tol, int Nl, int Nnu, double *xH1,
+    double *xH2, double *xHe1, double *xHe2, double *xHe3, double *H1i_src, double *He1i_src,
+    double *He2i_src, double *H1i_rec, double *He1i_rec, double *He2i_rec, double *H1h_src,
+    double *He1h_src, double *He2h_src, double *H1h_rec, double *He1h_rec, double *He2h_rec,
+    rb_info *info) {
+  int rc = check_fits(i_rec_meth, i_photo_fit, i_rate_fit);
+  if (rc) return rc;
+  PACK17;
+  return solve_one(RB_GEOM_SLAB_BGND, Edges, nH, nHe, T, 0, E_eV, shape, fixed_fcA, i_find_Teq,
+                   i_thin, z, Hz, tol, Nl, Nnu, outs, info);
+}
+
+extern "C" int rb_slab_plane_solve(
+    const double *Edges, const double *nH, const double *nHe, double *T, const double *E_eV,
+    const double *shape, int i_2side, int i_rec_meth, double fixed_fcA, int i_photo_fit,
+    int i_rate_fit, int i_find_Teq, int i_thin, double z, double Hz, double tol, int Nl,
+    int Nnu, double *xH1, double *xH2, double *xHe1, double *xHe2, double *xHe3,
+    double *H1i_src, double *He1i_src, double *He2i_src, double *H1i_rec, double *He1i_rec,
+    double *He2i_rec, double *H1h_src, double *He1h_src, double *He2h_src, double *H1h_rec,
+    double *He1h_rec, double *He2h_rec, rb_info *info) {
+  int rc = check_fits(i_rec_meth, i_photo_fit, i_rate_fit);
+  if (rc) return rc;
+  PACK17;
+  return solve_one(i_2side == 1 ? RB_GEOM_SLAB_PLANE_2 : RB_GEOM_SLAB_PLANE_1, Edges, nH, nHe,
+                   T, 0, E_eV, shape, fixed_fcA, i_find_Teq, i_thin, z, Hz, tol, Nl, Nnu, outs,
+                   info);
+}
+
+// ---------------------------------------------------------------------------
+// small device-buffer helper for the remaining entry points
+// ---------------------------------------------------------------------------
+struct DevBuf {
+  double *d = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    n = count;
+    if (cudaMalloc((void **)&d, std::max<size_t>(1, count) * 8) != cudaSuccess) {
+      cudaGetLastError();
+      d = nullptr;
+      return RB_ERR_NOMEM;
+    }
+    return RB_OK;
+  }
+  ~DevBuf() { if (d) cudaFree(d); }
+};
+
+static int need_device() {
+  if (rb_device_count() < 1) {
+    snprintf(g_cuda_msg, sizeof(g_cuda_msg), "no CUDA device visible (there is no CPU fallback)");
+    return RB_ERR_CUDA;
+  }
+  return RB_OK;
+}
+
+extern "C" int rb_set_column_vs_impact(const double *xH1, const double *xH2, const double *xHe1,
+                                       const double *xHe2, const double *xHe3,
+                                       const double *Edges, const double *nH, const double *nHe,
+                                       const double *T, int Nl, double *NH, double *NHe,
+                                       double *NH1, double *NHe1, double *NHe2) {
+  (void)xH2; (void)xHe3; (void)T;
+  if (Nl < 1) return RB_ERR_BAD_ARG;
+  int rc = need_device();
+  if (rc) return rc;
+  bool rev = false;
+  if (mono_inc(Edges, Nl + 1)) rev = true;          // sphere_base.f90:1150-1160
+  else if (!mono_dec(Edges, Nl + 1)) return RB_ERR_EDGES_NOT_MONOTONIC;
+  const size_t n = Nl;
+  std::vector<double> h(6 * n + 1);
+  for (int i = 0; i <= Nl; ++i) h[i] = Edges[rev ? Nl - i : i];
+  const double *src[5] = {nH, nHe, xH1, xHe1, xHe2};
+  for (int f = 0; f < 5; ++f)
+    for (int i = 0; i < Nl; ++i) h[(n + 1) + f * n + i] = src[f][rev ? Nl - 1 - i : i];
+  DevBuf in, out;
+  if ((rc = in.alloc(6 * n + 1))) return rc;
+  if ((rc = out.alloc(5 * n + 1))) return rc;
+  CK(cudaMemcpy(in.d, h.data(), (6 * n + 1) * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemset(out.d + 5 * n, 0, 8));
+  const double *dE = in.d, *dnH = in.d + n + 1, *dnHe = dnH + n, *dx1 = dnHe + n,
+               *dx2 = dx1 + n, *dx3 = dx2 + n;
+  k_column_vs_impact<<<(Nl + 127) / 128, 128>>>(dE, dnH, dnHe, dx1, dx2, dx3, Nl, out.d,
+                                                out.d + n, out.d + 2 * n, out.d + 3 * n,
+                                                out.d + 4 * n, (int *)(out.d + 5 * n));
+  CK(cudaGetLastError());
+  std::vector<double> o(5 * n + 1);
+  CK(cudaMemcpy(o.data(), out.d, (5 * n + 1) * 8, cudaMemcpyDeviceToHost));
+  int err;
+  memcpy(&err, &o[5 * n], sizeof(int));
+  if (err) return err;
+  double *dst[5] = {NH, NHe, NH1, NHe1, NHe2};
+  for (int f = 0; f < 5; ++f)
+    for (int i = 0; i < Nl; ++i) dst[f][i] = o[f * n + (rev ? Nl - 1 - i : i)];
+  return RB_OK;
+}
+
+// gather `nf` host arrays of nn doubles into one device buffer [nf][nn]
+static int upload_fields(DevBuf &buf, const double *const *fields, int nf, int nn) {
+  int rc = buf.alloc((size_t)nf * nn);
+  if (rc) return rc;
+  for (int f = 0; f < nf; ++f)
+    CK(cudaMemcpy(buf.d + (size_t)f * nn, fields[f], (size_t)nn * 8, cudaMemcpyHostToDevice));
+  return RB_OK;
+}
+
+extern "C" int rb_get_kchem(const double *T, const double *fcA_H2, const double *fcA_He2,
+                            const double *fcA_He3, int irate, int nn, double *reH2,
+                            double *reHe2, double *reHe3, double *ciH1, double *ciHe1,
+                            double *ciHe2) {
+  if (irate != 1) return RB_ERR_UNSUPPORTED;
+  if (nn < 1) return RB_ERR_BAD_ARG;
+  int rc = need_device();
+  if (rc) return rc;
+  DevBuf in, out;
+  const double *f[4] = {T, fcA_H2, fcA_He2, fcA_He3};
+  if ((rc = upload_fields(in, f, 4, nn))) return rc;
+  if ((rc = out.alloc((size_t)6 * nn))) return rc;
+  const size_t n = nn;
+  k_kchem<<<(nn + 127) / 128, 128>>>(in.d, in.d + n, in.d + 2 * n, in.d + 3 * n, nn, out.d,
+                                     out.d + n, out.d + 2 * n, out.d + 3 * n, out.d + 4 * n,
+                                     out.d + 5 * n);
+  CK(cudaGetLastError());
+  double *o[6] = {reH2, reHe2, reHe3, ciH1, ciHe1, ciHe2};
+  for (int q = 0; q < 6; ++q) CK(cudaMemcpy(o[q], out.d + q * n, n * 8, cudaMemcpyDeviceToHost));
+  return RB_OK;
+}
+
+extern "C" int rb_get_kcool(const double *T, const double *fcA_H2, const double *fcA_He2,
+                            const double *fcA_He3, int irate, int nn, double *recH2,
+                            double *recHe2, double *recHe3, double *cicH1, double *cicHe1,
+                            double *cicHe2, double *cecH1, double *cecHe2, double *bremss,
+                            double *compton) {
+  if (irate != 1) return RB_ERR_UNSUPPORTED;
+  if (nn < 1) return RB_ERR_BAD_ARG;
+  int rc = need_device();
+  if (rc) return rc;
+  DevBuf in, out;
+  const double *f[4] = {T, fcA_H2, fcA_He2, fcA_He3};
+  if ((rc = upload_fields(in, f, 4, nn))) return rc;
+  if ((rc = out.alloc((size_t)10 * nn))) return rc;
+  const size_t n = nn;
+  k_kcool<<<(nn + 127) / 128, 128>>>(in.d, in.d + n, in.d + 2 * n, in.d + 3 * n, nn, out.d);
+  CK(cudaGetLastError());
+  double *o[10] = {recH2, recHe2, recHe3, cicH1, cicHe1, cicHe2, cecH1, cecHe2, bremss, compton};
+  for (int q = 0; q < 10; ++q) CK(cudaMemcpy(o[q], out.d + q * n, n * 8, cudaMemcpyDeviceToHost));
+  return RB_OK;
+}
+
+static int fetch_err(DevBuf &out, size_t off) {
+  int err = 0;
+  if (cudaMemcpy(&err, out.d + off, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    cudaGetLastError();
+    return RB_ERR_CUDA;
+  }
+  return err;
+}
+
+extern "C" int rb_solve_ce(const double *reH2, const double *reHe2, const double *reHe3,
+                           const double *ciH1, const double *ciHe1, const double *ciHe2, int nn,
+                           double *xH1, double *xH2, double *xHe1, double *xHe2, double *xHe3) {
+  if (nn < 1) return RB_ERR_BAD_ARG;
+  int rc = need_device();
+  if (rc) return rc;
+  DevBuf in, out;
+  const double *f[6] = {reH2, reHe2, reHe3, ciH1, ciHe1, ciHe2};
+  if ((rc = upload_fields(in, f, 6, nn))) return rc;
+  const size_t n = nn;
+  if ((rc = out.alloc(5 * n + 1))) return rc;
+  CK(cudaMemset(out.d + 5 * n, 0, 8));
+  k_zone_pce<<<(nn + 127) / 128, 128>>>(in.d, nn, 0.0, out.d, (int *)(out.d + 5 * n), 1);
+  CK(cudaGetLastError());
+  double *o[5] = {xH1, xH2, xHe1, xHe2, xHe3};
+  for (int q = 0; q < 5; ++q) CK(cudaMemcpy(o[q], out.d + q * n, n * 8, cudaMemcpyDeviceToHost));
+  return fetch_err(out, 5 * n);
+}
+
+template <typename F>
+static int launch_lockstep(int nn, F &&launch) {
+  int cpt = 1;
+  while (cpt * 512 < nn) cpt *= 4;
+  if (cpt > 16) return RB_ERR_UNSUPPORTED;  // lock-step batch limit: 8192 zones
+  int threads = (nn + cpt - 1) / cpt;
+  threads = ((threads + 31) / 32) * 32;
+  launch(cpt, threads);
+  return RB_OK;
+}
+
+extern "C" int rb_solve_pce(const double *nH, const double *nHe, const double *reH2,
+                            const double *reHe2, const double *reHe3, const double *ciH1,
+                            const double *ciHe1, const double *ciHe2, const double *H1i,
+                            const double *He1i, const double *He2i, double tol, int nn,
+                            int lockstep, double *xH1, double *xH2, double *xHe1, double *xHe2,
+                            double *xHe3) {
+  if (nn < 1) return RB_ERR_BAD_ARG;
+  int rc = need_device();
+  if (rc) return rc;
+  DevBuf in, out;
+  const double *f[11] = {nH, nHe, reH2, reHe2, reHe3, ciH1, ciHe1, ciHe2, H1i, He1i, He2i};
+  if ((rc = upload_fields(in, f, 11, nn))) return rc;
+  const size_t n = nn;
+  if ((rc = out.alloc(5 * n + 1))) return rc;
+  CK(cudaMemset(out.d + 5 * n, 0, 8));
+  int *derr = (int *)(out.d + 5 * n);
+  if (lockstep) {
+    rc = launch_lockstep(nn, [&](int cpt, int threads) {
+      switch (cpt) {
+        case 1: k_zone_lockstep<1><<<1, threads>>>(in.d, nn, 0, 0, tol, out.d, derr, 0); break;
+        case 4: k_zone_lockstep<4><<<1, threads>>>(in.d, nn, 0, 0, tol, out.d, derr, 0); break;
+        default: k_zone_lockstep<16><<<1, threads>>>(in.d, nn, 0, 0, tol, out.d, derr, 0);
+      }
+    });
+    if (rc) return rc;
+  } else {
+    k_zone_pce<<<(nn + 127) / 128, 128>>>(in.d, nn, tol, out.d, derr, 0);
+  }
+  CK(cudaGetLastError());
+  double *o[5] = {xH1, xH2, xHe1, xHe2, xHe3};
+  for (int q = 0; q < 5; ++q) CK(cudaMemcpy(o[q], out.d + q * n, n * 8, cudaMemcpyDeviceToHost));
+  return fetch_err(out, 5 * n);
+}
+
+extern "C" int rb_solve_pcte(const double *nH, const double *nHe, const double *H1i,
+                             const double *He1i, const double *He2i, const double *H1h,
+                             const double *He1h, const double *He2h, double z, double Hz,
+                             const double *fcA_H2, const double *fcA_He2, const double *fcA_He3,
+                             int irate, double tol, int nn, int lockstep, double *xH1,
+                             double *xH2, double *xHe1, double *xHe2, double *xHe3, double *T) {
+  if (irate != 1) return RB_ERR_UNSUPPORTED;
+  if (nn < 1) return RB_ERR_BAD_ARG;
+  int rc = need_device();
+  if (rc) return rc;
+  if (lockstep) {  // the lock-step kernel carries one case-A triple for the batch
+    for (int i = 1; i < nn; ++i)
+      if (fcA_H2[i] != fcA_H2[0] || fcA_He2[i] != fcA_He2[0] || fcA_He3[i] != fcA_He3[0])
+        return RB_ERR_UNSUPPORTED;
+  }
+  DevBuf in, out;
+  const double *f[11] = {nH, nHe, H1i, He1i, He2i, H1h, He1h, He2h, fcA_H2, fcA_He2, fcA_He3};
+  if ((rc = upload_fields(in, f, 11, nn))) return rc;
+  const size_t n = nn;
+  if ((rc = out.alloc(6 * n + 1))) return rc;
+  CK(cudaMemset(out.d + 6 * n, 0, 8));
+  int *derr = (int *)(out.d + 6 * n);
+  if (lockstep) {
+    rc = launch_lockstep(nn, [&](int cpt, int threads) {
+      switch (cpt) {
+        case 1: k_zone_lockstep<1><<<1, threads>>>(in.d, nn, z, Hz, tol, out.d, derr, 1); break;
+        case 4: k_zone_lockstep<4><<<1, threads>>>(in.d, nn, z, Hz, tol, out.d, derr, 1); break;
+        default: k_zone_lockstep<16><<<1, threads>>>(in.d, nn, z, Hz, tol, out.d, derr, 1);
+      }
+    });
+    if (rc) return rc;
+  } else {
+    k_zone_pcte<<<(nn + 127) / 128, 128>>>(in.d, nn, z, Hz, tol, out.d, derr);
+  }
+  CK(cudaGetLastError());
+  double *o[6] = {xH1, xH2, xHe1, xHe2, xHe3, T};
+  for (int q = 0; q < 6; ++q) CK(cudaMemcpy(o[q], out.d + q * n, n * 8, cudaMemcpyDeviceToHost));
+  return fetch_err(out, 6 * n);
+}
+
+// ---------------------------------------------------------------------------
+// micro-benchmarks
+// ---------------------------------------------------------------------------
+extern "C" int rb_microbench(int kind, int device, double *ops_per_s) {
+  if (!ops_per_s || kind < 0 || kind > 3) return RB_ERR_BAD_ARG;
+  int rc = need_device();
+  if (rc) return rc;
+  if (device >= 0) CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device >= 0 ? device : 0));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  const int iters = (kind == 0) ? 4096 : (kind == 3 ? 128 : 512);
+  DevBuf out;
+  if ((rc = out.alloc((size_t)blocks * threads))) return rc;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    switch (kind) {
+      case 0: k_microbench<0><<<blocks, threads>>>(out.d, iters, 0.5); break;
+      case 1: k_microbench<1><<<blocks, threads>>>(out.d, iters, 0.5); break;
+      case 2: k_microbench<2><<<blocks, threads>>>(out.d, iters, 0.5); break;
+      default: k_microbench<3><<<blocks, threads>>>(out.d, iters, 0.5);
+    }
+    cudaEventRecord(e1);
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double ops = (double)blocks * threads * iters * 8.0;
+    if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CK(cudaGetLastError());
+  *ops_per_s = best;
+  return RB_OK;
+}

@@ -1,0 +1,64 @@
+"""Shared helpers: run one named configuration through the oracle and through
+the CUDA C ABI with identical inputs."""
+import numpy as np
+
+from rabacus_b200 import _lib, configs
+from rabacus_b200.plan import Plan
+
+OUT17 = ("xH1", "xH2", "xHe1", "xHe2", "xHe3", "H1i_src", "He1i_src", "He2i_src",
+         "H1i_rec", "He1i_rec", "He2i_rec", "H1h_src", "He1h_src", "He2h_src",
+         "H1h_rec", "He1h_rec", "He2h_rec")
+CHECKED = ("xH1", "xH2", "xHe1", "xHe2", "xHe3", "T", "H1i_src", "He1i_src", "He2i_src",
+           "H1h_src", "He1h_src", "He2h_src")
+
+
+def run_oracle(orc, cfg, tol=1e-4, max_sweeps=0, order=None, thin=False, flavour=0):
+    g = cfg["geometry"]
+    kw = dict(fixed_fcA=cfg["fixed_fcA"], i_find_Teq=1 if cfg["find_Teq"] else 0,
+              i_thin=1 if thin else 0, z=cfg["z"], Hz=cfg.get("Hz", 0.0), tol=tol,
+              max_sweeps=max_sweeps, flavour=flavour)
+    a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"])
+    if g == "sphere_bgnd":
+        return orc.sphere_bgnd_solve(*a, cfg["Nmu"], cfg["E_eV"], cfg["shape"],
+                                     order=orc.ORDER_JACOBI if order is None else order, **kw)
+    if g == "sphere_stromgren":
+        return orc.sphere_stromgren_solve(*a, 1, cfg["E_eV"], cfg["shape"], **kw)
+    if g == "slab_bgnd":
+        return orc.slab_bgnd_solve(*a, cfg["E_eV"], cfg["shape"], **kw)
+    return orc.slab_plane_solve(*a, cfg["E_eV"], cfg["shape"],
+                                i_2side=1 if g == "slab_plane_2" else 0, **kw)
+
+
+def run_gpu(cfg, tol=1e-4, max_sweeps=0, thin=False):
+    """Through the plan API of the C ABI (same code path as the one-shot entry
+    points, plus max_sweeps for sweep-level parity)."""
+    Nl, Nnu = cfg["nH"].size, cfg["E_eV"].size
+    plan = Plan(configs.GEOM_IDS[cfg["geometry"]], 1, Nl, Nnu, cfg["Nmu"],
+                find_Teq=cfg["find_Teq"], fixed_fcA=cfg["fixed_fcA"], tol=tol,
+                max_sweeps=max_sweeps)
+    plan.set_problem(0, cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], cfg["E_eV"],
+                     cfg["shape"], cfg["z"], cfg.get("Hz", 0.0))
+    plan.upload()
+    if thin:
+        plan.thin()
+        plan.sync()
+        info = plan.last_info()
+    else:
+        info = plan.solve()
+    res = plan.get_problem(0)
+    res["info"] = info
+    plan.close()
+    return res
+
+
+def compare(res_gpu, res_orc, names=CHECKED, rtol=1e-10):
+    worst = {}
+    for n in names:
+        a = np.asarray(res_gpu[n])
+        b = np.asarray(res_orc[n])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            r = np.abs(a - b) / np.abs(b)
+        r = np.where(a == b, 0.0, r)
+        worst[n] = float(np.nanmax(r))
+    bad = {k: v for k, v in worst.items() if not (v <= rtol)}
+    return worst, bad

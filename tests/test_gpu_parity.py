@@ -1,0 +1,308 @@
+"""GPU parity tests: the CUDA hot path (through the C ABI) against the CPU oracle
+on identical inputs.  FP64 tolerance stated by BASELINE.json's north_star:
+relative error <= 1e-10.
+
+Protocol:
+  (i)   sweep level : same input state -> 6 rates, x, T agree <= 1e-10
+  (ii)  solve level : same order and tol -> same sweep count and <= 1e-10
+  (iii) SphereBgnd vs the reference's Gauss-Seidel order: both run to a tight
+        tolerance so they sit on the common fixed point.
+"""
+import numpy as np
+import pytest
+
+from helpers import CHECKED, compare, run_gpu, run_oracle
+from rabacus_b200 import configs
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1.0e-10
+
+
+def _small_sphere(Nl=96, Nnu=128, Nmu=16, find_Teq=False, nH0=1.0, spec=None):
+    return configs.c4_sphere_bgnd(Nl, Nnu, Nmu, find_Teq, nH0=nH0, spectrum=spec)
+
+
+# ----------------------------------------------------------------- single zone
+def test_kchem_kcool_match_oracle(orc):
+    from rabacus_b200 import rabacus_fc as fc
+    T = np.logspace(np.log10(7.5e3), 5.0, 257)
+    for fcA in (1.0, 0.0, 0.37):
+        got = fc.get_kchem_v(T, fcA, fcA, fcA, 1, T.size)
+        ref = orc.get_kchem(T, fcA, fcA, fcA)
+        for g, r in zip(got, ref):
+            assert np.max(np.abs(g / r - 1)) < 1e-13
+        got = fc.get_kcool_v(T, fcA, fcA, fcA, 1, T.size)
+        ref = orc.get_kcool(T, fcA, fcA, fcA)
+        for g, r in zip(got, ref):
+            assert np.max(np.abs(g / r - 1)) < 1e-13
+
+
+def _zone_inputs(n=257):
+    T = np.logspace(4.0, 5.0, n)
+    nH = np.logspace(-5.0, 1.0, n)
+    nHe = nH * 0.25 * 0.24 / 0.76
+    H1i, He1i, He2i = 8.0e-13, 5.0e-13, 6.0e-15          # ~HM12 z=3 photo-rates
+    H1h, He1h, He2h = 5.0e-24, 6.0e-24, 2.0e-25
+    return T, nH, nHe, (H1i, He1i, He2i), (H1h, He1h, He2h)
+
+
+@pytest.mark.parametrize("lockstep", [False, True])
+def test_solve_pce_matches_oracle(orc, lockstep):
+    from rabacus_b200 import rabacus_fc as fc
+    T, nH, nHe, ion, _ = _zone_inputs()
+    k = orc.get_kchem(T, 1.0, 1.0, 1.0)
+    n = T.size
+    f = fc.solve_pce_v if lockstep else None
+    if lockstep:
+        got = f(nH, nHe, *k, *ion, 1e-8, n)
+    else:
+        got = [np.empty(n) for _ in range(5)]
+        for i in range(n):
+            r = fc.solve_pce_s(nH[i], nHe[i], *[a[i] for a in k], *ion, 1e-8)
+            for q in range(5):
+                got[q][i] = r[q]
+    ref = orc.solve_pce(nH, nHe, *k, *ion, 1e-8, vector=lockstep)
+    for g, r in zip(got, ref):
+        assert np.max(np.abs(g / r - 1)) < RTOL
+
+
+@pytest.mark.parametrize("lockstep", [False, True])
+def test_solve_pcte_matches_oracle(orc, lockstep):
+    from rabacus_b200 import rabacus_fc as fc
+    _, nH, nHe, ion, heat = _zone_inputs(129)
+    n = nH.size
+    if lockstep:
+        got = fc.solve_pcte_v(nH, nHe, *ion, *heat, 3.0, 0.0, 1.0, 1.0, 1.0, 1, 1e-7, n)
+    else:
+        from rabacus_b200.rabacus_fc import _solve_pcte
+        got = _solve_pcte((nH, nHe) + ion + heat, 3.0, 0.0, (1.0, 1.0, 1.0), 1, 1e-7, n, 0)
+    ref = orc.solve_pcte(nH, nHe, *ion, *heat, 3.0, 0.0, 1.0, 1.0, 1.0, 1e-7, vector=lockstep)
+    for g, r in zip(got, ref):
+        assert np.max(np.abs(g / r - 1)) < RTOL
+
+
+# ----------------------------------------------------------------- SphereBgnd
+@pytest.mark.parametrize("Nmu", [8, 16, 5, 33])
+@pytest.mark.parametrize("find_Teq", [False, True])
+def test_sphere_bgnd_thin_and_one_sweep(orc, spec128, Nmu, find_Teq):
+    cfg = _small_sphere(96, 128, Nmu, find_Teq, spec=spec128)
+    for kw in (dict(thin=True), dict(max_sweeps=1), dict(max_sweeps=3)):
+        g = run_gpu(cfg, **kw)
+        o = run_oracle(orc, cfg, **kw)
+        worst, bad = compare(g, o)
+        assert not bad, (kw, bad)
+
+
+def test_sphere_bgnd_decreasing_edges_same_as_increasing(orc, spec128):
+    cfg = _small_sphere(64, 128, 8, spec=spec128)
+    rev = dict(cfg)
+    for k in ("Edges", "nH", "nHe", "T"):
+        rev[k] = cfg[k][::-1].copy()
+    a = run_gpu(cfg, max_sweeps=2)
+    b = run_gpu(rev, max_sweeps=2)
+    for n in CHECKED:
+        assert np.array_equal(a[n], b[n][::-1])
+
+
+@pytest.mark.parametrize("find_Teq", [False, True])
+def test_sphere_bgnd_full_solve_same_iterations(orc, spec128, find_Teq):
+    cfg = _small_sphere(128, 128, 16, find_Teq, nH0=3.0, spec=spec128)
+    g = run_gpu(cfg, tol=1e-4)
+    o = run_oracle(orc, cfg, tol=1e-4)
+    assert g["iters"] == o["iters"]
+    worst, bad = compare(g, o)
+    assert not bad, bad
+
+
+def test_sphere_bgnd_vs_reference_gauss_seidel_fixed_point(orc, spec128):
+    """(iii): Jacobi on the GPU and the reference's sequential Gauss-Seidel order
+    converge to the same fixed point; compared at a tight tolerance."""
+    cfg = _small_sphere(48, 128, 8, False, nH0=0.3, spec=spec128)
+    g = run_gpu(cfg, tol=1e-12)
+    o = run_oracle(orc, cfg, tol=1e-12, order=orc.ORDER_GS)
+    worst, bad = compare(g, o, rtol=1e-9)
+    assert not bad, bad
+    # and the looser O(tol) agreement at the default tolerance
+    g = run_gpu(cfg, tol=1e-4)
+    o = run_oracle(orc, cfg, tol=1e-4, order=orc.ORDER_GS)
+    worst, bad = compare(g, o, rtol=5e-3)
+    assert not bad, bad
+
+
+def test_sphere_bgnd_hm12_512_frequencies(orc):
+    cfg = configs.c4_sphere_bgnd(128, 512, 32, False, nH0=1.0)
+    g = run_gpu(cfg, max_sweeps=2)
+    o = run_oracle(orc, cfg, max_sweeps=2)
+    worst, bad = compare(g, o)
+    assert not bad, bad
+
+
+def test_one_shot_entry_point_matches_plan(spec128):
+    from rabacus_b200 import rabacus_fc as fc
+    cfg = _small_sphere(64, 128, 8, True, spec=spec128)
+    T = cfg["T"].copy()
+    Ed, nH, nHe = cfg["Edges"].copy(), cfg["nH"].copy(), cfg["nHe"].copy()
+    out = fc.sphere_bgnd.sphere_bgnd_solve(Ed, nH, nHe, T, 8, cfg["E_eV"], cfg["shape"], 1, 1.0,
+                                           1, 1, 1, 0, 1.0, 1.0, 1.0, 3.0, 0.0, 1e-4, 64, 128)
+    g = run_gpu(cfg, tol=1e-4)
+    assert np.array_equal(out[0], g["xH1"])
+    assert np.array_equal(T, g["T"])          # intent(inout) T carries Teq
+    assert np.array_equal(Ed, cfg["Edges"])   # restored orientation
+    assert fc.last_info["iters"] == g["iters"]
+    for q in (8, 9, 10, 14, 15, 16):
+        assert not out[q].any()               # *_rec are zero for rec_meth=fixed
+
+
+# ----------------------------------------------------------------- other geometries
+def test_c1_iliev_stromgren_sphere(orc):
+    cfg = configs.c1_iliev_stromgren(128)
+    g = run_gpu(cfg, tol=1e-4)
+    o = run_oracle(orc, cfg, tol=1e-4)
+    assert g["iters"] == o["iters"]
+    worst, bad = compare(g, o)
+    assert not bad, bad
+    # Stromgren radius for this test problem is ~5.4 kpc: neutral outside
+    assert g["xH1"][0] < 1e-2 and g["xH1"][-1] > 0.5
+
+
+@pytest.mark.parametrize("find_Teq", [False, True])
+@pytest.mark.parametrize("two_sided", [False, True])
+def test_c2_slab_plane(orc, find_Teq, two_sided):
+    cfg = configs.c2_slab_plane(256, 128, find_Teq, two_sided)
+    g = run_gpu(cfg, tol=1e-4)
+    o = run_oracle(orc, cfg, tol=1e-4)
+    assert g["iters"] == o["iters"]
+    worst, bad = compare(g, o)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("find_Teq", [False, True])
+def test_c3_slab_bgnd(orc, find_Teq):
+    cfg = configs.c3_slab_bgnd(256, 128, find_Teq)
+    g = run_gpu(cfg, tol=1e-4)
+    o = run_oracle(orc, cfg, tol=1e-4)
+    assert g["iters"] == o["iters"]
+    worst, bad = compare(g, o)
+    assert not bad, bad
+    assert np.array_equal(g["xH1"], g["xH1"][::-1])  # mirrored
+
+
+def test_c3_slab_bgnd_full_size_one_sweep(orc):
+    cfg = configs.c3_slab_bgnd(1024, 512, False)
+    g = run_gpu(cfg, max_sweeps=2)
+    o = run_oracle(orc, cfg, max_sweeps=2)
+    worst, bad = compare(g, o)
+    assert not bad, bad
+
+
+def test_slab_asymmetric_density_and_odd_layers(orc, spec128):
+    """nH need not be symmetric; the mirror is unconditional and an odd middle
+    layer is never updated."""
+    cfg = configs.c3_slab_bgnd(65, 128, False)
+    cfg["E_eV"], cfg["shape"] = spec128
+    cfg["nH"] = cfg["nH"] * np.linspace(0.5, 3.0, 65)
+    cfg["nHe"] = cfg["nH"] * 0.08
+    g = run_gpu(cfg, max_sweeps=3)
+    o = run_oracle(orc, cfg, max_sweeps=3)
+    worst, bad = compare(g, o)
+    assert not bad, bad
+
+
+def test_set_column_vs_impact(orc, spec128):
+    from rabacus_b200 import rabacus_fc as fc
+    cfg = _small_sphere(200, 128, 8, spec=spec128)
+    g = run_gpu(cfg, max_sweeps=2)
+    args = (g["xH1"], g["xH2"], g["xHe1"], g["xHe2"], g["xHe3"], cfg["Edges"], cfg["nH"],
+            cfg["nHe"], cfg["T"])
+    got = fc.sphere_base.set_column_vs_impact(*args, 200)
+    ref = orc.set_column_vs_impact(*args)
+    for a, b in zip(got, ref):
+        assert np.max(np.abs(a / b - 1)) < RTOL
+
+
+# ----------------------------------------------------------------- errors, batches
+def test_errors_are_exceptions(spec128):
+    from rabacus_b200 import RabacusB200Error, rabacus_fc as fc
+    cfg = _small_sphere(16, 128, 4, spec=spec128)
+    bad = cfg["Edges"].copy()
+    bad[5] = bad[7]
+    bad[6] = bad[7] * 2
+    args = lambda Ed, rec: (Ed, cfg["nH"].copy(), cfg["nHe"].copy(), cfg["T"].copy(), 4,
+                            cfg["E_eV"], cfg["shape"], rec, 1.0, 1, 1, 0, 0, 1.0, 1.0, 1.0,
+                            0.0, 0.0, 1e-4, 16, 128)
+    with pytest.raises(RabacusB200Error) as e:
+        fc.sphere_bgnd.sphere_bgnd_solve(*args(bad, 1))
+    assert e.value.code == 1
+    with pytest.raises(RabacusB200Error) as e:
+        fc.sphere_bgnd.sphere_bgnd_solve(*args(cfg["Edges"].copy(), 4))
+    assert e.value.code == 9
+    # hollow sphere: innermost edge > impact parameter of some ray (geometry.f90:61-71)
+    hollow = np.linspace(1.0, 2.0, 17) * 3e21
+    with pytest.raises(RabacusB200Error) as e:
+        fc.sphere_bgnd.sphere_bgnd_solve(*args(hollow, 1))
+    assert e.value.code == 7
+
+
+def test_batched_problems_match_individual_solves(spec128):
+    """Independent problems in one plan (the C5 parameter-sweep path): every
+    problem stops at its own sweep count and equals its stand-alone solve."""
+    from rabacus_b200.plan import Plan
+    cfgs = [_small_sphere(64, 128, 8, False, nH0=n0, spec=spec128) for n0 in (0.05, 0.5, 5.0)]
+    cfgs[1]["Edges"] = cfgs[1]["Edges"] * 0.5
+    plan = Plan(0, len(cfgs), 64, 128, 8, tol=1e-4)
+    for b, c in enumerate(cfgs):
+        plan.set_problem(b, c["Edges"], c["nH"], c["nHe"], c["T"], c["E_eV"], c["shape"])
+    plan.upload()
+    plan.solve()
+    its = []
+    for b, c in enumerate(cfgs):
+        r = plan.get_problem(b)
+        s = run_gpu(c, tol=1e-4)
+        its.append(r["iters"])
+        assert r["iters"] == s["iters"]
+        for n in CHECKED:
+            assert np.array_equal(r[n], s[n]), n
+    assert len(set(its)) > 1  # they really did stop at different sweeps
+    plan.close()
+
+
+def test_cell_sharded_sweeps_equal_single_sweep(spec128):
+    """The multi-GPU decomposition (cells dealt cyclically) emulated on
+    one GPU: sweeping the shards one after another equals one full sweep."""
+    from rabacus_b200.plan import Plan
+    cfg = _small_sphere(96, 128, 8, True, spec=spec128)
+    outs = []
+    for world in (1, 4):
+        plan = Plan(0, 1, 96, 128, 8, find_Teq=True, tol=1e-4)
+        plan.set_problem(0, cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], cfg["E_eV"],
+                         cfg["shape"], 3.0, 0.0)
+        plan.upload()
+        plan.thin()
+        for _ in range(3):
+            # Jacobi: every shard must read the PRE-sweep state, so stage the
+            # shard results and apply them together, as the all-gather does.
+            if world == 1:
+                plan.sweep_local(0, 1)
+            else:
+                import torch
+                fields = [plan.field_tensor(i) for i in range(12)]
+                plan.sync()
+                before = [f.clone() for f in fields]
+                staged = [f.clone() for f in fields]
+                for r in range(world):
+                    for f, b in zip(fields, before):
+                        f.copy_(b)
+                    torch.cuda.synchronize()
+                    plan.sweep_local(r, world)
+                    plan.sync()
+                    for f, s in zip(fields, staged):
+                        s[r::world] = f[r::world]
+                for f, s in zip(fields, staged):
+                    f.copy_(s)
+                torch.cuda.synchronize()
+            plan.finish_sweep()
+        outs.append(plan.get_problem(0))
+        plan.close()
+    for n in CHECKED:
+        assert np.array_equal(outs[0][n], outs[1][n]), n
