@@ -51,8 +51,32 @@ def run_gpu(cfg, tol=1e-4, max_sweeps=0, thin=False):
     return res
 
 
-def compare(res_gpu, res_orc, names=CHECKED, rtol=1e-10):
+FRACTIONS = ("xH1", "xH2", "xHe1", "xHe2", "xHe3")
+TOL_FRAC = 1.0e-2  # sphere_bgnd.f90:46: the per-cell solvers run at tol*TOL_FRAC
+
+
+def frac_rtol(tol, rtol=1e-10):
+    """Tolerance for ionisation fractions: 1e-10, or 1% of the reference solver's
+    own stopping tolerance (tol*TOL_FRAC) where that is larger.
+
+    Why the fractions need this and the rates do not (measured, DESIGN.md
+    "Parity"): rates / T / sweep counts agree to <= 1e-12 / bit-exact / exactly.
+    But the reference's bisection on n_e starts from analytic_H1
+    (ion_solver.f90:172-183) whose discriminant dd = QQ^2 - 4 RR PP cancels
+    catastrophically in neutral gas, and it stops once successive iterates agree
+    to tol*TOL_FRAC -- so its n_e, and with it xH2 ~ 1/ne, xHe2 ~ 1/ne,
+    xHe3 ~ 1/ne^2 in cold neutral cells, is defined by the algorithm only to that
+    tolerance.  A 1-ulp libm difference in log10()/pow() inside get_kchem (CUDA
+    libdevice vs glibc) is amplified ~1e6x by the cancellation and shows up as
+    <= 4e-9 in those minority fractions; with identical rate coefficients the
+    CUDA and oracle solvers are bit-identical
+    (test_solver_bit_identical_given_same_coefficients)."""
+    return max(rtol, 1.0e-2 * tol * TOL_FRAC)
+
+
+def compare(res_gpu, res_orc, names=CHECKED, rtol=1e-10, tol=1e-4):
     worst = {}
+    bad = {}
     for n in names:
         a = np.asarray(res_gpu[n])
         b = np.asarray(res_orc[n])
@@ -60,5 +84,7 @@ def compare(res_gpu, res_orc, names=CHECKED, rtol=1e-10):
             r = np.abs(a - b) / np.abs(b)
         r = np.where(a == b, 0.0, r)
         worst[n] = float(np.nanmax(r))
-    bad = {k: v for k, v in worst.items() if not (v <= rtol)}
+        bound = frac_rtol(tol, rtol) if n in FRACTIONS else rtol
+        if not worst[n] <= bound:
+            bad[n] = worst[n]
     return worst, bad
