@@ -198,7 +198,8 @@ typedef struct rb_plan_desc {
   double fixed_fcA;
   double tol;
   int device;     /* CUDA device ordinal, -1 = current */
-  int max_sweeps; /* 0: reference limits; >0: stop every problem after this many */
+  int max_sweeps; /* 0: reference limits; >0: stop every problem after this many;
+                     <0: fixed-work mode, exactly -max_sweeps sweeps, convergence ignored */
 } rb_plan_desc;
 
 int rb_plan_create(rb_plan **plan, const rb_plan_desc *desc);
@@ -219,6 +220,12 @@ int rb_plan_sweep_local(rb_plan *plan, int cell_start, int cell_stride);
 /* convergence test on n_e over all cells + iteration bookkeeping
  * (sphere_bgnd.f90:284-296); returns the number of still-active problems */
 int rb_plan_finish_sweep(rb_plan *plan, int *n_active);
+/* cell-shard exchange (single-problem plans): pack the 12 state fields of the
+ * local cells into dev_send [12][n_local] / scatter an all-gathered buffer
+ * dev_recv [world][12][n_local] (cell il = j*world + g) back into the plan.
+ * Device pointers; enqueued on the plan's stream. */
+int rb_plan_pack_cells(rb_plan *plan, int cell_start, int cell_stride, double *dev_send);
+int rb_plan_unpack_cells(rb_plan *plan, int world, const double *dev_recv);
 /* thin state + sweeps to convergence on one GPU */
 int rb_plan_solve(rb_plan *plan, rb_info *info);
 /* D2H of one problem's results (un-reversed to the input order) */
@@ -235,6 +242,12 @@ void *rb_plan_stream(rb_plan *plan);
 int rb_plan_sync(rb_plan *plan);
 long long rb_plan_evals_per_sweep(const rb_plan *plan);
 int rb_plan_last_info(const rb_plan *plan, rb_info *info);
+
+/* bench helper: run `steps` Jacobi sweeps (rb_plan_sweep_local over all cells +
+ * rb_plan_finish_sweep) and return their summed device time in ms, measured
+ * with CUDA events on the plan's stream.  If flush_bytes > 0 a scratch buffer of
+ * that size is overwritten between steps (L2 flush), outside the timed spans. */
+int rb_plan_bench_steps(rb_plan *plan, int steps, size_t flush_bytes, double *ms_sum);
 
 /* FP64 pipe micro-benchmarks used as roofline denominators (bench.py):
  * kind 0 = DFMA, 1 = exp, 2 = sqrt, 3 = pow.  Returns operations / second. */

@@ -470,6 +470,38 @@ extern "C" int rb_plan_finish_sweep(rb_plan *p, int *n_active) {
   return RB_OK;
 }
 
+static int plan_sweep_cells(const rb_plan *p) {
+  const int g = p->d.geometry;
+  const bool two = (g == RB_GEOM_SLAB_PLANE_2 || g == RB_GEOM_SLAB_BGND);
+  return two ? p->d.Nl / 2 : p->d.Nl;
+}
+
+extern "C" int rb_plan_pack_cells(rb_plan *p, int cell_start, int cell_stride, double *dev_send) {
+  if (!p || !dev_send || cell_start < 0 || cell_stride < 1 || p->d.n_problems != 1)
+    return RB_ERR_BAD_ARG;
+  const int ncell = plan_sweep_cells(p);
+  const int n_local = (cell_start < ncell) ? (ncell - cell_start + cell_stride - 1) / cell_stride : 0;
+  if (n_local > 0) {
+    dim3 g((n_local + 127) / 128, 12);
+    k_pack_cells<<<g, 128, 0, p->stream>>>(p->P, cell_start, cell_stride, n_local, dev_send);
+    p->info.n_launches += 1;
+  }
+  CK(cudaGetLastError());
+  return RB_OK;
+}
+
+extern "C" int rb_plan_unpack_cells(rb_plan *p, int world, const double *dev_recv) {
+  if (!p || !dev_recv || world < 1 || p->d.n_problems != 1) return RB_ERR_BAD_ARG;
+  const int ncell = plan_sweep_cells(p);
+  if (ncell % world != 0) return RB_ERR_BAD_ARG;
+  const int n_local = ncell / world;
+  dim3 g((n_local + 127) / 128, 12, world);
+  k_unpack_cells<<<g, 128, 0, p->stream>>>(p->P, world, n_local, dev_recv);
+  p->info.n_launches += 1;
+  CK(cudaGetLastError());
+  return RB_OK;
+}
+
 extern "C" long long rb_plan_evals_per_sweep(const rb_plan *p) {
   if (!p) return 0;
   const int g = p->d.geometry;
@@ -529,6 +561,32 @@ extern "C" int rb_plan_solve(rb_plan *p, rb_info *info) {
   p->info.ms_total =
       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (info) *info = p->info;
+  return rc;
+}
+
+extern "C" int rb_plan_bench_steps(rb_plan *p, int steps, size_t flush_bytes, double *ms_sum) {
+  if (!p || steps < 0 || !ms_sum) return RB_ERR_BAD_ARG;
+  void *flush = nullptr;
+  if (flush_bytes > 0 && cudaMalloc(&flush, flush_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return RB_ERR_NOMEM;
+  }
+  double sum = 0.0;
+  int rc = RB_OK;
+  for (int s = 0; s < steps && rc == RB_OK; ++s) {
+    if (flush) cudaMemsetAsync(flush, s & 0xff, flush_bytes, p->stream);
+    cudaEventRecord(p->ev[6], p->stream);
+    rc = rb_plan_sweep_local(p, 0, 1);
+    int n_active = 0;
+    if (!rc) rc = rb_plan_finish_sweep(p, &n_active);
+    cudaEventRecord(p->ev[7], p->stream);
+    if (cudaEventSynchronize(p->ev[7]) != cudaSuccess) rc = RB_ERR_CUDA;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p->ev[6], p->ev[7]);
+    sum += ms;
+  }
+  if (flush) cudaFree(flush);
+  *ms_sum = sum;
   return rc;
 }
 

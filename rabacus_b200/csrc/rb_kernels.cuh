@@ -452,14 +452,17 @@ __global__ void k_finish_sweep(PlanDev P) {
       int act = 1;
       if (P.err[b]) act = 0;
       // sphere_bgnd.f90:284-288: the limit is tested before the increment
-      if (P.geom != RB_GEOM_SLAB_BGND && P.iters[b] > RB_OUTER_MAX_ITER) {
+      if (P.geom != RB_GEOM_SLAB_BGND && P.iters[b] > RB_OUTER_MAX_ITER && P.max_sweeps >= 0) {
         atomicMax(&P.err[b], RB_ERR_MAX_ITER_OUTER);
         act = 0;
       }
       P.iters[b] += 1;
-      if (!P.notconv[b]) act = 0;
-      if (P.geom == RB_GEOM_SLAB_BGND && P.iters[b] >= RB_SLAB_BGND_MAX_SWEEPS) act = 0;
+      // max_sweeps < 0: fixed-work mode (benchmarks): exactly -max_sweeps sweeps
+      if (!P.notconv[b] && P.max_sweeps >= 0) act = 0;
+      if (P.geom == RB_GEOM_SLAB_BGND && P.iters[b] >= RB_SLAB_BGND_MAX_SWEEPS &&
+          P.max_sweeps >= 0) act = 0;
       if (P.max_sweeps > 0 && P.iters[b] >= P.max_sweeps) act = 0;
+      if (P.max_sweeps < 0 && P.iters[b] >= -P.max_sweeps) act = 0;
       P.active[b] = act;
       mine += act;
     }
@@ -468,6 +471,35 @@ __global__ void k_finish_sweep(PlanDev P) {
   atomicAdd(&s_count, mine);
   __syncthreads();
   if (threadIdx.x == 0) *P.nactive = s_count;
+}
+
+// ---------------------------------------------------------------------------
+// cell-shard exchange helpers (multi-GPU Jacobi): 12 state fields
+// (5 fractions, T, 6 source rates) of the local cells il = start + j*stride are
+// packed as [12][n_local]; after the all-gather the buffer is [G][12][n_local]
+// and cell il = j*G + g comes from rank g.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double *plan_field(const PlanDev &P, int f) {
+  return f < 5 ? P.x[f] : (f == 5 ? P.T : P.src[f - 6]);
+}
+
+__global__ void k_pack_cells(PlanDev P, int cell_start, int cell_stride, int n_local,
+                             double *send) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y;
+  if (j >= n_local) return;
+  send[(size_t)f * n_local + j] = plan_field(P, f)[cell_start + j * cell_stride];
+}
+
+__global__ void k_unpack_cells(PlanDev P, int world, int n_local, const double *recv) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y, g = blockIdx.z;
+  if (j >= n_local) return;
+  const int il = j * world + g;
+  const double v = recv[((size_t)g * 12 + f) * n_local + j];
+  double *dst = plan_field(P, f);
+  dst[il] = v;
+  if (two_sided(P.geom)) dst[P.Nl - 1 - il] = v;  // mirrored half
 }
 
 __global__ void k_reset_resid(PlanDev P) {

@@ -85,6 +85,13 @@ class Plan(object):
         check(lib().rb_plan_solve(self._h, C.byref(info)))
         return info.as_dict()
 
+    def bench_steps(self, steps, flush_bytes=0):
+        """Run ``steps`` sweeps; returns their summed device time [ms] (CUDA events)."""
+        ms = C.c_double(0.0)
+        check(lib().rb_plan_bench_steps(self._h, C.c_int(int(steps)),
+                                        C.c_size_t(int(flush_bytes)), C.byref(ms)))
+        return ms.value
+
     def last_info(self):
         info = rb_info()
         check(lib().rb_plan_last_info(self._h, C.byref(info)))
@@ -124,45 +131,63 @@ class Plan(object):
         two = self.geometry in (GEOM_SLAB_PLANE_2, GEOM_SLAB_BGND)
         return self.Nl // 2 if two else self.Nl
 
-    def solve_cell_sharded(self, rank, world, group=None, max_sweeps=100000):
-        """Jacobi solve with the sweep's cells dealt cyclically over ``world`` ranks.
+    @property
+    def stream_ptr(self):
+        return lib().rb_plan_stream(self._h)
 
-        Requires ``torch.distributed`` to be initialised (NCCL on GPUs).  Every
-        rank must hold the same staged problem(s).  Returns the sweep count.
-        """
+    def pack_cells(self, cell_start, cell_stride, dev_send_ptr):
+        check(lib().rb_plan_pack_cells(self._h, C.c_int(cell_start), C.c_int(cell_stride),
+                                       C.c_void_p(dev_send_ptr)))
+
+    def unpack_cells(self, world, dev_recv_ptr):
+        check(lib().rb_plan_unpack_cells(self._h, C.c_int(world), C.c_void_p(dev_recv_ptr)))
+
+    def shard_buffers(self, world):
+        """(send [12, n_local], recv [world, 12, n_local]) float64 CUDA tensors."""
         import torch
-        import torch.distributed as dist
-        if self.n_problems != 1:
-            raise ValueError("cell sharding is defined for a single problem per plan")
         ncell = self.n_sweep_cells()
         if ncell % world != 0:
             raise ValueError("number of swept cells (%d) must be divisible by world size %d"
                              % (ncell, world))
-        two = ncell != self.Nl
-        fields = [self.field_tensor(f) for f in FIELDS]
         nloc = ncell // world
-        self.thin()
-        self.sync()
-        sweeps = 0
-        n_active = 1
-        send = torch.empty((len(FIELDS), nloc), dtype=torch.float64, device=fields[0].device)
+        dev = torch.cuda.current_device() if self.device < 0 else self.device
+        send = torch.empty((len(FIELDS), nloc), dtype=torch.float64, device="cuda:%d" % dev)
         recv = torch.empty((world, len(FIELDS), nloc), dtype=torch.float64,
-                           device=fields[0].device)
-        while n_active > 0 and sweeps < max_sweeps:
-            self.sweep_local(rank, world)
-            self.sync()  # plan stream -> torch stream hand-off
-            for i, f in enumerate(fields):
-                send[i] = f[:ncell].view(nloc, world)[:, rank]
-            dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
-            # recv[g, i, j] is field i of cell j*world + g
-            full = recv.permute(1, 2, 0).reshape(len(FIELDS), ncell)
-            for i, f in enumerate(fields):
-                f[:ncell] = full[i]
-                if two:  # mirrored half of the two-sided slabs (SURVEY Q12)
-                    f[self.Nl - ncell:] = torch.flip(full[i], dims=(0,))
-            torch.cuda.current_stream().synchronize()
-            n_active = self.finish_sweep()
-            sweeps += 1
+                           device="cuda:%d" % dev)
+        return send, recv
+
+    def sharded_sweep(self, rank, world, send, recv, group=None):
+        """One cell-sharded Jacobi sweep: local cells -> pack -> NCCL all-gather ->
+        unpack -> convergence test on the full arrays.  Must run with the plan's
+        stream as torch's current stream (see :meth:`solve_cell_sharded`) so that
+        kernels and the collective are ordered on the device without host syncs.
+        Returns the number of still-active problems (0 = converged)."""
+        import torch.distributed as dist
+        self.sweep_local(rank, world)
+        self.pack_cells(rank, world, send.data_ptr())
+        dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
+        self.unpack_cells(world, recv.data_ptr())
+        return self.finish_sweep()
+
+    def solve_cell_sharded(self, rank, world, group=None, max_sweeps=100000):
+        """Jacobi solve with the sweep's cells dealt cyclically over ``world`` ranks.
+
+        Requires ``torch.distributed`` to be initialised (NCCL on GPUs).  Every
+        rank must hold the same staged problem.  Returns the sweep count.
+        """
+        import torch
+        if self.n_problems != 1:
+            raise ValueError("cell sharding is defined for a single problem per plan")
+        send, recv = self.shard_buffers(world)
+        ext = torch.cuda.ExternalStream(self.stream_ptr)
+        sweeps = 0
+        with torch.cuda.stream(ext):
+            self.thin()
+            n_active = 1
+            while n_active > 0 and sweeps < max_sweeps:
+                n_active = self.sharded_sweep(rank, world, send, recv, group)
+                sweeps += 1
+        self.sync()
         return sweeps
 
 
