@@ -394,9 +394,9 @@ extern "C" int rb_plan_thin(rb_plan *p) {
   return RB_OK;
 }
 
-static int group_size(int ndir) {
+static int group_size(int ndir) {  // each thread of a group takes 2 directions
   int gs = 8;
-  while (gs < ndir && gs < 128) gs *= 2;
+  while (2 * gs < ndir && gs < 128) gs *= 2;
   return gs;
 }
 
@@ -425,7 +425,8 @@ extern "C" int rb_plan_sweep_local(rb_plan *p, int cell_start, int cell_stride) 
     const int gs = group_size(p->Ndir);
     const int cpb = 128 / gs;
     dim3 gn((n_local + cpb - 1) / cpb, B);
-    const size_t smem = (size_t)p->d.Nnu * kSpecStride * sizeof(double);
+    const size_t smem = ((size_t)p->d.Nnu * kSpecStride + kExpTabEntries * kExpTabCopies) *
+                        sizeof(double);
     if (g == RB_GEOM_SLAB_BGND) {
       if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(k_nu_rates<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -92,6 +92,81 @@ __global__ void k_pack_shells(PlanDev P) {
 //   il <  m : N(+mu) = A + d/2 ;  N(-mu) = 2 S - A - d/2 + t
 //   il == m : N(+mu) = N(-mu) = A + t/2
 // ---------------------------------------------------------------------------
+// sqrt(x) for finite x >= 0 in 6 FP64-pipe instructions: MUFU.RSQ64H seed
+// (rsqrt.approx.ftz.f64, rel. error 2^-22) + two coupled Newton (Goldschmidt)
+// steps on g ~ sqrt(x), h ~ 1/(2 sqrt(x)); result within ~0.6 ulp (CUDA's IEEE
+// sqrt() costs ~14).  Zero / denormal x returns 0.
+__device__ __forceinline__ double sqrt_pos(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double g0 = x * y;
+  const double h0 = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));
+  const double r0 = fma(-g0, h0, 0.5);
+  const double g1 = fma(g0, r0, g0);
+  const double h1 = fma(h0, r0, h0);
+  const double r1 = fma(-g1, h1, 0.5);
+  const double g2 = fma(g1, r1, g1);
+  return ((unsigned)__double2hiint(x) < 0x00100000u) ? 0.0 : g2;
+}
+
+struct ColAcc {
+  double S0, S1, S2;  // running through-sums (HI, HeI, HeII)
+  double A0, A1, A2;  // snapshot at the ray's own shell
+  double d0, d1, d2;  // own-shell segment * density
+  double s_prev;
+  double4 cur;
+};
+
+// advance over shell records k = kb .. ke (inclusive): segment k-1 is closed by
+// record k.  SNAP: also test whether segment k-1 is the ray's own shell.
+// Two records per trip with the next two prefetched, so that the L1 latency of
+// the (warp-uniform, broadcast) record loads is off the dependent chain.
+template <bool SNAP>
+__device__ __forceinline__ void col_advance(ColAcc &a, const double4 *__restrict__ pk, int kb,
+                                            int ke, int il, double p2, int kmax) {
+  if (kb > ke) return;
+  int k = kb;
+  double4 n0 = pk[k], n1 = pk[min(k + 1, kmax)];
+  for (; k + 1 <= ke; k += 2) {
+    const double4 f0 = pk[min(k + 2, kmax)], f1 = pk[min(k + 3, kmax)];
+    const double s0 = sqrt_pos(n0.x - p2);
+    const double s1 = sqrt_pos(n1.x - p2);
+    const double ds0 = fabs(s0 - a.s_prev);
+    const double ds1 = fabs(s1 - s0);
+    if (SNAP && k - 1 == il) {
+      a.A0 = a.S0; a.A1 = a.S1; a.A2 = a.S2;
+      a.d0 = ds0 * a.cur.y; a.d1 = ds0 * a.cur.z; a.d2 = ds0 * a.cur.w;
+    }
+    a.S0 = fma(ds0, a.cur.y, a.S0);
+    a.S1 = fma(ds0, a.cur.z, a.S1);
+    a.S2 = fma(ds0, a.cur.w, a.S2);
+    if (SNAP && k == il) {
+      a.A0 = a.S0; a.A1 = a.S1; a.A2 = a.S2;
+      a.d0 = ds1 * n0.y; a.d1 = ds1 * n0.z; a.d2 = ds1 * n0.w;
+    }
+    a.S0 = fma(ds1, n0.y, a.S0);
+    a.S1 = fma(ds1, n0.z, a.S1);
+    a.S2 = fma(ds1, n0.w, a.S2);
+    a.s_prev = s1;
+    a.cur = n1;
+    n0 = f0;
+    n1 = f1;
+  }
+  if (k <= ke) {
+    const double s0 = sqrt_pos(n0.x - p2);
+    const double ds0 = fabs(s0 - a.s_prev);
+    if (SNAP && k - 1 == il) {
+      a.A0 = a.S0; a.A1 = a.S1; a.A2 = a.S2;
+      a.d0 = ds0 * a.cur.y; a.d1 = ds0 * a.cur.z; a.d2 = ds0 * a.cur.w;
+    }
+    a.S0 = fma(ds0, a.cur.y, a.S0);
+    a.S1 = fma(ds0, a.cur.z, a.S1);
+    a.S2 = fma(ds0, a.cur.w, a.S2);
+    a.s_prev = s0;
+    a.cur = n0;
+  }
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 k_sphere_columns(PlanDev P, int cell_start, int cell_stride, int n_local) {
@@ -118,32 +193,33 @@ k_sphere_columns(PlanDev P, int cell_start, int cell_stride, int n_local) {
     atomicMax(&P.err[b], RB_ERR_RAY_GEOMETRY);
     return;
   }
-  int lo = 1, hi = Nl;
+  int lo = il + 1, hi = Nl;  // E_il >= r_ray >= p: the answer is > il
+  if (E[il] <= p_ray) lo = 1;  // degenerate (zero-width shells): full search
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
     if (E[mid] <= p_ray) hi = mid; else lo = mid + 1;
   }
   const int m = lo - 1;
 
-  double S0 = 0.0, S1 = 0.0, S2 = 0.0;  // running through-sums (HI, HeI, HeII)
-  double A0 = 0.0, A1 = 0.0, A2 = 0.0;  // snapshot at the ray's own shell
-  double d0 = 0.0, d1 = 0.0, d2 = 0.0;  // own-shell segment * density
-  double4 cur = pk[0];
-  double s_prev = sqrt(cur.x - p2);
-  for (int k = 1; k <= m; ++k) {
-    const double4 nxt = pk[k];
-    const double s = sqrt(nxt.x - p2);
-    const double ds = fabs(s - s_prev);  // segment through shell k-1
-    if (k - 1 == il) {
-      A0 = S0; A1 = S1; A2 = S2;
-      d0 = ds * cur.y; d1 = ds * cur.z; d2 = ds * cur.w;
-    }
-    S0 = fma(ds, cur.y, S0);
-    S1 = fma(ds, cur.z, S1);
-    S2 = fma(ds, cur.w, S2);
-    s_prev = s;
-    cur = nxt;
-  }
+  // The lanes of a warp hold cells il_w .. il_w + 31*stride: only records
+  // k-1 in that window can be a lane's own shell, so the snapshot test is
+  // confined to a warp-uniform sub-range of the loop.
+  const int lane = threadIdx.x & 31;
+  const int il_w0 = il - lane * cell_stride;
+  const int kA = il_w0 + 1;                        // first record that may close an own shell
+  const int kB = il_w0 + 31 * cell_stride + 1;     // last such record
+  ColAcc a;
+  a.S0 = a.S1 = a.S2 = 0.0;
+  a.A0 = a.A1 = a.A2 = 0.0;
+  a.d0 = a.d1 = a.d2 = 0.0;
+  a.cur = pk[0];
+  a.s_prev = sqrt_pos(a.cur.x - p2);
+  col_advance<false>(a, pk, 1, min(m, kA - 1), il, p2, Nl);
+  col_advance<true>(a, pk, max(1, kA), min(m, kB), il, p2, Nl);
+  col_advance<false>(a, pk, max(1, kB + 1), m, il, p2, Nl);
+  const double S0 = a.S0, S1 = a.S1, S2 = a.S2, A0 = a.A0, A1 = a.A1, A2 = a.A2;
+  const double d0 = a.d0, d1 = a.d1, d2 = a.d2, s_prev = a.s_prev;
+  const double4 cur = a.cur;
   // tangent shell m: cur = shell m record, s_prev = s_m
   const double t0 = 2.0 * s_prev * cur.y;
   const double t1 = 2.0 * s_prev * cur.z;
@@ -273,33 +349,95 @@ __global__ void __launch_bounds__(BLOCK) k_column_taus(PlanDev P) {
 }
 
 // ---------------------------------------------------------------------------
+// exp(x) for x <= 0 on the FP64 pipe in 10 instructions.
+//   n = rint(x * 64/ln2) = 64 e + j ;  r = x - n ln2/64  (|r| <= ln2/128)
+//   exp(x) = 2^e * 2^(j/64) * (1 + r + r^2/2 + ... + r^5/120)
+// 2^(j/64) comes from a 64-entry table in shared memory that is replicated 16x
+// (entry j, copy c at double index 16 j + c, lane reads copy lane%16) so that a
+// half-warp always hits 16 distinct 8-byte banks whatever j each lane needs.
+// Truncation r^6/720 <= 3.5e-17; total error ~1 ulp (CUDA's exp(): 1 ulp with 16
+// FP64 instructions + ~10 integer / branch).  Below -708 the result (a denormal
+// < 2.3e-308) is flushed to zero.
+// ---------------------------------------------------------------------------
+constexpr int kExpTabEntries = 64, kExpTabCopies = 16;
+
+// constants live in constant memory so that DFMA takes them as c[bank][offset]
+// operands (a 64-bit immediate would cost two UMOV per use)
+__constant__ double kExpC[8] = {
+    92.33248261689366,        // 64/ln2
+    -1.0830424696249145e-02,  // -ln2/64 (hi)
+    -3.623510646634843e-19,   // -ln2/64 (lo)
+    8.3333333333333332e-03,   // 1/120
+    4.1666666666666664e-02,   // 1/24
+    1.6666666666666666e-01,   // 1/6
+    0.5, 6755399441055744.0   // 1/2 ; 1.5 * 2^52
+};
+
+__device__ __forceinline__ void fill_exp_table(double *s_exp) {
+  for (int i = threadIdx.x; i < kExpTabEntries * kExpTabCopies; i += blockDim.x)
+    s_exp[i] = exp2((double)(i / kExpTabCopies) * (1.0 / kExpTabEntries));
+}
+
+// s_exp_lane: 32-bit shared-window address of this lane's table copy
+__device__ __forceinline__ double exp_nonpos(double x, unsigned s_exp_lane) {
+  const double t = fma(x, kExpC[0], kExpC[7]);
+  const int n = __double2loint(t);
+  const double nd = t - kExpC[7];
+  double r = fma(nd, kExpC[1], x);
+  r = fma(nd, kExpC[2], r);
+  double q = fma(r, kExpC[3], kExpC[4]);
+  q = fma(r, q, kExpC[5]);
+  q = fma(r, q, kExpC[6]);
+  const double r2 = r * r;
+  const double pl = fma(r2, q, r);
+  double T;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(s_exp_lane + ((n & (kExpTabEntries - 1)) << 7)));
+  const double v = fma(T, pl, T);
+  // x < -708 (or -inf): the result is below the normal range; it is flushed to
+  // zero (the reference's libm returns a denormal < 2.3e-308 there)
+  const bool under = (unsigned)__double2hiint(x) > 0xC0862000u;
+  return under ? 0.0
+               : __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+}
+
+// ---------------------------------------------------------------------------
 // k_nu_rates: fused optical depth -> attenuation -> 6 frequency integrals ->
 // direction quadrature, for the cells il = cell_start + j*cell_stride.
 //
-// Thread <-> ray; a group of GS threads (GS = 8..128, power of two) owns one
+// Thread <-> 2 rays; a group of GS threads (GS = 8..128, power of two) owns one
 // cell and strides over its directions; the per-frequency table
-// {sigma_X/sigma_X,th (3), W_ion,X (3), W_heat,X (3)} sits in shared memory and
-// is read as a broadcast (all lanes at the same nu).  Per (ray, nu):
-//     tau = sum_X tau_X,th * ra_X          (sphere_bgnd.f90:798-800, s_b.f90:267)
-//     a   = exp(-tau)   or   E2(tau)       (s_b.f90:268 ; :385-388)
+// {-sigma_X/sigma_X,th (3), W_ion,X (3), W_heat,X (3)} sits in shared memory and
+// is read as a broadcast (all lanes at the same nu), one read serving both rays.
+// Per (ray, nu):
+//     -tau = sum_X tau_X,th * (-ra_X)      (sphere_bgnd.f90:798-800, s_b.f90:267)
+//     a    = exp(-tau)   or   E2(tau)      (s_b.f90:268 ; :385-388)
 //     acc_j += W_j(nu) * a                 (s_b.f90:306-308,348-351 + utils.f90:19-20,
 //                                           trapezoid folded into W_j)
 // then   rate_j = sum_dir w_dir acc_j, and for SphereBgnd the reference's
 //     src <- (src_old + sum)/2             (sphere_bgnd.f90:837-856).
+// Algorithmic FP64 work per (ray, nu): 3 + 10 + 6 = 19 instructions.
 // ---------------------------------------------------------------------------
 template <int ATT_E2>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int gs) {
   const int b = blockIdx.y;
   if (!P.active[b]) return;
-  extern __shared__ double s_tab[];  // [Nnu][9]
+  extern __shared__ double s_dyn[];
+  double *s_exp = s_dyn;                                        // [64][16]
+  double *s_tab = s_dyn + kExpTabEntries * kExpTabCopies;       // [Nnu][9]
   __shared__ double s_red[6][4];
   const int Nnu = P.Nnu, Nl = P.Nl, ndir = P.Ndir;
   {
     const double *g = P.spec + (size_t)b * Nnu * kSpecStride;
-    for (int i = threadIdx.x; i < Nnu * kSpecStride; i += blockDim.x) s_tab[i] = g[i];
+    for (int i = threadIdx.x; i < Nnu * kSpecStride; i += blockDim.x) {
+      const double v = g[i];
+      s_tab[i] = (i % kSpecStride) < 3 ? -v : v;  // store -ra_X: the loop forms -tau
+    }
+    if (!ATT_E2) fill_exp_table(s_exp);
   }
   __syncthreads();
+  const unsigned s_exp_lane = (unsigned)__cvta_generic_to_shared(s_exp) +
+                              ((threadIdx.x & (kExpTabCopies - 1)) << 3);
 
   const int cpb = 128 / gs;             // cells per block
   const int grp = threadIdx.x / gs;     // which cell of the block
@@ -312,32 +450,45 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int gs) {
   double part[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (valid) {
     const double *col = P.col + c * (size_t)ndir * 3;
-    for (int idir = gl; idir < ndir; idir += gs) {
-      const double t0 = col[idir * 3 + 0];
-      const double t1 = col[idir * 3 + 1];
-      const double t2 = col[idir * 3 + 2];
+    for (int ia = gl; ia < ndir; ia += 2 * gs) {
+      const int ib = ia + gs;
+      const bool hb = ib < ndir;
+      const double t0 = col[ia * 3 + 0], t1 = col[ia * 3 + 1], t2 = col[ia * 3 + 2];
+      const double u0 = hb ? col[ib * 3 + 0] : 0.0, u1 = hb ? col[ib * 3 + 1] : 0.0,
+                   u2 = hb ? col[ib * 3 + 2] : 0.0;
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0;
+      double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0, b4 = 0.0, b5 = 0.0;
 #pragma unroll 2
       for (int k = 0; k < Nnu; ++k) {
         const double *row = s_tab + k * kSpecStride;
-        const double tau = fma(t2, row[2], fma(t1, row[1], t0 * row[0]));
-        const double att = ATT_E2 ? e2xa(tau) : exp(-tau);
-        a0 = fma(row[3], att, a0);
-        a1 = fma(row[4], att, a1);
-        a2 = fma(row[5], att, a2);
-        a3 = fma(row[6], att, a3);
-        a4 = fma(row[7], att, a4);
-        a5 = fma(row[8], att, a5);
+        const double r0 = row[0], r1 = row[1], r2 = row[2];
+        const double xa = fma(t2, r2, fma(t1, r1, t0 * r0));   // = -tau
+        const double xb = fma(u2, r2, fma(u1, r1, u0 * r0));
+        const double ea = ATT_E2 ? e2xa(-xa) : exp_nonpos(xa, s_exp_lane);
+        const double eb = ATT_E2 ? e2xa(-xb) : exp_nonpos(xb, s_exp_lane);
+        const double w3 = row[3], w4 = row[4], w5 = row[5], w6 = row[6], w7 = row[7],
+                     w8 = row[8];
+        a0 = fma(w3, ea, a0); b0 = fma(w3, eb, b0);
+        a1 = fma(w4, ea, a1); b1 = fma(w4, eb, b1);
+        a2 = fma(w5, ea, a2); b2 = fma(w5, eb, b2);
+        a3 = fma(w6, ea, a3); b3 = fma(w6, eb, b3);
+        a4 = fma(w7, ea, a4); b4 = fma(w7, eb, b4);
+        a5 = fma(w8, ea, a5); b5 = fma(w8, eb, b5);
       }
-      double w;
-      if (P.geom == RB_GEOM_SPHERE_BGND) w = P.wmu[idir];
-      else w = two_sided(P.geom) ? 0.5 : 1.0;
-      part[0] = fma(a0, w, part[0]);
-      part[1] = fma(a1, w, part[1]);
-      part[2] = fma(a2, w, part[2]);
-      part[3] = fma(a3, w, part[3]);
-      part[4] = fma(a4, w, part[4]);
-      part[5] = fma(a5, w, part[5]);
+      double wa, wb;
+      if (P.geom == RB_GEOM_SPHERE_BGND) {
+        wa = P.wmu[ia];
+        wb = hb ? P.wmu[ib] : 0.0;
+      } else {
+        wa = two_sided(P.geom) ? 0.5 : 1.0;
+        wb = hb ? wa : 0.0;
+      }
+      part[0] = fma(b0, wb, fma(a0, wa, part[0]));
+      part[1] = fma(b1, wb, fma(a1, wa, part[1]));
+      part[2] = fma(b2, wb, fma(a2, wa, part[2]));
+      part[3] = fma(b3, wb, fma(a3, wa, part[3]));
+      part[4] = fma(b4, wb, fma(a4, wa, part[4]));
+      part[5] = fma(b5, wb, fma(a5, wa, part[5]));
     }
   }
   // reduce over the group: shuffles inside a warp, shared memory across warps
