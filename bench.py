@@ -42,10 +42,10 @@ UNIT = "evals/s"
 # algorithmic FP64-pipe operations (DESIGN.md "Roofline"):
 #   frequency kernel, per (cell, ray, nu): 3 (tau = sum_X tau_X ra_X) + 6 (rate
 #   accumulations) + 10 (exp: scale, round, 2 reduce, 5 polynomial, 1 table merge)
-#   column kernel, per ray segment: 1 (E^2 - p^2) + 6 (sqrt: MUFU seed + 2 coupled
-#   Newton steps) + 1 (ds) + 3 (column FMAs)
+#   column kernel, per ray segment: 1 (E^2 - p^2) + 5 (sqrt: MUFU seed + one
+#   third-order correction) + 1 (ds) + 3 (column FMAs)
 OPS_PER_EVAL = 19
-OPS_PER_SEGMENT = 11
+OPS_PER_SEGMENT = 10
 
 
 def workload(args):

@@ -272,7 +272,7 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   } while (0)
   ALLOC(p->dEdges, B * (Nl + 1) * 8); ALLOC(p->dnH, NC * 8); ALLOC(p->dnHe, NC * 8);
   ALLOC(p->dT, NC * 8); ALLOC(p->dx, 5 * NC * 8); ALLOC(p->dsrc, 6 * NC * 8);
-  ALLOC(p->dconv, NC * 8); ALLOC(p->dpack, B * (Nl + 1) * sizeof(double4));
+  ALLOC(p->dconv, NC * 8); ALLOC(p->dpack, B * (Nl + 1 + kPackPad) * sizeof(double4));
   ALLOC(p->dspec, B * Nnu * kSpecStride * 8); ALLOC(p->dthin, B * 6 * 8);
   ALLOC(p->dmu, 2 * (size_t)std::max(1, d.Nmu) * 8);
   ALLOC(p->dcol, NC * (size_t)p->Ndir * 3 * 8); ALLOC(p->dzHz, B * 2 * 8);
@@ -409,11 +409,15 @@ extern "C" int rb_plan_sweep_local(rb_plan *p, int cell_start, int cell_stride) 
   cudaStream_t s = p->stream;
   cudaEventRecord(p->ev[0], s);
   if (g == RB_GEOM_SPHERE_BGND) {
-    dim3 gp((Nl + 1 + 255) / 256, B);
+    dim3 gp((Nl + 1 + kPackPad + 255) / 256, B);
     k_pack_shells<<<gp, 256, 0, s>>>(p->P);
     if (n_local > 0) {
-      dim3 gc((n_local + 127) / 128, (p->d.Nmu + 1) / 2, B);
-      k_sphere_columns<128><<<gc, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local);
+      const int npair = (p->d.Nmu + 1) / 2;
+      // 128 threads, one shell record per trip, <= 80 registers (6 CTAs/SM): the
+      // fastest of the {block, unroll, occupancy} variants timed on B200
+      // (profiles/r01_kernel_variants.md)
+      dim3 gc((n_local + 127) / 128, npair, B);
+      k_sphere_columns<128, 1, 6><<<gc, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local);
     }
     p->info.n_launches += 2;
   } else {
@@ -427,15 +431,18 @@ extern "C" int rb_plan_sweep_local(rb_plan *p, int cell_start, int cell_stride) 
     dim3 gn((n_local + cpb - 1) / cpb, B);
     const size_t smem = ((size_t)p->d.Nnu * kSpecStride + kExpTabEntries * kExpTabCopies) *
                         sizeof(double);
-    if (g == RB_GEOM_SLAB_BGND) {
-      if (smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(k_nu_rates<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_nu_rates<1><<<gn, 128, smem, s>>>(p->P, cell_start, cell_stride, n_local, gs);
-    } else {
-      if (smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(k_nu_rates<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_nu_rates<0><<<gn, 128, smem, s>>>(p->P, cell_start, cell_stride, n_local, gs);
-    }
+#define NU(ATT, KU, MINB)                                                                      \
+  do {                                                                                         \
+    if (smem > 48 * 1024)                                                                      \
+      CK(cudaFuncSetAttribute(k_nu_rates<ATT, KU, MINB>,                                       \
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    k_nu_rates<ATT, KU, MINB><<<gn, 128, smem, s>>>(p->P, cell_start, cell_stride, n_local, gs); \
+  } while (0)
+    // frequency loop unrolled 4x (2 rays x 4 frequencies = 8 independent exp chains
+    // per thread): fastest variant timed on B200 (profiles/r01_kernel_variants.md)
+    if (g == RB_GEOM_SLAB_BGND) NU(1, 1, 3);
+    else NU(0, 4, 3);
+#undef NU
     cudaEventRecord(p->ev[2], s);
     dim3 gs3((n_local + 127) / 128, B);
     k_cell_solve<<<gs3, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local);

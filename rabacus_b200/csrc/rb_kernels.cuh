@@ -25,6 +25,7 @@
 
 namespace rb {
 
+constexpr int kPackPad = 8;    // padding records after the Nl+1 shell records
 constexpr int kSpecStride = 9;  // per-frequency table: 3 sigma ratios, 3+3 weights
 
 // Everything a kernel needs, passed by value.
@@ -38,7 +39,7 @@ struct PlanDev {
   double *x[5];            // xH1,xH2,xHe1,xHe2,xHe3  [B][Nl]
   double *src[6];          // H1i,He1i,He2i,H1h,He1h,He2h  [B][Nl]
   double *conv_old;        // [B][Nl]
-  double4 *pack;           // [B][Nl+1]
+  double4 *pack;           // [B][Nl+1+kPackPad]
   const double *spec;      // [B][Nnu][9]
   const double *thin;      // [B][6] optically thin integrals (sum of weights)
   const double *mu, *wmu;  // [Nmu] Gauss-Legendre nodes / weights
@@ -60,7 +61,11 @@ __global__ void k_pack_shells(PlanDev P) {
   const int b = blockIdx.y;
   if (!P.active[b]) return;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k > P.Nl) return;
+  if (k > P.Nl + kPackPad - 1) return;
+  if (k > P.Nl) {  // padding read (never used) by the column kernel's prefetch
+    P.pack[(size_t)b * (P.Nl + 1 + kPackPad) + k] = make_double4(0.0, 0.0, 0.0, 0.0);
+    return;
+  }
   const double E = P.Edges[(size_t)b * (P.Nl + 1) + k];
   double4 v;
   v.x = E * E;  // geometry.f90:148  Edges(i1)*Edges(i1)
@@ -72,7 +77,7 @@ __global__ void k_pack_shells(PlanDev P) {
   } else {
     v.y = v.z = v.w = 0.0;
   }
-  P.pack[(size_t)b * (P.Nl + 1) + k] = v;
+  P.pack[(size_t)b * (P.Nl + 1 + kPackPad) + k] = v;
 }
 
 // ---------------------------------------------------------------------------
@@ -92,21 +97,22 @@ __global__ void k_pack_shells(PlanDev P) {
 //   il <  m : N(+mu) = A + d/2 ;  N(-mu) = 2 S - A - d/2 + t
 //   il == m : N(+mu) = N(-mu) = A + t/2
 // ---------------------------------------------------------------------------
-// sqrt(x) for finite x >= 0 in 6 FP64-pipe instructions: MUFU.RSQ64H seed
-// (rsqrt.approx.ftz.f64, rel. error 2^-22) + two coupled Newton (Goldschmidt)
-// steps on g ~ sqrt(x), h ~ 1/(2 sqrt(x)); result within ~0.6 ulp (CUDA's IEEE
-// sqrt() costs ~14).  Zero / denormal x returns 0.
+// sqrt(x) for finite x >= 0 in 5 FP64-pipe instructions.  y0 = MUFU.RSQ64H(x)
+// (rsqrt.approx.ftz.f64, relative error <= 2^-22) gives g0 = x y0 ~ sqrt(x) and the
+// exactly rounded residual e = 1 - g0 y0 = 1 - x y0^2; then
+//     sqrt(x) = g0 (1 - e)^(-1/2) = g0 (1 + e/2 + 3 e^2/8 + O(e^3)),
+// whose truncation 5 e^3/16 < 2^-63.  Result within ~0.5 ulp (CUDA's IEEE sqrt()
+// costs ~14 instructions).  x = 0: the seed +inf is clamped to a finite value by
+// one integer min on its high word, so g0 = 0 and the result is exactly 0.
 __device__ __forceinline__ double sqrt_pos(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  y = __hiloint2double(min(__double2hiint(y), 0x7fe00000), 0);
   const double g0 = x * y;
-  const double h0 = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));
-  const double r0 = fma(-g0, h0, 0.5);
-  const double g1 = fma(g0, r0, g0);
-  const double h1 = fma(h0, r0, h0);
-  const double r1 = fma(-g1, h1, 0.5);
-  const double g2 = fma(g1, r1, g1);
-  return ((unsigned)__double2hiint(x) < 0x00100000u) ? 0.0 : g2;
+  const double e = fma(-g0, y, 1.0);
+  const double q = fma(e, 0.375, 0.5);
+  const double ge = g0 * e;
+  return fma(ge, q, g0);
 }
 
 struct ColAcc {
@@ -117,58 +123,55 @@ struct ColAcc {
   double4 cur;
 };
 
+// close segment (k-1) with record `rec` = shell k
+template <bool SNAP>
+__device__ __forceinline__ void col_close(ColAcc &a, const double4 &rec, double s, int k, int il) {
+  const double ds = fabs(s - a.s_prev);
+  if (SNAP && k - 1 == il) {
+    a.A0 = a.S0; a.A1 = a.S1; a.A2 = a.S2;
+    a.d0 = ds * a.cur.y; a.d1 = ds * a.cur.z; a.d2 = ds * a.cur.w;
+  }
+  a.S0 = fma(ds, a.cur.y, a.S0);
+  a.S1 = fma(ds, a.cur.z, a.S1);
+  a.S2 = fma(ds, a.cur.w, a.S2);
+  a.s_prev = s;
+  a.cur = rec;
+}
+
 // advance over shell records k = kb .. ke (inclusive): segment k-1 is closed by
 // record k.  SNAP: also test whether segment k-1 is the ray's own shell.
-// Two records per trip with the next two prefetched, so that the L1 latency of
-// the (warp-uniform, broadcast) record loads is off the dependent chain.
-template <bool SNAP>
+// U records per trip (their U square roots are independent chains) with the
+// next U prefetched, so that the L1 latency of the (warp-uniform, broadcast)
+// record loads is off the dependent chain.  The record array is padded by
+// kPackPad entries, so the prefetch needs no bounds clamp.
+template <bool SNAP, int U>
 __device__ __forceinline__ void col_advance(ColAcc &a, const double4 *__restrict__ pk, int kb,
-                                            int ke, int il, double p2, int kmax) {
+                                            int ke, int il, double p2) {
   if (kb > ke) return;
   int k = kb;
-  double4 n0 = pk[k], n1 = pk[min(k + 1, kmax)];
-  for (; k + 1 <= ke; k += 2) {
-    const double4 f0 = pk[min(k + 2, kmax)], f1 = pk[min(k + 3, kmax)];
-    const double s0 = sqrt_pos(n0.x - p2);
-    const double s1 = sqrt_pos(n1.x - p2);
-    const double ds0 = fabs(s0 - a.s_prev);
-    const double ds1 = fabs(s1 - s0);
-    if (SNAP && k - 1 == il) {
-      a.A0 = a.S0; a.A1 = a.S1; a.A2 = a.S2;
-      a.d0 = ds0 * a.cur.y; a.d1 = ds0 * a.cur.z; a.d2 = ds0 * a.cur.w;
-    }
-    a.S0 = fma(ds0, a.cur.y, a.S0);
-    a.S1 = fma(ds0, a.cur.z, a.S1);
-    a.S2 = fma(ds0, a.cur.w, a.S2);
-    if (SNAP && k == il) {
-      a.A0 = a.S0; a.A1 = a.S1; a.A2 = a.S2;
-      a.d0 = ds1 * n0.y; a.d1 = ds1 * n0.z; a.d2 = ds1 * n0.w;
-    }
-    a.S0 = fma(ds1, n0.y, a.S0);
-    a.S1 = fma(ds1, n0.z, a.S1);
-    a.S2 = fma(ds1, n0.w, a.S2);
-    a.s_prev = s1;
-    a.cur = n1;
-    n0 = f0;
-    n1 = f1;
+  double4 n[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) n[u] = pk[k + u];
+  for (; k + U - 1 <= ke; k += U) {
+    double4 f[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) f[u] = pk[k + U + u];
+    double sq[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) sq[u] = sqrt_pos(n[u].x - p2);
+#pragma unroll
+    for (int u = 0; u < U; ++u) col_close<SNAP>(a, n[u], sq[u], k + u, il);
+#pragma unroll
+    for (int u = 0; u < U; ++u) n[u] = f[u];
   }
-  if (k <= ke) {
-    const double s0 = sqrt_pos(n0.x - p2);
-    const double ds0 = fabs(s0 - a.s_prev);
-    if (SNAP && k - 1 == il) {
-      a.A0 = a.S0; a.A1 = a.S1; a.A2 = a.S2;
-      a.d0 = ds0 * a.cur.y; a.d1 = ds0 * a.cur.z; a.d2 = ds0 * a.cur.w;
-    }
-    a.S0 = fma(ds0, a.cur.y, a.S0);
-    a.S1 = fma(ds0, a.cur.z, a.S1);
-    a.S2 = fma(ds0, a.cur.w, a.S2);
-    a.s_prev = s0;
-    a.cur = n0;
+#pragma unroll
+  for (int u = 0; u < U - 1; ++u) {
+    if (k + u <= ke) col_close<SNAP>(a, n[u], sqrt_pos(n[u].x - p2), k + u, il);
   }
 }
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+template <int BLOCK, int U, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
 k_sphere_columns(PlanDev P, int cell_start, int cell_stride, int n_local) {
   const int b = blockIdx.z;
   if (!P.active[b]) return;
@@ -180,7 +183,7 @@ k_sphere_columns(PlanDev P, int cell_start, int cell_stride, int n_local) {
   const int imu_in = ip;               // xi ascending: negative mu first
   const int imu_out = Nmu - 1 - ip;
   const double *E = P.Edges + (size_t)b * (Nl + 1);
-  const double4 *pk = P.pack + (size_t)b * (Nl + 1);
+  const double4 *pk = P.pack + (size_t)b * (Nl + 1 + kPackPad);
 
   const double mu = P.mu[imu_in];
   const double r_ray = (E[il] + E[il + 1]) * 0.5;
@@ -214,9 +217,9 @@ k_sphere_columns(PlanDev P, int cell_start, int cell_stride, int n_local) {
   a.d0 = a.d1 = a.d2 = 0.0;
   a.cur = pk[0];
   a.s_prev = sqrt_pos(a.cur.x - p2);
-  col_advance<false>(a, pk, 1, min(m, kA - 1), il, p2, Nl);
-  col_advance<true>(a, pk, max(1, kA), min(m, kB), il, p2, Nl);
-  col_advance<false>(a, pk, max(1, kB + 1), m, il, p2, Nl);
+  col_advance<false, U>(a, pk, 1, min(m, kA - 1), il, p2);
+  col_advance<true, U>(a, pk, max(1, kA), min(m, kB), il, p2);
+  col_advance<false, U>(a, pk, max(1, kB + 1), m, il, p2);
   const double S0 = a.S0, S1 = a.S1, S2 = a.S2, A0 = a.A0, A1 = a.A1, A2 = a.A2;
   const double d0 = a.d0, d1 = a.d1, d2 = a.d2, s_prev = a.s_prev;
   const double4 cur = a.cur;
@@ -417,8 +420,8 @@ __device__ __forceinline__ double exp_nonpos(double x, unsigned s_exp_lane) {
 //     src <- (src_old + sum)/2             (sphere_bgnd.f90:837-856).
 // Algorithmic FP64 work per (ray, nu): 3 + 10 + 6 = 19 instructions.
 // ---------------------------------------------------------------------------
-template <int ATT_E2>
-__global__ void __launch_bounds__(128, 4)
+template <int ATT_E2, int KU, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int gs) {
   const int b = blockIdx.y;
   if (!P.active[b]) return;
@@ -458,7 +461,7 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int gs) {
                    u2 = hb ? col[ib * 3 + 2] : 0.0;
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0;
       double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0, b4 = 0.0, b5 = 0.0;
-#pragma unroll 2
+#pragma unroll KU
       for (int k = 0; k < Nnu; ++k) {
         const double *row = s_tab + k * kSpecStride;
         const double r0 = row[0], r1 = row[1], r2 = row[2];
