@@ -1,0 +1,41 @@
+"""Index conventions of the multi-GPU decompositions (pure Python / numpy).
+
+The CUDA kernels ``k_pack_cells`` / ``k_unpack_cells`` (csrc/rb_kernels.cuh)
+implement exactly these two functions on the device; they are kept here as the
+executable specification that the CPU (gloo) tests exercise.
+
+Cells: the swept cells ``0 .. ncell-1`` are dealt cyclically, rank ``g`` owning
+``il = g, g + G, g + 2G, ...`` (ray cost grows smoothly with depth, so a cyclic
+deal balances it).  After each sweep every rank contributes ``[n_fields, n_local]``
+and receives ``[G, n_fields, n_local]``; cell ``il = j*G + g`` comes from rank ``g``.
+
+Problems (parameter sweeps): contiguous blocks, no exchange at all.
+"""
+import numpy as np
+
+
+def local_cells(rank, world, ncell):
+    return np.arange(rank, ncell, world)
+
+
+def pack_cells(fields, rank, world, ncell):
+    """fields: [n_fields, Nl] -> send buffer [n_fields, n_local]"""
+    return np.ascontiguousarray(fields[:, local_cells(rank, world, ncell)])
+
+
+def unpack_cells(recv, fields, world, ncell, mirror=False):
+    """recv: [world, n_fields, n_local]; scatter into fields [n_fields, Nl] in place.
+    mirror: two-sided slabs also fill the mirrored half."""
+    Nl = fields.shape[1]
+    for g in range(world):
+        idx = local_cells(g, world, ncell)
+        fields[:, idx] = recv[g]
+        if mirror:
+            fields[:, Nl - 1 - idx] = recv[g]
+    return fields
+
+
+def shard_problems(n_problems, rank, world):
+    per = (n_problems + world - 1) // world
+    lo = min(n_problems, rank * per)
+    return lo, min(n_problems, lo + per)

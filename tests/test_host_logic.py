@@ -1,0 +1,79 @@
+"""Host-side logic that needs no GPU: input producers, configuration builders,
+solver-class argument handling."""
+import numpy as np
+import pytest
+
+from rabacus_b200 import configs, rad_src
+
+
+def test_photon_grid_is_segmented_at_thresholds():
+    E, idx = rad_src.photon_energies(1.0, 400.0, 128)
+    assert E[0] == 13.6 and abs(E[-1] / (13.6 * 400) - 1) < 1e-12
+    assert E[idx["H1"]] == 13.6 and E[idx["He1"]] == 24.59 and abs(E[idx["He2"]] - 54.42) < 1e-12
+    assert np.all(np.diff(E) > 0)
+    with pytest.raises(ValueError):
+        rad_src.photon_energies(1.5, 400.0, 64)      # must cover the H I threshold
+    with pytest.raises(ValueError):
+        rad_src.photon_energies(1.0, 3.0, 64)        # must cover the He II threshold
+
+
+def test_hm12_table_interpolation_is_exact_at_table_redshifts():
+    tab = rad_src.HM12Table()
+    E = rad_src.C_CM_S * rad_src.H_EV_S / (10 ** tab.log_lam_cm[100:110])  # table wavelengths
+    for iz in (0, 17, 40):
+        got = tab.spectrum_E(tab.z[iz] + 1e-12, E)
+        assert np.allclose(np.log10(got), tab.logInu[100:110, iz], atol=1e-8)
+
+
+def test_sources_and_normalisation():
+    pt = rad_src.PointSource(1.0, 1.0, "monochromatic")
+    pt.normalize_Ln(5.0e48)
+    assert pt.Nnu == 1 and pt.monochromatic
+    Ln = pt.shape[0] / pt.E[0] * rad_src.ERG_2_EV
+    assert abs(Ln / 5.0e48 - 1) < 1e-14
+    pl = rad_src.PlaneSource(1.0, 400.0, "hm12", Nnu=64, z=3.0)
+    bg = rad_src.BackgroundSource(1.0, 400.0, "hm12", Nnu=64, z=3.0)
+    assert np.allclose(pl.shape, 4 * np.pi * bg.shape)           # plane.py:312-313
+    assert np.allclose(pl.thin_rates(), bg.thin_rates(), rtol=1e-14)
+    pl.normalize_H1i(1e-12)
+    assert abs(pl.thin_rates()[0] / 1e-12 - 1) < 1e-13
+    th = rad_src.BackgroundSource(1.0, 400.0, "thermal", Nnu=32, T_eff=1e5)
+    pw = rad_src.BackgroundSource(1.0, 400.0, "powerlaw", Nnu=32, alpha=-1.5)
+    assert th.shape.argmax() < 16 and abs(pw.shape[-1] / 400 ** -1.5 - 1) < 1e-12
+    with pytest.raises(ValueError):
+        rad_src.BackgroundSource(1.0, 2.0, "monochromatic")
+
+
+@pytest.mark.parametrize("name,Nl", [("c1", 128), ("c2", 256), ("c3", 1024), ("c4", 4096)])
+def test_named_configurations(name, Nl):
+    cfg = {"c1": configs.c1_iliev_stromgren, "c2": configs.c2_slab_plane,
+           "c3": configs.c3_slab_bgnd, "c4": configs.c4_sphere_bgnd}[name]()
+    assert cfg["nH"].size == Nl and cfg["Edges"].size == Nl + 1
+    assert cfg["E_eV"].size == cfg["shape"].size
+    assert np.all(cfg["shape"] > 0) and np.all(cfg["nH"] > 0)
+    if name == "c4":
+        assert cfg["E_eV"].size == 512 and cfg["Nmu"] == 256
+        assert abs(cfg["nH"][0] - 10.0) < 1e-12 and cfg["nH"][-1] < 1e-2     # r^-2 envelope
+
+
+def test_parameter_sweep_builder():
+    probs = configs.c5_sweep(n_nH=2, n_R=2, n_z=3, Nl=16, Nnu=32, Nmu=4)
+    assert len(probs) == 12
+    assert len({p["z"] for p in probs}) == 3 and len({p["Edges"][-1] for p in probs}) == 2
+
+
+def test_solver_classes_validate_arguments_before_calling_the_library():
+    import rabacus_b200 as ra
+    src = ra.BackgroundSource(1.0, 400.0, "hm12", Nnu=32, z=3.0)
+    Nl = 8
+    Ed, T, nH = np.linspace(0, 1e22, Nl + 1), np.full(Nl, 1e4), np.full(Nl, 1e-3)
+    with pytest.raises(ValueError, match="source type"):
+        ra.SphereStromgren(Ed, T, nH, nH * 0.1, src)
+    with pytest.raises(ValueError, match="rec_meth"):
+        ra.SphereBgnd(Ed, T, nH, nH * 0.1, src, rec_meth="thresh")
+    with pytest.raises(ValueError, match="redshift"):
+        ra.SphereBgnd(Ed, T, nH, nH * 0.1, src, find_Teq=True)
+    with pytest.raises(AssertionError):
+        ra.SphereBgnd(Ed[:-1], T, nH, nH * 0.1, src)
+    with pytest.raises(ValueError, match="even"):
+        ra.Slab2Bgnd(Ed[:-1], T[:-1], nH[:-1], nH[:-1] * 0.1, src)

@@ -1,0 +1,326 @@
+"""Pins the CPU oracle (oracle/, the C restatement of the reference's Fortran)
+against everything the reference itself offers for this path:
+
+* its independent Python codings of the HG97 fits and the Verner cross sections
+  (golden vectors generated from /root/reference by tests/golden/make_golden.py;
+  the reference's own test requires py<->Fortran agreement to 1e-10,
+  rabacus/unittest/test_atomic_rates.py:12);
+* its closed-form single-zone check (rabacus/unittest/test_ion_solver.py:12,29-35);
+* its analytic monochromatic slab (rabacus/unittest/test_slab_analytic.py:17,46-78);
+* its HM12 table literals and the spectrum-integral test
+  (rabacus/unittest/test_hm12.py:11-15,39-117; README.txt:233-243);
+* its 128-point HM12 spectrum fixture (rabacus/f2py/profile/spectrum_*.txt).
+The reference ships no golden outputs for the geometric solvers, so
+for those the oracle is additionally checked for internal consistency.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+KPC = 3.0856775814913673e21
+EV_2_ERG = 1.60217653e-12
+
+
+# ------------------------------------------------------------------ atomic data
+def test_hg97_fits_match_reference_python_twin(orc):
+    g = np.load(os.path.join(GOLDEN, "hg97_py_twin.npz"))
+    got = orc.hg97_all(g["T"])
+    rel = np.abs(got / g["rates"] - 1.0)
+    assert rel.max() < 1e-10, dict(zip(g["names"], rel.max(axis=0)))   # test_atomic_rates.py:12
+    assert rel.max() < 1e-14  # what is actually achieved
+
+
+def test_verner_sigma_matches_reference_python_twin(orc):
+    v = np.load(os.path.join(GOLDEN, "verner_py_twin.npz"))
+    for X in range(3):
+        got = orc.v96_sigma(X, v["E"])
+        ref = v["sigma"][:, X]
+        m = ref > 0
+        assert np.array_equal(got == 0, ~m)            # sigma = 0 strictly below threshold
+        assert np.max(np.abs(got[m] / ref[m] - 1)) < 1e-14
+    assert [orc.v96_Eth(X) for X in range(3)] == [13.60, 24.59, 54.42]
+
+
+def test_case_AB_mixing_limits(orc):
+    T = np.array([8.0e3, 1.0e4, 3.0e4, 9.0e4])
+    a = orc.hg97_all(T)
+    for fcA, cols in ((1.0, (0, 2, 5)), (0.0, (1, 3, 6))):
+        k = orc.get_kchem(T, fcA, fcA, fcA)
+        assert np.allclose(k[0], a[:, cols[0]], rtol=1e-13)
+        assert np.allclose(k[1], a[:, cols[1]] + a[:, 4], rtol=1e-13)   # + dielectronic
+        assert np.allclose(k[2], a[:, cols[2]], rtol=1e-13)
+    assert np.array_equal(orc.get_kchem(T, 0.3, 0.3, 0.3)[3], a[:, 7])   # ciH1 has no case
+
+
+def test_e1_e2_fits(orc):
+    from scipy.special import exp1, expn
+    x = np.concatenate([np.logspace(-8, 0, 50), np.linspace(1.0001, 60.0, 80)])
+    assert np.max(np.abs(orc.e1xa(x) / exp1(x) - 1)) < 5e-7      # A&S 5.1.53 / 5.1.56 accuracy
+    xs = x[x < 30]
+    assert np.max(np.abs(orc.e2xa(xs) - expn(2, xs))) < 2e-7
+    assert orc.e1xa(0.0)[0] == 1.0e300 and orc.e2xa(0.0)[0] == 1.0  # zhang_jin_f.f90:58,171
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 32, 33, 256])
+def test_gauss_legendre_rule(orc, n):
+    x, w = orc.p_quadrature_rule(n)
+    xr, wr = np.polynomial.legendre.leggauss(n)
+    assert np.max(np.abs(x - xr)) < 2e-14 and np.max(np.abs(w - wr)) < 2e-14
+    assert np.all(np.diff(x) > 0)                     # ascending, as the sweep assumes
+    assert abs(w.sum() - 2.0) < 1e-13
+
+
+def test_trapezoid(orc):
+    x = np.array([0.0, 1.0, 3.0, 3.5])
+    y = np.array([1.0, 2.0, 0.0, 4.0])
+    assert orc.integrate_trap(x, y) == 0.5 * ((3.0) * 1 + (2.0) * 2 + (4.0) * 0.5)
+
+
+# ------------------------------------------------------------------ HM12 pins
+def _photorates():
+    return np.load(os.path.join(GOLDEN, "hm12_photorates.npz"))
+
+
+def test_hm12_table_literals():
+    p = _photorates()
+    assert p["z"][0] == 0.0
+    assert abs(p["H1i"][0] / 0.228e-13 - 1) < 1e-6 and abs(p["H1h_eV"][0] / 0.889e-13 - 1) < 1e-6
+    i = int(np.argmin(np.abs(p["z"] - 15.1)))
+    assert abs(p["He2i"][i] / 0.192e-22 - 1) < 1e-6 and abs(p["He2h_eV"][i] / 0.154e-19 - 1) < 1e-6
+    # README.txt:233-243: HM12_Photorates_Table().He1h(3.0) = 3.39163517433e-12 eV/s
+    l1pz = np.log10(1.0 + p["z"])
+    He1h = 10 ** np.interp(np.log10(4.0), l1pz, np.log10(p["He1h_eV"]))
+    assert abs(He1h / 3.39163517433e-12 - 1) < 1e-10
+
+
+def test_host_spectrum_builder_reproduces_reference_fixture(spec128):
+    """rabacus_b200.rad_src (host-side input producer) against the 128-point
+    HM12 z=3 spectrum the reference's profiling harness ships."""
+    from rabacus_b200.rad_src import BackgroundSource
+    src = BackgroundSource.__new__(BackgroundSource)
+    try:
+        src.__init__(1.0, 400.0, "hm12", Nnu=128, z=3.0)
+    except ImportError:
+        pytest.skip("librabacus_b200.so not built")
+    E, I = spec128
+    assert np.max(np.abs(src.E / E - 1)) < 1e-11
+    assert np.max(np.abs(src.shape / I - 1)) < 1e-10
+
+
+def test_thin_rates_from_hm12_spectrum_match_tabulated_rates(orc):
+    """The reference's test_hm12.py:39-117: integrate spectrum x Verner sigma and
+    compare with the tabulated rates (5e-2 for z < 8.75), here through the
+    oracle's optically-thin state (bgnd_src_return_*_thin)."""
+    from rabacus_b200.rad_src import HM12Table
+    p = _photorates()
+    tab = HM12Table()
+    E = 13.6 * 10 ** np.linspace(0, np.log10(400.0), 2048)
+    Edges = np.linspace(0, KPC, 3)
+    one = np.ones(2)
+    for z in p["z"][p["z"] < 8.75][::6]:
+        Inu = tab.spectrum_E(float(z), E)
+        r = orc.sphere_bgnd_solve(Edges, one * 1e-4, one * 1e-5, one * 1e4, 2, E, Inu, i_thin=1)
+        i = int(np.argmin(np.abs(p["z"] - z)))
+        assert abs(r.H1i_src[0] / p["H1i"][i] - 1) < 5e-2
+        assert abs(r.He1i_src[0] / p["He1i"][i] - 1) < 5e-2
+        assert abs(r.He2i_src[0] / p["He2i"][i] - 1) < 5e-2
+        assert abs(r.H1h_src[0] / (p["H1h_eV"][i] * EV_2_ERG) - 1) < 5e-2
+        assert abs(r.He2h_src[0] / (p["He2h_eV"][i] * EV_2_ERG) - 1) < 5e-2
+
+
+# ------------------------------------------------------------------ single zone
+def _analytic_xH1(nH, y, reH2, ciH1, H1i):
+    """rabacus/atomic/hydrogen.py:130-171 (analytic_soltn_xH1)"""
+    RR = (ciH1 + reH2) * nH
+    QQ = -(H1i + reH2 * nH + RR * (1 + y))
+    PP = reH2 * nH * (1.0 + y)
+    dd = np.maximum(QQ * QQ - 4.0 * RR * PP, 0.0)
+    return PP / (-0.5 * (QQ - np.sqrt(dd)))
+
+
+@pytest.mark.parametrize("vector", [False, True])
+def test_pce_against_closed_form(orc, vector):
+    """rabacus/unittest/test_ion_solver.py:93-120 (TOL 1e-8)"""
+    p = _photorates()
+    l1pz = np.log10(1.0 + p["z"])
+    H1i, He1i, He2i = [10 ** np.interp(np.log10(4.0), l1pz, np.log10(p[k]))
+                       for k in ("H1i", "He1i", "He2i")]
+    N = 128
+    T = np.linspace(1.0e4, 1.0e5, N)
+    k = orc.get_kchem(T, 1.0, 1.0, 1.0)
+    nH = np.linspace(1.0e-4, 1.0e-3, N)
+    nHe = nH * 0.25 * 0.24 / 0.76
+    x = orc.solve_pce(nH, nHe, *k, H1i, He1i, He2i, 1e-10, vector=vector)
+    y = (x[3] + 2 * x[4]) * nHe / nH
+    assert np.max(np.abs(x[0] / _analytic_xH1(nH, y, k[0], k[3], H1i) - 1)) < 1e-8
+    assert np.allclose(x[0] + x[1], 1, atol=1e-14) and np.allclose(x[2] + x[3] + x[4], 1, atol=1e-14)
+
+
+def test_ce_against_closed_form(orc):
+    """rabacus/unittest/test_ion_solver.py:19-57"""
+    T = np.linspace(1.0e4, 1.0e5, 128)
+    k = orc.get_kchem(T, 1.0, 1.0, 1.0)
+    x = orc.solve_ce(*k)
+    nH = 1.0e-3
+    y = (x[3] + 2 * x[4]) * (nH * 0.1) / nH
+    assert np.max(np.abs(x[0] / _analytic_xH1(nH, y, k[0], k[3], 0.0) - 1)) < 1e-8
+
+
+def test_pcte_thermal_balance(orc):
+    nH = np.logspace(-4, -1, 16)
+    nHe = nH * 0.08
+    ion, heat = (8e-13, 5e-13, 6e-15), (5e-24, 6e-24, 2e-25)
+    xs = orc.solve_pcte(nH, nHe, *ion, *heat, 3.0, 0.0, 1.0, 1.0, 1.0, 1e-8)
+    T = xs[5]
+    assert np.all((T > 7.5e3) & (T < 1e5))
+    assert np.all(np.diff(T) < 0)        # denser gas cools better
+    # lock-step twin: same answer to the solver tolerance, not bit-identical
+    xv = orc.solve_pcte(nH, nHe, *ion, *heat, 3.0, 0.0, 1.0, 1.0, 1.0, 1e-8, vector=True)
+    assert np.max(np.abs(xv[5] / T - 1)) < 1e-6
+    one = orc.solve_pcte(nH[3:4], nHe[3:4], *ion, *heat, 3.0, 0.0, 1.0, 1.0, 1.0, 1e-8, vector=True)
+    assert one[5][0] == xs[5][3] and one[0][0] == xs[0][3]  # n = 1: the twins coincide
+
+
+def test_floor_temperature_branch(orc):
+    """ion_solver.f90:782-794: no heating -> equilibrium below TFLOOR -> PCE at 7.5e3 K"""
+    x = orc.solve_pcte([1e-2], [1e-3], 1e-14, 1e-14, 1e-16, 1e-30, 1e-30, 1e-32, 3.0, 0.0,
+                       1.0, 1.0, 1.0, 1e-8)
+    assert x[5][0] == 7.5e3
+
+
+# ------------------------------------------------------------------ geometry
+def test_ray_geometry_closed_form(orc):
+    """Uniform sphere: chord lengths are analytic."""
+    Nl = 50
+    E = np.linspace(1.0, 0.0, Nl + 1) * 10.0   # decreasing, outer first
+    n1 = np.ones(Nl)
+    for il in (0, 7, 31, 49):
+        r = 0.5 * (E[il] + E[il + 1])
+        for mu in (-0.93, -0.2, 0.0, 0.4, 0.99):
+            N = orc.sphere_ray_columns(E, n1, n1, n1, n1, n1, il, mu)[0]
+            # distance from r along direction mu to the sphere surface R=10, looking
+            # "up" (mu>0) or through the centre side (mu<=0): s = -r mu' + sqrt(R^2 - p^2)
+            p2 = r * r * (1 - mu * mu)
+            expect = np.sqrt(100.0 - p2) - r * abs(mu) if mu > 0 else np.sqrt(100.0 - p2) + r * abs(mu)
+            # the reference halves the first segment (sphere_bgnd.f90:784-786), i.e. it
+            # starts from the middle of the chord piece inside the starting shell rather
+            # than from r itself: the two differ by at most half that piece
+            s_top = np.sqrt(E[il] ** 2 - p2)
+            piece = s_top - np.sqrt(E[il + 1] ** 2 - p2) if E[il + 1] ** 2 > p2 else 2 * s_top
+            assert abs(N - expect) <= 0.5 * piece + 1e-12
+    m = orc.m_for_ray(E, 10, 0.0)
+    assert m == 10
+    assert orc.ds_segment(E, 10, 0.0, 10) == pytest.approx(2 * np.sqrt(E[10] ** 2 - (0.5 * (E[10] + E[11])) ** 2))
+
+
+def _sphere(Nl=48, Nmu=8, nH0=0.3, find_Teq=False, spec=None):
+    from rabacus_b200 import configs
+    return configs.c4_sphere_bgnd(Nl, 128, Nmu, find_Teq, nH0=nH0, spectrum=spec)
+
+
+def test_flavours_are_arithmetically_identical(orc, spec128):
+    """FAITHFUL keeps the per-segment tangent search and the six
+    attenuation recomputations (Q8); HOISTED removes them.  Same numbers."""
+    from helpers import run_oracle, CHECKED
+    cfg = _sphere(24, 6, spec=spec128)
+    a = run_oracle(orc, cfg, max_sweeps=3, flavour=orc.FLAVOUR_HOISTED)
+    b = run_oracle(orc, cfg, max_sweeps=3, flavour=orc.FLAVOUR_FAITHFUL)
+    for n in CHECKED:
+        assert np.array_equal(a[n], b[n]), n
+    assert b["counters"]["exp"] == 6 * a["counters"]["exp"]
+    assert a["counters"]["segments"] == b["counters"]["segments"]
+
+
+def test_gauss_seidel_and_jacobi_share_the_fixed_point(orc, spec128):
+    from helpers import run_oracle
+    cfg = _sphere(32, 8, spec=spec128)
+    gs = run_oracle(orc, cfg, tol=1e-12, order=orc.ORDER_GS)
+    ja = run_oracle(orc, cfg, tol=1e-12, order=orc.ORDER_JACOBI)
+    for n in ("xH1", "xHe1", "xHe2", "H1i_src", "He2h_src"):
+        assert np.max(np.abs(gs[n] / ja[n] - 1)) < 1e-9, n
+    # the fixed point of src <- (src + sum_i w_i rate_i)/2 is
+    # sum_i w_i rate_i with sum w = 2, i.e. TWICE the angle mean: the barely shielded
+    # outermost shell ends at almost 2x the optically thin rate.  Reproduced as is.
+    ratio = gs["H1i_src"][-1] / run_oracle(orc, cfg, thin=True)["H1i_src"][-1]
+    assert 1.5 < ratio <= 2.0 + 1e-12
+
+
+def test_sphere_orientation_invariance(orc, spec128):
+    from helpers import run_oracle, CHECKED
+    cfg = _sphere(20, 4, spec=spec128)
+    rev = dict(cfg)
+    for k in ("Edges", "nH", "nHe", "T"):
+        rev[k] = cfg[k][::-1].copy()
+    a = run_oracle(orc, cfg, max_sweeps=2)
+    b = run_oracle(orc, rev, max_sweeps=2)
+    for n in CHECKED:
+        assert np.array_equal(a[n], b[n][::-1]), n
+
+
+def test_oracle_errors(orc, spec128):
+    cfg = _sphere(8, 4, spec=spec128)
+    bad = cfg["Edges"].copy()
+    bad[3] = bad[5]
+    with pytest.raises(orc.OracleError, match="monotonic"):
+        orc.sphere_bgnd_solve(bad, cfg["nH"], cfg["nHe"], cfg["T"], 4, *spec128)
+    hollow = np.linspace(1.0, 2.0, 9) * 3e21
+    with pytest.raises(orc.OracleError, match="ray geometry"):
+        orc.sphere_bgnd_solve(hollow, cfg["nH"], cfg["nHe"], cfg["T"], 4, *spec128)
+    with pytest.raises(orc.OracleError, match="unsupported"):
+        orc.sphere_bgnd_solve(cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], 4, *spec128,
+                              i_rec_meth=4)
+
+
+def test_analytic_monochromatic_slab(orc):
+    """rabacus/unittest/test_slab_analytic.py: 4096-layer slab, monochromatic plane
+    source, pure hydrogen, against the closed-form tau(xH1) of
+    rabacus/atomic/hydrogen.py:173-212, tolerance 1e-3."""
+    nH, T, H1i = 1.5e-3, 1.0e4, 8.0e-13
+    E = np.array([18.0])
+    sigma = orc.v96_sigma(0, E)[0]
+    k = orc.get_kchem([T], 1.0, 0.0, 0.0)
+    reH2, ciH1 = k[0][0], k[3][0]
+    x0 = _analytic_xH1(nH, 0.0, reH2, ciH1, H1i)
+    xc = reH2 / (reH2 + ciH1)
+    lx = np.linspace(np.log10(x0) + 1e-4 * (np.log10(xc) - np.log10(x0)),
+                     np.log10(xc) - 1e-4 * (np.log10(xc) - np.log10(x0)), 500)
+    x = 10 ** lx
+    tau = (1 / x0 - 1 / x) + np.log(x * (1 - x0) / (x0 * (1 - x))) + \
+        (1 / xc) * np.log(x * (xc - x0) / (x0 * (xc - x)))
+    L = tau / sigma / nH
+    Nl = 4096
+    Edges = np.linspace(0.0, L.max() * 1.1, Nl + 1)
+    # monochromatic plane source normalised to H1i: Fn sigma = H1i ; shape = Fu = Fn E / erg_2_eV
+    shape = np.array([H1i / sigma * E[0] / 6.241509479607719e11])
+    r = orc.slab_plane_solve(Edges, np.full(Nl, nH), np.full(Nl, nH * 1e-10), np.full(Nl, T), E,
+                             shape, i_2side=0, fixed_fcA=1.0, tol=1e-4)
+    z_c = 0.5 * (Edges[1:] + Edges[:-1])
+    sel = (L > z_c.min()) & (L < z_c.max())
+    num = 10 ** np.interp(L[sel], z_c, np.log10(r.xH1))
+    assert np.max(np.abs(num - x[sel]) / x[sel]) < 1e-3
+
+
+def test_two_sided_slabs_are_mirrored_and_thin_limit(orc, spec128):
+    from rabacus_b200 import configs
+    cfg = configs.c3_slab_bgnd(64, 128, False)
+    cfg["E_eV"], cfg["shape"] = spec128
+    r = orc.slab_bgnd_solve(cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], *spec128, tol=1e-4)
+    assert np.array_equal(r.xH1, r.xH1[::-1]) and np.array_equal(r.H1i_src, r.H1i_src[::-1])
+    thin = orc.slab_bgnd_solve(cfg["Edges"], cfg["nH"] * 1e-12, cfg["nHe"] * 1e-12, cfg["T"],
+                               *spec128, tol=1e-4)
+    t0 = orc.slab_bgnd_solve(cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], *spec128, i_thin=1)
+    assert np.max(np.abs(thin.H1i_src / t0.H1i_src - 1)) < 1e-6   # E2(0) = 1 on both sides
+
+
+def test_iliev_test1_stromgren_radius(orc):
+    from rabacus_b200 import configs
+    c = configs.c1_iliev_stromgren(128)
+    r = orc.sphere_stromgren_solve(c["Edges"], c["nH"], c["nHe"], c["T"], 1, c["E_eV"], c["shape"],
+                                   fixed_fcA=0.0, tol=1e-4)
+    r_c = 0.5 * (c["Edges"][1:] + c["Edges"][:-1]) / KPC
+    r_half = np.interp(0.5, r.xH1, r_c)
+    # Iliev+06 test 1: r_S = (3 Ndot / (4 pi alpha_B nH^2))^(1/3) = 5.4 kpc
+    assert 5.0 < r_half < 5.8
