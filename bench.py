@@ -59,37 +59,70 @@ def workload_name(args):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML in
+    process, every ~2 ms; nvidia-smi subprocess as a fallback)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+            ("sw_power_cap", 0x4))
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.stop_flag = index, False
+        self.sm, self.max_mhz, self.reasons, self.n = [], None, set(), 0
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        p = self.nvml
+        self.sm.append(int(p.nvmlDeviceGetClockInfo(self.h, p.NVML_CLOCK_SM)))
+        try:
+            r = p.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = p.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in self.BITS:
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                             timeout=5).stdout.strip()
+        c = [v.strip() for v in out.split(",")]
+        if c and c[0].isdigit():
+            self.sm.append(int(c[0]))
+            self.max_mhz = int(c[1]) if c[1].isdigit() else self.max_mhz
+            for i, (name, _) in enumerate(self.BITS):
+                if len(c) > 2 + i and c[2 + i].lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index),
-                                      "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([c.strip() for c in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                    time.sleep(0.002)
+                else:
+                    self._sample_smi()
+                    time.sleep(0.05)
+                self.n += 1
             except Exception:
-                pass
-            time.sleep(0.1)
+                time.sleep(0.05)
 
     def summary(self):
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        reasons = [n for i, n in enumerate(names)
-                   if any(len(s) > 2 + i and s[2 + i].lower().startswith("active")
-                          for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def segments_per_sweep(cfg, Nmu):
@@ -255,9 +288,6 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    if sampler:
-        sampler.stop_flag = True
-        sampler.join(timeout=2)
     launches = info["n_launches"] - launches0
     value = evals_sweep * K / (ms * 1e-3)
 
@@ -311,6 +341,10 @@ def main():
                "d2h_bytes_per_step": d2h, "step": "one rb_sphere_bgnd_solve call (upload, thin "
                "start, %d sweeps to tol=1e-4, download)" % iters, "solve_wall_ms": solve_ms,
                "sweeps": iters}
+
+    if sampler:  # sampled over the kernel-timed region and the e2e solves
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
 
     if rank != 0:
         if dist is not None:

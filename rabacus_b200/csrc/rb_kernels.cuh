@@ -43,12 +43,17 @@ struct PlanDev {
   const double *spec;      // [B][Nnu][9]
   const double *thin;      // [B][6] optically thin integrals (sum of weights)
   const double *mu, *wmu;  // [Nmu] Gauss-Legendre nodes / weights
-  double *col;             // [B][Nl][Ndir][3] threshold optical depths per ray
+  double *col;             // [B][Ndir][3][Nl] threshold optical depths per ray (cell fastest:
+                           // the column kernel's lanes are consecutive cells -> coalesced stores)
   const double *zHz;       // [B][2]
   int *active, *notconv, *iters, *err;  // [B]
   unsigned long long *resid_bits;       // [B]
   int *nactive;                         // [1]
 };
+
+__device__ __forceinline__ size_t col_index(const PlanDev &P, int b, int il, int idir, int X) {
+  return (((size_t)b * P.Ndir + idir) * 3 + X) * (size_t)P.Nl + il;
+}
 
 __device__ __forceinline__ bool two_sided(int geom) {
   return geom == RB_GEOM_SLAB_PLANE_2 || geom == RB_GEOM_SLAB_BGND;
@@ -241,19 +246,18 @@ k_sphere_columns(PlanDev P, int cell_start, int cell_stride, int n_local) {
     Nin2 = (2.0 * S2 - A2 - 0.5 * d2) + t2;
   }
   // tau_X_th = N_X * sigma_X_th   (sphere_bgnd.f90:794-796)
-  double *col = P.col + ((size_t)b * Nl + il) * (size_t)Nmu * 3;
   if (imu_in == imu_out) {  // odd Nmu: the mu ~ 0 node, both formulas agree
     const bool inward = (mu <= 0.0);
-    col[imu_in * 3 + 0] = (inward ? Nin0 : Nout0) * P.sigma_th[0];
-    col[imu_in * 3 + 1] = (inward ? Nin1 : Nout1) * P.sigma_th[1];
-    col[imu_in * 3 + 2] = (inward ? Nin2 : Nout2) * P.sigma_th[2];
+    P.col[col_index(P, b, il, imu_in, 0)] = (inward ? Nin0 : Nout0) * P.sigma_th[0];
+    P.col[col_index(P, b, il, imu_in, 1)] = (inward ? Nin1 : Nout1) * P.sigma_th[1];
+    P.col[col_index(P, b, il, imu_in, 2)] = (inward ? Nin2 : Nout2) * P.sigma_th[2];
   } else {
-    col[imu_in * 3 + 0] = Nin0 * P.sigma_th[0];
-    col[imu_in * 3 + 1] = Nin1 * P.sigma_th[1];
-    col[imu_in * 3 + 2] = Nin2 * P.sigma_th[2];
-    col[imu_out * 3 + 0] = Nout0 * P.sigma_th[0];
-    col[imu_out * 3 + 1] = Nout1 * P.sigma_th[1];
-    col[imu_out * 3 + 2] = Nout2 * P.sigma_th[2];
+    P.col[col_index(P, b, il, imu_in, 0)] = Nin0 * P.sigma_th[0];
+    P.col[col_index(P, b, il, imu_in, 1)] = Nin1 * P.sigma_th[1];
+    P.col[col_index(P, b, il, imu_in, 2)] = Nin2 * P.sigma_th[2];
+    P.col[col_index(P, b, il, imu_out, 0)] = Nout0 * P.sigma_th[0];
+    P.col[col_index(P, b, il, imu_out, 1)] = Nout1 * P.sigma_th[1];
+    P.col[col_index(P, b, il, imu_out, 2)] = Nout2 * P.sigma_th[2];
   }
 }
 
@@ -321,7 +325,7 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_column_taus(PlanDev P) {
   const int b = blockIdx.x;
   if (!P.active[b]) return;
-  const int Nl = P.Nl, ndir = P.Ndir;
+  const int Nl = P.Nl;
   __shared__ double wsum[3][BLOCK / 32];
   const double *E = P.Edges + (size_t)b * (Nl + 1);
   const int per = (Nl + BLOCK - 1) / BLOCK;
@@ -341,10 +345,9 @@ __global__ void __launch_bounds__(BLOCK) k_column_taus(PlanDev P) {
     for (int q = k0; q < k1; ++q) {
       const int k = pass ? (Nl - 1 - q) : q;
       layer_dtau(P, E, b, k, dt);
-      double *col = P.col + ((size_t)b * Nl + k) * (size_t)ndir * 3 + pass * 3;
 #pragma unroll
       for (int X = 0; X < 3; ++X) {
-        col[X] = run[X] + 0.5 * dt[X];   // slab_bgnd.f90:701-713
+        P.col[col_index(P, b, k, pass, X)] = run[X] + 0.5 * dt[X];   // slab_bgnd.f90:701-713
         run[X] += dt[X];
       }
     }
@@ -452,13 +455,14 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int gs) {
 
   double part[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (valid) {
-    const double *col = P.col + c * (size_t)ndir * 3;
     for (int ia = gl; ia < ndir; ia += 2 * gs) {
       const int ib = ia + gs;
       const bool hb = ib < ndir;
-      const double t0 = col[ia * 3 + 0], t1 = col[ia * 3 + 1], t2 = col[ia * 3 + 2];
-      const double u0 = hb ? col[ib * 3 + 0] : 0.0, u1 = hb ? col[ib * 3 + 1] : 0.0,
-                   u2 = hb ? col[ib * 3 + 2] : 0.0;
+      const double t0 = P.col[col_index(P, b, il, ia, 0)], t1 = P.col[col_index(P, b, il, ia, 1)],
+                   t2 = P.col[col_index(P, b, il, ia, 2)];
+      const double u0 = hb ? P.col[col_index(P, b, il, ib, 0)] : 0.0,
+                   u1 = hb ? P.col[col_index(P, b, il, ib, 1)] : 0.0,
+                   u2 = hb ? P.col[col_index(P, b, il, ib, 2)] : 0.0;
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0;
       double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0, b4 = 0.0, b5 = 0.0;
 #pragma unroll KU
