@@ -162,7 +162,7 @@ def cpu_sweep_seconds(cfg, args):
     return max(t, 1e-9), oracle.num_threads(), res
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """CPU arm: the reference's algorithm on the host cores (oracle port)."""
     if rank != 0:
         return
@@ -192,7 +192,16 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line: everything else (NCCL's version
+    banner, library chatter) is sent to stderr; returns a handle on the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -212,9 +221,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    out = _claim_stdout()
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     import numpy as np
@@ -419,7 +429,7 @@ def main():
         "clocks": sampler.summary() if sampler else None,
         "solve": {"sweeps_to_converge": iters, "wall_ms": solve_ms},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
