@@ -218,8 +218,13 @@ int rb_plan_thin(rb_plan *plan);
  * convergence. */
 int rb_plan_sweep_local(rb_plan *plan, int cell_start, int cell_stride);
 /* convergence test on n_e over all cells + iteration bookkeeping
- * (sphere_bgnd.f90:284-296); returns the number of still-active problems */
+ * (sphere_bgnd.f90:284-296); returns the number of still-active problems.
+ * rb_plan_finish_sweep = _async + poll until drained.  With _async / _poll the
+ * host may enqueue up to 6 sweeps ahead of the read-back: sweeps enqueued after
+ * a problem converged are no-ops on the device (per-problem `active` flags). */
 int rb_plan_finish_sweep(rb_plan *plan, int *n_active);
+int rb_plan_finish_sweep_async(rb_plan *plan);
+int rb_plan_poll_sweep(rb_plan *plan, int *n_active);
 /* cell-shard exchange (single-problem plans): pack the 12 state fields of the
  * local cells into dev_send [12][n_local] / scatter an all-gathered buffer
  * dev_recv [world][12][n_local] (cell il = j*world + g) back into the plan.

@@ -48,7 +48,8 @@ EXPORTS = (
     "rb_get_kchem", "rb_get_kcool", "rb_solve_ce", "rb_solve_pce", "rb_solve_pcte",
     "rb_photo_sigma", "rb_photo_Eth", "rb_gauss_legendre",
     "rb_plan_create", "rb_plan_destroy", "rb_plan_set_problem", "rb_plan_upload",
-    "rb_plan_thin", "rb_plan_sweep_local", "rb_plan_finish_sweep", "rb_plan_solve",
+    "rb_plan_thin", "rb_plan_sweep_local", "rb_plan_finish_sweep", "rb_plan_finish_sweep_async",
+    "rb_plan_poll_sweep", "rb_plan_solve",
     "rb_plan_get_problem", "rb_plan_field_ptr", "rb_plan_stream", "rb_plan_sync",
     "rb_plan_evals_per_sweep", "rb_plan_last_info", "rb_plan_bench_steps", "rb_plan_pack_cells",
     "rb_plan_unpack_cells", "rb_microbench",

@@ -208,8 +208,11 @@ struct rb_plan {
   int *hflags = nullptr;
   std::vector<char> reversed;
   std::vector<double> mu, wmu;
-  cudaEvent_t ev[8];
+  cudaEvent_t ev[8];                 // [4],[5]: solve span; [6],[7]: bench step span
+  cudaEvent_t sev[kSlots][5];        // per in-flight sweep: 4 stage boundaries + done
   bool ev_ok = false;
+  long long sweeps_issued = 0, sweeps_polled = 0;
+  int last_active = 0;
   rb_info info;
   PlanDev P;
 };
@@ -225,7 +228,10 @@ extern "C" void rb_plan_destroy(rb_plan *p) {
   cudaFreeHost(p->hEdges); cudaFreeHost(p->hnH); cudaFreeHost(p->hnHe); cudaFreeHost(p->hT);
   cudaFreeHost(p->hspec); cudaFreeHost(p->hthin); cudaFreeHost(p->hzHz);
   cudaFreeHost(p->hout); cudaFreeHost(p->hflags);
-  if (p->ev_ok) for (auto &e : p->ev) cudaEventDestroy(e);
+  if (p->ev_ok) {
+    for (auto &e : p->ev) cudaEventDestroy(e);
+    for (auto &sl : p->sev) for (auto &e : sl) cudaEventDestroy(e);
+  }
   if (p->stream) cudaStreamDestroy(p->stream);
   cudaGetLastError();
   delete p;
@@ -276,11 +282,11 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   ALLOC(p->dspec, B * Nnu * kSpecStride * 8); ALLOC(p->dthin, B * 6 * 8);
   ALLOC(p->dmu, 2 * (size_t)std::max(1, d.Nmu) * 8);
   ALLOC(p->dcol, NC * (size_t)p->Ndir * 3 * 8); ALLOC(p->dzHz, B * 2 * 8);
-  ALLOC(p->dflags, (4 * B + 4) * sizeof(int)); ALLOC(p->dresid, B * 8);
+  ALLOC(p->dflags, (3 * B + kSlots) * sizeof(int)); ALLOC(p->dresid, B * 8);
   HALLOC(p->hEdges, B * (Nl + 1) * 8); HALLOC(p->hnH, NC * 8); HALLOC(p->hnHe, NC * 8);
   HALLOC(p->hT, NC * 8); HALLOC(p->hspec, B * Nnu * kSpecStride * 8);
   HALLOC(p->hthin, B * 6 * 8); HALLOC(p->hzHz, B * 2 * 8); HALLOC(p->hout, 12 * NC * 8);
-  HALLOC(p->hflags, (4 * B + 4) * sizeof(int));
+  HALLOC(p->hflags, (3 * B + kSlots) * sizeof(int));
 #undef ALLOC
 #undef HALLOC
   p->reversed.assign(B, 0);
@@ -289,6 +295,7 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
     return RB_ERR_CUDA;
   }
   for (auto &e : p->ev) cudaEventCreate(&e);
+  for (auto &sl : p->sev) for (auto &e : sl) cudaEventCreate(&e);
   p->ev_ok = true;
   if (d.geometry == RB_GEOM_SPHERE_BGND) {
     p->mu.resize(d.Nmu); p->wmu.resize(d.Nmu);
@@ -308,8 +315,8 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   P.conv_old = p->dconv; P.pack = p->dpack; P.spec = p->dspec; P.thin = p->dthin;
   P.mu = p->dmu; P.wmu = p->dmu + std::max(1, d.Nmu); P.col = p->dcol; P.zHz = p->dzHz;
   if (d.geometry == RB_GEOM_SPHERE_BGND) P.wmu = p->dmu + d.Nmu;
-  P.active = p->dflags; P.notconv = p->dflags + B; P.iters = p->dflags + 2 * B;
-  P.err = p->dflags + 3 * B; P.nactive = p->dflags + 4 * B; P.resid_bits = p->dresid;
+  P.active = p->dflags; P.iters = p->dflags + B; P.err = p->dflags + 2 * B;
+  P.nactive = p->dflags + 3 * B; P.resid_bits = p->dresid;
   *out = p;
   return RB_OK;
 }
@@ -366,10 +373,12 @@ extern "C" int rb_plan_upload(rb_plan *p) {
   CK(cudaMemcpyAsync(p->dthin, p->hthin, B * 6 * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(p->dzHz, p->hzHz, B * 2 * 8, cudaMemcpyHostToDevice, s));
   for (size_t b = 0; b < B; ++b) {
-    p->hflags[b] = 1; p->hflags[B + b] = 0; p->hflags[2 * B + b] = 0; p->hflags[3 * B + b] = 0;
+    p->hflags[b] = 1; p->hflags[B + b] = 0; p->hflags[2 * B + b] = 0;
   }
-  p->hflags[4 * B] = (int)B;
-  CK(cudaMemcpyAsync(p->dflags, p->hflags, (4 * B + 4) * sizeof(int), cudaMemcpyHostToDevice, s));
+  for (int q = 0; q < kSlots; ++q) p->hflags[3 * B + q] = 0;
+  CK(cudaMemcpyAsync(p->dflags, p->hflags, (3 * B + kSlots) * sizeof(int), cudaMemcpyHostToDevice, s));
+  p->sweeps_issued = p->sweeps_polled = 0;
+  p->last_active = (int)B;
   CK(cudaMemsetAsync(p->dresid, 0, B * 8, s));
   memset(&p->info, 0, sizeof(p->info));
   p->info.resid = NAN;
@@ -407,7 +416,8 @@ extern "C" int rb_plan_sweep_local(rb_plan *p, int cell_start, int cell_stride) 
   const int ncell = two ? Nl / 2 : Nl;  // slab_bgnd.f90:686 (Nl2 = Nl/2)
   const int n_local = (cell_start < ncell) ? (ncell - cell_start + cell_stride - 1) / cell_stride : 0;
   cudaStream_t s = p->stream;
-  cudaEventRecord(p->ev[0], s);
+  cudaEvent_t *sev = p->sev[p->sweeps_issued % kSlots];
+  cudaEventRecord(sev[0], s);
   if (g == RB_GEOM_SPHERE_BGND) {
     dim3 gp((Nl + 1 + kPackPad + 255) / 256, B);
     k_pack_shells<<<gp, 256, 0, s>>>(p->P);
@@ -424,7 +434,7 @@ extern "C" int rb_plan_sweep_local(rb_plan *p, int cell_start, int cell_stride) 
     k_column_taus<512><<<B, 512, 0, s>>>(p->P);
     p->info.n_launches += 1;
   }
-  cudaEventRecord(p->ev[1], s);
+  cudaEventRecord(sev[1], s);
   if (n_local > 0) {
     const int gs = group_size(p->Ndir);
     const int cpb = 128 / gs;
@@ -443,38 +453,63 @@ extern "C" int rb_plan_sweep_local(rb_plan *p, int cell_start, int cell_stride) 
     if (g == RB_GEOM_SLAB_BGND) NU(1, 1, 3);
     else NU(0, 4, 3);
 #undef NU
-    cudaEventRecord(p->ev[2], s);
+    cudaEventRecord(sev[2], s);
     dim3 gs3((n_local + 127) / 128, B);
     k_cell_solve<<<gs3, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local);
     p->info.n_launches += 2;
   } else {
-    cudaEventRecord(p->ev[2], s);
+    cudaEventRecord(sev[2], s);
   }
-  cudaEventRecord(p->ev[3], s);
+  cudaEventRecord(sev[3], s);
   CK(cudaGetLastError());
   return RB_OK;
 }
 
-extern "C" int rb_plan_finish_sweep(rb_plan *p, int *n_active) {
+// convergence test + bookkeeping of the sweep just enqueued; does not wait.
+extern "C" int rb_plan_finish_sweep_async(rb_plan *p) {
   if (!p) return RB_ERR_BAD_ARG;
-  const int Nl = p->d.Nl, B = p->d.n_problems;
+  if (p->sweeps_issued - p->sweeps_polled >= kSlots - 1) return RB_ERR_BAD_ARG;  // poll first
+  const int B = p->d.n_problems;
+  const int slot = (int)(p->sweeps_issued % kSlots);
   cudaStream_t s = p->stream;
-  k_reset_resid<<<(B + 255) / 256, 256, 0, s>>>(p->P);
-  dim3 gc((Nl + 255) / 256, B);
-  k_convergence<<<gc, 256, 0, s>>>(p->P);
-  k_finish_sweep<<<1, 256, 0, s>>>(p->P);
-  p->info.n_launches += 3;
-  CK(cudaMemcpyAsync(p->hflags + 4 * B, p->dflags + 4 * B, sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  k_converge_finish<256><<<B, 256, 0, s>>>(p->P, slot);
+  p->info.n_launches += 1;
+  CK(cudaMemcpyAsync(p->hflags + 3 * B + slot, p->dflags + 3 * B + slot, sizeof(int),
+                     cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(p->sev[slot][4], s));
+  p->sweeps_issued += 1;
   CK(cudaGetLastError());
-  // accumulate per-stage device times of the sweep just finished
-  float ms;
-  if (cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]) == cudaSuccess) p->info.ms_columns += ms;
-  if (cudaEventElapsedTime(&ms, p->ev[1], p->ev[2]) == cudaSuccess) p->info.ms_nu += ms;
-  if (cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]) == cudaSuccess) p->info.ms_cell += ms;
+  return RB_OK;
+}
+
+// wait for the oldest un-polled sweep; returns the number of problems still active after it
+extern "C" int rb_plan_poll_sweep(rb_plan *p, int *n_active) {
+  if (!p || p->sweeps_polled >= p->sweeps_issued) return RB_ERR_BAD_ARG;
+  const int B = p->d.n_problems;
+  const int slot = (int)(p->sweeps_polled % kSlots);
+  CK(cudaEventSynchronize(p->sev[slot][4]));
+  float ms;  // per-stage device times of that sweep
+  cudaEvent_t *sev = p->sev[slot];
+  if (cudaEventElapsedTime(&ms, sev[0], sev[1]) == cudaSuccess) p->info.ms_columns += ms;
+  if (cudaEventElapsedTime(&ms, sev[1], sev[2]) == cudaSuccess) p->info.ms_nu += ms;
+  if (cudaEventElapsedTime(&ms, sev[2], sev[3]) == cudaSuccess) p->info.ms_cell += ms;
   cudaGetLastError();
+  p->sweeps_polled += 1;
   p->info.iters += 1;
-  if (n_active) *n_active = p->hflags[4 * B];
+  p->last_active = p->hflags[3 * B + slot];
+  if (n_active) *n_active = p->last_active;
+  return RB_OK;
+}
+
+extern "C" int rb_plan_finish_sweep(rb_plan *p, int *n_active) {
+  int rc = rb_plan_finish_sweep_async(p);
+  if (rc) return rc;
+  int n = 0;
+  while (p->sweeps_polled < p->sweeps_issued) {
+    rc = rb_plan_poll_sweep(p, &n);
+    if (rc) return rc;
+  }
+  if (n_active) *n_active = n;
   return RB_OK;
 }
 
@@ -520,11 +555,11 @@ extern "C" long long rb_plan_evals_per_sweep(const rb_plan *p) {
 
 static int plan_check_errors(rb_plan *p) {
   const size_t B = p->d.n_problems;
-  CK(cudaMemcpyAsync(p->hflags, p->dflags, (4 * B + 4) * sizeof(int), cudaMemcpyDeviceToHost,
+  CK(cudaMemcpyAsync(p->hflags, p->dflags, 3 * B * sizeof(int), cudaMemcpyDeviceToHost,
                      p->stream));
   CK(cudaStreamSynchronize(p->stream));
   int rc = 0;
-  for (size_t b = 0; b < B; ++b) rc = std::max(rc, p->hflags[3 * B + b]);
+  for (size_t b = 0; b < B; ++b) rc = std::max(rc, p->hflags[2 * B + b]);
   return rc;
 }
 
@@ -537,14 +572,27 @@ extern "C" int rb_plan_solve(rb_plan *p, rb_info *info) {
   if (rc) return rc;
   rc = plan_check_errors(p);
   if (rc) return rc;
+  // Sweeps are enqueued up to kDepth ahead of the convergence read-back: the
+  // device-side `active` flags turn the kernels of any sweep enqueued after a
+  // problem converged into immediate returns, so the iterates are exactly those
+  // of a sweep-by-sweep loop while the host never stalls the stream.
+  const int kDepth = 4;
   long long evals = 0;
-  int n_active = (int)B;
-  while (n_active > 0) {
-    rc = rb_plan_sweep_local(p, 0, 1);
+  int n_active = (int)B, active_during = (int)B;
+  bool stop = false;
+  for (;;) {
+    if (!stop && p->sweeps_issued - p->sweeps_polled < kDepth) {
+      rc = rb_plan_sweep_local(p, 0, 1);
+      if (!rc) rc = rb_plan_finish_sweep_async(p);
+      if (rc) return rc;
+      continue;
+    }
+    if (p->sweeps_polled >= p->sweeps_issued) break;
+    rc = rb_plan_poll_sweep(p, &n_active);
     if (rc) return rc;
-    evals += rb_plan_evals_per_sweep(p) * n_active;
-    rc = rb_plan_finish_sweep(p, &n_active);
-    if (rc) return rc;
+    evals += rb_plan_evals_per_sweep(p) * active_during;
+    active_during = n_active;
+    if (n_active == 0) stop = true;
   }
   cudaEventRecord(p->ev[5], p->stream);
   rc = plan_check_errors(p);
@@ -553,7 +601,7 @@ extern "C" int rb_plan_solve(rb_plan *p, rb_info *info) {
   p->info.ms_device = ms;
   p->info.evals = evals;
   int itmax = 0;
-  for (size_t b = 0; b < B; ++b) itmax = std::max(itmax, p->hflags[2 * B + b]);
+  for (size_t b = 0; b < B; ++b) itmax = std::max(itmax, p->hflags[B + b]);
   p->info.iters = itmax;
   {
     std::vector<unsigned long long> r(B);
@@ -618,7 +666,7 @@ extern "C" int rb_plan_get_problem(rb_plan *p, int b, double *T, double *xH1, do
   for (int f = 0; f < 6; ++f)
     CK(cudaMemcpyAsync(h + (6 + f) * Nl, p->dsrc + f * NC + b * Nl, Nl * 8,
                        cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(p->hflags + 2 * B + b, p->dflags + 2 * B + b, sizeof(int),
+  CK(cudaMemcpyAsync(p->hflags + B + b, p->dflags + B + b, sizeof(int),
                      cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   double *outs[12] = {xH1, xH2, xHe1, xHe2, xHe3, T, H1i, He1i, He2i, H1h, He1h, He2h};
@@ -627,7 +675,7 @@ extern "C" int rb_plan_get_problem(rb_plan *p, int b, double *T, double *xH1, do
     if (!outs[f]) continue;
     for (size_t i = 0; i < Nl; ++i) outs[f][i] = h[f * Nl + (rev ? Nl - 1 - i : i)];
   }
-  if (iters) *iters = p->hflags[2 * B + b];
+  if (iters) *iters = p->hflags[B + b];
   return RB_OK;
 }
 

@@ -13,7 +13,7 @@
 //                        source_point.f90:299-395, source_plane.f90:249-342)
 //   k_cell_solve         batched per-cell solve_pce_s / solve_pcte_s
 //                        (reference hot loop C: sphere_bgnd.f90:886-907)
-//   k_convergence, k_finish_sweep   n_e convergence test and iteration control
+//   k_converge_finish    n_e convergence test and iteration control
 //                        (sphere_bgnd.f90:284-296)
 //   k_thin_state         optically thin start with the lock-step `_v` solvers
 //                        (sphere_bgnd.f90:379-499; ion_solver.f90:565-696,884-1056)
@@ -46,9 +46,9 @@ struct PlanDev {
   double *col;             // [B][Ndir][3][Nl] threshold optical depths per ray (cell fastest:
                            // the column kernel's lanes are consecutive cells -> coalesced stores)
   const double *zHz;       // [B][2]
-  int *active, *notconv, *iters, *err;  // [B]
+  int *active, *iters, *err;            // [B]
   unsigned long long *resid_bits;       // [B]
-  int *nactive;                         // [1]
+  int *nactive;                         // [kSlots] active-problem count per sweep slot
 };
 
 __device__ __forceinline__ size_t col_index(const PlanDev &P, int b, int il, int idir, int X) {
@@ -582,53 +582,56 @@ k_cell_solve(PlanDev P, int cell_start, int cell_stride, int n_local) {
 }
 
 // ---------------------------------------------------------------------------
-// k_convergence: ne = xH2 nH + (xHe2 + 2 xHe3) nHe over ALL cells;
-// all(|ne/ne_old - 1| < tol)   (sphere_bgnd.f90:289-296)
+// k_converge_finish: one block per problem.  n_e = xH2 nH + (xHe2 + 2 xHe3) nHe
+// over ALL cells; converged when all(|ne/ne_old - 1| < tol)
+// (sphere_bgnd.f90:289-296); then the iteration bookkeeping of the drivers
+// (sphere_bgnd.f90:284-288; slab_bgnd.f90:278-282).  The number of problems still
+// active is accumulated in nactive[slot]; the next slot is cleared for the
+// following sweep, so the host can enqueue sweeps ahead and poll later: once a
+// problem is inactive every kernel returns immediately for it.
 // ---------------------------------------------------------------------------
-__global__ void k_convergence(PlanDev P) {
-  const int b = blockIdx.y;
-  if (!P.active[b]) return;
-  const int il = blockIdx.x * blockDim.x + threadIdx.x;
-  if (il >= P.Nl) return;
-  const size_t c = (size_t)b * P.Nl + il;
-  const double ne = P.x[1][c] * P.nH[c] + (P.x[3][c] + 2.0 * P.x[4][c]) * P.nHe[c];
-  const double change = fabs(ne / P.conv_old[c] - 1.0);
-  if (!(change < P.tol)) P.notconv[b] = 1;
-  if (change == change)
-    atomicMax(&P.resid_bits[b], (unsigned long long)__double_as_longlong(change));
-  P.conv_old[c] = ne;
-}
+constexpr int kSlots = 8;
 
-// one block; iteration bookkeeping per problem
-__global__ void k_finish_sweep(PlanDev P) {
-  __shared__ int s_count;
-  if (threadIdx.x == 0) s_count = 0;
-  __syncthreads();
-  int mine = 0;
-  for (int b = threadIdx.x; b < P.B; b += blockDim.x) {
-    if (P.active[b]) {
-      int act = 1;
-      if (P.err[b]) act = 0;
-      // sphere_bgnd.f90:284-288: the limit is tested before the increment
-      if (P.geom != RB_GEOM_SLAB_BGND && P.iters[b] > RB_OUTER_MAX_ITER && P.max_sweeps >= 0) {
-        atomicMax(&P.err[b], RB_ERR_MAX_ITER_OUTER);
-        act = 0;
-      }
-      P.iters[b] += 1;
-      // max_sweeps < 0: fixed-work mode (benchmarks): exactly -max_sweeps sweeps
-      if (!P.notconv[b] && P.max_sweeps >= 0) act = 0;
-      if (P.geom == RB_GEOM_SLAB_BGND && P.iters[b] >= RB_SLAB_BGND_MAX_SWEEPS &&
-          P.max_sweeps >= 0) act = 0;
-      if (P.max_sweeps > 0 && P.iters[b] >= P.max_sweeps) act = 0;
-      if (P.max_sweeps < 0 && P.iters[b] >= -P.max_sweeps) act = 0;
-      P.active[b] = act;
-      mine += act;
-    }
-    P.notconv[b] = 0;
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_converge_finish(PlanDev P, int slot) {
+  const int b = blockIdx.x;
+  if (b == 0 && threadIdx.x == 0) P.nactive[(slot + 1) % kSlots] = 0;
+  if (!P.active[b]) return;
+  __shared__ double s_max[BLOCK / 32];
+  int notconv = 0;
+  double worst = 0.0;
+  for (int il = threadIdx.x; il < P.Nl; il += BLOCK) {
+    const size_t c = (size_t)b * P.Nl + il;
+    const double ne = P.x[1][c] * P.nH[c] + (P.x[3][c] + 2.0 * P.x[4][c]) * P.nHe[c];
+    const double change = fabs(ne / P.conv_old[c] - 1.0);
+    if (!(change < P.tol)) notconv = 1;
+    if (change > worst) worst = change;  // NaN never wins: it only sets notconv
+    P.conv_old[c] = ne;
   }
-  atomicAdd(&s_count, mine);
+  notconv = __syncthreads_or(notconv);
+  for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_down_sync(0xffffffffu, worst, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = worst;
   __syncthreads();
-  if (threadIdx.x == 0) *P.nactive = s_count;
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < BLOCK / 32; ++w) worst = fmax(worst, s_max[w]);
+    P.resid_bits[b] = (unsigned long long)__double_as_longlong(worst);
+    int act = 1;
+    if (P.err[b]) act = 0;
+    // sphere_bgnd.f90:284-288: the limit is tested before the increment
+    if (P.geom != RB_GEOM_SLAB_BGND && P.iters[b] > RB_OUTER_MAX_ITER && P.max_sweeps >= 0) {
+      atomicMax(&P.err[b], RB_ERR_MAX_ITER_OUTER);
+      act = 0;
+    }
+    P.iters[b] += 1;
+    // max_sweeps < 0: fixed-work mode (benchmarks): exactly -max_sweeps sweeps
+    if (!notconv && P.max_sweeps >= 0) act = 0;
+    if (P.geom == RB_GEOM_SLAB_BGND && P.iters[b] >= RB_SLAB_BGND_MAX_SWEEPS &&
+        P.max_sweeps >= 0) act = 0;
+    if (P.max_sweeps > 0 && P.iters[b] >= P.max_sweeps) act = 0;
+    if (P.max_sweeps < 0 && P.iters[b] >= -P.max_sweeps) act = 0;
+    P.active[b] = act;
+    if (act) atomicAdd(&P.nactive[slot], 1);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -658,11 +661,6 @@ __global__ void k_unpack_cells(PlanDev P, int world, int n_local, const double *
   double *dst = plan_field(P, f);
   dst[il] = v;
   if (two_sided(P.geom)) dst[P.Nl - 1 - il] = v;  // mirrored half
-}
-
-__global__ void k_reset_resid(PlanDev P) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < P.B && P.active[b]) P.resid_bits[b] = 0ull;
 }
 
 // ---------------------------------------------------------------------------

@@ -77,6 +77,16 @@ class Plan(object):
         check(lib().rb_plan_finish_sweep(self._h, C.byref(n)))
         return n.value
 
+    def finish_sweep_async(self):
+        """Enqueue the convergence test of the sweep just enqueued; does not wait."""
+        check(lib().rb_plan_finish_sweep_async(self._h))
+
+    def poll_sweep(self):
+        """Wait for the oldest un-polled sweep; number of problems still active after it."""
+        n = C.c_int(0)
+        check(lib().rb_plan_poll_sweep(self._h, C.byref(n)))
+        return n.value
+
     def sync(self):
         check(lib().rb_plan_sync(self._h))
 
@@ -156,37 +166,55 @@ class Plan(object):
                            device="cuda:%d" % dev)
         return send, recv
 
-    def sharded_sweep(self, rank, world, send, recv, group=None):
-        """One cell-sharded Jacobi sweep: local cells -> pack -> NCCL all-gather ->
-        unpack -> convergence test on the full arrays.  Must run with the plan's
-        stream as torch's current stream (see :meth:`solve_cell_sharded`) so that
-        kernels and the collective are ordered on the device without host syncs.
-        Returns the number of still-active problems (0 = converged)."""
+    def enqueue_sharded_sweep(self, rank, world, send, recv, group=None):
+        """Enqueue one cell-sharded Jacobi sweep: local cells -> pack -> NCCL
+        all-gather -> unpack -> convergence test on the full arrays.  Must run with
+        the plan's stream as torch's current stream (see :meth:`solve_cell_sharded`)
+        so that kernels and the collective are ordered on the device without host
+        synchronisation."""
         import torch.distributed as dist
         self.sweep_local(rank, world)
         self.pack_cells(rank, world, send.data_ptr())
         dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
         self.unpack_cells(world, recv.data_ptr())
-        return self.finish_sweep()
+        self.finish_sweep_async()
 
-    def solve_cell_sharded(self, rank, world, group=None, max_sweeps=100000):
+    def sharded_sweep(self, rank, world, send, recv, group=None):
+        """One sharded sweep, waited for; returns the number of still-active problems."""
+        self.enqueue_sharded_sweep(rank, world, send, recv, group)
+        return self.poll_sweep()
+
+    def solve_cell_sharded(self, rank, world, group=None, max_sweeps=100000, depth=3):
         """Jacobi solve with the sweep's cells dealt cyclically over ``world`` ranks.
 
         Requires ``torch.distributed`` to be initialised (NCCL on GPUs).  Every
-        rank must hold the same staged problem.  Returns the sweep count.
+        rank must hold the same staged problem.  Sweeps are enqueued ``depth`` ahead
+        of the convergence read-back (sweeps enqueued after convergence are no-ops
+        on the device and every rank takes the same decisions, so the collectives
+        stay matched).  Returns the sweep count.
         """
         import torch
         if self.n_problems != 1:
             raise ValueError("cell sharding is defined for a single problem per plan")
         send, recv = self.shard_buffers(world)
         ext = torch.cuda.ExternalStream(self.stream_ptr)
-        sweeps = 0
+        issued = polled = sweeps = 0
+        stop = False
         with torch.cuda.stream(ext):
             self.thin()
-            n_active = 1
-            while n_active > 0 and sweeps < max_sweeps:
-                n_active = self.sharded_sweep(rank, world, send, recv, group)
-                sweeps += 1
+            while True:
+                if not stop and issued - polled < depth and issued < max_sweeps:
+                    self.enqueue_sharded_sweep(rank, world, send, recv, group)
+                    issued += 1
+                    continue
+                if polled >= issued:
+                    break
+                n_active = self.poll_sweep()
+                polled += 1
+                if not stop:
+                    sweeps = polled
+                if n_active == 0:
+                    stop = True
         self.sync()
         return sweeps
 
