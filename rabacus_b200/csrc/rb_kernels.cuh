@@ -25,6 +25,14 @@
 
 namespace rb {
 
+#ifndef RB_LS_UNROLL
+#define RB_LS_UNROLL _Pragma("unroll")
+#endif
+#ifndef RB_FLAG_T
+#define RB_FLAG_T bool
+#endif
+typedef RB_FLAG_T rb_flag_t;
+
 constexpr int kPackPad = 8;    // padding records after the Nl+1 shell records
 constexpr int kSpecStride = 9;  // per-frequency table: 3 sigma ratios, 3+3 weights
 
@@ -666,15 +674,25 @@ __global__ void k_unpack_cells(PlanDev P, int world, int n_local, const double *
 // ---------------------------------------------------------------------------
 // lock-step ("_v") solvers, one block per problem, CPT cells per thread.
 // ---------------------------------------------------------------------------
+// block-wide any(): the lock-step loops' `any(err > tol)` (ion_solver.f90:620,988).
+// On the host (unit-testing the loop logic) a "block" is one thread.
+__host__ __device__ __forceinline__ int block_any(int v) {
+#ifdef __CUDA_ARCH__
+  return __syncthreads_or(v);
+#else
+  return v;
+#endif
+}
+
 template <int CPT>
-__device__ int pce_lockstep(const double (&nH)[CPT], const double (&nHe)[CPT],
+__host__ __device__ int pce_lockstep(const double (&nH)[CPT], const double (&nHe)[CPT],
                             const rb_kchem_t (&k)[CPT], const PhotoRates (&p)[CPT],
-                            const bool (&valid)[CPT], double tol,
+                            const rb_flag_t (&valid)[CPT], double tol,
                             rb_frac_t (&x)[CPT]) {
   PceState s[CPT];
-  bool ok[CPT];
+  rb_flag_t ok[CPT];
   int rc = 0;
-#pragma unroll 1
+RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) {
     ok[i] = valid[i];
     if (ok[i]) {
@@ -685,34 +703,34 @@ __device__ int pce_lockstep(const double (&nH)[CPT], const double (&nHe)[CPT],
   int iter = 0;
   for (;;) {
     int any = 0;
-#pragma unroll 1
+RB_LS_UNROLL
     for (int i = 0; i < CPT; ++i)
       if (ok[i] && s[i].err > tol) any = 1;
-    if (!__syncthreads_or(any)) break;  // ion_solver.f90:620
-#pragma unroll 1
+    if (!block_any(any)) break;  // ion_solver.f90:620
+RB_LS_UNROLL
     for (int i = 0; i < CPT; ++i)
       if (ok[i]) pce_step(nH[i], nHe[i], k[i], p[i].H1i, p[i].He1i, p[i].He2i, x[i], s[i], true);
     iter = iter + 1;
     if (iter > RB_ION_MAX_ITER) { rc = ION_ERR_MAX_ITER_PCE; break; }
   }
-#pragma unroll 1
+RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i)
     if (ok[i]) zero_absent_species(nH[i], nHe[i], x[i]);
   return rc;
 }
 
 template <int CPT>
-__device__ int dudT_lockstep(const double (&nH)[CPT], const double (&nHe)[CPT],
+__host__ __device__ int dudT_lockstep(const double (&nH)[CPT], const double (&nHe)[CPT],
                              const double (&T)[CPT], const PhotoRates (&p)[CPT],
-                             const bool (&valid)[CPT], double z, double Hz,
+                             const rb_flag_t (&valid)[CPT], double z, double Hz,
                              const CaseA &fc, double tol, double (&dudT)[CPT]) {
   rb_kchem_t kc[CPT];
   rb_frac_t x[CPT];
-#pragma unroll 1
+RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i)
     if (valid[i]) kc[i] = get_kchem(T[i], fc.H2, fc.He2, fc.He3);
   const int rc = pce_lockstep<CPT>(nH, nHe, kc, p, valid, tol, x);
-#pragma unroll 1
+RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) {
     if (valid[i]) {
       const rb_kcool_t kl = get_kcool(T[i], fc.H2, fc.He2, fc.He3);
@@ -729,22 +747,22 @@ __device__ int dudT_lockstep(const double (&nH)[CPT], const double (&nHe)[CPT],
 
 // ion_solver.f90:884-1056 (solve_pcte_v)
 template <int CPT>
-__device__ int pcte_lockstep(const double (&nH)[CPT], const double (&nHe)[CPT],
-                             const PhotoRates (&p)[CPT], const bool (&valid)[CPT],
+__host__ __device__ int pcte_lockstep(const double (&nH)[CPT], const double (&nHe)[CPT],
+                             const PhotoRates (&p)[CPT], const rb_flag_t (&valid)[CPT],
                              double z, double Hz, const CaseA &fc, double tol,
                              rb_frac_t (&x)[CPT], double (&T)[CPT]) {
   double Tleft[CPT], Tright[CPT], dudT[CPT], err[CPT];
-  bool floor_[CPT];
+  rb_flag_t floor_[CPT];
   int rc = 0, r;
-#pragma unroll 1
+RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) { Tleft[i] = RB_TFLOOR; Tright[i] = RB_TMAX; }
   r = dudT_lockstep<CPT>(nH, nHe, Tleft, p, valid, z, Hz, fc, tol, dudT);
   if (r) rc = r;
-#pragma unroll 1
+RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) floor_[i] = valid[i] && (dudT[i] < 0.0);
   r = dudT_lockstep<CPT>(nH, nHe, Tright, p, valid, z, Hz, fc, tol, dudT);
   if (r) rc = r;
-#pragma unroll 1
+RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) {
     if (valid[i] && !floor_[i] && dudT[i] > 0.0) rc = ION_ERR_T_NOT_BRACKETED;
     if (floor_[i]) {
@@ -758,13 +776,13 @@ __device__ int pcte_lockstep(const double (&nH)[CPT], const double (&nHe)[CPT],
   int iter = 0;
   for (;;) {
     int any = 0;
-#pragma unroll 1
+RB_LS_UNROLL
     for (int i = 0; i < CPT; ++i)
       if (valid[i] && err[i] > tol) any = 1;
-    if (!__syncthreads_or(any)) break;  // ion_solver.f90:988
+    if (!block_any(any)) break;  // ion_solver.f90:988
     r = dudT_lockstep<CPT>(nH, nHe, T, p, valid, z, Hz, fc, tol, dudT);
     if (r) rc = r;
-#pragma unroll 1
+RB_LS_UNROLL
     for (int i = 0; i < CPT; ++i) {
       const double Told = T[i];
       if (dudT[i] < 0.0 && !floor_[i]) {
@@ -780,7 +798,7 @@ __device__ int pcte_lockstep(const double (&nH)[CPT], const double (&nHe)[CPT],
     if (iter > RB_ION_MAX_ITER) { rc = ION_ERR_MAX_ITER_PCTE; break; }
   }
   rb_kchem_t kc[CPT];
-#pragma unroll 1
+RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i)
     if (valid[i]) kc[i] = get_kchem(T[i], fc.H2, fc.He2, fc.He3);
   r = pce_lockstep<CPT>(nH, nHe, kc, p, valid, tol, x);
@@ -796,10 +814,10 @@ __global__ void __launch_bounds__(512) k_thin_state(PlanDev P) {
   const int Nl = P.Nl;
   double nH[CPT], nHe[CPT], T[CPT];
   PhotoRates p[CPT];
-  bool valid[CPT];
+  rb_flag_t valid[CPT];
   rb_frac_t x[CPT];
   const double *E = P.Edges + (size_t)b * (Nl + 1);
-#pragma unroll 1
+RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) {
     const int il = threadIdx.x + i * blockDim.x;
     valid[i] = il < Nl;
@@ -822,13 +840,13 @@ __global__ void __launch_bounds__(512) k_thin_state(PlanDev P) {
                             P.tol_inner, x, T);
   } else {
     rb_kchem_t k[CPT];
-#pragma unroll 1
+RB_LS_UNROLL
     for (int i = 0; i < CPT; ++i)
       if (valid[i]) k[i] = get_kchem(T[i], fc.H2, fc.He2, fc.He3);
     rc = pce_lockstep<CPT>(nH, nHe, k, p, valid, P.tol_inner, x);
   }
   if (rc) atomicMax(&P.err[b], rc);
-#pragma unroll 1
+RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) {
     if (!valid[i]) continue;
     const int il = threadIdx.x + i * blockDim.x;
@@ -959,11 +977,11 @@ k_zone_lockstep(const double *in, int nn, double z, double Hz, double tol, doubl
   const size_t n = (size_t)nn;
   double nH[CPT], nHe[CPT], T[CPT];
   PhotoRates p[CPT];
-  bool valid[CPT];
+  rb_flag_t valid[CPT];
   rb_frac_t x[CPT];
   rb_kchem_t k[CPT];
   CaseA fc = {1.0, 1.0, 1.0};
-#pragma unroll 1
+RB_LS_UNROLL
   for (int q = 0; q < CPT; ++q) {
     const int i = threadIdx.x + q * blockDim.x;
     valid[q] = i < nn;
@@ -986,7 +1004,7 @@ k_zone_lockstep(const double *in, int nn, double z, double Hz, double tol, doubl
   if (pcte) rc = pcte_lockstep<CPT>(nH, nHe, p, valid, z, Hz, fc, tol, x, T);
   else rc = pce_lockstep<CPT>(nH, nHe, k, p, valid, tol, x);
   if (rc) atomicMax(err, rc);
-#pragma unroll 1
+RB_LS_UNROLL
   for (int q = 0; q < CPT; ++q) {
     const int i = threadIdx.x + q * blockDim.x;
     if (i >= nn) continue;
