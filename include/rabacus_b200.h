@@ -68,6 +68,11 @@ const char *rb_strerror(int code);
 /* number of visible CUDA devices (0 if none / no driver) */
 int rb_device_count(void);
 const char *rb_version(void);
+/* The host-pointer entry points below keep up to 8 released plans (device and
+ * pinned buffers, stream, events) and re-arm one when a later call has the same
+ * geometry and grid shape on the same device; rb_cache_clear() frees them.  (The
+ * reference allocates its work arrays per call, sphere_bgnd.f90:157-175.) */
+void rb_cache_clear(void);
 
 /* ------------------------------------------------------------------------
  * Host-pointer entry points == the f2py boundary.

@@ -42,7 +42,7 @@ GEOM_SPHERE_BGND, GEOM_SPHERE_STROMGREN, GEOM_SLAB_PLANE_1, GEOM_SLAB_PLANE_2, \
 
 # every symbol declared in include/rabacus_b200.h
 EXPORTS = (
-    "rb_strerror", "rb_device_count", "rb_version",
+    "rb_strerror", "rb_device_count", "rb_version", "rb_cache_clear",
     "rb_sphere_bgnd_solve", "rb_sphere_stromgren_solve", "rb_slab_bgnd_solve",
     "rb_slab_plane_solve", "rb_set_column_vs_impact",
     "rb_get_kchem", "rb_get_kcool", "rb_solve_ce", "rb_solve_pce", "rb_solve_pcte",
@@ -79,6 +79,7 @@ def lib():
         L.rb_plan_evals_per_sweep.restype = C.c_longlong
         L.rb_plan_evals_per_sweep.argtypes = [C.c_void_p]
         L.rb_plan_destroy.restype = None
+        L.rb_cache_clear.restype = None
         L.rb_plan_destroy.argtypes = [C.c_void_p]
         _lib = L
     return _lib

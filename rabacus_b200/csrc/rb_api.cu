@@ -199,7 +199,11 @@ struct rb_plan {
   double *dsrc = nullptr;   // 6*B*Nl
   double *dconv = nullptr;
   double4 *dpack = nullptr;
-  double *dspec = nullptr, *dthin = nullptr, *dmu = nullptr, *dcol = nullptr, *dzHz = nullptr;
+  double *dspec = nullptr, *dthin = nullptr, *dmu = nullptr, *dzHz = nullptr;
+  double4 *dcol = nullptr;
+  unsigned *ditems = nullptr;   // column-kernel work list (LPT order), see build_items
+  int n_items = 0, items_start = -1, items_stride = -1, n_sm = 148;
+  std::vector<double> items_edges;  // problem-0 edges the list was built from
   int *dflags = nullptr;    // active, notconv, iters, err : 4*B, then nactive
   unsigned long long *dresid = nullptr;
   // pinned host staging
@@ -224,7 +228,7 @@ extern "C" void rb_plan_destroy(rb_plan *p) {
   cudaFree(p->dEdges); cudaFree(p->dnH); cudaFree(p->dnHe); cudaFree(p->dT);
   cudaFree(p->dx); cudaFree(p->dsrc); cudaFree(p->dconv); cudaFree(p->dpack);
   cudaFree(p->dspec); cudaFree(p->dthin); cudaFree(p->dmu); cudaFree(p->dcol);
-  cudaFree(p->dzHz); cudaFree(p->dflags); cudaFree(p->dresid);
+  cudaFree(p->dzHz); cudaFree(p->dflags); cudaFree(p->dresid); cudaFree(p->ditems);
   cudaFreeHost(p->hEdges); cudaFreeHost(p->hnH); cudaFreeHost(p->hnHe); cudaFreeHost(p->hT);
   cudaFreeHost(p->hspec); cudaFreeHost(p->hthin); cudaFreeHost(p->hzHz);
   cudaFreeHost(p->hout); cudaFreeHost(p->hflags);
@@ -281,7 +285,14 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   ALLOC(p->dconv, NC * 8); ALLOC(p->dpack, B * (Nl + 1 + kPackPad) * sizeof(double4));
   ALLOC(p->dspec, B * Nnu * kSpecStride * 8); ALLOC(p->dthin, B * 6 * 8);
   ALLOC(p->dmu, 2 * (size_t)std::max(1, d.Nmu) * 8);
-  ALLOC(p->dcol, NC * (size_t)p->Ndir * 3 * 8); ALLOC(p->dzHz, B * 2 * 8);
+  ALLOC(p->dcol, NC * (size_t)p->Ndir * sizeof(double4)); ALLOC(p->dzHz, B * 2 * 8);
+  if (d.geometry == RB_GEOM_SPHERE_BGND)
+    ALLOC(p->ditems, (size_t)((Nl + 31) / 32) * ((d.Nmu + 1) / 2) * sizeof(unsigned));
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
   ALLOC(p->dflags, (3 * B + kSlots) * sizeof(int)); ALLOC(p->dresid, B * 8);
   HALLOC(p->hEdges, B * (Nl + 1) * 8); HALLOC(p->hnH, NC * 8); HALLOC(p->hnHe, NC * 8);
   HALLOC(p->hT, NC * 8); HALLOC(p->hspec, B * Nnu * kSpecStride * 8);
@@ -403,10 +414,126 @@ extern "C" int rb_plan_thin(rb_plan *p) {
   return RB_OK;
 }
 
-static int group_size(int ndir) {  // each thread of a group takes 2 directions
-  int gs = 8;
-  while (2 * gs < ndir && gs < 128) gs *= 2;
-  return gs;
+// Work list of the shared-memory column kernel: one item per (block of 32
+// consecutive local cells, |mu| pair), sorted by descending ray length m+1 of the
+// block's innermost cell (longest-processing-time-first).  Built from problem 0's
+// edges (all problems of a plan share the shape; the order is a scheduling
+// heuristic only) and cached until the edges or the cell deal change.
+static int build_items(rb_plan *p, int cell_start, int cell_stride, int n_local) {
+  const int Nl = p->d.Nl, Nmu = p->d.Nmu;
+  const double *E = p->hEdges;  // solver orientation: non-increasing
+  if (p->items_start == cell_start && p->items_stride == cell_stride &&
+      p->items_edges.size() == (size_t)Nl + 1 &&
+      memcmp(p->items_edges.data(), E, sizeof(double) * (Nl + 1)) == 0)
+    return RB_OK;
+  const int nblk = (n_local + 31) / 32, npair = (Nmu + 1) / 2;
+  if (nblk > 0xffff || npair > 0xffff) return RB_ERR_UNSUPPORTED;
+  std::vector<std::pair<int, unsigned>> v;
+  v.reserve((size_t)nblk * npair);
+  for (int ip = 0; ip < npair; ++ip) {
+    const double mu = p->mu[ip];
+    const double st = sqrt(1.0 - mu * mu);
+    for (int jb = 0; jb < nblk; ++jb) {
+      const int j = std::min(n_local - 1, jb * 32 + 31);
+      const int il = cell_start + j * cell_stride;
+      const double pr = 0.5 * (E[il] + E[il + 1]) * st;
+      int lo = 1, hi = Nl;  // smallest i >= 1 with E_i <= p
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (E[mid] <= pr) hi = mid; else lo = mid + 1;
+      }
+      v.emplace_back(-lo, (unsigned)jb | ((unsigned)ip << 16));
+    }
+  }
+  std::sort(v.begin(), v.end());
+  std::vector<unsigned> items(v.size());
+  for (size_t i = 0; i < v.size(); ++i) items[i] = v[i].second;
+  p->n_items = (int)items.size();
+  CK(cudaMemcpyAsync(p->ditems, items.data(), items.size() * sizeof(unsigned),
+                     cudaMemcpyHostToDevice, p->stream));
+  CK(cudaStreamSynchronize(p->stream));  // `items` is pageable and dies here
+  p->items_start = cell_start; p->items_stride = cell_stride;
+  p->items_edges.assign(E, E + Nl + 1);
+  return RB_OK;
+}
+
+template <typename K>
+static int set_smem(K kern, size_t smem) {
+  if (smem > 48 * 1024)
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return RB_OK;
+}
+
+static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, int n_local) {
+  const int Nl = p->d.Nl, B = p->d.n_problems;
+  cudaStream_t s = p->stream;
+  const size_t smem = (size_t)(Nl + 1 + kPackPad) * sizeof(double4);
+  const size_t kMaxSmem = 227 * 1024 - 1024;
+  if (smem > kMaxSmem) {  // records do not fit in shared memory: global-memory fallback
+    dim3 gp((Nl + 1 + kPackPad + 255) / 256, B);
+    k_pack_shells<<<gp, 256, 0, s>>>(p->P);
+    dim3 gc((n_local + 127) / 128, (p->d.Nmu + 1) / 2, B);
+    k_sphere_columns<128, 1, 6><<<gc, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local);
+    p->info.n_launches += 2;
+    return RB_OK;
+  }
+  int rc = build_items(p, cell_start, cell_stride, n_local);
+  if (rc) return rc;
+  // 24 warps per SM at <= 80 registers; as many CTAs per SM as the records allow
+  int cps = (int)std::min<size_t>(3, kMaxSmem / (smem + 1024));
+  const int warps = 24 / cps;
+  const int want = p->n_sm * cps;  // CTAs that fill the GPU once
+  int per_problem = std::max(1, (want + B - 1) / B);
+  per_problem = std::min(per_problem, (p->n_items + warps - 1) / warps);
+  dim3 g(per_problem, B);
+#define COLS(THREADS, MINB)                                                                  \
+  do {                                                                                       \
+    rc = set_smem(k_sphere_columns_smem<THREADS, 1, MINB>, smem);                            \
+    if (rc) return rc;                                                                       \
+    k_sphere_columns_smem<THREADS, 1, MINB><<<g, THREADS, smem, s>>>(                        \
+        p->P, cell_start, cell_stride, n_local, p->ditems, p->n_items);                      \
+  } while (0)
+  if (cps == 1) COLS(768, 1);
+  else if (cps == 2) COLS(384, 2);
+  else COLS(256, 3);
+#undef COLS
+  p->info.n_launches += 1;
+  return RB_OK;
+}
+
+static int launch_nu_rates(rb_plan *p, int cell_start, int cell_stride, int n_local) {
+  const int B = p->d.n_problems, Nnu = p->d.Nnu, g = p->d.geometry;
+  cudaStream_t s = p->stream;
+  int rc = RB_OK;
+#define NU(ATT, KU, RU, BLOCK, MINB)                                                         \
+  do {                                                                                       \
+    const int ndir_pad = (p->Ndir + RU - 1) / RU * RU;                                       \
+    const size_t smem = (size_t)ndir_pad * sizeof(double4) +                                 \
+                        (ATT ? 0 : kExpTabEntries * kExpTabCopies * sizeof(double));         \
+    rc = set_smem(k_nu_rates<ATT, KU, RU, BLOCK, MINB>, smem);                               \
+    if (rc) return rc;                                                                       \
+    int occ = 1;                                                                             \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_nu_rates<ATT, KU, RU, BLOCK, MINB>, \
+                                                  BLOCK, smem);                              \
+    const int want = p->n_sm * std::max(1, occ);                                             \
+    const int per_problem = std::min(n_local, std::max(1, (want + B - 1) / B));              \
+    dim3 gn(per_problem, B);                                                                 \
+    k_nu_rates<ATT, KU, RU, BLOCK, MINB><<<gn, BLOCK, smem, s>>>(p->P, cell_start,           \
+                                                                 cell_stride, n_local);      \
+  } while (0)
+  // thread <-> 4 frequencies, 2 rays in flight: 8 independent exp chains per thread
+  if (g == RB_GEOM_SLAB_BGND) {
+    if (Nnu <= 32) NU(1, 1, 1, 32, 8);
+    else if (Nnu <= 64) NU(1, 1, 1, 64, 4);
+    else NU(1, 1, 1, 128, 3);
+  } else {
+    if (Nnu <= 128) NU(0, 4, 2, 32, 12);
+    else if (Nnu <= 256) NU(0, 4, 2, 64, 6);
+    else NU(0, 4, 2, 128, 4);
+  }
+#undef NU
+  p->info.n_launches += 1;
+  return rc;
 }
 
 extern "C" int rb_plan_sweep_local(rb_plan *p, int cell_start, int cell_stride) {
@@ -417,46 +544,23 @@ extern "C" int rb_plan_sweep_local(rb_plan *p, int cell_start, int cell_stride) 
   const int n_local = (cell_start < ncell) ? (ncell - cell_start + cell_stride - 1) / cell_stride : 0;
   cudaStream_t s = p->stream;
   cudaEvent_t *sev = p->sev[p->sweeps_issued % kSlots];
+  int rc = RB_OK;
   cudaEventRecord(sev[0], s);
   if (g == RB_GEOM_SPHERE_BGND) {
-    dim3 gp((Nl + 1 + kPackPad + 255) / 256, B);
-    k_pack_shells<<<gp, 256, 0, s>>>(p->P);
-    if (n_local > 0) {
-      const int npair = (p->d.Nmu + 1) / 2;
-      // 128 threads, one shell record per trip, <= 80 registers (6 CTAs/SM): the
-      // fastest of the {block, unroll, occupancy} variants timed on B200
-      // (profiles/r01_kernel_variants.md)
-      dim3 gc((n_local + 127) / 128, npair, B);
-      k_sphere_columns<128, 1, 6><<<gc, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local);
-    }
-    p->info.n_launches += 2;
+    if (n_local > 0) rc = launch_sphere_columns(p, cell_start, cell_stride, n_local);
+    if (rc) return rc;
   } else {
     k_column_taus<512><<<B, 512, 0, s>>>(p->P);
     p->info.n_launches += 1;
   }
   cudaEventRecord(sev[1], s);
   if (n_local > 0) {
-    const int gs = group_size(p->Ndir);
-    const int cpb = 128 / gs;
-    dim3 gn((n_local + cpb - 1) / cpb, B);
-    const size_t smem = ((size_t)p->d.Nnu * kSpecStride + kExpTabEntries * kExpTabCopies) *
-                        sizeof(double);
-#define NU(ATT, KU, MINB)                                                                      \
-  do {                                                                                         \
-    if (smem > 48 * 1024)                                                                      \
-      CK(cudaFuncSetAttribute(k_nu_rates<ATT, KU, MINB>,                                       \
-                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-    k_nu_rates<ATT, KU, MINB><<<gn, 128, smem, s>>>(p->P, cell_start, cell_stride, n_local, gs); \
-  } while (0)
-    // frequency loop unrolled 4x (2 rays x 4 frequencies = 8 independent exp chains
-    // per thread): fastest variant timed on B200 (profiles/r01_kernel_variants.md)
-    if (g == RB_GEOM_SLAB_BGND) NU(1, 1, 3);
-    else NU(0, 4, 3);
-#undef NU
+    rc = launch_nu_rates(p, cell_start, cell_stride, n_local);
+    if (rc) return rc;
     cudaEventRecord(sev[2], s);
     dim3 gs3((n_local + 127) / 128, B);
     k_cell_solve<<<gs3, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local);
-    p->info.n_launches += 2;
+    p->info.n_launches += 1;
   } else {
     cudaEventRecord(sev[2], s);
   }
@@ -702,6 +806,69 @@ static int check_fits(int i_rec_meth, int i_photo_fit, int i_rate_fit) {
   return RB_OK;
 }
 
+// ---------------------------------------------------------------------------
+// plan cache for the one-shot entry points: a solver class calls rb_*_solve once
+// per solve, typically many times with the same grid shape; creating a plan
+// (15 cudaMalloc, 9 cudaMallocHost, stream, 48 events) costs more than a small
+// solve, so released plans are kept and re-armed when the shape matches.
+// ---------------------------------------------------------------------------
+#include <mutex>
+static std::mutex g_cache_mu;
+static std::vector<rb_plan *> g_cache;
+static const size_t kCacheMax = 8;
+
+static int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) cudaGetLastError();
+  return dev;
+}
+
+static int plan_acquire(rb_plan **out, const rb_plan_desc &d) {
+  const int dev = d.device >= 0 ? d.device : current_device();
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (size_t i = 0; i < g_cache.size(); ++i) {
+      rb_plan *p = g_cache[i];
+      if (p->d.geometry == d.geometry && p->d.n_problems == d.n_problems && p->d.Nl == d.Nl &&
+          p->d.Nnu == d.Nnu && p->d.Nmu == d.Nmu && p->d.device == dev) {
+        g_cache.erase(g_cache.begin() + i);
+        p->d.i_find_Teq = d.i_find_Teq; p->d.fixed_fcA = d.fixed_fcA; p->d.tol = d.tol;
+        p->d.max_sweeps = d.max_sweeps;
+        p->P.find_Teq = d.i_find_Teq; p->P.max_sweeps = d.max_sweeps; p->P.fcA = d.fixed_fcA;
+        p->P.tol = d.tol; p->P.tol_inner = d.tol * RB_TOL_FRAC;
+        *out = p;
+        return RB_OK;
+      }
+    }
+  }
+  rb_plan_desc dd = d;
+  dd.device = dev;
+  return rb_plan_create(out, &dd);
+}
+
+static void plan_release(rb_plan *p) {
+  if (!p) return;
+  rb_plan *evict = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache.push_back(p);
+    if (g_cache.size() > kCacheMax) {
+      evict = g_cache.front();
+      g_cache.erase(g_cache.begin());
+    }
+  }
+  if (evict) rb_plan_destroy(evict);
+}
+
+extern "C" void rb_cache_clear(void) {
+  std::vector<rb_plan *> all;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    all.swap(g_cache);
+  }
+  for (rb_plan *p : all) rb_plan_destroy(p);
+}
+
 static int solve_one(int geom, const double *Edges, const double *nH, const double *nHe,
                      double *T, int Nmu, const double *E_eV, const double *shape,
                      double fixed_fcA, int i_find_Teq, int i_thin, double z, double Hz,
@@ -712,7 +879,7 @@ static int solve_one(int geom, const double *Edges, const double *nH, const doub
   d.geometry = geom; d.n_problems = 1; d.Nl = Nl; d.Nnu = Nnu; d.Nmu = Nmu;
   d.i_find_Teq = i_find_Teq; d.fixed_fcA = fixed_fcA; d.tol = tol; d.device = -1;
   rb_plan *p = nullptr;
-  int rc = rb_plan_create(&p, &d);
+  int rc = plan_acquire(&p, d);
   if (rc) return rc;
   rc = rb_plan_set_problem(p, 0, Edges, nH, nHe, T, E_eV, shape, z, Hz);
   if (!rc) rc = rb_plan_upload(p);
@@ -738,7 +905,8 @@ static int solve_one(int geom, const double *Edges, const double *nH, const doub
     info->ms_total =
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   }
-  rb_plan_destroy(p);
+  if (rc == RB_OK) plan_release(p);
+  else rb_plan_destroy(p);
   return rc;
 }
 

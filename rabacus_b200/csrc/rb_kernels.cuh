@@ -51,34 +51,27 @@ struct PlanDev {
   const double *spec;      // [B][Nnu][9]
   const double *thin;      // [B][6] optically thin integrals (sum of weights)
   const double *mu, *wmu;  // [Nmu] Gauss-Legendre nodes / weights
-  double *col;             // [B][Ndir][3][Nl] threshold optical depths per ray (cell fastest:
-                           // the column kernel's lanes are consecutive cells -> coalesced stores)
+  double4 *col;            // [B][Nl][Ndir] per ray {tau_HI,th, tau_HeI,th, tau_HeII,th, quadrature
+                           // weight}: one aligned 32-byte sector per ray, written whole by the
+                           // column kernels, and one contiguous Ndir*32 B run per cell for the
+                           // frequency kernel
   const double *zHz;       // [B][2]
   int *active, *iters, *err;            // [B]
   unsigned long long *resid_bits;       // [B]
   int *nactive;                         // [kSlots] active-problem count per sweep slot
 };
 
-__device__ __forceinline__ size_t col_index(const PlanDev &P, int b, int il, int idir, int X) {
-  return (((size_t)b * P.Ndir + idir) * 3 + X) * (size_t)P.Nl + il;
+__device__ __forceinline__ size_t col_index(const PlanDev &P, int b, int il, int idir) {
+  return ((size_t)b * P.Nl + il) * (size_t)P.Ndir + idir;
 }
 
 __device__ __forceinline__ bool two_sided(int geom) {
   return geom == RB_GEOM_SLAB_PLANE_2 || geom == RB_GEOM_SLAB_BGND;
 }
 
-// ---------------------------------------------------------------------------
-// k_pack_shells: one thread per (problem, shell edge k = 0..Nl)
-// ---------------------------------------------------------------------------
-__global__ void k_pack_shells(PlanDev P) {
-  const int b = blockIdx.y;
-  if (!P.active[b]) return;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k > P.Nl + kPackPad - 1) return;
-  if (k > P.Nl) {  // padding read (never used) by the column kernel's prefetch
-    P.pack[(size_t)b * (P.Nl + 1 + kPackPad) + k] = make_double4(0.0, 0.0, 0.0, 0.0);
-    return;
-  }
+// shell record k of problem b (k_pack_shells / the shared-memory fill)
+__device__ __forceinline__ double4 shell_record(const PlanDev &P, int b, int k) {
+  if (k > P.Nl) return make_double4(0.0, 0.0, 0.0, 0.0);  // padding read by the prefetch
   const double E = P.Edges[(size_t)b * (P.Nl + 1) + k];
   double4 v;
   v.x = E * E;  // geometry.f90:148  Edges(i1)*Edges(i1)
@@ -90,7 +83,19 @@ __global__ void k_pack_shells(PlanDev P) {
   } else {
     v.y = v.z = v.w = 0.0;
   }
-  P.pack[(size_t)b * (P.Nl + 1 + kPackPad) + k] = v;
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// k_pack_shells: one thread per (problem, shell edge k = 0..Nl) -- only for the
+// global-memory fallback of the column kernel
+// ---------------------------------------------------------------------------
+__global__ void k_pack_shells(PlanDev P) {
+  const int b = blockIdx.y;
+  if (!P.active[b]) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > P.Nl + kPackPad - 1) return;
+  P.pack[(size_t)b * (P.Nl + 1 + kPackPad) + k] = shell_record(P, b, k);
 }
 
 // ---------------------------------------------------------------------------
@@ -183,20 +188,16 @@ __device__ __forceinline__ void col_advance(ColAcc &a, const double4 *__restrict
   }
 }
 
-template <int BLOCK, int U, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB)
-k_sphere_columns(PlanDev P, int cell_start, int cell_stride, int n_local) {
-  const int b = blockIdx.z;
-  if (!P.active[b]) return;
-  const int j = blockIdx.x * BLOCK + threadIdx.x;
-  if (j >= n_local) return;
-  const int il = cell_start + j * cell_stride;
+// One (cell il, |mu| pair ip) of SphereBgnd: both rays' threshold optical depths.
+// `pk` = shell records (global or shared), `il_w0` = cell of lane 0 of the warp.
+template <int U>
+__device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il, int il_w0,
+                                                int cell_stride, int ip,
+                                                const double4 *__restrict__ pk, bool store) {
   const int Nl = P.Nl, Nmu = P.Nmu;
-  const int ip = blockIdx.y;
   const int imu_in = ip;               // xi ascending: negative mu first
   const int imu_out = Nmu - 1 - ip;
   const double *E = P.Edges + (size_t)b * (Nl + 1);
-  const double4 *pk = P.pack + (size_t)b * (Nl + 1 + kPackPad);
 
   const double mu = P.mu[imu_in];
   const double r_ray = (E[il] + E[il + 1]) * 0.5;
@@ -220,8 +221,6 @@ k_sphere_columns(PlanDev P, int cell_start, int cell_stride, int n_local) {
   // The lanes of a warp hold cells il_w .. il_w + 31*stride: only records
   // k-1 in that window can be a lane's own shell, so the snapshot test is
   // confined to a warp-uniform sub-range of the loop.
-  const int lane = threadIdx.x & 31;
-  const int il_w0 = il - lane * cell_stride;
   const int kA = il_w0 + 1;                        // first record that may close an own shell
   const int kB = il_w0 + 31 * cell_stride + 1;     // last such record
   ColAcc a;
@@ -253,19 +252,69 @@ k_sphere_columns(PlanDev P, int cell_start, int cell_stride, int n_local) {
     Nin1 = (2.0 * S1 - A1 - 0.5 * d1) + t1;
     Nin2 = (2.0 * S2 - A2 - 0.5 * d2) + t2;
   }
-  // tau_X_th = N_X * sigma_X_th   (sphere_bgnd.f90:794-796)
+  // tau_X_th = N_X * sigma_X_th   (sphere_bgnd.f90:794-796); 4th slot: GL weight
+  if (!store) return;
   if (imu_in == imu_out) {  // odd Nmu: the mu ~ 0 node, both formulas agree
     const bool inward = (mu <= 0.0);
-    P.col[col_index(P, b, il, imu_in, 0)] = (inward ? Nin0 : Nout0) * P.sigma_th[0];
-    P.col[col_index(P, b, il, imu_in, 1)] = (inward ? Nin1 : Nout1) * P.sigma_th[1];
-    P.col[col_index(P, b, il, imu_in, 2)] = (inward ? Nin2 : Nout2) * P.sigma_th[2];
+    P.col[col_index(P, b, il, imu_in)] =
+        make_double4((inward ? Nin0 : Nout0) * P.sigma_th[0], (inward ? Nin1 : Nout1) * P.sigma_th[1],
+                     (inward ? Nin2 : Nout2) * P.sigma_th[2], P.wmu[imu_in]);
   } else {
-    P.col[col_index(P, b, il, imu_in, 0)] = Nin0 * P.sigma_th[0];
-    P.col[col_index(P, b, il, imu_in, 1)] = Nin1 * P.sigma_th[1];
-    P.col[col_index(P, b, il, imu_in, 2)] = Nin2 * P.sigma_th[2];
-    P.col[col_index(P, b, il, imu_out, 0)] = Nout0 * P.sigma_th[0];
-    P.col[col_index(P, b, il, imu_out, 1)] = Nout1 * P.sigma_th[1];
-    P.col[col_index(P, b, il, imu_out, 2)] = Nout2 * P.sigma_th[2];
+    P.col[col_index(P, b, il, imu_in)] = make_double4(
+        Nin0 * P.sigma_th[0], Nin1 * P.sigma_th[1], Nin2 * P.sigma_th[2], P.wmu[imu_in]);
+    P.col[col_index(P, b, il, imu_out)] = make_double4(
+        Nout0 * P.sigma_th[0], Nout1 * P.sigma_th[1], Nout2 * P.sigma_th[2], P.wmu[imu_out]);
+  }
+}
+
+// Fallback for grids whose shell records do not fit in shared memory
+// (Nl > ~7000): records read from global memory (k_pack_shells), one thread per
+// (cell, |mu| pair).
+template <int BLOCK, int U, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_sphere_columns(PlanDev P, int cell_start, int cell_stride, int n_local) {
+  const int b = blockIdx.z;
+  if (!P.active[b]) return;
+  const int j = blockIdx.x * BLOCK + threadIdx.x;
+  if (j >= n_local) return;
+  const int il = cell_start + j * cell_stride;
+  const int lane = threadIdx.x & 31;
+  sphere_ray_pair<U>(P, b, il, il - lane * cell_stride, cell_stride, blockIdx.y,
+                     P.pack + (size_t)b * (P.Nl + 1 + kPackPad), true);
+}
+
+// ---------------------------------------------------------------------------
+// k_sphere_columns_smem: the ray-segment column kernel (reference hot loop A).
+// A CTA first stages the problem's Nl+1 shell records {E^2, n_HI, n_HeI, n_HeII}
+// in shared memory (coalesced loads of Edges, nH, nHe and the three fractions;
+// this replaces the separate pack kernel), then its warps walk a list of work
+// items -- (block of 32 consecutive local cells, |mu| pair) -- sorted by
+// descending ray length on the host (longest-processing-time-first: the grid
+// drains evenly although ray lengths span 1..Nl shells).  In the segment loop
+// every lane of a warp reads the same record: a shared-memory broadcast instead
+// of an L1 round trip per segment.
+// grid = (CTAs per problem, B); items[it] = jblk | ip << 16.
+// ---------------------------------------------------------------------------
+template <int THREADS, int U, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_sphere_columns_smem(PlanDev P, int cell_start, int cell_stride, int n_local,
+                      const unsigned *__restrict__ items, int n_items) {
+  const int b = blockIdx.y;
+  if (!P.active[b]) return;
+  extern __shared__ double4 s_pk[];
+  const int nrec = P.Nl + 1 + kPackPad;
+  for (int k = threadIdx.x; k < nrec; k += THREADS) s_pk[k] = shell_record(P, b, k);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int nwarp = THREADS / 32;
+  for (int it = blockIdx.x * nwarp + (threadIdx.x >> 5); it < n_items; it += gridDim.x * nwarp) {
+    const unsigned item = items[it];
+    const int jw = (int)(item & 0xffffu) * 32;
+    const int ip = (int)(item >> 16);
+    const int j = jw + lane;
+    const bool valid = j < n_local;
+    const int il = cell_start + (valid ? j : n_local - 1) * cell_stride;
+    sphere_ray_pair<U>(P, b, il, cell_start + jw * cell_stride, cell_stride, ip, s_pk, valid);
   }
 }
 
@@ -353,11 +402,12 @@ __global__ void __launch_bounds__(BLOCK) k_column_taus(PlanDev P) {
     for (int q = k0; q < k1; ++q) {
       const int k = pass ? (Nl - 1 - q) : q;
       layer_dtau(P, E, b, k, dt);
+      // slab_bgnd.f90:701-713; 4th slot: weight of the direction (1/2 + 1/2 for the
+      // two-sided slabs, slab_bgnd.f90:718-747)
+      P.col[col_index(P, b, k, pass)] = make_double4(run[0] + 0.5 * dt[0], run[1] + 0.5 * dt[1],
+                                                     run[2] + 0.5 * dt[2], npass == 2 ? 0.5 : 1.0);
 #pragma unroll
-      for (int X = 0; X < 3; ++X) {
-        P.col[col_index(P, b, k, pass, X)] = run[X] + 0.5 * dt[X];   // slab_bgnd.f90:701-713
-        run[X] += dt[X];
-      }
+      for (int X = 0; X < 3; ++X) run[X] += dt[X];
     }
   }
 }
@@ -415,132 +465,125 @@ __device__ __forceinline__ double exp_nonpos(double x, unsigned s_exp_lane) {
 }
 
 // ---------------------------------------------------------------------------
-// k_nu_rates: fused optical depth -> attenuation -> 6 frequency integrals ->
-// direction quadrature, for the cells il = cell_start + j*cell_stride.
+// k_nu_rates: fused optical depth -> attenuation -> direction quadrature -> 6
+// frequency integrals, for the cells il = cell_start + j*cell_stride
+// (reference hot loop B: sphere_bgnd.f90:794-856, source_background.f90:259-446).
 //
-// Thread <-> 2 rays; a group of GS threads (GS = 8..128, power of two) owns one
-// cell and strides over its directions; the per-frequency table
-// {-sigma_X/sigma_X,th (3), W_ion,X (3), W_heat,X (3)} sits in shared memory and
-// is read as a broadcast (all lanes at the same nu), one read serving both rays.
-// Per (ray, nu):
+// Thread <-> KU frequencies, kept in registers as -sigma_X(nu)/sigma_X,th; the
+// CTA (BLOCK threads = BLOCK*KU frequencies per pass) owns one cell at a time
+// and walks its rays, whose records {tau_HI,th, tau_HeI,th, tau_HeII,th, w} are
+// staged in shared memory (one contiguous run per cell) and read as broadcasts,
+// one read serving all KU frequencies.  Per (ray, nu):
 //     -tau = sum_X tau_X,th * (-ra_X)      (sphere_bgnd.f90:798-800, s_b.f90:267)
 //     a    = exp(-tau)   or   E2(tau)      (s_b.f90:268 ; :385-388)
-//     acc_j += W_j(nu) * a                 (s_b.f90:306-308,348-351 + utils.f90:19-20,
-//                                           trapezoid folded into W_j)
-// then   rate_j = sum_dir w_dir acc_j, and for SphereBgnd the reference's
+//     A(nu) += w_ray * a
+// and once per (cell, nu):  rate_j += W_j(nu) * A(nu)   (s_b.f90:306-308,348-351 +
+// utils.f90:19-20, trapezoid folded into W_j).  The reference integrates over
+// nu per ray and then sums the rays (sphere_bgnd.f90:837-856); both sums are
+// finite and linear, so they are exchanged here: the six weighted accumulations
+// are paid per (cell, nu) instead of per (cell, ray, nu).  Then for SphereBgnd
 //     src <- (src_old + sum)/2             (sphere_bgnd.f90:837-856).
-// Algorithmic FP64 work per (ray, nu): 3 + 10 + 6 = 19 instructions.
+// Algorithmic FP64 work per (ray, nu): 3 + 10 + 1 = 14 instructions.
+// grid = (CTAs per problem, B); a CTA strides over the problem's local cells.
 // ---------------------------------------------------------------------------
-template <int ATT_E2, int KU, int MINB>
-__global__ void __launch_bounds__(128, MINB)
-k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int gs) {
+template <int ATT_E2, int KU, int RU, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local) {
   const int b = blockIdx.y;
   if (!P.active[b]) return;
-  extern __shared__ double s_dyn[];
-  double *s_exp = s_dyn;                                        // [64][16]
-  double *s_tab = s_dyn + kExpTabEntries * kExpTabCopies;       // [Nnu][9]
-  __shared__ double s_red[6][4];
+  extern __shared__ double4 s_dyn4[];
+  double4 *s_ray = s_dyn4;                                     // [ndir_pad]
   const int Nnu = P.Nnu, Nl = P.Nl, ndir = P.Ndir;
-  {
-    const double *g = P.spec + (size_t)b * Nnu * kSpecStride;
-    for (int i = threadIdx.x; i < Nnu * kSpecStride; i += blockDim.x) {
-      const double v = g[i];
-      s_tab[i] = (i % kSpecStride) < 3 ? -v : v;  // store -ra_X: the loop forms -tau
-    }
-    if (!ATT_E2) fill_exp_table(s_exp);
-  }
-  __syncthreads();
+  const int ndir_pad = (ndir + RU - 1) / RU * RU;
+  double *s_exp = reinterpret_cast<double *>(s_dyn4 + ndir_pad);   // [64][16]
+  __shared__ double s_red[6][BLOCK / 32];
+  if (!ATT_E2) fill_exp_table(s_exp);
   const unsigned s_exp_lane = (unsigned)__cvta_generic_to_shared(s_exp) +
                               ((threadIdx.x & (kExpTabCopies - 1)) << 3);
+  const double *spec = P.spec + (size_t)b * Nnu * kSpecStride;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
-  const int cpb = 128 / gs;             // cells per block
-  const int grp = threadIdx.x / gs;     // which cell of the block
-  const int gl = threadIdx.x % gs;      // lane within the group
-  const int j = blockIdx.x * cpb + grp;
-  const bool valid = (j < n_local);
-  const int il = valid ? cell_start + j * cell_stride : 0;
-  const size_t c = (size_t)b * Nl + il;
-
-  double part[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if (valid) {
-    for (int ia = gl; ia < ndir; ia += 2 * gs) {
-      const int ib = ia + gs;
-      const bool hb = ib < ndir;
-      const double t0 = P.col[col_index(P, b, il, ia, 0)], t1 = P.col[col_index(P, b, il, ia, 1)],
-                   t2 = P.col[col_index(P, b, il, ia, 2)];
-      const double u0 = hb ? P.col[col_index(P, b, il, ib, 0)] : 0.0,
-                   u1 = hb ? P.col[col_index(P, b, il, ib, 1)] : 0.0,
-                   u2 = hb ? P.col[col_index(P, b, il, ib, 2)] : 0.0;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0;
-      double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0, b4 = 0.0, b5 = 0.0;
-#pragma unroll KU
-      for (int k = 0; k < Nnu; ++k) {
-        const double *row = s_tab + k * kSpecStride;
-        const double r0 = row[0], r1 = row[1], r2 = row[2];
-        const double xa = fma(t2, r2, fma(t1, r1, t0 * r0));   // = -tau
-        const double xb = fma(u2, r2, fma(u1, r1, u0 * r0));
-        const double ea = ATT_E2 ? e2xa(-xa) : exp_nonpos(xa, s_exp_lane);
-        const double eb = ATT_E2 ? e2xa(-xb) : exp_nonpos(xb, s_exp_lane);
-        const double w3 = row[3], w4 = row[4], w5 = row[5], w6 = row[6], w7 = row[7],
-                     w8 = row[8];
-        a0 = fma(w3, ea, a0); b0 = fma(w3, eb, b0);
-        a1 = fma(w4, ea, a1); b1 = fma(w4, eb, b1);
-        a2 = fma(w5, ea, a2); b2 = fma(w5, eb, b2);
-        a3 = fma(w6, ea, a3); b3 = fma(w6, eb, b3);
-        a4 = fma(w7, ea, a4); b4 = fma(w7, eb, b4);
-        a5 = fma(w8, ea, a5); b5 = fma(w8, eb, b5);
-      }
-      double wa, wb;
-      if (P.geom == RB_GEOM_SPHERE_BGND) {
-        wa = P.wmu[ia];
-        wb = hb ? P.wmu[ib] : 0.0;
-      } else {
-        wa = two_sided(P.geom) ? 0.5 : 1.0;
-        wb = hb ? wa : 0.0;
-      }
-      part[0] = fma(b0, wb, fma(a0, wa, part[0]));
-      part[1] = fma(b1, wb, fma(a1, wa, part[1]));
-      part[2] = fma(b2, wb, fma(a2, wa, part[2]));
-      part[3] = fma(b3, wb, fma(a3, wa, part[3]));
-      part[4] = fma(b4, wb, fma(a4, wa, part[4]));
-      part[5] = fma(b5, wb, fma(a5, wa, part[5]));
+  for (int j = blockIdx.x; j < n_local; j += gridDim.x) {
+    const int il = cell_start + j * cell_stride;
+    const size_t c = (size_t)b * Nl + il;
+    __syncthreads();  // previous cell's rays / reduction scratch are no longer read
+    {
+      const double4 *g = P.col + col_index(P, b, il, 0);
+      for (int i = threadIdx.x; i < ndir_pad; i += BLOCK)
+        s_ray[i] = (i < ndir) ? g[i] : make_double4(0.0, 0.0, 0.0, 0.0);  // pad: weight 0
     }
-  }
-  // reduce over the group: shuffles inside a warp, shared memory across warps
-  const int wl = (gs < 32) ? gs : 32;
-#pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    double v = part[q];
-    for (int o = wl >> 1; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o, wl);
-    part[q] = v;
-  }
-  if (gs > 32) {
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0)
-      for (int q = 0; q < 6; ++q) s_red[q][wid] = part[q];
     __syncthreads();
-    if (gl == 0) {
-      const int w0 = threadIdx.x >> 5, nw = gs >> 5;
-      for (int q = 0; q < 6; ++q) {
-        double v = 0.0;
-        for (int w = 0; w < nw; ++w) v += s_red[q][w0 + w];
-        part[q] = v;
+    double part[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int k0 = 0; k0 < Nnu; k0 += BLOCK * KU) {
+      double n0[KU], n1[KU], n2[KU], A[KU];
+#pragma unroll
+      for (int u = 0; u < KU; ++u) {
+        const int k = k0 + u * BLOCK + threadIdx.x;
+        const bool has = k < Nnu;
+        const double *row = spec + (size_t)(has ? k : 0) * kSpecStride;
+        n0[u] = has ? -row[0] : 0.0;  // -ra_X: the loop forms -tau
+        n1[u] = has ? -row[1] : 0.0;
+        n2[u] = has ? -row[2] : 0.0;
+        A[u] = 0.0;
+      }
+#pragma unroll 1
+      for (int i = 0; i < ndir_pad; i += RU) {
+        double4 ry[RU];
+#pragma unroll
+        for (int r = 0; r < RU; ++r) ry[r] = s_ray[i + r];
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+#pragma unroll
+          for (int u = 0; u < KU; ++u) {
+            const double x = fma(ry[r].z, n2[u], fma(ry[r].y, n1[u], ry[r].x * n0[u]));  // -tau
+            const double a = ATT_E2 ? e2xa(-x) : exp_nonpos(x, s_exp_lane);
+            A[u] = fma(ry[r].w, a, A[u]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < KU; ++u) {
+        const int k = k0 + u * BLOCK + threadIdx.x;
+        if (k < Nnu) {
+          const double *row = spec + (size_t)k * kSpecStride;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) part[q] = fma(row[3 + q], A[u], part[q]);
+        }
       }
     }
-  }
-  if (valid && gl == 0) {
-    double scale = 1.0;
-    if (P.geom == RB_GEOM_SPHERE_STROMGREN) {
-      // point source dilution 1/(4 pi r_c^2): source_point.f90:348
-      const double *E = P.Edges + (size_t)b * (Nl + 1);
-      const double r_c = (E[il] + E[il + 1]) * 0.5;
-      scale = 1.0 / (4.0 * RB_PI * r_c * r_c);
-    }
+    // reduce over the CTA: shuffles inside a warp, shared memory across warps
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
-      double v = part[q] * scale;
-      if (P.geom == RB_GEOM_SPHERE_BGND) v = (P.src[q][c] + v) * 0.5;
-      P.src[q][c] = v;
+      double v = part[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      part[q] = v;
+    }
+    if (BLOCK > 32) {
+      if (lane == 0)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) s_red[q][wid] = part[q];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      double scale = 1.0;
+      if (P.geom == RB_GEOM_SPHERE_STROMGREN) {
+        // point source dilution 1/(4 pi r_c^2): source_point.f90:348
+        const double *E = P.Edges + (size_t)b * (Nl + 1);
+        const double r_c = (E[il] + E[il + 1]) * 0.5;
+        scale = 1.0 / (4.0 * RB_PI * r_c * r_c);
+      }
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        double v = part[q];
+        if (BLOCK > 32) {
+          v = 0.0;
+          for (int w = 0; w < BLOCK / 32; ++w) v += s_red[q][w];
+        }
+        v *= scale;
+        if (P.geom == RB_GEOM_SPHERE_BGND) v = (P.src[q][c] + v) * 0.5;
+        P.src[q][c] = v;
+      }
     }
   }
 }
