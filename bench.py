@@ -265,7 +265,8 @@ def main():
     if world == 1:
         plan.thin()
         plan.bench_steps(W, flush_bytes)
-        launches0 = plan.last_info()["n_launches"]
+        info0 = plan.last_info()
+        launches0 = info0["n_launches"]
         barrier()
         if sampler:
             sampler.start()
@@ -280,7 +281,8 @@ def main():
             plan.thin()
             for _ in range(W):
                 plan.sharded_sweep(rank, world, send, recv)
-            launches0 = plan.last_info()["n_launches"]
+            info0 = plan.last_info()
+            launches0 = info0["n_launches"]
             barrier()
             if sampler:
                 sampler.start()
@@ -371,9 +373,10 @@ def main():
         _lib.check(_lib.lib().rb_microbench(kind, local_rank, C.byref(v)))
         peak[name] = v.value
     n_seg = segments_per_sweep(cfg, args.Nmu)
-    ms_cols = (plan_all["ms_columns"]) / (W + K)
-    ms_nu = (plan_all["ms_nu"]) / (W + K)
-    ms_cell = (plan_all["ms_cell"]) / (W + K)
+    # stage times of the K timed sweeps only (warm-up sweeps subtracted)
+    ms_cols = (plan_all["ms_columns"] - info0["ms_columns"]) / K
+    ms_nu = (plan_all["ms_nu"] - info0["ms_nu"]) / K
+    ms_cell = (plan_all["ms_cell"] - info0["ms_cell"]) / K
     if world > 1:
         n_seg_local, ev_local = n_seg / world, evals_sweep / world
     else:

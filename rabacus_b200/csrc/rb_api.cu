@@ -202,6 +202,7 @@ struct rb_plan {
   double *dspec = nullptr, *dthin = nullptr, *dmu = nullptr, *dzHz = nullptr;
   double4 *dcol = nullptr;
   unsigned *ditems = nullptr;   // column-kernel work list (LPT order), see build_items
+  int *dwork = nullptr;         // [B] next-item counters of the column kernel
   int n_items = 0, items_start = -1, items_stride = -1, n_sm = 148;
   std::vector<double> items_edges;  // problem-0 edges the list was built from
   int *dflags = nullptr;    // active, notconv, iters, err : 4*B, then nactive
@@ -228,7 +229,7 @@ extern "C" void rb_plan_destroy(rb_plan *p) {
   cudaFree(p->dEdges); cudaFree(p->dnH); cudaFree(p->dnHe); cudaFree(p->dT);
   cudaFree(p->dx); cudaFree(p->dsrc); cudaFree(p->dconv); cudaFree(p->dpack);
   cudaFree(p->dspec); cudaFree(p->dthin); cudaFree(p->dmu); cudaFree(p->dcol);
-  cudaFree(p->dzHz); cudaFree(p->dflags); cudaFree(p->dresid); cudaFree(p->ditems);
+  cudaFree(p->dzHz); cudaFree(p->dflags); cudaFree(p->dresid); cudaFree(p->ditems); cudaFree(p->dwork);
   cudaFreeHost(p->hEdges); cudaFreeHost(p->hnH); cudaFreeHost(p->hnHe); cudaFreeHost(p->hT);
   cudaFreeHost(p->hspec); cudaFreeHost(p->hthin); cudaFreeHost(p->hzHz);
   cudaFreeHost(p->hout); cudaFreeHost(p->hflags);
@@ -286,6 +287,7 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   ALLOC(p->dspec, B * Nnu * kSpecStride * 8); ALLOC(p->dthin, B * 6 * 8);
   ALLOC(p->dmu, 2 * (size_t)std::max(1, d.Nmu) * 8);
   ALLOC(p->dcol, NC * (size_t)p->Ndir * sizeof(double4)); ALLOC(p->dzHz, B * 2 * 8);
+  ALLOC(p->dwork, B * sizeof(int));
   if (d.geometry == RB_GEOM_SPHERE_BGND)
     ALLOC(p->ditems, (size_t)((Nl + 31) / 32) * ((d.Nmu + 1) / 2) * sizeof(unsigned));
   {
@@ -399,14 +401,26 @@ extern "C" int rb_plan_upload(rb_plan *p) {
 extern "C" int rb_plan_thin(rb_plan *p) {
   if (!p) return RB_ERR_BAD_ARG;
   const int Nl = p->d.Nl, B = p->d.n_problems;
-  int cpt = 1;
-  while (cpt * 512 < Nl) cpt *= 4;
-  int threads = (Nl + cpt - 1) / cpt;
+  // one cell per thread over a cluster of up to 8 CTAs of 512 threads; two cells per
+  // thread beyond 4096 cells
+  int cs = 1;
+  while (cs < kMaxCluster && cs * 512 < Nl) cs *= 2;
+  const int cpt = (Nl + cs * 512 - 1) / (cs * 512);
+  int threads = (Nl + cs * cpt - 1) / (cs * cpt);
   threads = ((threads + 31) / 32) * 32;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(B * cs);
+  cfg.blockDim = dim3(threads);
+  cfg.stream = p->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
   switch (cpt) {
-    case 1: k_thin_state<1><<<B, threads, 0, p->stream>>>(p->P); break;
-    case 4: k_thin_state<4><<<B, threads, 0, p->stream>>>(p->P); break;
-    case 16: k_thin_state<16><<<B, threads, 0, p->stream>>>(p->P); break;
+    case 1: CK(cudaLaunchKernelEx(&cfg, k_thin_state<1>, p->P, cs)); break;
+    case 2: CK(cudaLaunchKernelEx(&cfg, k_thin_state<2>, p->P, cs)); break;
     default: return RB_ERR_UNSUPPORTED;
   }
   p->info.n_launches += 1;
@@ -483,15 +497,17 @@ static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, in
   int cps = (int)std::min<size_t>(3, kMaxSmem / (smem + 1024));
   const int warps = 24 / cps;
   const int want = p->n_sm * cps;  // CTAs that fill the GPU once
-  int per_problem = std::max(1, (want + B - 1) / B);
+  const int waves = (B > 1) ? 4 : 1;  // batches: ~4 CTAs per resident slot (finer tail)
+  int per_problem = std::max(1, (waves * want + B - 1) / B);
   per_problem = std::min(per_problem, (p->n_items + warps - 1) / warps);
   dim3 g(per_problem, B);
+  CK(cudaMemsetAsync(p->dwork, 0, B * sizeof(int), s));
 #define COLS(THREADS, MINB)                                                                  \
   do {                                                                                       \
     rc = set_smem(k_sphere_columns_smem<THREADS, 1, MINB>, smem);                            \
     if (rc) return rc;                                                                       \
     k_sphere_columns_smem<THREADS, 1, MINB><<<g, THREADS, smem, s>>>(                        \
-        p->P, cell_start, cell_stride, n_local, p->ditems, p->n_items);                      \
+        p->P, cell_start, cell_stride, n_local, p->ditems, p->n_items, p->dwork);            \
   } while (0)
   if (cps == 1) COLS(768, 1);
   else if (cps == 2) COLS(384, 2);
@@ -527,7 +543,9 @@ static int launch_nu_rates(rb_plan *p, int cell_start, int cell_stride, int n_lo
     else if (Nnu <= 64) NU(1, 1, 1, 64, 4);
     else NU(1, 1, 1, 128, 3);
   } else {
-    if (Nnu <= 128) NU(0, 4, 2, 32, 12);
+    // timed on B200 (profiles/r01_kernel_variants.md): 4 frequencies x 2 rays in flight
+    // for wide grids; one warp per cell, 4 frequencies x 1 ray, 16 warps/SM for Nnu <= 128
+    if (Nnu <= 128) NU(0, 4, 1, 32, 16);
     else if (Nnu <= 256) NU(0, 4, 2, 64, 6);
     else NU(0, 4, 2, 128, 4);
   }
@@ -558,8 +576,32 @@ extern "C" int rb_plan_sweep_local(rb_plan *p, int cell_start, int cell_stride) 
     rc = launch_nu_rates(p, cell_start, cell_stride, n_local);
     if (rc) return rc;
     cudaEventRecord(sev[2], s);
-    dim3 gs3((n_local + 127) / 128, B);
-    k_cell_solve<<<gs3, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local);
+    // find_Teq: G lanes per cell bisect T speculatively (k_cell_solve_spec); G is the
+    // largest group that keeps the launch within ~one wave of resident threads, and
+    // batches with more cells than that run one thread per cell.
+    int G = 1;
+    if (p->d.i_find_Teq) {
+      const char *fenv = getenv("RB_SPEC_G");  // testing knob: force the group size
+      const int forced = fenv ? atoi(fenv) : 0;
+      const long long cells_now = (long long)n_local * B;
+      const long long budget = (long long)p->n_sm * 512;
+      G = 32;
+      while (G > 1 && cells_now * G > budget) G >>= 1;
+      if (G < 4) G = 1;
+      if (forced == 1 || forced == 4 || forced == 8 || forced == 16 || forced == 32) G = forced;
+    }
+    if (G == 1) {
+      dim3 gs3((n_local + 127) / 128, B);
+      k_cell_solve<<<gs3, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local);
+    } else {
+      dim3 gs3(((long long)n_local * G + 127) / 128, B);
+      switch (G) {
+        case 32: k_cell_solve_spec<32><<<gs3, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local); break;
+        case 16: k_cell_solve_spec<16><<<gs3, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local); break;
+        case 8: k_cell_solve_spec<8><<<gs3, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local); break;
+        default: k_cell_solve_spec<4><<<gs3, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local);
+      }
+    }
     p->info.n_launches += 1;
   } else {
     cudaEventRecord(sev[2], s);

@@ -178,6 +178,38 @@ RB_HDN int get_dudT(double nH, double nHe, double T, const PhotoRates &p,
   return ION_OK;
 }
 
+// get_dudT that also hands back the fractions of its solve_pce: when the T
+// bisection stops at a temperature that has been probed, these ARE the final
+// fractions (solve_pcte's last statement re-solves at that same T).
+RB_HDN int probe_T(double nH, double nHe, double T, const PhotoRates &p, double z,
+                   double Hz, const CaseA &fc, double tol, double &dudT, rb_frac_t &x) {
+  const rb_kchem_t kc = get_kchem(T, fc.H2, fc.He2, fc.He3);
+  const rb_kcool_t kl = get_kcool(T, fc.H2, fc.He2, fc.He3);
+  const int rc = solve_pce(nH, nHe, kc, p.H1i, p.He1i, p.He2i, tol, x);
+  if (rc) return rc;
+  const double heat =
+      get_heat(nH, nHe, p.H1h, p.He1h, p.He2h, x.xH1, x.xHe1, x.xHe2);
+  const double cool = get_cool(nH, nHe, T, kl, x, z, Hz);
+  dudT = heat - cool;
+  return ION_OK;
+}
+
+// State of solve_pcte's bisection (:796-850) and its two branches.
+struct TBisect {
+  double Tl, Tr, T, err;
+};
+RB_HD void tbisect_step(TBisect &s, bool neg) {
+  const double Told = s.T;
+  if (neg) {
+    s.Tr = s.T;
+    s.T = (s.Tl + s.T) * 0.5;
+  } else {
+    s.Tl = s.T;
+    s.T = (s.T + s.Tr) * 0.5;
+  }
+  s.err = fabs(1.0 - s.T / Told);
+}
+
 RB_HDN int solve_pcte(double nH, double nHe, const PhotoRates &p, double z,
                      double Hz, const CaseA &fc, double tol, rb_frac_t &x,
                      double &Tout) {

@@ -21,6 +21,8 @@
 // None of this is a dense contraction: no tensor cores.  The governing
 // resource is the FP64 pipe (DFMA + software exp / sqrt / pow), see DESIGN.md.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "rb_ion.cuh"
 
 namespace rb {
@@ -298,7 +300,7 @@ k_sphere_columns(PlanDev P, int cell_start, int cell_stride, int n_local) {
 template <int THREADS, int U, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_sphere_columns_smem(PlanDev P, int cell_start, int cell_stride, int n_local,
-                      const unsigned *__restrict__ items, int n_items) {
+                      const unsigned *__restrict__ items, int n_items, int *work) {
   const int b = blockIdx.y;
   if (!P.active[b]) return;
   extern __shared__ double4 s_pk[];
@@ -306,8 +308,13 @@ k_sphere_columns_smem(PlanDev P, int cell_start, int cell_stride, int n_local,
   for (int k = threadIdx.x; k < nrec; k += THREADS) s_pk[k] = shell_record(P, b, k);
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int nwarp = THREADS / 32;
-  for (int it = blockIdx.x * nwarp + (threadIdx.x >> 5); it < n_items; it += gridDim.x * nwarp) {
+  // items are handed out by a per-problem counter (zeroed before the launch):
+  // longest rays first, whichever warp is free takes the next one
+  int it = 0, nxt = 0;
+  if (lane == 0) it = atomicAdd(&work[b], 1);
+  it = __shfl_sync(0xffffffffu, it, 0);
+  while (it < n_items) {
+    if (lane == 0) nxt = atomicAdd(&work[b], 1);  // in flight while this item is traced
     const unsigned item = items[it];
     const int jw = (int)(item & 0xffffu) * 32;
     const int ip = (int)(item >> 16);
@@ -315,6 +322,7 @@ k_sphere_columns_smem(PlanDev P, int cell_start, int cell_stride, int n_local,
     const bool valid = j < n_local;
     const int il = cell_start + (valid ? j : n_local - 1) * cell_stride;
     sphere_ray_pair<U>(P, b, il, cell_start + jw * cell_stride, cell_stride, ip, s_pk, valid);
+    it = __shfl_sync(0xffffffffu, nxt, 0);
   }
 }
 
@@ -633,6 +641,117 @@ k_cell_solve(PlanDev P, int cell_start, int cell_stride, int n_local) {
 }
 
 // ---------------------------------------------------------------------------
+// k_cell_solve_spec: solve_pcte_s (ion_solver.f90:729-880) with a group of G
+// lanes per cell.  The reference bisects T serially: ~22 probes of
+// get_dudT (each = 16 rate fits + a solve_pce), i.e. a dependent chain of
+// ~3e5 instructions per cell -- pure latency when a sweep has only Nl cells.
+// Here the lanes of a group evaluate, in one pass, every temperature the
+// bisection can reach in its next L = log2(G) steps (the G-1 nodes of a binary
+// tree, each lane replaying the reference's mid-point arithmetic along its own
+// path), then the group walks the tree with the signs it has found.  Brackets,
+// mid-points, stopping rule and the final fractions are those of the serial
+// algorithm bit for bit; the bisection is ~L times shorter in wall time.
+// Round 0 also carries the two bracket probes (lanes 0, 1).
+// ---------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(128)
+k_cell_solve_spec(PlanDev P, int cell_start, int cell_stride, int n_local) {
+  const int b = blockIdx.y;
+  if (!P.active[b]) return;
+  constexpr int L = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : 2;
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  const int j = t / G, sub = t % G;
+  const bool valid = j < n_local;
+  const int il = cell_start + (valid ? j : n_local - 1) * cell_stride;
+  const int lane = threadIdx.x & 31, gbase = lane & ~(G - 1);
+  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+  const size_t c = (size_t)b * P.Nl + il;
+  PhotoRates p;
+  p.H1i = P.src[0][c]; p.He1i = P.src[1][c]; p.He2i = P.src[2][c];
+  p.H1h = P.src[3][c]; p.He1h = P.src[4][c]; p.He2h = P.src[5][c];
+  const double nH = P.nH[c], nHe = P.nHe[c];
+  const double z = P.zHz[2 * b], Hz = P.zHz[2 * b + 1];
+  const CaseA fc = {P.fcA, P.fcA, P.fcA};
+  const double tol = P.tol_inner;
+
+  TBisect root;
+  root.Tl = RB_TFLOOR; root.Tr = RB_TMAX;
+  root.T = (log10(root.Tl) + log10(root.Tr)) * 0.5;   // :814-815
+  root.T = pow(10.0, root.T);
+  root.err = 1.7976931348623157e308;
+  int rc = 0, iter = 0, src = 0;   // src: lane of the group holding the answer
+  bool done = false;
+  rb_frac_t x;
+  double dudT = 0.0, Tfinal = root.Tl;
+  int first = 1;
+  while (!done) {
+    // ---- my temperature for this round
+    int node;          // heap index in this round's tree (root = 1), 0 = bracket probe
+    const int nlev = first ? L - 1 : L;
+    if (first) node = (sub >= 2 && sub - 1 < (1 << (L - 1))) ? sub - 1 : (sub < 2 ? 0 : 1);
+    else node = sub == 0 ? 1 : sub;
+    TBisect mine = root;
+    if (node > 0) {
+      const int depth = 31 - __clz(node);
+      for (int i = depth - 1; i >= 0; --i) tbisect_step(mine, ((node >> i) & 1) == 0);
+    }
+    const double myT = (first && sub == 0) ? root.Tl : (first && sub == 1) ? root.Tr : mine.T;
+    int prc = probe_T(nH, nHe, myT, p, z, Hz, fc, tol, dudT, x);
+    // ---- brackets (round 0): :771-812
+    if (first) {
+      const double dmin = __shfl_sync(mask, dudT, gbase + 0);
+      const int rmin = __shfl_sync(mask, prc, gbase + 0);
+      const double dmax = __shfl_sync(mask, dudT, gbase + 1);
+      const int rmax = __shfl_sync(mask, prc, gbase + 1);
+      if (rmin) { rc = rmin; done = true; }
+      else if (dmin < 0.0) { done = true; src = 0; Tfinal = root.Tl; }   // :782-794 floor
+      else if (rmax) { rc = rmax; done = true; }
+      else if (dmax > 0.0) { rc = ION_ERR_T_NOT_BRACKETED; done = true; }
+    }
+    // ---- walk the tree with the signs found (uniform over the group)
+    const int lane0 = first ? 1 : 0;   // node n was probed by lane n + lane0 (node 1 also by lane 0)
+    int n = 1;
+    for (int lev = 0; lev < nlev && !done; ++lev) {
+      if (!(root.err > tol)) {   // loop test of :820: T = root.T has been probed by node n
+        done = true; src = n + lane0; Tfinal = root.T;
+        break;
+      }
+      const double d = __shfl_sync(mask, dudT, gbase + n + lane0);
+      const int r = __shfl_sync(mask, prc, gbase + n + lane0);
+      if (r) { rc = r; done = true; break; }
+      const bool neg = d < 0.0;
+      tbisect_step(root, neg);
+      n = 2 * n + (neg ? 0 : 1);
+      iter = iter + 1;
+      if (iter > RB_ION_MAX_ITER) { rc = ION_ERR_MAX_ITER_PCTE; done = true; }
+    }
+    first = 0;
+  }
+  if (rc) {
+    if (valid && sub == 0) atomicMax(&P.err[b], rc);
+    return;
+  }
+  rb_frac_t xo;
+  xo.xH1 = __shfl_sync(mask, x.xH1, gbase + src);
+  xo.xH2 = __shfl_sync(mask, x.xH2, gbase + src);
+  xo.xHe1 = __shfl_sync(mask, x.xHe1, gbase + src);
+  xo.xHe2 = __shfl_sync(mask, x.xHe2, gbase + src);
+  xo.xHe3 = __shfl_sync(mask, x.xHe3, gbase + src);
+  if (!valid || sub != 0) return;
+  P.x[0][c] = xo.xH1; P.x[1][c] = xo.xH2; P.x[2][c] = xo.xHe1;
+  P.x[3][c] = xo.xHe2; P.x[4][c] = xo.xHe3;
+  P.T[c] = Tfinal;
+  if (two_sided(P.geom)) {
+    const size_t cm = (size_t)b * P.Nl + (P.Nl - 1 - il);
+    P.x[0][cm] = xo.xH1; P.x[1][cm] = xo.xH2; P.x[2][cm] = xo.xHe1;
+    P.x[3][cm] = xo.xHe2; P.x[4][cm] = xo.xHe3;
+    P.T[cm] = Tfinal;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) P.src[q][cm] = P.src[q][c];
+  }
+}
+
+// ---------------------------------------------------------------------------
 // k_converge_finish: one block per problem.  n_e = xH2 nH + (xHe2 + 2 xHe3) nHe
 // over ALL cells; converged when all(|ne/ne_old - 1| < tol)
 // (sphere_bgnd.f90:289-296); then the iteration bookkeeping of the drivers
@@ -717,21 +836,46 @@ __global__ void k_unpack_cells(PlanDev P, int world, int n_local, const double *
 // ---------------------------------------------------------------------------
 // lock-step ("_v") solvers, one block per problem, CPT cells per thread.
 // ---------------------------------------------------------------------------
-// block-wide any(): the lock-step loops' `any(err > tol)` (ion_solver.f90:620,988).
-// On the host (unit-testing the loop logic) a "block" is one thread.
-__host__ __device__ __forceinline__ int block_any(int v) {
+// any() of the lock-step loops (`any(err > tol)`, ion_solver.f90:620,988) over all
+// the threads that share one problem.  BlockAny: one CTA (on the host, where the
+// loop logic is unit-tested, a "block" is one thread).  ClusterAny: the CTAs of a
+// thread-block cluster exchange their block results through distributed shared
+// memory -- every CTA writes its flag into every peer's `flags` and the cluster
+// barrier orders the writes; the two flag rows alternate so that a CTA that is
+// already in the next call cannot overwrite a row a slower peer still reads.
+struct BlockAny {
+  __host__ __device__ __forceinline__ int operator()(int v) {
 #ifdef __CUDA_ARCH__
-  return __syncthreads_or(v);
+    return __syncthreads_or(v);
 #else
-  return v;
+    return v;
 #endif
-}
+  }
+};
 
-template <int CPT>
+constexpr int kMaxCluster = 8;
+struct ClusterAny {
+  int *flags;  // shared memory, [2][kMaxCluster]
+  int size, rank, par;
+  __device__ __forceinline__ int operator()(int v) {
+    int any = __syncthreads_or(v);
+    if (size == 1) return any;
+    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+    if ((int)threadIdx.x < size)
+      *cl.map_shared_rank(flags + par * kMaxCluster + rank, threadIdx.x) = any;
+    cl.sync();
+    any = 0;
+    for (int q = 0; q < size; ++q) any |= flags[par * kMaxCluster + q];
+    par ^= 1;
+    return any;
+  }
+};
+
+template <int CPT, class ANY>
 __host__ __device__ int pce_lockstep(const double (&nH)[CPT], const double (&nHe)[CPT],
                             const rb_kchem_t (&k)[CPT], const PhotoRates (&p)[CPT],
                             const rb_flag_t (&valid)[CPT], double tol,
-                            rb_frac_t (&x)[CPT]) {
+                            rb_frac_t (&x)[CPT], ANY &block_any) {
   PceState s[CPT];
   rb_flag_t ok[CPT];
   int rc = 0;
@@ -762,17 +906,17 @@ RB_LS_UNROLL
   return rc;
 }
 
-template <int CPT>
+template <int CPT, class ANY>
 __host__ __device__ int dudT_lockstep(const double (&nH)[CPT], const double (&nHe)[CPT],
                              const double (&T)[CPT], const PhotoRates (&p)[CPT],
                              const rb_flag_t (&valid)[CPT], double z, double Hz,
-                             const CaseA &fc, double tol, double (&dudT)[CPT]) {
+                             const CaseA &fc, double tol, double (&dudT)[CPT], ANY &block_any) {
   rb_kchem_t kc[CPT];
   rb_frac_t x[CPT];
 RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i)
     if (valid[i]) kc[i] = get_kchem(T[i], fc.H2, fc.He2, fc.He3);
-  const int rc = pce_lockstep<CPT>(nH, nHe, kc, p, valid, tol, x);
+  const int rc = pce_lockstep<CPT>(nH, nHe, kc, p, valid, tol, x, block_any);
 RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) {
     if (valid[i]) {
@@ -789,21 +933,21 @@ RB_LS_UNROLL
 }
 
 // ion_solver.f90:884-1056 (solve_pcte_v)
-template <int CPT>
+template <int CPT, class ANY>
 __host__ __device__ int pcte_lockstep(const double (&nH)[CPT], const double (&nHe)[CPT],
                              const PhotoRates (&p)[CPT], const rb_flag_t (&valid)[CPT],
                              double z, double Hz, const CaseA &fc, double tol,
-                             rb_frac_t (&x)[CPT], double (&T)[CPT]) {
+                             rb_frac_t (&x)[CPT], double (&T)[CPT], ANY &block_any) {
   double Tleft[CPT], Tright[CPT], dudT[CPT], err[CPT];
   rb_flag_t floor_[CPT];
   int rc = 0, r;
 RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) { Tleft[i] = RB_TFLOOR; Tright[i] = RB_TMAX; }
-  r = dudT_lockstep<CPT>(nH, nHe, Tleft, p, valid, z, Hz, fc, tol, dudT);
+  r = dudT_lockstep<CPT>(nH, nHe, Tleft, p, valid, z, Hz, fc, tol, dudT, block_any);
   if (r) rc = r;
 RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) floor_[i] = valid[i] && (dudT[i] < 0.0);
-  r = dudT_lockstep<CPT>(nH, nHe, Tright, p, valid, z, Hz, fc, tol, dudT);
+  r = dudT_lockstep<CPT>(nH, nHe, Tright, p, valid, z, Hz, fc, tol, dudT, block_any);
   if (r) rc = r;
 RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) {
@@ -823,7 +967,7 @@ RB_LS_UNROLL
     for (int i = 0; i < CPT; ++i)
       if (valid[i] && err[i] > tol) any = 1;
     if (!block_any(any)) break;  // ion_solver.f90:988
-    r = dudT_lockstep<CPT>(nH, nHe, T, p, valid, z, Hz, fc, tol, dudT);
+    r = dudT_lockstep<CPT>(nH, nHe, T, p, valid, z, Hz, fc, tol, dudT, block_any);
     if (r) rc = r;
 RB_LS_UNROLL
     for (int i = 0; i < CPT; ++i) {
@@ -844,17 +988,24 @@ RB_LS_UNROLL
 RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i)
     if (valid[i]) kc[i] = get_kchem(T[i], fc.H2, fc.He2, fc.He3);
-  r = pce_lockstep<CPT>(nH, nHe, kc, p, valid, tol, x);
+  r = pce_lockstep<CPT>(nH, nHe, kc, p, valid, tol, x, block_any);
   if (r) rc = r;
   return rc;
 }
 
 // k_thin_state: optically thin rates, lock-step solve, n_e reference for the
-// convergence test (sphere_bgnd.f90:260-262)
+// convergence test (sphere_bgnd.f90:260-262).  One thread-block cluster of
+// `csize` CTAs per problem (grid = B * csize); the `_v` solvers' any() spans the
+// cluster (ClusterAny), so that up to 8 x 512 cells iterate in lock step with
+// one cell per thread.
 template <int CPT>
-__global__ void __launch_bounds__(512) k_thin_state(PlanDev P) {
-  const int b = blockIdx.x;
+__global__ void __launch_bounds__(512) k_thin_state(PlanDev P, int csize) {
+  const int b = blockIdx.x / csize, crank = blockIdx.x % csize;
   const int Nl = P.Nl;
+  __shared__ int s_flags[2 * kMaxCluster];
+  ClusterAny any_fn = {s_flags, csize, crank, 0};
+  const int tid = crank * blockDim.x + threadIdx.x;   // thread index within the problem
+  const int tstride = csize * blockDim.x;
   double nH[CPT], nHe[CPT], T[CPT];
   PhotoRates p[CPT];
   rb_flag_t valid[CPT];
@@ -862,7 +1013,7 @@ __global__ void __launch_bounds__(512) k_thin_state(PlanDev P) {
   const double *E = P.Edges + (size_t)b * (Nl + 1);
 RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) {
-    const int il = threadIdx.x + i * blockDim.x;
+    const int il = tid + i * tstride;
     valid[i] = il < Nl;
     const size_t c = (size_t)b * Nl + (valid[i] ? il : 0);
     nH[i] = P.nH[c]; nHe[i] = P.nHe[c]; T[i] = P.T[c];
@@ -880,19 +1031,19 @@ RB_LS_UNROLL
   const CaseA fc = {P.fcA, P.fcA, P.fcA};
   if (P.find_Teq) {
     rc = pcte_lockstep<CPT>(nH, nHe, p, valid, P.zHz[2 * b], P.zHz[2 * b + 1], fc,
-                            P.tol_inner, x, T);
+                            P.tol_inner, x, T, any_fn);
   } else {
     rb_kchem_t k[CPT];
 RB_LS_UNROLL
     for (int i = 0; i < CPT; ++i)
       if (valid[i]) k[i] = get_kchem(T[i], fc.H2, fc.He2, fc.He3);
-    rc = pce_lockstep<CPT>(nH, nHe, k, p, valid, P.tol_inner, x);
+    rc = pce_lockstep<CPT>(nH, nHe, k, p, valid, P.tol_inner, x, any_fn);
   }
   if (rc) atomicMax(&P.err[b], rc);
 RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) {
     if (!valid[i]) continue;
-    const int il = threadIdx.x + i * blockDim.x;
+    const int il = tid + i * tstride;
     const size_t c = (size_t)b * Nl + il;
     P.x[0][c] = x[i].xH1; P.x[1][c] = x[i].xH2; P.x[2][c] = x[i].xHe1;
     P.x[3][c] = x[i].xHe2; P.x[4][c] = x[i].xHe3;
@@ -1044,8 +1195,9 @@ RB_LS_UNROLL
     }
   }
   int rc;
-  if (pcte) rc = pcte_lockstep<CPT>(nH, nHe, p, valid, z, Hz, fc, tol, x, T);
-  else rc = pce_lockstep<CPT>(nH, nHe, k, p, valid, tol, x);
+  BlockAny any_fn;
+  if (pcte) rc = pcte_lockstep<CPT>(nH, nHe, p, valid, z, Hz, fc, tol, x, T, any_fn);
+  else rc = pce_lockstep<CPT>(nH, nHe, k, p, valid, tol, x, any_fn);
   if (rc) atomicMax(err, rc);
 RB_LS_UNROLL
   for (int q = 0; q < CPT; ++q) {

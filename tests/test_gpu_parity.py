@@ -16,7 +16,7 @@ Protocol:
 import numpy as np
 import pytest
 
-from helpers import CHECKED, compare, run_gpu, run_oracle
+from helpers import CHECKED, compare, frac_rtol, run_gpu, run_oracle
 from rabacus_b200 import configs
 
 pytestmark = pytest.mark.gpu
@@ -85,6 +85,61 @@ def test_solve_pcte_matches_oracle(orc, lockstep):
     ref = orc.solve_pcte(nH, nHe, *ion, *heat, 3.0, 0.0, 1.0, 1.0, 1.0, 1e-7, vector=lockstep)
     for g, r in zip(got, ref):
         assert np.max(np.abs(g / r - 1)) < RTOL
+
+
+@pytest.mark.parametrize("n", [513, 600, 2100, 8192])
+def test_lockstep_solvers_many_zones_per_thread(orc, n):
+    """The `_v` twins with more zones than one block has threads (4 and 16 zones
+    per thread): every zone must walk the oracle's lock-step path."""
+    from rabacus_b200 import rabacus_fc as fc
+    nH = np.logspace(-4.0, -1.0, n)
+    nHe = nH * 0.08
+    ion, heat = (8e-13, 5e-13, 6e-15), (5e-24, 6e-24, 2e-25)
+    k = orc.get_kchem(np.full(n, 1.0e4), 1.0, 1.0, 1.0)
+    got = fc.solve_pce_v(nH, nHe, *k, *ion, 1e-8, n)
+    ref = orc.solve_pce(nH, nHe, *k, *ion, 1e-8, vector=True)
+    for g, r in zip(got, ref):
+        assert np.max(np.abs(g / r - 1)) < RTOL
+    got = fc.solve_pcte_v(nH, nHe, *ion, *heat, 3.0, 0.0, 1.0, 1.0, 1.0, 1, 1e-7, n)
+    ref = orc.solve_pcte(nH, nHe, *ion, *heat, 3.0, 0.0, 1.0, 1.0, 1.0, 1e-7, vector=True)
+    assert np.array_equal(got[5], ref[5])          # T: same bisection path
+    for g, r in zip(got[:5], ref[:5]):
+        assert np.max(np.abs(g / r - 1)) < frac_rtol(1e-7 / 1e-2)
+
+
+@pytest.mark.parametrize("G", [1, 4, 8, 16, 32])
+def test_speculative_T_bisection_equals_serial(orc, spec128, G, monkeypatch):
+    """k_cell_solve_spec (G lanes per cell probing the next log2 G bisection levels
+    at once) must return the serial solve_pcte_s result: T bit-identical to the
+    oracle for every group size, fractions within the solver tolerance policy."""
+    monkeypatch.setenv("RB_SPEC_G", str(G))
+    cfg = _small_sphere(96, 128, 8, True, spec=spec128)
+    for kw in (dict(max_sweeps=1), dict(max_sweeps=4)):
+        g = run_gpu(cfg, **kw)
+        o = run_oracle(orc, cfg, **kw)
+        assert np.array_equal(g["T"], o["T"])
+        worst, bad = compare(g, o)
+        assert not bad, (G, kw, bad)
+    cfg = configs.c2_slab_plane(64, 128, True, True)   # floor cells + mirrored halves
+    g = run_gpu(cfg)
+    o = run_oracle(orc, cfg)
+    assert g["iters"] == o["iters"]
+    assert np.array_equal(g["T"], o["T"])
+    worst, bad = compare(g, o)
+    assert not bad, (G, bad)
+
+
+@pytest.mark.parametrize("Nl", [700, 2100, 4500])
+@pytest.mark.parametrize("find_Teq", [False, True])
+def test_thin_state_across_a_cluster(orc, spec128, Nl, find_Teq):
+    """Optically thin start with the lock-step solvers spread over a thread-block
+    cluster (2, 8 CTAs; 2 cells per thread at 4500): any() must span all cells."""
+    cfg = _small_sphere(Nl, 128, 4, find_Teq, spec=spec128)
+    g = run_gpu(cfg, thin=True)
+    o = run_oracle(orc, cfg, thin=True)
+    assert np.array_equal(g["T"], o["T"])
+    worst, bad = compare(g, o)
+    assert not bad, bad
 
 
 def test_solver_bit_identical_given_same_coefficients(orc):
