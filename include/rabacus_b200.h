@@ -42,6 +42,7 @@ extern "C" {
 #define RB_ERR_UNSUPPORTED 9 /* rec_meth != fixed: SURVEY 8(f) "next" */
 #define RB_ERR_CUDA 10
 #define RB_ERR_NOMEM 11
+#define RB_ERR_PEER_TIMEOUT 12 /* cell-sharded sweep: a peer rank never reached the barrier */
 
 /* geometry / driver selector for plans */
 #define RB_GEOM_SPHERE_BGND 0      /* rabacus/f2py/sphere_bgnd.f90 */
@@ -236,6 +237,28 @@ int rb_plan_poll_sweep(rb_plan *plan, int *n_active);
  * Device pointers; enqueued on the plan's stream. */
 int rb_plan_pack_cells(rb_plan *plan, int cell_start, int cell_stride, double *dev_send);
 int rb_plan_unpack_cells(rb_plan *plan, int world, const double *dev_recv);
+/* Cell sharding over peer memory (NVLink/NVSwitch), one process per GPU, no
+ * collective library on the per-sweep path.  Rank `rank` of `world` (<= 8) sweeps
+ * the cells il = rank + j*world of a single-problem plan.
+ *   rb_plan_peer_alloc   allocates this rank's staging + flag buffer and returns
+ *                        its 64-byte CUDA IPC handle;
+ *   rb_plan_peer_connect takes all ranks' handles ([world][64], exchanged by the
+ *                        caller, e.g. torch.distributed.all_gather) and maps them;
+ *   rb_plan_sweep_sharded enqueues one sweep: columns -> frequency integrals ->
+ *                        cell solve, whose epilogue stores the new fractions into
+ *                        every rank's staging buffer -> k_exchange_finish (flag
+ *                        barrier across the GPUs, scatter, convergence test on
+ *                        the full arrays).  Poll with rb_plan_poll_sweep.
+ *   rb_plan_solve_sharded thin start + pipelined sweeps to convergence; every
+ *                        rank takes the same decisions (Jacobi: the iterates and
+ *                        the sweep count equal those of one GPU).  T and the six
+ *                        rates of the other ranks' cells are NOT exchanged per
+ *                        sweep: gather them once afterwards
+ *                        (rb_plan_pack_cells / all-gather / rb_plan_unpack_cells). */
+int rb_plan_peer_alloc(rb_plan *plan, int rank, int world, unsigned char handle[64]);
+int rb_plan_peer_connect(rb_plan *plan, const unsigned char *handles);
+int rb_plan_sweep_sharded(rb_plan *plan);
+int rb_plan_solve_sharded(rb_plan *plan, rb_info *info);
 /* thin state + sweeps to convergence on one GPU */
 int rb_plan_solve(rb_plan *plan, rb_info *info);
 /* D2H of one problem's results (un-reversed to the input order) */
@@ -254,7 +277,7 @@ long long rb_plan_evals_per_sweep(const rb_plan *plan);
 int rb_plan_last_info(const rb_plan *plan, rb_info *info);
 
 /* bench helper: run `steps` Jacobi sweeps (rb_plan_sweep_local over all cells +
- * rb_plan_finish_sweep) and return their summed device time in ms, measured
+ * rb_plan_finish_sweep; rb_plan_sweep_sharded on a peer-connected plan) and return their summed device time in ms, measured
  * with CUDA events on the plan's stream.  If flush_bytes > 0 a scratch buffer of
  * that size is overwritten between steps (L2 flush), outside the timed spans. */
 int rb_plan_bench_steps(rb_plan *plan, int steps, size_t flush_bytes, double *ms_sum);

@@ -53,6 +53,7 @@ EXPORTS = (
     "rb_plan_get_problem", "rb_plan_field_ptr", "rb_plan_stream", "rb_plan_sync",
     "rb_plan_evals_per_sweep", "rb_plan_last_info", "rb_plan_bench_steps", "rb_plan_pack_cells",
     "rb_plan_unpack_cells", "rb_microbench",
+    "rb_plan_peer_alloc", "rb_plan_peer_connect", "rb_plan_sweep_sharded", "rb_plan_solve_sharded",
 )
 
 _lib = None

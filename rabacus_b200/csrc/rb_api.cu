@@ -40,6 +40,7 @@ extern "C" const char *rb_strerror(int code) {
     case RB_ERR_UNSUPPORTED: return "option not supported by the CUDA path (only rec_meth='fixed', verner, hg97)";
     case RB_ERR_CUDA: return g_cuda_msg[0] ? g_cuda_msg : "CUDA error / no CUDA device";
     case RB_ERR_NOMEM: return "out of memory";
+    case RB_ERR_PEER_TIMEOUT: return "cell-sharded sweep: a peer rank did not reach the barrier within 2 s";
   }
   return "unknown error";
 }
@@ -203,6 +204,12 @@ struct rb_plan {
   double4 *dcol = nullptr;
   unsigned *ditems = nullptr;   // column-kernel work list (LPT order), see build_items
   int *dwork = nullptr;         // [B] next-item counters of the column kernel
+  // cell sharding over peer memory
+  PeerDev Q;                    // world == 1 when not connected
+  void *dpeer = nullptr;        // this rank's flags (256 B) + staging
+  void *peer_base[kMaxPeers] = {nullptr};  // mapped bases (own = dpeer)
+  unsigned long long peer_epoch = 0;
+  int peer_world = 1;
   int n_items = 0, items_start = -1, items_stride = -1, n_sm = 148;
   std::vector<double> items_edges;  // problem-0 edges the list was built from
   int *dflags = nullptr;    // active, notconv, iters, err : 4*B, then nactive
@@ -317,6 +324,8 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
     cudaMemcpy(p->dmu + d.Nmu, p->wmu.data(), d.Nmu * 8, cudaMemcpyHostToDevice);
   }
   memset(&p->info, 0, sizeof(p->info));
+  memset(&p->Q, 0, sizeof(p->Q));
+  p->Q.world = 1;
   PlanDev &P = p->P;
   P.B = d.n_problems; P.Nl = d.Nl; P.Nnu = d.Nnu; P.Nmu = d.Nmu; P.Ndir = p->Ndir;
   P.geom = d.geometry; P.find_Teq = d.i_find_Teq; P.max_sweeps = d.max_sweeps;
@@ -554,8 +563,10 @@ static int launch_nu_rates(rb_plan *p, int cell_start, int cell_stride, int n_lo
   return rc;
 }
 
-extern "C" int rb_plan_sweep_local(rb_plan *p, int cell_start, int cell_stride) {
+static int sweep_impl(rb_plan *p, int cell_start, int cell_stride, bool scatter) {
   if (!p || cell_start < 0 || cell_stride < 1) return RB_ERR_BAD_ARG;
+  PeerDev Q = p->Q;
+  if (!scatter) Q.world = 1;
   const int Nl = p->d.Nl, B = p->d.n_problems, g = p->d.geometry;
   const bool two = (g == RB_GEOM_SLAB_PLANE_2 || g == RB_GEOM_SLAB_BGND);
   const int ncell = two ? Nl / 2 : Nl;  // slab_bgnd.f90:686 (Nl2 = Nl/2)
@@ -592,14 +603,14 @@ extern "C" int rb_plan_sweep_local(rb_plan *p, int cell_start, int cell_stride) 
     }
     if (G == 1) {
       dim3 gs3((n_local + 127) / 128, B);
-      k_cell_solve<<<gs3, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local);
+      k_cell_solve<<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local);
     } else {
       dim3 gs3(((long long)n_local * G + 127) / 128, B);
       switch (G) {
-        case 32: k_cell_solve_spec<32><<<gs3, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local); break;
-        case 16: k_cell_solve_spec<16><<<gs3, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local); break;
-        case 8: k_cell_solve_spec<8><<<gs3, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local); break;
-        default: k_cell_solve_spec<4><<<gs3, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local);
+        case 32: k_cell_solve_spec<32><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local); break;
+        case 16: k_cell_solve_spec<16><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local); break;
+        case 8: k_cell_solve_spec<8><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local); break;
+        default: k_cell_solve_spec<4><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local);
       }
     }
     p->info.n_launches += 1;
@@ -607,6 +618,80 @@ extern "C" int rb_plan_sweep_local(rb_plan *p, int cell_start, int cell_stride) 
     cudaEventRecord(sev[2], s);
   }
   cudaEventRecord(sev[3], s);
+  CK(cudaGetLastError());
+  return RB_OK;
+}
+
+extern "C" int rb_plan_sweep_local(rb_plan *p, int cell_start, int cell_stride) {
+  return sweep_impl(p, cell_start, cell_stride, false);
+}
+
+// ---------------------------------------------------------------------------
+// cell sharding over peer memory
+// ---------------------------------------------------------------------------
+static int plan_sweep_cells(const rb_plan *p);
+
+extern "C" int rb_plan_peer_alloc(rb_plan *p, int rank, int world, unsigned char handle[64]) {
+  if (!p || !handle || world < 1 || world > kMaxPeers || rank < 0 || rank >= world ||
+      p->d.n_problems != 1 || p->dpeer)
+    return RB_ERR_BAD_ARG;
+  const int ncell = plan_sweep_cells(p);
+  if (ncell % world != 0) return RB_ERR_BAD_ARG;
+  const int n_local = ncell / world;
+  const size_t bytes = 256 + (size_t)2 * world * 5 * n_local * sizeof(double);
+  if (cudaMalloc(&p->dpeer, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    p->dpeer = nullptr;
+    return RB_ERR_NOMEM;
+  }
+  CK(cudaMemset(p->dpeer, 0, bytes));
+  CK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, p->dpeer));
+  static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+  memcpy(handle, &h, 64);
+  p->Q.world = 1;  // not usable until rb_plan_peer_connect
+  p->Q.rank = rank; p->Q.n_local = n_local; p->Q.parity = 0;
+  p->peer_world = world;
+  p->peer_base[rank] = p->dpeer;
+  return RB_OK;
+}
+
+extern "C" int rb_plan_peer_connect(rb_plan *p, const unsigned char *handles) {
+  if (!p || !handles || !p->dpeer) return RB_ERR_BAD_ARG;
+  const int world = p->peer_world, rank = p->Q.rank;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * 64, 64);
+    CK(cudaIpcOpenMemHandle(&p->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  for (int r = 0; r < world; ++r) {
+    p->Q.flags[r] = (unsigned long long *)p->peer_base[r];
+    p->Q.stage[r] = (double *)((char *)p->peer_base[r] + 256);
+  }
+  p->Q.world = world;
+  p->Q.parity = 0;
+  p->peer_epoch = 0;
+  return RB_OK;
+}
+
+extern "C" int rb_plan_sweep_sharded(rb_plan *p) {
+  if (!p || p->Q.world < 2) return RB_ERR_BAD_ARG;
+  if (p->sweeps_issued - p->sweeps_polled >= kSlots - 1) return RB_ERR_BAD_ARG;  // poll first
+  p->peer_epoch += 1;
+  p->Q.epoch = p->peer_epoch;
+  p->Q.parity = (int)(p->peer_epoch & 1);
+  int rc = sweep_impl(p, p->Q.rank, p->Q.world, true);
+  if (rc) return rc;
+  const int slot = (int)(p->sweeps_issued % kSlots);
+  cudaStream_t s = p->stream;
+  k_exchange_finish<256><<<1, 256, 0, s>>>(p->P, p->Q, slot);
+  p->info.n_launches += 1;
+  CK(cudaMemcpyAsync(p->hflags + 3 + slot, p->dflags + 3 + slot, sizeof(int),
+                     cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(p->sev[slot][4], s));
+  p->sweeps_issued += 1;
   CK(cudaGetLastError());
   return RB_OK;
 }
@@ -709,7 +794,7 @@ static int plan_check_errors(rb_plan *p) {
   return rc;
 }
 
-extern "C" int rb_plan_solve(rb_plan *p, rb_info *info) {
+static int solve_loop(rb_plan *p, rb_info *info, bool sharded) {
   if (!p) return RB_ERR_BAD_ARG;
   const auto t0 = std::chrono::steady_clock::now();
   const size_t B = p->d.n_problems;
@@ -728,8 +813,12 @@ extern "C" int rb_plan_solve(rb_plan *p, rb_info *info) {
   bool stop = false;
   for (;;) {
     if (!stop && p->sweeps_issued - p->sweeps_polled < kDepth) {
-      rc = rb_plan_sweep_local(p, 0, 1);
-      if (!rc) rc = rb_plan_finish_sweep_async(p);
+      if (sharded) {
+        rc = rb_plan_sweep_sharded(p);
+      } else {
+        rc = rb_plan_sweep_local(p, 0, 1);
+        if (!rc) rc = rb_plan_finish_sweep_async(p);
+      }
       if (rc) return rc;
       continue;
     }
@@ -766,6 +855,12 @@ extern "C" int rb_plan_solve(rb_plan *p, rb_info *info) {
   return rc;
 }
 
+extern "C" int rb_plan_solve(rb_plan *p, rb_info *info) { return solve_loop(p, info, false); }
+extern "C" int rb_plan_solve_sharded(rb_plan *p, rb_info *info) {
+  if (!p || p->Q.world < 2) return RB_ERR_BAD_ARG;
+  return solve_loop(p, info, true);
+}
+
 extern "C" int rb_plan_bench_steps(rb_plan *p, int steps, size_t flush_bytes, double *ms_sum) {
   if (!p || steps < 0 || !ms_sum) return RB_ERR_BAD_ARG;
   void *flush = nullptr;
@@ -778,9 +873,14 @@ extern "C" int rb_plan_bench_steps(rb_plan *p, int steps, size_t flush_bytes, do
   for (int s = 0; s < steps && rc == RB_OK; ++s) {
     if (flush) cudaMemsetAsync(flush, s & 0xff, flush_bytes, p->stream);
     cudaEventRecord(p->ev[6], p->stream);
-    rc = rb_plan_sweep_local(p, 0, 1);
     int n_active = 0;
-    if (!rc) rc = rb_plan_finish_sweep(p, &n_active);
+    if (p->Q.world > 1) {
+      rc = rb_plan_sweep_sharded(p);
+      if (!rc) rc = rb_plan_poll_sweep(p, &n_active);
+    } else {
+      rc = rb_plan_sweep_local(p, 0, 1);
+      if (!rc) rc = rb_plan_finish_sweep(p, &n_active);
+    }
     cudaEventRecord(p->ev[7], p->stream);
     if (cudaEventSynchronize(p->ev[7]) != cudaSuccess) rc = RB_ERR_CUDA;
     float ms = 0.f;

@@ -63,6 +63,30 @@ struct PlanDev {
   int *nactive;                         // [kSlots] active-problem count per sweep slot
 };
 
+// Cell-sharded multi-GPU exchange over peer memory (NVLink / NVSwitch), SURVEY 8e.
+// Rank r owns the swept cells il = r + j*world.  The cell solver writes the five
+// new fractions of its cells straight into EVERY rank's staging buffer (remote
+// stores, `stage[r]` are cudaIpc-mapped peer pointers); the finish kernel then
+// raises this rank's flag on every peer, waits for all peers' flags, scatters
+// the staged fractions into the full state arrays and runs the convergence test.
+// Two staging rows alternate: a rank can run at most one barrier ahead.
+constexpr int kMaxPeers = 8;
+struct PeerDev {
+  int world, rank, n_local, parity;
+  unsigned long long epoch;               // flag value that means "this sweep is staged"
+  double *stage[kMaxPeers];               // rank r's staging [2][world][5][n_local]
+  unsigned long long *flags[kMaxPeers];   // rank r's flags [kMaxPeers], written by its peers
+};
+
+__device__ __forceinline__ void peer_scatter(const PeerDev &Q, int j, const rb_frac_t &x) {
+  const size_t n = (size_t)Q.n_local;
+  const size_t off = ((size_t)(Q.parity * Q.world + Q.rank) * 5) * n + j;
+  for (int r = 0; r < Q.world; ++r) {
+    double *d = Q.stage[r] + off;
+    d[0] = x.xH1; d[n] = x.xH2; d[2 * n] = x.xHe1; d[3 * n] = x.xHe2; d[4 * n] = x.xHe3;
+  }
+}
+
 __device__ __forceinline__ size_t col_index(const PlanDev &P, int b, int il, int idir) {
   return ((size_t)b * P.Nl + il) * (size_t)P.Ndir + idir;
 }
@@ -602,7 +626,7 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local) {
 // first half and mirror (slab_bgnd.f90:842-865).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-k_cell_solve(PlanDev P, int cell_start, int cell_stride, int n_local) {
+k_cell_solve(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_local) {
   const int b = blockIdx.y;
   if (!P.active[b]) return;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -630,6 +654,7 @@ k_cell_solve(PlanDev P, int cell_start, int cell_stride, int n_local) {
   P.x[0][c] = x.xH1; P.x[1][c] = x.xH2; P.x[2][c] = x.xHe1;
   P.x[3][c] = x.xHe2; P.x[4][c] = x.xHe3;
   if (P.find_Teq) P.T[c] = T;
+  if (Q.world > 1) peer_scatter(Q, j, x);
   if (two_sided(P.geom)) {
     const size_t cm = (size_t)b * P.Nl + (P.Nl - 1 - il);
     P.x[0][cm] = x.xH1; P.x[1][cm] = x.xH2; P.x[2][cm] = x.xHe1;
@@ -655,7 +680,7 @@ k_cell_solve(PlanDev P, int cell_start, int cell_stride, int n_local) {
 // ---------------------------------------------------------------------------
 template <int G>
 __global__ void __launch_bounds__(128)
-k_cell_solve_spec(PlanDev P, int cell_start, int cell_stride, int n_local) {
+k_cell_solve_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_local) {
   const int b = blockIdx.y;
   if (!P.active[b]) return;
   constexpr int L = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : 2;
@@ -741,6 +766,7 @@ k_cell_solve_spec(PlanDev P, int cell_start, int cell_stride, int n_local) {
   P.x[0][c] = xo.xH1; P.x[1][c] = xo.xH2; P.x[2][c] = xo.xHe1;
   P.x[3][c] = xo.xHe2; P.x[4][c] = xo.xHe3;
   P.T[c] = Tfinal;
+  if (Q.world > 1) peer_scatter(Q, j, xo);
   if (two_sided(P.geom)) {
     const size_t cm = (size_t)b * P.Nl + (P.Nl - 1 - il);
     P.x[0][cm] = xo.xH1; P.x[1][cm] = xo.xH2; P.x[2][cm] = xo.xHe1;
@@ -763,7 +789,7 @@ k_cell_solve_spec(PlanDev P, int cell_start, int cell_stride, int n_local) {
 constexpr int kSlots = 8;
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_converge_finish(PlanDev P, int slot) {
+__device__ __forceinline__ void converge_finish(const PlanDev &P, int slot) {
   const int b = blockIdx.x;
   if (b == 0 && threadIdx.x == 0) P.nactive[(slot + 1) % kSlots] = 0;
   if (!P.active[b]) return;
@@ -802,6 +828,62 @@ __global__ void __launch_bounds__(BLOCK) k_converge_finish(PlanDev P, int slot) 
     P.active[b] = act;
     if (act) atomicAdd(&P.nactive[slot], 1);
   }
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_converge_finish(PlanDev P, int slot) {
+  converge_finish<BLOCK>(P, slot);
+}
+
+// k_exchange_finish: the cell-sharded sweep's barrier + scatter + convergence test
+// (single-problem plans; one CTA).  Thread 0 publishes "my cells are staged
+// everywhere" (system-scope release after the cell kernel's remote stores) and
+// acquires the same from every peer; a peer that never arrives trips a 2 s
+// timeout (RB_ERR_PEER_TIMEOUT) instead of hanging the GPU.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_exchange_finish(PlanDev P, PeerDev Q, int slot) {
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    for (int r = 0; r < Q.world; ++r)
+      if (r != Q.rank)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(Q.flags[r] + Q.rank), "l"(Q.epoch)
+                     : "memory");
+    const unsigned long long t0 = global_ns();
+    for (int r = 0; r < Q.world; ++r) {
+      if (r == Q.rank) continue;
+      for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(Q.flags[Q.rank] + r)
+                     : "memory");
+        if (v >= Q.epoch) break;
+        if (global_ns() - t0 > 2000000000ull) {
+          atomicMax(&P.err[0], RB_ERR_PEER_TIMEOUT);
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (P.active[0]) {
+    const size_t n = (size_t)Q.n_local;
+    const double *st = Q.stage[Q.rank] + (size_t)Q.parity * Q.world * 5 * n;
+    const int total = Q.world * 5 * Q.n_local;
+    for (int i = threadIdx.x; i < total; i += BLOCK) {
+      const int j = i % Q.n_local, f = (i / Q.n_local) % 5, g = i / (5 * Q.n_local);
+      const double v = __ldcv(st + i);
+      const int il = j * Q.world + g;
+      P.x[f][il] = v;
+      if (two_sided(P.geom)) P.x[f][P.Nl - 1 - il] = v;  // mirrored half
+    }
+  }
+  __syncthreads();
+  converge_finish<BLOCK>(P, slot);
 }
 
 // ---------------------------------------------------------------------------

@@ -166,6 +166,43 @@ class Plan(object):
                            device="cuda:%d" % dev)
         return send, recv
 
+    # ------------------------------------------------------------------ peer-memory sharding
+    def connect_peers(self, rank, world, group=None):
+        """Map every rank's staging buffer into this process (CUDA IPC over
+        NVLink/NVSwitch peer access).  Collective over ``group``; afterwards
+        :meth:`solve_cell_sharded` exchanges the fractions with remote stores from
+        the cell-solver kernel and a flag barrier -- no collective per sweep."""
+        import torch
+        import torch.distributed as dist
+        h = (C.c_ubyte * 64)()
+        check(lib().rb_plan_peer_alloc(self._h, C.c_int(rank), C.c_int(world), h))
+        mine = torch.tensor(list(bytes(h)), dtype=torch.uint8)
+        dev = torch.cuda.current_device() if self.device < 0 else self.device
+        if dist.get_backend(group) == "nccl":
+            mine = mine.to("cuda:%d" % dev)
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine, group=group)
+        blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+        buf = (C.c_ubyte * (64 * world)).from_buffer_copy(blob)
+        check(lib().rb_plan_peer_connect(self._h, buf))
+        self._peer = (rank, world)
+
+    def sweep_sharded(self):
+        check(lib().rb_plan_sweep_sharded(self._h))
+
+    def gather_cells(self, rank, world, group=None):
+        """One all-gather of the 12 state fields of every rank's cells (T and the
+        six rates are not exchanged per sweep on the peer path)."""
+        import torch
+        import torch.distributed as dist
+        send, recv = self.shard_buffers(world)
+        ext = torch.cuda.ExternalStream(self.stream_ptr)
+        with torch.cuda.stream(ext):
+            self.pack_cells(rank, world, send.data_ptr())
+            dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
+            self.unpack_cells(world, recv.data_ptr())
+        self.sync()
+
     def enqueue_sharded_sweep(self, rank, world, send, recv, group=None):
         """Enqueue one cell-sharded Jacobi sweep: local cells -> pack -> NCCL
         all-gather -> unpack -> convergence test on the full arrays.  Must run with
@@ -196,6 +233,12 @@ class Plan(object):
         import torch
         if self.n_problems != 1:
             raise ValueError("cell sharding is defined for a single problem per plan")
+        if getattr(self, "_peer", None) == (rank, world):
+            # peer-memory path: the whole pipelined loop runs in the library
+            info = rb_info()
+            check(lib().rb_plan_solve_sharded(self._h, C.byref(info)))
+            self.gather_cells(rank, world, group)
+            return info.iters
         send, recv = self.shard_buffers(world)
         ext = torch.cuda.ExternalStream(self.stream_ptr)
         issued = polled = sweeps = 0
