@@ -62,6 +62,7 @@ typedef struct rb_info {
   double ms_columns;  /* summed device time of the column (ray / scan) kernel */
   double ms_nu;       /* summed device time of the frequency-integral kernel */
   double ms_cell;     /* summed device time of the cell-solver kernel */
+  double ms_rec;      /* summed device time of the recombination-photon kernels */
   long long evals;    /* cell*ray*frequency evaluations performed */
 } rb_info;
 
@@ -206,6 +207,11 @@ typedef struct rb_plan_desc {
   int device;     /* CUDA device ordinal, -1 = current */
   int max_sweeps; /* 0: reference limits; >0: stop every problem after this many;
                      <0: fixed-work mode, exactly -max_sweeps sweeps, convergence ignored */
+  int i_rec_meth; /* 0 or 1: fixed case-A fraction; spheres: 2 outward, 3 radial,
+                     4 isotropic (sphere_base.f90:79-1083); slabs: 2 = "ray"
+                     (slab_base.f90:163-560).  != 1 forces case-A rates. */
+  double em_fac[3]; /* isotropic: multipliers of the H1/He1/He2 recombination emission
+                       (sphere_bgnd.f90:75-77); 0,0,0 is read as 1,1,1 */
 } rb_plan_desc;
 
 int rb_plan_create(rb_plan **plan, const rb_plan_desc *desc);
@@ -267,6 +273,10 @@ int rb_plan_get_problem(rb_plan *plan, int b, double *T, double *xH1,
                         double *H1i_src, double *He1i_src, double *He2i_src,
                         double *H1h_src, double *He1h_src, double *He2h_src,
                         int *iters);
+/* D2H of one problem's recombination-photon rates (zeros for rec_meth = fixed) */
+int rb_plan_get_rec(rb_plan *plan, int b, double *H1i_rec, double *He1i_rec,
+                    double *He2i_rec, double *H1h_rec, double *He1h_rec,
+                    double *He2h_rec);
 /* device pointers for torch / NCCL interop: fields are [n_problems*Nl] float64.
  * 0..4 = xH1,xH2,xHe1,xHe2,xHe3 ; 5 = T ; 6..11 = H1i,He1i,He2i,H1h,He1h,He2h src */
 void *rb_plan_field_ptr(rb_plan *plan, int field);

@@ -95,7 +95,7 @@ double orc_ds_segment(const double *Edges, int il, double mu, int j, int Nl,
 }
 
 /* same arithmetic as ds_segment with m and p hoisted out (flavour HOISTED) */
-static double ds_hoisted(const double *Edges, double p_ray, int m, int j) {
+double orc_ds_hoisted(const double *Edges, double p_ray, int m, int j) {
   double s1, s2;
   if (j == m) {
     s1 = sqrt(Edges[j] * Edges[j] - p_ray * p_ray);
@@ -128,7 +128,7 @@ static int ray_columns(const double *Edges, const double *nH, const double *nHe,
       ds = orc_ds_segment(Edges, il, mu, j, Nl, &e);
       if (e) return e;
     } else {
-      ds = ds_hoisted(Edges, p_ray, m, j);
+      ds = orc_ds_hoisted(Edges, p_ray, m, j);
     }
     if (j == j0) ds = ds * 0.5;
     NH1 = NH1 + ds * nH[jnl] * xH1[jnl];
@@ -413,12 +413,52 @@ static void add_counters(long long *counters, const cnt_t *c) {
 
 /* ---------------------------------------------------------------------- */
 /* sphere_bgnd.f90:578-918 (sphere_bgnd_sweep), rec_meth fixed.            */
+/* recombination radiation at the current state, before the cell loop:
+ * sphere_bgnd.f90:686-735, sphere_stromgren.f90:713-757 (i_rec_meth 2,3,4),
+ * slab_bgnd.f90:653-672, slab_plane.f90:657-676,974-993 (i_rec_meth 2).
+ * geom: 0 sphere with decreasing Edges, 1 sphere with increasing Edges, 2 slab */
+static int rec_photons(int geom, int i_rec_meth, const spec_t *s,
+                       const double *Edges, const double *nH, const double *nHe,
+                       const double *T, int Nmu, const double em_fac[3], int Nl,
+                       out_t *o) {
+  if (i_rec_meth == 1) {
+    for (int X = 0; X < 3; X++)
+      for (int i = 0; i < Nl; i++) {
+        o->ion_rec[X][i] = 0.0;
+        o->heat_rec[X][i] = 0.0;
+      }
+    return ORC_OK;
+  }
+  if (geom == 2) {
+    orc_rec_slab(o->xH1, o->xH2, o->xHe1, o->xHe2, o->xHe3, Edges, nH, nHe, T,
+                 s->sigma_th, s->E_th, Nl, o->ion_rec, o->heat_rec);
+    return ORC_OK;
+  }
+  const int dec = (geom == 0);
+  if (i_rec_meth == 2)
+    orc_rec_outward(o->xH1, o->xH2, o->xHe1, o->xHe2, o->xHe3, Edges, nH, nHe, T,
+                    dec, s->sigma_th, s->E_th, Nl, o->ion_rec, o->heat_rec);
+  else if (i_rec_meth == 3)
+    orc_rec_radial(o->xH1, o->xH2, o->xHe1, o->xHe2, o->xHe3, Edges, nH, nHe, T,
+                   dec, s->sigma_th, s->E_th, Nl, o->ion_rec, o->heat_rec);
+  else
+    return orc_rec_isotropic(o->xH1, o->xH2, o->xHe1, o->xHe2, o->xHe3, Edges, nH,
+                             nHe, T, dec, Nmu, s->sigma_th, s->E_th, em_fac, Nl,
+                             o->ion_rec, o->heat_rec);
+  return ORC_OK;
+}
+
 static int sphere_bgnd_sweep(const spec_t *s, const double *Edges,
                              const double *nH, const double *nHe, double *T,
                              int Nmu, double fcA, int i_find_Teq, double z,
                              double Hz, double tol, int Nl, int order,
-                             int flavour, out_t *o, cnt_t *cnt) {
+                             int flavour, int i_rec_meth, const double em_fac[3],
+                             out_t *o, cnt_t *cnt) {
   int Nnu = s->Nnu;
+  {
+    int rrc = rec_photons(0, i_rec_meth, s, Edges, nH, nHe, T, Nmu, em_fac, Nl, o);
+    if (rrc) return rrc;
+  }
   double *xi = (double *)malloc(sizeof(double) * 2 * (size_t)Nmu);
   double *wi = xi + Nmu;
   orc_p_quadrature_rule(Nmu, xi, wi); /* :743 */
@@ -479,8 +519,13 @@ static int sphere_bgnd_sweep(const spec_t *s, const double *Edges,
         }
         o->ion_src[X][il] = a * 0.5;
         o->heat_src[X][il] = b * 0.5;
-        ion[X] = o->ion_src[X][il]; /* i_rec_meth == 1: :861-881 */
-        heat[X] = o->heat_src[X][il];
+        /* :861-881 (i_rec_meth == 1: the rec arrays are zero) */
+        ion[X] = o->ion_src[X][il] + o->ion_rec[X][il];
+        heat[X] = o->heat_src[X][il] + o->heat_rec[X][il];
+        if (i_rec_meth == 1) {
+          ion[X] = o->ion_src[X][il];
+          heat[X] = o->heat_src[X][il];
+        }
       }
       rc = cell_solve(i_find_Teq, nH[il], nHe[il], ion, heat, z, Hz, fcA, tol,
                       &o->xH1[il], &o->xH2[il], &o->xHe1[il], &o->xHe2[il],
@@ -527,9 +572,9 @@ int orc_sphere_bgnd_solve(
     double *H1h_src, double *He1h_src, double *He2h_src, double *H1h_rec,
     double *He1h_rec, double *He2h_rec, const orc_opts *opts, int *iters,
     long long *counters) {
-  (void)em_H1_fac; (void)em_He1_fac; (void)em_He2_fac;
-  if (i_rec_meth != 1 || i_photo_fit != 1 || i_rate_fit != 1 || Nl < 1 ||
-      Nnu < 1 || Nmu < 1)
+  const double em_fac[3] = {em_H1_fac, em_He1_fac, em_He2_fac};
+  if (i_rec_meth < 1 || i_rec_meth > 4 || i_photo_fit != 1 || i_rate_fit != 1 ||
+      Nl < 1 || Nnu < 1 || Nmu < 1)
     return ORC_ERR_BAD_ARG;
   int order = opts ? opts->order : ORC_ORDER_GS;
   int flavour = opts ? opts->flavour : ORC_FLAVOUR_HOISTED;
@@ -550,7 +595,7 @@ int orc_sphere_bgnd_solve(
   }
   spec_t s;
   spec_init(&s, SRC_BGND, E_eV, shape, Nnu);
-  double fcA = fixed_fcA; /* i_rec_meth == 1: :435-443, :676-684 */
+  double fcA = (i_rec_meth == 1) ? fixed_fcA : 1.0; /* :435-443, :676-684 */
   cnt_t cnt = {0, 0, 0, 0};
 
   int rc = thin_state(&s, NULL, nH, nHe, T, fcA, i_find_Teq, z, Hz, tol, Nl, &o);
@@ -562,7 +607,7 @@ int orc_sphere_bgnd_solve(
     int not_converged = 1;
     while (not_converged) {
       rc = sphere_bgnd_sweep(&s, Edges, nH, nHe, T, Nmu, fcA, i_find_Teq, z, Hz,
-                             tol, Nl, order, flavour, &o, &cnt);
+                             tol, Nl, order, flavour, i_rec_meth, em_fac, &o, &cnt);
       if (rc) break;
       if (iter > OUTER_MAX_ITER) { /* :284-287 */
         rc = ORC_ERR_MAX_ITER_OUTER;
@@ -606,8 +651,14 @@ static void optical_depths(const double *dtau, int inl, int Nl, double *lo,
 static int column_sweep(int kind, const spec_t *s, const double *Edges,
                         const double *nH, const double *nHe, double *T,
                         double fcA, int i_find_Teq, double z, double Hz,
-                        double tol, int Nl, int flavour, out_t *o, cnt_t *cnt) {
+                        double tol, int Nl, int flavour, int i_rec_meth, int Nmu,
+                        const double em_fac[3], out_t *o, cnt_t *cnt) {
   int Nnu = s->Nnu;
+  {
+    int rrc = rec_photons(kind == 0 ? 1 : 2, i_rec_meth, s, Edges, nH, nHe, T, Nmu,
+                          em_fac, Nl, o);
+    if (rrc) return rrc;
+  }
   size_t n = (size_t)Nl;
   double *buf = (double *)malloc(sizeof(double) * 5 * n);
   double *r_c = buf, *dtau[3] = {buf + n, buf + 2 * n, buf + 3 * n};
@@ -654,6 +705,10 @@ static int column_sweep(int kind, const spec_t *s, const double *Edges,
       for (int X = 0; X < 3; X++) {
         o->ion_src[X][inl] = ion[X];
         o->heat_src[X][inl] = heat[X];
+        if (i_rec_meth != 1) { /* totals: slab_bgnd.f90:752-760,800-808 and twins */
+          ion[X] = o->ion_src[X][inl] + o->ion_rec[X][inl];
+          heat[X] = o->heat_src[X][inl] + o->heat_rec[X][inl];
+        }
       }
       int rc = cell_solve(i_find_Teq, nH[inl], nHe[inl], ion, heat, z, Hz, fcA,
                           tol, &o->xH1[inl], &o->xH2[inl], &o->xHe1[inl],
@@ -699,9 +754,9 @@ int orc_sphere_stromgren_solve(
     double *H1h_src, double *He1h_src, double *He2h_src, double *H1h_rec,
     double *He1h_rec, double *He2h_rec, const orc_opts *opts, int *iters,
     long long *counters) {
-  (void)Nmu; (void)em_H1_fac; (void)em_He1_fac; (void)em_He2_fac;
-  if (i_rec_meth != 1 || i_photo_fit != 1 || i_rate_fit != 1 || Nl < 1 ||
-      Nnu < 1)
+  const double em_fac[3] = {em_H1_fac, em_He1_fac, em_He2_fac};
+  if (i_rec_meth < 1 || i_rec_meth > 4 || i_photo_fit != 1 || i_rate_fit != 1 ||
+      Nl < 1 || Nnu < 1 || (i_rec_meth == 4 && Nmu < 1))
     return ORC_ERR_BAD_ARG;
   int flavour = opts ? opts->flavour : ORC_FLAVOUR_HOISTED;
   int max_sweeps = opts ? opts->max_sweeps : 0;
@@ -720,7 +775,7 @@ int orc_sphere_stromgren_solve(
   }
   spec_t s;
   spec_init(&s, SRC_POINT, E_eV, shape, Nnu);
-  double fcA = fixed_fcA;
+  double fcA = (i_rec_meth == 1) ? fixed_fcA : 1.0; /* sphere_stromgren.f90:450-458 */
   cnt_t cnt = {0, 0, 0, 0};
   double *r_c = (double *)malloc(sizeof(double) * (size_t)Nl);
   for (int i = 0; i < Nl; i++) r_c[i] = (Edges[i] + Edges[i + 1]) * 0.5;
@@ -733,7 +788,7 @@ int orc_sphere_stromgren_solve(
     int iter = 0, not_converged = 1;
     while (not_converged) {
       rc = column_sweep(0, &s, Edges, nH, nHe, T, fcA, i_find_Teq, z, Hz, tol,
-                        Nl, flavour, &o, &cnt);
+                        Nl, flavour, i_rec_meth, Nmu, em_fac, &o, &cnt);
       if (rc) break;
       if (iter > OUTER_MAX_ITER) {
         rc = ORC_ERR_MAX_ITER_OUTER;
@@ -767,8 +822,9 @@ int orc_slab_bgnd_solve(
     double *H1h_src, double *He1h_src, double *He2h_src, double *H1h_rec,
     double *He1h_rec, double *He2h_rec, const orc_opts *opts, int *iters,
     long long *counters) {
-  if (i_rec_meth != 1 || i_photo_fit != 1 || i_rate_fit != 1 || Nl < 1 ||
-      Nnu < 1)
+  const double em_fac[3] = {1.0, 1.0, 1.0};
+  if (i_rec_meth < 1 || i_rec_meth > 2 || i_photo_fit != 1 || i_rate_fit != 1 ||
+      Nl < 1 || Nnu < 1)
     return ORC_ERR_BAD_ARG;
   int flavour = opts ? opts->flavour : ORC_FLAVOUR_HOISTED;
   int max_sweeps = opts ? opts->max_sweeps : 0;
@@ -779,7 +835,7 @@ int orc_slab_bgnd_solve(
   if (iters) *iters = 0;
   spec_t s;
   spec_init(&s, SRC_BGND, E_eV, shape, Nnu);
-  double fcA = fixed_fcA; /* slab_bgnd.f90:411-413 */
+  double fcA = (i_rec_meth == 1) ? fixed_fcA : 1.0; /* slab_bgnd.f90:411-419 */
   cnt_t cnt = {0, 0, 0, 0};
   int rc = thin_state(&s, NULL, nH, nHe, T, fcA, i_find_Teq, z, Hz, tol, Nl, &o);
   if (rc == ORC_OK && i_thin != 1) {
@@ -789,7 +845,7 @@ int orc_slab_bgnd_solve(
     int iter = 0, not_converged = 1;
     while (not_converged) {
       rc = column_sweep(3, &s, Edges, nH, nHe, T, fcA, i_find_Teq, z, Hz, tol,
-                        Nl, flavour, &o, &cnt);
+                        Nl, flavour, i_rec_meth, 0, em_fac, &o, &cnt);
       if (rc) break;
       iter = iter + 1;
       if (ne_converged(nH, nHe, &o, conv_old, tol, Nl)) not_converged = 0;
@@ -815,8 +871,9 @@ int orc_slab_plane_solve(
     double *He2i_rec, double *H1h_src, double *He1h_src, double *He2h_src,
     double *H1h_rec, double *He1h_rec, double *He2h_rec, const orc_opts *opts,
     int *iters, long long *counters) {
-  if (i_rec_meth != 1 || i_photo_fit != 1 || i_rate_fit != 1 || Nl < 1 ||
-      Nnu < 1)
+  const double em_fac[3] = {1.0, 1.0, 1.0};
+  if (i_rec_meth < 1 || i_rec_meth > 2 || i_photo_fit != 1 || i_rate_fit != 1 ||
+      Nl < 1 || Nnu < 1)
     return ORC_ERR_BAD_ARG;
   int flavour = opts ? opts->flavour : ORC_FLAVOUR_HOISTED;
   int max_sweeps = opts ? opts->max_sweeps : 0;
@@ -827,7 +884,7 @@ int orc_slab_plane_solve(
   if (iters) *iters = 0;
   spec_t s;
   spec_init(&s, SRC_PLANE, E_eV, shape, Nnu);
-  double fcA = fixed_fcA;
+  double fcA = (i_rec_meth == 1) ? fixed_fcA : 1.0; /* slab_plane.f90:411-419 */
   cnt_t cnt = {0, 0, 0, 0};
   int rc = thin_state(&s, NULL, nH, nHe, T, fcA, i_find_Teq, z, Hz, tol, Nl, &o);
   if (rc == ORC_OK && i_thin != 1) {
@@ -837,7 +894,8 @@ int orc_slab_plane_solve(
     int iter = 0, not_converged = 1;
     while (not_converged) {
       rc = column_sweep(i_2side == 1 ? 2 : 1, &s, Edges, nH, nHe, T, fcA,
-                        i_find_Teq, z, Hz, tol, Nl, flavour, &o, &cnt);
+                        i_find_Teq, z, Hz, tol, Nl, flavour, i_rec_meth, 0, em_fac,
+                        &o, &cnt);
       if (rc) break;
       if (iter > OUTER_MAX_ITER) { /* :265-268 */
         rc = ORC_ERR_MAX_ITER_OUTER;
@@ -884,7 +942,7 @@ int orc_set_column_vs_impact(double *xH1, double *xH2, double *xHe1,
       double a = 0.0, b = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
       for (int j = 0; j <= 2 * m; j++) {
         int jnl = m - abs(m - j);
-        double ds = ds_hoisted(Edges, p_ray, m, j);
+        double ds = orc_ds_hoisted(Edges, p_ray, m, j);
         a = a + ds * nH[jnl];
         b = b + ds * nHe[jnl];
         c1 = c1 + ds * nH[jnl] * xH1[jnl];

@@ -54,4 +54,31 @@ int orc_pcte1(double nH, double nHe, double H1i, double He1i, double He2i,
               double *xH1, double *xH2, double *xHe1, double *xHe2,
               double *xHe3, double *T);
 
+
+/* geometry.f90:146-165 with m and p hoisted (rb_oracle_geom.c) */
+double orc_ds_hoisted(const double *Edges, double p_ray, int m, int j);
+
+/* recombination-photon transfer (rb_oracle_rec.c) */
+void orc_rec_outward(const double *xH1, const double *xH2, const double *xHe1,
+                     const double *xHe2, const double *xHe3, const double *Edges,
+                     const double *nH, const double *nHe, const double *T,
+                     int have_dec, const double sigma_th[3], const double E_th[3],
+                     int Nl, double *ion[3], double *heat[3]);
+void orc_rec_radial(const double *xH1, const double *xH2, const double *xHe1,
+                    const double *xHe2, const double *xHe3, const double *Edges,
+                    const double *nH, const double *nHe, const double *T,
+                    int have_dec, const double sigma_th[3], const double E_th[3],
+                    int Nl, double *ion[3], double *heat[3]);
+int orc_rec_isotropic(const double *xH1, const double *xH2, const double *xHe1,
+                      const double *xHe2, const double *xHe3, const double *Edges,
+                      const double *nH, const double *nHe, const double *T,
+                      int have_dec, int Nmu, const double sigma_th[3],
+                      const double E_th[3], const double em_fac[3], int Nl,
+                      double *ion[3], double *heat[3]);
+void orc_rec_slab(const double *xH1, const double *xH2, const double *xHe1,
+                  const double *xHe2, const double *xHe3, const double *Edges,
+                  const double *nH, const double *nHe, const double *T,
+                  const double sigma_th[3], const double E_th[3], int Nl,
+                  double *ion[3], double *heat[3]);
+
 #endif

@@ -24,7 +24,7 @@ class rb_info(C.Structure):
     _fields_ = [("iters", C.c_int), ("n_launches", C.c_int), ("resid", C.c_double),
                 ("ms_total", C.c_double), ("ms_device", C.c_double),
                 ("ms_columns", C.c_double), ("ms_nu", C.c_double),
-                ("ms_cell", C.c_double), ("evals", C.c_longlong)]
+                ("ms_cell", C.c_double), ("ms_rec", C.c_double), ("evals", C.c_longlong)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -34,7 +34,7 @@ class rb_plan_desc(C.Structure):
     _fields_ = [("geometry", C.c_int), ("n_problems", C.c_int), ("Nl", C.c_int),
                 ("Nnu", C.c_int), ("Nmu", C.c_int), ("i_find_Teq", C.c_int),
                 ("fixed_fcA", C.c_double), ("tol", C.c_double), ("device", C.c_int),
-                ("max_sweeps", C.c_int)]
+                ("max_sweeps", C.c_int), ("i_rec_meth", C.c_int), ("em_fac", C.c_double * 3)]
 
 
 GEOM_SPHERE_BGND, GEOM_SPHERE_STROMGREN, GEOM_SLAB_PLANE_1, GEOM_SLAB_PLANE_2, \
@@ -50,7 +50,7 @@ EXPORTS = (
     "rb_plan_create", "rb_plan_destroy", "rb_plan_set_problem", "rb_plan_upload",
     "rb_plan_thin", "rb_plan_sweep_local", "rb_plan_finish_sweep", "rb_plan_finish_sweep_async",
     "rb_plan_poll_sweep", "rb_plan_solve",
-    "rb_plan_get_problem", "rb_plan_field_ptr", "rb_plan_stream", "rb_plan_sync",
+    "rb_plan_get_problem", "rb_plan_get_rec", "rb_plan_field_ptr", "rb_plan_stream", "rb_plan_sync",
     "rb_plan_evals_per_sweep", "rb_plan_last_info", "rb_plan_bench_steps", "rb_plan_pack_cells",
     "rb_plan_unpack_cells", "rb_microbench",
     "rb_plan_peer_alloc", "rb_plan_peer_connect", "rb_plan_sweep_sharded", "rb_plan_solve_sharded",

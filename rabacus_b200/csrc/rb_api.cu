@@ -7,7 +7,7 @@
 #include <cstring>
 #include <vector>
 
-#include "rb_kernels.cuh"
+#include "rb_rec.cuh"
 
 using namespace rb;
 
@@ -37,7 +37,7 @@ extern "C" const char *rb_strerror(int code) {
     case RB_ERR_NAN: return "NaN in solve_ce";
     case RB_ERR_RAY_GEOMETRY: return "ray geometry undefined (no shell edge <= impact parameter)";
     case RB_ERR_BAD_ARG: return "bad argument";
-    case RB_ERR_UNSUPPORTED: return "option not supported by the CUDA path (only rec_meth='fixed', verner, hg97)";
+    case RB_ERR_UNSUPPORTED: return "option not supported by the CUDA path (fits: verner / hg97 only; photon transfer rec_meth: one GPU, all cells)";
     case RB_ERR_CUDA: return g_cuda_msg[0] ? g_cuda_msg : "CUDA error / no CUDA device";
     case RB_ERR_NOMEM: return "out of memory";
     case RB_ERR_PEER_TIMEOUT: return "cell-sharded sweep: a peer rank did not reach the barrier within 2 s";
@@ -204,6 +204,14 @@ struct rb_plan {
   double4 *dcol = nullptr;
   unsigned *ditems = nullptr;   // column-kernel work list (LPT order), see build_items
   int *dwork = nullptr;         // [B] next-item counters of the column kernel
+  // recombination-photon transfer (rec_meth != fixed)
+  int rec_meth = 1;
+  double *drec = nullptr;       // 6*B*Nl output rates (always allocated; zero for fixed)
+  double *drecbuf = nullptr;    // scratch: em[3], F0[3], dtau[3], r_c (10*B*Nl), tlo, records
+  double4 *drecI = nullptr;     // isotropic on a plan whose col buffer is too small
+  RecDev R;
+  RecConst K;
+  cudaEvent_t rev[kSlots];      // after the rec kernels of each in-flight sweep
   // cell sharding over peer memory
   PeerDev Q;                    // world == 1 when not connected
   void *dpeer = nullptr;        // this rank's flags (256 B) + staging
@@ -243,6 +251,7 @@ extern "C" void rb_plan_destroy(rb_plan *p) {
   if (p->ev_ok) {
     for (auto &e : p->ev) cudaEventDestroy(e);
     for (auto &sl : p->sev) for (auto &e : sl) cudaEventDestroy(e);
+    for (auto &e : p->rev) cudaEventDestroy(e);
   }
   if (p->stream) cudaStreamDestroy(p->stream);
   cudaGetLastError();
@@ -257,6 +266,10 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
       d.Nnu < 1 || !(d.tol > 0.0))
     return RB_ERR_BAD_ARG;
   if (d.geometry == RB_GEOM_SPHERE_BGND && d.Nmu < 1) return RB_ERR_BAD_ARG;
+  const int rec_meth = d.i_rec_meth == 0 ? 1 : d.i_rec_meth;
+  const bool sphere = d.geometry == RB_GEOM_SPHERE_BGND || d.geometry == RB_GEOM_SPHERE_STROMGREN;
+  if (rec_meth < 1 || rec_meth > (sphere ? 4 : 2)) return RB_ERR_BAD_ARG;
+  if (rec_meth == 4 && d.Nmu < 1) return RB_ERR_BAD_ARG;
   if (d.Nl > 512 * 16) return RB_ERR_UNSUPPORTED;  // lock-step thin-state kernel limit
   if (rb_device_count() < 1) {
     snprintf(g_cuda_msg, sizeof(g_cuda_msg), "no CUDA device visible (there is no CPU fallback)");
@@ -295,6 +308,15 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   ALLOC(p->dmu, 2 * (size_t)std::max(1, d.Nmu) * 8);
   ALLOC(p->dcol, NC * (size_t)p->Ndir * sizeof(double4)); ALLOC(p->dzHz, B * 2 * 8);
   ALLOC(p->dwork, B * sizeof(int));
+  ALLOC(p->drec, 6 * NC * 8);
+  p->rec_meth = rec_meth;
+  if (rec_meth != 1) {
+    // em[3] F0[3] dtau[3] r_c | tlo [B][3][Nl+1] | recA, recB [B][Nl+1] double4
+    const size_t n_scal = 10 * NC + 3 * B * (Nl + 1);
+    ALLOC(p->drecbuf, n_scal * 8 + 2 * B * (Nl + 1) * sizeof(double4) + 32);
+    if (rec_meth == 4 && d.geometry != RB_GEOM_SPHERE_BGND)
+      ALLOC(p->drecI, NC * (size_t)d.Nmu * sizeof(double4));
+  }
   if (d.geometry == RB_GEOM_SPHERE_BGND)
     ALLOC(p->ditems, (size_t)((Nl + 31) / 32) * ((d.Nmu + 1) / 2) * sizeof(unsigned));
   {
@@ -316,8 +338,9 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   }
   for (auto &e : p->ev) cudaEventCreate(&e);
   for (auto &sl : p->sev) for (auto &e : sl) cudaEventCreate(&e);
+  for (auto &e : p->rev) cudaEventCreate(&e);
   p->ev_ok = true;
-  if (d.geometry == RB_GEOM_SPHERE_BGND) {
+  if (d.geometry == RB_GEOM_SPHERE_BGND || rec_meth == 4) {
     p->mu.resize(d.Nmu); p->wmu.resize(d.Nmu);
     rb_gauss_legendre(d.Nmu, p->mu.data(), p->wmu.data());  // sphere_bgnd.f90:743
     cudaMemcpy(p->dmu, p->mu.data(), d.Nmu * 8, cudaMemcpyHostToDevice);
@@ -336,7 +359,36 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   for (int i = 0; i < 6; ++i) P.src[i] = p->dsrc + i * NC;
   P.conv_old = p->dconv; P.pack = p->dpack; P.spec = p->dspec; P.thin = p->dthin;
   P.mu = p->dmu; P.wmu = p->dmu + std::max(1, d.Nmu); P.col = p->dcol; P.zHz = p->dzHz;
-  if (d.geometry == RB_GEOM_SPHERE_BGND) P.wmu = p->dmu + d.Nmu;
+  if (d.geometry == RB_GEOM_SPHERE_BGND || rec_meth == 4) P.wmu = p->dmu + d.Nmu;
+  for (int i = 0; i < 6; ++i) P.rec[i] = p->drec + i * NC;
+  if (rec_meth != 1) P.fcA = 1.0;  // sphere_bgnd.f90:435-443,676-684: case A with photon transfer
+  {
+    RecDev &R = p->R;
+    memset(&R, 0, sizeof(R));
+    for (int i = 0; i < 6; ++i) R.rec[i] = P.rec[i];
+    if (rec_meth != 1) {
+      double *q = p->drecbuf;
+      for (int X = 0; X < 3; ++X) { R.em[X] = q + X * NC; R.F0[X] = q + (3 + X) * NC;
+                                    R.dtau[X] = q + (6 + X) * NC; }
+      R.r_c = q + 9 * NC;
+      R.tlo = q + 10 * NC;
+      size_t off = (10 * NC + 3 * B * (Nl + 1)) * 8;
+      off = (off + 31) / 32 * 32;
+      R.recA = (double4 *)((char *)p->drecbuf + off);
+      R.recB = R.recA + B * (Nl + 1);
+      R.Iray = p->drecI ? p->drecI : p->dcol;  // SphereBgnd: the ray buffer is free until
+                                               // the column kernel of the same sweep
+    }
+    RecConst &K = p->K;
+    // sphere_base.f90:224-236
+    K.sH1_H1 = p->sigma_th[0]; K.sHe1_He1 = p->sigma_th[1]; K.sHe2_He2 = p->sigma_th[2];
+    for (int X = 0; X < 3; ++X) K.E_th[X] = v96_row(X).Eth;
+    K.sH1_He1 = v96_sigma(0, K.E_th[1]);
+    K.sH1_He2 = v96_sigma(0, K.E_th[2]);
+    K.sHe1_He2 = v96_sigma(1, K.E_th[2]);
+    const bool unset = d.em_fac[0] == 0.0 && d.em_fac[1] == 0.0 && d.em_fac[2] == 0.0;
+    for (int X = 0; X < 3; ++X) K.em_fac[X] = unset ? 1.0 : d.em_fac[X];
+  }
   P.active = p->dflags; P.iters = p->dflags + B; P.err = p->dflags + 2 * B;
   P.nactive = p->dflags + 3 * B; P.resid_bits = p->dresid;
   *out = p;
@@ -427,6 +479,7 @@ extern "C" int rb_plan_thin(rb_plan *p) {
   at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
+  CK(cudaMemsetAsync(p->drec, 0, 6 * cells(p) * 8, p->stream));  // sphere_bgnd.f90:490-496
   switch (cpt) {
     case 1: CK(cudaLaunchKernelEx(&cfg, k_thin_state<1>, p->P, cs)); break;
     case 2: CK(cudaLaunchKernelEx(&cfg, k_thin_state<2>, p->P, cs)); break;
@@ -563,6 +616,34 @@ static int launch_nu_rates(rb_plan *p, int cell_start, int cell_stride, int n_lo
   return rc;
 }
 
+// recombination-photon rates of all cells from the current state (rb_rec.cuh)
+static int launch_rec(rb_plan *p) {
+  const int Nl = p->d.Nl, B = p->d.n_problems, g = p->d.geometry;
+  cudaStream_t s = p->stream;
+  const bool sphere = g == RB_GEOM_SPHERE_BGND || g == RB_GEOM_SPHERE_STROMGREN;
+  dim3 gp((Nl + 1 + 127) / 128, B);
+  k_rec_prep<<<gp, 128, 0, s>>>(p->P, p->R, p->K, p->rec_meth);
+  dim3 gc((Nl + 63) / 64, B);
+  if (!sphere) {
+    k_rec_slab_prefix<<<B, 32, 0, s>>>(p->P, p->R, p->K);
+    k_rec_slab<<<gc, 64, 0, s>>>(p->P, p->R, p->K);
+    p->info.n_launches += 3;
+  } else if (p->rec_meth == 2) {
+    k_rec_outward<<<gc, 64, 0, s>>>(p->P, p->R, p->K);
+    p->info.n_launches += 2;
+  } else if (p->rec_meth == 3) {
+    k_rec_radial<<<gc, 64, 0, s>>>(p->P, p->R, p->K);
+    p->info.n_launches += 2;
+  } else {
+    dim3 gr((Nl + 127) / 128, p->d.Nmu, B);
+    k_rec_iso_rays<<<gr, 128, 0, s>>>(p->P, p->R, p->d.Nmu);
+    k_rec_iso_finish<<<gc, 64, 0, s>>>(p->P, p->R, p->K, p->d.Nmu);
+    p->info.n_launches += 3;
+  }
+  CK(cudaGetLastError());
+  return RB_OK;
+}
+
 static int sweep_impl(rb_plan *p, int cell_start, int cell_stride, bool scatter) {
   if (!p || cell_start < 0 || cell_stride < 1) return RB_ERR_BAD_ARG;
   PeerDev Q = p->Q;
@@ -574,6 +655,12 @@ static int sweep_impl(rb_plan *p, int cell_start, int cell_stride, bool scatter)
   cudaStream_t s = p->stream;
   cudaEvent_t *sev = p->sev[p->sweeps_issued % kSlots];
   int rc = RB_OK;
+  cudaEventRecord(p->rev[p->sweeps_issued % kSlots], s);
+  if (p->rec_meth != 1) {
+    if (cell_stride != 1 || scatter) return RB_ERR_UNSUPPORTED;  // photon transfer: one GPU
+    rc = launch_rec(p);
+    if (rc) return rc;
+  }
   cudaEventRecord(sev[0], s);
   if (g == RB_GEOM_SPHERE_BGND) {
     if (n_local > 0) rc = launch_sphere_columns(p, cell_start, cell_stride, n_local);
@@ -635,6 +722,7 @@ extern "C" int rb_plan_peer_alloc(rb_plan *p, int rank, int world, unsigned char
   if (!p || !handle || world < 1 || world > kMaxPeers || rank < 0 || rank >= world ||
       p->d.n_problems != 1 || p->dpeer)
     return RB_ERR_BAD_ARG;
+  if (p->rec_meth != 1) return RB_ERR_UNSUPPORTED;
   const int ncell = plan_sweep_cells(p);
   if (ncell % world != 0) return RB_ERR_BAD_ARG;
   const int n_local = ncell / world;
@@ -721,6 +809,7 @@ extern "C" int rb_plan_poll_sweep(rb_plan *p, int *n_active) {
   CK(cudaEventSynchronize(p->sev[slot][4]));
   float ms;  // per-stage device times of that sweep
   cudaEvent_t *sev = p->sev[slot];
+  if (cudaEventElapsedTime(&ms, p->rev[slot], sev[0]) == cudaSuccess) p->info.ms_rec += ms;
   if (cudaEventElapsedTime(&ms, sev[0], sev[1]) == cudaSuccess) p->info.ms_columns += ms;
   if (cudaEventElapsedTime(&ms, sev[1], sev[2]) == cudaSuccess) p->info.ms_nu += ms;
   if (cudaEventElapsedTime(&ms, sev[2], sev[3]) == cudaSuccess) p->info.ms_cell += ms;
@@ -925,6 +1014,24 @@ extern "C" int rb_plan_get_problem(rb_plan *p, int b, double *T, double *xH1, do
   return RB_OK;
 }
 
+extern "C" int rb_plan_get_rec(rb_plan *p, int b, double *H1i, double *He1i, double *He2i,
+                               double *H1h, double *He1h, double *He2h) {
+  if (!p || b < 0 || b >= p->d.n_problems) return RB_ERR_BAD_ARG;
+  const size_t B = p->d.n_problems, Nl = p->d.Nl, NC = B * Nl;
+  double *h = p->hout;  // 12*NC doubles of pinned staging; 6*Nl used
+  for (int f = 0; f < 6; ++f)
+    CK(cudaMemcpyAsync(h + f * Nl, p->drec + f * NC + b * Nl, Nl * 8, cudaMemcpyDeviceToHost,
+                       p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  double *outs[6] = {H1i, He1i, He2i, H1h, He1h, He2h};
+  const bool rev = p->reversed[b];
+  for (int f = 0; f < 6; ++f) {
+    if (!outs[f]) continue;
+    for (size_t i = 0; i < Nl; ++i) outs[f][i] = h[f * Nl + (rev ? Nl - 1 - i : i)];
+  }
+  return RB_OK;
+}
+
 extern "C" void *rb_plan_field_ptr(rb_plan *p, int field) {
   if (!p || field < 0 || field > 11) return nullptr;
   const size_t NC = cells(p);
@@ -942,9 +1049,12 @@ extern "C" int rb_plan_sync(rb_plan *p) {
 // ---------------------------------------------------------------------------
 // host-pointer entry points (the f2py boundary)
 // ---------------------------------------------------------------------------
-static int check_fits(int i_rec_meth, int i_photo_fit, int i_rate_fit) {
-  if (i_rec_meth < 1 || i_rec_meth > 4) return RB_ERR_BAD_ARG;
-  if (i_rec_meth != 1 || i_photo_fit != 1 || i_rate_fit != 1) return RB_ERR_UNSUPPORTED;
+// i_rec_meth: spheres {1 fixed, 2 outward, 3 radial, 4 isotropic} (sphere_base.py:84-91),
+// slabs {1 fixed, 2 ray} (slab_base.py:97-100); only Verner 96 / Hui-Gnedin 97 fits exist
+static int check_fits(int geom, int i_rec_meth, int i_photo_fit, int i_rate_fit) {
+  const bool sphere = geom == RB_GEOM_SPHERE_BGND || geom == RB_GEOM_SPHERE_STROMGREN;
+  if (i_rec_meth < 1 || i_rec_meth > (sphere ? 4 : 2)) return RB_ERR_BAD_ARG;
+  if (i_photo_fit != 1 || i_rate_fit != 1) return RB_ERR_UNSUPPORTED;
   return RB_OK;
 }
 
@@ -972,12 +1082,18 @@ static int plan_acquire(rb_plan **out, const rb_plan_desc &d) {
     for (size_t i = 0; i < g_cache.size(); ++i) {
       rb_plan *p = g_cache[i];
       if (p->d.geometry == d.geometry && p->d.n_problems == d.n_problems && p->d.Nl == d.Nl &&
-          p->d.Nnu == d.Nnu && p->d.Nmu == d.Nmu && p->d.device == dev) {
+          p->d.Nnu == d.Nnu && p->d.Nmu == d.Nmu && p->d.device == dev &&
+          p->rec_meth == (d.i_rec_meth == 0 ? 1 : d.i_rec_meth)) {
         g_cache.erase(g_cache.begin() + i);
         p->d.i_find_Teq = d.i_find_Teq; p->d.fixed_fcA = d.fixed_fcA; p->d.tol = d.tol;
         p->d.max_sweeps = d.max_sweeps;
-        p->P.find_Teq = d.i_find_Teq; p->P.max_sweeps = d.max_sweeps; p->P.fcA = d.fixed_fcA;
+        p->P.find_Teq = d.i_find_Teq; p->P.max_sweeps = d.max_sweeps;
+        p->P.fcA = (p->rec_meth == 1) ? d.fixed_fcA : 1.0;
         p->P.tol = d.tol; p->P.tol_inner = d.tol * RB_TOL_FRAC;
+        {
+          const bool unset = d.em_fac[0] == 0.0 && d.em_fac[1] == 0.0 && d.em_fac[2] == 0.0;
+          for (int X = 0; X < 3; ++X) p->K.em_fac[X] = unset ? 1.0 : d.em_fac[X];
+        }
         *out = p;
         return RB_OK;
       }
@@ -1014,12 +1130,15 @@ extern "C" void rb_cache_clear(void) {
 static int solve_one(int geom, const double *Edges, const double *nH, const double *nHe,
                      double *T, int Nmu, const double *E_eV, const double *shape,
                      double fixed_fcA, int i_find_Teq, int i_thin, double z, double Hz,
-                     double tol, int Nl, int Nnu, double *outs[17], rb_info *info) {
+                     double tol, int Nl, int Nnu, double *outs[17], rb_info *info,
+                     int i_rec_meth = 1, const double *em_fac = nullptr) {
   const auto t0 = std::chrono::steady_clock::now();
   rb_plan_desc d;
   memset(&d, 0, sizeof(d));
   d.geometry = geom; d.n_problems = 1; d.Nl = Nl; d.Nnu = Nnu; d.Nmu = Nmu;
   d.i_find_Teq = i_find_Teq; d.fixed_fcA = fixed_fcA; d.tol = tol; d.device = -1;
+  d.i_rec_meth = i_rec_meth;
+  for (int X = 0; X < 3; ++X) d.em_fac[X] = em_fac ? em_fac[X] : 1.0;
   rb_plan *p = nullptr;
   int rc = plan_acquire(&p, d);
   if (rc) return rc;
@@ -1038,9 +1157,8 @@ static int solve_one(int geom, const double *Edges, const double *nH, const doub
     // the two-sided slabs mirror T unconditionally.
     rc = rb_plan_get_problem(p, 0, T, outs[0], outs[1], outs[2], outs[3], outs[4], outs[5],
                              outs[6], outs[7], outs[11], outs[12], outs[13], nullptr);
-    const int rec_idx[6] = {8, 9, 10, 14, 15, 16};  // *_rec outputs are zero for rec_meth=fixed
-    for (int q = 0; q < 6; ++q)
-      if (outs[rec_idx[q]]) memset(outs[rec_idx[q]], 0, sizeof(double) * (size_t)Nl);
+    if (!rc)  // *_rec outputs (zeros for rec_meth = fixed)
+      rc = rb_plan_get_rec(p, 0, outs[8], outs[9], outs[10], outs[14], outs[15], outs[16]);
   }
   if (info) {
     *info = p->info;
@@ -1065,12 +1183,12 @@ extern "C" int rb_sphere_bgnd_solve(
     double *xHe2, double *xHe3, double *H1i_src, double *He1i_src, double *He2i_src,
     double *H1i_rec, double *He1i_rec, double *He2i_rec, double *H1h_src, double *He1h_src,
     double *He2h_src, double *H1h_rec, double *He1h_rec, double *He2h_rec, rb_info *info) {
-  (void)em_H1_fac; (void)em_He1_fac; (void)em_He2_fac;
-  int rc = check_fits(i_rec_meth, i_photo_fit, i_rate_fit);
+  const double em_fac[3] = {em_H1_fac, em_He1_fac, em_He2_fac};
+  int rc = check_fits(RB_GEOM_SPHERE_BGND, i_rec_meth, i_photo_fit, i_rate_fit);
   if (rc) return rc;
   PACK17;
   return solve_one(RB_GEOM_SPHERE_BGND, Edges, nH, nHe, T, Nmu, E_eV, shape, fixed_fcA,
-                   i_find_Teq, i_thin, z, Hz, tol, Nl, Nnu, outs, info);
+                   i_find_Teq, i_thin, z, Hz, tol, Nl, Nnu, outs, info, i_rec_meth, em_fac);
 }
 
 extern "C" int rb_sphere_stromgren_solve(
@@ -1081,12 +1199,12 @@ extern "C" int rb_sphere_stromgren_solve(
     double *xHe2, double *xHe3, double *H1i_src, double *He1i_src, double *He2i_src,
     double *H1i_rec, double *He1i_rec, double *He2i_rec, double *H1h_src, double *He1h_src,
     double *He2h_src, double *H1h_rec, double *He1h_rec, double *He2h_rec, rb_info *info) {
-  (void)em_H1_fac; (void)em_He1_fac; (void)em_He2_fac;
-  int rc = check_fits(i_rec_meth, i_photo_fit, i_rate_fit);
+  const double em_fac[3] = {em_H1_fac, em_He1_fac, em_He2_fac};
+  int rc = check_fits(RB_GEOM_SPHERE_STROMGREN, i_rec_meth, i_photo_fit, i_rate_fit);
   if (rc) return rc;
   PACK17;
   return solve_one(RB_GEOM_SPHERE_STROMGREN, Edges, nH, nHe, T, Nmu, E_eV, shape, fixed_fcA,
-                   i_find_Teq, i_thin, z, Hz, tol, Nl, Nnu, outs, info);
+                   i_find_Teq, i_thin, z, Hz, tol, Nl, Nnu, outs, info, i_rec_meth, em_fac);
 }
 
 extern "C" int rb_slab_bgnd_solve(
@@ -1097,11 +1215,11 @@ extern "C" int rb_slab_bgnd_solve(
     double *He2i_src, double *H1i_rec, double *He1i_rec, double *He2i_rec, double *H1h_src,
     double *He1h_src, double *He2h_src, double *H1h_rec, double *He1h_rec, double *He2h_rec,
     rb_info *info) {
-  int rc = check_fits(i_rec_meth, i_photo_fit, i_rate_fit);
+  int rc = check_fits(RB_GEOM_SLAB_BGND, i_rec_meth, i_photo_fit, i_rate_fit);
   if (rc) return rc;
   PACK17;
   return solve_one(RB_GEOM_SLAB_BGND, Edges, nH, nHe, T, 0, E_eV, shape, fixed_fcA, i_find_Teq,
-                   i_thin, z, Hz, tol, Nl, Nnu, outs, info);
+                   i_thin, z, Hz, tol, Nl, Nnu, outs, info, i_rec_meth);
 }
 
 extern "C" int rb_slab_plane_solve(
@@ -1112,12 +1230,12 @@ extern "C" int rb_slab_plane_solve(
     double *H1i_src, double *He1i_src, double *He2i_src, double *H1i_rec, double *He1i_rec,
     double *He2i_rec, double *H1h_src, double *He1h_src, double *He2h_src, double *H1h_rec,
     double *He1h_rec, double *He2h_rec, rb_info *info) {
-  int rc = check_fits(i_rec_meth, i_photo_fit, i_rate_fit);
+  int rc = check_fits(RB_GEOM_SLAB_PLANE_1, i_rec_meth, i_photo_fit, i_rate_fit);
   if (rc) return rc;
   PACK17;
   return solve_one(i_2side == 1 ? RB_GEOM_SLAB_PLANE_2 : RB_GEOM_SLAB_PLANE_1, Edges, nH, nHe,
                    T, 0, E_eV, shape, fixed_fcA, i_find_Teq, i_thin, z, Hz, tol, Nl, Nnu, outs,
-                   info);
+                   info, i_rec_meth);
 }
 
 // ---------------------------------------------------------------------------

@@ -47,7 +47,9 @@ struct PlanDev {
   const double *nH, *nHe;  // [B][Nl]
   double *T;               // [B][Nl]
   double *x[5];            // xH1,xH2,xHe1,xHe2,xHe3  [B][Nl]
-  double *src[6];          // H1i,He1i,He2i,H1h,He1h,He2h  [B][Nl]
+  double *src[6];          // H1i,He1i,He2i,H1h,He1h,He2h  [B][Nl]  (source photons)
+  double *rec[6];          // the same six rates from recombination photons (zero for
+                           // rec_meth = fixed; rb_rec.cuh otherwise)
   double *conv_old;        // [B][Nl]
   double4 *pack;           // [B][Nl+1+kPackPad]
   const double *spec;      // [B][Nnu][9]
@@ -633,9 +635,10 @@ k_cell_solve(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_local)
   if (j >= n_local) return;
   const int il = cell_start + j * cell_stride;
   const size_t c = (size_t)b * P.Nl + il;
-  PhotoRates p;
-  p.H1i = P.src[0][c]; p.He1i = P.src[1][c]; p.He2i = P.src[2][c];
-  p.H1h = P.src[3][c]; p.He1h = P.src[4][c]; p.He2h = P.src[5][c];
+  PhotoRates p;  // total = source + recombination photons (sphere_bgnd.f90:861-881)
+  p.H1i = P.src[0][c] + P.rec[0][c]; p.He1i = P.src[1][c] + P.rec[1][c];
+  p.He2i = P.src[2][c] + P.rec[2][c]; p.H1h = P.src[3][c] + P.rec[3][c];
+  p.He1h = P.src[4][c] + P.rec[4][c]; p.He2h = P.src[5][c] + P.rec[5][c];
   const double nH = P.nH[c], nHe = P.nHe[c];
   rb_frac_t x;
   double T = P.T[c];
@@ -661,7 +664,10 @@ k_cell_solve(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_local)
     P.x[3][cm] = x.xHe2; P.x[4][cm] = x.xHe3;
     P.T[cm] = T;
 #pragma unroll
-    for (int q = 0; q < 6; ++q) P.src[q][cm] = P.src[q][c];
+    for (int q = 0; q < 6; ++q) {
+      P.src[q][cm] = P.src[q][c];
+      P.rec[q][cm] = P.rec[q][c];  // slab_bgnd.f90:842-865
+    }
   }
 }
 
@@ -691,9 +697,10 @@ k_cell_solve_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_l
   const int lane = threadIdx.x & 31, gbase = lane & ~(G - 1);
   const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
   const size_t c = (size_t)b * P.Nl + il;
-  PhotoRates p;
-  p.H1i = P.src[0][c]; p.He1i = P.src[1][c]; p.He2i = P.src[2][c];
-  p.H1h = P.src[3][c]; p.He1h = P.src[4][c]; p.He2h = P.src[5][c];
+  PhotoRates p;  // total = source + recombination photons (sphere_bgnd.f90:861-881)
+  p.H1i = P.src[0][c] + P.rec[0][c]; p.He1i = P.src[1][c] + P.rec[1][c];
+  p.He2i = P.src[2][c] + P.rec[2][c]; p.H1h = P.src[3][c] + P.rec[3][c];
+  p.He1h = P.src[4][c] + P.rec[4][c]; p.He2h = P.src[5][c] + P.rec[5][c];
   const double nH = P.nH[c], nHe = P.nHe[c];
   const double z = P.zHz[2 * b], Hz = P.zHz[2 * b + 1];
   const CaseA fc = {P.fcA, P.fcA, P.fcA};
@@ -773,7 +780,10 @@ k_cell_solve_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_l
     P.x[3][cm] = xo.xHe2; P.x[4][cm] = xo.xHe3;
     P.T[cm] = Tfinal;
 #pragma unroll
-    for (int q = 0; q < 6; ++q) P.src[q][cm] = P.src[q][c];
+    for (int q = 0; q < 6; ++q) {
+      P.src[q][cm] = P.src[q][c];
+      P.rec[q][cm] = P.rec[q][c];  // slab_bgnd.f90:842-865
+    }
   }
 }
 

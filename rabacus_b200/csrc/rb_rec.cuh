@@ -1,0 +1,446 @@
+// rb_rec.cuh -- recombination-photon transfer (rec_meth != fixed), SURVEY 8f-1.
+//
+// Every sweep of the reference first evaluates, from the pre-sweep state, the
+// photo-ionisation / heating rates that ground-state recombination photons of
+// H II, He II and He III add in every cell, then solves the cells with case-A
+// rates and (source + recombination) photo-rates:
+//   sphere_bgnd.f90:686-735,861-881; sphere_stromgren.f90:713-757,805-843;
+//   slab_bgnd.f90:653-672,752-808; slab_plane.f90:657-676,716-753,974-993.
+// Kernels here (each cites the routine it restates):
+//   k_rec_prep        emission coefficients, shell fluxes, opacities per cell
+//   k_rec_outward     sphere_base.f90:79-346   one thread per solve layer
+//   k_rec_radial      sphere_base.f90:392-750  one thread per solve layer
+//   k_rec_iso_rays    sphere_base.f90:800-1083 one thread per (cell, ray)
+//   k_rec_iso_finish  angle average + rates
+//   k_rec_slab        slab_base.f90:163-560    one thread per layer
+// Index orientation: the sphere routines work on a fixed orientation (outward
+// and isotropic: index 0 = outermost shell; radial: index 0 = innermost) and the
+// reference reverses the arrays on entry when the caller's differ
+// (reverse_arrays, sphere_base.f90:1404-1452); here routine index i maps to plan
+// cell (flip ? Nl-1-i : i), which keeps every running sum in the reference's
+// order.  SphereBgnd plans are stored outermost-first, SphereStromgren plans
+// innermost-first (rb_plan_set_problem).
+#pragma once
+#include "rb_kernels.cuh"
+
+namespace rb {
+
+// cross sections at the three thresholds (sphere_base.f90:224-236) + thresholds
+struct RecConst {
+  double sH1_H1, sH1_He1, sH1_He2, sHe1_He1, sHe1_He2, sHe2_He2;
+  double E_th[3];
+  double em_fac[3];
+};
+
+// per-cell scratch, all [B][Nl] in PLAN orientation
+struct RecDev {
+  double *em[3];    // emission coefficients (isotropic: already times em_fac)
+  double *F0[3];    // flux leaving the shell (outward / radial)
+  double *dtau[3];  // threshold optical depths through the shell (outward / radial / slab)
+  double *r_c;      // shell centre
+  double4 *recA;    // isotropic: [B][Nl+1] {E^2, dk_EH1, dk_EHe1, dk_EHe2}, index 0 = outermost
+  double4 *recB;    // isotropic: [B][Nl+1] {em_EH1, em_EHe1, em_EHe2, 0}
+  double4 *Iray;    // isotropic: [B][Nl][Nmu] specific intensities per ray
+  double *tlo;      // slabs: [B][3][Nl+1] optical depth below each edge at the 3 line energies
+  double *rec[6];   // OUTPUT rates H1i, He1i, He2i, H1h, He1h, He2h  [B][Nl]
+};
+
+__device__ __forceinline__ bool plan_outer_first(int geom) { return geom == RB_GEOM_SPHERE_BGND; }
+
+// ---------------------------------------------------------------------------
+// k_rec_prep: one thread per (problem, cell).
+// ---------------------------------------------------------------------------
+__global__ void k_rec_prep(PlanDev P, RecDev R, RecConst K, int rec_meth) {
+  const int b = blockIdx.y;
+  if (!P.active[b]) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Nl = P.Nl;
+  const bool sphere = (P.geom == RB_GEOM_SPHERE_BGND || P.geom == RB_GEOM_SPHERE_STROMGREN);
+  const double *E = P.Edges + (size_t)b * (Nl + 1);
+  if (sphere && rec_meth == 4 && i == Nl) {  // innermost edge record (routine index Nl)
+    const double Ee = plan_outer_first(P.geom) ? E[Nl] : E[0];
+    R.recA[(size_t)b * (Nl + 1) + Nl] = make_double4(Ee * Ee, 0.0, 0.0, 0.0);
+    R.recB[(size_t)b * (Nl + 1) + Nl] = make_double4(0.0, 0.0, 0.0, 0.0);
+  }
+  if (i >= Nl) return;
+  const size_t c = (size_t)b * Nl + i;
+  const double nH = P.nH[c], nHe = P.nHe[c], T = P.T[c];
+  const double xH1 = P.x[0][c], xH2 = P.x[1][c], xHe1 = P.x[2][c], xHe2 = P.x[3][c],
+               xHe3 = P.x[4][c];
+  // case A - case B = recombinations to the ground state (sphere_base.f90:238-262)
+  const rb_kchem_t kA = get_kchem(T, 1.0, 1.0, 1.0);
+  const rb_kchem_t kB = get_kchem(T, 0.0, 0.0, 0.0);
+  const double reH2_1 = kA.reH2 - kB.reH2, reHe2_1 = kA.reHe2 - kB.reHe2,
+               reHe3_1 = kA.reHe3 - kB.reHe3;
+  const double ne = xH2 * nH + (xHe2 + 2.0 * xHe3) * nHe;  // :267
+  double em[3];
+  em[0] = (reH2_1 * nH * xH2 * ne) / (4.0 * RB_PI);   // :269-271
+  em[1] = (reHe2_1 * nHe * xHe2 * ne) / (4.0 * RB_PI);
+  em[2] = (reHe3_1 * nHe * xHe3 * ne) / (4.0 * RB_PI);
+  if (sphere && rec_meth == 4) {
+    // :878-892, :935-937 ; records in the routine's orientation (0 = outermost)
+    const int k = plan_outer_first(P.geom) ? i : Nl - 1 - i;
+    const double Ek = plan_outer_first(P.geom) ? E[i] : E[i + 1];  // outer edge of the shell
+    const double kH1_H1 = nH * xH1 * K.sH1_H1, kHe1_H1 = nH * xH1 * K.sH1_He1,
+                 kHe2_H1 = nH * xH1 * K.sH1_He2, kHe1_He1 = nHe * xHe1 * K.sHe1_He1,
+                 kHe2_He1 = nHe * xHe1 * K.sHe1_He2, kHe2_He2 = nHe * xHe2 * K.sHe2_He2;
+    R.recA[(size_t)b * (Nl + 1) + k] =
+        make_double4(Ek * Ek, kH1_H1, kHe1_H1 + kHe1_He1, kHe2_H1 + kHe2_He1 + kHe2_He2);
+    R.recB[(size_t)b * (Nl + 1) + k] =
+        make_double4(em[0] * K.em_fac[0], em[1] * K.em_fac[1], em[2] * K.em_fac[2], 0.0);
+    return;
+  }
+  const double Ei = E[i], Ej = E[i + 1];
+  double dl;
+  if (sphere) {
+    dl = fabs(Ei - Ej);                       // sphere_base.f90:1534
+    const double r_c = (Ei + Ej) * 0.5;       // :1535
+    const double area = 4.0 * RB_PI * r_c * r_c;                                    // :220
+    const double vol = fabs(4.0 / 3.0 * RB_PI * (Ei * Ei * Ei - Ej * Ej * Ej));     // :221
+    R.r_c[c] = r_c;
+    for (int X = 0; X < 3; ++X) R.F0[X][c] = em[X] * 4.0 * RB_PI * vol / area;      // :281-283
+  } else {
+    dl = Ej - Ei;                             // slab_base.f90:250
+    R.r_c[c] = dl;
+  }
+  const double dNH = dl * nH, dNHe = dl * nHe;
+  R.dtau[0][c] = dNH * xH1 * P.sigma_th[0];   // :216-218
+  R.dtau[1][c] = dNHe * xHe1 * P.sigma_th[1];
+  R.dtau[2][c] = dNHe * xHe2 * P.sigma_th[2];
+  for (int X = 0; X < 3; ++X) R.em[X][c] = em[X];
+}
+
+// one recombining layer (sphere_base.f90:275-307): the three fluxes
+struct RecRatios {
+  double a0, b0, b1, c0, c1, c2;  // sigma_X(E_Y,th) / sigma_X,th
+};
+__device__ __forceinline__ RecRatios rec_ratios(const PlanDev &P, const RecConst &K) {
+  RecRatios q;
+  q.a0 = K.sH1_H1 / P.sigma_th[0];
+  q.b0 = K.sH1_He1 / P.sigma_th[0]; q.b1 = K.sHe1_He1 / P.sigma_th[1];
+  q.c0 = K.sH1_He2 / P.sigma_th[0]; q.c1 = K.sHe1_He2 / P.sigma_th[1];
+  q.c2 = K.sHe2_He2 / P.sigma_th[2];
+  return q;
+}
+__device__ __forceinline__ void rec_add_layer(const RecRatios &q, const double (&tau)[3], double g,
+                                              double fac, double F0a, double F0b, double F0c,
+                                              double (&F)[3]) {
+  double t = tau[0] * q.a0;
+  F[0] = F[0] + fac * F0a * g * exp(-t);
+  t = tau[0] * q.b0 + tau[1] * q.b1;
+  F[1] = F[1] + fac * F0b * g * exp(-t);
+  t = tau[0] * q.c0 + tau[1] * q.c1 + tau[2] * q.c2;
+  F[2] = F[2] + fac * F0c * g * exp(-t);
+}
+// sphere_base.f90:311-333
+__device__ __forceinline__ void rec_store_flux_rates(const RecDev &R, const RecConst &K, size_t c,
+                                                     const double (&F)[3]) {
+  R.rec[0][c] = F[0] * K.sH1_H1 + F[1] * K.sH1_He1 + F[2] * K.sH1_He2;
+  R.rec[1][c] = F[1] * K.sHe1_He1 + F[2] * K.sHe1_He2;
+  R.rec[2][c] = F[2] * K.sHe2_He2;
+  double h = F[1] * (K.E_th[1] - K.E_th[0]) * K.sH1_He1 + F[2] * (K.E_th[2] - K.E_th[0]) * K.sH1_He2;
+  R.rec[3][c] = h * RB_EV_2_ERG;
+  h = F[1] * K.sHe1_He1 + F[2] * K.sHe1_He2;  // sic (no energy factor in the reference)
+  R.rec[4][c] = h * RB_EV_2_ERG;
+  R.rec[5][c] = 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// k_rec_outward (sphere_base.f90:79-346): routine index 0 = outermost shell; each
+// solve layer collects the flux of the layers at smaller radii.
+// ---------------------------------------------------------------------------
+__global__ void k_rec_outward(PlanDev P, RecDev R, RecConst K) {
+  const int b = blockIdx.y;
+  if (!P.active[b]) return;
+  const int isl = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Nl = P.Nl;
+  if (isl >= Nl) return;
+  const bool flip = !plan_outer_first(P.geom);
+  const size_t base = (size_t)b * Nl;
+#define RIX(i) (base + (flip ? Nl - 1 - (i) : (i)))
+  const RecRatios q = rec_ratios(P, K);
+  double tau[3] = {0.0, 0.0, 0.0}, F[3] = {0.0, 0.0, 0.0};
+  const double rs = R.r_c[RIX(isl)];
+  for (int irl = isl; irl < Nl; ++irl) {
+    const size_t ci = RIX(irl);
+#pragma unroll
+    for (int X = 0; X < 3; ++X) {  // :249-266
+      if (irl <= isl + 1) {
+        tau[X] = tau[X] + R.dtau[X][ci] * 0.5;
+      } else {
+        tau[X] = tau[X] + R.dtau[X][RIX(irl - 1)] * 0.5;
+        tau[X] = tau[X] + R.dtau[X][ci] * 0.5;
+      }
+    }
+    const double rr = R.r_c[ci] / rs;
+    rec_add_layer(q, tau, rr * rr, 1.0, R.F0[0][ci], R.F0[1][ci], R.F0[2][ci], F);
+  }
+  rec_store_flux_rates(R, K, RIX(isl), F);
+#undef RIX
+}
+
+// ---------------------------------------------------------------------------
+// k_rec_radial (sphere_base.f90:392-750): routine index 1 = innermost shell
+// (1-based as in the Fortran); "lower" leg runs isl, isl-1, .., 1, then through the
+// centre -1, .., -Nl; "upper" leg isl .. Nl; each contribution weighs one half.
+// ---------------------------------------------------------------------------
+__global__ void k_rec_radial(PlanDev P, RecDev R, RecConst K) {
+  const int b = blockIdx.y;
+  if (!P.active[b]) return;
+  const int isl1 = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int Nl = P.Nl;
+  if (isl1 > Nl) return;
+  const bool flip = plan_outer_first(P.geom);
+  const size_t base = (size_t)b * Nl;
+#define RIX1(i1) (base + (flip ? Nl - (i1) : (i1)-1))
+  const RecRatios q = rec_ratios(P, K);
+  double tau[3] = {0.0, 0.0, 0.0}, F[3] = {0.0, 0.0, 0.0};
+  const double rs = R.r_c[RIX1(isl1)];
+  for (int il = isl1; il >= -Nl; --il) {  // :558-617
+    if (il == 0) continue;
+    const int irl1 = il < 0 ? -il : il;
+    const size_t ci = RIX1(irl1);
+#pragma unroll
+    for (int X = 0; X < 3; ++X) {
+      if (irl1 == isl1 || irl1 == isl1 - 1) {
+        tau[X] = tau[X] + R.dtau[X][ci] * 0.5;
+      } else if (irl1 < isl1 - 1) {
+        tau[X] = tau[X] + R.dtau[X][RIX1(irl1 + 1)] * 0.5;
+        tau[X] = tau[X] + R.dtau[X][ci] * 0.5;
+      }
+    }
+    const double rr = R.r_c[ci] / rs;
+    rec_add_layer(q, tau, rr * rr, 0.5, R.F0[0][ci], R.F0[1][ci], R.F0[2][ci], F);
+  }
+  tau[0] = tau[1] = tau[2] = 0.0;
+  for (int irl1 = isl1; irl1 <= Nl; ++irl1) {  // :625-684
+    const size_t ci = RIX1(irl1);
+#pragma unroll
+    for (int X = 0; X < 3; ++X) {
+      if (irl1 <= isl1 + 1) {
+        tau[X] = tau[X] + R.dtau[X][ci] * 0.5;
+      } else {
+        tau[X] = tau[X] + R.dtau[X][ci] * 0.5;
+        tau[X] = tau[X] + R.dtau[X][RIX1(irl1 - 1)] * 0.5;
+      }
+    }
+    const double rr = R.r_c[ci] / rs;
+    rec_add_layer(q, tau, rr * rr, 0.5, R.F0[0][ci], R.F0[1][ci], R.F0[2][ci], F);
+  }
+  rec_store_flux_rates(R, K, RIX1(isl1), F);
+#undef RIX1
+}
+
+// ---------------------------------------------------------------------------
+// k_rec_iso_rays (sphere_base.f90:966-1016): one thread per (cell, ray).  Lanes
+// are consecutive cells of one direction (near-equal ray lengths, broadcast
+// record reads).  Along the ray, from the cell outwards:
+//     tau_E += ds dk_E(shell) ;  I_E += em_E(shell) ds exp(-tau_E)
+// for the three threshold energies.  Segment lengths as in the column kernel
+// (geometry.f90:146-165): shell k < m: |s_{k+1} - s_k|, tangent shell m: 2 s_m,
+// first segment halved.  mu <= 0: shells il, il+1, .., m, m-1, .., 0;
+// mu > 0: il, il-1, .., 0.
+// ---------------------------------------------------------------------------
+struct IsoAcc {
+  double tau[3], I[3];
+};
+__device__ __forceinline__ void iso_step(IsoAcc &a, double ds, const double4 &ka, const double4 &kb,
+                                         unsigned s_exp_lane) {
+  a.tau[0] = a.tau[0] + ds * ka.y;
+  a.tau[1] = a.tau[1] + ds * ka.z;
+  a.tau[2] = a.tau[2] + ds * ka.w;
+  a.I[0] = a.I[0] + kb.x * ds * exp_nonpos(-a.tau[0], s_exp_lane);
+  a.I[1] = a.I[1] + kb.y * ds * exp_nonpos(-a.tau[1], s_exp_lane);
+  a.I[2] = a.I[2] + kb.z * ds * exp_nonpos(-a.tau[2], s_exp_lane);
+}
+
+__global__ void __launch_bounds__(128) k_rec_iso_rays(PlanDev P, RecDev R, int Nmu) {
+  const int b = blockIdx.z;
+  if (!P.active[b]) return;
+  __shared__ double s_exp[kExpTabEntries * kExpTabCopies];
+  fill_exp_table(s_exp);
+  __syncthreads();
+  const unsigned s_exp_lane = (unsigned)__cvta_generic_to_shared(s_exp) +
+                              ((threadIdx.x & (kExpTabCopies - 1)) << 3);
+  const int il = blockIdx.x * blockDim.x + threadIdx.x;  // routine index, 0 = outermost
+  const int imu = blockIdx.y;
+  const int Nl = P.Nl;
+  if (il >= Nl) return;
+  const double4 *ka = R.recA + (size_t)b * (Nl + 1);
+  const double4 *kb = R.recB + (size_t)b * (Nl + 1);
+  const double mu = P.mu[imu];
+  // the edges themselves (not their squares) define r and p: read them from the plan
+  const double *E = P.Edges + (size_t)b * (Nl + 1);
+  const bool of = plan_outer_first(P.geom);
+  const double Ea = of ? E[il] : E[Nl - il], Eb = of ? E[il + 1] : E[Nl - il - 1];
+  const double r_ray = (Ea + Eb) * 0.5;
+  const double p_ray = r_ray * sqrt(1.0 - mu * mu);
+  const double p2 = p_ray * p_ray;
+  // m_for_ray (geometry.f90:61-71) on the outermost-first edges
+  const double E_in = of ? E[Nl] : E[0];
+  if (E_in > p_ray) {
+    atomicMax(&P.err[b], RB_ERR_RAY_GEOMETRY);
+    return;
+  }
+  int lo = 1, hi = Nl;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const double Em = of ? E[mid] : E[Nl - mid];
+    if (Em <= p_ray) hi = mid; else lo = mid + 1;
+  }
+  const int m = lo - 1;
+  IsoAcc a;
+  a.tau[0] = a.tau[1] = a.tau[2] = 0.0;
+  a.I[0] = a.I[1] = a.I[2] = 0.0;
+  int k_out;          // first shell of the outward leg
+  double s_hi;        // s at the inner edge of that shell (s_{k_out+1}), unused when k_out == m
+  bool first = true;
+  if (mu <= 0.0) {
+    // inward leg: shells il .. m
+    double s_k = sqrt_pos(ka[il].x - p2);
+    for (int k = il; k <= m; ++k) {
+      double ds, s_n = 0.0;
+      if (k < m) {
+        s_n = sqrt_pos(ka[k + 1].x - p2);
+        ds = fabs(s_n - s_k);
+      } else {
+        ds = 2.0 * s_k;
+      }
+      if (first) { ds = ds * 0.5; first = false; }
+      iso_step(a, ds, ka[k], kb[k], s_exp_lane);
+      if (k < m) s_k = s_n;
+    }
+    k_out = m - 1;
+    s_hi = s_k;  // = s_m
+  } else {
+    k_out = il;
+    s_hi = (il < m) ? sqrt_pos(ka[il + 1].x - p2) : 0.0;
+  }
+  // outward leg: shells k_out .. 0
+  for (int k = k_out; k >= 0; --k) {
+    const double s_k = sqrt_pos(ka[k].x - p2);
+    double ds = (k == m) ? 2.0 * s_k : fabs(s_hi - s_k);
+    if (first) { ds = ds * 0.5; first = false; }
+    iso_step(a, ds, ka[k], kb[k], s_exp_lane);
+    s_hi = s_k;
+  }
+  R.Iray[((size_t)b * Nl + il) * Nmu + imu] = make_double4(a.I[0], a.I[1], a.I[2], 0.0);
+}
+
+// angle average J = (1/2) sum_mu I w (sphere_base.f90:1020-1032) and the rates (:1037-1061)
+__global__ void k_rec_iso_finish(PlanDev P, RecDev R, RecConst K, int Nmu) {
+  const int b = blockIdx.y;
+  if (!P.active[b]) return;
+  const int il = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Nl = P.Nl;
+  if (il >= Nl) return;
+  double J[3] = {0.0, 0.0, 0.0};
+  const double4 *I = R.Iray + ((size_t)b * Nl + il) * Nmu;
+  for (int imu = 0; imu < Nmu; ++imu) {
+    const double4 v = I[imu];
+    const double w = P.wmu[imu];
+    J[0] = J[0] + v.x * w; J[1] = J[1] + v.y * w; J[2] = J[2] + v.z * w;
+  }
+  J[0] = J[0] * 0.5; J[1] = J[1] * 0.5; J[2] = J[2] * 0.5;
+  const size_t c = (size_t)b * Nl + (plan_outer_first(P.geom) ? il : Nl - 1 - il);
+  R.rec[0][c] = (J[0] * K.sH1_H1 + J[1] * K.sH1_He1 + J[2] * K.sH1_He2) * 4.0 * RB_PI;
+  R.rec[1][c] = (J[1] * K.sHe1_He1 + J[2] * K.sHe1_He2) * 4.0 * RB_PI;
+  R.rec[2][c] = (J[2] * K.sHe2_He2) * 4.0 * RB_PI;
+  double h = (J[1] * (K.E_th[1] - K.E_th[0]) * K.sH1_He1 +
+              J[2] * (K.E_th[2] - K.E_th[0]) * K.sH1_He2) * 4.0 * RB_PI;
+  R.rec[3][c] = h * RB_EV_2_ERG;
+  h = (J[1] * K.sHe1_He1 + J[2] * K.sHe1_He2) * 4.0 * RB_PI;
+  R.rec[4][c] = h * RB_EV_2_ERG;
+  R.rec[5][c] = 0.0;
+}
+
+// slab_base.f90:344-366: tau_X_lo(k) = tau_X_lo(k-1) + sum_Y dtau_Y,th(k-1) ra_Y(E_X), a
+// sequential running sum per line energy (one thread each, Nl dependent adds)
+__global__ void k_rec_slab_prefix(PlanDev P, RecDev R, RecConst K) {
+  const int b = blockIdx.x, X = threadIdx.x;
+  if (!P.active[b] || X > 2) return;
+  const int Nl = P.Nl;
+  const size_t base = (size_t)b * Nl;
+  double *t = R.tlo + ((size_t)b * 3 + X) * (Nl + 1);
+  const double r0 = (X == 0) ? 1.0 : (X == 1 ? K.sH1_He1 / K.sH1_H1 : K.sH1_He2 / K.sH1_H1);
+  const double r1 = (X == 1) ? 1.0 : K.sHe1_He2 / K.sHe1_He1;
+  double acc = 0.0;
+  t[0] = acc;
+  for (int k = 1; k <= Nl; ++k) {
+    if (X == 0) acc = acc + R.dtau[0][base + k - 1] * r0;
+    else if (X == 1) acc = acc + R.dtau[0][base + k - 1] * r0 + R.dtau[1][base + k - 1] * r1;
+    else acc = acc + R.dtau[0][base + k - 1] * r0 + R.dtau[1][base + k - 1] * r1 +
+               R.dtau[2][base + k - 1] * 1.0;
+    t[k] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k_rec_slab (slab_base.f90:163-560): one thread per layer k.  Optical depths at
+// the three recombination energies from the layer centre to every edge, E1
+// kernels on the edges, trapezoid rule over the edges below and above.
+// The running trapezoid sums are accumulated walking away from the layer (the
+// reference fills J_int first and sums from edge 0 upwards: same terms, the
+// lower sum in the opposite order).
+// ---------------------------------------------------------------------------
+__global__ void k_rec_slab(PlanDev P, RecDev R, RecConst K) {
+  const int b = blockIdx.y;
+  if (!P.active[b]) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Nl = P.Nl;
+  if (k >= Nl) return;
+  const size_t base = (size_t)b * Nl;
+  const double *E = P.Edges + (size_t)b * (Nl + 1);
+  double J[3];
+#pragma unroll
+  for (int X = 0; X < 3; ++X) {
+    const double *tl = R.tlo + ((size_t)b * 3 + X) * (Nl + 1);
+    // optical depth through layer i at this line energy, as the reference forms it
+    auto dtau_at = [&](int i) { return tl[i + 1] - tl[i]; };
+    auto em_edge = [&](int e) {  // :378-392
+      if (e == 0) return R.em[X][base] * 0.5;
+      if (e == Nl) return R.em[X][base + Nl - 1] * 0.5;
+      return (R.em[X][base + e - 1] + R.em[X][base + e]) * 0.5;
+    };
+    const double tau0 = dtau_at(k) * 0.5;
+    const double dl = R.r_c[base + k];
+    double Jlo = dl * R.em[X][base + k] * e1xa(tau0) * 0.5;  // :404-405
+    double Jhi = Jlo;
+    if (k != 0) {  // :411-421
+      double tau = tau0;
+      double y_hi = em_edge(k) * e1xa(tau);
+      double ss = 0.0;
+      for (int i = k - 1; i >= 0; --i) {
+        tau = tau + dtau_at(i);
+        const double y_lo = em_edge(i) * e1xa(tau);
+        ss = ss + (y_hi + y_lo) * (E[i + 1] - E[i]);
+        y_hi = y_lo;
+      }
+      Jlo = Jlo + 0.5 * ss;
+    }
+    if (k != Nl - 1) {  // :425-435
+      double tau = tau0;
+      double y_lo = em_edge(k + 1) * e1xa(tau);
+      double ss = 0.0;
+      for (int i = k + 1; i <= Nl - 1; ++i) {
+        tau = tau + dtau_at(i);
+        const double y_hi = em_edge(i + 1) * e1xa(tau);
+        ss = ss + (y_hi + y_lo) * (E[i + 1] - E[i]);
+        y_lo = y_hi;
+      }
+      Jhi = Jhi + 0.5 * ss;
+    }
+    J[X] = (Jlo + Jhi) * 4.0 * RB_PI * 0.5;  // :544-552
+  }
+  const size_t c = base + k;
+  // :556-572
+  R.rec[0][c] = J[2] * K.sH1_He2 + J[1] * K.sH1_He1 + J[0] * K.sH1_H1;
+  R.rec[1][c] = J[2] * K.sHe1_He2 + J[1] * K.sHe1_He1;
+  R.rec[2][c] = J[2] * K.sHe2_He2;
+  R.rec[3][c] = J[2] * (K.E_th[2] - K.E_th[0]) * K.sH1_He2 * RB_EV_2_ERG +
+                J[1] * (K.E_th[1] - K.E_th[0]) * K.sH1_He1 * RB_EV_2_ERG;
+  R.rec[4][c] = J[2] * (K.E_th[2] - K.E_th[0]) * K.sHe1_He2 * RB_EV_2_ERG;  // sic
+  R.rec[5][c] = 0.0;
+}
+
+}  // namespace rb

@@ -24,6 +24,7 @@ _DP = C.POINTER(C.c_double)
 
 FIELDS = ("xH1", "xH2", "xHe1", "xHe2", "xHe3", "T", "H1i_src", "He1i_src", "He2i_src",
           "H1h_src", "He1h_src", "He2h_src")
+REC_FIELDS = ("H1i_rec", "He1i_rec", "He2i_rec", "H1h_rec", "He1h_rec", "He2h_rec")
 
 
 def _p(a):
@@ -32,10 +33,11 @@ def _p(a):
 
 class Plan(object):
     def __init__(self, geometry, n_problems, Nl, Nnu, Nmu=0, find_Teq=False, fixed_fcA=1.0,
-                 tol=1.0e-4, device=-1, max_sweeps=0):
+                 tol=1.0e-4, device=-1, max_sweeps=0, i_rec_meth=1, em_fac=(1.0, 1.0, 1.0)):
         self.desc = rb_plan_desc(int(geometry), int(n_problems), int(Nl), int(Nnu), int(Nmu),
                                  1 if find_Teq else 0, float(fixed_fcA), float(tol),
-                                 int(device), int(max_sweeps))
+                                 int(device), int(max_sweeps), int(i_rec_meth),
+                                 (C.c_double * 3)(*[float(v) for v in em_fac]))
         self._h = C.c_void_p()
         check(lib().rb_plan_create(C.byref(self._h), C.byref(self.desc)))
         self.n_problems, self.Nl, self.Nnu, self.Nmu = n_problems, Nl, Nnu, Nmu
@@ -121,6 +123,9 @@ class Plan(object):
         check(lib().rb_plan_get_problem(self._h, C.c_int(b), *[_p(outs[k]) for k in order],
                                         C.byref(it)))
         outs["iters"] = it.value
+        rec = {k: np.zeros(self.Nl) for k in REC_FIELDS}
+        check(lib().rb_plan_get_rec(self._h, C.c_int(b), *[_p(rec[k]) for k in REC_FIELDS]))
+        outs.update(rec)
         return outs
 
     # ------------------------------------------------------------------ torch interop

@@ -10,19 +10,22 @@ OUT17 = ("xH1", "xH2", "xHe1", "xHe2", "xHe3", "H1i_src", "He1i_src", "He2i_src"
          "H1h_rec", "He1h_rec", "He2h_rec")
 CHECKED = ("xH1", "xH2", "xHe1", "xHe2", "xHe3", "T", "H1i_src", "He1i_src", "He2i_src",
            "H1h_src", "He1h_src", "He2h_src")
+CHECKED_REC = CHECKED + ("H1i_rec", "He1i_rec", "He2i_rec", "H1h_rec", "He1h_rec")
 
 
 def run_oracle(orc, cfg, tol=1e-4, max_sweeps=0, order=None, thin=False, flavour=0):
     g = cfg["geometry"]
     kw = dict(fixed_fcA=cfg["fixed_fcA"], i_find_Teq=1 if cfg["find_Teq"] else 0,
               i_thin=1 if thin else 0, z=cfg["z"], Hz=cfg.get("Hz", 0.0), tol=tol,
-              max_sweeps=max_sweeps, flavour=flavour)
+              max_sweeps=max_sweeps, flavour=flavour, i_rec_meth=cfg.get("i_rec_meth", 1))
     a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"])
+    em = cfg.get("em_fac", (1.0, 1.0, 1.0))
     if g == "sphere_bgnd":
-        return orc.sphere_bgnd_solve(*a, cfg["Nmu"], cfg["E_eV"], cfg["shape"],
+        return orc.sphere_bgnd_solve(*a, cfg["Nmu"], cfg["E_eV"], cfg["shape"], em_fac=em,
                                      order=orc.ORDER_JACOBI if order is None else order, **kw)
     if g == "sphere_stromgren":
-        return orc.sphere_stromgren_solve(*a, 1, cfg["E_eV"], cfg["shape"], **kw)
+        return orc.sphere_stromgren_solve(*a, max(1, cfg["Nmu"]), cfg["E_eV"], cfg["shape"],
+                                          em_fac=em, **kw)
     if g == "slab_bgnd":
         return orc.slab_bgnd_solve(*a, cfg["E_eV"], cfg["shape"], **kw)
     return orc.slab_plane_solve(*a, cfg["E_eV"], cfg["shape"],
@@ -35,7 +38,8 @@ def run_gpu(cfg, tol=1e-4, max_sweeps=0, thin=False):
     Nl, Nnu = cfg["nH"].size, cfg["E_eV"].size
     plan = Plan(configs.GEOM_IDS[cfg["geometry"]], 1, Nl, Nnu, cfg["Nmu"],
                 find_Teq=cfg["find_Teq"], fixed_fcA=cfg["fixed_fcA"], tol=tol,
-                max_sweeps=max_sweeps)
+                max_sweeps=max_sweeps, i_rec_meth=cfg.get("i_rec_meth", 1),
+                em_fac=cfg.get("em_fac", (1.0, 1.0, 1.0)))
     plan.set_problem(0, cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], cfg["E_eV"],
                      cfg["shape"], cfg["z"], cfg.get("Hz", 0.0))
     plan.upload()
@@ -84,7 +88,9 @@ def compare(res_gpu, res_orc, names=CHECKED, rtol=1e-10, tol=1e-4):
             r = np.abs(a - b) / np.abs(b)
         r = np.where(a == b, 0.0, r)
         worst[n] = float(np.nanmax(r))
-        bound = frac_rtol(tol, rtol) if n in FRACTIONS else rtol
+        # recombination-photon rates are linear in the emitting ions' fractions
+        # (em_X = alpha_1 n x_ion ne, sphere_base.f90:269-271): same policy as fractions
+        bound = frac_rtol(tol, rtol) if (n in FRACTIONS or n.endswith("_rec")) else rtol
         if not worst[n] <= bound:
             bad[n] = worst[n]
     return worst, bad

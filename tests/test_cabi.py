@@ -67,9 +67,15 @@ def test_argument_checks_happen_before_the_device_is_touched():
     args = [np.linspace(0, 1e22, Nl + 1), np.full(Nl, 1e-3), np.full(Nl, 1e-4), np.full(Nl, 1e4),
             4, np.array([13.6, 20.]), np.ones(2) * 1e-22, 3, 1.0, 1, 1, 0, 0, 1., 1., 1., 0.0, 0.0,
             1e-4, Nl, 2]
-    with pytest.raises(RabacusB200Error) as e:   # rec_meth = radial is a SURVEY 8(f) "next" row
+    args[9] = 2                                   # photo fits other than Verner 96 do not exist
+    with pytest.raises(RabacusB200Error) as e:
         fc.sphere_bgnd.sphere_bgnd_solve(*args)
     assert e.value.code == 9
+    args[9] = 1
+    args[7] = 5                                   # rec_meth outside {fixed, outward, radial, isotropic}
+    with pytest.raises(RabacusB200Error) as e:
+        fc.sphere_bgnd.sphere_bgnd_solve(*args)
+    assert e.value.code == 8
     args[7] = 1
     args[3] = np.full(Nl, 1e4, dtype=np.float32)  # f2py intent(inout) needs float64
     with pytest.raises(TypeError):
@@ -89,6 +95,7 @@ def test_host_helpers_match_oracle(orc):
 
 
 def test_struct_layouts_match_header():
-    # rb_info: 2 ints, 6 doubles, 1 long long ; rb_plan_desc: 6 ints, 2 doubles, 2 ints
-    assert C.sizeof(_lib.rb_info) == 8 + 6 * 8 + 8
-    assert C.sizeof(_lib.rb_plan_desc) == 24 + 16 + 8
+    # rb_info: 2 ints, 7 doubles, 1 long long ; rb_plan_desc: 6 ints, 2 doubles, 3 ints
+    # (+ padding), 3 doubles
+    assert C.sizeof(_lib.rb_info) == 8 + 7 * 8 + 8
+    assert C.sizeof(_lib.rb_plan_desc) == 24 + 16 + 16 + 24

@@ -16,7 +16,7 @@ Protocol:
 import numpy as np
 import pytest
 
-from helpers import CHECKED, compare, frac_rtol, run_gpu, run_oracle
+from helpers import CHECKED, CHECKED_REC, compare, frac_rtol, run_gpu, run_oracle
 from rabacus_b200 import configs
 
 pytestmark = pytest.mark.gpu
@@ -308,8 +308,12 @@ def test_errors_are_exceptions(spec128):
         fc.sphere_bgnd.sphere_bgnd_solve(*args(bad, 1))
     assert e.value.code == 1
     with pytest.raises(RabacusB200Error) as e:
-        fc.sphere_bgnd.sphere_bgnd_solve(*args(cfg["Edges"].copy(), 4))
-    assert e.value.code == 9
+        fc.sphere_bgnd.sphere_bgnd_solve(*args(cfg["Edges"].copy(), 5))
+    assert e.value.code == 8
+    # the hollow sphere also trips the ray geometry of the isotropic photon transfer
+    with pytest.raises(RabacusB200Error) as e:
+        fc.sphere_bgnd.sphere_bgnd_solve(*args(np.linspace(1.0, 2.0, 17) * 3e21, 4))
+    assert e.value.code == 7
     # hollow sphere: innermost edge > impact parameter of some ray (geometry.f90:61-71)
     hollow = np.linspace(1.0, 2.0, 17) * 3e21
     with pytest.raises(RabacusB200Error) as e:
@@ -379,3 +383,59 @@ def test_cell_sharded_sweeps_equal_single_sweep(spec128):
         plan.close()
     for n in CHECKED:
         assert np.array_equal(outs[0][n], outs[1][n]), n
+
+
+# ----------------------------------------------------------------- recombination photons
+@pytest.mark.parametrize("meth", [2, 3, 4])
+@pytest.mark.parametrize("find_Teq", [False, True])
+def test_sphere_bgnd_recombination_photons(orc, spec128, meth, find_Teq):
+    """rec_meth = outward / radial / isotropic (sphere_base.f90:79-1083) inside the
+    SphereBgnd sweep: case-A rates, total = source + recombination photo-rates."""
+    cfg = _small_sphere(64, 128, 8, find_Teq, nH0=1.0, spec=spec128)
+    cfg["i_rec_meth"] = meth
+    cfg["em_fac"] = (1.0, 0.7, 1.3) if meth == 4 else (1.0, 1.0, 1.0)
+    for kw in (dict(max_sweeps=1), dict(max_sweeps=3), dict()):
+        g = run_gpu(cfg, **kw)
+        o = run_oracle(orc, cfg, **kw)
+        assert g["iters"] == o["iters"], kw
+        worst, bad = compare(g, o, names=CHECKED_REC)
+        assert not bad, (meth, kw, bad)
+        assert float(np.max(o["H1i_rec"])) > 0.0
+
+
+@pytest.mark.parametrize("meth", [2, 3, 4])
+def test_stromgren_recombination_photons(orc, meth):
+    """The same three methods on the innermost-first orientation (SphereStromgren),
+    including input given with decreasing Edges."""
+    cfg = configs.c1_iliev_stromgren(64)
+    cfg["i_rec_meth"] = meth
+    cfg["Nmu"] = 8
+    g = run_gpu(cfg)
+    o = run_oracle(orc, cfg)
+    assert g["iters"] == o["iters"]
+    worst, bad = compare(g, o, names=CHECKED_REC)
+    assert not bad, (meth, bad)
+    rev = dict(cfg)
+    for k in ("Edges", "nH", "nHe", "T"):
+        rev[k] = cfg[k][::-1].copy()
+    g2 = run_gpu(rev)
+    for n in CHECKED_REC:
+        assert np.array_equal(g2[n][::-1], g[n]), n
+
+
+@pytest.mark.parametrize("geom", ["slab_plane_1", "slab_plane_2", "slab_bgnd"])
+@pytest.mark.parametrize("find_Teq", [False, True])
+def test_slab_recombination_photons(orc, geom, find_Teq):
+    """rec_meth = "ray" for the slabs (slab_base.f90:163-560): E1 kernels on the
+    layer edges, trapezoid rule below and above every layer."""
+    if geom == "slab_bgnd":
+        cfg = configs.c3_slab_bgnd(96, 128, find_Teq)
+    else:
+        cfg = configs.c2_slab_plane(96, 128, find_Teq, geom == "slab_plane_2")
+    cfg["i_rec_meth"] = 2
+    for kw in (dict(max_sweeps=2), dict()):
+        g = run_gpu(cfg, **kw)
+        o = run_oracle(orc, cfg, **kw)
+        assert g["iters"] == o["iters"], kw
+        worst, bad = compare(g, o, names=CHECKED_REC)
+        assert not bad, (geom, kw, bad)

@@ -271,7 +271,7 @@ def test_oracle_errors(orc, spec128):
         orc.sphere_bgnd_solve(hollow, cfg["nH"], cfg["nHe"], cfg["T"], 4, *spec128)
     with pytest.raises(orc.OracleError, match="unsupported"):
         orc.sphere_bgnd_solve(cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], 4, *spec128,
-                              i_rec_meth=4)
+                              i_rec_meth=5)
 
 
 def test_analytic_monochromatic_slab(orc):
@@ -324,3 +324,45 @@ def test_iliev_test1_stromgren_radius(orc):
     r_half = np.interp(0.5, r.xH1, r_c)
     # Iliev+06 test 1: r_S = (3 Ndot / (4 pi alpha_B nH^2))^(1/3) = 5.4 kpc
     assert 5.0 < r_half < 5.8
+
+
+# ----------------------------------------------------------------- recombination photons
+def test_recombination_photons_orientation_invariance(orc, spec128):
+    """The three sphere methods reverse their inputs on entry when the caller's
+    orientation differs (sphere_base.f90:1404-1452): solving with increasing or
+    decreasing Edges must give the same cells bit for bit."""
+    cfg = _sphere(24, 4, spec=spec128)
+    for meth in (2, 3, 4):
+        a = orc.sphere_bgnd_solve(cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], 4, *spec128,
+                                  i_rec_meth=meth, order=orc.ORDER_JACOBI, max_sweeps=3)
+        b = orc.sphere_bgnd_solve(cfg["Edges"][::-1], cfg["nH"][::-1], cfg["nHe"][::-1],
+                                  cfg["T"][::-1], 4, *spec128, i_rec_meth=meth,
+                                  order=orc.ORDER_JACOBI, max_sweeps=3)
+        for n in ("xH1", "H1i_rec", "He1i_rec", "H1h_rec", "H1i_src"):
+            assert np.array_equal(a[n], b[n][::-1]), (meth, n)
+        assert np.all(a["H1i_rec"] > 0.0) and np.all(a["He2h_rec"] == 0.0)
+
+
+def test_recombination_photons_physical_limits(orc, spec128):
+    """Known limits of the photon-transfer closures: (i) with rec_meth != fixed the
+    chemistry runs with case-A rates, so switching the recombination emission off
+    (isotropic, em_fac = 0) must equal rec_meth = fixed with fixed_fcA = 1;
+    (ii) in a slab the diffuse field raises the H I photo-rate everywhere, and the
+    neutral fraction drops relative to case A without transfer."""
+    cfg = _sphere(24, 4, spec=spec128)
+    a = orc.sphere_bgnd_solve(cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], 4, *spec128,
+                              i_rec_meth=4, em_fac=(0.0, 0.0, 0.0), order=orc.ORDER_JACOBI)
+    b = orc.sphere_bgnd_solve(cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], 4, *spec128,
+                              i_rec_meth=1, fixed_fcA=1.0, order=orc.ORDER_JACOBI)
+    assert a["iters"] == b["iters"]
+    for n in ("xH1", "xHe1", "xHe2", "H1i_src", "H1h_src"):
+        assert np.array_equal(a[n], b[n]), n
+    from rabacus_b200 import configs
+    c2 = configs.c2_slab_plane(48, 128, False, True)
+    a = orc.slab_plane_solve(c2["Edges"], c2["nH"], c2["nHe"], c2["T"], c2["E_eV"], c2["shape"],
+                             i_2side=1, i_rec_meth=2, z=3.0)
+    b = orc.slab_plane_solve(c2["Edges"], c2["nH"], c2["nHe"], c2["T"], c2["E_eV"], c2["shape"],
+                             i_2side=1, i_rec_meth=1, fixed_fcA=1.0, z=3.0)
+    assert np.all(a["H1i_rec"] > 0.0)
+    assert np.all(a["xH1"] <= b["xH1"] * (1 + 1e-12))
+    assert np.array_equal(a["xH1"], a["xH1"][::-1])     # mirrored halves (SURVEY Q12)
