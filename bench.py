@@ -401,9 +401,17 @@ def main():
         k["tflops"] = 2.0 * k["alg_ops"] / (k["ms"] * 1e-3) / 1e12 if k["ms"] > 0 else 0.0
         k["frac"] = k["tflops"] / peak_tflops if peak_tflops > 0 else 0.0
     dom = max(kern, key=lambda n: kern[n]["ms"])
+    traffic = None  # DRAM bytes per launch of that kernel from the committed ncu capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f)["bytes_per_launch"].get(dom) if world == 1 else None
+    except Exception:
+        traffic = None
     roofline = {
         "bound": "fp64", "kernel": dom, "achieved": kern[dom]["tflops"], "peak": peak_tflops,
-        "unit": "TFLOP/s", "frac": kern[dom]["frac"], "traffic": None,
+        "unit": "TFLOP/s", "frac": kern[dom]["frac"], "traffic": traffic,
+        "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + "
+                          "dram__bytes_write.sum per launch; the 33.5 MB ray buffer stays in L2)",
         "peak_source": "measured in this run: DFMA micro-benchmark (rb_microbench), "
                        "MEASURED_PEAKS.json has no FP64 figure",
         "ms_per_launch": kern[dom]["ms"],
