@@ -159,7 +159,7 @@ static void build_spec_table(int geom, const double *E, const double *shape, int
                              const double sigma_th[3], double *tab, double *thin) {
   const int kind = source_kind(geom);
   const double four_pi = 4.0 * RB_PI;
-  for (int q = 0; q < 6; ++q) thin[q] = 0.0;
+  for (int q = 0; q < kThinStride; ++q) thin[q] = 0.0;
   for (int k = 0; k < Nnu; ++k) {
     double *row = tab + (size_t)k * kSpecStride;
     double wk, base;
@@ -182,6 +182,7 @@ static void build_spec_table(int geom, const double *E, const double *shape, int
       row[6 + X] = yh * wk;
       thin[X] += row[3 + X];
       thin[3 + X] += row[6 + X];
+      thin[6 + X] = std::max(thin[6 + X], row[X]);  // max_nu sigma_X(nu)/sigma_X,th
     }
   }
 }
@@ -304,7 +305,7 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   ALLOC(p->dEdges, B * (Nl + 1) * 8); ALLOC(p->dnH, NC * 8); ALLOC(p->dnHe, NC * 8);
   ALLOC(p->dT, NC * 8); ALLOC(p->dx, 5 * NC * 8); ALLOC(p->dsrc, 6 * NC * 8);
   ALLOC(p->dconv, NC * 8); ALLOC(p->dpack, B * (Nl + 1 + kPackPad) * sizeof(double4));
-  ALLOC(p->dspec, B * Nnu * kSpecStride * 8); ALLOC(p->dthin, B * 6 * 8);
+  ALLOC(p->dspec, B * Nnu * kSpecStride * 8); ALLOC(p->dthin, B * kThinStride * 8);
   ALLOC(p->dmu, 2 * (size_t)std::max(1, d.Nmu) * 8);
   ALLOC(p->dcol, NC * (size_t)p->Ndir * sizeof(double4)); ALLOC(p->dzHz, B * 2 * 8);
   ALLOC(p->dwork, B * sizeof(int));
@@ -327,7 +328,7 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   ALLOC(p->dflags, (3 * B + kSlots) * sizeof(int)); ALLOC(p->dresid, B * 8);
   HALLOC(p->hEdges, B * (Nl + 1) * 8); HALLOC(p->hnH, NC * 8); HALLOC(p->hnHe, NC * 8);
   HALLOC(p->hT, NC * 8); HALLOC(p->hspec, B * Nnu * kSpecStride * 8);
-  HALLOC(p->hthin, B * 6 * 8); HALLOC(p->hzHz, B * 2 * 8); HALLOC(p->hout, 12 * NC * 8);
+  HALLOC(p->hthin, B * kThinStride * 8); HALLOC(p->hzHz, B * 2 * 8); HALLOC(p->hout, 12 * NC * 8);
   HALLOC(p->hflags, (3 * B + kSlots) * sizeof(int));
 #undef ALLOC
 #undef HALLOC
@@ -429,7 +430,7 @@ extern "C" int rb_plan_set_problem(rb_plan *p, int b, const double *Edges, const
     hH[i] = nH[s]; hHe[i] = nHe[s]; hT[i] = T[s];
   }
   build_spec_table(g, E_eV, shape, Nnu, p->sigma_th,
-                   p->hspec + (size_t)b * Nnu * kSpecStride, p->hthin + (size_t)b * 6);
+                   p->hspec + (size_t)b * Nnu * kSpecStride, p->hthin + (size_t)b * kThinStride);
   p->hzHz[2 * b] = z;
   p->hzHz[2 * b + 1] = Hz;
   return RB_OK;
@@ -444,7 +445,7 @@ extern "C" int rb_plan_upload(rb_plan *p) {
   CK(cudaMemcpyAsync(p->dnHe, p->hnHe, NC * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(p->dT, p->hT, NC * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(p->dspec, p->hspec, B * Nnu * kSpecStride * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(p->dthin, p->hthin, B * 6 * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->dthin, p->hthin, B * kThinStride * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(p->dzHz, p->hzHz, B * 2 * 8, cudaMemcpyHostToDevice, s));
   for (size_t b = 0; b < B; ++b) {
     p->hflags[b] = 1; p->hflags[B + b] = 0; p->hflags[2 * B + b] = 0;
@@ -583,33 +584,33 @@ static int launch_nu_rates(rb_plan *p, int cell_start, int cell_stride, int n_lo
   const int B = p->d.n_problems, Nnu = p->d.Nnu, g = p->d.geometry;
   cudaStream_t s = p->stream;
   int rc = RB_OK;
-#define NU(ATT, KU, RU, BLOCK, MINB)                                                         \
+#define NU(ATT, KU, RU, BLOCK, MINB, LTAB)                                                   \
   do {                                                                                       \
     const int ndir_pad = (p->Ndir + RU - 1) / RU * RU;                                       \
-    const size_t smem = (size_t)ndir_pad * sizeof(double4) +                                 \
-                        (ATT ? 0 : kExpTabEntries * kExpTabCopies * sizeof(double));         \
-    rc = set_smem(k_nu_rates<ATT, KU, RU, BLOCK, MINB>, smem);                               \
+    const size_t smem = (size_t)ndir_pad * sizeof(double4);                                  \
+    rc = set_smem(k_nu_rates<ATT, KU, RU, BLOCK, MINB, LTAB>, smem);                         \
     if (rc) return rc;                                                                       \
     int occ = 1;                                                                             \
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_nu_rates<ATT, KU, RU, BLOCK, MINB>, \
-                                                  BLOCK, smem);                              \
-    const int want = p->n_sm * std::max(1, occ);                                             \
-    const int per_problem = std::min(n_local, std::max(1, (want + B - 1) / B));              \
-    dim3 gn(per_problem, B);                                                                 \
-    k_nu_rates<ATT, KU, RU, BLOCK, MINB><<<gn, BLOCK, smem, s>>>(p->P, cell_start,           \
-                                                                 cell_stride, n_local);      \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                           \
+        &occ, k_nu_rates<ATT, KU, RU, BLOCK, MINB, LTAB>, BLOCK, smem);                      \
+    const long long want = (long long)p->n_sm * std::max(1, occ);                            \
+    dim3 gn((unsigned)std::min<long long>(want, (long long)n_local * B));                    \
+    k_nu_rates<ATT, KU, RU, BLOCK, MINB, LTAB><<<gn, BLOCK, smem, s>>>(                      \
+        p->P, cell_start, cell_stride, n_local);                                             \
   } while (0)
   // thread <-> 4 frequencies, 2 rays in flight: 8 independent exp chains per thread
   if (g == RB_GEOM_SLAB_BGND) {
-    if (Nnu <= 32) NU(1, 1, 1, 32, 8);
-    else if (Nnu <= 64) NU(1, 1, 1, 64, 4);
-    else NU(1, 1, 1, 128, 3);
+    if (Nnu <= 32) NU(1, 1, 1, 32, 8, 0);
+    else if (Nnu <= 64) NU(1, 1, 1, 64, 4, 0);
+    else NU(1, 1, 1, 128, 3, 0);
   } else {
     // timed on B200 (profiles/r01_kernel_variants.md): 4 frequencies x 2 rays in flight
-    // for wide grids; one warp per cell, 4 frequencies x 1 ray, 16 warps/SM for Nnu <= 128
-    if (Nnu <= 128) NU(0, 4, 1, 32, 16);
-    else if (Nnu <= 256) NU(0, 4, 2, 64, 6);
-    else NU(0, 4, 2, 128, 4);
+    // for wide grids; one warp per cell, 4 frequencies x 1 ray, 16 warps/SM for Nnu <= 128.
+    // exp table: 256 entries (degree-4 polynomial) where one CTA serves 128 threads,
+    // 64 entries (degree 5) for the small CTAs
+    if (Nnu <= 128) NU(0, 4, 1, 32, 16, 6);
+    else if (Nnu <= 256) NU(0, 4, 2, 64, 6, 6);
+    else NU(0, 4, 2, 128, 4, 8);
   }
 #undef NU
   p->info.n_launches += 1;

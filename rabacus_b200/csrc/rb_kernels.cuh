@@ -37,6 +37,7 @@ typedef RB_FLAG_T rb_flag_t;
 
 constexpr int kPackPad = 8;    // padding records after the Nl+1 shell records
 constexpr int kSpecStride = 9;  // per-frequency table: 3 sigma ratios, 3+3 weights
+constexpr int kThinStride = 9;  // per problem: 6 optically thin integrals, 3 max sigma ratios
 
 // Everything a kernel needs, passed by value.
 struct PlanDev {
@@ -53,7 +54,7 @@ struct PlanDev {
   double *conv_old;        // [B][Nl]
   double4 *pack;           // [B][Nl+1+kPackPad]
   const double *spec;      // [B][Nnu][9]
-  const double *thin;      // [B][6] optically thin integrals (sum of weights)
+  const double *thin;      // [B][9] optically thin integrals (sum of weights), max_nu sigma ratios
   const double *mu, *wmu;  // [Nmu] Gauss-Legendre nodes / weights
   double4 *col;            // [B][Nl][Ndir] per ray {tau_HI,th, tau_HeI,th, tau_HeII,th, quadrature
                            // weight}: one aligned 32-byte sector per ray, written whole by the
@@ -447,55 +448,63 @@ __global__ void __launch_bounds__(BLOCK) k_column_taus(PlanDev P) {
 }
 
 // ---------------------------------------------------------------------------
-// exp(x) for x <= 0 on the FP64 pipe in 10 instructions.
-//   n = rint(x * 64/ln2) = 64 e + j ;  r = x - n ln2/64  (|r| <= ln2/128)
-//   exp(x) = 2^e * 2^(j/64) * (1 + r + r^2/2 + ... + r^5/120)
-// 2^(j/64) comes from a 64-entry table in shared memory that is replicated 16x
-// (entry j, copy c at double index 16 j + c, lane reads copy lane%16) so that a
-// half-warp always hits 16 distinct 8-byte banks whatever j each lane needs.
-// Truncation r^6/720 <= 3.5e-17; total error ~1 ulp (CUDA's exp(): 1 ulp with 16
-// FP64 instructions + ~10 integer / branch).  Below -708 the result (a denormal
-// < 2.3e-308) is flushed to zero.
+// exp() of the hot loops.
 // ---------------------------------------------------------------------------
-constexpr int kExpTabEntries = 64, kExpTabCopies = 16;
+constexpr int kExpTabCopies = 16;
 
-// constants live in constant memory so that DFMA takes them as c[bank][offset]
-// operands (a 64-bit immediate would cost two UMOV per use)
-__constant__ double kExpC[8] = {
-    92.33248261689366,        // 64/ln2
-    -1.0830424696249145e-02,  // -ln2/64 (hi)
-    -3.623510646634843e-19,   // -ln2/64 (lo)
-    8.3333333333333332e-03,   // 1/120
-    4.1666666666666664e-02,   // 1/24
-    1.6666666666666666e-01,   // 1/6
-    0.5, 6755399441055744.0   // 1/2 ; 1.5 * 2^52
-};
+// exp(x) for -708 <= x <= 0 with a 2^L-entry table (L = 6: degree-5 polynomial,
+// L = 8: degree 4), 8 / 7 FP64 instructions + 6 integer / load instructions:
+//   t = x 2^L/ln2 + 1.5 2^52 ; n = low word of t = 2^L e + j ; r = x - n ln2/2^L
+//   exp(x) = 2^e 2^(j/2^L) (1 + r + r^2/2 + ...)
+// The reduction uses the rounded constant ln2/2^L in one fma (error |x| 1.1e-16
+// relative to exp(x), i.e. below 1 ulp wherever exp(x) > 1e-3 and weighted by
+// exp(-|x|) in every sum this feeds); the table is a static __shared__ array (its
+// address is an immediate of the LDS), entry j copy c at double index 16 j + c,
+// `lane_off` = 8 (lane % 16): a half-warp always hits 16 distinct 8-byte banks.
+// Range: x is clamped to >= -708.0 by one unsigned integer min on its high word (for
+// negative doubles the bit pattern grows with the magnitude); exp(-708) = 3e-308 then
+// stands in for values the reference's libm returns as denormals or zero -- neither is
+// visible in any sum this feeds.
+// constants in constant memory: the loop then takes them as c[bank][offset] / uniform
+// register operands instead of rebuilding 64-bit immediates with two moves each
+__constant__ double kExpF6[7] = {92.33248261689366,          // 64/ln2
+                                 -1.0830424696249145e-02,    // -ln2/64
+                                 8.3333333333333332e-03, 4.1666666666666664e-02,
+                                 1.6666666666666666e-01, 0.5, 6755399441055744.0};
+__constant__ double kExpF8[7] = {369.32993046757463,         // 256/ln2
+                                 -2.7076061740622863e-03,    // -ln2/256
+                                 0.0, 4.1666666666666664e-02,
+                                 1.6666666666666666e-01, 0.5, 6755399441055744.0};
 
-__device__ __forceinline__ void fill_exp_table(double *s_exp) {
-  for (int i = threadIdx.x; i < kExpTabEntries * kExpTabCopies; i += blockDim.x)
-    s_exp[i] = exp2((double)(i / kExpTabCopies) * (1.0 / kExpTabEntries));
-}
-
-// s_exp_lane: 32-bit shared-window address of this lane's table copy
-__device__ __forceinline__ double exp_nonpos(double x, unsigned s_exp_lane) {
-  const double t = fma(x, kExpC[0], kExpC[7]);
+template <int L>
+__device__ __forceinline__ double exp_fast(double x, const double *s_tab, unsigned lane_off) {
+  const double *C = (L >= 8) ? kExpF8 : kExpF6;
+  x = __hiloint2double((int)min((unsigned)__double2hiint(x), 0xC0862000u), __double2loint(x));
+  const double t = fma(x, C[0], C[6]);
   const int n = __double2loint(t);
-  const double nd = t - kExpC[7];
-  double r = fma(nd, kExpC[1], x);
-  r = fma(nd, kExpC[2], r);
-  double q = fma(r, kExpC[3], kExpC[4]);
-  q = fma(r, q, kExpC[5]);
-  q = fma(r, q, kExpC[6]);
+  const double nd = t - C[6];
+  const double r = fma(nd, C[1], x);
+  double q;
+  if (L >= 8) {
+    q = fma(r, C[3], C[4]);
+  } else {
+    q = fma(r, C[2], C[3]);
+    q = fma(r, q, C[4]);
+  }
+  q = fma(r, q, C[5]);
   const double r2 = r * r;
   const double pl = fma(r2, q, r);
-  double T;
-  asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(s_exp_lane + ((n & (kExpTabEntries - 1)) << 7)));
+  const unsigned off = ((unsigned)(n << 7) & (unsigned)(((1 << L) - 1) << 7)) | lane_off;
+  const double T = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(s_tab) + off);
   const double v = fma(T, pl, T);
-  // x < -708 (or -inf): the result is below the normal range; it is flushed to
-  // zero (the reference's libm returns a denormal < 2.3e-308 there)
-  const bool under = (unsigned)__double2hiint(x) > 0xC0862000u;
-  return under ? 0.0
-               : __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+  return __hiloint2double(__double2hiint(v) + (n & ~((1 << L) - 1)) * (1 << (20 - L)),
+                          __double2loint(v));
+}
+
+template <int L>
+__device__ __forceinline__ void fill_exp_table_L(double *s_exp) {
+  for (int i = threadIdx.x; i < (1 << L) * kExpTabCopies; i += blockDim.x)
+    s_exp[i] = exp2((double)(i / kExpTabCopies) * (1.0 / (double)(1 << L)));
 }
 
 // ---------------------------------------------------------------------------
@@ -518,26 +527,29 @@ __device__ __forceinline__ double exp_nonpos(double x, unsigned s_exp_lane) {
 // are paid per (cell, nu) instead of per (cell, ray, nu).  Then for SphereBgnd
 //     src <- (src_old + sum)/2             (sphere_bgnd.f90:837-856).
 // Algorithmic FP64 work per (ray, nu): 3 + 10 + 1 = 14 instructions.
-// grid = (CTAs per problem, B); a CTA strides over the problem's local cells.
+// grid = one wave of CTAs striding over the flat list of (problem, local cell).
 // ---------------------------------------------------------------------------
-template <int ATT_E2, int KU, int RU, int BLOCK, int MINB>
+template <int ATT_E2, int KU, int RU, int BLOCK, int MINB, int LTAB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local) {
-  const int b = blockIdx.y;
-  if (!P.active[b]) return;
   extern __shared__ double4 s_dyn4[];
   double4 *s_ray = s_dyn4;                                     // [ndir_pad]
   const int Nnu = P.Nnu, Nl = P.Nl, ndir = P.Ndir;
   const int ndir_pad = (ndir + RU - 1) / RU * RU;
-  double *s_exp = reinterpret_cast<double *>(s_dyn4 + ndir_pad);   // [64][16]
+  __shared__ double s_exp[ATT_E2 ? 1 : (1 << LTAB) * kExpTabCopies];   // [2^LTAB][16]
   __shared__ double s_red[6][BLOCK / 32];
-  if (!ATT_E2) fill_exp_table(s_exp);
-  const unsigned s_exp_lane = (unsigned)__cvta_generic_to_shared(s_exp) +
-                              ((threadIdx.x & (kExpTabCopies - 1)) << 3);
-  const double *spec = P.spec + (size_t)b * Nnu * kSpecStride;
+  if (!ATT_E2) fill_exp_table_L<LTAB>(s_exp);
+  const unsigned lane_off = (threadIdx.x & (kExpTabCopies - 1)) << 3;
+
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
-  for (int j = blockIdx.x; j < n_local; j += gridDim.x) {
+  // the grid is one wave of CTAs striding over the flat list of (problem, local cell):
+  // balanced to one cell whatever the batch size, also while problems drop out
+  const long long total = (long long)P.B * n_local;
+  for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+    const int b = (int)(w / n_local), j = (int)(w % n_local);
+    if (!P.active[b]) continue;
+    const double *spec = P.spec + (size_t)b * Nnu * kSpecStride;
     const int il = cell_start + j * cell_stride;
     const size_t c = (size_t)b * Nl + il;
     __syncthreads();  // previous cell's rays / reduction scratch are no longer read
@@ -570,7 +582,7 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local) {
 #pragma unroll
           for (int u = 0; u < KU; ++u) {
             const double x = fma(ry[r].z, n2[u], fma(ry[r].y, n1[u], ry[r].x * n0[u]));  // -tau
-            const double a = ATT_E2 ? e2xa(-x) : exp_nonpos(x, s_exp_lane);
+            const double a = ATT_E2 ? e2xa(-x) : exp_fast<LTAB>(x, s_exp, lane_off);
             A[u] = fma(ry[r].w, a, A[u]);
           }
         }
@@ -1115,7 +1127,7 @@ RB_LS_UNROLL
       const double r_c = (E[q] + E[q + 1]) * 0.5;
       scale = 1.0 / (4.0 * RB_PI * r_c * r_c);
     }
-    const double *th = P.thin + (size_t)b * 6;
+    const double *th = P.thin + (size_t)b * kThinStride;
     p[i].H1i = th[0] * scale; p[i].He1i = th[1] * scale; p[i].He2i = th[2] * scale;
     p[i].H1h = th[3] * scale; p[i].He1h = th[4] * scale; p[i].He2h = th[5] * scale;
   }

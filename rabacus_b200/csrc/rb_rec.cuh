@@ -245,23 +245,22 @@ struct IsoAcc {
   double tau[3], I[3];
 };
 __device__ __forceinline__ void iso_step(IsoAcc &a, double ds, const double4 &ka, const double4 &kb,
-                                         unsigned s_exp_lane) {
+                                         const double *s_exp, unsigned lane_off) {
   a.tau[0] = a.tau[0] + ds * ka.y;
   a.tau[1] = a.tau[1] + ds * ka.z;
   a.tau[2] = a.tau[2] + ds * ka.w;
-  a.I[0] = a.I[0] + kb.x * ds * exp_nonpos(-a.tau[0], s_exp_lane);
-  a.I[1] = a.I[1] + kb.y * ds * exp_nonpos(-a.tau[1], s_exp_lane);
-  a.I[2] = a.I[2] + kb.z * ds * exp_nonpos(-a.tau[2], s_exp_lane);
+  a.I[0] = a.I[0] + kb.x * ds * exp_fast<6>(-a.tau[0], s_exp, lane_off);
+  a.I[1] = a.I[1] + kb.y * ds * exp_fast<6>(-a.tau[1], s_exp, lane_off);
+  a.I[2] = a.I[2] + kb.z * ds * exp_fast<6>(-a.tau[2], s_exp, lane_off);
 }
 
 __global__ void __launch_bounds__(128) k_rec_iso_rays(PlanDev P, RecDev R, int Nmu) {
   const int b = blockIdx.z;
   if (!P.active[b]) return;
-  __shared__ double s_exp[kExpTabEntries * kExpTabCopies];
-  fill_exp_table(s_exp);
+  __shared__ double s_exp[64 * kExpTabCopies];
+  fill_exp_table_L<6>(s_exp);
   __syncthreads();
-  const unsigned s_exp_lane = (unsigned)__cvta_generic_to_shared(s_exp) +
-                              ((threadIdx.x & (kExpTabCopies - 1)) << 3);
+  const unsigned lane_off = (threadIdx.x & (kExpTabCopies - 1)) << 3;
   const int il = blockIdx.x * blockDim.x + threadIdx.x;  // routine index, 0 = outermost
   const int imu = blockIdx.y;
   const int Nl = P.Nl;
@@ -307,7 +306,7 @@ __global__ void __launch_bounds__(128) k_rec_iso_rays(PlanDev P, RecDev R, int N
         ds = 2.0 * s_k;
       }
       if (first) { ds = ds * 0.5; first = false; }
-      iso_step(a, ds, ka[k], kb[k], s_exp_lane);
+      iso_step(a, ds, ka[k], kb[k], s_exp, lane_off);
       if (k < m) s_k = s_n;
     }
     k_out = m - 1;
@@ -321,7 +320,7 @@ __global__ void __launch_bounds__(128) k_rec_iso_rays(PlanDev P, RecDev R, int N
     const double s_k = sqrt_pos(ka[k].x - p2);
     double ds = (k == m) ? 2.0 * s_k : fabs(s_hi - s_k);
     if (first) { ds = ds * 0.5; first = false; }
-    iso_step(a, ds, ka[k], kb[k], s_exp_lane);
+    iso_step(a, ds, ka[k], kb[k], s_exp, lane_off);
     s_hi = s_k;
   }
   R.Iray[((size_t)b * Nl + il) * Nmu + imu] = make_double4(a.I[0], a.I[1], a.I[2], 0.0);
