@@ -40,12 +40,12 @@ METRIC = "SphereBgnd cell*ray*freq evals/s"
 UNIT = "evals/s"
 
 # algorithmic FP64-pipe operations (DESIGN.md "Roofline"):
-#   frequency kernel, per (cell, ray, nu): 3 (tau = sum_X tau_X ra_X) + 10 (exp:
-#   scale, round, 2 reduce, 5 polynomial, 1 table merge) + 1 (A(nu) += w_ray a); the six
-#   rate accumulations are per (cell, nu), 1/Nmu of that, and are not counted
+#   frequency kernel, per (cell, ray, nu): 3 (tau = sum_X tau_X ra_X) + 8 (exp: scale,
+#   round, reduce, 4 polynomial, table merge) + 1 (A(nu) += w_ray a); the six rate
+#   accumulations are per (cell, nu), 1/Nmu of that, and are not counted
 #   column kernel, per ray segment: 1 (E^2 - p^2) + 5 (sqrt: MUFU seed + one
 #   third-order correction) + 1 (ds) + 3 (column FMAs)
-OPS_PER_EVAL = 14
+OPS_PER_EVAL = 12
 OPS_PER_SEGMENT = 10
 
 

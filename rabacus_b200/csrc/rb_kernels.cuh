@@ -503,8 +503,11 @@ __device__ __forceinline__ double exp_fast(double x, const double *s_tab, unsign
 
 template <int L>
 __device__ __forceinline__ void fill_exp_table_L(double *s_exp) {
-  for (int i = threadIdx.x; i < (1 << L) * kExpTabCopies; i += blockDim.x)
-    s_exp[i] = exp2((double)(i / kExpTabCopies) * (1.0 / (double)(1 << L)));
+  for (int j = threadIdx.x; j < (1 << L); j += blockDim.x) {
+    const double v = exp2((double)j * (1.0 / (double)(1 << L)));
+#pragma unroll
+    for (int c = 0; c < kExpTabCopies; ++c) s_exp[j * kExpTabCopies + c] = v;
+  }
 }
 
 // ---------------------------------------------------------------------------
