@@ -219,7 +219,9 @@ struct rb_plan {
   void *peer_base[kMaxPeers] = {nullptr};  // mapped bases (own = dpeer)
   unsigned long long peer_epoch = 0;
   int peer_world = 1;
-  int n_items = 0, items_start = -1, items_stride = -1, n_sm = 148;
+  int n_items = 0, items_start = -1, items_stride = -1, items_chunks = 1, n_sm = 148;
+  double *dpart = nullptr;      // chunk partial sums of the column kernel (nchunk > 1)
+  size_t part_bytes = 0;
   std::vector<double> items_edges;  // problem-0 edges the list was built from
   int *dflags = nullptr;    // active, notconv, iters, err : 4*B, then nactive
   unsigned long long *dresid = nullptr;
@@ -319,7 +321,7 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
       ALLOC(p->drecI, NC * (size_t)d.Nmu * sizeof(double4));
   }
   if (d.geometry == RB_GEOM_SPHERE_BGND)
-    ALLOC(p->ditems, (size_t)((Nl + 31) / 32) * ((d.Nmu + 1) / 2) * sizeof(unsigned));
+    ALLOC(p->ditems, (size_t)((Nl + 31) / 32) * ((d.Nmu + 1) / 2) * 8 * sizeof(unsigned));
   {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -496,17 +498,18 @@ extern "C" int rb_plan_thin(rb_plan *p) {
 // block's innermost cell (longest-processing-time-first).  Built from problem 0's
 // edges (all problems of a plan share the shape; the order is a scheduling
 // heuristic only) and cached until the edges or the cell deal change.
-static int build_items(rb_plan *p, int cell_start, int cell_stride, int n_local) {
+static int build_items(rb_plan *p, int cell_start, int cell_stride, int n_local, int nchunk) {
   const int Nl = p->d.Nl, Nmu = p->d.Nmu;
   const double *E = p->hEdges;  // solver orientation: non-increasing
   if (p->items_start == cell_start && p->items_stride == cell_stride &&
-      p->items_edges.size() == (size_t)Nl + 1 &&
+      p->items_chunks == nchunk && p->items_edges.size() == (size_t)Nl + 1 &&
       memcmp(p->items_edges.data(), E, sizeof(double) * (Nl + 1)) == 0)
     return RB_OK;
   const int nblk = (n_local + 31) / 32, npair = (Nmu + 1) / 2;
-  if (nblk > 0xffff || npair > 0xffff) return RB_ERR_UNSUPPORTED;
+  if (nblk > 0xfff || npair > 0xffff || nchunk > 15) return RB_ERR_UNSUPPORTED;
+  const int Q = (Nl + nchunk - 1) / nchunk;
   std::vector<std::pair<int, unsigned>> v;
-  v.reserve((size_t)nblk * npair);
+  v.reserve((size_t)nblk * npair * nchunk);
   for (int ip = 0; ip < npair; ++ip) {
     const double mu = p->mu[ip];
     const double st = sqrt(1.0 - mu * mu);
@@ -519,7 +522,13 @@ static int build_items(rb_plan *p, int cell_start, int cell_stride, int n_local)
         const int mid = (lo + hi) >> 1;
         if (E[mid] <= pr) hi = mid; else lo = mid + 1;
       }
-      v.emplace_back(-lo, (unsigned)jb | ((unsigned)ip << 16));
+      const int m = lo - 1;
+      for (int c = 0; c < nchunk; ++c) {  // records c*Q .. (c+1)*Q-1, up to m
+        const int len = (nchunk == 1) ? m + 1 : std::min(m, (c + 1) * Q - 1) - std::max(1, c * Q) + 1;
+        // (chunks that are empty for the whole block stay in the list: their lanes store the
+        // zero partials the combine kernel reads)
+        v.emplace_back(-std::max(len, 0), (unsigned)jb | ((unsigned)c << 12) | ((unsigned)ip << 16));
+      }
     }
   }
   std::sort(v.begin(), v.end());
@@ -529,7 +538,7 @@ static int build_items(rb_plan *p, int cell_start, int cell_stride, int n_local)
   CK(cudaMemcpyAsync(p->ditems, items.data(), items.size() * sizeof(unsigned),
                      cudaMemcpyHostToDevice, p->stream));
   CK(cudaStreamSynchronize(p->stream));  // `items` is pageable and dies here
-  p->items_start = cell_start; p->items_stride = cell_stride;
+  p->items_start = cell_start; p->items_stride = cell_stride; p->items_chunks = nchunk;
   p->items_edges.assign(E, E + Nl + 1);
   return RB_OK;
 }
@@ -554,12 +563,36 @@ static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, in
     p->info.n_launches += 2;
     return RB_OK;
   }
-  int rc = build_items(p, cell_start, cell_stride, n_local);
-  if (rc) return rc;
   // 24 warps per SM at <= 80 registers; as many CTAs per SM as the records allow
   int cps = (int)std::min<size_t>(3, kMaxSmem / (smem + 1024));
   const int warps = 24 / cps;
   const int want = p->n_sm * cps;  // CTAs that fill the GPU once
+  // too few rays per launch to keep every warp busy with whole walks (cell shards over many
+  // GPUs, small grids): cut every walk into nchunk pieces (separate work items)
+  int nchunk = 1;
+  {
+    const long long lane_items = (long long)((n_local + 31) / 32) * ((p->d.Nmu + 1) / 2) * B;
+    const long long warps_total = (long long)p->n_sm * 24;
+    while (nchunk < 8 && lane_items * nchunk * 2 < warps_total * 3) nchunk *= 2;
+    const char *cenv = getenv("RB_COLS_CHUNKS");  // testing knob
+    if (cenv && atoi(cenv) >= 1 && atoi(cenv) <= 8) nchunk = atoi(cenv);
+    while (nchunk > 1 && Nl < 8 * nchunk) nchunk /= 2;
+  }
+  int rc = build_items(p, cell_start, cell_stride, n_local, nchunk);
+  if (rc) return rc;
+  if (nchunk > 1) {
+    const size_t need = (size_t)B * ((p->d.Nmu + 1) / 2) * n_local * nchunk * kPartStride * 8;
+    if (need > p->part_bytes) {
+      cudaFree(p->dpart);
+      p->dpart = nullptr; p->part_bytes = 0;
+      if (cudaMalloc((void **)&p->dpart, need) != cudaSuccess) {
+        cudaGetLastError();
+        return RB_ERR_NOMEM;
+      }
+      p->part_bytes = need;
+    }
+  }
+
   const int waves = (B > 1) ? 4 : 1;  // batches: ~4 CTAs per resident slot (finer tail)
   int per_problem = std::max(1, (waves * want + B - 1) / B);
   per_problem = std::min(per_problem, (p->n_items + warps - 1) / warps);
@@ -570,13 +603,20 @@ static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, in
     rc = set_smem(k_sphere_columns_smem<THREADS, 1, MINB>, smem);                            \
     if (rc) return rc;                                                                       \
     k_sphere_columns_smem<THREADS, 1, MINB><<<g, THREADS, smem, s>>>(                        \
-        p->P, cell_start, cell_stride, n_local, p->ditems, p->n_items, p->dwork);            \
+        p->P, cell_start, cell_stride, n_local, p->ditems, p->n_items, p->dwork, nchunk,     \
+        p->dpart);                                                                           \
   } while (0)
   if (cps == 1) COLS(768, 1);
   else if (cps == 2) COLS(384, 2);
   else COLS(256, 3);
 #undef COLS
   p->info.n_launches += 1;
+  if (nchunk > 1) {
+    dim3 gm((n_local + 127) / 128, (p->d.Nmu + 1) / 2, B);
+    k_columns_combine<<<gm, 128, 0, s>>>(p->P, cell_start, cell_stride, n_local, nchunk,
+                                         p->dpart);
+    p->info.n_launches += 1;
+  }
   return RB_OK;
 }
 

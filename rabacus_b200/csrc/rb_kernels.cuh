@@ -217,18 +217,55 @@ __device__ __forceinline__ void col_advance(ColAcc &a, const double4 *__restrict
   }
 }
 
+// +mu / -mu assembly of one ray pair from the sums of its walk (header comment of
+// this section) and the store of its two ray records.
+// tau_X_th = N_X * sigma_X_th   (sphere_bgnd.f90:794-796); 4th slot: GL weight
+__device__ __forceinline__ void store_ray_pair(const PlanDev &P, int b, int il, int ip, int m,
+                                               double mu, const double (&S)[3],
+                                               const double (&A)[3], const double (&d)[3],
+                                               const double (&t)[3]) {
+  const int imu_in = ip, imu_out = P.Nmu - 1 - ip;
+  double Nout[3], Nin[3];
+#pragma unroll
+  for (int X = 0; X < 3; ++X) {
+    if (il == m) {
+      Nout[X] = Nin[X] = S[X] + 0.5 * t[X];
+    } else {
+      Nout[X] = A[X] + 0.5 * d[X];
+      Nin[X] = (2.0 * S[X] - A[X] - 0.5 * d[X]) + t[X];
+    }
+  }
+  if (imu_in == imu_out) {  // odd Nmu: the mu ~ 0 node, both formulas agree
+    const bool inward = (mu <= 0.0);
+    P.col[col_index(P, b, il, imu_in)] =
+        make_double4((inward ? Nin[0] : Nout[0]) * P.sigma_th[0],
+                     (inward ? Nin[1] : Nout[1]) * P.sigma_th[1],
+                     (inward ? Nin[2] : Nout[2]) * P.sigma_th[2], P.wmu[imu_in]);
+  } else {
+    P.col[col_index(P, b, il, imu_in)] = make_double4(
+        Nin[0] * P.sigma_th[0], Nin[1] * P.sigma_th[1], Nin[2] * P.sigma_th[2], P.wmu[imu_in]);
+    P.col[col_index(P, b, il, imu_out)] = make_double4(
+        Nout[0] * P.sigma_th[0], Nout[1] * P.sigma_th[1], Nout[2] * P.sigma_th[2], P.wmu[imu_out]);
+  }
+}
+
 // One (cell il, |mu| pair ip) of SphereBgnd: both rays' threshold optical depths.
 // `pk` = shell records (global or shared), `il_w0` = cell of lane 0 of the warp.
+// nchunk == 1: the whole walk, result stored as two ray records.  nchunk > 1: the
+// walk is cut at the shell records c*Q (Q = ceil(Nl/nchunk)) and this call does
+// chunk `chunk` only, leaving its partial sums {S, A, d, t, has_own} in
+// `part` for k_columns_combine -- finer work items for launches with few rays.
+constexpr int kPartStride = 13;
 template <int U>
 __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il, int il_w0,
                                                 int cell_stride, int ip,
-                                                const double4 *__restrict__ pk, bool store) {
-  const int Nl = P.Nl, Nmu = P.Nmu;
-  const int imu_in = ip;               // xi ascending: negative mu first
-  const int imu_out = Nmu - 1 - ip;
+                                                const double4 *__restrict__ pk, bool store,
+                                                int nchunk = 1, int chunk = 0,
+                                                double *part = nullptr) {
+  const int Nl = P.Nl;
   const double *E = P.Edges + (size_t)b * (Nl + 1);
 
-  const double mu = P.mu[imu_in];
+  const double mu = P.mu[ip];  // xi ascending: negative mu first
   const double r_ray = (E[il] + E[il + 1]) * 0.5;
   const double p_ray = r_ray * sqrt(1.0 - mu * mu);
   const double p2 = p_ray * p_ray;
@@ -247,6 +284,13 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
   }
   const int m = lo - 1;
 
+  // records this call closes segments with: k = kb .. ke (segment k-1 is closed by record k)
+  int kb = 1, ke = m;
+  if (nchunk > 1) {
+    const int Q = (Nl + nchunk - 1) / nchunk;
+    kb = max(1, chunk * Q);
+    ke = min(m, (chunk + 1) * Q - 1);
+  }
   // The lanes of a warp hold cells il_w .. il_w + 31*stride: only records
   // k-1 in that window can be a lane's own shell, so the snapshot test is
   // confined to a warp-uniform sub-range of the loop.
@@ -256,44 +300,32 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
   a.S0 = a.S1 = a.S2 = 0.0;
   a.A0 = a.A1 = a.A2 = 0.0;
   a.d0 = a.d1 = a.d2 = 0.0;
-  a.cur = pk[0];
-  a.s_prev = sqrt_pos(a.cur.x - p2);
-  col_advance<false, U>(a, pk, 1, min(m, kA - 1), il, p2);
-  col_advance<true, U>(a, pk, max(1, kA), min(m, kB), il, p2);
-  col_advance<false, U>(a, pk, max(1, kB + 1), m, il, p2);
-  const double S0 = a.S0, S1 = a.S1, S2 = a.S2, A0 = a.A0, A1 = a.A1, A2 = a.A2;
-  const double d0 = a.d0, d1 = a.d1, d2 = a.d2, s_prev = a.s_prev;
-  const double4 cur = a.cur;
-  // tangent shell m: cur = shell m record, s_prev = s_m
-  const double t0 = 2.0 * s_prev * cur.y;
-  const double t1 = 2.0 * s_prev * cur.z;
-  const double t2 = 2.0 * s_prev * cur.w;
-  double Nout0, Nout1, Nout2, Nin0, Nin1, Nin2;
-  if (il == m) {
-    Nout0 = Nin0 = S0 + 0.5 * t0;
-    Nout1 = Nin1 = S1 + 0.5 * t1;
-    Nout2 = Nin2 = S2 + 0.5 * t2;
-  } else {
-    Nout0 = A0 + 0.5 * d0;
-    Nout1 = A1 + 0.5 * d1;
-    Nout2 = A2 + 0.5 * d2;
-    Nin0 = (2.0 * S0 - A0 - 0.5 * d0) + t0;
-    Nin1 = (2.0 * S1 - A1 - 0.5 * d1) + t1;
-    Nin2 = (2.0 * S2 - A2 - 0.5 * d2) + t2;
+  a.cur = pk[min(kb - 1, Nl)];
+  a.s_prev = (kb - 1 <= m) ? sqrt_pos(a.cur.x - p2) : 0.0;  // s_{kb-1}; beyond m: empty chunk
+  col_advance<false, U>(a, pk, kb, min(ke, kA - 1), il, p2);
+  col_advance<true, U>(a, pk, max(kb, kA), min(ke, kB), il, p2);
+  col_advance<false, U>(a, pk, max(kb, kB + 1), ke, il, p2);
+  const double S[3] = {a.S0, a.S1, a.S2}, A[3] = {a.A0, a.A1, a.A2}, d[3] = {a.d0, a.d1, a.d2};
+  // tangent shell m: after closing with record m, cur = shell m record, s_prev = s_m
+  // (m == 0: nothing is closed, cur = pk[0], s_prev = s_0 from the initialisation)
+  const bool has_tangent = (nchunk == 1) || (ke == m && (kb <= ke || (m == 0 && chunk == 0)));
+  double t[3] = {0.0, 0.0, 0.0};
+  if (has_tangent) {
+    t[0] = 2.0 * a.s_prev * a.cur.y; t[1] = 2.0 * a.s_prev * a.cur.z;
+    t[2] = 2.0 * a.s_prev * a.cur.w;
   }
-  // tau_X_th = N_X * sigma_X_th   (sphere_bgnd.f90:794-796); 4th slot: GL weight
   if (!store) return;
-  if (imu_in == imu_out) {  // odd Nmu: the mu ~ 0 node, both formulas agree
-    const bool inward = (mu <= 0.0);
-    P.col[col_index(P, b, il, imu_in)] =
-        make_double4((inward ? Nin0 : Nout0) * P.sigma_th[0], (inward ? Nin1 : Nout1) * P.sigma_th[1],
-                     (inward ? Nin2 : Nout2) * P.sigma_th[2], P.wmu[imu_in]);
-  } else {
-    P.col[col_index(P, b, il, imu_in)] = make_double4(
-        Nin0 * P.sigma_th[0], Nin1 * P.sigma_th[1], Nin2 * P.sigma_th[2], P.wmu[imu_in]);
-    P.col[col_index(P, b, il, imu_out)] = make_double4(
-        Nout0 * P.sigma_th[0], Nout1 * P.sigma_th[1], Nout2 * P.sigma_th[2], P.wmu[imu_out]);
+  if (nchunk == 1) {
+    store_ray_pair(P, b, il, ip, m, mu, S, A, d, t);
+    return;
   }
+  // own shell closed in this chunk?  (record il+1 in [kb, ke])
+  const bool has_own = (il + 1 >= kb) && (il + 1 <= ke);
+#pragma unroll
+  for (int X = 0; X < 3; ++X) {
+    part[X] = S[X]; part[3 + X] = A[X]; part[6 + X] = d[X]; part[9 + X] = t[X];
+  }
+  part[12] = has_own ? 1.0 : 0.0;
 }
 
 // Fallback for grids whose shell records do not fit in shared memory
@@ -322,12 +354,16 @@ k_sphere_columns(PlanDev P, int cell_start, int cell_stride, int n_local) {
 // drains evenly although ray lengths span 1..Nl shells).  In the segment loop
 // every lane of a warp reads the same record: a shared-memory broadcast instead
 // of an L1 round trip per segment.
-// grid = (CTAs per problem, B); items[it] = jblk | ip << 16.
+// grid = (CTAs per problem, B); items[it] = jblk | chunk << 12 | ip << 16.  With
+// nchunk > 1 (few rays per launch: cell shards over many GPUs, small grids) every
+// walk is cut into nchunk pieces that are separate items; k_columns_combine adds
+// the pieces up in shell order and stores the ray records.
 // ---------------------------------------------------------------------------
 template <int THREADS, int U, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_sphere_columns_smem(PlanDev P, int cell_start, int cell_stride, int n_local,
-                      const unsigned *__restrict__ items, int n_items, int *work) {
+                      const unsigned *__restrict__ items, int n_items, int *work, int nchunk,
+                      double *__restrict__ part) {
   const int b = blockIdx.y;
   if (!P.active[b]) return;
   extern __shared__ double4 s_pk[];
@@ -343,14 +379,60 @@ k_sphere_columns_smem(PlanDev P, int cell_start, int cell_stride, int n_local,
   while (it < n_items) {
     if (lane == 0) nxt = atomicAdd(&work[b], 1);  // in flight while this item is traced
     const unsigned item = items[it];
-    const int jw = (int)(item & 0xffffu) * 32;
+    const int jw = (int)(item & 0xfffu) * 32;
+    const int chunk = (int)((item >> 12) & 0xfu);
     const int ip = (int)(item >> 16);
     const int j = jw + lane;
     const bool valid = j < n_local;
     const int il = cell_start + (valid ? j : n_local - 1) * cell_stride;
-    sphere_ray_pair<U>(P, b, il, cell_start + jw * cell_stride, cell_stride, ip, s_pk, valid);
+    double *pp = nullptr;
+    if (nchunk > 1)
+      pp = part + ((((size_t)b * ((P.Nmu + 1) / 2) + ip) * n_local + (valid ? j : 0)) * nchunk +
+                   chunk) * kPartStride;
+    sphere_ray_pair<U>(P, b, il, cell_start + jw * cell_stride, cell_stride, ip, s_pk, valid,
+                       nchunk, chunk, pp);
     it = __shfl_sync(0xffffffffu, nxt, 0);
   }
+}
+
+// k_columns_combine: one thread per (local cell, |mu| pair): sums the chunk partials in
+// shell order.  A (the sum up to the own shell) = chunks before the one that closed the
+// own shell + that chunk's snapshot.
+__global__ void k_columns_combine(PlanDev P, int cell_start, int cell_stride, int n_local,
+                                  int nchunk, const double *__restrict__ part) {
+  const int b = blockIdx.z;
+  if (!P.active[b]) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ip = blockIdx.y;
+  if (j >= n_local) return;
+  const int il = cell_start + j * cell_stride;
+  const int Nl = P.Nl;
+  const double *E = P.Edges + (size_t)b * (Nl + 1);
+  const double mu = P.mu[ip];
+  const double r_ray = (E[il] + E[il + 1]) * 0.5;
+  const double p_ray = r_ray * sqrt(1.0 - mu * mu);
+  if (E[Nl] > p_ray) return;  // the walk kernel has raised RB_ERR_RAY_GEOMETRY
+  int lo = il + 1, hi = Nl;
+  if (E[il] <= p_ray) lo = 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (E[mid] <= p_ray) hi = mid; else lo = mid + 1;
+  }
+  const int m = lo - 1;
+  const double *pp = part + (((size_t)b * ((P.Nmu + 1) / 2) + ip) * n_local + j) * nchunk *
+                                kPartStride;
+  double S[3] = {0.0, 0.0, 0.0}, A[3] = {0.0, 0.0, 0.0}, d[3] = {0.0, 0.0, 0.0},
+         t[3] = {0.0, 0.0, 0.0};
+  for (int c = 0; c < nchunk; ++c) {
+    const double *q = pp + c * kPartStride;
+    if (q[12] != 0.0) {
+#pragma unroll
+      for (int X = 0; X < 3; ++X) { A[X] = S[X] + q[3 + X]; d[X] = q[6 + X]; }
+    }
+#pragma unroll
+    for (int X = 0; X < 3; ++X) { S[X] = S[X] + q[X]; t[X] = t[X] + q[9 + X]; }
+  }
+  store_ray_pair(P, b, il, ip, m, mu, S, A, d, t);
 }
 
 // ---------------------------------------------------------------------------

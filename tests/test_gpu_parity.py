@@ -211,6 +211,33 @@ def test_sphere_bgnd_hm12_512_frequencies(orc):
     assert not bad, bad
 
 
+def test_c4_full_size_sweeps_match_oracle(orc):
+    """BASELINE.json configs[3] at full size (4096 shells x 512 frequencies x 256 rays):
+    optically thin start + two Jacobi sweeps against the oracle (a few seconds of
+    OpenMP on the host), then size-independent properties of the converged solve:
+    every fraction in [0, 1] and closed per element, neutral fraction rising inwards
+    through the self-shielding transition, source rates bounded by the thin rates."""
+    cfg = configs.c4_sphere_bgnd(4096, 512, 256, False)
+    g = run_gpu(cfg, max_sweeps=2)
+    o = run_oracle(orc, cfg, max_sweeps=2)
+    worst, bad = compare(g, o)
+    assert not bad, bad
+    thin = run_gpu(cfg, thin=True)
+    full = run_gpu(cfg)
+    assert 10 < full["iters"] < 500
+    for a, b_, c in (("xH1", "xH2", None), ("xHe1", "xHe2", "xHe3")):
+        tot = full[a] + full[b_] + (full[c] if c else 0.0)
+        assert np.max(np.abs(tot - 1.0)) < 1e-12
+        assert np.all(full[a] >= 0.0) and np.all(full[a] <= 1.0)
+    # Edges increase outwards in this config: the centre is shielded, the surface is not
+    assert full["xH1"][0] > 0.9 and full["xH1"][-1] < 1e-2
+    for n in ("H1i_src", "He1i_src", "He2i_src", "H1h_src", "He1h_src", "He2h_src"):
+        # SURVEY Q1: the fixed point of src <- (src + sum_mu w rate)/2 is sum_mu w rate
+        # = 2 x the angle mean, so the bound is twice the optically thin rate
+        assert np.all(full[n] <= 2.0 * thin[n] * (1 + 1e-12)), n
+        assert np.all(full[n] >= 0.0)
+
+
 def test_one_shot_entry_point_matches_plan(spec128):
     from rabacus_b200 import rabacus_fc as fc
     cfg = _small_sphere(64, 128, 8, True, spec=spec128)
