@@ -223,6 +223,8 @@ struct rb_plan {
   double *dpart = nullptr;      // chunk partial sums of the column kernel (nchunk > 1)
   size_t part_bytes = 0;
   std::vector<double> items_edges;  // problem-0 edges the list was built from
+  std::vector<double> spec_E, spec_shape;  // spectrum of the last table built (set_problem)
+  int spec_src = -1;                       // problem slot holding that table
   int *dflags = nullptr;    // active, notconv, iters, err : 4*B, then nactive
   unsigned long long *dresid = nullptr;
   // pinned host staging
@@ -431,8 +433,24 @@ extern "C" int rb_plan_set_problem(rb_plan *p, int b, const double *Edges, const
     const int s = rev ? Nl - 1 - i : i;
     hH[i] = nH[s]; hHe[i] = nHe[s]; hT[i] = T[s];
   }
-  build_spec_table(g, E_eV, shape, Nnu, p->sigma_th,
-                   p->hspec + (size_t)b * Nnu * kSpecStride, p->hthin + (size_t)b * kThinStride);
+  // parameter sweeps reuse a handful of spectra over thousands of problems (C5: 16 for
+  // 8192): the per-frequency table (3 Verner cross sections per frequency) is rebuilt only
+  // when the spectrum differs from the one the previous call built
+  double *tab = p->hspec + (size_t)b * Nnu * kSpecStride, *thin = p->hthin + (size_t)b * kThinStride;
+  if (p->spec_src >= 0 && p->spec_E.size() == (size_t)Nnu &&
+      memcmp(p->spec_E.data(), E_eV, sizeof(double) * Nnu) == 0 &&
+      memcmp(p->spec_shape.data(), shape, sizeof(double) * Nnu) == 0) {
+    if (p->spec_src != b) {
+      memcpy(tab, p->hspec + (size_t)p->spec_src * Nnu * kSpecStride,
+             sizeof(double) * Nnu * kSpecStride);
+      memcpy(thin, p->hthin + (size_t)p->spec_src * kThinStride, sizeof(double) * kThinStride);
+    }
+  } else {
+    build_spec_table(g, E_eV, shape, Nnu, p->sigma_th, tab, thin);
+    p->spec_E.assign(E_eV, E_eV + Nnu);
+    p->spec_shape.assign(shape, shape + Nnu);
+  }
+  p->spec_src = b;
   p->hzHz[2 * b] = z;
   p->hzHz[2 * b + 1] = Hz;
   return RB_OK;
