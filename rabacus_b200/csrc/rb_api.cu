@@ -199,7 +199,7 @@ struct rb_plan {
   double *dEdges = nullptr, *dnH = nullptr, *dnHe = nullptr, *dT = nullptr;
   double *dx = nullptr;     // 5*B*Nl
   double *dsrc = nullptr;   // 6*B*Nl
-  double *dconv = nullptr;
+  double *dconv = nullptr, *dkchem = nullptr;
   double4 *dpack = nullptr;
   double *dspec = nullptr, *dthin = nullptr, *dmu = nullptr, *dzHz = nullptr;
   double4 *dcol = nullptr;
@@ -223,8 +223,11 @@ struct rb_plan {
   double *dpart = nullptr;      // chunk partial sums of the column kernel (nchunk > 1)
   size_t part_bytes = 0;
   std::vector<double> items_edges;  // problem-0 edges the list was built from
-  std::vector<double> spec_E, spec_shape;  // spectrum of the last table built (set_problem)
-  int spec_src = -1;                       // problem slot holding that table
+  struct SpecEntry {                       // per-frequency tables of the last 32 distinct
+    std::vector<double> E, shape, tab;     // spectra staged through rb_plan_set_problem
+    double thin[kThinStride];
+  };
+  std::vector<SpecEntry> spec_cache;
   int *dflags = nullptr;    // active, notconv, iters, err : 4*B, then nactive
   unsigned long long *dresid = nullptr;
   // pinned host staging
@@ -247,7 +250,7 @@ static size_t cells(const rb_plan *p) { return (size_t)p->d.n_problems * p->d.Nl
 extern "C" void rb_plan_destroy(rb_plan *p) {
   if (!p) return;
   cudaFree(p->dEdges); cudaFree(p->dnH); cudaFree(p->dnHe); cudaFree(p->dT);
-  cudaFree(p->dx); cudaFree(p->dsrc); cudaFree(p->dconv); cudaFree(p->dpack);
+  cudaFree(p->dx); cudaFree(p->dsrc); cudaFree(p->dconv); cudaFree(p->dkchem); cudaFree(p->dpack);
   cudaFree(p->dspec); cudaFree(p->dthin); cudaFree(p->dmu); cudaFree(p->dcol);
   cudaFree(p->dzHz); cudaFree(p->dflags); cudaFree(p->dresid); cudaFree(p->ditems); cudaFree(p->dwork);
   cudaFreeHost(p->hEdges); cudaFreeHost(p->hnH); cudaFreeHost(p->hnHe); cudaFreeHost(p->hT);
@@ -308,7 +311,7 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   } while (0)
   ALLOC(p->dEdges, B * (Nl + 1) * 8); ALLOC(p->dnH, NC * 8); ALLOC(p->dnHe, NC * 8);
   ALLOC(p->dT, NC * 8); ALLOC(p->dx, 5 * NC * 8); ALLOC(p->dsrc, 6 * NC * 8);
-  ALLOC(p->dconv, NC * 8); ALLOC(p->dpack, B * (Nl + 1 + kPackPad) * sizeof(double4));
+  ALLOC(p->dconv, NC * 8); ALLOC(p->dkchem, 6 * NC * 8); ALLOC(p->dpack, B * (Nl + 1 + kPackPad) * sizeof(double4));
   ALLOC(p->dspec, B * Nnu * kSpecStride * 8); ALLOC(p->dthin, B * kThinStride * 8);
   ALLOC(p->dmu, 2 * (size_t)std::max(1, d.Nmu) * 8);
   ALLOC(p->dcol, NC * (size_t)p->Ndir * sizeof(double4)); ALLOC(p->dzHz, B * 2 * 8);
@@ -362,7 +365,7 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   P.Edges = p->dEdges; P.nH = p->dnH; P.nHe = p->dnHe; P.T = p->dT;
   for (int i = 0; i < 5; ++i) P.x[i] = p->dx + i * NC;
   for (int i = 0; i < 6; ++i) P.src[i] = p->dsrc + i * NC;
-  P.conv_old = p->dconv; P.pack = p->dpack; P.spec = p->dspec; P.thin = p->dthin;
+  P.conv_old = p->dconv; P.kchem = p->dkchem; P.pack = p->dpack; P.spec = p->dspec; P.thin = p->dthin;
   P.mu = p->dmu; P.wmu = p->dmu + std::max(1, d.Nmu); P.col = p->dcol; P.zHz = p->dzHz;
   if (d.geometry == RB_GEOM_SPHERE_BGND || rec_meth == 4) P.wmu = p->dmu + d.Nmu;
   for (int i = 0; i < 6; ++i) P.rec[i] = p->drec + i * NC;
@@ -434,23 +437,29 @@ extern "C" int rb_plan_set_problem(rb_plan *p, int b, const double *Edges, const
     hH[i] = nH[s]; hHe[i] = nHe[s]; hT[i] = T[s];
   }
   // parameter sweeps reuse a handful of spectra over thousands of problems (C5: 16 for
-  // 8192): the per-frequency table (3 Verner cross sections per frequency) is rebuilt only
-  // when the spectrum differs from the one the previous call built
+  // 8192): the per-frequency table (3 Verner cross sections per frequency) is built once
+  // per distinct spectrum (the last 32 are kept)
   double *tab = p->hspec + (size_t)b * Nnu * kSpecStride, *thin = p->hthin + (size_t)b * kThinStride;
-  if (p->spec_src >= 0 && p->spec_E.size() == (size_t)Nnu &&
-      memcmp(p->spec_E.data(), E_eV, sizeof(double) * Nnu) == 0 &&
-      memcmp(p->spec_shape.data(), shape, sizeof(double) * Nnu) == 0) {
-    if (p->spec_src != b) {
-      memcpy(tab, p->hspec + (size_t)p->spec_src * Nnu * kSpecStride,
-             sizeof(double) * Nnu * kSpecStride);
-      memcpy(thin, p->hthin + (size_t)p->spec_src * kThinStride, sizeof(double) * kThinStride);
-    }
+  int hit = -1;
+  for (size_t q = 0; q < p->spec_cache.size() && hit < 0; ++q) {
+    const rb_plan::SpecEntry &e = p->spec_cache[q];
+    if (memcmp(e.E.data(), E_eV, sizeof(double) * Nnu) == 0 &&
+        memcmp(e.shape.data(), shape, sizeof(double) * Nnu) == 0)
+      hit = (int)q;
+  }
+  if (hit >= 0) {
+    memcpy(tab, p->spec_cache[hit].tab.data(), sizeof(double) * Nnu * kSpecStride);
+    memcpy(thin, p->spec_cache[hit].thin, sizeof(double) * kThinStride);
   } else {
     build_spec_table(g, E_eV, shape, Nnu, p->sigma_th, tab, thin);
-    p->spec_E.assign(E_eV, E_eV + Nnu);
-    p->spec_shape.assign(shape, shape + Nnu);
+    if (p->spec_cache.size() >= 32) p->spec_cache.erase(p->spec_cache.begin());
+    p->spec_cache.emplace_back();
+    rb_plan::SpecEntry &e = p->spec_cache.back();
+    e.E.assign(E_eV, E_eV + Nnu);
+    e.shape.assign(shape, shape + Nnu);
+    e.tab.assign(tab, tab + (size_t)Nnu * kSpecStride);
+    memcpy(e.thin, thin, sizeof(double) * kThinStride);
   }
-  p->spec_src = b;
   p->hzHz[2 * b] = z;
   p->hzHz[2 * b + 1] = Hz;
   return RB_OK;
@@ -653,9 +662,11 @@ static int launch_nu_rates(rb_plan *p, int cell_start, int cell_stride, int n_lo
         &occ, k_nu_rates<ATT, KU, RU, BLOCK, MINB, LTAB>, BLOCK, smem);                      \
     /* 4 CTAs per resident slot: the hardware scheduler evens out the tail (+3 %) */       \
     const long long want = (long long)p->n_sm * std::max(1, occ) * 4;                        \
-    dim3 gn((unsigned)std::min<long long>(want, (long long)n_local * B));                    \
+    const int cpu = (B > 1) ? std::min(16, n_local) : 1;                                     \
+    const long long units = (long long)((n_local + cpu - 1) / cpu) * B;                      \
+    dim3 gn((unsigned)std::min<long long>(want, units));                                     \
     k_nu_rates<ATT, KU, RU, BLOCK, MINB, LTAB><<<gn, BLOCK, smem, s>>>(                      \
-        p->P, cell_start, cell_stride, n_local);                                             \
+        p->P, cell_start, cell_stride, n_local, cpu);                                        \
   } while (0)
   // thread <-> 4 frequencies, 2 rays in flight: 8 independent exp chains per thread
   if (g == RB_GEOM_SLAB_BGND) {

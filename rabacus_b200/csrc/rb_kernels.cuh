@@ -52,6 +52,8 @@ struct PlanDev {
   double *rec[6];          // the same six rates from recombination photons (zero for
                            // rec_meth = fixed; rb_rec.cuh otherwise)
   double *conv_old;        // [B][Nl]
+  double *kchem;           // [6][B][Nl] fixed-T runs: the six rate coefficients of every cell,
+                           // evaluated once by the thin-state kernel (T never changes)
   double4 *pack;           // [B][Nl+1+kPackPad]
   const double *spec;      // [B][Nnu][9]
   const double *thin;      // [B][9] optically thin integrals (sum of weights), max_nu sigma ratios
@@ -612,11 +614,11 @@ __device__ __forceinline__ void fill_exp_table_L(double *s_exp) {
 // are paid per (cell, nu) instead of per (cell, ray, nu).  Then for SphereBgnd
 //     src <- (src_old + sum)/2             (sphere_bgnd.f90:837-856).
 // Algorithmic FP64 work per (ray, nu): 3 + 10 + 1 = 14 instructions.
-// grid = one wave of CTAs striding over the flat list of (problem, local cell).
+// grid = a few waves of CTAs striding over the flat list of (problem, unit of cells).
 // ---------------------------------------------------------------------------
 template <int ATT_E2, int KU, int RU, int BLOCK, int MINB, int LTAB>
 __global__ void __launch_bounds__(BLOCK, MINB)
-k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local) {
+k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int cpu) {
   extern __shared__ double4 s_dyn4[];
   double4 *s_ray = s_dyn4;                                     // [ndir_pad]
   const int Nnu = P.Nnu, Nl = P.Nl, ndir = P.Ndir;
@@ -630,10 +632,15 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local) {
 
   // the grid is one wave of CTAs striding over the flat list of (problem, local cell):
   // balanced to one cell whatever the batch size, also while problems drop out
-  const long long total = (long long)P.B * n_local;
-  for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-    const int b = (int)(w / n_local), j = (int)(w % n_local);
-    if (!P.active[b]) continue;
+  // (in batches a work unit is `cpu` consecutive cells of one problem, so that a CTA
+  // re-reads one problem's frequency table from L1 instead of a new one from L2 per cell)
+  const int upp = (n_local + cpu - 1) / cpu;   // units per problem
+  const long long total = (long long)P.B * upp * cpu;
+  for (long long w = (long long)blockIdx.x * cpu; w < total; w += (long long)gridDim.x * cpu)
+  for (int q = 0; q < cpu; ++q) {
+    const long long u = w / cpu;
+    const int b = (int)(u / upp), j = (int)(u % upp) * cpu + q;
+    if (j >= n_local || !P.active[b]) continue;
     const double *spec = P.spec + (size_t)b * Nnu * kSpecStride;
     const int il = cell_start + j * cell_stride;
     const size_t c = (size_t)b * Nl + il;
@@ -744,7 +751,12 @@ k_cell_solve(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_local)
     const CaseA fc = {P.fcA, P.fcA, P.fcA};
     rc = solve_pcte(nH, nHe, p, P.zHz[2 * b], P.zHz[2 * b + 1], fc, P.tol_inner, x, T);
   } else {
-    const rb_kchem_t k = get_kchem(T, P.fcA, P.fcA, P.fcA);
+    // get_kchem(T) of sphere_bgnd.f90:897-899: T is fixed, the coefficients were stored
+    // by k_thin_state
+    const size_t NC = (size_t)P.B * P.Nl;
+    rb_kchem_t k;
+    k.reH2 = P.kchem[c]; k.reHe2 = P.kchem[NC + c]; k.reHe3 = P.kchem[2 * NC + c];
+    k.ciH1 = P.kchem[3 * NC + c]; k.ciHe1 = P.kchem[4 * NC + c]; k.ciHe2 = P.kchem[5 * NC + c];
     rc = solve_pce(nH, nHe, k, p.H1i, p.He1i, p.He2i, P.tol_inner, x);
   }
   if (rc) {
@@ -1227,6 +1239,15 @@ RB_LS_UNROLL
     for (int i = 0; i < CPT; ++i)
       if (valid[i]) k[i] = get_kchem(T[i], fc.H2, fc.He2, fc.He3);
     rc = pce_lockstep<CPT>(nH, nHe, k, p, valid, P.tol_inner, x, any_fn);
+    const size_t NC = (size_t)P.B * Nl;
+RB_LS_UNROLL
+    for (int i = 0; i < CPT; ++i) {
+      if (!valid[i]) continue;
+      const size_t c = (size_t)b * Nl + tid + i * tstride;
+      P.kchem[c] = k[i].reH2; P.kchem[NC + c] = k[i].reHe2; P.kchem[2 * NC + c] = k[i].reHe3;
+      P.kchem[3 * NC + c] = k[i].ciH1; P.kchem[4 * NC + c] = k[i].ciHe1;
+      P.kchem[5 * NC + c] = k[i].ciHe2;
+    }
   }
   if (rc) atomicMax(&P.err[b], rc);
 RB_LS_UNROLL
