@@ -745,16 +745,15 @@ static int sweep_impl(rb_plan *p, int cell_start, int cell_stride, bool scatter)
     rc = launch_nu_rates(p, cell_start, cell_stride, n_local);
     if (rc) return rc;
     cudaEventRecord(sev[2], s);
-    // find_Teq: G lanes per cell bisect T speculatively (k_cell_solve_spec); G is the
-    // largest group that keeps the launch within ~one wave of resident threads, and
-    // batches with more cells than that run one thread per cell.
-    int G = 1;
-    if (p->d.i_find_Teq) {
+    // G lanes per cell run the bisection (on T with find_Teq: k_cell_solve_spec, on n_e at
+    // fixed T: k_cell_solve_pce_spec) speculatively; G is the largest group that keeps the
+    // launch within ~one wave of resident threads, larger batches run one thread per cell.
+    int G = 32;
+    {
       const char *fenv = getenv("RB_SPEC_G");  // testing knob: force the group size
       const int forced = fenv ? atoi(fenv) : 0;
       const long long cells_now = (long long)n_local * B;
       const long long budget = (long long)p->n_sm * 512;
-      G = 32;
       while (G > 1 && cells_now * G > budget) G >>= 1;
       if (G < 4) G = 1;
       if (forced == 1 || forced == 4 || forced == 8 || forced == 16 || forced == 32) G = forced;
@@ -764,12 +763,15 @@ static int sweep_impl(rb_plan *p, int cell_start, int cell_stride, bool scatter)
       k_cell_solve<<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local);
     } else {
       dim3 gs3(((long long)n_local * G + 127) / 128, B);
-      switch (G) {
-        case 32: k_cell_solve_spec<32><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local); break;
-        case 16: k_cell_solve_spec<16><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local); break;
-        case 8: k_cell_solve_spec<8><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local); break;
-        default: k_cell_solve_spec<4><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local);
-      }
+#define CELL(KERN)                                                                           \
+  switch (G) {                                                                               \
+    case 32: KERN<32><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local); break; \
+    case 16: KERN<16><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local); break; \
+    case 8: KERN<8><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local); break;   \
+    default: KERN<4><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local);         \
+  }
+      if (p->d.i_find_Teq) { CELL(k_cell_solve_spec) } else { CELL(k_cell_solve_pce_spec) }
+#undef CELL
     }
     p->info.n_launches += 1;
   } else {

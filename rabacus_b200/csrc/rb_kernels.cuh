@@ -781,6 +781,120 @@ k_cell_solve(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_local)
 }
 
 // ---------------------------------------------------------------------------
+// k_cell_solve_pce_spec: solve_pce_s (ion_solver.f90:440-562) with a group of G
+// lanes per cell (fixed-T runs).  The reference bisects n_e serially: ~25
+// dependent evaluations of implicit_ionfracs (a dozen FP64 divisions each) --
+// 35 us of pure latency per sweep whatever the number of cells.  As in
+// k_cell_solve_spec the lanes of a group evaluate every n_e the bisection can
+// reach in its next L = log2(G) steps (each lane replays the reference's
+// mid-point arithmetic along its own path) and the group then walks the tree:
+// a step needs the fractions of the node (for the stopping rule
+// |max(x/x_old) - 1| <= tol, :507-512) and its direction bit ratio_ne > 1.
+// Brackets, mid-points, stopping rule and result are the serial algorithm's bit
+// for bit.
+// ---------------------------------------------------------------------------
+struct NeBisect {
+  double left, right, ne;
+};
+__device__ __forceinline__ void nebisect_step(NeBisect &s, bool up) {
+  if (up) {  // :515-517
+    s.left = s.ne;
+    s.ne = (s.ne + s.right) * 0.5;
+  } else {   // :519-521
+    s.right = s.ne;
+    s.ne = (s.left + s.ne) * 0.5;
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(128)
+k_cell_solve_pce_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_local) {
+  const int b = blockIdx.y;
+  if (!P.active[b]) return;
+  constexpr int L = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : 2;
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  const int j = t / G, sub = t % G;
+  const bool valid = j < n_local;
+  const int il = cell_start + (valid ? j : n_local - 1) * cell_stride;
+  const int lane = threadIdx.x & 31, gbase = lane & ~(G - 1);
+  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+  const size_t c = (size_t)b * P.Nl + il;
+  const size_t NC = (size_t)P.B * P.Nl;
+  const double H1i = P.src[0][c] + P.rec[0][c], He1i = P.src[1][c] + P.rec[1][c],
+               He2i = P.src[2][c] + P.rec[2][c];
+  const double nH = P.nH[c], nHe = P.nHe[c];
+  rb_kchem_t k;
+  k.reH2 = P.kchem[c]; k.reHe2 = P.kchem[NC + c]; k.reHe3 = P.kchem[2 * NC + c];
+  k.ciH1 = P.kchem[3 * NC + c]; k.ciHe1 = P.kchem[4 * NC + c]; k.ciHe2 = P.kchem[5 * NC + c];
+
+  rb_frac_t xlast;   // fractions of the last executed iteration (the result)
+  PceState st;
+  int rc = pce_init(nH, nHe, k, H1i, xlast, st);   // uniform over the group
+  NeBisect root = {st.ne_left, st.ne_right, st.ne};
+  double o1 = st.xH1_old, o2 = st.xHe1_old, o3 = st.xHe3_old, err = st.err;
+  int iter = 0;
+  bool done = (rc != 0);
+  while (!done) {
+    // ---- my node of this round's tree (heap index, root = 1); lane 0 doubles the root
+    const int node = sub == 0 ? 1 : sub;
+    NeBisect mine = root;
+    // the direction taken at an ancestor is that ancestor's own result: a lane can only
+    // replay a path, so it evaluates the ancestors' bits as assumed by its heap index
+    const int depth = 31 - __clz(node);
+    for (int i = depth - 1; i >= 0; --i) nebisect_step(mine, ((node >> i) & 1) != 0);
+    rb_frac_t x;
+    implicit_ionfracs(mine.ne, k, H1i, He1i, He2i, x);
+    const double ne_new = ne_of(nH, nHe, x);
+    const bool up = (ne_new / mine.ne) > 1.0;   // ratio_ne of :503
+    const unsigned ups = __ballot_sync(mask, up) >> gbase;
+    // ---- walk
+    int n = 1, last = -1;
+    for (int lev = 0; lev < L; ++lev) {
+      if (!(err > P.tol_inner)) { done = true; break; }   // loop test of :495
+      const double a1 = __shfl_sync(mask, x.xH1, gbase + n);
+      const double a2 = __shfl_sync(mask, x.xHe1, gbase + n);
+      const double a3 = __shfl_sync(mask, x.xHe3, gbase + n);
+      err = fabs(fmax(fmax(a1 / o1, a2 / o2), a3 / o3) - 1.0);   // :507-512
+      o1 = a1; o2 = a2; o3 = a3;
+      const bool u = (ups >> n) & 1u;
+      nebisect_step(root, u);
+      last = n;
+      n = 2 * n + (u ? 1 : 0);
+      iter = iter + 1;
+      if (iter > RB_ION_MAX_ITER) { rc = ION_ERR_MAX_ITER_PCE; done = true; break; }
+    }
+    if (last >= 0) {   // keep the fractions of the last executed iteration
+      xlast.xH1 = __shfl_sync(mask, x.xH1, gbase + last);
+      xlast.xH2 = __shfl_sync(mask, x.xH2, gbase + last);
+      xlast.xHe1 = __shfl_sync(mask, x.xHe1, gbase + last);
+      xlast.xHe2 = __shfl_sync(mask, x.xHe2, gbase + last);
+      xlast.xHe3 = __shfl_sync(mask, x.xHe3, gbase + last);
+    }
+    if (!done && !(err > P.tol_inner)) done = true;
+  }
+  if (rc) {
+    if (valid && sub == 0) atomicMax(&P.err[b], rc);
+    return;
+  }
+  if (!valid || sub != 0) return;
+  zero_absent_species(nH, nHe, xlast);
+  P.x[0][c] = xlast.xH1; P.x[1][c] = xlast.xH2; P.x[2][c] = xlast.xHe1;
+  P.x[3][c] = xlast.xHe2; P.x[4][c] = xlast.xHe3;
+  if (Q.world > 1) peer_scatter(Q, j, xlast);
+  if (two_sided(P.geom)) {
+    const size_t cm = (size_t)b * P.Nl + (P.Nl - 1 - il);
+    P.x[0][cm] = xlast.xH1; P.x[1][cm] = xlast.xH2; P.x[2][cm] = xlast.xHe1;
+    P.x[3][cm] = xlast.xHe2; P.x[4][cm] = xlast.xHe3;
+    P.T[cm] = P.T[c];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      P.src[q][cm] = P.src[q][c];
+      P.rec[q][cm] = P.rec[q][c];  // slab_bgnd.f90:842-865
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // k_cell_solve_spec: solve_pcte_s (ion_solver.f90:729-880) with a group of G
 // lanes per cell.  The reference bisects T serially: ~22 probes of
 // get_dudT (each = 16 rate fits + a solve_pce), i.e. a dependent chain of

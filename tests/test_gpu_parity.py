@@ -129,6 +129,28 @@ def test_speculative_T_bisection_equals_serial(orc, spec128, G, monkeypatch):
     assert not bad, (G, bad)
 
 
+def test_speculative_ne_bisection_is_bit_identical_to_serial(orc, spec128, monkeypatch):
+    """k_cell_solve_pce_spec (fixed T: G lanes per cell probing the next log2 G steps of
+    the n_e bisection at once) against the one-thread-per-cell kernel: every output
+    bit-identical for every group size, on a sphere, a one-sided slab and a mirrored one."""
+    cases = [_small_sphere(96, 128, 8, False, spec=spec128),
+             configs.c2_slab_plane(64, 128, False, False),
+             configs.c3_slab_bgnd(64, 128, False)]
+    for cfg in cases:
+        monkeypatch.setenv("RB_SPEC_G", "1")
+        ref = run_gpu(cfg)
+        o = run_oracle(orc, cfg)
+        assert ref["iters"] == o["iters"]
+        worst, bad = compare(ref, o)
+        assert not bad, bad
+        for G in (4, 8, 16, 32):
+            monkeypatch.setenv("RB_SPEC_G", str(G))
+            g = run_gpu(cfg)
+            assert g["iters"] == ref["iters"], G
+            for n in CHECKED:
+                assert np.array_equal(g[n], ref[n]), (cfg["geometry"], G, n)
+
+
 @pytest.mark.parametrize("Nl", [700, 2100, 4500])
 @pytest.mark.parametrize("find_Teq", [False, True])
 def test_thin_state_across_a_cluster(orc, spec128, Nl, find_Teq):
