@@ -488,3 +488,35 @@ def test_slab_recombination_photons(orc, geom, find_Teq):
         assert g["iters"] == o["iters"], kw
         worst, bad = compare(g, o, names=CHECKED_REC)
         assert not bad, (geom, kw, bad)
+
+
+def test_public_classes_with_recombination_photons(orc):
+    """The wrapper classes (same constructor keywords as ra.SphereBgnd / ra.Slab2Bgnd)
+    with rec_meth strings: results equal the oracle's, *_rec and the totals are set."""
+    import rabacus_b200 as ra
+    from rabacus_b200.rad_src import KPC_CM
+    src = ra.BackgroundSource(1.0, 400.0, "hm12", Nnu=64, z=3.0)
+    Nl = 48
+    Edges = np.linspace(0.0, 12.0 * KPC_CM, Nl + 1)
+    r = 0.5 * (Edges[1:] + Edges[:-1])
+    nH = 0.5 * np.where(r < KPC_CM, 1.0, (r / KPC_CM) ** -2.0)
+    nHe = nH * 0.08
+    T = np.full(Nl, 1.0e4)
+    s = ra.SphereBgnd(Edges, T, nH, nHe, src, rec_meth="isotropic", Nmu=8, em_He1_fac=0.5)
+    o = orc.sphere_bgnd_solve(Edges, nH, nHe, T, 8, src.E, src.shape, i_rec_meth=4,
+                              em_fac=(1.0, 0.5, 1.0), order=orc.ORDER_JACOBI)
+    assert s.itr == o["iters"]
+    got = {n: getattr(s, n) for n in CHECKED_REC if n != "T"}
+    got["T"] = s.T
+    worst, bad = compare(got, o, names=CHECKED_REC)
+    assert not bad, bad
+    assert np.array_equal(s.H1i, s.H1i_src + s.H1i_rec) and np.all(s.H1i_rec > 0.0)
+    sl = ra.Slab2Bgnd(Edges, T, np.full(Nl, 5e-3), np.full(Nl, 4e-4), src, rec_meth="ray")
+    o = orc.slab_bgnd_solve(Edges, np.full(Nl, 5e-3), np.full(Nl, 4e-4), T, src.E, src.shape,
+                            i_rec_meth=2)
+    got = {n: getattr(sl, n) for n in CHECKED_REC if n != "T"}
+    got["T"] = sl.T
+    worst, bad = compare(got, o, names=CHECKED_REC)
+    assert not bad, bad
+    with pytest.raises(ValueError):
+        ra.Slab2Bgnd(Edges, T, nH, nHe, src, rec_meth="isotropic")
