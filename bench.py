@@ -418,6 +418,7 @@ def main():
         "kernels": {n: {"ms": round(v["ms"], 4), "tflops": round(v["tflops"], 3),
                         "frac": round(v["frac"], 4)} for n, v in kern.items()},
         "ms_cell_solve": round(ms_cell, 4),
+        "ms_finish": round((plan_all["ms_finish"] - info0["ms_finish"]) / K, 4),
         "step_frac_of_fp64_peak": (2.0 * (ev_local * OPS_PER_EVAL + n_seg_local * OPS_PER_SEGMENT)
                                    / (ms / K * 1e-3) / 1e12) / peak_tflops,
         "microbench_ops_per_s": peak,

@@ -63,6 +63,7 @@ typedef struct rb_info {
   double ms_nu;       /* summed device time of the frequency-integral kernel */
   double ms_cell;     /* summed device time of the cell-solver kernel */
   double ms_rec;      /* summed device time of the recombination-photon kernels */
+  double ms_finish;   /* summed device time of the convergence / exchange kernel + read-back */
   long long evals;    /* cell*ray*frequency evaluations performed */
 } rb_info;
 

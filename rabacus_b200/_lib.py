@@ -24,7 +24,8 @@ class rb_info(C.Structure):
     _fields_ = [("iters", C.c_int), ("n_launches", C.c_int), ("resid", C.c_double),
                 ("ms_total", C.c_double), ("ms_device", C.c_double),
                 ("ms_columns", C.c_double), ("ms_nu", C.c_double),
-                ("ms_cell", C.c_double), ("ms_rec", C.c_double), ("evals", C.c_longlong)]
+                ("ms_cell", C.c_double), ("ms_rec", C.c_double), ("ms_finish", C.c_double),
+                ("evals", C.c_longlong)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

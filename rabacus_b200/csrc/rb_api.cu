@@ -847,7 +847,7 @@ extern "C" int rb_plan_sweep_sharded(rb_plan *p) {
   if (rc) return rc;
   const int slot = (int)(p->sweeps_issued % kSlots);
   cudaStream_t s = p->stream;
-  k_exchange_finish<256><<<1, 256, 0, s>>>(p->P, p->Q, slot);
+  k_exchange_finish<1024><<<1, 1024, 0, s>>>(p->P, p->Q, slot);
   p->info.n_launches += 1;
   CK(cudaMemcpyAsync(p->hflags + 3 + slot, p->dflags + 3 + slot, sizeof(int),
                      cudaMemcpyDeviceToHost, s));
@@ -864,7 +864,7 @@ extern "C" int rb_plan_finish_sweep_async(rb_plan *p) {
   const int B = p->d.n_problems;
   const int slot = (int)(p->sweeps_issued % kSlots);
   cudaStream_t s = p->stream;
-  k_converge_finish<256><<<B, 256, 0, s>>>(p->P, slot);
+  k_converge_finish<1024><<<B, 1024, 0, s>>>(p->P, slot);
   p->info.n_launches += 1;
   CK(cudaMemcpyAsync(p->hflags + 3 * B + slot, p->dflags + 3 * B + slot, sizeof(int),
                      cudaMemcpyDeviceToHost, s));
@@ -886,6 +886,7 @@ extern "C" int rb_plan_poll_sweep(rb_plan *p, int *n_active) {
   if (cudaEventElapsedTime(&ms, sev[0], sev[1]) == cudaSuccess) p->info.ms_columns += ms;
   if (cudaEventElapsedTime(&ms, sev[1], sev[2]) == cudaSuccess) p->info.ms_nu += ms;
   if (cudaEventElapsedTime(&ms, sev[2], sev[3]) == cudaSuccess) p->info.ms_cell += ms;
+  if (cudaEventElapsedTime(&ms, sev[3], sev[4]) == cudaSuccess) p->info.ms_finish += ms;
   cudaGetLastError();
   p->sweeps_polled += 1;
   p->info.iters += 1;

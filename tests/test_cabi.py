@@ -95,7 +95,7 @@ def test_host_helpers_match_oracle(orc):
 
 
 def test_struct_layouts_match_header():
-    # rb_info: 2 ints, 7 doubles, 1 long long ; rb_plan_desc: 6 ints, 2 doubles, 3 ints
+    # rb_info: 2 ints, 8 doubles, 1 long long ; rb_plan_desc: 6 ints, 2 doubles, 3 ints
     # (+ padding), 3 doubles
-    assert C.sizeof(_lib.rb_info) == 8 + 7 * 8 + 8
+    assert C.sizeof(_lib.rb_info) == 8 + 8 * 8 + 8
     assert C.sizeof(_lib.rb_plan_desc) == 24 + 16 + 16 + 24
