@@ -635,11 +635,10 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int cpu) {
   // (in batches a work unit is `cpu` consecutive cells of one problem, so that a CTA
   // re-reads one problem's frequency table from L1 instead of a new one from L2 per cell)
   const int upp = (n_local + cpu - 1) / cpu;   // units per problem
-  const long long total = (long long)P.B * upp * cpu;
-  for (long long w = (long long)blockIdx.x * cpu; w < total; w += (long long)gridDim.x * cpu)
+  const int n_units = P.B * upp;
+  for (int u = blockIdx.x; u < n_units; u += gridDim.x)
   for (int q = 0; q < cpu; ++q) {
-    const long long u = w / cpu;
-    const int b = (int)(u / upp), j = (int)(u % upp) * cpu + q;
+    const int b = u / upp, j = (u % upp) * cpu + q;
     if (j >= n_local || !P.active[b]) continue;
     const double *spec = P.spec + (size_t)b * Nnu * kSpecStride;
     const int il = cell_start + j * cell_stride;
