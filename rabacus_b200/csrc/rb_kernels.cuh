@@ -153,10 +153,14 @@ __global__ void k_pack_shells(PlanDev P) {
 // whose truncation 5 e^3/16 < 2^-63.  Result within ~0.5 ulp (CUDA's IEEE sqrt()
 // costs ~14 instructions).  x = 0: the seed +inf is clamped to a finite value by
 // one integer min on its high word, so g0 = 0 and the result is exactly 0.
+template <bool SAFE = true>
 __device__ __forceinline__ double sqrt_pos(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  y = __hiloint2double(min(__double2hiint(y), 0x7fe00000), 0);
+  // x = 0: the seed is +inf and 0 * inf = NaN.  SAFE clamps the seed (one integer min on
+  // its high word) so that the result is exactly 0; callers that can prove x > 0 (the
+  // column walk, see sphere_ray_pair) skip it.
+  if (SAFE) y = __hiloint2double(min(__double2hiint(y), 0x7fe00000), 0);
   const double g0 = x * y;
   const double e = fma(-g0, y, 1.0);
   const double q = fma(e, 0.375, 0.5);
@@ -193,7 +197,7 @@ __device__ __forceinline__ void col_close(ColAcc &a, const double4 &rec, double 
 // next U prefetched, so that the L1 latency of the (warp-uniform, broadcast)
 // record loads is off the dependent chain.  The record array is padded by
 // kPackPad entries, so the prefetch needs no bounds clamp.
-template <bool SNAP, int U>
+template <bool SNAP, int U, bool SAFE>
 __device__ __forceinline__ void col_advance(ColAcc &a, const double4 *__restrict__ pk, int kb,
                                             int ke, int il, double p2) {
   if (kb > ke) return;
@@ -207,7 +211,7 @@ __device__ __forceinline__ void col_advance(ColAcc &a, const double4 *__restrict
     for (int u = 0; u < U; ++u) f[u] = pk[k + U + u];
     double sq[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) sq[u] = sqrt_pos(n[u].x - p2);
+    for (int u = 0; u < U; ++u) sq[u] = sqrt_pos<SAFE>(n[u].x - p2);
 #pragma unroll
     for (int u = 0; u < U; ++u) col_close<SNAP>(a, n[u], sq[u], k + u, il);
 #pragma unroll
@@ -215,8 +219,22 @@ __device__ __forceinline__ void col_advance(ColAcc &a, const double4 *__restrict
   }
 #pragma unroll
   for (int u = 0; u < U - 1; ++u) {
-    if (k + u <= ke) col_close<SNAP>(a, n[u], sqrt_pos(n[u].x - p2), k + u, il);
+    if (k + u <= ke) col_close<SNAP>(a, n[u], sqrt_pos<SAFE>(n[u].x - p2), k + u, il);
   }
+}
+
+// the walk over shell records kb .. ke of one ray pair (see sphere_ray_pair)
+template <int U, bool SAFE>
+__device__ __forceinline__ void col_walk(ColAcc &a, const double4 *__restrict__ pk, int kb, int ke,
+                                         int kA, int kB, int il, int m, int Nl, double p2) {
+  a.S0 = a.S1 = a.S2 = 0.0;
+  a.A0 = a.A1 = a.A2 = 0.0;
+  a.d0 = a.d1 = a.d2 = 0.0;
+  a.cur = pk[min(kb - 1, Nl)];
+  a.s_prev = (kb - 1 <= m) ? sqrt_pos<true>(a.cur.x - p2) : 0.0;  // s_{kb-1}; beyond m: empty chunk
+  col_advance<false, U, SAFE>(a, pk, kb, min(ke, kA - 1), il, p2);
+  col_advance<true, U, SAFE>(a, pk, max(kb, kA), min(ke, kB), il, p2);
+  col_advance<false, U, SAFE>(a, pk, max(kb, kB + 1), ke, il, p2);
 }
 
 // +mu / -mu assembly of one ray pair from the sums of its walk (header comment of
@@ -298,15 +316,12 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
   // confined to a warp-uniform sub-range of the loop.
   const int kA = il_w0 + 1;                        // first record that may close an own shell
   const int kB = il_w0 + 31 * cell_stride + 1;     // last such record
+  // The walk only takes square roots of E_k^2 - p^2 for k <= m, i.e. E_k >= E_m > p (m is
+  // the last edge above the impact parameter).  Two distinct doubles a > b >= 0 differ by at
+  // least 2^-52 relative, their squares by 2^-51 >= 2 ulp, so fl(a^2) > fl(b^2): the
+  // argument is strictly positive and the seed needs no clamp inside the loop.
   ColAcc a;
-  a.S0 = a.S1 = a.S2 = 0.0;
-  a.A0 = a.A1 = a.A2 = 0.0;
-  a.d0 = a.d1 = a.d2 = 0.0;
-  a.cur = pk[min(kb - 1, Nl)];
-  a.s_prev = (kb - 1 <= m) ? sqrt_pos(a.cur.x - p2) : 0.0;  // s_{kb-1}; beyond m: empty chunk
-  col_advance<false, U>(a, pk, kb, min(ke, kA - 1), il, p2);
-  col_advance<true, U>(a, pk, max(kb, kA), min(ke, kB), il, p2);
-  col_advance<false, U>(a, pk, max(kb, kB + 1), ke, il, p2);
+  col_walk<U, false>(a, pk, kb, ke, kA, kB, il, m, Nl, p2);
   const double S[3] = {a.S0, a.S1, a.S2}, A[3] = {a.A0, a.A1, a.A2}, d[3] = {a.d0, a.d1, a.d2};
   // tangent shell m: after closing with record m, cur = shell m record, s_prev = s_m
   // (m == 0: nothing is closed, cur = pk[0], s_prev = s_0 from the initialisation)
