@@ -596,8 +596,12 @@ __device__ __forceinline__ double exp_fast(double x, const double *s_tab, unsign
   const unsigned off = ((unsigned)(n << 7) & (unsigned)(((1 << L) - 1) << 7)) | lane_off;
   const double T = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(s_tab) + off);
   const double v = fma(T, pl, T);
-  return __hiloint2double(__double2hiint(v) + (n & ~((1 << L) - 1)) * (1 << (20 - L)),
-                          __double2loint(v));
+  // exponent: hi += (n >> L) << 20 = (n & ~(2^L - 1)) * 2^(20-L), kept as lop3 + one imad
+  int hi;
+  asm("mad.lo.s32 %0, %1, %2, %3;"
+      : "=r"(hi)
+      : "r"(n & ~((1 << L) - 1)), "n"(1 << (20 - L)), "r"(__double2hiint(v)));
+  return __hiloint2double(hi, __double2loint(v));
 }
 
 template <int L>
