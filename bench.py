@@ -43,10 +43,10 @@ UNIT = "evals/s"
 #   frequency kernel, per (cell, ray, nu): 3 (tau = sum_X tau_X ra_X) + 8 (exp: scale,
 #   round, reduce, 4 polynomial, table merge) + 1 (A(nu) += w_ray a); the six rate
 #   accumulations are per (cell, nu), 1/Nmu of that, and are not counted
-#   column kernel, per ray segment: 1 (E^2 - p^2) + 5 (sqrt: MUFU seed + one
-#   third-order correction) + 1 (ds) + 3 (column FMAs)
+#   column kernel, per shell edge of a ray pair: 1 (E^2 - p^2) + 5 (sqrt: MUFU seed + one
+#   third-order correction) + 3 (column FMAs, summed by parts: P += s_k (c_k - c_{k-1}))
 OPS_PER_EVAL = 12
-OPS_PER_SEGMENT = 10
+OPS_PER_SEGMENT = 9
 
 
 def workload(args):

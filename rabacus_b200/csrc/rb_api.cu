@@ -534,7 +534,7 @@ static int build_items(rb_plan *p, int cell_start, int cell_stride, int n_local,
     return RB_OK;
   const int nblk = (n_local + 31) / 32, npair = (Nmu + 1) / 2;
   if (nblk > 0xfff || npair > 0xffff || nchunk > 15) return RB_ERR_UNSUPPORTED;
-  const int Q = (Nl + nchunk - 1) / nchunk;
+  const int Q = (Nl + nchunk) / nchunk;  // edges per chunk, as in sphere_ray_pair
   std::vector<std::pair<int, unsigned>> v;
   v.reserve((size_t)nblk * npair * nchunk);
   for (int ip = 0; ip < npair; ++ip) {
@@ -550,8 +550,8 @@ static int build_items(rb_plan *p, int cell_start, int cell_stride, int n_local,
         if (E[mid] <= pr) hi = mid; else lo = mid + 1;
       }
       const int m = lo - 1;
-      for (int c = 0; c < nchunk; ++c) {  // records c*Q .. (c+1)*Q-1, up to m
-        const int len = (nchunk == 1) ? m + 1 : std::min(m, (c + 1) * Q - 1) - std::max(1, c * Q) + 1;
+      for (int c = 0; c < nchunk; ++c) {  // shell edges c*Q .. (c+1)*Q-1, up to m
+        const int len = (nchunk == 1) ? m + 1 : std::min(m, (c + 1) * Q - 1) - c * Q + 1;
         // (chunks that are empty for the whole block stay in the list: their lanes store the
         // zero partials the combine kernel reads)
         v.emplace_back(-std::max(len, 0), (unsigned)jb | ((unsigned)c << 12) | ((unsigned)ip << 16));

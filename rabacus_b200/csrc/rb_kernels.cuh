@@ -100,21 +100,23 @@ __device__ __forceinline__ bool two_sided(int geom) {
   return geom == RB_GEOM_SLAB_PLANE_2 || geom == RB_GEOM_SLAB_BGND;
 }
 
-// shell record k of problem b (k_pack_shells / the shared-memory fill)
+// absorber densities {n_HI, n_HeI, n_HeII} of shell k (zero outside 0 .. Nl-1)
+__device__ __forceinline__ double3 shell_dens(const PlanDev &P, int b, int k) {
+  if (k < 0 || k >= P.Nl) return make_double3(0.0, 0.0, 0.0);
+  const size_t c = (size_t)b * P.Nl + k;
+  return make_double3(P.nH[c] * P.x[0][c], P.nHe[c] * P.x[2][c], P.nHe[c] * P.x[3][c]);
+}
+
+// shell record k of problem b (k_pack_shells / the shared-memory fill):
+// {E_k^2, c_k - c_{k-1}} for the three absorbers -- the column sums are taken in
+// summed-by-parts form (see the column kernel), which needs the density STEPS at the
+// shell edges rather than the densities.
 __device__ __forceinline__ double4 shell_record(const PlanDev &P, int b, int k) {
   if (k > P.Nl) return make_double4(0.0, 0.0, 0.0, 0.0);  // padding read by the prefetch
   const double E = P.Edges[(size_t)b * (P.Nl + 1) + k];
-  double4 v;
-  v.x = E * E;  // geometry.f90:148  Edges(i1)*Edges(i1)
-  if (k < P.Nl) {
-    const size_t c = (size_t)b * P.Nl + k;
-    v.y = P.nH[c] * P.x[0][c];
-    v.z = P.nHe[c] * P.x[2][c];
-    v.w = P.nHe[c] * P.x[3][c];
-  } else {
-    v.y = v.z = v.w = 0.0;
-  }
-  return v;
+  const double3 c1 = shell_dens(P, b, k), c0 = shell_dens(P, b, k - 1);
+  // geometry.f90:148  Edges(i1)*Edges(i1)
+  return make_double4(E * E, c1.x - c0.x, c1.y - c0.y, c1.z - c0.z);
 }
 
 // ---------------------------------------------------------------------------
@@ -145,6 +147,15 @@ __global__ void k_pack_shells(PlanDev P) {
 // d = ds_il c_il, t = 2 s_m c_m:
 //   il <  m : N(+mu) = A + d/2 ;  N(-mu) = 2 S - A - d/2 + t
 //   il == m : N(+mu) = N(-mu) = A + t/2
+// Summation by parts: with the density steps D_k = c_k - c_{k-1} (c_{-1} = 0) and
+// P_j = sum_{k<=j} s_k D_k  (s_k decreases with k, so ds_k = s_k - s_{k+1}):
+//   S + t/2 = P_m ,   A = P_{il-1} - s_il c_{il-1}
+// so that per shell edge the loop does  x = E_k^2 - p^2, s = sqrt(x), P += s D_k
+// (9 FP64 instructions: no ds, no carried s_{k-1}) and
+//   il <  m : N(+mu) = A + d/2 ;  N(-mu) = 2 P_m - A - d/2
+//   il == m : N(+mu) = N(-mu) = P_m
+// with d = (s_il - s_{il+1}) c_il from the two roots caught on the way.  Same terms as
+// the reference's running sums, associated differently: results agree to ~1e-14.
 // ---------------------------------------------------------------------------
 // sqrt(x) for finite x >= 0 in 5 FP64-pipe instructions.  y0 = MUFU.RSQ64H(x)
 // (rsqrt.approx.ftz.f64, relative error <= 2^-22) gives g0 = x y0 ~ sqrt(x) and the
@@ -169,33 +180,28 @@ __device__ __forceinline__ double sqrt_pos(double x) {
 }
 
 struct ColAcc {
-  double S0, S1, S2;  // running through-sums (HI, HeI, HeII)
-  double A0, A1, A2;  // snapshot at the ray's own shell
-  double d0, d1, d2;  // own-shell segment * density
-  double s_prev;
-  double4 cur;
+  double P0, P1, P2;     // running sum of s_k D_k (HI, HeI, HeII)
+  double A0, A1, A2;     // its value before the own shell's edge (P_{il-1})
+  double s_il, s_il1;    // roots at the own shell's two edges
 };
 
-// close segment (k-1) with record `rec` = shell k
+// add shell edge k (record `rec`); SNAP: k may be the own shell's outer or inner edge
 template <bool SNAP>
 __device__ __forceinline__ void col_close(ColAcc &a, const double4 &rec, double s, int k, int il) {
-  const double ds = fabs(s - a.s_prev);
-  if (SNAP && k - 1 == il) {
-    a.A0 = a.S0; a.A1 = a.S1; a.A2 = a.S2;
-    a.d0 = ds * a.cur.y; a.d1 = ds * a.cur.z; a.d2 = ds * a.cur.w;
+  if (SNAP) {
+    if (k == il) {
+      a.A0 = a.P0; a.A1 = a.P1; a.A2 = a.P2;
+      a.s_il = s;
+    }
+    if (k == il + 1) a.s_il1 = s;
   }
-  a.S0 = fma(ds, a.cur.y, a.S0);
-  a.S1 = fma(ds, a.cur.z, a.S1);
-  a.S2 = fma(ds, a.cur.w, a.S2);
-  a.s_prev = s;
-  a.cur = rec;
+  a.P0 = fma(s, rec.y, a.P0);
+  a.P1 = fma(s, rec.z, a.P1);
+  a.P2 = fma(s, rec.w, a.P2);
 }
 
-// advance over shell records k = kb .. ke (inclusive): segment k-1 is closed by
-// record k.  SNAP: also test whether segment k-1 is the ray's own shell.
-// U records per trip (their U square roots are independent chains) with the
-// next U prefetched, so that the L1 latency of the (warp-uniform, broadcast)
-// record loads is off the dependent chain.  The record array is padded by
+// advance over shell edges k = kb .. ke (inclusive).  U records per trip (their U square
+// roots are independent chains) with the next U prefetched.  The record array is padded by
 // kPackPad entries, so the prefetch needs no bounds clamp.
 template <bool SNAP, int U, bool SAFE>
 __device__ __forceinline__ void col_advance(ColAcc &a, const double4 *__restrict__ pk, int kb,
@@ -223,36 +229,41 @@ __device__ __forceinline__ void col_advance(ColAcc &a, const double4 *__restrict
   }
 }
 
-// the walk over shell records kb .. ke of one ray pair (see sphere_ray_pair)
+// the walk over shell edges kb .. ke of one ray pair (see sphere_ray_pair); [kA, kB] is
+// the warp-uniform window of edges that can be a lane's own-shell edge
 template <int U, bool SAFE>
 __device__ __forceinline__ void col_walk(ColAcc &a, const double4 *__restrict__ pk, int kb, int ke,
-                                         int kA, int kB, int il, int m, int Nl, double p2) {
-  a.S0 = a.S1 = a.S2 = 0.0;
+                                         int kA, int kB, int il, double p2) {
+  a.P0 = a.P1 = a.P2 = 0.0;
   a.A0 = a.A1 = a.A2 = 0.0;
-  a.d0 = a.d1 = a.d2 = 0.0;
-  a.cur = pk[min(kb - 1, Nl)];
-  a.s_prev = (kb - 1 <= m) ? sqrt_pos<true>(a.cur.x - p2) : 0.0;  // s_{kb-1}; beyond m: empty chunk
+  a.s_il = a.s_il1 = 0.0;
   col_advance<false, U, SAFE>(a, pk, kb, min(ke, kA - 1), il, p2);
   col_advance<true, U, SAFE>(a, pk, max(kb, kA), min(ke, kB), il, p2);
   col_advance<false, U, SAFE>(a, pk, max(kb, kB + 1), ke, il, p2);
 }
 
 // +mu / -mu assembly of one ray pair from the sums of its walk (header comment of
-// this section) and the store of its two ray records.
+// this section) and the store of its two ray records.  Pm = P_m, Pa = P_{il-1}.
 // tau_X_th = N_X * sigma_X_th   (sphere_bgnd.f90:794-796); 4th slot: GL weight
 __device__ __forceinline__ void store_ray_pair(const PlanDev &P, int b, int il, int ip, int m,
-                                               double mu, const double (&S)[3],
-                                               const double (&A)[3], const double (&d)[3],
-                                               const double (&t)[3]) {
+                                               double mu, const double (&Pm)[3],
+                                               const double (&Pa)[3], double s_il,
+                                               double s_il1) {
   const int imu_in = ip, imu_out = P.Nmu - 1 - ip;
   double Nout[3], Nin[3];
+  if (il == m) {
 #pragma unroll
-  for (int X = 0; X < 3; ++X) {
-    if (il == m) {
-      Nout[X] = Nin[X] = S[X] + 0.5 * t[X];
-    } else {
-      Nout[X] = A[X] + 0.5 * d[X];
-      Nin[X] = (2.0 * S[X] - A[X] - 0.5 * d[X]) + t[X];
+    for (int X = 0; X < 3; ++X) Nout[X] = Nin[X] = Pm[X];
+  } else {
+    const double3 c0 = shell_dens(P, b, il - 1), c1 = shell_dens(P, b, il);
+    const double cm[3] = {c0.x, c0.y, c0.z}, cc[3] = {c1.x, c1.y, c1.z};
+    const double ds = s_il - s_il1;
+#pragma unroll
+    for (int X = 0; X < 3; ++X) {
+      const double A = Pa[X] - s_il * cm[X];
+      const double d = ds * cc[X];
+      Nout[X] = A + 0.5 * d;
+      Nin[X] = 2.0 * Pm[X] - A - 0.5 * d;
     }
   }
   if (imu_in == imu_out) {  // odd Nmu: the mu ~ 0 node, both formulas agree
@@ -273,9 +284,10 @@ __device__ __forceinline__ void store_ray_pair(const PlanDev &P, int b, int il, 
 // `pk` = shell records (global or shared), `il_w0` = cell of lane 0 of the warp.
 // nchunk == 1: the whole walk, result stored as two ray records.  nchunk > 1: the
 // walk is cut at the shell records c*Q (Q = ceil(Nl/nchunk)) and this call does
-// chunk `chunk` only, leaving its partial sums {S, A, d, t, has_own} in
-// `part` for k_columns_combine -- finer work items for launches with few rays.
-constexpr int kPartStride = 13;
+// chunk `chunk` only, leaving its partial sums {P, P before the own shell, the two
+// own-shell roots, flags} in `part` for k_columns_combine -- finer work items for
+// launches with few rays.
+constexpr int kPartStride = 9;
 template <int U>
 __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il, int il_w0,
                                                 int cell_stride, int ip,
@@ -304,45 +316,36 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
   }
   const int m = lo - 1;
 
-  // records this call closes segments with: k = kb .. ke (segment k-1 is closed by record k)
-  int kb = 1, ke = m;
+  // shell edges of this call: k = kb .. ke, all of 0 .. m without chunks
+  int kb = 0, ke = m;
   if (nchunk > 1) {
-    const int Q = (Nl + nchunk - 1) / nchunk;
-    kb = max(1, chunk * Q);
+    const int Q = (Nl + nchunk) / nchunk;   // ceil((Nl + 1) / nchunk)
+    kb = chunk * Q;
     ke = min(m, (chunk + 1) * Q - 1);
   }
-  // The lanes of a warp hold cells il_w .. il_w + 31*stride: only records
-  // k-1 in that window can be a lane's own shell, so the snapshot test is
-  // confined to a warp-uniform sub-range of the loop.
-  const int kA = il_w0 + 1;                        // first record that may close an own shell
-  const int kB = il_w0 + 31 * cell_stride + 1;     // last such record
+  // The lanes of a warp hold cells il_w .. il_w + 31*stride: only edges in
+  // [il_w, il_w + 31*stride + 1] can be a lane's own-shell edge, so the snapshot
+  // test is confined to a warp-uniform sub-range of the loop.
+  const int kA = il_w0;
+  const int kB = il_w0 + 31 * cell_stride + 1;
   // The walk only takes square roots of E_k^2 - p^2 for k <= m, i.e. E_k >= E_m > p (m is
   // the last edge above the impact parameter).  Two distinct doubles a > b >= 0 differ by at
   // least 2^-52 relative, their squares by 2^-51 >= 2 ulp, so fl(a^2) > fl(b^2): the
   // argument is strictly positive and the seed needs no clamp inside the loop.
   ColAcc a;
-  col_walk<U, false>(a, pk, kb, ke, kA, kB, il, m, Nl, p2);
-  const double S[3] = {a.S0, a.S1, a.S2}, A[3] = {a.A0, a.A1, a.A2}, d[3] = {a.d0, a.d1, a.d2};
-  // tangent shell m: after closing with record m, cur = shell m record, s_prev = s_m
-  // (m == 0: nothing is closed, cur = pk[0], s_prev = s_0 from the initialisation)
-  const bool has_tangent = (nchunk == 1) || (ke == m && (kb <= ke || (m == 0 && chunk == 0)));
-  double t[3] = {0.0, 0.0, 0.0};
-  if (has_tangent) {
-    t[0] = 2.0 * a.s_prev * a.cur.y; t[1] = 2.0 * a.s_prev * a.cur.z;
-    t[2] = 2.0 * a.s_prev * a.cur.w;
-  }
+  col_walk<U, false>(a, pk, kb, ke, kA, kB, il, p2);
   if (!store) return;
+  const double Pm[3] = {a.P0, a.P1, a.P2}, Pa[3] = {a.A0, a.A1, a.A2};
   if (nchunk == 1) {
-    store_ray_pair(P, b, il, ip, m, mu, S, A, d, t);
+    store_ray_pair(P, b, il, ip, m, mu, Pm, Pa, a.s_il, a.s_il1);
     return;
   }
-  // own shell closed in this chunk?  (record il+1 in [kb, ke])
-  const bool has_own = (il + 1 >= kb) && (il + 1 <= ke);
+  // chunk partials: the chunk sum, and what the own shell's edges left in this chunk
+  const bool has_il = (il >= kb) && (il <= ke), has_il1 = (il + 1 >= kb) && (il + 1 <= ke);
 #pragma unroll
-  for (int X = 0; X < 3; ++X) {
-    part[X] = S[X]; part[3 + X] = A[X]; part[6 + X] = d[X]; part[9 + X] = t[X];
-  }
-  part[12] = has_own ? 1.0 : 0.0;
+  for (int X = 0; X < 3; ++X) { part[X] = Pm[X]; part[3 + X] = Pa[X]; }
+  part[6] = a.s_il; part[7] = a.s_il1;
+  part[8] = (has_il ? 1.0 : 0.0) + (has_il1 ? 2.0 : 0.0);
 }
 
 // Fallback for grids whose shell records do not fit in shared memory
@@ -413,8 +416,8 @@ k_sphere_columns_smem(PlanDev P, int cell_start, int cell_stride, int n_local,
 }
 
 // k_columns_combine: one thread per (local cell, |mu| pair): sums the chunk partials in
-// shell order.  A (the sum up to the own shell) = chunks before the one that closed the
-// own shell + that chunk's snapshot.
+// shell order.  P_{il-1} = chunks before the one that holds the own shell's outer edge +
+// that chunk's snapshot.
 __global__ void k_columns_combine(PlanDev P, int cell_start, int cell_stride, int n_local,
                                   int nchunk, const double *__restrict__ part) {
   const int b = blockIdx.z;
@@ -438,18 +441,20 @@ __global__ void k_columns_combine(PlanDev P, int cell_start, int cell_stride, in
   const int m = lo - 1;
   const double *pp = part + (((size_t)b * ((P.Nmu + 1) / 2) + ip) * n_local + j) * nchunk *
                                 kPartStride;
-  double S[3] = {0.0, 0.0, 0.0}, A[3] = {0.0, 0.0, 0.0}, d[3] = {0.0, 0.0, 0.0},
-         t[3] = {0.0, 0.0, 0.0};
+  double Pm[3] = {0.0, 0.0, 0.0}, Pa[3] = {0.0, 0.0, 0.0}, s_il = 0.0, s_il1 = 0.0;
   for (int c = 0; c < nchunk; ++c) {
     const double *q = pp + c * kPartStride;
-    if (q[12] != 0.0) {
+    const int flags = (int)q[8];
+    if (flags & 1) {   // P_{il-1} = chunks before + this chunk's sum up to the own shell
 #pragma unroll
-      for (int X = 0; X < 3; ++X) { A[X] = S[X] + q[3 + X]; d[X] = q[6 + X]; }
+      for (int X = 0; X < 3; ++X) Pa[X] = Pm[X] + q[3 + X];
+      s_il = q[6];
     }
+    if (flags & 2) s_il1 = q[7];
 #pragma unroll
-    for (int X = 0; X < 3; ++X) { S[X] = S[X] + q[X]; t[X] = t[X] + q[9 + X]; }
+    for (int X = 0; X < 3; ++X) Pm[X] = Pm[X] + q[X];
   }
-  store_ray_pair(P, b, il, ip, m, mu, S, A, d, t);
+  store_ray_pair(P, b, il, ip, m, mu, Pm, Pa, s_il, s_il1);
 }
 
 // ---------------------------------------------------------------------------
