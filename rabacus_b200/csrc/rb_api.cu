@@ -590,16 +590,16 @@ static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, in
     p->info.n_launches += 2;
     return RB_OK;
   }
-  // 24 warps per SM at <= 80 registers; as many CTAs per SM as the records allow
+  // as many CTAs per SM as the records allow (up to 3), 16-18 warps per SM in all
   int cps = (int)std::min<size_t>(3, kMaxSmem / (smem + 1024));
-  const int warps = 24 / cps;
+  const int warps = (cps == 1) ? 16 : (cps == 2 ? 8 : 6);
   const int want = p->n_sm * cps;  // CTAs that fill the GPU once
   // too few rays per launch to keep every warp busy with whole walks (cell shards over many
   // GPUs, small grids): cut every walk into nchunk pieces (separate work items)
   int nchunk = 1;
   {
     const long long lane_items = (long long)((n_local + 31) / 32) * ((p->d.Nmu + 1) / 2) * B;
-    const long long warps_total = (long long)p->n_sm * 24;
+    const long long warps_total = (long long)p->n_sm * warps * cps;
     while (nchunk < 8 && lane_items * nchunk * 2 < warps_total * 3) nchunk *= 2;
     const char *cenv = getenv("RB_COLS_CHUNKS");  // testing knob
     if (cenv && atoi(cenv) >= 1 && atoi(cenv) <= 8) nchunk = atoi(cenv);
@@ -633,9 +633,11 @@ static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, in
         p->P, cell_start, cell_stride, n_local, p->ditems, p->n_items, p->dwork, nchunk,     \
         p->dpart);                                                                           \
   } while (0)
-  if (cps == 1) COLS(768, 1);
-  else if (cps == 2) COLS(384, 2);
-  else COLS(256, 3);
+  // 16-18 warps per SM at ~100 registers beat 24 warps at 80 (1.035 vs 1.068 ms at C4,
+  // profiles/r01_kernel_variants.md)
+  if (cps == 1) COLS(512, 1);
+  else if (cps == 2) COLS(256, 2);
+  else COLS(192, 3);
 #undef COLS
   p->info.n_launches += 1;
   if (nchunk > 1) {
