@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "rb_api.cu")
 OUT = os.path.join(HERE, "librabacus_b200.so")
-DEPS = [os.path.join(HERE, "csrc", f) for f in
-        ("rb_api.cu", "rb_kernels.cuh", "rb_ion.cuh", "rb_atomic.cuh", "rb_common.cuh")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc")))
+        if f.endswith((".cu", ".cuh", ".h"))]
 DEPS.append(os.path.join(os.path.dirname(HERE), "include", "rabacus_b200.h"))
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",

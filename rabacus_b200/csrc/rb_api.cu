@@ -210,6 +210,9 @@ struct rb_plan {
   double *drec = nullptr;       // 6*B*Nl output rates (always allocated; zero for fixed)
   double *drecbuf = nullptr;    // scratch: em[3], F0[3], dtau[3], r_c (10*B*Nl), tlo, records
   double4 *drecI = nullptr;     // isotropic on a plan whose col buffer is too small
+  unsigned *diso_items = nullptr;  // isotropic: (32-cell block, ray) work list, longest first
+  int n_iso_items = 0;
+  std::vector<double> iso_edges;   // edges the list was built from
   RecDev R;
   RecConst K;
   cudaEvent_t rev[kSlots];      // after the rec kernels of each in-flight sweep
@@ -324,6 +327,9 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
     ALLOC(p->drecbuf, n_scal * 8 + 2 * B * (Nl + 1) * sizeof(double4) + 32);
     if (rec_meth == 4 && d.geometry != RB_GEOM_SPHERE_BGND)
       ALLOC(p->drecI, NC * (size_t)d.Nmu * sizeof(double4));
+    if (rec_meth == 4) {
+      ALLOC(p->diso_items, (size_t)((Nl + 31) / 32) * d.Nmu * sizeof(unsigned));
+    }
   }
   if (d.geometry == RB_GEOM_SPHERE_BGND)
     ALLOC(p->ditems, (size_t)((Nl + 31) / 32) * ((d.Nmu + 1) / 2) * 8 * sizeof(unsigned));
@@ -689,6 +695,47 @@ static int launch_nu_rates(rb_plan *p, int cell_start, int cell_stride, int n_lo
   return rc;
 }
 
+// isotropic photon transfer: work list (block of 32 cells in the routine's outermost-first
+// order, ray), sorted by descending path length of the block's innermost cell
+// (mu <= 0: 2m - il + 1 shells, mu > 0: il + 1); cached until the edges change
+static int build_iso_items(rb_plan *p) {
+  const int Nl = p->d.Nl, Nmu = p->d.Nmu;
+  const double *E = p->hEdges;  // problem 0, plan orientation
+  if (p->iso_edges.size() == (size_t)Nl + 1 &&
+      memcmp(p->iso_edges.data(), E, sizeof(double) * (Nl + 1)) == 0)
+    return RB_OK;
+  const bool of = p->d.geometry == RB_GEOM_SPHERE_BGND;  // outermost-first storage
+  auto Eo = [&](int i) { return of ? E[i] : E[Nl - i]; };   // edge i, outermost first
+  const int nblk = (Nl + 31) / 32;
+  std::vector<std::pair<int, unsigned>> v;
+  v.reserve((size_t)nblk * Nmu);
+  for (int imu = 0; imu < Nmu; ++imu) {
+    const double mu = p->mu[imu];
+    const double st = sqrt(1.0 - mu * mu);
+    for (int jb = 0; jb < nblk; ++jb) {
+      const int il = std::min(Nl - 1, jb * 32 + 31);
+      const double pr = 0.5 * (Eo(il) + Eo(il + 1)) * st;
+      int lo = 1, hi = Nl;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (Eo(mid) <= pr) hi = mid; else lo = mid + 1;
+      }
+      const int m = lo - 1;
+      const int len = (mu <= 0.0) ? 2 * m - il + 1 : il + 1;
+      v.emplace_back(-len, (unsigned)jb | ((unsigned)imu << 16));
+    }
+  }
+  std::sort(v.begin(), v.end());
+  std::vector<unsigned> items(v.size());
+  for (size_t i = 0; i < v.size(); ++i) items[i] = v[i].second;
+  p->n_iso_items = (int)items.size();
+  CK(cudaMemcpyAsync(p->diso_items, items.data(), items.size() * sizeof(unsigned),
+                     cudaMemcpyHostToDevice, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  p->iso_edges.assign(E, E + Nl + 1);
+  return RB_OK;
+}
+
 // recombination-photon rates of all cells from the current state (rb_rec.cuh)
 static int launch_rec(rb_plan *p) {
   const int Nl = p->d.Nl, B = p->d.n_problems, g = p->d.geometry;
@@ -708,8 +755,22 @@ static int launch_rec(rb_plan *p) {
     k_rec_radial<<<gc, 64, 0, s>>>(p->P, p->R, p->K);
     p->info.n_launches += 2;
   } else {
-    dim3 gr((Nl + 127) / 128, p->d.Nmu, B);
-    k_rec_iso_rays<<<gr, 128, 0, s>>>(p->P, p->R, p->d.Nmu);
+    const size_t smem = (size_t)(Nl + 1) * 56;
+    if (smem <= 227 * 1024 - 1024 && (Nl + 31) / 32 <= 0xffff) {
+      int rc = build_iso_items(p);
+      if (rc) return rc;
+      CK(cudaMemsetAsync(p->dwork, 0, B * sizeof(int), s));
+      rc = set_smem(k_rec_iso_rays_smem<512>, smem);
+      if (rc) return rc;
+      const int per_problem = std::max(1, std::min((p->n_iso_items + 15) / 16,
+                                                   ((B > 1 ? 4 : 1) * p->n_sm + B - 1) / B));
+      dim3 gr(per_problem, B);
+      k_rec_iso_rays_smem<512><<<gr, 512, smem, s>>>(p->P, p->R, p->d.Nmu, p->diso_items,
+                                                      p->n_iso_items, p->dwork);
+    } else {
+      dim3 gr((Nl + 127) / 128, p->d.Nmu, B);
+      k_rec_iso_rays<<<gr, 128, 0, s>>>(p->P, p->R, p->d.Nmu);
+    }
     k_rec_iso_finish<<<gc, 64, 0, s>>>(p->P, p->R, p->K, p->d.Nmu);
     p->info.n_launches += 3;
   }

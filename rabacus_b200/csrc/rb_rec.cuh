@@ -326,6 +326,166 @@ __global__ void __launch_bounds__(128) k_rec_iso_rays(PlanDev P, RecDev R, int N
   R.Iray[((size_t)b * Nl + il) * Nmu + imu] = make_double4(a.I[0], a.I[1], a.I[2], 0.0);
 }
 
+// ---------------------------------------------------------------------------
+// k_rec_iso_rays_smem: the same rays with the shell data of the problem staged in
+// shared memory (56 B per shell: E^2 | dk_EH1, dk_EHe1, dk_EHe2, em_EH1 | em_EHe1,
+// em_EHe2 -- the 4097 edges of C4 fill 224 KB, one CTA per SM) and a 512-byte exp table
+// (exp_small).  Work items = (block of 32 consecutive cells, ray) handed out
+// longest path first by an atomic counter; unclamped square root inside the walk
+// (E_k > p for k <= m, see sphere_ray_pair).  grid = (CTAs per problem, B);
+// items[it] = ilblk | imu << 16.
+// ---------------------------------------------------------------------------
+struct IsoSmem {
+  const double *E2;    // [nrec]
+  const double4 *K;    // [nrec] {dk0, dk1, dk2, em0}
+  const double2 *M;    // [nrec] {em1, em2}
+};
+
+// exp(x), -708 <= x <= 0, with a 32-entry 2^(j/32) table of two copies (512 B: all that
+// is left of shared memory beside the shell data of a 4096-shell problem; even / odd lanes
+// read their own copy) and a degree-6 polynomial (|r| <= ln2/64, truncation
+// r^7/5040 < 4e-18); otherwise exp_fast.  10 FP64 instructions.
+__constant__ double kExpS[8] = {46.16624130844683,            // 32/ln2
+                                -2.1660849392498290e-02,      // -ln2/32
+                                1.3888888888888889e-03, 8.3333333333333332e-03,
+                                4.1666666666666664e-02, 1.6666666666666666e-01, 0.5,
+                                6755399441055744.0};
+__device__ __forceinline__ double exp_small(double x, const double *s_tab, unsigned lane_off) {
+  x = __hiloint2double((int)min((unsigned)__double2hiint(x), 0xC0862000u), __double2loint(x));
+  const double t = fma(x, kExpS[0], kExpS[7]);
+  const int n = __double2loint(t);
+  const double nd = t - kExpS[7];
+  const double r = fma(nd, kExpS[1], x);
+  double q = fma(r, kExpS[2], kExpS[3]);
+  q = fma(r, q, kExpS[4]);
+  q = fma(r, q, kExpS[5]);
+  q = fma(r, q, kExpS[6]);
+  const double r2 = r * r;
+  const double pl = fma(r2, q, r);
+  const unsigned off = ((unsigned)(n << 4) & (31u << 4)) | lane_off;
+  const double T = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(s_tab) + off);
+  const double v = fma(T, pl, T);
+  int hi;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(hi) : "r"(n & ~31), "n"(1 << 15), "r"(__double2hiint(v)));
+  return __hiloint2double(hi, __double2loint(v));
+}
+
+__device__ __forceinline__ void iso_step_s(IsoAcc &a, double ds, const IsoSmem &S, int k,
+                                           const double *s_tab, unsigned lane_off) {
+  const double4 kk = S.K[k];
+  const double2 mm = S.M[k];
+  // fused multiply-adds (the reference rounds the products separately: 1e-16 per step)
+  a.tau[0] = fma(ds, kk.x, a.tau[0]);
+  a.tau[1] = fma(ds, kk.y, a.tau[1]);
+  a.tau[2] = fma(ds, kk.z, a.tau[2]);
+  a.I[0] = fma(kk.w * ds, exp_small(-a.tau[0], s_tab, lane_off), a.I[0]);
+  a.I[1] = fma(mm.x * ds, exp_small(-a.tau[1], s_tab, lane_off), a.I[1]);
+  a.I[2] = fma(mm.y * ds, exp_small(-a.tau[2], s_tab, lane_off), a.I[2]);
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+k_rec_iso_rays_smem(PlanDev P, RecDev R, int Nmu, const unsigned *__restrict__ items, int n_items,
+                    int *work) {
+  const int b = blockIdx.y;
+  if (!P.active[b]) return;
+  extern __shared__ double4 s_iso[];
+  const int Nl = P.Nl;
+  const int nrec = Nl + 1;
+  double4 *sK = s_iso;
+  double2 *sM = reinterpret_cast<double2 *>(sK + nrec);
+  double *sE2 = reinterpret_cast<double *>(sM + nrec);
+  {
+    const double4 *ka = R.recA + (size_t)b * (Nl + 1);
+    const double4 *kb = R.recB + (size_t)b * (Nl + 1);
+    for (int k = threadIdx.x; k < nrec; k += THREADS) {
+      const double4 A = ka[k], Bv = kb[k];
+      sE2[k] = A.x;
+      sK[k] = make_double4(A.y, A.z, A.w, Bv.x);
+      sM[k] = make_double2(Bv.y, Bv.z);
+    }
+  }
+  __syncthreads();
+  const IsoSmem S = {sE2, sK, sM};
+  __shared__ double s_tab[64];   // [32 entries][2 copies]
+  if (threadIdx.x < 64) s_tab[threadIdx.x] = exp2((double)(threadIdx.x >> 1) * (1.0 / 32.0));
+  __syncthreads();
+  const unsigned lane_off = (threadIdx.x & 1) << 3;
+  const int lane = threadIdx.x & 31;
+  const double *E = P.Edges + (size_t)b * (Nl + 1);
+  const bool of = plan_outer_first(P.geom);
+  const double E_in = of ? E[Nl] : E[0];
+  int it = 0, nxt = 0;
+  if (lane == 0) it = atomicAdd(&work[b], 1);
+  it = __shfl_sync(0xffffffffu, it, 0);
+  while (it < n_items) {
+    if (lane == 0) nxt = atomicAdd(&work[b], 1);
+    const unsigned item = items[it];
+    const int imu = (int)(item >> 16);
+    const int il_raw = (int)(item & 0xffffu) * 32 + lane;   // routine index, 0 = outermost
+    const bool valid = il_raw < Nl;
+    const int il = valid ? il_raw : Nl - 1;
+    const double mu = P.mu[imu];
+    const double Ea = of ? E[il] : E[Nl - il], Eb = of ? E[il + 1] : E[Nl - il - 1];
+    const double r_ray = (Ea + Eb) * 0.5;
+    const double p_ray = r_ray * sqrt(1.0 - mu * mu);
+    const double p2 = p_ray * p_ray;
+    if (E_in > p_ray) {  // m_for_ray undefined (geometry.f90:61-71)
+      atomicMax(&P.err[b], RB_ERR_RAY_GEOMETRY);
+    } else {
+      int lo = 1, hi = Nl;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const double Em = of ? E[mid] : E[Nl - mid];
+        if (Em <= p_ray) hi = mid; else lo = mid + 1;
+      }
+      const int m = lo - 1;
+      IsoAcc a;
+      a.tau[0] = a.tau[1] = a.tau[2] = 0.0;
+      a.I[0] = a.I[1] = a.I[2] = 0.0;
+      int k_out;
+      double s_hi;
+      // the halved first segment and the tangent shell are peeled off so that the two long
+      // loops are branch-free (the compiler interleaves two shells: 6 exp chains in flight)
+      double s_k = sqrt_pos<false>(S.E2[il] - p2);
+      if (mu <= 0.0) {
+        if (il < m) {
+          double s_n = sqrt_pos<false>(S.E2[il + 1] - p2);
+          iso_step_s(a, fabs(s_n - s_k) * 0.5, S, il, s_tab, lane_off);
+          s_k = s_n;
+#pragma unroll 2
+          for (int k = il + 1; k < m; ++k) {   // inward leg
+            s_n = sqrt_pos<false>(S.E2[k + 1] - p2);
+            iso_step_s(a, fabs(s_n - s_k), S, k, s_tab, lane_off);
+            s_k = s_n;
+          }
+          iso_step_s(a, 2.0 * s_k, S, m, s_tab, lane_off);   // tangent shell
+        } else {
+          iso_step_s(a, (2.0 * s_k) * 0.5, S, m, s_tab, lane_off);  // own shell is the tangent shell
+        }
+        k_out = m - 1;
+        s_hi = s_k;  // = s_m
+      } else {
+        double ds;
+        if (il < m) ds = fabs(sqrt_pos<false>(S.E2[il + 1] - p2) - s_k) * 0.5;
+        else ds = (2.0 * s_k) * 0.5;
+        iso_step_s(a, ds, S, il, s_tab, lane_off);
+        k_out = il - 1;
+        s_hi = s_k;
+      }
+#pragma unroll 2
+      for (int k = k_out; k >= 0; --k) {   // outward leg
+        const double s_o = sqrt_pos<false>(S.E2[k] - p2);
+        iso_step_s(a, fabs(s_hi - s_o), S, k, s_tab, lane_off);
+        s_hi = s_o;
+      }
+      if (valid)
+        R.Iray[((size_t)b * Nl + il) * Nmu + imu] = make_double4(a.I[0], a.I[1], a.I[2], 0.0);
+    }
+    it = __shfl_sync(0xffffffffu, nxt, 0);
+  }
+}
+
 // angle average J = (1/2) sum_mu I w (sphere_base.f90:1020-1032) and the rates (:1037-1061)
 __global__ void k_rec_iso_finish(PlanDev P, RecDev R, RecConst K, int Nmu) {
   const int b = blockIdx.y;
