@@ -606,7 +606,7 @@ static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, in
   {
     const long long lane_items = (long long)((n_local + 31) / 32) * ((p->d.Nmu + 1) / 2) * B;
     const long long warps_total = (long long)p->n_sm * warps * cps;
-    while (nchunk < 8 && lane_items * nchunk * 2 < warps_total * 3) nchunk *= 2;
+    while (nchunk < 8 && lane_items * nchunk < warps_total * 6) nchunk *= 2;  // >= 6 items per warp
     const char *cenv = getenv("RB_COLS_CHUNKS");  // testing knob
     if (cenv && atoi(cenv) >= 1 && atoi(cenv) <= 8) nchunk = atoi(cenv);
     while (nchunk > 1 && Nl < 8 * nchunk) nchunk /= 2;
