@@ -216,6 +216,12 @@ struct rb_plan {
   RecDev R;
   RecConst K;
   cudaEvent_t rev[kSlots];      // after the rec kernels of each in-flight sweep
+  // CUDA graphs of one sweep (one per in-flight slot), see solve_loop
+  cudaGraphExec_t gexec[kSlots] = {nullptr};
+  int graph_nl[kSlots] = {0};          // kernel launches inside each graph
+  PlanDev gP;                           // kernel arguments the graphs were captured with
+  bool capturing = false, graphs_ok = true;
+  bool slot_timed[kSlots] = {false};    // stage events of that slot are valid (direct launches)
   // cell sharding over peer memory
   PeerDev Q;                    // world == 1 when not connected
   void *dpeer = nullptr;        // this rank's flags (256 B) + staging
@@ -789,13 +795,15 @@ static int sweep_impl(rb_plan *p, int cell_start, int cell_stride, bool scatter)
   cudaStream_t s = p->stream;
   cudaEvent_t *sev = p->sev[p->sweeps_issued % kSlots];
   int rc = RB_OK;
-  cudaEventRecord(p->rev[p->sweeps_issued % kSlots], s);
+  const bool timed = !p->capturing;   // stage events are not captured into graphs
+  p->slot_timed[p->sweeps_issued % kSlots] = timed;
+  if (timed) cudaEventRecord(p->rev[p->sweeps_issued % kSlots], s);
   if (p->rec_meth != 1) {
     if (cell_stride != 1 || scatter) return RB_ERR_UNSUPPORTED;  // photon transfer: one GPU
     rc = launch_rec(p);
     if (rc) return rc;
   }
-  cudaEventRecord(sev[0], s);
+  if (timed) cudaEventRecord(sev[0], s);
   if (g == RB_GEOM_SPHERE_BGND) {
     if (n_local > 0) rc = launch_sphere_columns(p, cell_start, cell_stride, n_local);
     if (rc) return rc;
@@ -803,11 +811,11 @@ static int sweep_impl(rb_plan *p, int cell_start, int cell_stride, bool scatter)
     k_column_taus<512><<<B, 512, 0, s>>>(p->P);
     p->info.n_launches += 1;
   }
-  cudaEventRecord(sev[1], s);
+  if (timed) cudaEventRecord(sev[1], s);
   if (n_local > 0) {
     rc = launch_nu_rates(p, cell_start, cell_stride, n_local);
     if (rc) return rc;
-    cudaEventRecord(sev[2], s);
+    if (timed) cudaEventRecord(sev[2], s);
     // G lanes per cell run the bisection (on T with find_Teq: k_cell_solve_spec, on n_e at
     // fixed T: k_cell_solve_pce_spec) speculatively; G is the largest group that keeps the
     // launch within ~one wave of resident threads, larger batches run one thread per cell.
@@ -838,10 +846,10 @@ static int sweep_impl(rb_plan *p, int cell_start, int cell_stride, bool scatter)
     }
     p->info.n_launches += 1;
   } else {
-    cudaEventRecord(sev[2], s);
+    if (timed) cudaEventRecord(sev[2], s);
   }
-  cudaEventRecord(sev[3], s);
-  CK(cudaGetLastError());
+  if (timed) cudaEventRecord(sev[3], s);
+  if (timed) CK(cudaGetLastError());
   return RB_OK;
 }
 
@@ -921,19 +929,73 @@ extern "C" int rb_plan_sweep_sharded(rb_plan *p) {
 }
 
 // convergence test + bookkeeping of the sweep just enqueued; does not wait.
-extern "C" int rb_plan_finish_sweep_async(rb_plan *p) {
-  if (!p) return RB_ERR_BAD_ARG;
-  if (p->sweeps_issued - p->sweeps_polled >= kSlots - 1) return RB_ERR_BAD_ARG;  // poll first
+static int finish_body(rb_plan *p, int slot) {
   const int B = p->d.n_problems;
-  const int slot = (int)(p->sweeps_issued % kSlots);
   cudaStream_t s = p->stream;
   k_converge_finish<1024><<<B, 1024, 0, s>>>(p->P, slot);
   p->info.n_launches += 1;
   CK(cudaMemcpyAsync(p->hflags + 3 * B + slot, p->dflags + 3 * B + slot, sizeof(int),
                      cudaMemcpyDeviceToHost, s));
-  CK(cudaEventRecord(p->sev[slot][4], s));
+  return RB_OK;
+}
+
+extern "C" int rb_plan_finish_sweep_async(rb_plan *p) {
+  if (!p) return RB_ERR_BAD_ARG;
+  if (p->sweeps_issued - p->sweeps_polled >= kSlots - 1) return RB_ERR_BAD_ARG;  // poll first
+  const int slot = (int)(p->sweeps_issued % kSlots);
+  int rc = finish_body(p, slot);
+  if (rc) return rc;
+  CK(cudaEventRecord(p->sev[slot][4], p->stream));
   p->sweeps_issued += 1;
   CK(cudaGetLastError());
+  return RB_OK;
+}
+
+// One whole sweep (all cells) + convergence test as a CUDA graph launch.  A sweep is 4-7
+// small launches; for the column geometries and small grids they cost more than the kernels
+// (70-100 us per sweep of ~40 us of work), so rb_plan_solve replays a captured graph per
+// in-flight slot (the slot index is a kernel argument).  Graphs are re-captured when a
+// kernel argument changed (the plan was re-armed with other flags).  Stage events are not
+// part of the graphs: per-stage times come from direct launches (first sweep, bench).
+static int sweep_graph(rb_plan *p) {
+  if (p->sweeps_issued - p->sweeps_polled >= kSlots - 1) return RB_ERR_BAD_ARG;
+  const int slot = (int)(p->sweeps_issued % kSlots);
+  cudaStream_t s = p->stream;
+  if (memcmp(&p->gP, &p->P, sizeof(PlanDev)) != 0) {
+    for (auto &g : p->gexec)
+      if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    p->gP = p->P;
+  }
+  if (!p->gexec[slot]) {
+    const int nl0 = p->info.n_launches;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      p->graphs_ok = false;
+      return RB_ERR_UNSUPPORTED;
+    }
+    p->capturing = true;
+    int rc = sweep_impl(p, 0, 1, false);
+    if (!rc) rc = finish_body(p, slot);
+    p->capturing = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s, &graph);
+    p->graph_nl[slot] = p->info.n_launches - nl0;
+    p->info.n_launches = nl0;
+    if (rc || e != cudaSuccess || !graph ||
+        cudaGraphInstantiate(&p->gexec[slot], graph, 0) != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      p->gexec[slot] = nullptr;
+      p->graphs_ok = false;
+      return rc ? rc : RB_ERR_UNSUPPORTED;
+    }
+    cudaGraphDestroy(graph);
+  }
+  p->slot_timed[slot] = false;
+  CK(cudaGraphLaunch(p->gexec[slot], s));
+  p->info.n_launches += p->graph_nl[slot];
+  CK(cudaEventRecord(p->sev[slot][4], s));
+  p->sweeps_issued += 1;
   return RB_OK;
 }
 
@@ -945,12 +1007,14 @@ extern "C" int rb_plan_poll_sweep(rb_plan *p, int *n_active) {
   CK(cudaEventSynchronize(p->sev[slot][4]));
   float ms;  // per-stage device times of that sweep
   cudaEvent_t *sev = p->sev[slot];
-  if (cudaEventElapsedTime(&ms, p->rev[slot], sev[0]) == cudaSuccess) p->info.ms_rec += ms;
-  if (cudaEventElapsedTime(&ms, sev[0], sev[1]) == cudaSuccess) p->info.ms_columns += ms;
-  if (cudaEventElapsedTime(&ms, sev[1], sev[2]) == cudaSuccess) p->info.ms_nu += ms;
-  if (cudaEventElapsedTime(&ms, sev[2], sev[3]) == cudaSuccess) p->info.ms_cell += ms;
-  if (cudaEventElapsedTime(&ms, sev[3], sev[4]) == cudaSuccess) p->info.ms_finish += ms;
-  cudaGetLastError();
+  if (p->slot_timed[slot]) {
+    if (cudaEventElapsedTime(&ms, p->rev[slot], sev[0]) == cudaSuccess) p->info.ms_rec += ms;
+    if (cudaEventElapsedTime(&ms, sev[0], sev[1]) == cudaSuccess) p->info.ms_columns += ms;
+    if (cudaEventElapsedTime(&ms, sev[1], sev[2]) == cudaSuccess) p->info.ms_nu += ms;
+    if (cudaEventElapsedTime(&ms, sev[2], sev[3]) == cudaSuccess) p->info.ms_cell += ms;
+    if (cudaEventElapsedTime(&ms, sev[3], sev[4]) == cudaSuccess) p->info.ms_finish += ms;
+    cudaGetLastError();
+  }
   p->sweeps_polled += 1;
   p->info.iters += 1;
   p->last_active = p->hflags[3 * B + slot];
@@ -1034,6 +1098,8 @@ static int solve_loop(rb_plan *p, rb_info *info, bool sharded) {
   // problem converged into immediate returns, so the iterates are exactly those
   // of a sweep-by-sweep loop while the host never stalls the stream.
   const int kDepth = 4;
+  const char *genv = getenv("RB_NO_GRAPHS");  // testing knob: direct launches only
+  const bool use_graphs = !(genv && atoi(genv) != 0);
   long long evals = 0;
   int n_active = (int)B, active_during = (int)B;
   bool stop = false;
@@ -1041,6 +1107,14 @@ static int solve_loop(rb_plan *p, rb_info *info, bool sharded) {
     if (!stop && p->sweeps_issued - p->sweeps_polled < kDepth) {
       if (sharded) {
         rc = rb_plan_sweep_sharded(p);
+      } else if (use_graphs && p->graphs_ok && p->sweeps_issued > 0) {
+        // (the first sweep goes out directly: it builds the cached work lists, sets the
+        // kernels' shared-memory attributes and gives the stage times of one sweep)
+        rc = sweep_graph(p);
+        if (rc && !p->graphs_ok) {  // capture not possible: direct launches from here on
+          rc = rb_plan_sweep_local(p, 0, 1);
+          if (!rc) rc = rb_plan_finish_sweep_async(p);
+        }
       } else {
         rc = rb_plan_sweep_local(p, 0, 1);
         if (!rc) rc = rb_plan_finish_sweep_async(p);

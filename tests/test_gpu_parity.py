@@ -520,3 +520,34 @@ def test_public_classes_with_recombination_photons(orc):
     assert not bad, bad
     with pytest.raises(ValueError):
         ra.Slab2Bgnd(Edges, T, nH, nHe, src, rec_meth="isotropic")
+
+
+def test_graph_replay_equals_direct_launches(orc, spec128, monkeypatch):
+    """rb_plan_solve replays one captured CUDA graph per in-flight sweep slot after the
+    first sweep; the results must be those of direct kernel launches bit for bit, also
+    when a cached plan is re-armed with other flags (graphs are re-captured)."""
+    from rabacus_b200 import rabacus_fc as fc
+    cases = [_small_sphere(96, 128, 8, False, spec=spec128),
+             _small_sphere(96, 128, 8, True, spec=spec128),
+             configs.c3_slab_bgnd(64, 128, False), configs.c1_iliev_stromgren(64)]
+    for cfg in cases:
+        monkeypatch.setenv("RB_NO_GRAPHS", "1")
+        ref = run_gpu(cfg)
+        monkeypatch.delenv("RB_NO_GRAPHS")
+        g = run_gpu(cfg)
+        assert g["iters"] == ref["iters"]
+        for n in CHECKED:
+            assert np.array_equal(g[n], ref[n]), (cfg["geometry"], n)
+    # one-shot entry point: the cached plan is reused with a different tolerance and find_Teq
+    cfg = _small_sphere(64, 128, 8, False, spec=spec128)
+    outs = []
+    for tol, teq in ((1e-4, 0), (1e-6, 0), (1e-4, 1), (1e-4, 0)):
+        T = cfg["T"].copy()
+        o = fc.sphere_bgnd.sphere_bgnd_solve(
+            cfg["Edges"].copy(), cfg["nH"].copy(), cfg["nHe"].copy(), T, 8, cfg["E_eV"],
+            cfg["shape"], 1, 1.0, 1, 1, teq, 0, 1.0, 1.0, 1.0, 3.0, 0.0, tol, 64, 128)
+        outs.append((o, dict(fc.last_info)["iters"]))
+    assert outs[1][1] > outs[0][1]                      # the tighter tolerance took effect
+    assert outs[3][1] == outs[0][1]
+    for a, b_ in zip(outs[0][0], outs[3][0]):
+        assert np.array_equal(a, b_)
