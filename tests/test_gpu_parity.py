@@ -551,3 +551,54 @@ def test_graph_replay_equals_direct_launches(orc, spec128, monkeypatch):
     assert outs[3][1] == outs[0][1]
     for a, b_ in zip(outs[0][0], outs[3][0]):
         assert np.array_equal(a, b_)
+
+
+@pytest.mark.parametrize("Nl,Nnu,Nmu", [(1, 16, 4), (2, 16, 1), (3, 1, 2), (33, 2, 3),
+                                        (7500, 16, 4), (8192, 8, 2)])
+def test_sphere_bgnd_edge_sizes(orc, Nl, Nnu, Nmu):
+    """Smallest and largest grids: one and two shells, one ray, one and two frequencies
+    (the monochromatic branch), and grids whose shell records do not fit in shared memory
+    (the global-memory column kernel, two cells per thread in the thin-state cluster)."""
+    from rabacus_b200.rad_src import BackgroundSource
+    if Nnu == 1:
+        src = BackgroundSource(1.5, 1.5, "monochromatic")
+        src.normalize_n(1.0e-5)
+        spec = (src.E.copy(), src.shape.copy())
+    else:
+        spec = configs.hm12_background(Nnu, 3.0)
+    cfg = configs.c4_sphere_bgnd(Nl, Nnu, Nmu, False, nH0=0.3, spectrum=spec)
+    for kw in (dict(thin=True), dict(max_sweeps=2)):
+        g = run_gpu(cfg, **kw)
+        o = run_oracle(orc, cfg, **kw)
+        worst, bad = compare(g, o)
+        assert not bad, (kw, bad)
+
+
+def test_hot_and_cold_cells(orc, spec128):
+    """A wide spread of fixed temperatures in one problem (7.9e3 .. 1.6e5 K)."""
+    cfg = _small_sphere(64, 128, 8, False, spec=spec128)
+    cfg["T"] = np.logspace(3.9, 5.2, 64)
+    g = run_gpu(cfg, max_sweeps=3)
+    o = run_oracle(orc, cfg, max_sweeps=3)
+    worst, bad = compare(g, o)
+    assert not bad, bad
+
+
+def test_absent_species(orc, spec128):
+    """Cells without helium (zero_absent_species, ion_solver.f90:548-560).  In such a cell
+    the reference's starting guess (analytic_H1, exact for pure hydrogen) already is the
+    fixed point of the n_e bisection, so ratio_ne = 1 +- 1 ulp and the FIRST branch of
+    solve_pce (:515-521) is decided by rounding noise; the iteration then returns from the
+    far bracket and stops at its own tolerance (1e-2 tol = 1e-6 on successive fractions).
+    Any two builds of the reference agree there only to that tolerance: measured CUDA vs
+    oracle 9e-6 on xH1 (tested bound: 100 x the solver tolerance); He fractions are
+    exactly zero on both sides."""
+    cfg = _small_sphere(64, 128, 8, False, spec=spec128)
+    cfg["nHe"] = cfg["nHe"].copy()
+    cfg["nHe"][::3] = 0.0
+    g = run_gpu(cfg, max_sweeps=3)
+    o = run_oracle(orc, cfg, max_sweeps=3)
+    worst, bad = compare(g, o, rtol=1e-4, tol=1.0)   # tol=1.0 -> fractions bound 1e-4 too
+    assert not bad, bad
+    for n in ("xHe1", "xHe2", "xHe3"):
+        assert np.all(g[n][::3] == 0.0) and np.all(o[n][::3] == 0.0)
