@@ -755,10 +755,12 @@ static int launch_rec(rb_plan *p) {
     k_rec_slab<<<gc, 64, 0, s>>>(p->P, p->R, p->K);
     p->info.n_launches += 3;
   } else if (p->rec_meth == 2) {
-    k_rec_outward<<<gc, 64, 0, s>>>(p->P, p->R, p->K);
+    dim3 gw((Nl + 3) / 4, B);   // one warp per solve layer
+    k_rec_outward<<<gw, 128, 0, s>>>(p->P, p->R, p->K);
     p->info.n_launches += 2;
   } else if (p->rec_meth == 3) {
-    k_rec_radial<<<gc, 64, 0, s>>>(p->P, p->R, p->K);
+    dim3 gw((Nl + 3) / 4, B);
+    k_rec_radial<<<gw, 128, 0, s>>>(p->P, p->R, p->K);
     p->info.n_launches += 2;
   } else {
     const size_t smem = (size_t)(Nl + 1) * 56;
