@@ -752,8 +752,12 @@ static int launch_rec(rb_plan *p) {
   dim3 gc((Nl + 63) / 64, B);
   if (!sphere) {
     k_rec_slab_prefix<<<B, 32, 0, s>>>(p->P, p->R, p->K);
-    k_rec_slab<<<gc, 64, 0, s>>>(p->P, p->R, p->K);
-    p->info.n_launches += 3;
+    // J of the three lines goes through the (unused for slabs) F0 scratch: [B][3][Nl]
+    double *J = p->R.F0[0];
+    dim3 gw((Nl + 3) / 4, 3, B);   // one warp per (layer, line)
+    k_rec_slab<<<gw, 128, 0, s>>>(p->P, p->R, J);
+    k_rec_slab_finish<<<gc, 64, 0, s>>>(p->P, p->R, p->K, J);
+    p->info.n_launches += 4;
   } else if (p->rec_meth == 2) {
     dim3 gw((Nl + 3) / 4, B);   // one warp per solve layer
     k_rec_outward<<<gw, 128, 0, s>>>(p->P, p->R, p->K);

@@ -8,11 +8,11 @@
 //   slab_bgnd.f90:653-672,752-808; slab_plane.f90:657-676,716-753,974-993.
 // Kernels here (each cites the routine it restates):
 //   k_rec_prep        emission coefficients, shell fluxes, opacities per cell
-//   k_rec_outward     sphere_base.f90:79-346   one thread per solve layer
-//   k_rec_radial      sphere_base.f90:392-750  one thread per solve layer
-//   k_rec_iso_rays    sphere_base.f90:800-1083 one thread per (cell, ray)
+//   k_rec_outward     sphere_base.f90:79-346   one warp per solve layer
+//   k_rec_radial      sphere_base.f90:392-750  one warp per solve layer
+//   k_rec_iso_rays    sphere_base.f90:800-1083 one lane per (cell, ray) (_smem: shell data in shared memory)
 //   k_rec_iso_finish  angle average + rates
-//   k_rec_slab        slab_base.f90:163-560    one thread per layer
+//   k_rec_slab        slab_base.f90:163-560    one warp per (layer, line)
 // Index orientation: the sphere routines work on a fixed orientation (outward
 // and isotropic: index 0 = outermost shell; radial: index 0 = innermost) and the
 // reference reverses the arrays on entry when the caller's differ
@@ -578,70 +578,100 @@ __global__ void k_rec_slab_prefix(PlanDev P, RecDev R, RecConst K) {
 }
 
 // ---------------------------------------------------------------------------
-// k_rec_slab (slab_base.f90:163-560): one thread per layer k.  Optical depths at
-// the three recombination energies from the layer centre to every edge, E1
-// kernels on the edges, trapezoid rule over the edges below and above.
-// The running trapezoid sums are accumulated walking away from the layer (the
-// reference fills J_int first and sums from edge 0 upwards: same terms, the
-// lower sum in the opposite order).
+// k_rec_slab (slab_base.f90:163-560): one warp per (layer k, recombination line X).
+// Optical depths at the line energy from the layer centre to every edge, E1 kernels
+// on the edges, trapezoid rule over the edges below and above (:402-538).  Each of the
+// two walks is cut into 32 pieces: a first pass + exclusive warp scan gives every lane
+// the optical depth at the start of its piece, the second pass evaluates the E1 kernels
+// and its part of the trapezoid sum, a shuffle tree adds the parts (the reference
+// fills J_int edge by edge and sums from edge 0 upwards: same terms, re-associated).
+// The three lines' J are combined into the six rates by k_rec_slab_finish.
 // ---------------------------------------------------------------------------
-__global__ void k_rec_slab(PlanDev P, RecDev R, RecConst K) {
+__global__ void __launch_bounds__(128) k_rec_slab(PlanDev P, RecDev R, double *Jout) {
+  const int b = blockIdx.z;
+  if (!P.active[b]) return;
+  const int k = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int X = blockIdx.y;
+  const int Nl = P.Nl;
+  if (k >= Nl) return;
+  const int lane = threadIdx.x & 31;
+  const size_t base = (size_t)b * Nl;
+  const double *E = P.Edges + (size_t)b * (Nl + 1);
+  const double *tl = R.tlo + ((size_t)b * 3 + X) * (Nl + 1);
+  const double *em = R.em[X] + base;
+  auto dtau_at = [&](int i) { return tl[i + 1] - tl[i]; };   // as the reference forms it
+  auto em_edge = [&](int e) {  // :378-392
+    if (e == 0) return em[0] * 0.5;
+    if (e == Nl) return em[Nl - 1] * 0.5;
+    return (em[e - 1] + em[e]) * 0.5;
+  };
+  const double tau0 = dtau_at(k) * 0.5;
+  const double self = R.r_c[base + k] * em[k] * e1xa(tau0) * 0.5;   // :404-405 (r_c holds dl)
+  double ss_lo = 0.0, ss_hi = 0.0;
+  {  // lower integral (:411-421): edges i = k-1 .. 0, position q <-> i = k-1-q
+    const int Nq = k;
+    const int C = (Nq + 31) / 32;
+    const int q0 = min(Nq, lane * C), q1 = min(Nq, q0 + C);
+    double t = 0.0;
+    for (int q = q0; q < q1; ++q) t = t + dtau_at(k - 1 - q);
+    const double incl = warp_incl_scan(t);
+    const double prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    double tau = tau0 + ((lane == 0) ? 0.0 : prev);
+    if (q0 < q1) {
+      double y_hi = em_edge(k - q0) * e1xa(tau);
+      for (int q = q0; q < q1; ++q) {
+        const int i = k - 1 - q;
+        tau = tau + dtau_at(i);
+        const double y_lo = em_edge(i) * e1xa(tau);
+        ss_lo = ss_lo + (y_hi + y_lo) * (E[i + 1] - E[i]);
+        y_hi = y_lo;
+      }
+    }
+  }
+  {  // upper integral (:425-435): layers i = k+1 .. Nl-1, position q <-> i = k+1+q
+    const int Nq = Nl - 1 - k;
+    const int C = (Nq + 31) / 32;
+    const int q0 = min(Nq, lane * C), q1 = min(Nq, q0 + C);
+    double t = 0.0;
+    for (int q = q0; q < q1; ++q) t = t + dtau_at(k + 1 + q);
+    const double incl = warp_incl_scan(t);
+    const double prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    double tau = tau0 + ((lane == 0) ? 0.0 : prev);
+    if (q0 < q1) {
+      double y_lo = em_edge(k + 1 + q0) * e1xa(tau);
+      for (int q = q0; q < q1; ++q) {
+        const int i = k + 1 + q;
+        tau = tau + dtau_at(i);
+        const double y_hi = em_edge(i + 1) * e1xa(tau);
+        ss_hi = ss_hi + (y_hi + y_lo) * (E[i + 1] - E[i]);
+        y_lo = y_hi;
+      }
+    }
+  }
+  ss_lo = warp_sum(ss_lo);
+  ss_hi = warp_sum(ss_hi);
+  if (lane == 0) {
+    const double Jlo = self + 0.5 * ss_lo, Jhi = self + 0.5 * ss_hi;
+    Jout[((size_t)b * 3 + X) * Nl + k] = (Jlo + Jhi) * 4.0 * RB_PI * 0.5;  // :544-552
+  }
+}
+
+// slab_base.f90:556-572: the six rates from the three lines' J
+__global__ void k_rec_slab_finish(PlanDev P, RecDev R, RecConst K, const double *Jin) {
   const int b = blockIdx.y;
   if (!P.active[b]) return;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int Nl = P.Nl;
   if (k >= Nl) return;
-  const size_t base = (size_t)b * Nl;
-  const double *E = P.Edges + (size_t)b * (Nl + 1);
-  double J[3];
-#pragma unroll
-  for (int X = 0; X < 3; ++X) {
-    const double *tl = R.tlo + ((size_t)b * 3 + X) * (Nl + 1);
-    // optical depth through layer i at this line energy, as the reference forms it
-    auto dtau_at = [&](int i) { return tl[i + 1] - tl[i]; };
-    auto em_edge = [&](int e) {  // :378-392
-      if (e == 0) return R.em[X][base] * 0.5;
-      if (e == Nl) return R.em[X][base + Nl - 1] * 0.5;
-      return (R.em[X][base + e - 1] + R.em[X][base + e]) * 0.5;
-    };
-    const double tau0 = dtau_at(k) * 0.5;
-    const double dl = R.r_c[base + k];
-    double Jlo = dl * R.em[X][base + k] * e1xa(tau0) * 0.5;  // :404-405
-    double Jhi = Jlo;
-    if (k != 0) {  // :411-421
-      double tau = tau0;
-      double y_hi = em_edge(k) * e1xa(tau);
-      double ss = 0.0;
-      for (int i = k - 1; i >= 0; --i) {
-        tau = tau + dtau_at(i);
-        const double y_lo = em_edge(i) * e1xa(tau);
-        ss = ss + (y_hi + y_lo) * (E[i + 1] - E[i]);
-        y_hi = y_lo;
-      }
-      Jlo = Jlo + 0.5 * ss;
-    }
-    if (k != Nl - 1) {  // :425-435
-      double tau = tau0;
-      double y_lo = em_edge(k + 1) * e1xa(tau);
-      double ss = 0.0;
-      for (int i = k + 1; i <= Nl - 1; ++i) {
-        tau = tau + dtau_at(i);
-        const double y_hi = em_edge(i + 1) * e1xa(tau);
-        ss = ss + (y_hi + y_lo) * (E[i + 1] - E[i]);
-        y_lo = y_hi;
-      }
-      Jhi = Jhi + 0.5 * ss;
-    }
-    J[X] = (Jlo + Jhi) * 4.0 * RB_PI * 0.5;  // :544-552
-  }
-  const size_t c = base + k;
-  // :556-572
-  R.rec[0][c] = J[2] * K.sH1_He2 + J[1] * K.sH1_He1 + J[0] * K.sH1_H1;
-  R.rec[1][c] = J[2] * K.sHe1_He2 + J[1] * K.sHe1_He1;
-  R.rec[2][c] = J[2] * K.sHe2_He2;
-  R.rec[3][c] = J[2] * (K.E_th[2] - K.E_th[0]) * K.sH1_He2 * RB_EV_2_ERG +
-                J[1] * (K.E_th[1] - K.E_th[0]) * K.sH1_He1 * RB_EV_2_ERG;
-  R.rec[4][c] = J[2] * (K.E_th[2] - K.E_th[0]) * K.sHe1_He2 * RB_EV_2_ERG;  // sic
+  const double J0 = Jin[((size_t)b * 3 + 0) * Nl + k], J1 = Jin[((size_t)b * 3 + 1) * Nl + k],
+               J2 = Jin[((size_t)b * 3 + 2) * Nl + k];
+  const size_t c = (size_t)b * Nl + k;
+  R.rec[0][c] = J2 * K.sH1_He2 + J1 * K.sH1_He1 + J0 * K.sH1_H1;
+  R.rec[1][c] = J2 * K.sHe1_He2 + J1 * K.sHe1_He1;
+  R.rec[2][c] = J2 * K.sHe2_He2;
+  R.rec[3][c] = J2 * (K.E_th[2] - K.E_th[0]) * K.sH1_He2 * RB_EV_2_ERG +
+                J1 * (K.E_th[1] - K.E_th[0]) * K.sH1_He1 * RB_EV_2_ERG;
+  R.rec[4][c] = J2 * (K.E_th[2] - K.E_th[0]) * K.sHe1_He2 * RB_EV_2_ERG;  // sic
   R.rec[5][c] = 0.0;
 }
 
