@@ -1,22 +1,28 @@
 // rb_kernels.cuh -- sm_100a FP64 kernels of the Rabacus hot path.
 //
-//   k_pack_shells        per-sweep staging of {E_k^2, nH x_HI, nHe x_HeI, nHe x_HeII}
-//   k_sphere_columns     ray-segment column densities in concentric shells
-//                        (reference hot loop A: sphere_bgnd.f90:764-792 with
-//                         geometry.f90:37-168)
+//   k_sphere_columns_smem  ray-pair column densities in concentric shells: shell
+//                        records staged in shared memory, LPT work list, summed by
+//                        parts (reference hot loop A: sphere_bgnd.f90:764-792 with
+//                        geometry.f90:37-168); k_columns_combine for chunked walks;
+//                        k_pack_shells + k_sphere_columns: global-memory fallback
 //   k_column_taus        threshold optical depths below/above each layer by a
 //                        block-wide warp-shuffle scan (slab_base.f90:63-115,
 //                         sphere_base.f90:1232-1367)
-//   k_nu_rates           fused tau(nu) -> attenuation -> 6 trapezoid integrals ->
-//                        direction quadrature (reference hot loop B:
+//   k_nu_rates           fused tau(nu) -> attenuation -> direction quadrature -> 6
+//                        trapezoid integrals (reference hot loop B:
 //                        sphere_bgnd.f90:794-856 with source_background.f90:259-446,
 //                        source_point.f90:299-395, source_plane.f90:249-342)
 //   k_cell_solve         batched per-cell solve_pce_s / solve_pcte_s
-//                        (reference hot loop C: sphere_bgnd.f90:886-907)
+//                        (reference hot loop C: sphere_bgnd.f90:886-907);
+//   k_cell_solve_pce_spec / k_cell_solve_spec: the same bisections (on n_e / on T)
+//                        evaluated speculatively by a group of lanes per cell
 //   k_converge_finish    n_e convergence test and iteration control
-//                        (sphere_bgnd.f90:284-296)
-//   k_thin_state         optically thin start with the lock-step `_v` solvers
+//                        (sphere_bgnd.f90:284-296); k_exchange_finish: the same after
+//                        the cell-shard exchange over peer memory
+//   k_thin_state         optically thin start with the lock-step `_v` solvers over a
+//                        thread-block cluster
 //                        (sphere_bgnd.f90:379-499; ion_solver.f90:565-696,884-1056)
+// Recombination-photon transfer: rb_rec.cuh.
 //
 // None of this is a dense contraction: no tensor cores.  The governing
 // resource is the FP64 pipe (DFMA + software exp / sqrt / pow), see DESIGN.md.
