@@ -39,7 +39,7 @@ extern "C" {
 #define RB_ERR_NAN 6
 #define RB_ERR_RAY_GEOMETRY 7
 #define RB_ERR_BAD_ARG 8
-#define RB_ERR_UNSUPPORTED 9 /* rec_meth != fixed: SURVEY 8(f) "next" */
+#define RB_ERR_UNSUPPORTED 9 /* fits other than verner / hg97, sizes beyond a kernel's limit */
 #define RB_ERR_CUDA 10
 #define RB_ERR_NOMEM 11
 #define RB_ERR_PEER_TIMEOUT 12 /* cell-sharded sweep: a peer rank never reached the barrier */
@@ -238,9 +238,9 @@ int rb_plan_sweep_local(rb_plan *plan, int cell_start, int cell_stride);
 int rb_plan_finish_sweep(rb_plan *plan, int *n_active);
 int rb_plan_finish_sweep_async(rb_plan *plan);
 int rb_plan_poll_sweep(rb_plan *plan, int *n_active);
-/* cell-shard exchange (single-problem plans): pack the 12 state fields of the
- * local cells into dev_send [12][n_local] / scatter an all-gathered buffer
- * dev_recv [world][12][n_local] (cell il = j*world + g) back into the plan.
+/* cell-shard exchange (single-problem plans): pack the 18 state fields of the
+ * local cells into dev_send [18][n_local] / scatter an all-gathered buffer
+ * dev_recv [world][18][n_local] (cell il = j*world + g) back into the plan.
  * Device pointers; enqueued on the plan's stream. */
 int rb_plan_pack_cells(rb_plan *plan, int cell_start, int cell_stride, double *dev_send);
 int rb_plan_unpack_cells(rb_plan *plan, int world, const double *dev_recv);

@@ -37,7 +37,7 @@ extern "C" const char *rb_strerror(int code) {
     case RB_ERR_NAN: return "NaN in solve_ce";
     case RB_ERR_RAY_GEOMETRY: return "ray geometry undefined (no shell edge <= impact parameter)";
     case RB_ERR_BAD_ARG: return "bad argument";
-    case RB_ERR_UNSUPPORTED: return "option not supported by the CUDA path (fits: verner / hg97 only; photon transfer rec_meth: one GPU, all cells)";
+    case RB_ERR_UNSUPPORTED: return "option not supported by the CUDA path (fits: verner / hg97 only)";
     case RB_ERR_CUDA: return g_cuda_msg[0] ? g_cuda_msg : "CUDA error / no CUDA device";
     case RB_ERR_NOMEM: return "out of memory";
     case RB_ERR_PEER_TIMEOUT: return "cell-sharded sweep: a peer rank did not reach the barrier within 2 s";
@@ -213,6 +213,7 @@ struct rb_plan {
   unsigned *diso_items = nullptr;  // isotropic: (32-cell block, ray) work list, longest first
   int n_iso_items = 0;
   std::vector<double> iso_edges;   // edges the list was built from
+  int iso_cells[3] = {-1, -1, -1}; // (start, stride, n) of the cell list it was built for
   RecDev R;
   RecConst K;
   cudaEvent_t rev[kSlots];      // after the rec kernels of each in-flight sweep
@@ -704,30 +705,36 @@ static int launch_nu_rates(rb_plan *p, int cell_start, int cell_stride, int n_lo
 // isotropic photon transfer: work list (block of 32 cells in the routine's outermost-first
 // order, ray), sorted by descending path length of the block's innermost cell
 // (mu <= 0: 2m - il + 1 shells, mu > 0: il + 1); cached until the edges change
-static int build_iso_items(rb_plan *p) {
+static int build_iso_items(rb_plan *p, const RecCells &L) {
   const int Nl = p->d.Nl, Nmu = p->d.Nmu;
   const double *E = p->hEdges;  // problem 0, plan orientation
-  if (p->iso_edges.size() == (size_t)Nl + 1 &&
+  if (p->iso_edges.size() == (size_t)Nl + 1 && p->iso_cells[0] == L.start &&
+      p->iso_cells[1] == L.stride && p->iso_cells[2] == L.n_total &&
       memcmp(p->iso_edges.data(), E, sizeof(double) * (Nl + 1)) == 0)
     return RB_OK;
   const bool of = p->d.geometry == RB_GEOM_SPHERE_BGND;  // outermost-first storage
   auto Eo = [&](int i) { return of ? E[i] : E[Nl - i]; };   // edge i, outermost first
-  const int nblk = (Nl + 31) / 32;
+  const int nblk = (L.n_total + 31) / 32;
   std::vector<std::pair<int, unsigned>> v;
   v.reserve((size_t)nblk * Nmu);
   for (int imu = 0; imu < Nmu; ++imu) {
     const double mu = p->mu[imu];
     const double st = sqrt(1.0 - mu * mu);
     for (int jb = 0; jb < nblk; ++jb) {
-      const int il = std::min(Nl - 1, jb * 32 + 31);
-      const double pr = 0.5 * (Eo(il) + Eo(il + 1)) * st;
-      int lo = 1, hi = Nl;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (Eo(mid) <= pr) hi = mid; else lo = mid + 1;
+      int len = 0;   // the longer of the block's two end cells
+      for (int e = 0; e < 2; ++e) {
+        const int j = e ? std::min(L.n_total - 1, jb * 32 + 31) : jb * 32;
+        const int pc = L.start + j * L.stride;
+        const int il = of ? pc : Nl - 1 - pc;
+        const double pr = 0.5 * (Eo(il) + Eo(il + 1)) * st;
+        int lo = 1, hi = Nl;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (Eo(mid) <= pr) hi = mid; else lo = mid + 1;
+        }
+        const int m = lo - 1;
+        len = std::max(len, (mu <= 0.0) ? 2 * m - il + 1 : il + 1);
       }
-      const int m = lo - 1;
-      const int len = (mu <= 0.0) ? 2 * m - il + 1 : il + 1;
       v.emplace_back(-len, (unsigned)jb | ((unsigned)imu << 16));
     }
   }
@@ -739,37 +746,44 @@ static int build_iso_items(rb_plan *p) {
                      cudaMemcpyHostToDevice, p->stream));
   CK(cudaStreamSynchronize(p->stream));
   p->iso_edges.assign(E, E + Nl + 1);
+  p->iso_cells[0] = L.start; p->iso_cells[1] = L.stride; p->iso_cells[2] = L.n_total;
   return RB_OK;
 }
 
-// recombination-photon rates of all cells from the current state (rb_rec.cuh)
-static int launch_rec(rb_plan *p) {
+// recombination-photon rates of the cells of list L from the current state (rb_rec.cuh);
+// the per-cell preparation (emissivities, shell optical depths) covers all cells
+static int launch_rec(rb_plan *p, const RecCells &L) {
   const int Nl = p->d.Nl, B = p->d.n_problems, g = p->d.geometry;
+  const int nc = L.n_total;
   cudaStream_t s = p->stream;
   const bool sphere = g == RB_GEOM_SPHERE_BGND || g == RB_GEOM_SPHERE_STROMGREN;
   dim3 gp((Nl + 1 + 127) / 128, B);
   k_rec_prep<<<gp, 128, 0, s>>>(p->P, p->R, p->K, p->rec_meth);
-  dim3 gc((Nl + 63) / 64, B);
+  dim3 gc((nc + 63) / 64, B);
+  if (nc == 0) {
+    p->info.n_launches += 1;
+    return RB_OK;
+  }
   if (!sphere) {
     k_rec_slab_prefix<<<B, 32, 0, s>>>(p->P, p->R, p->K);
     // J of the three lines goes through the (unused for slabs) F0 scratch: [B][3][Nl]
     double *J = p->R.F0[0];
-    dim3 gw((Nl + 3) / 4, 3, B);   // one warp per (layer, line)
-    k_rec_slab<<<gw, 128, 0, s>>>(p->P, p->R, J);
-    k_rec_slab_finish<<<gc, 64, 0, s>>>(p->P, p->R, p->K, J);
+    dim3 gw((nc + 3) / 4, 3, B);   // one warp per (layer, line)
+    k_rec_slab<<<gw, 128, 0, s>>>(p->P, p->R, J, L);
+    k_rec_slab_finish<<<gc, 64, 0, s>>>(p->P, p->R, p->K, J, L);
     p->info.n_launches += 4;
   } else if (p->rec_meth == 2) {
-    dim3 gw((Nl + 3) / 4, B);   // one warp per solve layer
-    k_rec_outward<<<gw, 128, 0, s>>>(p->P, p->R, p->K);
+    dim3 gw((nc + 3) / 4, B);   // one warp per solve layer
+    k_rec_outward<<<gw, 128, 0, s>>>(p->P, p->R, p->K, L);
     p->info.n_launches += 2;
   } else if (p->rec_meth == 3) {
-    dim3 gw((Nl + 3) / 4, B);
-    k_rec_radial<<<gw, 128, 0, s>>>(p->P, p->R, p->K);
+    dim3 gw((nc + 3) / 4, B);
+    k_rec_radial<<<gw, 128, 0, s>>>(p->P, p->R, p->K, L);
     p->info.n_launches += 2;
   } else {
     const size_t smem = (size_t)(Nl + 1) * 56;
     if (smem <= 227 * 1024 - 1024 && (Nl + 31) / 32 <= 0xffff) {
-      int rc = build_iso_items(p);
+      int rc = build_iso_items(p, L);
       if (rc) return rc;
       CK(cudaMemsetAsync(p->dwork, 0, B * sizeof(int), s));
       rc = set_smem(k_rec_iso_rays_smem<512>, smem);
@@ -778,12 +792,12 @@ static int launch_rec(rb_plan *p) {
                                                    ((B > 1 ? 4 : 1) * p->n_sm + B - 1) / B));
       dim3 gr(per_problem, B);
       k_rec_iso_rays_smem<512><<<gr, 512, smem, s>>>(p->P, p->R, p->d.Nmu, p->diso_items,
-                                                      p->n_iso_items, p->dwork);
+                                                      p->n_iso_items, p->dwork, L);
     } else {
-      dim3 gr((Nl + 127) / 128, p->d.Nmu, B);
-      k_rec_iso_rays<<<gr, 128, 0, s>>>(p->P, p->R, p->d.Nmu);
+      dim3 gr((nc + 127) / 128, p->d.Nmu, B);
+      k_rec_iso_rays<<<gr, 128, 0, s>>>(p->P, p->R, p->d.Nmu, L);
     }
-    k_rec_iso_finish<<<gc, 64, 0, s>>>(p->P, p->R, p->K, p->d.Nmu);
+    k_rec_iso_finish<<<gc, 64, 0, s>>>(p->P, p->R, p->K, p->d.Nmu, L);
     p->info.n_launches += 3;
   }
   CK(cudaGetLastError());
@@ -805,8 +819,14 @@ static int sweep_impl(rb_plan *p, int cell_start, int cell_stride, bool scatter)
   p->slot_timed[p->sweeps_issued % kSlots] = timed;
   if (timed) cudaEventRecord(p->rev[p->sweeps_issued % kSlots], s);
   if (p->rec_meth != 1) {
-    if (cell_stride != 1 || scatter) return RB_ERR_UNSUPPORTED;  // photon transfer: one GPU
-    rc = launch_rec(p);
+    // photon transfer for this rank's solve layers.  One GPU: all Nl layers (slabs too:
+    // the reference fills both halves before the mirrored copy, slab_base.f90:163).
+    RecCells L = {cell_start, cell_stride, n_local, n_local};
+    if (two) {
+      if (cell_start == 0 && cell_stride == 1) L.n_local = L.n_total = Nl;
+      else L.n_total = n_local + (Nl & 1);   // + the never-solved middle layer of an odd Nl
+    }
+    rc = launch_rec(p, L);
     if (rc) return rc;
   }
   if (timed) cudaEventRecord(sev[0], s);
@@ -872,11 +892,10 @@ extern "C" int rb_plan_peer_alloc(rb_plan *p, int rank, int world, unsigned char
   if (!p || !handle || world < 1 || world > kMaxPeers || rank < 0 || rank >= world ||
       p->d.n_problems != 1 || p->dpeer)
     return RB_ERR_BAD_ARG;
-  if (p->rec_meth != 1) return RB_ERR_UNSUPPORTED;
   const int ncell = plan_sweep_cells(p);
   if (ncell % world != 0) return RB_ERR_BAD_ARG;
   const int n_local = ncell / world;
-  const size_t bytes = 256 + (size_t)2 * world * 5 * n_local * sizeof(double);
+  const size_t bytes = 256 + (size_t)2 * world * kPeerFields * n_local * sizeof(double);
   if (cudaMalloc(&p->dpeer, bytes) != cudaSuccess) {
     cudaGetLastError();
     p->dpeer = nullptr;
@@ -1052,7 +1071,7 @@ extern "C" int rb_plan_pack_cells(rb_plan *p, int cell_start, int cell_stride, d
   const int ncell = plan_sweep_cells(p);
   const int n_local = (cell_start < ncell) ? (ncell - cell_start + cell_stride - 1) / cell_stride : 0;
   if (n_local > 0) {
-    dim3 g((n_local + 127) / 128, 12);
+    dim3 g((n_local + 127) / 128, kExchangeFields);
     k_pack_cells<<<g, 128, 0, p->stream>>>(p->P, cell_start, cell_stride, n_local, dev_send);
     p->info.n_launches += 1;
   }
@@ -1065,7 +1084,7 @@ extern "C" int rb_plan_unpack_cells(rb_plan *p, int world, const double *dev_rec
   const int ncell = plan_sweep_cells(p);
   if (ncell % world != 0) return RB_ERR_BAD_ARG;
   const int n_local = ncell / world;
-  dim3 g((n_local + 127) / 128, 12, world);
+  dim3 g((n_local + 127) / 128, kExchangeFields, world);
   k_unpack_cells<<<g, 128, 0, p->stream>>>(p->P, world, n_local, dev_recv);
   p->info.n_launches += 1;
   CK(cudaGetLastError());

@@ -85,16 +85,20 @@ constexpr int kMaxPeers = 8;
 struct PeerDev {
   int world, rank, n_local, parity;
   unsigned long long epoch;               // flag value that means "this sweep is staged"
-  double *stage[kMaxPeers];               // rank r's staging [2][world][5][n_local]
+  double *stage[kMaxPeers];               // rank r's staging [2][world][6][n_local]
   unsigned long long *flags[kMaxPeers];   // rank r's flags [kMaxPeers], written by its peers
 };
 
-__device__ __forceinline__ void peer_scatter(const PeerDev &Q, int j, const rb_frac_t &x) {
+constexpr int kExchangeFields = 18;  // rb_plan_pack_cells / rb_plan_unpack_cells
+constexpr int kPeerFields = 6;  // five fractions + T (the photon-transfer closures read all T)
+__device__ __forceinline__ void peer_scatter(const PeerDev &Q, int j, const rb_frac_t &x,
+                                             double T) {
   const size_t n = (size_t)Q.n_local;
-  const size_t off = ((size_t)(Q.parity * Q.world + Q.rank) * 5) * n + j;
+  const size_t off = ((size_t)(Q.parity * Q.world + Q.rank) * kPeerFields) * n + j;
   for (int r = 0; r < Q.world; ++r) {
     double *d = Q.stage[r] + off;
     d[0] = x.xH1; d[n] = x.xH2; d[2 * n] = x.xHe1; d[3 * n] = x.xHe2; d[4 * n] = x.xHe3;
+    d[5 * n] = T;
   }
 }
 
@@ -795,7 +799,7 @@ k_cell_solve(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_local)
   P.x[0][c] = x.xH1; P.x[1][c] = x.xH2; P.x[2][c] = x.xHe1;
   P.x[3][c] = x.xHe2; P.x[4][c] = x.xHe3;
   if (P.find_Teq) P.T[c] = T;
-  if (Q.world > 1) peer_scatter(Q, j, x);
+  if (Q.world > 1) peer_scatter(Q, j, x, T);
   if (two_sided(P.geom)) {
     const size_t cm = (size_t)b * P.Nl + (P.Nl - 1 - il);
     P.x[0][cm] = x.xH1; P.x[1][cm] = x.xH2; P.x[2][cm] = x.xHe1;
@@ -909,7 +913,7 @@ k_cell_solve_pce_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int
   zero_absent_species(nH, nHe, xlast);
   P.x[0][c] = xlast.xH1; P.x[1][c] = xlast.xH2; P.x[2][c] = xlast.xHe1;
   P.x[3][c] = xlast.xHe2; P.x[4][c] = xlast.xHe3;
-  if (Q.world > 1) peer_scatter(Q, j, xlast);
+  if (Q.world > 1) peer_scatter(Q, j, xlast, P.T[c]);
   if (two_sided(P.geom)) {
     const size_t cm = (size_t)b * P.Nl + (P.Nl - 1 - il);
     P.x[0][cm] = xlast.xH1; P.x[1][cm] = xlast.xH2; P.x[2][cm] = xlast.xHe1;
@@ -1025,7 +1029,7 @@ k_cell_solve_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_l
   P.x[0][c] = xo.xH1; P.x[1][c] = xo.xH2; P.x[2][c] = xo.xHe1;
   P.x[3][c] = xo.xHe2; P.x[4][c] = xo.xHe3;
   P.T[c] = Tfinal;
-  if (Q.world > 1) peer_scatter(Q, j, xo);
+  if (Q.world > 1) peer_scatter(Q, j, xo, Tfinal);
   if (two_sided(P.geom)) {
     const size_t cm = (size_t)b * P.Nl + (P.Nl - 1 - il);
     P.x[0][cm] = xo.xH1; P.x[1][cm] = xo.xH2; P.x[2][cm] = xo.xHe1;
@@ -1134,14 +1138,16 @@ __global__ void __launch_bounds__(BLOCK) k_exchange_finish(PlanDev P, PeerDev Q,
   __syncthreads();
   if (P.active[0]) {
     const size_t n = (size_t)Q.n_local;
-    const double *st = Q.stage[Q.rank] + (size_t)Q.parity * Q.world * 5 * n;
-    const int total = Q.world * 5 * Q.n_local;
+    const double *st = Q.stage[Q.rank] + (size_t)Q.parity * Q.world * kPeerFields * n;
+    const int total = Q.world * kPeerFields * Q.n_local;
     for (int i = threadIdx.x; i < total; i += BLOCK) {
-      const int j = i % Q.n_local, f = (i / Q.n_local) % 5, g = i / (5 * Q.n_local);
+      const int j = i % Q.n_local, f = (i / Q.n_local) % kPeerFields,
+                g = i / (kPeerFields * Q.n_local);
       const double v = __ldcv(st + i);
       const int il = j * Q.world + g;
-      P.x[f][il] = v;
-      if (two_sided(P.geom)) P.x[f][P.Nl - 1 - il] = v;  // mirrored half
+      double *dst = (f < 5) ? P.x[f] : P.T;
+      dst[il] = v;
+      if (two_sided(P.geom)) dst[P.Nl - 1 - il] = v;  // mirrored half
     }
   }
   __syncthreads();
@@ -1149,13 +1155,14 @@ __global__ void __launch_bounds__(BLOCK) k_exchange_finish(PlanDev P, PeerDev Q,
 }
 
 // ---------------------------------------------------------------------------
-// cell-shard exchange helpers (multi-GPU Jacobi): 12 state fields
-// (5 fractions, T, 6 source rates) of the local cells il = start + j*stride are
-// packed as [12][n_local]; after the all-gather the buffer is [G][12][n_local]
+// cell-shard exchange helpers (multi-GPU Jacobi): 18 state fields
+// (5 fractions, T, 6 source rates, 6 recombination rates) of the local cells
+// il = start + j*stride are packed as [18][n_local]; after the all-gather the buffer is
+// [G][18][n_local]
 // and cell il = j*G + g comes from rank g.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double *plan_field(const PlanDev &P, int f) {
-  return f < 5 ? P.x[f] : (f == 5 ? P.T : P.src[f - 6]);
+  return f < 5 ? P.x[f] : (f == 5 ? P.T : (f < 12 ? P.src[f - 6] : P.rec[f - 12]));
 }
 
 __global__ void k_pack_cells(PlanDev P, int cell_start, int cell_stride, int n_local,
@@ -1171,7 +1178,7 @@ __global__ void k_unpack_cells(PlanDev P, int world, int n_local, const double *
   const int f = blockIdx.y, g = blockIdx.z;
   if (j >= n_local) return;
   const int il = j * world + g;
-  const double v = recv[((size_t)g * 12 + f) * n_local + j];
+  const double v = recv[((size_t)g * gridDim.y + f) * n_local + j];
   double *dst = plan_field(P, f);
   dst[il] = v;
   if (two_sided(P.geom)) dst[P.Nl - 1 - il] = v;  // mirrored half

@@ -47,6 +47,16 @@ struct RecDev {
 
 __device__ __forceinline__ bool plan_outer_first(int geom) { return geom == RB_GEOM_SPHERE_BGND; }
 
+// The closures run for the solve layers of one cell shard: plan cells
+// start + j*stride, j < n_local (all cells on one GPU: 0, 1, Nl).  Slabs sharded over
+// their first half add the never-solved middle layer of an odd Nl as entry n_local.
+struct RecCells {
+  int start, stride, n_local, n_total;
+  __device__ __forceinline__ int cell(int j, int Nl) const {
+    return j < n_local ? start + j * stride : Nl / 2;
+  }
+};
+
 // ---------------------------------------------------------------------------
 // k_rec_prep: one thread per (problem, cell).
 // ---------------------------------------------------------------------------
@@ -188,13 +198,15 @@ __device__ __forceinline__ void rec_leg(int Nq, IRL irl_of, INC add_inc, double 
 
 // k_rec_outward (sphere_base.f90:79-346): routine index 0 = outermost shell; each solve
 // layer collects the flux of the layers at smaller radii.  One warp per solve layer.
-__global__ void __launch_bounds__(128) k_rec_outward(PlanDev P, RecDev R, RecConst K) {
+__global__ void __launch_bounds__(128) k_rec_outward(PlanDev P, RecDev R, RecConst K,
+                                                     RecCells L) {
   const int b = blockIdx.y;
   if (!P.active[b]) return;
-  const int isl = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int j = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int Nl = P.Nl;
-  if (isl >= Nl) return;
+  if (j >= L.n_total) return;
   const bool flip = !plan_outer_first(P.geom);
+  const int isl = flip ? Nl - 1 - L.cell(j, Nl) : L.cell(j, Nl);
   const size_t base = (size_t)b * Nl;
   auto rix = [=](int i) { return base + (flip ? Nl - 1 - i : i); };
   const RecRatios q6 = rec_ratios(P, K);
@@ -223,13 +235,15 @@ __global__ void __launch_bounds__(128) k_rec_outward(PlanDev P, RecDev R, RecCon
 // k_rec_radial (sphere_base.f90:392-750): routine index 1 = innermost shell (1-based as
 // in the Fortran); "lower" leg runs isl, isl-1, .., 1, then through the centre -1, ..,
 // -Nl; "upper" leg isl .. Nl; each contribution weighs one half.  One warp per layer.
-__global__ void __launch_bounds__(128) k_rec_radial(PlanDev P, RecDev R, RecConst K) {
+__global__ void __launch_bounds__(128) k_rec_radial(PlanDev P, RecDev R, RecConst K,
+                                                    RecCells L) {
   const int b = blockIdx.y;
   if (!P.active[b]) return;
-  const int isl1 = blockIdx.x * 4 + (threadIdx.x >> 5) + 1;
+  const int j = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int Nl = P.Nl;
-  if (isl1 > Nl) return;
+  if (j >= L.n_total) return;
   const bool flip = plan_outer_first(P.geom);
+  const int isl1 = flip ? Nl - L.cell(j, Nl) : L.cell(j, Nl) + 1;
   const size_t base = (size_t)b * Nl;
   auto rix1 = [=](int i1) { return base + (flip ? Nl - i1 : i1 - 1); };
   const RecRatios q6 = rec_ratios(P, K);
@@ -297,17 +311,19 @@ __device__ __forceinline__ void iso_step(IsoAcc &a, double ds, const double4 &ka
   a.I[2] = a.I[2] + kb.z * ds * exp_fast<6>(-a.tau[2], s_exp, lane_off);
 }
 
-__global__ void __launch_bounds__(128) k_rec_iso_rays(PlanDev P, RecDev R, int Nmu) {
+__global__ void __launch_bounds__(128) k_rec_iso_rays(PlanDev P, RecDev R, int Nmu, RecCells L) {
   const int b = blockIdx.z;
   if (!P.active[b]) return;
   __shared__ double s_exp[64 * kExpTabCopies];
   fill_exp_table_L<6>(s_exp);
   __syncthreads();
   const unsigned lane_off = (threadIdx.x & (kExpTabCopies - 1)) << 3;
-  const int il = blockIdx.x * blockDim.x + threadIdx.x;  // routine index, 0 = outermost
+  const int jl = blockIdx.x * blockDim.x + threadIdx.x;
   const int imu = blockIdx.y;
   const int Nl = P.Nl;
-  if (il >= Nl) return;
+  if (jl >= L.n_total) return;
+  // routine index, 0 = outermost
+  const int il = plan_outer_first(P.geom) ? L.cell(jl, Nl) : Nl - 1 - L.cell(jl, Nl);
   const double4 *ka = R.recA + (size_t)b * (Nl + 1);
   const double4 *kb = R.recB + (size_t)b * (Nl + 1);
   const double mu = P.mu[imu];
@@ -376,7 +392,7 @@ __global__ void __launch_bounds__(128) k_rec_iso_rays(PlanDev P, RecDev R, int N
 // (exp_small).  Work items = (block of 32 consecutive cells, ray) handed out
 // longest path first by an atomic counter; unclamped square root inside the walk
 // (E_k > p for k <= m, see sphere_ray_pair).  grid = (CTAs per problem, B);
-// items[it] = ilblk | imu << 16.
+// items[it] = jblk | imu << 16, jblk = block of 32 consecutive entries of the cell list.
 // ---------------------------------------------------------------------------
 struct IsoSmem {
   const double *E2;    // [nrec]
@@ -429,7 +445,7 @@ __device__ __forceinline__ void iso_step_s(IsoAcc &a, double ds, const IsoSmem &
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 k_rec_iso_rays_smem(PlanDev P, RecDev R, int Nmu, const unsigned *__restrict__ items, int n_items,
-                    int *work) {
+                    int *work, RecCells L) {
   const int b = blockIdx.y;
   if (!P.active[b]) return;
   extern __shared__ double4 s_iso[];
@@ -465,9 +481,10 @@ k_rec_iso_rays_smem(PlanDev P, RecDev R, int Nmu, const unsigned *__restrict__ i
     if (lane == 0) nxt = atomicAdd(&work[b], 1);
     const unsigned item = items[it];
     const int imu = (int)(item >> 16);
-    const int il_raw = (int)(item & 0xffffu) * 32 + lane;   // routine index, 0 = outermost
-    const bool valid = il_raw < Nl;
-    const int il = valid ? il_raw : Nl - 1;
+    const int j_raw = (int)(item & 0xffffu) * 32 + lane;
+    const bool valid = j_raw < L.n_total;
+    const int pc = L.cell(valid ? j_raw : L.n_total - 1, Nl);
+    const int il = of ? pc : Nl - 1 - pc;   // routine index, 0 = outermost
     const double mu = P.mu[imu];
     const double Ea = of ? E[il] : E[Nl - il], Eb = of ? E[il + 1] : E[Nl - il - 1];
     const double r_ray = (Ea + Eb) * 0.5;
@@ -530,12 +547,13 @@ k_rec_iso_rays_smem(PlanDev P, RecDev R, int Nmu, const unsigned *__restrict__ i
 }
 
 // angle average J = (1/2) sum_mu I w (sphere_base.f90:1020-1032) and the rates (:1037-1061)
-__global__ void k_rec_iso_finish(PlanDev P, RecDev R, RecConst K, int Nmu) {
+__global__ void k_rec_iso_finish(PlanDev P, RecDev R, RecConst K, int Nmu, RecCells L) {
   const int b = blockIdx.y;
   if (!P.active[b]) return;
-  const int il = blockIdx.x * blockDim.x + threadIdx.x;
+  const int jl = blockIdx.x * blockDim.x + threadIdx.x;
   const int Nl = P.Nl;
-  if (il >= Nl) return;
+  if (jl >= L.n_total) return;
+  const int il = plan_outer_first(P.geom) ? L.cell(jl, Nl) : Nl - 1 - L.cell(jl, Nl);
   double J[3] = {0.0, 0.0, 0.0};
   const double4 *I = R.Iray + ((size_t)b * Nl + il) * Nmu;
   for (int imu = 0; imu < Nmu; ++imu) {
@@ -587,13 +605,14 @@ __global__ void k_rec_slab_prefix(PlanDev P, RecDev R, RecConst K) {
 // fills J_int edge by edge and sums from edge 0 upwards: same terms, re-associated).
 // The three lines' J are combined into the six rates by k_rec_slab_finish.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_rec_slab(PlanDev P, RecDev R, double *Jout) {
+__global__ void __launch_bounds__(128) k_rec_slab(PlanDev P, RecDev R, double *Jout, RecCells L) {
   const int b = blockIdx.z;
   if (!P.active[b]) return;
-  const int k = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int jl = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int X = blockIdx.y;
   const int Nl = P.Nl;
-  if (k >= Nl) return;
+  if (jl >= L.n_total) return;
+  const int k = L.cell(jl, Nl);
   const int lane = threadIdx.x & 31;
   const size_t base = (size_t)b * Nl;
   const double *E = P.Edges + (size_t)b * (Nl + 1);
@@ -657,12 +676,14 @@ __global__ void __launch_bounds__(128) k_rec_slab(PlanDev P, RecDev R, double *J
 }
 
 // slab_base.f90:556-572: the six rates from the three lines' J
-__global__ void k_rec_slab_finish(PlanDev P, RecDev R, RecConst K, const double *Jin) {
+__global__ void k_rec_slab_finish(PlanDev P, RecDev R, RecConst K, const double *Jin,
+                                  RecCells L) {
   const int b = blockIdx.y;
   if (!P.active[b]) return;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int jl = blockIdx.x * blockDim.x + threadIdx.x;
   const int Nl = P.Nl;
-  if (k >= Nl) return;
+  if (jl >= L.n_total) return;
+  const int k = L.cell(jl, Nl);
   const double J0 = Jin[((size_t)b * 3 + 0) * Nl + k], J1 = Jin[((size_t)b * 3 + 1) * Nl + k],
                J2 = Jin[((size_t)b * 3 + 2) * Nl + k];
   const size_t c = (size_t)b * Nl + k;

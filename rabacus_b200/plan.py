@@ -158,7 +158,7 @@ class Plan(object):
         check(lib().rb_plan_unpack_cells(self._h, C.c_int(world), C.c_void_p(dev_recv_ptr)))
 
     def shard_buffers(self, world):
-        """(send [12, n_local], recv [world, 12, n_local]) float64 CUDA tensors."""
+        """(send [18, n_local], recv [world, 18, n_local]) float64 CUDA tensors."""
         import torch
         ncell = self.n_sweep_cells()
         if ncell % world != 0:
@@ -166,8 +166,9 @@ class Plan(object):
                              % (ncell, world))
         nloc = ncell // world
         dev = torch.cuda.current_device() if self.device < 0 else self.device
-        send = torch.empty((len(FIELDS), nloc), dtype=torch.float64, device="cuda:%d" % dev)
-        recv = torch.empty((world, len(FIELDS), nloc), dtype=torch.float64,
+        nf = len(FIELDS) + len(REC_FIELDS)
+        send = torch.empty((nf, nloc), dtype=torch.float64, device="cuda:%d" % dev)
+        recv = torch.empty((world, nf, nloc), dtype=torch.float64,
                            device="cuda:%d" % dev)
         return send, recv
 
@@ -196,8 +197,8 @@ class Plan(object):
         check(lib().rb_plan_sweep_sharded(self._h))
 
     def gather_cells(self, rank, world, group=None):
-        """One all-gather of the 12 state fields of every rank's cells (T and the
-        six rates are not exchanged per sweep on the peer path)."""
+        """One all-gather of the 18 state fields of every rank's cells (the twelve
+        rates are not exchanged per sweep on the peer path)."""
         import torch
         import torch.distributed as dist
         send, recv = self.shard_buffers(world)

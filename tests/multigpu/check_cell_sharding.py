@@ -19,14 +19,15 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from rabacus_b200 import configs  # noqa: E402
-from rabacus_b200.plan import FIELDS, Plan  # noqa: E402
+from rabacus_b200.plan import FIELDS, REC_FIELDS, Plan  # noqa: E402
 
 
 def make_plan(cfg, local_rank, **kw):
     Nl, Nnu = cfg["nH"].size, cfg["E_eV"].size
     plan = Plan(configs.GEOM_IDS[cfg["geometry"]], 1, Nl, Nnu, cfg["Nmu"],
                 find_Teq=cfg["find_Teq"], fixed_fcA=cfg["fixed_fcA"], tol=1e-4,
-                device=local_rank, **kw)
+                device=local_rank, i_rec_meth=cfg.get("i_rec_meth", 1),
+                em_fac=cfg.get("em_fac", (1.0, 1.0, 1.0)), **kw)
     plan.set_problem(0, cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], cfg["E_eV"],
                      cfg["shape"], cfg["z"], 0.0)
     plan.upload()
@@ -44,6 +45,23 @@ def main():
              ("sphere 256x128x16 Teq", configs.c4_sphere_bgnd(256, 128, 16, True, nH0=3.0)),
              ("slab2bgnd 512x128", configs.c3_slab_bgnd(512, 128, True)),
              ("slabpln 256x128", configs.c2_slab_plane(256, 128, False))]
+    # recombination-photon transfer under cell sharding: every rank runs the closure for
+    # its own solve layers only (rb_rec.cuh RecCells)
+    for meth, tag in ((2, "outward"), (3, "radial"), (4, "isotropic")):
+        cfg = configs.c4_sphere_bgnd(256, 128, 16, meth == 3, nH0=3.0)
+        cfg["i_rec_meth"] = meth
+        if meth == 4:
+            cfg["em_fac"] = (1.0, 0.7, 1.3)
+        cases.append(("sphere 256 rec %s" % tag, cfg))
+    cfg = configs.c1_iliev_stromgren(256)
+    cfg["i_rec_meth"] = 4
+    cfg["Nmu"] = 8
+    cases.append(("stromgren 256 rec iso", cfg))
+    for nm, cfg in (("slab2bgnd 512 rec ray", configs.c3_slab_bgnd(512, 128, True)),
+                    ("slabpln2 253 rec ray", configs.c2_slab_plane(253, 128, False, True)),
+                    ("slabpln 256 rec ray", configs.c2_slab_plane(256, 128, False))):
+        cfg["i_rec_meth"] = 2
+        cases.append((nm, cfg))
     for name, cfg in cases:
         p1 = make_plan(cfg, local_rank)
         i1 = p1.solve()
@@ -57,7 +75,8 @@ def main():
             n = p.solve_cell_sharded(rank, world)
             out = p.get_problem(0)
             p.close()
-            same = n == i1["iters"] and all(np.array_equal(out[k], ref[k]) for k in FIELDS)
+            same = n == i1["iters"] and all(np.array_equal(out[k], ref[k])
+                                            for k in FIELDS + REC_FIELDS)
             res[mode] = (n, same)
             ok = ok and same
         if rank == 0:
