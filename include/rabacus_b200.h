@@ -159,6 +159,17 @@ int rb_get_kcool(const double *T, const double *fcA_H2, const double *fcA_He2,
                  double *recHe2, double *recHe3, double *cicH1, double *cicHe1,
                  double *cicHe2, double *cecH1, double *cecHe2, double *bremss,
                  double *compton);
+/* Diagnostics for the arithmetic of csrc/rb_fastpow.cuh (x**y of the Hui & Gnedin fits,
+ * hui_gnedin_97.f90:21-322): out[i] = x[i]**y[i], and the 6 + 10 coefficients of
+ * get_kchem_s / get_kcool_s (chem_cool_rates.f90:45-204) as out16[16][n].  on_device = 0
+ * evaluates the same inline source with the host compiler (unit tests without a GPU),
+ * 1 runs one CUDA thread per element.  Not used by any solver entry point. */
+/* on != 0: evaluate the Hui & Gnedin fits with libm / libdevice pow() statement by
+ * statement instead of csrc/rb_fastpow.cuh (A/B tests of the two forms); host build + current device. */
+int rb_diag_use_libm_pow(int on);
+int rb_diag_pow(const double *x, const double *y, int n, double *out, int on_device);
+int rb_diag_hg97(const double *T, const double *fcA_H2, const double *fcA_He2,
+                 const double *fcA_He3, int n, double *out16, int on_device);
 int rb_solve_ce(const double *reH2, const double *reHe2, const double *reHe3,
                 const double *ciH1, const double *ciHe1, const double *ciHe2,
                 int nn, double *xH1, double *xH2, double *xHe1, double *xHe2,

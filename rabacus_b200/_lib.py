@@ -46,7 +46,7 @@ EXPORTS = (
     "rb_strerror", "rb_device_count", "rb_version", "rb_cache_clear",
     "rb_sphere_bgnd_solve", "rb_sphere_stromgren_solve", "rb_slab_bgnd_solve",
     "rb_slab_plane_solve", "rb_set_column_vs_impact",
-    "rb_get_kchem", "rb_get_kcool", "rb_solve_ce", "rb_solve_pce", "rb_solve_pcte",
+    "rb_get_kchem", "rb_get_kcool", "rb_diag_pow", "rb_diag_hg97", "rb_diag_use_libm_pow", "rb_solve_ce", "rb_solve_pce", "rb_solve_pcte",
     "rb_photo_sigma", "rb_photo_Eth", "rb_gauss_legendre",
     "rb_plan_create", "rb_plan_destroy", "rb_plan_set_problem", "rb_plan_upload",
     "rb_plan_thin", "rb_plan_sweep_local", "rb_plan_finish_sweep", "rb_plan_finish_sweep_async",

@@ -1592,6 +1592,88 @@ extern "C" int rb_get_kcool(const double *T, const double *fcA_H2, const double 
   return RB_OK;
 }
 
+// ---------------------------------------------------------------------------
+// diagnostics for the unit tests of rb_fastpow.cuh / hg97_eval: the SAME inline source
+// evaluated by the host compiler (on_device = 0; runs without a GPU, compared with
+// mpmath / the oracle in tests/test_host_logic.py) or by one CUDA thread per element.
+// Not reachable from any solver entry point.
+// ---------------------------------------------------------------------------
+__global__ void k_diag_pow(const double *x, const double *y, int n, double *out) {
+  pow_tables_to_smem();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = pow_fast(x[i], y[i]);
+}
+__global__ void k_diag_hg97(const double *T, const double *a, const double *b, const double *c,
+                            int n, double *out) {
+  pow_tables_to_smem();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rb_kchem_t kc;
+  rb_kcool_t kl;
+  get_kchem_kcool(T[i], a[i], b[i], c[i], kc, kl);
+  const double v[16] = {kc.reH2, kc.reHe2, kc.reHe3, kc.ciH1, kc.ciHe1, kc.ciHe2,
+                        kl.recH2, kl.recHe2, kl.recHe3, kl.cicH1, kl.cicHe1, kl.cicHe2,
+                        kl.cecH1, kl.cecHe2, kl.bremss, kl.compton};
+  for (int q = 0; q < 16; ++q) out[(size_t)q * n + i] = v[q];
+}
+
+extern "C" int rb_diag_use_libm_pow(int on) {
+  h_hg_libm = on ? 1 : 0;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    return RB_OK;  // host build only (CPU unit tests)
+  }
+  CK(cudaMemcpyToSymbol(d_hg_libm, &h_hg_libm, sizeof(int)));   // current device
+  return RB_OK;
+}
+
+extern "C" int rb_diag_pow(const double *x, const double *y, int n, double *out, int on_device) {
+  if (!x || !y || !out || n < 1) return RB_ERR_BAD_ARG;
+  if (!on_device) {
+    for (int i = 0; i < n; ++i) out[i] = pow_fast(x[i], y[i]);
+    return RB_OK;
+  }
+  int rc = need_device();
+  if (rc) return rc;
+  DevBuf in, o;
+  const double *f[2] = {x, y};
+  if ((rc = upload_fields(in, f, 2, n))) return rc;
+  if ((rc = o.alloc((size_t)n))) return rc;
+  k_diag_pow<<<(n + 127) / 128, 128>>>(in.d, in.d + n, n, o.d);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, o.d, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  return RB_OK;
+}
+
+extern "C" int rb_diag_hg97(const double *T, const double *fcA_H2, const double *fcA_He2,
+                            const double *fcA_He3, int n, double *out16, int on_device) {
+  if (!T || !fcA_H2 || !fcA_He2 || !fcA_He3 || !out16 || n < 1) return RB_ERR_BAD_ARG;
+  if (!on_device) {
+    for (int i = 0; i < n; ++i) {
+      rb_kchem_t kc;
+      rb_kcool_t kl;
+      get_kchem_kcool(T[i], fcA_H2[i], fcA_He2[i], fcA_He3[i], kc, kl);
+      const double v[16] = {kc.reH2, kc.reHe2, kc.reHe3, kc.ciH1, kc.ciHe1, kc.ciHe2,
+                            kl.recH2, kl.recHe2, kl.recHe3, kl.cicH1, kl.cicHe1, kl.cicHe2,
+                            kl.cecH1, kl.cecHe2, kl.bremss, kl.compton};
+      for (int q = 0; q < 16; ++q) out16[(size_t)q * n + i] = v[q];
+    }
+    return RB_OK;
+  }
+  int rc = need_device();
+  if (rc) return rc;
+  DevBuf in, o;
+  const double *f[4] = {T, fcA_H2, fcA_He2, fcA_He3};
+  if ((rc = upload_fields(in, f, 4, n))) return rc;
+  if ((rc = o.alloc((size_t)16 * n))) return rc;
+  const size_t nn = n;
+  k_diag_hg97<<<(n + 127) / 128, 128>>>(in.d, in.d + nn, in.d + 2 * nn, in.d + 3 * nn, n, o.d);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out16, o.d, (size_t)16 * n * 8, cudaMemcpyDeviceToHost));
+  return RB_OK;
+}
+
 static int fetch_err(DevBuf &out, size_t off) {
   int err = 0;
   if (cudaMemcpy(&err, out.d + off, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {

@@ -9,6 +9,7 @@
 //     (reference: rabacus/f2py/zhang_jin_f.f90:15-173)
 #pragma once
 #include "rb_common.cuh"
+#include "rb_fastpow.cuh"
 
 namespace rb {
 
@@ -68,9 +69,10 @@ RB_HD double mix_caseAB(double a, double b, double fcA) {
   return pow(10.0, log10(a) * fcA + log10(b) * (1.0 - fcA));
 }
 
-// chem_cool_rates.f90:45-88 (get_kchem_s)
-RB_HDN rb_kchem_t get_kchem(double T, double fcA_H2, double fcA_He2,
-                           double fcA_He3) {
+// chem_cool_rates.f90:45-88 (get_kchem_s), every power through libm / libdevice pow():
+// the statement-by-statement form, used outside the validated range of rb_fastpow.cuh
+RB_HDN rb_kchem_t get_kchem_libm(double T, double fcA_H2, double fcA_He2,
+                                double fcA_He3) {
   const double lH1 = 2.0 * RB_T_H1 / T;
   const double lHe1 = 2.0 * RB_T_He1 / T;
   const double lHe2 = 2.0 * RB_T_He2 / T;
@@ -91,9 +93,9 @@ RB_HDN rb_kchem_t get_kchem(double T, double fcA_H2, double fcA_He2,
   return k;
 }
 
-// chem_cool_rates.f90:147-204 (get_kcool_s)
-RB_HDN rb_kcool_t get_kcool(double T, double fcA_H2, double fcA_He2,
-                           double fcA_He3) {
+// chem_cool_rates.f90:147-204 (get_kcool_s), libm form
+RB_HDN rb_kcool_t get_kcool_libm(double T, double fcA_H2, double fcA_He2,
+                                double fcA_He3) {
   const double lH1 = 2.0 * RB_T_H1 / T;
   const double lHe1 = 2.0 * RB_T_He1 / T;
   const double lHe2 = 2.0 * RB_T_He2 / T;
@@ -131,6 +133,132 @@ RB_HDN rb_kcool_t get_kcool(double T, double fcA_H2, double fcA_He2,
   const double d = 5.5 - log10(T);
   k.bremss = 1.43e-27 * sqrt(T) * (1.1 + 0.34 * exp(-(d * d) / 3.0));
   return k;
+}
+
+// ---------------------------------------------------------------------------
+// The same fits with the powers of rb_fastpow.cuh (every statement keeps the reference's
+// operation order; only x**y is evaluated by exp_dd(y log_dd(x)), < 0.53 ulp) and with the
+// sub-expressions that get_kchem_s and get_kcool_s both evaluate computed once:
+// T**-1.5, the three Lotz collisional-ionisation fits (ci* and cic* differ by kB T_X,
+// hui_gnedin_97.f90:252-277), the dielectronic term, the HeII case A/B fits, the
+// exp(-0.75 lam/2) factors.  One temperature probe of solve_pcte: 43 powers from 27
+// logarithms instead of 61 pow() calls.
+// ---------------------------------------------------------------------------
+struct HgBase {  // lam = 2 T_X / T and its logarithm
+  double lam;
+  DD L;
+};
+RB_HD HgBase hg_base(double lam) {
+  HgBase b;
+  b.lam = lam;
+  b.L = log_dd(lam);
+  return b;
+}
+RB_HD double hg_pw(const HgBase &b, double y) { return pow_from_log_nf(b.L, y); }
+// (1 + (lam/t3)^t4)^t5
+RB_HD double hg_den(const HgBase &b, double t3, double t4, double t5) {
+  return pow_fast_nf(1.0 + pow_fast_nf(b.lam / t3, t4), t5);
+}
+RB_HD double hg_ferland_f(const HgBase &b, double t1, double t2, double t3, double t4, double t5) {
+  return t1 * hg_pw(b, t2) / hg_den(b, t3, t4, t5);
+}
+RB_HD double mix_caseAB_f(double a, double b, double fcA) {
+  return pow10_fast_nf(log10_call(a) * fcA + log10_call(b) * (1.0 - fcA));
+}
+
+// valid range of the fast evaluation (all bases normal, all |y log x| < 700);
+// rb_diag_use_libm_pow(1) forces the libm statement form everywhere (A/B tests)
+static int h_hg_libm = 0;
+#ifdef __CUDACC__
+static __device__ int d_hg_libm = 0;
+#endif
+RB_HD bool hg_fast_ok(double T) {
+#ifdef __CUDA_ARCH__
+  if (d_hg_libm) return false;
+#else
+  if (h_hg_libm) return false;
+#endif
+  return T >= 1.0 && T <= 1.0e12;
+}
+
+template <bool CHEM, bool COOL>
+RB_HD void hg97_eval(double T, double fcA_H2, double fcA_He2, double fcA_He3, rb_kchem_t &kc,
+                     rb_kcool_t &kl) {
+  const HgBase H1 = hg_base(2.0 * RB_T_H1 / T);
+  const HgBase He1 = hg_base(2.0 * RB_T_He1 / T);
+  const HgBase He2 = hg_base(2.0 * RB_T_He2 / T);
+  const double Tm15 = pow_fast_nf(T, -1.5);
+  // Lotz fits, hui_gnedin_97.f90:101-155 (rates) = :252-277 (cooling) / (kB T_X)
+  const double lotzH1 = 21.11 * Tm15 * exp_call(-H1.lam * 0.5) * hg_pw(H1, -1.089) /
+                        hg_den(H1, 0.354, 0.874, 1.101);
+  const double lotzHe1 = 32.38 * Tm15 * exp_call(-He1.lam * 0.5) * hg_pw(He1, -1.146) /
+                         hg_den(He1, 0.416, 0.987, 1.056);
+  const double lotzHe2 = 19.95 * Tm15 * exp_call(-He2.lam * 0.5) * hg_pw(He2, -1.089) /
+                         hg_den(He2, 0.553, 0.735, 1.275);
+  const double eHe2 = exp_call(-0.75 * He2.lam * 0.5);
+  const double di = 1.90e-3 * Tm15 * eHe2 * (1.0 + 0.3 * exp_call(-0.15 * He2.lam * 0.5));
+  const double he2a = 3.0e-14 * hg_pw(He1, 0.654);
+  const double he2b = 1.26e-14 * hg_pw(He1, 0.750);
+  if (CHEM) {  // chem_cool_rates.f90:45-88
+    kc.reH2 = mix_caseAB_f(hg_ferland_f(H1, 1.269e-13, 1.503, 0.522, 0.470, 1.923),
+                           hg_ferland_f(H1, 2.753e-14, 1.500, 2.740, 0.407, 2.242), fcA_H2);
+    kc.reHe2 = mix_caseAB_f(he2a, he2b, fcA_He2);
+    kc.reHe2 = kc.reHe2 + di;
+    kc.reHe3 = mix_caseAB_f(hg_ferland_f(He2, 2.0 * 1.269e-13, 1.503, 0.522, 0.470, 1.923),
+                            hg_ferland_f(He2, 2.0 * 2.753e-14, 1.500, 2.740, 0.407, 2.242),
+                            fcA_He3);
+    kc.ciH1 = lotzH1;
+    kc.ciHe1 = lotzHe1;
+    kc.ciHe2 = lotzHe2;
+  }
+  if (COOL) {  // chem_cool_rates.f90:147-204
+    const double recH2a = 1.778e-29 * T * hg_pw(H1, 1.965) / hg_den(H1, 0.541, 0.502, 2.697);
+    const double recH2b = 3.435e-30 * T * hg_pw(H1, 1.970) / hg_den(H1, 2.250, 0.376, 3.720);
+    kl.recH2 = mix_caseAB_f(recH2a, recH2b, fcA_H2);
+    const double recHe2a = RB_KB_ERG_K * T * he2a;
+    const double recHe2b = RB_KB_ERG_K * T * he2b;
+    kl.recHe2 = mix_caseAB_f(recHe2a, recHe2b, fcA_He2);
+    kl.recHe2 = kl.recHe2 + 0.75 * RB_KB_ERG_K * RB_T_He2 * di;
+    const double recHe3a =
+        (8.0 * 1.778e-29) * T * hg_pw(He2, 1.965) / hg_den(He2, 0.541, 0.502, 2.697);
+    const double recHe3b =
+        (8.0 * 3.435e-30) * T * hg_pw(He2, 1.970) / hg_den(He2, 2.250, 0.376, 3.720);
+    kl.recHe3 = mix_caseAB_f(recHe3a, recHe3b, fcA_He3);
+    kl.cicH1 = RB_KB_ERG_K * RB_T_H1 * lotzH1;
+    kl.cicHe1 = RB_KB_ERG_K * RB_T_He1 * lotzHe1;
+    kl.cicHe2 = RB_KB_ERG_K * RB_T_He2 * lotzHe2;
+    const double den = 1.0 + sqrt(T * 1.0e-5);
+    kl.cecH1 = 7.5e-19 * exp_call(-0.75 * H1.lam * 0.5) / den;
+    kl.cecHe2 = 5.54e-17 * pow_fast_nf(1.0 / T, 0.397) * eHe2 / den;
+    kl.compton = 5.65e-36;
+    const double d = 5.5 - log10_call(T);
+    kl.bremss = 1.43e-27 * sqrt(T) * (1.1 + 0.34 * exp_call(-(d * d) / 3.0));
+  }
+}
+
+RB_HDN rb_kchem_t get_kchem(double T, double fcA_H2, double fcA_He2, double fcA_He3) {
+  if (!hg_fast_ok(T)) return get_kchem_libm(T, fcA_H2, fcA_He2, fcA_He3);
+  rb_kchem_t kc;
+  rb_kcool_t kl;
+  hg97_eval<true, false>(T, fcA_H2, fcA_He2, fcA_He3, kc, kl);
+  return kc;
+}
+RB_HDN rb_kcool_t get_kcool(double T, double fcA_H2, double fcA_He2, double fcA_He3) {
+  if (!hg_fast_ok(T)) return get_kcool_libm(T, fcA_H2, fcA_He2, fcA_He3);
+  rb_kchem_t kc;
+  rb_kcool_t kl;
+  hg97_eval<false, true>(T, fcA_H2, fcA_He2, fcA_He3, kc, kl);
+  return kl;
+}
+// both sets at one temperature (one probe of solve_pcte, ion_solver.f90:1089-1134)
+RB_HDN void get_kchem_kcool(double T, double fcA_H2, double fcA_He2, double fcA_He3,
+                            rb_kchem_t &kc, rb_kcool_t &kl) {
+  if (!hg_fast_ok(T)) {
+    kc = get_kchem_libm(T, fcA_H2, fcA_He2, fcA_He3);
+    kl = get_kcool_libm(T, fcA_H2, fcA_He2, fcA_He3);
+    return;
+  }
+  hg97_eval<true, true>(T, fcA_H2, fcA_He2, fcA_He3, kc, kl);
 }
 
 // chem_cool_rates.f90:268-284

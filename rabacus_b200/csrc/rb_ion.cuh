@@ -166,8 +166,9 @@ RB_HDN int solve_pce(double nH, double nHe, const rb_kchem_t &k, double H1i,
 
 RB_HDN int get_dudT(double nH, double nHe, double T, const PhotoRates &p,
                    double z, double Hz, const CaseA &fc, double tol, double &dudT) {
-  const rb_kchem_t kc = get_kchem(T, fc.H2, fc.He2, fc.He3);
-  const rb_kcool_t kl = get_kcool(T, fc.H2, fc.He2, fc.He3);
+  rb_kchem_t kc;
+  rb_kcool_t kl;
+  get_kchem_kcool(T, fc.H2, fc.He2, fc.He3, kc, kl);
   rb_frac_t x;
   const int rc = solve_pce(nH, nHe, kc, p.H1i, p.He1i, p.He2i, tol, x);
   if (rc) return rc;
@@ -183,8 +184,9 @@ RB_HDN int get_dudT(double nH, double nHe, double T, const PhotoRates &p,
 // fractions (solve_pcte's last statement re-solves at that same T).
 RB_HDN int probe_T(double nH, double nHe, double T, const PhotoRates &p, double z,
                    double Hz, const CaseA &fc, double tol, double &dudT, rb_frac_t &x) {
-  const rb_kchem_t kc = get_kchem(T, fc.H2, fc.He2, fc.He3);
-  const rb_kcool_t kl = get_kcool(T, fc.H2, fc.He2, fc.He3);
+  rb_kchem_t kc;
+  rb_kcool_t kl;
+  get_kchem_kcool(T, fc.H2, fc.He2, fc.He3, kc, kl);
   const int rc = solve_pce(nH, nHe, kc, p.H1i, p.He1i, p.He2i, tol, x);
   if (rc) return rc;
   const double heat =

@@ -766,6 +766,7 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int cpu) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_cell_solve(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_local) {
+  pow_tables_to_smem();
   const int b = blockIdx.y;
   if (!P.active[b]) return;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -943,6 +944,7 @@ k_cell_solve_pce_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int
 template <int G>
 __global__ void __launch_bounds__(128)
 k_cell_solve_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_local) {
+  pow_tables_to_smem();
   const int b = blockIdx.y;
   if (!P.active[b]) return;
   constexpr int L = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : 2;
@@ -1351,6 +1353,7 @@ RB_LS_UNROLL
 // one cell per thread.
 template <int CPT>
 __global__ void __launch_bounds__(512) k_thin_state(PlanDev P, int csize) {
+  pow_tables_to_smem();
   const int b = blockIdx.x / csize, crank = blockIdx.x % csize;
   const int Nl = P.Nl;
   __shared__ int s_flags[2 * kMaxCluster];
@@ -1463,6 +1466,7 @@ __global__ void k_column_vs_impact(const double *E, const double *nH, const doub
 __global__ void k_kchem(const double *T, const double *a, const double *b_, const double *c,
                         int nn, double *o0, double *o1, double *o2, double *o3, double *o4,
                         double *o5) {
+  pow_tables_to_smem();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nn) return;
   const rb_kchem_t k = get_kchem(T[i], a[i], b_[i], c[i]);
@@ -1472,6 +1476,7 @@ __global__ void k_kchem(const double *T, const double *a, const double *b_, cons
 
 __global__ void k_kcool(const double *T, const double *a, const double *b_, const double *c,
                         int nn, double *o) {  // o: [10][nn]
+  pow_tables_to_smem();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nn) return;
   const rb_kcool_t k = get_kcool(T[i], a[i], b_[i], c[i]);
@@ -1509,6 +1514,7 @@ __global__ void k_zone_pce(const double *in, int nn, double tol, double *out, in
 // in: [11][nn] = nH,nHe,H1i,He1i,He2i,H1h,He1h,He2h,fcA_H2,fcA_He2,fcA_He3 ; out [6][nn]
 __global__ void k_zone_pcte(const double *in, int nn, double z, double Hz, double tol,
                             double *out, int *err) {
+  pow_tables_to_smem();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nn) return;
   const size_t n = (size_t)nn;
@@ -1528,6 +1534,7 @@ template <int CPT>
 __global__ void __launch_bounds__(512)
 k_zone_lockstep(const double *in, int nn, double z, double Hz, double tol, double *out,
                 int *err, int pcte) {
+  pow_tables_to_smem();
   const size_t n = (size_t)nn;
   double nH[CPT], nHe[CPT], T[CPT];
   PhotoRates p[CPT];

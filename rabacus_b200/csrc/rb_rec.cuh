@@ -61,6 +61,7 @@ struct RecCells {
 // k_rec_prep: one thread per (problem, cell).
 // ---------------------------------------------------------------------------
 __global__ void k_rec_prep(PlanDev P, RecDev R, RecConst K, int rec_meth) {
+  pow_tables_to_smem();
   const int b = blockIdx.y;
   if (!P.active[b]) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

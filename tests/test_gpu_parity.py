@@ -602,3 +602,29 @@ def test_absent_species(orc, spec128):
     assert not bad, bad
     for n in ("xHe1", "xHe2", "xHe3"):
         assert np.all(g[n][::3] == 0.0) and np.all(o[n][::3] == 0.0)
+
+
+# ----------------------------------------------------------------- table-driven powers (rb_fastpow.cuh)
+def test_fastpow_device_equals_host_build_bit_for_bit():
+    """pow_fast is IEEE add / multiply / fma and table reads only: the sm_100a build and the
+    host build of the same source give identical bits (the host build is checked against
+    mpmath in tests/test_host_logic.py)."""
+    from test_host_logic import _diag_pow, fastpow_samples
+    x, y = fastpow_samples(200000, seed=5)
+    assert np.array_equal(_diag_pow(x, y, 1), _diag_pow(x, y, 0))
+
+
+def test_hg97_device_coefficients_match_oracle(orc):
+    """All 16 rate / cooling coefficients of one temperature probe, CUDA fast evaluation
+    vs the oracle's libm statement form, over the solver's range and outside it."""
+    from test_host_logic import _diag_hg97
+    rng = np.random.default_rng(7)
+    n = 100000
+    T = 10 ** rng.uniform(0.0, 12.0, n)
+    T[: n // 2] = 10 ** rng.uniform(np.log10(7.5e3), 5.0, n // 2)
+    f = [rng.choice([0.0, 1.0, 0.3, 0.77], n) for _ in range(3)]
+    out = _diag_hg97(T, *f, on_device=1)
+    ref = np.array(list(orc.get_kchem(T, *f)) + list(orc.get_kcool(T, *f)))
+    with np.errstate(all="ignore"):
+        rel = np.where(out == ref, 0.0, np.abs(out - ref) / np.abs(ref))
+    assert np.nanmax(rel) <= 2e-14
