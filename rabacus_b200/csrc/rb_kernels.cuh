@@ -764,6 +764,8 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int cpu) {
 // the source rates (sphere_bgnd.f90:861-881).  Two-sided slabs compute the
 // first half and mirror (slab_bgnd.f90:842-865).
 // ---------------------------------------------------------------------------
+// (128 registers / 4 CTAs per SM: capping at 96 / 80 / 64 registers for 5 / 6 / 8 CTAs
+// measured 18.1 / 17.3 / 18.1 ms against 17.3 ms on a 2048-problem find_Teq batch)
 __global__ void __launch_bounds__(128)
 k_cell_solve(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_local) {
   pow_tables_to_smem();
