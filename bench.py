@@ -366,6 +366,23 @@ def main():
                "start, %d sweeps to tol=1e-4, download)" % iters, "solve_wall_ms": solve_ms,
                "sweeps": iters}
 
+    # the workload's second flavour ("both fixed T and find_Teq"): wall time of
+    # one converged equilibrium-temperature solve through the same entry point
+    solve_teq = None
+    if e2e is not None and world == 1 and not args.find_Teq:
+        def teq_call():
+            T = cfg["T"].copy()
+            rabacus_fc.sphere_bgnd.sphere_bgnd_solve(
+                cfg["Edges"].copy(), cfg["nH"].copy(), cfg["nHe"].copy(), T, args.Nmu,
+                cfg["E_eV"], cfg["shape"], 1, 1.0, 1, 1, 1, 0, 1.0, 1.0, 1.0,
+                cfg["z"], 0.0, 1e-4, args.Nl, args.Nnu)
+            return dict(rabacus_fc.last_info)
+        teq_call()
+        t0 = time.perf_counter()
+        inf = teq_call()
+        solve_teq = {"sweeps_to_converge": int(inf["iters"]),
+                     "wall_ms": (time.perf_counter() - t0) * 1e3}
+
     if sampler:  # sampled over the kernel-timed region and the e2e solves
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -449,12 +466,13 @@ def main():
                                      (", fractions exchanged by remote stores over NVLink peer "
                                       "memory + flag barrier (no collective per sweep)"
                                       if args.exchange == "peer" else
-                                      ", NCCL all-gather of 12 state fields per sweep")),
+                                      ", NCCL all-gather of 18 state fields per sweep")),
                    "l2": "256 MiB scratch overwritten between steps (not timed); working set "
                          "per sweep ~25 MB of column data, compute bound"},
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "clocks": sampler.summary() if sampler else None,
         "solve": {"sweeps_to_converge": iters, "wall_ms": solve_ms},
+        "solve_find_Teq": solve_teq,
     }
     print(json.dumps(line), file=out, flush=True)
     if dist is not None:
