@@ -274,3 +274,11 @@ def shard_problems(n_problems, rank, world):
     lo = min(n_problems, rank * per)
     hi = min(n_problems, lo + per)
     return lo, hi
+
+
+def deal_problems(n_problems, rank, world):
+    """Shuffled deal of a problem batch (balances sweep counts across ranks); see
+    :func:`rabacus_b200.sharding.deal_problems`."""
+    from .sharding import deal_problems as _deal
+    return _deal(n_problems, rank, world)
+

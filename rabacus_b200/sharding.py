@@ -39,3 +39,16 @@ def shard_problems(n_problems, rank, world):
     per = (n_problems + world - 1) // world
     lo = min(n_problems, rank * per)
     return lo, min(n_problems, lo + per)
+
+
+def deal_problems(n_problems, rank, world, seed=0):
+    """Shuffled deal of a problem batch: a fixed pseudo-random permutation (same on every
+    rank) dealt cyclically; returns this rank's problem indices, ascending.  A parameter
+    sweep is ordered along its axes and the sweep count varies smoothly along them, so
+    contiguous blocks leave the rank with the slowest corner of the grid behind (C5 with
+    find_Teq on 8 GPUs: 0.84 s for the slowest block against 0.61 s for the fastest), and
+    a plain cyclic deal aliases with an axis whose length is a multiple of the world size
+    (z has 16 values: ranks 0..7 would only ever see two redshifts each).  No
+    communication in any case."""
+    perm = np.random.default_rng(seed).permutation(n_problems)
+    return np.sort(perm[rank::world])

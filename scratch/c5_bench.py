@@ -1,13 +1,13 @@
 """C5 (BASELINE.json configs[4]): parameter sweep of 8192 independent SphereBgnd solves
-(32 nH0 x 16 R x 16 z; Nl=512, Nnu=128, Nmu=32), problems block-partitioned over the
-ranks, no communication.  Prints one JSON line (rank 0): whole-job evals/s over full solves."""
+(32 nH0 x 16 R x 16 z; Nl=512, Nnu=128, Nmu=32), problems dealt (shuffled) over the
+ranks (--block: contiguous blocks), no communication.  Prints one JSON line (rank 0): whole-job evals/s over full solves."""
 import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from rabacus_b200 import configs
-from rabacus_b200.plan import Plan, shard_problems
+from rabacus_b200.plan import Plan, shard_problems, deal_problems
 
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -19,8 +19,11 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 t0 = time.perf_counter()
 probs = configs.c5_sweep(find_Teq=find_Teq)
-lo, hi = shard_problems(len(probs), rank, world)
-mine = probs[lo:hi]
+if "--block" in sys.argv:
+    lo, hi = shard_problems(len(probs), rank, world)
+    mine = probs[lo:hi]
+else:
+    mine = [probs[i] for i in deal_problems(len(probs), rank, world)]
 t_build = time.perf_counter() - t0
 plan = Plan(0, len(mine), 512, 128, 32, find_Teq=find_Teq, tol=1e-4, device=local)
 t0 = time.perf_counter()

@@ -98,3 +98,9 @@ def test_index_conventions():
     parts = [sharding.shard_problems(8192, r, 8) for r in range(8)]
     assert parts[0] == (0, 1024) and parts[-1] == (7168, 8192)
     assert sharding.shard_problems(10, 3, 4) == (9, 10) and sharding.shard_problems(3, 3, 4) == (3, 3)
+    deals = [sharding.deal_problems(8192, r, 8) for r in range(8)]
+    assert all(d.size == 1024 for d in deals) and all(np.all(np.diff(d) > 0) for d in deals)
+    # no aliasing with a 16-long fastest axis: every rank sees every value of i % 16
+    assert all(np.unique(d % 16).size == 16 for d in deals)
+    assert np.array_equal(np.sort(np.concatenate(deals)), np.arange(8192))
+    assert [sharding.deal_problems(10, r, 4).size for r in range(4)] == [3, 3, 2, 2]
