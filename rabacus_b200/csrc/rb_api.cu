@@ -222,6 +222,8 @@ struct rb_plan {
   int graph_nl[kSlots] = {0};          // kernel launches inside each graph
   PlanDev gP;                           // kernel arguments the graphs were captured with
   bool capturing = false, graphs_ok = true;
+  int active_hint = 0;   // problems still iterating at the last read-back (0: all)
+  int gG = 0;            // lane-group size of the cell solver the graphs were captured with
   bool slot_timed[kSlots] = {false};    // stage events of that slot are valid (direct launches)
   // cell sharding over peer memory
   PeerDev Q;                    // world == 1 when not connected
@@ -495,6 +497,7 @@ extern "C" int rb_plan_upload(rb_plan *p) {
   for (int q = 0; q < kSlots; ++q) p->hflags[3 * B + q] = 0;
   CK(cudaMemcpyAsync(p->dflags, p->hflags, (3 * B + kSlots) * sizeof(int), cudaMemcpyHostToDevice, s));
   p->sweeps_issued = p->sweeps_polled = 0;
+  p->active_hint = 0;
   p->last_active = (int)B;
   CK(cudaMemsetAsync(p->dresid, 0, B * 8, s));
   memset(&p->info, 0, sizeof(p->info));
@@ -804,6 +807,27 @@ static int launch_rec(rb_plan *p, const RecCells &L) {
   return RB_OK;
 }
 
+// Lanes per cell in the cell solver.  G lanes run the bisection (on T with find_Teq:
+// k_cell_solve_spec, on n_e at fixed T: k_cell_solve_pce_spec) speculatively; G is the
+// largest group that keeps the cells of the problems STILL ITERATING (as of the last
+// convergence read-back: the tail of a batch is a few problems, whose serial bisections
+// would be pure latency) within ~one wave of resident threads and the grid - which spans
+// all problems, converged ones return at once - below 2^17 CTAs; larger batches run one
+// thread per cell.  Every G gives the serial algorithm's results bit for bit.
+static int cell_group_size(const rb_plan *p, int n_local) {
+  const int B = p->d.n_problems;
+  const char *fenv = getenv("RB_SPEC_G");  // testing knob: force the group size
+  const int forced = fenv ? atoi(fenv) : 0;
+  if (forced == 1 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
+  const int live = (p->active_hint > 0) ? std::min(B, p->active_hint) : B;
+  const long long cells_now = (long long)n_local * live;
+  const long long budget = (long long)p->n_sm * 512;
+  int G = 32;
+  while (G > 1 && cells_now * G > budget) G >>= 1;
+  while (G > 1 && ((long long)n_local * G + 127) / 128 * B > (1ll << 17)) G >>= 1;
+  return G < 4 ? 1 : G;
+}
+
 static int sweep_impl(rb_plan *p, int cell_start, int cell_stride, bool scatter) {
   if (!p || cell_start < 0 || cell_stride < 1) return RB_ERR_BAD_ARG;
   PeerDev Q = p->Q;
@@ -845,16 +869,7 @@ static int sweep_impl(rb_plan *p, int cell_start, int cell_stride, bool scatter)
     // G lanes per cell run the bisection (on T with find_Teq: k_cell_solve_spec, on n_e at
     // fixed T: k_cell_solve_pce_spec) speculatively; G is the largest group that keeps the
     // launch within ~one wave of resident threads, larger batches run one thread per cell.
-    int G = 32;
-    {
-      const char *fenv = getenv("RB_SPEC_G");  // testing knob: force the group size
-      const int forced = fenv ? atoi(fenv) : 0;
-      const long long cells_now = (long long)n_local * B;
-      const long long budget = (long long)p->n_sm * 512;
-      while (G > 1 && cells_now * G > budget) G >>= 1;
-      if (G < 4) G = 1;
-      if (forced == 1 || forced == 4 || forced == 8 || forced == 16 || forced == 32) G = forced;
-    }
+    const int G = cell_group_size(p, n_local);
     if (G == 1) {
       dim3 gs3((n_local + 127) / 128, B);
       k_cell_solve<<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local);
@@ -986,10 +1001,12 @@ static int sweep_graph(rb_plan *p) {
   if (p->sweeps_issued - p->sweeps_polled >= kSlots - 1) return RB_ERR_BAD_ARG;
   const int slot = (int)(p->sweeps_issued % kSlots);
   cudaStream_t s = p->stream;
-  if (memcmp(&p->gP, &p->P, sizeof(PlanDev)) != 0) {
+  const int Gnow = cell_group_size(p, plan_sweep_cells(p));
+  if (memcmp(&p->gP, &p->P, sizeof(PlanDev)) != 0 || Gnow != p->gG) {
     for (auto &g : p->gexec)
       if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     p->gP = p->P;
+    p->gG = Gnow;
   }
   if (!p->gexec[slot]) {
     const int nl0 = p->info.n_launches;
@@ -1152,6 +1169,7 @@ static int solve_loop(rb_plan *p, rb_info *info, bool sharded) {
     if (rc) return rc;
     evals += rb_plan_evals_per_sweep(p) * active_during;
     active_during = n_active;
+    p->active_hint = n_active;
     if (n_active == 0) stop = true;
   }
   cudaEventRecord(p->ev[5], p->stream);

@@ -19,11 +19,14 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 t0 = time.perf_counter()
 probs = configs.c5_sweep(find_Teq=find_Teq)
+prank, pworld = rank, world
+if "--as-rank" in sys.argv:   # one rank's share of an N-GPU run, alone on one GPU: --as-rank r/N
+    prank, pworld = (int(v) for v in sys.argv[sys.argv.index("--as-rank") + 1].split("/"))
 if "--block" in sys.argv:
-    lo, hi = shard_problems(len(probs), rank, world)
+    lo, hi = shard_problems(len(probs), prank, pworld)
     mine = probs[lo:hi]
 else:
-    mine = [probs[i] for i in deal_problems(len(probs), rank, world)]
+    mine = [probs[i] for i in deal_problems(len(probs), prank, pworld)]
 t_build = time.perf_counter() - t0
 plan = Plan(0, len(mine), 512, 128, 32, find_Teq=find_Teq, tol=1e-4, device=local)
 t0 = time.perf_counter()
