@@ -58,7 +58,9 @@ def main():
     cfg["Nmu"] = 8
     cases.append(("stromgren 256 rec iso", cfg))
     for nm, cfg in (("slab2bgnd 512 rec ray", configs.c3_slab_bgnd(512, 128, True)),
-                    ("slabpln2 253 rec ray", configs.c2_slab_plane(253, 128, False, True)),
+                    # odd Nl: the middle layer is never solved; Nl/2 divisible by the world size
+                    ("slabpln2 odd rec ray", configs.c2_slab_plane(2 * world * 31 + 1, 128, False,
+                                                                   True)),
                     ("slabpln 256 rec ray", configs.c2_slab_plane(256, 128, False))):
         cfg["i_rec_meth"] = 2
         cases.append((nm, cfg))
@@ -84,7 +86,7 @@ def main():
                                                                   res["nccl"]), flush=True)
     # timing at C4 size: peer-memory path vs NCCL path, device ms per sweep
     cfg = configs.c4_sphere_bgnd(4096, 512, 256, False)
-    for mode in ("peer", "nccl"):
+    for mode in (() if os.environ.get("RB_CHECK_NO_TIMING") else ("peer", "nccl")):
         p = make_plan(cfg, local_rank, max_sweeps=-(10 ** 9))
         torch.cuda.synchronize(); dist.barrier()
         if mode == "peer":
