@@ -628,3 +628,24 @@ def test_hg97_device_coefficients_match_oracle(orc):
     with np.errstate(all="ignore"):
         rel = np.where(out == ref, 0.0, np.abs(out - ref) / np.abs(ref))
     assert np.nanmax(rel) <= 2e-14
+
+
+def test_solve_with_table_driven_powers_equals_libm_form(spec128):
+    """A/B over whole find_Teq solves: the Hui & Gnedin fits through rb_fastpow.cuh vs through
+    libdevice's pow(): same sweep count, temperatures bit-identical, rates <= 1e-12,
+    fractions within the fraction policy."""
+    import ctypes as C
+    from rabacus_b200 import _lib
+    cfgs = [_small_sphere(96, 128, 8, True, nH0=1.0, spec=spec128),
+            configs.c2_slab_plane(128, 128, True), configs.c3_slab_bgnd(128, 128, True)]
+    for cfg in cfgs:
+        fast = run_gpu(cfg)
+        assert _lib.lib().rb_diag_use_libm_pow(C.c_int(1)) == 0
+        try:
+            slow = run_gpu(cfg)
+        finally:
+            assert _lib.lib().rb_diag_use_libm_pow(C.c_int(0)) == 0
+        assert fast["iters"] == slow["iters"]
+        assert np.array_equal(fast["T"], slow["T"])
+        worst, bad = compare(fast, slow)
+        assert not bad, bad

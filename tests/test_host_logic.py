@@ -155,3 +155,22 @@ def test_hg97_fast_evaluation_matches_the_libm_statement_form(orc):
         rel = np.where(out == ref, 0.0, np.abs(out - ref) / np.abs(ref))
     assert np.nanmax(rel) <= 2e-14
     assert np.array_equal(out[:, -4:], ref[:, -4:], equal_nan=True)
+
+
+def test_hg97_libm_statement_form_is_bit_identical_to_the_oracle(orc):
+    """rb_diag_use_libm_pow(1) selects the statement-by-statement libm form of the fits; built
+    by the host compiler it calls the same glibc pow/exp/log10 as the oracle's C and must
+    agree with it bit for bit -- the two codings of chem_cool_rates.f90:45-204 pin each other."""
+    import ctypes as C
+    from rabacus_b200 import _lib
+    rng = np.random.default_rng(3)
+    n = 5000
+    T = 10 ** rng.uniform(2.0, 9.0, n)
+    f = [rng.choice([0.0, 1.0, 0.5], n) for _ in range(3)]
+    assert _lib.lib().rb_diag_use_libm_pow(C.c_int(1)) == 0
+    try:
+        out = _diag_hg97(T, *f)
+    finally:
+        assert _lib.lib().rb_diag_use_libm_pow(C.c_int(0)) == 0
+    ref = np.array(list(orc.get_kchem(T, *f)) + list(orc.get_kcool(T, *f)))
+    assert np.array_equal(out, ref)
