@@ -223,7 +223,8 @@ struct rb_plan {
   PlanDev gP;                           // kernel arguments the graphs were captured with
   bool capturing = false, graphs_ok = true;
   int active_hint = 0;   // problems still iterating at the last read-back (0: all)
-  int gG = 0;            // lane-group size of the cell solver the graphs were captured with
+  int g_live = 0;        // live_problems() the graphs were captured for
+  int direct_live = -1;  // live_problems() of the last directly launched sweep
   bool slot_timed[kSlots] = {false};    // stage events of that slot are valid (direct launches)
   // cell sharding over peer memory
   PeerDev Q;                    // world == 1 when not connected
@@ -498,6 +499,7 @@ extern "C" int rb_plan_upload(rb_plan *p) {
   CK(cudaMemcpyAsync(p->dflags, p->hflags, (3 * B + kSlots) * sizeof(int), cudaMemcpyHostToDevice, s));
   p->sweeps_issued = p->sweeps_polled = 0;
   p->active_hint = 0;
+  p->direct_live = -1;
   p->last_active = (int)B;
   CK(cudaMemsetAsync(p->dresid, 0, B * 8, s));
   memset(&p->info, 0, sizeof(p->info));
@@ -593,6 +595,20 @@ static int set_smem(K kern, size_t smem) {
   return RB_OK;
 }
 
+// Problems of the batch that were still iterating at the last convergence read-back,
+// rounded up to B / 4^k.  The launch shapes that spread ONE problem's work over the GPU
+// (CTAs per problem and chunks per walk in the column kernel, cells per work unit in the
+// frequency kernel, lanes per cell in the cell solver) follow it, so that the tail of a
+// batch -- a handful of problems left -- still fills the SMs.  None of these choices
+// changes a result bit.  Captured graphs are keyed on it (sweep_graph).
+static int live_problems(const rb_plan *p) {
+  const int B = p->d.n_problems;
+  if (p->active_hint <= 0 || p->active_hint >= B) return B;
+  int q = B;
+  while (q / 4 >= p->active_hint && q / 4 >= 1) q /= 4;
+  return q;
+}
+
 static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, int n_local) {
   const int Nl = p->d.Nl, B = p->d.n_problems;
   cudaStream_t s = p->stream;
@@ -614,7 +630,8 @@ static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, in
   // GPUs, small grids): cut every walk into nchunk pieces (separate work items)
   int nchunk = 1;
   {
-    const long long lane_items = (long long)((n_local + 31) / 32) * ((p->d.Nmu + 1) / 2) * B;
+    const long long lane_items =
+        (long long)((n_local + 31) / 32) * ((p->d.Nmu + 1) / 2) * live_problems(p);
     const long long warps_total = (long long)p->n_sm * warps * cps;
     while (nchunk < 8 && lane_items * nchunk < warps_total * 6) nchunk *= 2;  // >= 6 items per warp
     const char *cenv = getenv("RB_COLS_CHUNKS");  // testing knob
@@ -637,8 +654,11 @@ static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, in
   }
 
   const int waves = (B > 1) ? 4 : 1;  // batches: ~4 CTAs per resident slot (finer tail)
-  int per_problem = std::max(1, (waves * want + B - 1) / B);
+  const int live = live_problems(p);
+  int per_problem = std::max(1, (waves * want + live - 1) / live);
   per_problem = std::min(per_problem, (p->n_items + warps - 1) / warps);
+  // the grid spans all B problems (converged ones return at once): bound it
+  per_problem = std::min(per_problem, std::max(1, (1 << 17) / B));
   dim3 g(per_problem, B);
   CK(cudaMemsetAsync(p->dwork, 0, B * sizeof(int), s));
 #define COLS(THREADS, MINB)                                                                  \
@@ -680,7 +700,17 @@ static int launch_nu_rates(rb_plan *p, int cell_start, int cell_stride, int n_lo
         &occ, k_nu_rates<ATT, KU, RU, BLOCK, MINB, LTAB>, BLOCK, smem);                      \
     /* 4 CTAs per resident slot: the hardware scheduler evens out the tail (+3 %) */       \
     const long long want = (long long)p->n_sm * std::max(1, occ) * 4;                        \
-    const int cpu = (B > 1) ? std::min(16, n_local) : 1;                                     \
+    /* cells per work unit: 16 in a full batch (a CTA re-reads one problem's frequency   */ \
+    /* table from L1), fewer when few problems are left (>= 2 units per resident CTA),   */ \
+    /* bounded below so that the flat unit list stays under 2^20 entries                 */ \
+    int cpu = 1;                                                                             \
+    if (B > 1) {                                                                             \
+      const long long slots = (long long)p->n_sm * std::max(1, occ);                         \
+      const long long fit = (long long)live_problems(p) * n_local / (2 * slots);             \
+      cpu = (int)std::min<long long>(16, std::max<long long>(1, fit));                       \
+      while (cpu < 16 && (long long)B * ((n_local + cpu - 1) / cpu) > (1ll << 20)) cpu *= 2; \
+      cpu = std::min(cpu, n_local);                                                          \
+    }                                                                                        \
     const long long units = (long long)((n_local + cpu - 1) / cpu) * B;                      \
     dim3 gn((unsigned)std::min<long long>(want, units));                                     \
     k_nu_rates<ATT, KU, RU, BLOCK, MINB, LTAB><<<gn, BLOCK, smem, s>>>(                      \
@@ -819,8 +849,7 @@ static int cell_group_size(const rb_plan *p, int n_local) {
   const char *fenv = getenv("RB_SPEC_G");  // testing knob: force the group size
   const int forced = fenv ? atoi(fenv) : 0;
   if (forced == 1 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
-  const int live = (p->active_hint > 0) ? std::min(B, p->active_hint) : B;
-  const long long cells_now = (long long)n_local * live;
+  const long long cells_now = (long long)n_local * live_problems(p);
   const long long budget = (long long)p->n_sm * 512;
   int G = 32;
   while (G > 1 && cells_now * G > budget) G >>= 1;
@@ -1001,12 +1030,12 @@ static int sweep_graph(rb_plan *p) {
   if (p->sweeps_issued - p->sweeps_polled >= kSlots - 1) return RB_ERR_BAD_ARG;
   const int slot = (int)(p->sweeps_issued % kSlots);
   cudaStream_t s = p->stream;
-  const int Gnow = cell_group_size(p, plan_sweep_cells(p));
-  if (memcmp(&p->gP, &p->P, sizeof(PlanDev)) != 0 || Gnow != p->gG) {
+  const int live_now = live_problems(p);
+  if (memcmp(&p->gP, &p->P, sizeof(PlanDev)) != 0 || live_now != p->g_live) {
     for (auto &g : p->gexec)
       if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     p->gP = p->P;
-    p->gG = Gnow;
+    p->g_live = live_now;
   }
   if (!p->gexec[slot]) {
     const int nl0 = p->info.n_launches;
@@ -1149,17 +1178,22 @@ static int solve_loop(rb_plan *p, rb_info *info, bool sharded) {
     if (!stop && p->sweeps_issued - p->sweeps_polled < kDepth) {
       if (sharded) {
         rc = rb_plan_sweep_sharded(p);
-      } else if (use_graphs && p->graphs_ok && p->sweeps_issued > 0) {
-        // (the first sweep goes out directly: it builds the cached work lists, sets the
-        // kernels' shared-memory attributes and gives the stage times of one sweep)
+      } else if (use_graphs && p->graphs_ok && p->sweeps_issued > 0 &&
+                 live_problems(p) == p->direct_live) {
+        // (the first sweep, and the first one after the launch shapes changed with the number
+        // of live problems, goes out directly: it builds the cached work lists -- a host
+        // copy that cannot be captured --, sets the kernels' shared-memory attributes and
+        // gives the stage times of one sweep)
         rc = sweep_graph(p);
         if (rc && !p->graphs_ok) {  // capture not possible: direct launches from here on
           rc = rb_plan_sweep_local(p, 0, 1);
           if (!rc) rc = rb_plan_finish_sweep_async(p);
         }
       } else {
+        const int live_now = live_problems(p);
         rc = rb_plan_sweep_local(p, 0, 1);
         if (!rc) rc = rb_plan_finish_sweep_async(p);
+        if (!rc) p->direct_live = live_now;
       }
       if (rc) return rc;
       continue;
