@@ -12,7 +12,7 @@ rates 1/s and erg/s.  The numerics are the CUDA C ABI behind
 """
 import numpy as np
 
-from . import rabacus_fc
+from . import post, rabacus_fc
 
 _REC = {"fixed": 1, "outward": 2, "radial": 3, "isotropic": 4, "ray": 2}
 
@@ -173,9 +173,17 @@ class _SlabBase(_GeomBase):
         self.NH1_thru = np.sum(self.dNH1)
         self.NHe1_thru = np.sum(self.dNHe1)
         self.NHe2_thru = np.sum(self.dNHe2)
+        with np.errstate(divide="ignore"):
+            self.logNH1_thru = np.log10(self.NH1_thru)
+            self.logNHe1_thru = np.log10(self.NHe1_thru)
+            self.logNHe2_thru = np.log10(self.NHe2_thru)
         self.NH1_c = np.cumsum(self.dNH1) - 0.5 * self.dNH1
         self.NHe1_c = np.cumsum(self.dNHe1) - 0.5 * self.dNHe1
         self.NHe2_c = np.cumsum(self.dNHe2) - 0.5 * self.dNHe2
+        # slab_base.py:300-311, 369-431: mean molecular weight, central values, averages
+        self.dz = self.dl
+        self.mu = post.mean_molecular_weight(self.xH2, self.xHe2, self.xHe3)
+        self.avg = post.slab_averages(self)
 
 
 class Slab2Bgnd(_SlabBase):

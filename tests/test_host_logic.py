@@ -174,3 +174,73 @@ def test_hg97_libm_statement_form_is_bit_identical_to_the_oracle(orc):
         assert _lib.lib().rb_diag_use_libm_pow(C.c_int(0)) == 0
     ref = np.array(list(orc.get_kchem(T, *f)) + list(orc.get_kcool(T, *f)))
     assert np.array_equal(out, ref)
+
+
+# ----------------------------------------------------------------- slab post-processing
+def test_mean_molecular_weight_limits():
+    """jeans.py:45-64 with the wrapper's default Yp = 0.248: neutral gas 4/(4 - 3 Yp),
+    fully ionised 4/(8 - 5 Yp)."""
+    from rabacus_b200 import post
+    Yp = 0.248
+    assert post.mean_molecular_weight(0.0, 0.0, 0.0) == 4.0 / (4.0 - 3.0 * Yp)
+    assert abs(post.mean_molecular_weight(1.0, 0.0, 1.0) - 4.0 / (8.0 - 5.0 * Yp)) < 1e-15
+    mu = post.mean_molecular_weight(np.array([0.0, 0.5, 1.0]), np.zeros(3), np.zeros(3))
+    assert np.all(np.diff(mu) < 0)
+
+
+def test_slab_averages_follow_the_reference_definitions():
+    """slab_base.py:120-283, 369-431: <q>_w = trap(z_c, w q) / trap(z_c, w) for the six
+    weightings and the central-layer sample, on a synthetic slab."""
+    from rabacus_b200 import post
+
+    class Obj(object):
+        pass
+    o = Obj()
+    Nl = 16
+    rng = np.random.default_rng(4)
+    o.Nl = Nl
+    Edges = np.linspace(0.0, 3.0, Nl + 1) ** 1.3
+    o.dz = Edges[1:] - Edges[:-1]
+    o.z_c = Edges[:-1] + 0.5 * o.dz
+    for name in set(post.AVERAGED_FIELDS + post.CENTRAL_FIELDS):
+        setattr(o, name, rng.uniform(0.1, 1.0, Nl))
+    o.T = np.full(Nl, 1.0e4)                      # a constant field averages to itself
+    avg = post.slab_averages(o)
+    for w in ("v_w", "nH_w", "nHe_w", "nH1_w", "nHe1_w", "nHe2_w"):
+        assert abs(getattr(avg, w).T / 1.0e4 - 1.0) < 1e-14
+    wa = o.nH * o.xH1
+    ref = rad_src.trap(o.z_c, wa * o.H1i_src) / rad_src.trap(o.z_c, wa)
+    assert avg.nH1_w.H1i_src == ref
+    lo, hi = o.xHe2.min(), o.xHe2.max()
+    assert lo <= avg.v_w.xHe2 <= hi
+    assert avg.cen.ne == o.ne[Nl // 2] and avg.cen.He2h_rec == o.He2h_rec[Nl // 2]
+
+
+def test_slab_wrapper_post_processing_sets_reference_attributes(monkeypatch):
+    """The slab wrappers' __post__ attributes (slab_base.py:286-437) from a synthetic solver
+    result; the GPU-backed ChemistryRates is stubbed so that this runs without a device."""
+    from rabacus_b200 import solvers
+
+    class KA(object):
+        def __init__(self, T, *a, **k):
+            for n in ("reH2", "reHe2", "reHe3", "ciH1", "ciHe1", "ciHe2"):
+                setattr(self, n, np.full(np.size(T), 1.0e-13))
+    monkeypatch.setattr(solvers, "ChemistryRates", KA)
+    Nl = 12
+    rng = np.random.default_rng(6)
+    s = object.__new__(solvers.Slab2Bgnd)
+    s.Nl = Nl
+    s.Edges = np.linspace(0.0, 1.0e21, Nl + 1)
+    s.nH = np.full(Nl, 1.0e-2); s.nHe = np.full(Nl, 1.0e-3); s.T = np.full(Nl, 1.0e4)
+    s.atomic_fit_name = "hg97"
+    out = [rng.uniform(0.05, 0.9, Nl) for _ in range(17)]
+    monkeypatch.setattr(solvers.rabacus_fc, "last_info", {"iters": 7}, raising=False)
+    s._attach(out)
+    s._post()
+    assert s.itr == 7
+    assert np.array_equal(s.dz, s.Edges[1:] - s.Edges[:-1]) and s.z_c.size == Nl
+    assert s.mu.shape == (Nl,) and np.all(s.mu > 0.5) and np.all(s.mu < 1.3)
+    assert np.isclose(s.logNH1_thru, np.log10(np.sum(s.dz * s.nH * s.xH1)))
+    for w in ("v_w", "nH_w", "nHe_w", "nH1_w", "nHe1_w", "nHe2_w"):
+        assert np.isfinite(getattr(s.avg, w).H1h_rec)
+    assert s.avg.cen.xH1 == s.xH1[Nl // 2]
