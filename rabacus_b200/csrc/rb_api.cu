@@ -637,6 +637,12 @@ static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, in
     const char *cenv = getenv("RB_COLS_CHUNKS");  // testing knob
     if (cenv && atoi(cenv) >= 1 && atoi(cenv) <= 8) nchunk = atoi(cenv);
     while (nchunk > 1 && Nl < 8 * nchunk) nchunk /= 2;
+    // the chunk partials are indexed by problem: keep them under 2 GiB for any batch size
+    // (the tail of a large batch then walks unchunked)
+    auto part_bytes = [&](int nc) {
+      return (size_t)B * ((p->d.Nmu + 1) / 2) * n_local * nc * kPartStride * sizeof(double);
+    };
+    while (nchunk > 1 && part_bytes(nchunk) > ((size_t)2 << 30)) nchunk /= 2;
   }
   int rc = build_items(p, cell_start, cell_stride, n_local, nchunk);
   if (rc) return rc;

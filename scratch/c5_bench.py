@@ -56,6 +56,8 @@ if rank == 0:
                       "evals_per_s": tot / tmax, "max_sweeps": info["iters"],
                       "stage_ms_rank0": {k: round(info[k], 1) for k in ("ms_columns", "ms_nu", "ms_cell")},
                       "host_build_s": round(t_build, 2), "host_stage_s": round(t_stage, 2),
-                      "per_rank_s": [round(float(e[1]), 3) for e in evs]}))
+                      "per_rank_s": [round(float(e[1]), 3) for e in evs],
+                      "dev_mem_used_gb_rank0": round((torch.cuda.mem_get_info()[1]
+                                                      - torch.cuda.mem_get_info()[0]) / 2**30, 2)}))
 if dist:
     dist.barrier(); dist.destroy_process_group()
