@@ -1289,12 +1289,18 @@ extern "C" int rb_plan_get_problem(rb_plan *p, int b, double *T, double *xH1, do
   const size_t B = p->d.n_problems, Nl = p->d.Nl, NC = B * Nl;
   double *h = p->hout;  // 12 fields of Nl
   cudaStream_t s = p->stream;
-  for (int f = 0; f < 5; ++f)
-    CK(cudaMemcpyAsync(h + f * Nl, p->dx + f * NC + b * Nl, Nl * 8, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(h + 5 * Nl, p->dT + b * Nl, Nl * 8, cudaMemcpyDeviceToHost, s));
-  for (int f = 0; f < 6; ++f)
-    CK(cudaMemcpyAsync(h + (6 + f) * Nl, p->dsrc + f * NC + b * Nl, Nl * 8,
-                       cudaMemcpyDeviceToHost, s));
+  if (B == 1) {  // [5][Nl] and [6][Nl] are contiguous: three copies instead of twelve
+    CK(cudaMemcpyAsync(h, p->dx, 5 * Nl * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h + 5 * Nl, p->dT, Nl * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h + 6 * Nl, p->dsrc, 6 * Nl * 8, cudaMemcpyDeviceToHost, s));
+  } else {
+    for (int f = 0; f < 5; ++f)
+      CK(cudaMemcpyAsync(h + f * Nl, p->dx + f * NC + b * Nl, Nl * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h + 5 * Nl, p->dT + b * Nl, Nl * 8, cudaMemcpyDeviceToHost, s));
+    for (int f = 0; f < 6; ++f)
+      CK(cudaMemcpyAsync(h + (6 + f) * Nl, p->dsrc + f * NC + b * Nl, Nl * 8,
+                         cudaMemcpyDeviceToHost, s));
+  }
   CK(cudaMemcpyAsync(p->hflags + B + b, p->dflags + B + b, sizeof(int),
                      cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -1313,9 +1319,13 @@ extern "C" int rb_plan_get_rec(rb_plan *p, int b, double *H1i, double *He1i, dou
   if (!p || b < 0 || b >= p->d.n_problems) return RB_ERR_BAD_ARG;
   const size_t B = p->d.n_problems, Nl = p->d.Nl, NC = B * Nl;
   double *h = p->hout;  // 12*NC doubles of pinned staging; 6*Nl used
-  for (int f = 0; f < 6; ++f)
-    CK(cudaMemcpyAsync(h + f * Nl, p->drec + f * NC + b * Nl, Nl * 8, cudaMemcpyDeviceToHost,
-                       p->stream));
+  if (B == 1) {
+    CK(cudaMemcpyAsync(h, p->drec, 6 * Nl * 8, cudaMemcpyDeviceToHost, p->stream));
+  } else {
+    for (int f = 0; f < 6; ++f)
+      CK(cudaMemcpyAsync(h + f * Nl, p->drec + f * NC + b * Nl, Nl * 8, cudaMemcpyDeviceToHost,
+                         p->stream));
+  }
   CK(cudaStreamSynchronize(p->stream));
   double *outs[6] = {H1i, He1i, He2i, H1h, He1h, He2h};
   const bool rev = p->reversed[b];
