@@ -1251,25 +1251,45 @@ extern "C" int rb_plan_bench_steps(rb_plan *p, int steps, size_t flush_bytes, do
     cudaGetLastError();
     return RB_ERR_NOMEM;
   }
-  double sum = 0.0;
+  // Every step is bracketed by its own pair of events in the stream (the L2 flush lies
+  // between the pairs); the steps are enqueued up to four ahead of the convergence
+  // read-backs like in solve_loop, so that the host's latency -- at N > 1 the slowest
+  // rank's, handed on by the cross-GPU barrier -- is not part of what is timed.
+  const int kDepth = 4;
+  std::vector<cudaEvent_t> ev((size_t)2 * steps, nullptr);
   int rc = RB_OK;
-  for (int s = 0; s < steps && rc == RB_OK; ++s) {
-    if (flush) cudaMemsetAsync(flush, s & 0xff, flush_bytes, p->stream);
-    cudaEventRecord(p->ev[6], p->stream);
-    int n_active = 0;
-    if (p->Q.world > 1) {
-      rc = rb_plan_sweep_sharded(p);
-      if (!rc) rc = rb_plan_poll_sweep(p, &n_active);
-    } else {
-      rc = rb_plan_sweep_local(p, 0, 1);
-      if (!rc) rc = rb_plan_finish_sweep(p, &n_active);
+  for (auto &e : ev)
+    if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); rc = RB_ERR_CUDA; break; }
+  int issued = 0, polled = 0, n_active = 0;
+  while (rc == RB_OK && polled < steps) {
+    if (issued < steps && p->sweeps_issued - p->sweeps_polled < kDepth) {
+      if (flush) cudaMemsetAsync(flush, issued & 0xff, flush_bytes, p->stream);
+      cudaEventRecord(ev[2 * issued], p->stream);
+      if (p->Q.world > 1) {
+        rc = rb_plan_sweep_sharded(p);
+      } else {
+        rc = rb_plan_sweep_local(p, 0, 1);
+        if (!rc) rc = rb_plan_finish_sweep_async(p);
+      }
+      cudaEventRecord(ev[2 * issued + 1], p->stream);
+      ++issued;
+      continue;
     }
-    cudaEventRecord(p->ev[7], p->stream);
-    if (cudaEventSynchronize(p->ev[7]) != cudaSuccess) rc = RB_ERR_CUDA;
+    rc = rb_plan_poll_sweep(p, &n_active);
+    ++polled;
+  }
+  if (cudaStreamSynchronize(p->stream) != cudaSuccess && rc == RB_OK) rc = RB_ERR_CUDA;
+  double sum = 0.0;
+  for (int s = 0; s < issued && rc == RB_OK; ++s) {
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, p->ev[6], p->ev[7]);
+    if (cudaEventElapsedTime(&ms, ev[2 * s], ev[2 * s + 1]) != cudaSuccess) {
+      cudaGetLastError();
+      rc = RB_ERR_CUDA;
+    }
     sum += ms;
   }
+  for (auto &e : ev)
+    if (e) cudaEventDestroy(e);
   if (flush) cudaFree(flush);
   *ms_sum = sum;
   return rc;
