@@ -159,17 +159,6 @@ int rb_get_kcool(const double *T, const double *fcA_H2, const double *fcA_He2,
                  double *recHe2, double *recHe3, double *cicH1, double *cicHe1,
                  double *cicHe2, double *cecH1, double *cecHe2, double *bremss,
                  double *compton);
-/* Diagnostics for the arithmetic of csrc/rb_fastpow.cuh (x**y of the Hui & Gnedin fits,
- * hui_gnedin_97.f90:21-322): out[i] = x[i]**y[i], and the 6 + 10 coefficients of
- * get_kchem_s / get_kcool_s (chem_cool_rates.f90:45-204) as out16[16][n].  on_device = 0
- * evaluates the same inline source with the host compiler (unit tests without a GPU),
- * 1 runs one CUDA thread per element.  Not used by any solver entry point. */
-/* on != 0: evaluate the Hui & Gnedin fits with libm / libdevice pow() statement by
- * statement instead of csrc/rb_fastpow.cuh (A/B tests of the two forms); host build + current device. */
-int rb_diag_use_libm_pow(int on);
-int rb_diag_pow(const double *x, const double *y, int n, double *out, int on_device);
-int rb_diag_hg97(const double *T, const double *fcA_H2, const double *fcA_He2,
-                 const double *fcA_He3, int n, double *out16, int on_device);
 int rb_solve_ce(const double *reH2, const double *reHe2, const double *reHe3,
                 const double *ciH1, const double *ciHe1, const double *ciHe2,
                 int nn, double *xH1, double *xH2, double *xHe1, double *xHe2,
@@ -223,7 +212,10 @@ typedef struct rb_plan_desc {
                      4 isotropic (sphere_base.f90:79-1083); slabs: 2 = "ray"
                      (slab_base.f90:163-560).  != 1 forces case-A rates. */
   double em_fac[3]; /* isotropic: multipliers of the H1/He1/He2 recombination emission
-                       (sphere_bgnd.f90:75-77); 0,0,0 is read as 1,1,1 */
+                       (sphere_bgnd.f90:75-77, applied at sphere_base.f90:955) */
+  int em_fac_set;   /* 0: em_fac is ignored and (1,1,1) is used (a zeroed desc gives the
+                       reference's Python defaults, sphere_bgnd.py:138-150); != 0: em_fac is
+                       used as given, explicit zeros switch the emission off */
 } rb_plan_desc;
 
 int rb_plan_create(rb_plan **plan, const rb_plan_desc *desc);
@@ -298,15 +290,7 @@ int rb_plan_sync(rb_plan *plan);
 long long rb_plan_evals_per_sweep(const rb_plan *plan);
 int rb_plan_last_info(const rb_plan *plan, rb_info *info);
 
-/* bench helper: run `steps` Jacobi sweeps (rb_plan_sweep_local over all cells +
- * rb_plan_finish_sweep; rb_plan_sweep_sharded on a peer-connected plan) and return their summed device time in ms, measured
- * with CUDA events on the plan's stream.  If flush_bytes > 0 a scratch buffer of
- * that size is overwritten between steps (L2 flush), outside the timed spans. */
-int rb_plan_bench_steps(rb_plan *plan, int steps, size_t flush_bytes, double *ms_sum);
-
-/* FP64 pipe micro-benchmarks used as roofline denominators (bench.py):
- * kind 0 = DFMA, 1 = exp, 2 = sqrt, 3 = pow.  Returns operations / second. */
-int rb_microbench(int kind, int device, double *ops_per_s);
+/* (measurement and diagnostic entry points: rabacus_b200/csrc/rb_internal.h) */
 
 #ifdef __cplusplus
 }

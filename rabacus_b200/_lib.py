@@ -35,7 +35,8 @@ class rb_plan_desc(C.Structure):
     _fields_ = [("geometry", C.c_int), ("n_problems", C.c_int), ("Nl", C.c_int),
                 ("Nnu", C.c_int), ("Nmu", C.c_int), ("i_find_Teq", C.c_int),
                 ("fixed_fcA", C.c_double), ("tol", C.c_double), ("device", C.c_int),
-                ("max_sweeps", C.c_int), ("i_rec_meth", C.c_int), ("em_fac", C.c_double * 3)]
+                ("max_sweeps", C.c_int), ("i_rec_meth", C.c_int), ("em_fac", C.c_double * 3),
+                ("em_fac_set", C.c_int)]
 
 
 GEOM_SPHERE_BGND, GEOM_SPHERE_STROMGREN, GEOM_SLAB_PLANE_1, GEOM_SLAB_PLANE_2, \
@@ -46,16 +47,21 @@ EXPORTS = (
     "rb_strerror", "rb_device_count", "rb_version", "rb_cache_clear",
     "rb_sphere_bgnd_solve", "rb_sphere_stromgren_solve", "rb_slab_bgnd_solve",
     "rb_slab_plane_solve", "rb_set_column_vs_impact",
-    "rb_get_kchem", "rb_get_kcool", "rb_diag_pow", "rb_diag_hg97", "rb_diag_use_libm_pow", "rb_solve_ce", "rb_solve_pce", "rb_solve_pcte",
+    "rb_get_kchem", "rb_get_kcool", "rb_solve_ce", "rb_solve_pce", "rb_solve_pcte",
     "rb_photo_sigma", "rb_photo_Eth", "rb_gauss_legendre",
     "rb_plan_create", "rb_plan_destroy", "rb_plan_set_problem", "rb_plan_upload",
     "rb_plan_thin", "rb_plan_sweep_local", "rb_plan_finish_sweep", "rb_plan_finish_sweep_async",
     "rb_plan_poll_sweep", "rb_plan_solve",
     "rb_plan_get_problem", "rb_plan_get_rec", "rb_plan_field_ptr", "rb_plan_stream", "rb_plan_sync",
-    "rb_plan_evals_per_sweep", "rb_plan_last_info", "rb_plan_bench_steps", "rb_plan_pack_cells",
-    "rb_plan_unpack_cells", "rb_microbench",
+    "rb_plan_evals_per_sweep", "rb_plan_last_info", "rb_plan_pack_cells",
+    "rb_plan_unpack_cells",
     "rb_plan_peer_alloc", "rb_plan_peer_connect", "rb_plan_sweep_sharded", "rb_plan_solve_sharded",
 )
+
+# measurement / diagnostic symbols declared in rabacus_b200/csrc/rb_internal.h (not part of
+# the drop-in boundary)
+INTERNAL = ("rbi_diag_pow", "rbi_diag_hg97", "rbi_plan_set_libm_pow", "rbi_plan_bench_steps",
+            "rbi_microbench")
 
 _lib = None
 

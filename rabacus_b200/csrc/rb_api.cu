@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "rb_rec.cuh"
+#include "rb_internal.h"
 
 using namespace rb;
 
@@ -192,6 +193,7 @@ static void build_spec_table(int geom, const double *E, const double *shape, int
 // ---------------------------------------------------------------------------
 struct rb_plan {
   rb_plan_desc d;
+  int dev = 0;   // CUDA device the plan lives on (every entry point switches to it)
   int Ndir;
   double sigma_th[3];
   cudaStream_t stream = nullptr;
@@ -220,17 +222,26 @@ struct rb_plan {
   // CUDA graphs of one sweep (one per in-flight slot), see solve_loop
   cudaGraphExec_t gexec[kSlots] = {nullptr};
   int graph_nl[kSlots] = {0};          // kernel launches inside each graph
-  PlanDev gP;                           // kernel arguments the graphs were captured with
+  // everything a captured sweep bakes in: the by-value kernel arguments (PlanDev, the
+  // photon-transfer constants and scratch pointers), the method and the launch-shape knobs
+  struct GraphKey {
+    PlanDev P;
+    RecConst K;
+    RecDev R;
+    PeerDev Q;
+    int rec_meth, live, spec_g, cols_chunks, sharded;
+  };
+  GraphKey gkey;
+  bool gkey_valid = false;
   bool capturing = false, graphs_ok = true;
   int active_hint = 0;   // problems still iterating at the last read-back (0: all)
-  int g_live = 0;        // live_problems() the graphs were captured for
   int direct_live = -1;  // live_problems() of the last directly launched sweep
   bool slot_timed[kSlots] = {false};    // stage events of that slot are valid (direct launches)
   // cell sharding over peer memory
   PeerDev Q;                    // world == 1 when not connected
   void *dpeer = nullptr;        // this rank's flags (256 B) + staging
   void *peer_base[kMaxPeers] = {nullptr};  // mapped bases (own = dpeer)
-  unsigned long long peer_epoch = 0;
+  long long peer_sweeps = 0;    // sharded sweeps enqueued since rb_plan_peer_connect
   int peer_world = 1;
   int n_items = 0, items_start = -1, items_stride = -1, items_chunks = 1, n_sm = 148;
   double *dpart = nullptr;      // chunk partial sums of the column kernel (nchunk > 1)
@@ -260,8 +271,39 @@ struct rb_plan {
 
 static size_t cells(const rb_plan *p) { return (size_t)p->d.n_problems * p->d.Nl; }
 
+// Every plan entry point runs on the plan's device and leaves the caller's current device
+// as it found it (a process may hold plans on several GPUs, or share the thread with torch).
+struct DevGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    if (dev >= 0 && dev != prev) switched = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DevGuard() {
+    if (switched && prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define PLAN_DEV(p) DevGuard dev_guard_((p) ? (p)->dev : -1)
+
+static void destroy_graphs(rb_plan *p) {
+  for (auto &g : p->gexec)
+    if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+  p->gkey_valid = false;
+}
+
 extern "C" void rb_plan_destroy(rb_plan *p) {
   if (!p) return;
+  PLAN_DEV(p);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  destroy_graphs(p);
+  cudaFree(p->drec); cudaFree(p->drecbuf); cudaFree(p->drecI); cudaFree(p->diso_items);
+  cudaFree(p->dpart);
+  if (p->dpeer) {
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (p->peer_base[r] && p->peer_base[r] != p->dpeer) cudaIpcCloseMemHandle(p->peer_base[r]);
+    cudaFree(p->dpeer);
+  }
   cudaFree(p->dEdges); cudaFree(p->dnH); cudaFree(p->dnHe); cudaFree(p->dT);
   cudaFree(p->dx); cudaFree(p->dsrc); cudaFree(p->dconv); cudaFree(p->dkchem); cudaFree(p->dpack);
   cudaFree(p->dspec); cudaFree(p->dthin); cudaFree(p->dmu); cudaFree(p->dcol);
@@ -296,9 +338,18 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
     snprintf(g_cuda_msg, sizeof(g_cuda_msg), "no CUDA device visible (there is no CPU fallback)");
     return RB_ERR_CUDA;
   }
-  if (d.device >= 0) CK(cudaSetDevice(d.device));
+  int dev_now = 0;
+  if (cudaGetDevice(&dev_now) != cudaSuccess) cudaGetLastError();
+  const int dev = d.device >= 0 ? d.device : dev_now;
+  DevGuard dev_guard_(dev);
+  if (dev != dev_now && !dev_guard_.switched) {
+    snprintf(g_cuda_msg, sizeof(g_cuda_msg), "cannot select CUDA device %d", dev);
+    return RB_ERR_CUDA;
+  }
   rb_plan *p = new rb_plan();
   p->d = d;
+  p->d.device = dev;
+  p->dev = dev;
   switch (d.geometry) {
     case RB_GEOM_SPHERE_BGND: p->Ndir = d.Nmu; break;
     case RB_GEOM_SLAB_PLANE_2: case RB_GEOM_SLAB_BGND: p->Ndir = 2; break;
@@ -343,11 +394,7 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   }
   if (d.geometry == RB_GEOM_SPHERE_BGND)
     ALLOC(p->ditems, (size_t)((Nl + 31) / 32) * ((d.Nmu + 1) / 2) * 8 * sizeof(unsigned));
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev);
-  }
+  cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev);
   ALLOC(p->dflags, (3 * B + kSlots) * sizeof(int)); ALLOC(p->dresid, B * 8);
   HALLOC(p->hEdges, B * (Nl + 1) * 8); HALLOC(p->hnH, NC * 8); HALLOC(p->hnHe, NC * 8);
   HALLOC(p->hT, NC * 8); HALLOC(p->hspec, B * Nnu * kSpecStride * 8);
@@ -374,8 +421,10 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   memset(&p->Q, 0, sizeof(p->Q));
   p->Q.world = 1;
   PlanDev &P = p->P;
+  memset(&P, 0, sizeof(P));
   P.B = d.n_problems; P.Nl = d.Nl; P.Nnu = d.Nnu; P.Nmu = d.Nmu; P.Ndir = p->Ndir;
   P.geom = d.geometry; P.find_Teq = d.i_find_Teq; P.max_sweeps = d.max_sweeps;
+  P.libm_pow = 0; P.pad0_ = 0;
   P.fcA = d.fixed_fcA; P.tol = d.tol; P.tol_inner = d.tol * RB_TOL_FRAC;
   for (int X = 0; X < 3; ++X) P.sigma_th[X] = p->sigma_th[X];
   P.Edges = p->dEdges; P.nH = p->dnH; P.nHe = p->dnHe; P.T = p->dT;
@@ -410,8 +459,9 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
     K.sH1_He1 = v96_sigma(0, K.E_th[1]);
     K.sH1_He2 = v96_sigma(0, K.E_th[2]);
     K.sHe1_He2 = v96_sigma(1, K.E_th[2]);
-    const bool unset = d.em_fac[0] == 0.0 && d.em_fac[1] == 0.0 && d.em_fac[2] == 0.0;
-    for (int X = 0; X < 3; ++X) K.em_fac[X] = unset ? 1.0 : d.em_fac[X];
+    // sphere_base.f90:955: the factors multiply the emissivities, so explicit zeros mean
+    // "no recombination emission"; only a desc that never set them (em_fac_set == 0) gets 1
+    for (int X = 0; X < 3; ++X) K.em_fac[X] = d.em_fac_set ? d.em_fac[X] : 1.0;
   }
   P.active = p->dflags; P.iters = p->dflags + B; P.err = p->dflags + 2 * B;
   P.nactive = p->dflags + 3 * B; P.resid_bits = p->dresid;
@@ -483,6 +533,7 @@ extern "C" int rb_plan_set_problem(rb_plan *p, int b, const double *Edges, const
 
 extern "C" int rb_plan_upload(rb_plan *p) {
   if (!p) return RB_ERR_BAD_ARG;
+  PLAN_DEV(p);
   const size_t B = p->d.n_problems, Nl = p->d.Nl, Nnu = p->d.Nnu, NC = B * Nl;
   cudaStream_t s = p->stream;
   CK(cudaMemcpyAsync(p->dEdges, p->hEdges, B * (Nl + 1) * 8, cudaMemcpyHostToDevice, s));
@@ -509,6 +560,7 @@ extern "C" int rb_plan_upload(rb_plan *p) {
 
 extern "C" int rb_plan_thin(rb_plan *p) {
   if (!p) return RB_ERR_BAD_ARG;
+  PLAN_DEV(p);
   const int Nl = p->d.Nl, B = p->d.n_problems;
   // one cell per thread over a cluster of up to 8 CTAs of 512 threads; two cells per
   // thread beyond 4096 cells
@@ -865,6 +917,7 @@ static int cell_group_size(const rb_plan *p, int n_local) {
 
 static int sweep_impl(rb_plan *p, int cell_start, int cell_stride, bool scatter) {
   if (!p || cell_start < 0 || cell_stride < 1) return RB_ERR_BAD_ARG;
+  PLAN_DEV(p);
   PeerDev Q = p->Q;
   if (!scatter) Q.world = 1;
   const int Nl = p->d.Nl, B = p->d.n_problems, g = p->d.geometry;
@@ -938,10 +991,19 @@ extern "C" int rb_plan_sweep_local(rb_plan *p, int cell_start, int cell_stride) 
 // ---------------------------------------------------------------------------
 static int plan_sweep_cells(const rb_plan *p);
 
+static unsigned long long peer_timeout_ns() {
+  // RB_PEER_TIMEOUT_MS: how long a rank waits for its peers at the per-sweep barrier
+  const char *e = getenv("RB_PEER_TIMEOUT_MS");
+  double ms = e ? atof(e) : 0.0;
+  if (!(ms > 0.0)) ms = 2000.0;
+  return (unsigned long long)(ms * 1.0e6);
+}
+
 extern "C" int rb_plan_peer_alloc(rb_plan *p, int rank, int world, unsigned char handle[64]) {
   if (!p || !handle || world < 1 || world > kMaxPeers || rank < 0 || rank >= world ||
       p->d.n_problems != 1 || p->dpeer)
     return RB_ERR_BAD_ARG;
+  PLAN_DEV(p);
   const int ncell = plan_sweep_cells(p);
   if (ncell % world != 0) return RB_ERR_BAD_ARG;
   const int n_local = ncell / world;
@@ -958,7 +1020,7 @@ extern "C" int rb_plan_peer_alloc(rb_plan *p, int rank, int world, unsigned char
   static_assert(sizeof(h) == 64, "CUDA IPC handle size");
   memcpy(handle, &h, 64);
   p->Q.world = 1;  // not usable until rb_plan_peer_connect
-  p->Q.rank = rank; p->Q.n_local = n_local; p->Q.parity = 0;
+  p->Q.rank = rank; p->Q.n_local = n_local;
   p->peer_world = world;
   p->peer_base[rank] = p->dpeer;
   return RB_OK;
@@ -966,6 +1028,7 @@ extern "C" int rb_plan_peer_alloc(rb_plan *p, int rank, int world, unsigned char
 
 extern "C" int rb_plan_peer_connect(rb_plan *p, const unsigned char *handles) {
   if (!p || !handles || !p->dpeer) return RB_ERR_BAD_ARG;
+  PLAN_DEV(p);
   const int world = p->peer_world, rank = p->Q.rank;
   for (int r = 0; r < world; ++r) {
     if (r == rank) continue;
@@ -977,28 +1040,42 @@ extern "C" int rb_plan_peer_connect(rb_plan *p, const unsigned char *handles) {
     p->Q.flags[r] = (unsigned long long *)p->peer_base[r];
     p->Q.stage[r] = (double *)((char *)p->peer_base[r] + 256);
   }
+  p->Q.ctl = (unsigned long long *)p->dpeer + kPeerCtl;
+  p->Q.timeout_ns = peer_timeout_ns();
   p->Q.world = world;
-  p->Q.parity = 0;
-  p->peer_epoch = 0;
+  p->peer_sweeps = 0;
+  destroy_graphs(p);
+  return RB_OK;
+}
+
+// the barrier + scatter + convergence test that ends a cell-sharded sweep, and its read-back
+static int exchange_body(rb_plan *p, const PeerDev &Q, int slot) {
+  cudaStream_t s = p->stream;
+  const int ncell = Q.world * Q.n_local;
+  const int ctas = std::max(1, std::min(32, (ncell + 255) / 256));
+  k_exchange_finish<256><<<ctas, 256, 0, s>>>(p->P, Q, slot);
+  p->info.n_launches += 1;
+  CK(cudaMemcpyAsync(p->hflags + 3 + slot, p->dflags + 3 + slot, sizeof(int),
+                     cudaMemcpyDeviceToHost, s));
   return RB_OK;
 }
 
 extern "C" int rb_plan_sweep_sharded(rb_plan *p) {
   if (!p || p->Q.world < 2) return RB_ERR_BAD_ARG;
   if (p->sweeps_issued - p->sweeps_polled >= kSlots - 1) return RB_ERR_BAD_ARG;  // poll first
-  p->peer_epoch += 1;
-  p->Q.epoch = p->peer_epoch;
-  p->Q.parity = (int)(p->peer_epoch & 1);
+  PLAN_DEV(p);
   int rc = sweep_impl(p, p->Q.rank, p->Q.world, true);
   if (rc) return rc;
   const int slot = (int)(p->sweeps_issued % kSlots);
-  cudaStream_t s = p->stream;
-  k_exchange_finish<1024><<<1, 1024, 0, s>>>(p->P, p->Q, slot);
-  p->info.n_launches += 1;
-  CK(cudaMemcpyAsync(p->hflags + 3 + slot, p->dflags + 3 + slot, sizeof(int),
-                     cudaMemcpyDeviceToHost, s));
-  CK(cudaEventRecord(p->sev[slot][4], s));
+  PeerDev Q = p->Q;
+  // the first barrier after connecting also absorbs the peers' one-off costs (module load,
+  // work-list build with its host synchronisation): ten times the timeout
+  if (p->peer_sweeps == 0) Q.timeout_ns *= 10ull;
+  rc = exchange_body(p, Q, slot);
+  if (rc) return rc;
+  CK(cudaEventRecord(p->sev[slot][4], p->stream));
   p->sweeps_issued += 1;
+  p->peer_sweeps += 1;
   CK(cudaGetLastError());
   return RB_OK;
 }
@@ -1016,6 +1093,7 @@ static int finish_body(rb_plan *p, int slot) {
 
 extern "C" int rb_plan_finish_sweep_async(rb_plan *p) {
   if (!p) return RB_ERR_BAD_ARG;
+  PLAN_DEV(p);
   if (p->sweeps_issued - p->sweeps_polled >= kSlots - 1) return RB_ERR_BAD_ARG;  // poll first
   const int slot = (int)(p->sweeps_issued % kSlots);
   int rc = finish_body(p, slot);
@@ -1032,16 +1110,28 @@ extern "C" int rb_plan_finish_sweep_async(rb_plan *p) {
 // in-flight slot (the slot index is a kernel argument).  Graphs are re-captured when a
 // kernel argument changed (the plan was re-armed with other flags).  Stage events are not
 // part of the graphs: per-stage times come from direct launches (first sweep, bench).
-static int sweep_graph(rb_plan *p) {
+static int sweep_graph(rb_plan *p, bool sharded) {
   if (p->sweeps_issued - p->sweeps_polled >= kSlots - 1) return RB_ERR_BAD_ARG;
   const int slot = (int)(p->sweeps_issued % kSlots);
   cudaStream_t s = p->stream;
-  const int live_now = live_problems(p);
-  if (memcmp(&p->gP, &p->P, sizeof(PlanDev)) != 0 || live_now != p->g_live) {
-    for (auto &g : p->gexec)
-      if (g) { cudaGraphExecDestroy(g); g = nullptr; }
-    p->gP = p->P;
-    p->g_live = live_now;
+  rb_plan::GraphKey key;
+  memset(&key, 0, sizeof(key));
+  memcpy(&key.P, &p->P, sizeof(PlanDev));
+  memcpy(&key.K, &p->K, sizeof(RecConst));
+  memcpy(&key.R, &p->R, sizeof(RecDev));
+  if (sharded) memcpy(&key.Q, &p->Q, sizeof(PeerDev));
+  key.rec_meth = p->rec_meth;
+  key.live = live_problems(p);
+  key.sharded = sharded ? 1 : 0;
+  {
+    const char *a = getenv("RB_SPEC_G"), *b = getenv("RB_COLS_CHUNKS");
+    key.spec_g = a ? atoi(a) : 0;
+    key.cols_chunks = b ? atoi(b) : 0;
+  }
+  if (!p->gkey_valid || memcmp(&p->gkey, &key, sizeof(key)) != 0) {
+    destroy_graphs(p);
+    memcpy(&p->gkey, &key, sizeof(key));
+    p->gkey_valid = true;
   }
   if (!p->gexec[slot]) {
     const int nl0 = p->info.n_launches;
@@ -1051,8 +1141,14 @@ static int sweep_graph(rb_plan *p) {
       return RB_ERR_UNSUPPORTED;
     }
     p->capturing = true;
-    int rc = sweep_impl(p, 0, 1, false);
-    if (!rc) rc = finish_body(p, slot);
+    int rc;
+    if (sharded) {
+      rc = sweep_impl(p, p->Q.rank, p->Q.world, true);
+      if (!rc) rc = exchange_body(p, p->Q, slot);
+    } else {
+      rc = sweep_impl(p, 0, 1, false);
+      if (!rc) rc = finish_body(p, slot);
+    }
     p->capturing = false;
     cudaGraph_t graph = nullptr;
     const cudaError_t e = cudaStreamEndCapture(s, &graph);
@@ -1073,12 +1169,14 @@ static int sweep_graph(rb_plan *p) {
   p->info.n_launches += p->graph_nl[slot];
   CK(cudaEventRecord(p->sev[slot][4], s));
   p->sweeps_issued += 1;
+  if (sharded) p->peer_sweeps += 1;
   return RB_OK;
 }
 
 // wait for the oldest un-polled sweep; returns the number of problems still active after it
 extern "C" int rb_plan_poll_sweep(rb_plan *p, int *n_active) {
   if (!p || p->sweeps_polled >= p->sweeps_issued) return RB_ERR_BAD_ARG;
+  PLAN_DEV(p);
   const int B = p->d.n_problems;
   const int slot = (int)(p->sweeps_polled % kSlots);
   CK(cudaEventSynchronize(p->sev[slot][4]));
@@ -1120,6 +1218,7 @@ static int plan_sweep_cells(const rb_plan *p) {
 extern "C" int rb_plan_pack_cells(rb_plan *p, int cell_start, int cell_stride, double *dev_send) {
   if (!p || !dev_send || cell_start < 0 || cell_stride < 1 || p->d.n_problems != 1)
     return RB_ERR_BAD_ARG;
+  PLAN_DEV(p);
   const int ncell = plan_sweep_cells(p);
   const int n_local = (cell_start < ncell) ? (ncell - cell_start + cell_stride - 1) / cell_stride : 0;
   if (n_local > 0) {
@@ -1133,6 +1232,7 @@ extern "C" int rb_plan_pack_cells(rb_plan *p, int cell_start, int cell_stride, d
 
 extern "C" int rb_plan_unpack_cells(rb_plan *p, int world, const double *dev_recv) {
   if (!p || !dev_recv || world < 1 || p->d.n_problems != 1) return RB_ERR_BAD_ARG;
+  PLAN_DEV(p);
   const int ncell = plan_sweep_cells(p);
   if (ncell % world != 0) return RB_ERR_BAD_ARG;
   const int n_local = ncell / world;
@@ -1161,8 +1261,16 @@ static int plan_check_errors(rb_plan *p) {
   return rc;
 }
 
+static int direct_sweep(rb_plan *p, bool sharded) {
+  if (sharded) return rb_plan_sweep_sharded(p);
+  int rc = rb_plan_sweep_local(p, 0, 1);
+  if (!rc) rc = rb_plan_finish_sweep_async(p);
+  return rc;
+}
+
 static int solve_loop(rb_plan *p, rb_info *info, bool sharded) {
   if (!p) return RB_ERR_BAD_ARG;
+  PLAN_DEV(p);
   const auto t0 = std::chrono::steady_clock::now();
   const size_t B = p->d.n_problems;
   cudaEventRecord(p->ev[4], p->stream);
@@ -1182,23 +1290,19 @@ static int solve_loop(rb_plan *p, rb_info *info, bool sharded) {
   bool stop = false;
   for (;;) {
     if (!stop && p->sweeps_issued - p->sweeps_polled < kDepth) {
-      if (sharded) {
-        rc = rb_plan_sweep_sharded(p);
-      } else if (use_graphs && p->graphs_ok && p->sweeps_issued > 0 &&
-                 live_problems(p) == p->direct_live) {
+      if (use_graphs && p->graphs_ok && p->sweeps_issued > 0 &&
+          live_problems(p) == p->direct_live) {
         // (the first sweep, and the first one after the launch shapes changed with the number
         // of live problems, goes out directly: it builds the cached work lists -- a host
         // copy that cannot be captured --, sets the kernels' shared-memory attributes and
         // gives the stage times of one sweep)
-        rc = sweep_graph(p);
+        rc = sweep_graph(p, sharded);
         if (rc && !p->graphs_ok) {  // capture not possible: direct launches from here on
-          rc = rb_plan_sweep_local(p, 0, 1);
-          if (!rc) rc = rb_plan_finish_sweep_async(p);
+          rc = direct_sweep(p, sharded);
         }
       } else {
         const int live_now = live_problems(p);
-        rc = rb_plan_sweep_local(p, 0, 1);
-        if (!rc) rc = rb_plan_finish_sweep_async(p);
+        rc = direct_sweep(p, sharded);
         if (!rc) p->direct_live = live_now;
       }
       if (rc) return rc;
@@ -1244,8 +1348,12 @@ extern "C" int rb_plan_solve_sharded(rb_plan *p, rb_info *info) {
   return solve_loop(p, info, true);
 }
 
-extern "C" int rb_plan_bench_steps(rb_plan *p, int steps, size_t flush_bytes, double *ms_sum) {
+// `graphs` != 0: after the first step (direct launches: work lists, stage times) every step
+// is one CUDA-graph launch, as in rb_plan_solve -- what a short sharded sweep needs, whose
+// seven launches cost as much as its kernels.  Stage times are then those of direct steps.
+static int bench_steps(rb_plan *p, int steps, size_t flush_bytes, double *ms_sum, int graphs) {
   if (!p || steps < 0 || !ms_sum) return RB_ERR_BAD_ARG;
+  PLAN_DEV(p);
   void *flush = nullptr;
   if (flush_bytes > 0 && cudaMalloc(&flush, flush_bytes) != cudaSuccess) {
     cudaGetLastError();
@@ -1256,6 +1364,7 @@ extern "C" int rb_plan_bench_steps(rb_plan *p, int steps, size_t flush_bytes, do
   // read-backs like in solve_loop, so that the host's latency -- at N > 1 the slowest
   // rank's, handed on by the cross-GPU barrier -- is not part of what is timed.
   const int kDepth = 4;
+  const bool sharded = p->Q.world > 1;
   std::vector<cudaEvent_t> ev((size_t)2 * steps, nullptr);
   int rc = RB_OK;
   for (auto &e : ev)
@@ -1265,11 +1374,11 @@ extern "C" int rb_plan_bench_steps(rb_plan *p, int steps, size_t flush_bytes, do
     if (issued < steps && p->sweeps_issued - p->sweeps_polled < kDepth) {
       if (flush) cudaMemsetAsync(flush, issued & 0xff, flush_bytes, p->stream);
       cudaEventRecord(ev[2 * issued], p->stream);
-      if (p->Q.world > 1) {
-        rc = rb_plan_sweep_sharded(p);
+      if (graphs && p->graphs_ok && p->sweeps_issued > 0 && p->d.n_problems == 1) {
+        rc = sweep_graph(p, sharded);
+        if (rc && !p->graphs_ok) rc = direct_sweep(p, sharded);
       } else {
-        rc = rb_plan_sweep_local(p, 0, 1);
-        if (!rc) rc = rb_plan_finish_sweep_async(p);
+        rc = direct_sweep(p, sharded);
       }
       cudaEventRecord(ev[2 * issued + 1], p->stream);
       ++issued;
@@ -1295,6 +1404,11 @@ extern "C" int rb_plan_bench_steps(rb_plan *p, int steps, size_t flush_bytes, do
   return rc;
 }
 
+extern "C" int rbi_plan_bench_steps(rb_plan *p, int steps, size_t flush_bytes, int graphs,
+                                    double *ms_sum) {
+  return bench_steps(p, steps, flush_bytes, ms_sum, graphs);
+}
+
 extern "C" int rb_plan_last_info(const rb_plan *p, rb_info *info) {
   if (!p || !info) return RB_ERR_BAD_ARG;
   *info = p->info;
@@ -1306,6 +1420,7 @@ extern "C" int rb_plan_get_problem(rb_plan *p, int b, double *T, double *xH1, do
                                    double *He1i, double *He2i, double *H1h, double *He1h,
                                    double *He2h, int *iters) {
   if (!p || b < 0 || b >= p->d.n_problems) return RB_ERR_BAD_ARG;
+  PLAN_DEV(p);
   const size_t B = p->d.n_problems, Nl = p->d.Nl, NC = B * Nl;
   double *h = p->hout;  // 12 fields of Nl
   cudaStream_t s = p->stream;
@@ -1337,6 +1452,7 @@ extern "C" int rb_plan_get_problem(rb_plan *p, int b, double *T, double *xH1, do
 extern "C" int rb_plan_get_rec(rb_plan *p, int b, double *H1i, double *He1i, double *He2i,
                                double *H1h, double *He1h, double *He2h) {
   if (!p || b < 0 || b >= p->d.n_problems) return RB_ERR_BAD_ARG;
+  PLAN_DEV(p);
   const size_t B = p->d.n_problems, Nl = p->d.Nl, NC = B * Nl;
   double *h = p->hout;  // 12*NC doubles of pinned staging; 6*Nl used
   if (B == 1) {
@@ -1366,6 +1482,7 @@ extern "C" void *rb_plan_field_ptr(rb_plan *p, int field) {
 extern "C" void *rb_plan_stream(rb_plan *p) { return p ? (void *)p->stream : nullptr; }
 extern "C" int rb_plan_sync(rb_plan *p) {
   if (!p) return RB_ERR_BAD_ARG;
+  PLAN_DEV(p);
   CK(cudaStreamSynchronize(p->stream));
   return RB_OK;
 }
@@ -1412,12 +1529,11 @@ static int plan_acquire(rb_plan **out, const rb_plan_desc &d) {
         p->d.i_find_Teq = d.i_find_Teq; p->d.fixed_fcA = d.fixed_fcA; p->d.tol = d.tol;
         p->d.max_sweeps = d.max_sweeps;
         p->P.find_Teq = d.i_find_Teq; p->P.max_sweeps = d.max_sweeps;
+        p->P.libm_pow = 0;
         p->P.fcA = (p->rec_meth == 1) ? d.fixed_fcA : 1.0;
         p->P.tol = d.tol; p->P.tol_inner = d.tol * RB_TOL_FRAC;
-        {
-          const bool unset = d.em_fac[0] == 0.0 && d.em_fac[1] == 0.0 && d.em_fac[2] == 0.0;
-          for (int X = 0; X < 3; ++X) p->K.em_fac[X] = unset ? 1.0 : d.em_fac[X];
-        }
+        for (int X = 0; X < 3; ++X) p->K.em_fac[X] = d.em_fac_set ? d.em_fac[X] : 1.0;
+        // (captured graphs are keyed on everything re-armed here: sweep_graph's GraphKey)
         *out = p;
         return RB_OK;
       }
@@ -1463,9 +1579,11 @@ static int solve_one(int geom, const double *Edges, const double *nH, const doub
   d.i_find_Teq = i_find_Teq; d.fixed_fcA = fixed_fcA; d.tol = tol; d.device = -1;
   d.i_rec_meth = i_rec_meth;
   for (int X = 0; X < 3; ++X) d.em_fac[X] = em_fac ? em_fac[X] : 1.0;
+  d.em_fac_set = 1;
   rb_plan *p = nullptr;
   int rc = plan_acquire(&p, d);
   if (rc) return rc;
+  PLAN_DEV(p);
   rc = rb_plan_set_problem(p, 0, Edges, nH, nHe, T, E_eV, shape, z, Hz);
   if (!rc) rc = rb_plan_upload(p);
   if (!rc) {
@@ -1692,31 +1810,26 @@ __global__ void k_diag_pow(const double *x, const double *y, int n, double *out)
   if (i < n) out[i] = pow_fast(x[i], y[i]);
 }
 __global__ void k_diag_hg97(const double *T, const double *a, const double *b, const double *c,
-                            int n, double *out) {
+                            int n, double *out, int libm) {
   pow_tables_to_smem();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   rb_kchem_t kc;
   rb_kcool_t kl;
-  get_kchem_kcool(T[i], a[i], b[i], c[i], kc, kl);
+  get_kchem_kcool(T[i], a[i], b[i], c[i], kc, kl, libm);
   const double v[16] = {kc.reH2, kc.reHe2, kc.reHe3, kc.ciH1, kc.ciHe1, kc.ciHe2,
                         kl.recH2, kl.recHe2, kl.recHe3, kl.cicH1, kl.cicHe1, kl.cicHe2,
                         kl.cecH1, kl.cecHe2, kl.bremss, kl.compton};
   for (int q = 0; q < 16; ++q) out[(size_t)q * n + i] = v[q];
 }
 
-extern "C" int rb_diag_use_libm_pow(int on) {
-  h_hg_libm = on ? 1 : 0;
-  int n = 0;
-  if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) {
-    cudaGetLastError();
-    return RB_OK;  // host build only (CPU unit tests)
-  }
-  CK(cudaMemcpyToSymbol(d_hg_libm, &h_hg_libm, sizeof(int)));   // current device
+extern "C" int rbi_plan_set_libm_pow(rb_plan *p, int on) {
+  if (!p) return RB_ERR_BAD_ARG;
+  p->P.libm_pow = on ? 1 : 0;   // part of the graph key: captured sweeps are re-captured
   return RB_OK;
 }
 
-extern "C" int rb_diag_pow(const double *x, const double *y, int n, double *out, int on_device) {
+extern "C" int rbi_diag_pow(const double *x, const double *y, int n, double *out, int on_device) {
   if (!x || !y || !out || n < 1) return RB_ERR_BAD_ARG;
   if (!on_device) {
     for (int i = 0; i < n; ++i) out[i] = pow_fast(x[i], y[i]);
@@ -1734,14 +1847,15 @@ extern "C" int rb_diag_pow(const double *x, const double *y, int n, double *out,
   return RB_OK;
 }
 
-extern "C" int rb_diag_hg97(const double *T, const double *fcA_H2, const double *fcA_He2,
-                            const double *fcA_He3, int n, double *out16, int on_device) {
+extern "C" int rbi_diag_hg97(const double *T, const double *fcA_H2, const double *fcA_He2,
+                             const double *fcA_He3, int n, double *out16, int on_device,
+                             int libm) {
   if (!T || !fcA_H2 || !fcA_He2 || !fcA_He3 || !out16 || n < 1) return RB_ERR_BAD_ARG;
   if (!on_device) {
     for (int i = 0; i < n; ++i) {
       rb_kchem_t kc;
       rb_kcool_t kl;
-      get_kchem_kcool(T[i], fcA_H2[i], fcA_He2[i], fcA_He3[i], kc, kl);
+      get_kchem_kcool(T[i], fcA_H2[i], fcA_He2[i], fcA_He3[i], kc, kl, libm);
       const double v[16] = {kc.reH2, kc.reHe2, kc.reHe3, kc.ciH1, kc.ciHe1, kc.ciHe2,
                             kl.recH2, kl.recHe2, kl.recHe3, kl.cicH1, kl.cicHe1, kl.cicHe2,
                             kl.cecH1, kl.cecHe2, kl.bremss, kl.compton};
@@ -1756,7 +1870,8 @@ extern "C" int rb_diag_hg97(const double *T, const double *fcA_H2, const double 
   if ((rc = upload_fields(in, f, 4, n))) return rc;
   if ((rc = o.alloc((size_t)16 * n))) return rc;
   const size_t nn = n;
-  k_diag_hg97<<<(n + 127) / 128, 128>>>(in.d, in.d + nn, in.d + 2 * nn, in.d + 3 * nn, n, o.d);
+  k_diag_hg97<<<(n + 127) / 128, 128>>>(in.d, in.d + nn, in.d + 2 * nn, in.d + 3 * nn, n, o.d,
+                                        libm);
   CK(cudaGetLastError());
   CK(cudaMemcpy(out16, o.d, (size_t)16 * n * 8, cudaMemcpyDeviceToHost));
   return RB_OK;
@@ -1878,21 +1993,26 @@ extern "C" int rb_solve_pcte(const double *nH, const double *nHe, const double *
 // ---------------------------------------------------------------------------
 // micro-benchmarks
 // ---------------------------------------------------------------------------
-extern "C" int rb_microbench(int kind, int device, double *ops_per_s) {
+extern "C" int rbi_microbench(int kind, int device, double *ops_per_s) {
   if (!ops_per_s || kind < 0 || kind > 3) return RB_ERR_BAD_ARG;
   int rc = need_device();
   if (rc) return rc;
-  if (device >= 0) CK(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device >= 0 ? device : 0));
-  const int blocks = prop.multiProcessorCount * 8, threads = 256;
-  const int iters = (kind == 0) ? 4096 : (kind == 3 ? 128 : 512);
+  DevGuard dev_guard_(device);
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  int n_sm = 0;
+  CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  // DFMA: 4 CTAs x 8 warps per SM, 64 FMAs per trip, ~60 ms per repetition at 17e12 FMA/s
+  const int blocks = n_sm * (kind == 0 ? 4 : 8), threads = 256;
+  const int iters = (kind == 0) ? 100000 : (kind == 3 ? 128 : 512);
+  const double per_trip = (kind == 0) ? 64.0 : 8.0;
   DevBuf out;
   if ((rc = out.alloc((size_t)blocks * threads))) return rc;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   double best = 0.0;
-  for (int rep = 0; rep < 4; ++rep) {
+  const int reps = (kind == 0) ? 3 : 4;
+  for (int rep = 0; rep < reps; ++rep) {
     cudaEventRecord(e0);
     switch (kind) {
       case 0: k_microbench<0><<<blocks, threads>>>(out.d, iters, 0.5); break;
@@ -1904,7 +2024,7 @@ extern "C" int rb_microbench(int kind, int device, double *ops_per_s) {
     CK(cudaEventSynchronize(e1));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    const double ops = (double)blocks * threads * iters * 8.0;
+    const double ops = (double)blocks * threads * iters * per_trip;
     if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);

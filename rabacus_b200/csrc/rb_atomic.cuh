@@ -166,20 +166,9 @@ RB_HD double mix_caseAB_f(double a, double b, double fcA) {
   return pow10_fast_nf(log10_call(a) * fcA + log10_call(b) * (1.0 - fcA));
 }
 
-// valid range of the fast evaluation (all bases normal, all |y log x| < 700);
-// rb_diag_use_libm_pow(1) forces the libm statement form everywhere (A/B tests)
-static int h_hg_libm = 0;
-#ifdef __CUDACC__
-static __device__ int d_hg_libm = 0;
-#endif
-RB_HD bool hg_fast_ok(double T) {
-#ifdef __CUDA_ARCH__
-  if (d_hg_libm) return false;
-#else
-  if (h_hg_libm) return false;
-#endif
-  return T >= 1.0 && T <= 1.0e12;
-}
+// valid range of the fast evaluation (all bases normal, all |y log x| < 700); `libm` != 0
+// forces the libm statement form everywhere (a per-plan flag for A/B tests, rb_internal.h)
+RB_HD bool hg_fast_ok(double T, int libm) { return !libm && T >= 1.0 && T <= 1.0e12; }
 
 template <bool CHEM, bool COOL>
 RB_HD void hg97_eval(double T, double fcA_H2, double fcA_He2, double fcA_He3, rb_kchem_t &kc,
@@ -236,15 +225,17 @@ RB_HD void hg97_eval(double T, double fcA_H2, double fcA_He2, double fcA_He3, rb
   }
 }
 
-RB_HDN rb_kchem_t get_kchem(double T, double fcA_H2, double fcA_He2, double fcA_He3) {
-  if (!hg_fast_ok(T)) return get_kchem_libm(T, fcA_H2, fcA_He2, fcA_He3);
+RB_HDN rb_kchem_t get_kchem(double T, double fcA_H2, double fcA_He2, double fcA_He3,
+                            int libm = 0) {
+  if (!hg_fast_ok(T, libm)) return get_kchem_libm(T, fcA_H2, fcA_He2, fcA_He3);
   rb_kchem_t kc;
   rb_kcool_t kl;
   hg97_eval<true, false>(T, fcA_H2, fcA_He2, fcA_He3, kc, kl);
   return kc;
 }
-RB_HDN rb_kcool_t get_kcool(double T, double fcA_H2, double fcA_He2, double fcA_He3) {
-  if (!hg_fast_ok(T)) return get_kcool_libm(T, fcA_H2, fcA_He2, fcA_He3);
+RB_HDN rb_kcool_t get_kcool(double T, double fcA_H2, double fcA_He2, double fcA_He3,
+                            int libm = 0) {
+  if (!hg_fast_ok(T, libm)) return get_kcool_libm(T, fcA_H2, fcA_He2, fcA_He3);
   rb_kchem_t kc;
   rb_kcool_t kl;
   hg97_eval<false, true>(T, fcA_H2, fcA_He2, fcA_He3, kc, kl);
@@ -252,8 +243,8 @@ RB_HDN rb_kcool_t get_kcool(double T, double fcA_H2, double fcA_He2, double fcA_
 }
 // both sets at one temperature (one probe of solve_pcte, ion_solver.f90:1089-1134)
 RB_HDN void get_kchem_kcool(double T, double fcA_H2, double fcA_He2, double fcA_He3,
-                            rb_kchem_t &kc, rb_kcool_t &kl) {
-  if (!hg_fast_ok(T)) {
+                            rb_kchem_t &kc, rb_kcool_t &kl, int libm = 0) {
+  if (!hg_fast_ok(T, libm)) {
     kc = get_kchem_libm(T, fcA_H2, fcA_He2, fcA_He3);
     kl = get_kcool_libm(T, fcA_H2, fcA_He2, fcA_He3);
     return;

@@ -1,0 +1,48 @@
+/*
+ * rb_internal.h -- measurement and diagnostic entry points of librabacus_b200.so.
+ *
+ * NOT part of the drop-in boundary (include/rabacus_b200.h): nothing here replaces an
+ * interface of the reference.  These symbols exist for bench.py (timed steps, FP64-pipe
+ * micro-benchmarks) and for the unit tests of the arithmetic in rb_fastpow.cuh /
+ * rb_atomic.cuh; no solver entry point calls them.
+ */
+#ifndef RB_INTERNAL_H
+#define RB_INTERNAL_H
+
+#include "../../include/rabacus_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* out[i] = x[i]**y[i] by csrc/rb_fastpow.cuh.  on_device = 0 evaluates the same inline
+ * source with the host compiler (unit tests without a GPU), 1 runs one CUDA thread per
+ * element. */
+int rbi_diag_pow(const double *x, const double *y, int n, double *out, int on_device);
+/* The 6 + 10 coefficients of get_kchem_s / get_kcool_s (chem_cool_rates.f90:45-204) as
+ * out16[16][n].  libm != 0: every power through libm / libdevice pow(), statement by
+ * statement, instead of the table-driven form. */
+int rbi_diag_hg97(const double *T, const double *fcA_H2, const double *fcA_He2,
+                  const double *fcA_He3, int n, double *out16, int on_device, int libm);
+/* Per-plan A/B switch: on != 0 makes every kernel of THIS plan evaluate the Hui & Gnedin
+ * fits through libdevice pow() (no global state; other plans are unaffected). */
+int rbi_plan_set_libm_pow(rb_plan *plan, int on);
+
+/* Run `steps` Jacobi sweeps (rb_plan_sweep_local over all cells + rb_plan_finish_sweep;
+ * rb_plan_sweep_sharded on a peer-connected plan) and return their summed device time in
+ * ms, every step bracketed by its own pair of CUDA events on the plan's stream.  If
+ * flush_bytes > 0 a scratch buffer of that size is overwritten between steps (L2 flush),
+ * outside the timed spans.  graphs != 0: steps after the first are replayed as CUDA
+ * graphs like in rb_plan_solve (single-problem plans). */
+int rbi_plan_bench_steps(rb_plan *plan, int steps, size_t flush_bytes, int graphs,
+                         double *ms_sum);
+
+/* FP64 pipe micro-benchmarks used as roofline denominators (bench.py):
+ * kind 0 = DFMA (64 FMAs per loop trip on 32 independent chains, >= 50 ms per repetition),
+ * 1 = exp, 2 = sqrt, 3 = pow (CUDA library functions).  Returns operations / second. */
+int rbi_microbench(int kind, int device, double *ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

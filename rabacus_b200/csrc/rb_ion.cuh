@@ -29,6 +29,7 @@ struct PhotoRates {
 // drivers; independent in the single-zone API)
 struct CaseA {
   double H2, He2, He3;
+  int libm = 0;  // != 0: Hui & Gnedin fits through libm pow() (diagnostic A/B, rb_internal.h)
 };
 
 RB_HD void fpc(rb_frac_t &x) {
@@ -168,7 +169,7 @@ RB_HDN int get_dudT(double nH, double nHe, double T, const PhotoRates &p,
                    double z, double Hz, const CaseA &fc, double tol, double &dudT) {
   rb_kchem_t kc;
   rb_kcool_t kl;
-  get_kchem_kcool(T, fc.H2, fc.He2, fc.He3, kc, kl);
+  get_kchem_kcool(T, fc.H2, fc.He2, fc.He3, kc, kl, fc.libm);
   rb_frac_t x;
   const int rc = solve_pce(nH, nHe, kc, p.H1i, p.He1i, p.He2i, tol, x);
   if (rc) return rc;
@@ -186,7 +187,7 @@ RB_HDN int probe_T(double nH, double nHe, double T, const PhotoRates &p, double 
                    double Hz, const CaseA &fc, double tol, double &dudT, rb_frac_t &x) {
   rb_kchem_t kc;
   rb_kcool_t kl;
-  get_kchem_kcool(T, fc.H2, fc.He2, fc.He3, kc, kl);
+  get_kchem_kcool(T, fc.H2, fc.He2, fc.He3, kc, kl, fc.libm);
   const int rc = solve_pce(nH, nHe, kc, p.H1i, p.He1i, p.He2i, tol, x);
   if (rc) return rc;
   const double heat =
@@ -220,7 +221,7 @@ RB_HDN int solve_pcte(double nH, double nHe, const PhotoRates &p, double z,
   int rc = get_dudT(nH, nHe, Tleft, p, z, Hz, fc, tol, dudTmin);
   if (rc) return rc;
   if (dudTmin < 0.0) {  // :782-794: equilibrium below the floor
-    const rb_kchem_t kc = get_kchem(Tleft, fc.H2, fc.He2, fc.He3);
+    const rb_kchem_t kc = get_kchem(Tleft, fc.H2, fc.He2, fc.He3, fc.libm);
     rc = solve_pce(nH, nHe, kc, p.H1i, p.He1i, p.He2i, tol, x);
     Tout = Tleft;
     return rc;
@@ -248,7 +249,7 @@ RB_HDN int solve_pcte(double nH, double nHe, const PhotoRates &p, double z,
     iter = iter + 1;
     if (iter > RB_ION_MAX_ITER) return ION_ERR_MAX_ITER_PCTE;
   }
-  const rb_kchem_t kc = get_kchem(T, fc.H2, fc.He2, fc.He3);
+  const rb_kchem_t kc = get_kchem(T, fc.H2, fc.He2, fc.He3, fc.libm);
   rc = solve_pce(nH, nHe, kc, p.H1i, p.He1i, p.He2i, tol, x);
   if (rc) return rc;
   zero_absent_species(nH, nHe, x);

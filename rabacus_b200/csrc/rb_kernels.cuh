@@ -48,6 +48,7 @@ constexpr int kThinStride = 9;  // per problem: 6 optically thin integrals, 3 ma
 // Everything a kernel needs, passed by value.
 struct PlanDev {
   int B, Nl, Nnu, Nmu, Ndir, geom, find_Teq, max_sweeps;
+  int libm_pow, pad0_;     // libm_pow != 0: rate fits through libm pow() (diagnostic A/B)
   double fcA, tol, tol_inner;
   double sigma_th[3];
   const double *Edges;  // [B][Nl+1] in solver orientation
@@ -82,19 +83,32 @@ struct PlanDev {
 // the staged fractions into the full state arrays and runs the convergence test.
 // Two staging rows alternate: a rank can run at most one barrier ahead.
 constexpr int kMaxPeers = 8;
+// Layout of a rank's peer buffer: 256 control bytes, then the staging rows.
+//   u64[0..7]   flags, slot r written by rank r ("my cells of sweep e are staged here")
+//   u64[16]     epoch: sweeps this rank has completed (device-resident, so that a sharded
+//               sweep has no per-sweep kernel argument and can be replayed as a CUDA graph)
+//   u64[17..19] arrival counter / not-converged count / worst change of the multi-CTA finish
+constexpr int kPeerCtl = 16;
+constexpr unsigned long long kPeerPoison = ~0ull;   // flag value: "a rank gave up, abort"
 struct PeerDev {
-  int world, rank, n_local, parity;
-  unsigned long long epoch;               // flag value that means "this sweep is staged"
+  int world, rank, n_local, pad_;
+  unsigned long long timeout_ns;          // barrier timeout (RB_ERR_PEER_TIMEOUT)
+  unsigned long long *ctl;                // this rank's control words (own buffer + kPeerCtl)
   double *stage[kMaxPeers];               // rank r's staging [2][world][6][n_local]
   unsigned long long *flags[kMaxPeers];   // rank r's flags [kMaxPeers], written by its peers
 };
 
 constexpr int kExchangeFields = 18;  // rb_plan_pack_cells / rb_plan_unpack_cells
 constexpr int kPeerFields = 6;  // five fractions + T (the photon-transfer closures read all T)
+// id of the sweep in flight = completed sweeps + 1; its staging row alternates
+__device__ __forceinline__ unsigned long long peer_sweep_id(const PeerDev &Q) {
+  return *(volatile const unsigned long long *)Q.ctl + 1ull;
+}
 __device__ __forceinline__ void peer_scatter(const PeerDev &Q, int j, const rb_frac_t &x,
                                              double T) {
   const size_t n = (size_t)Q.n_local;
-  const size_t off = ((size_t)(Q.parity * Q.world + Q.rank) * kPeerFields) * n + j;
+  const int parity = (int)(peer_sweep_id(Q) & 1ull);
+  const size_t off = ((size_t)(parity * Q.world + Q.rank) * kPeerFields) * n + j;
   for (int r = 0; r < Q.world; ++r) {
     double *d = Q.stage[r] + off;
     d[0] = x.xH1; d[n] = x.xH2; d[2 * n] = x.xHe1; d[3 * n] = x.xHe2; d[4 * n] = x.xHe3;
@@ -784,7 +798,7 @@ k_cell_solve(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_local)
   double T = P.T[c];
   int rc;
   if (P.find_Teq) {
-    const CaseA fc = {P.fcA, P.fcA, P.fcA};
+    const CaseA fc = {P.fcA, P.fcA, P.fcA, P.libm_pow};
     rc = solve_pcte(nH, nHe, p, P.zHz[2 * b], P.zHz[2 * b + 1], fc, P.tol_inner, x, T);
   } else {
     // get_kchem(T) of sphere_bgnd.f90:897-899: T is fixed, the coefficients were stored
@@ -963,7 +977,7 @@ k_cell_solve_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_l
   p.He1h = P.src[4][c] + P.rec[4][c]; p.He2h = P.src[5][c] + P.rec[5][c];
   const double nH = P.nH[c], nHe = P.nHe[c];
   const double z = P.zHz[2 * b], Hz = P.zHz[2 * b + 1];
-  const CaseA fc = {P.fcA, P.fcA, P.fcA};
+  const CaseA fc = {P.fcA, P.fcA, P.fcA, P.libm_pow};
   const double tol = P.tol_inner;
 
   TBisect root;
@@ -1058,6 +1072,38 @@ k_cell_solve_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_l
 // ---------------------------------------------------------------------------
 constexpr int kSlots = 8;
 
+// change of n_e in one cell (sphere_bgnd.f90:289-296); updates the reference value
+__device__ __forceinline__ void cell_change(const PlanDev &P, size_t c, int &notconv,
+                                            double &worst) {
+  const double ne = P.x[1][c] * P.nH[c] + (P.x[3][c] + 2.0 * P.x[4][c]) * P.nHe[c];
+  const double change = fabs(ne / P.conv_old[c] - 1.0);
+  if (!(change < P.tol)) notconv = 1;
+  if (change > worst) worst = change;  // NaN never wins: it only sets notconv
+  P.conv_old[c] = ne;
+}
+
+// iteration bookkeeping of the drivers for problem b, by one thread
+__device__ __forceinline__ void finish_bookkeeping(const PlanDev &P, int b, int slot, int notconv,
+                                                   double worst) {
+  P.resid_bits[b] = (unsigned long long)__double_as_longlong(worst);
+  int act = 1;
+  if (P.err[b]) act = 0;
+  // sphere_bgnd.f90:284-288: the limit is tested before the increment
+  if (P.geom != RB_GEOM_SLAB_BGND && P.iters[b] > RB_OUTER_MAX_ITER && P.max_sweeps >= 0) {
+    atomicMax(&P.err[b], RB_ERR_MAX_ITER_OUTER);
+    act = 0;
+  }
+  P.iters[b] += 1;
+  // max_sweeps < 0: fixed-work mode (benchmarks): exactly -max_sweeps sweeps
+  if (!notconv && P.max_sweeps >= 0) act = 0;
+  if (P.geom == RB_GEOM_SLAB_BGND && P.iters[b] >= RB_SLAB_BGND_MAX_SWEEPS &&
+      P.max_sweeps >= 0) act = 0;
+  if (P.max_sweeps > 0 && P.iters[b] >= P.max_sweeps) act = 0;
+  if (P.max_sweeps < 0 && P.iters[b] >= -P.max_sweeps) act = 0;
+  P.active[b] = act;
+  if (act) atomicAdd(&P.nactive[slot], 1);
+}
+
 template <int BLOCK>
 __device__ __forceinline__ void converge_finish(const PlanDev &P, int slot) {
   const int b = blockIdx.x;
@@ -1066,37 +1112,15 @@ __device__ __forceinline__ void converge_finish(const PlanDev &P, int slot) {
   __shared__ double s_max[BLOCK / 32];
   int notconv = 0;
   double worst = 0.0;
-  for (int il = threadIdx.x; il < P.Nl; il += BLOCK) {
-    const size_t c = (size_t)b * P.Nl + il;
-    const double ne = P.x[1][c] * P.nH[c] + (P.x[3][c] + 2.0 * P.x[4][c]) * P.nHe[c];
-    const double change = fabs(ne / P.conv_old[c] - 1.0);
-    if (!(change < P.tol)) notconv = 1;
-    if (change > worst) worst = change;  // NaN never wins: it only sets notconv
-    P.conv_old[c] = ne;
-  }
+  for (int il = threadIdx.x; il < P.Nl; il += BLOCK)
+    cell_change(P, (size_t)b * P.Nl + il, notconv, worst);
   notconv = __syncthreads_or(notconv);
   for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_down_sync(0xffffffffu, worst, o));
   if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = worst;
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < BLOCK / 32; ++w) worst = fmax(worst, s_max[w]);
-    P.resid_bits[b] = (unsigned long long)__double_as_longlong(worst);
-    int act = 1;
-    if (P.err[b]) act = 0;
-    // sphere_bgnd.f90:284-288: the limit is tested before the increment
-    if (P.geom != RB_GEOM_SLAB_BGND && P.iters[b] > RB_OUTER_MAX_ITER && P.max_sweeps >= 0) {
-      atomicMax(&P.err[b], RB_ERR_MAX_ITER_OUTER);
-      act = 0;
-    }
-    P.iters[b] += 1;
-    // max_sweeps < 0: fixed-work mode (benchmarks): exactly -max_sweeps sweeps
-    if (!notconv && P.max_sweeps >= 0) act = 0;
-    if (P.geom == RB_GEOM_SLAB_BGND && P.iters[b] >= RB_SLAB_BGND_MAX_SWEEPS &&
-        P.max_sweeps >= 0) act = 0;
-    if (P.max_sweeps > 0 && P.iters[b] >= P.max_sweeps) act = 0;
-    if (P.max_sweeps < 0 && P.iters[b] >= -P.max_sweeps) act = 0;
-    P.active[b] = act;
-    if (act) atomicAdd(&P.nactive[slot], 1);
+    finish_bookkeeping(P, b, slot, notconv, worst);
   }
 }
 
@@ -1106,10 +1130,14 @@ __global__ void __launch_bounds__(BLOCK) k_converge_finish(PlanDev P, int slot) 
 }
 
 // k_exchange_finish: the cell-sharded sweep's barrier + scatter + convergence test
-// (single-problem plans; one CTA).  Thread 0 publishes "my cells are staged
-// everywhere" (system-scope release after the cell kernel's remote stores) and
-// acquires the same from every peer; a peer that never arrives trips a 2 s
-// timeout (RB_ERR_PEER_TIMEOUT) instead of hanging the GPU.
+// (single-problem plans), spread over a few CTAs.  CTA 0 publishes "my cells of sweep e
+// are staged everywhere" (system-scope release after the cell kernel's remote stores);
+// every CTA acquires the same from every peer, scatters its slice of the staged fractions
+// into the full state arrays and tests the cells it scattered; the CTA that arrives last
+// does the bookkeeping and advances the device-resident sweep counter.  A peer that never
+// arrives trips the timeout: the rank raises RB_ERR_PEER_TIMEOUT, skips the scatter and
+// poisons its flag on every peer, so that all ranks abort the solve instead of iterating
+// on half-written staging (the plan is unusable afterwards).
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -1118,44 +1146,87 @@ __device__ __forceinline__ unsigned long long global_ns() {
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_exchange_finish(PlanDev P, PeerDev Q, int slot) {
+  __shared__ int s_bad;
+  __shared__ double s_max[BLOCK / 32];
+  const unsigned long long e = peer_sweep_id(Q);   // read by every CTA before it arrives
   if (threadIdx.x == 0) {
-    __threadfence_system();
-    for (int r = 0; r < Q.world; ++r)
-      if (r != Q.rank)
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(Q.flags[r] + Q.rank), "l"(Q.epoch)
-                     : "memory");
+    int bad = 0;
+    if (blockIdx.x == 0) {
+      P.nactive[(slot + 1) % kSlots] = 0;
+      __threadfence_system();
+      for (int r = 0; r < Q.world; ++r)
+        if (r != Q.rank)
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(Q.flags[r] + Q.rank), "l"(e)
+                       : "memory");
+    }
     const unsigned long long t0 = global_ns();
-    for (int r = 0; r < Q.world; ++r) {
+    for (int r = 0; r < Q.world && !bad; ++r) {
       if (r == Q.rank) continue;
       for (;;) {
         unsigned long long v;
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(Q.flags[Q.rank] + r)
                      : "memory");
-        if (v >= Q.epoch) break;
-        if (global_ns() - t0 > 2000000000ull) {
-          atomicMax(&P.err[0], RB_ERR_PEER_TIMEOUT);
-          break;
-        }
+        if (v == kPeerPoison) { bad = 1; break; }
+        if (v >= e) break;
+        if (global_ns() - t0 > Q.timeout_ns) { bad = 1; break; }
       }
     }
+    if (bad) {
+      atomicMax(&P.err[0], RB_ERR_PEER_TIMEOUT);
+      for (int r = 0; r < Q.world; ++r)
+        if (r != Q.rank)
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(Q.flags[r] + Q.rank),
+                       "l"(kPeerPoison) : "memory");
+    }
+    s_bad = bad;
   }
   __syncthreads();
-  if (P.active[0]) {
+  int notconv = 0;
+  double worst = 0.0;
+  if (P.active[0] && !s_bad) {
     const size_t n = (size_t)Q.n_local;
-    const double *st = Q.stage[Q.rank] + (size_t)Q.parity * Q.world * kPeerFields * n;
-    const int total = Q.world * kPeerFields * Q.n_local;
-    for (int i = threadIdx.x; i < total; i += BLOCK) {
-      const int j = i % Q.n_local, f = (i / Q.n_local) % kPeerFields,
-                g = i / (kPeerFields * Q.n_local);
-      const double v = __ldcv(st + i);
+    const double *st = Q.stage[Q.rank] + (size_t)(e & 1ull) * Q.world * kPeerFields * n;
+    const int ncell = Q.world * Q.n_local;
+    const bool two = two_sided(P.geom);
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < ncell; i += gridDim.x * BLOCK) {
+      const int g = i / Q.n_local, j = i - g * Q.n_local;
       const int il = j * Q.world + g;
-      double *dst = (f < 5) ? P.x[f] : P.T;
-      dst[il] = v;
-      if (two_sided(P.geom)) dst[P.Nl - 1 - il] = v;  // mirrored half
+#pragma unroll
+      for (int f = 0; f < kPeerFields; ++f) {
+        const double v = __ldcv(st + ((size_t)g * kPeerFields + f) * n + j);
+        double *dst = (f < 5) ? P.x[f] : P.T;
+        dst[il] = v;
+        if (two) dst[P.Nl - 1 - il] = v;  // mirrored half
+      }
+      cell_change(P, (size_t)il, notconv, worst);
+      if (two) cell_change(P, (size_t)(P.Nl - 1 - il), notconv, worst);
+    }
+    // the never-solved middle layer of a two-sided slab with odd Nl
+    if (two && (P.Nl & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+      cell_change(P, (size_t)(P.Nl / 2), notconv, worst);
+  }
+  notconv = __syncthreads_or(notconv);
+  for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_down_sync(0xffffffffu, worst, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = worst;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < BLOCK / 32; ++w) worst = fmax(worst, s_max[w]);
+    unsigned long long *ctl = Q.ctl;
+    if (notconv) atomicAdd(ctl + 2, 1ull);
+    atomicMax(ctl + 3, (unsigned long long)__double_as_longlong(worst));  // worst >= 0
+    __threadfence();
+    const unsigned long long arrived = atomicAdd(ctl + 1, 1ull);
+    if (arrived == (unsigned long long)gridDim.x - 1ull) {   // last CTA of this rank
+      __threadfence();
+      const unsigned long long nc = atomicAdd(ctl + 2, 0ull);
+      const unsigned long long wb = atomicAdd(ctl + 3, 0ull);
+      if (P.active[0])
+        finish_bookkeeping(P, 0, slot, nc != 0ull, __longlong_as_double((long long)wb));
+      ctl[1] = 0ull; ctl[2] = 0ull; ctl[3] = 0ull;
+      __threadfence();
+      *(volatile unsigned long long *)ctl = e;   // sweep e is complete on this rank
     }
   }
-  __syncthreads();
-  converge_finish<BLOCK>(P, slot);
 }
 
 // ---------------------------------------------------------------------------
@@ -1270,12 +1341,12 @@ __host__ __device__ int dudT_lockstep(const double (&nH)[CPT], const double (&nH
   rb_frac_t x[CPT];
 RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i)
-    if (valid[i]) kc[i] = get_kchem(T[i], fc.H2, fc.He2, fc.He3);
+    if (valid[i]) kc[i] = get_kchem(T[i], fc.H2, fc.He2, fc.He3, fc.libm);
   const int rc = pce_lockstep<CPT>(nH, nHe, kc, p, valid, tol, x, block_any);
 RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) {
     if (valid[i]) {
-      const rb_kcool_t kl = get_kcool(T[i], fc.H2, fc.He2, fc.He3);
+      const rb_kcool_t kl = get_kcool(T[i], fc.H2, fc.He2, fc.He3, fc.libm);
       const double heat = get_heat(nH[i], nHe[i], p[i].H1h, p[i].He1h, p[i].He2h,
                                    x[i].xH1, x[i].xHe1, x[i].xHe2);
       const double cool = get_cool(nH[i], nHe[i], T[i], kl, x[i], z, Hz);
@@ -1342,7 +1413,7 @@ RB_LS_UNROLL
   rb_kchem_t kc[CPT];
 RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i)
-    if (valid[i]) kc[i] = get_kchem(T[i], fc.H2, fc.He2, fc.He3);
+    if (valid[i]) kc[i] = get_kchem(T[i], fc.H2, fc.He2, fc.He3, fc.libm);
   r = pce_lockstep<CPT>(nH, nHe, kc, p, valid, tol, x, block_any);
   if (r) rc = r;
   return rc;
@@ -1384,7 +1455,7 @@ RB_LS_UNROLL
     p[i].H1h = th[3] * scale; p[i].He1h = th[4] * scale; p[i].He2h = th[5] * scale;
   }
   int rc;
-  const CaseA fc = {P.fcA, P.fcA, P.fcA};
+  const CaseA fc = {P.fcA, P.fcA, P.fcA, P.libm_pow};
   if (P.find_Teq) {
     rc = pcte_lockstep<CPT>(nH, nHe, p, valid, P.zHz[2 * b], P.zHz[2 * b + 1], fc,
                             P.tol_inner, x, T, any_fn);
@@ -1392,7 +1463,7 @@ RB_LS_UNROLL
     rb_kchem_t k[CPT];
 RB_LS_UNROLL
     for (int i = 0; i < CPT; ++i)
-      if (valid[i]) k[i] = get_kchem(T[i], fc.H2, fc.He2, fc.He3);
+      if (valid[i]) k[i] = get_kchem(T[i], fc.H2, fc.He2, fc.He3, fc.libm);
     rc = pce_lockstep<CPT>(nH, nHe, k, p, valid, P.tol_inner, x, any_fn);
     const size_t NC = (size_t)P.B * Nl;
 RB_LS_UNROLL
@@ -1581,16 +1652,33 @@ RB_LS_UNROLL
 // ---------------------------------------------------------------------------
 // FP64-pipe micro-benchmarks (roofline denominators)
 // ---------------------------------------------------------------------------
+// KIND 0 (DFMA): 32 independent accumulators, 64 FMAs per loop trip fully unrolled, so that
+// the loop's own integer add / compare / branch are ~3 of 67 instructions (each non-FP64
+// instruction costs a dispatch slot: with 8 FMAs per trip the figure read 8 % low).
 template <int KIND>
 __global__ void __launch_bounds__(256) k_microbench(double *out, int iters, double seed) {
+  if (KIND == 0) {
+    double a[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) a[q] = seed + threadIdx.x * 1e-9 + 0.01 * q;
+    const double m = 0.999999, c = 1e-7;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int q = 0; q < 32; ++q) a[q] = fma(a[q], m, c);
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) sum += a[q];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = sum;
+    return;
+  }
   double a0 = seed + threadIdx.x * 1e-9, a1 = a0 + 0.1, a2 = a0 + 0.2, a3 = a0 + 0.3;
   double a4 = a0 + 0.4, a5 = a0 + 0.5, a6 = a0 + 0.6, a7 = a0 + 0.7;
-  const double m = 0.999999, c = 1e-7;
   for (int i = 0; i < iters; ++i) {
-    if (KIND == 0) {
-      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
-    } else if (KIND == 1) {
+    if (KIND == 1) {
       a0 = exp(-a0) + 0.5; a1 = exp(-a1) + 0.5; a2 = exp(-a2) + 0.5; a3 = exp(-a3) + 0.5;
       a4 = exp(-a4) + 0.5; a5 = exp(-a5) + 0.5; a6 = exp(-a6) + 0.5; a7 = exp(-a7) + 0.5;
     } else if (KIND == 2) {

@@ -79,8 +79,8 @@ __global__ void k_rec_prep(PlanDev P, RecDev R, RecConst K, int rec_meth) {
   const double xH1 = P.x[0][c], xH2 = P.x[1][c], xHe1 = P.x[2][c], xHe2 = P.x[3][c],
                xHe3 = P.x[4][c];
   // case A - case B = recombinations to the ground state (sphere_base.f90:238-262)
-  const rb_kchem_t kA = get_kchem(T, 1.0, 1.0, 1.0);
-  const rb_kchem_t kB = get_kchem(T, 0.0, 0.0, 0.0);
+  const rb_kchem_t kA = get_kchem(T, 1.0, 1.0, 1.0, P.libm_pow);
+  const rb_kchem_t kB = get_kchem(T, 0.0, 0.0, 0.0, P.libm_pow);
   const double reH2_1 = kA.reH2 - kB.reH2, reHe2_1 = kA.reHe2 - kB.reHe2,
                reHe3_1 = kA.reHe3 - kB.reHe3;
   const double ne = xH2 * nH + (xHe2 + 2.0 * xHe3) * nHe;  // :267

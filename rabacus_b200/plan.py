@@ -37,7 +37,7 @@ class Plan(object):
         self.desc = rb_plan_desc(int(geometry), int(n_problems), int(Nl), int(Nnu), int(Nmu),
                                  1 if find_Teq else 0, float(fixed_fcA), float(tol),
                                  int(device), int(max_sweeps), int(i_rec_meth),
-                                 (C.c_double * 3)(*[float(v) for v in em_fac]))
+                                 (C.c_double * 3)(*[float(v) for v in em_fac]), 1)
         self._h = C.c_void_p()
         check(lib().rb_plan_create(C.byref(self._h), C.byref(self.desc)))
         self.n_problems, self.Nl, self.Nnu, self.Nmu = n_problems, Nl, Nnu, Nmu
@@ -97,12 +97,18 @@ class Plan(object):
         check(lib().rb_plan_solve(self._h, C.byref(info)))
         return info.as_dict()
 
-    def bench_steps(self, steps, flush_bytes=0):
-        """Run ``steps`` sweeps; returns their summed device time [ms] (CUDA events)."""
+    def bench_steps(self, steps, flush_bytes=0, graphs=False):
+        """Run ``steps`` sweeps; returns their summed device time [ms] (CUDA events).
+        ``graphs``: replay the sweeps as CUDA graphs like :meth:`solve` does."""
         ms = C.c_double(0.0)
-        check(lib().rb_plan_bench_steps(self._h, C.c_int(int(steps)),
-                                        C.c_size_t(int(flush_bytes)), C.byref(ms)))
+        check(lib().rbi_plan_bench_steps(self._h, C.c_int(int(steps)),
+                                         C.c_size_t(int(flush_bytes)),
+                                         C.c_int(1 if graphs else 0), C.byref(ms)))
         return ms.value
+
+    def set_libm_pow(self, on):
+        """Diagnostic A/B switch of THIS plan: rate fits through libdevice pow()."""
+        check(lib().rbi_plan_set_libm_pow(self._h, C.c_int(1 if on else 0)))
 
     def last_info(self):
         info = rb_info()

@@ -3,14 +3,14 @@ sys.path.insert(0, '/root/repo')
 from rabacus_b200 import _lib
 L = _lib.lib()
 def P(a): return a.ctypes.data_as(C.POINTER(C.c_double))
-L.rb_diag_pow.argtypes = [C.POINTER(C.c_double)]*2 + [C.c_int, C.POINTER(C.c_double), C.c_int]
+L.rbi_diag_pow.argtypes = [C.POINTER(C.c_double)]*2 + [C.c_int, C.POINTER(C.c_double), C.c_int]
 rng = np.random.default_rng(1)
 n = 400000
 # bases / exponents as in the fits: lam in [1e-6, 2e6], (1+u), T, 10 ; y in [-4, 4]
 x = np.concatenate([10**rng.uniform(-6, 6.5, n//2), 1 + 10**rng.uniform(-8, 7, n//4), rng.uniform(0.5, 2.0, n//4)])
 y = rng.uniform(-4, 4, n)
 out = np.empty(n)
-assert L.rb_diag_pow(P(x), P(y), n, P(out), 0) == 0
+assert L.rbi_diag_pow(P(x), P(y), n, P(out), 0) == 0
 ref = np.power(x, y)
 ulp = np.spacing(np.abs(ref))
 d = (out - ref)/ulp

@@ -11,7 +11,7 @@ T[:n//2] = 10**rng.uniform(np.log10(7.5e3), 5.0, n//2)
 T[-5:] = [0.5, 1e13, 1.0, 1e12, 7500.0]
 f = [rng.choice([0.0, 1.0, 0.3, 0.77], n) for _ in range(3)]
 out = np.empty((16, n))
-assert L.rb_diag_hg97(P(T), P(f[0]), P(f[1]), P(f[2]), n, P(out), 0) == 0
+assert L.rbi_diag_hg97(P(T), P(f[0]), P(f[1]), P(f[2]), n, P(out), 0, 0) == 0
 ref = np.array(list(orc.get_kchem(T, *f)) + list(orc.get_kcool(T, *f)))
 names = "reH2 reHe2 reHe3 ciH1 ciHe1 ciHe2 recH2 recHe2 recHe3 cicH1 cicHe1 cicHe2 cecH1 cecHe2 bremss compton".split()
 with np.errstate(all="ignore"):

@@ -11,8 +11,8 @@ probs = configs.c5_sweep(find_Teq=True)[:: 8192 // nprob]
 res = {}
 modes = [int(c) for c in os.environ.get("RB_AB_MODES", "1010")]
 for libm in modes:
-    assert L.rb_diag_use_libm_pow(C.c_int(libm)) == 0
     plan = Plan(0, len(probs), 512, 128, 32, find_Teq=True, tol=1e-4)
+    plan.set_libm_pow(libm)
     for b, c in enumerate(probs):
         plan.set_problem(b, c["Edges"], c["nH"], c["nHe"], c["T"], c["E_eV"], c["shape"], c["z"])
     plan.upload()

@@ -32,7 +32,7 @@ def run_oracle(orc, cfg, tol=1e-4, max_sweeps=0, order=None, thin=False, flavour
                                 i_2side=1 if g == "slab_plane_2" else 0, **kw)
 
 
-def run_gpu(cfg, tol=1e-4, max_sweeps=0, thin=False):
+def run_gpu(cfg, tol=1e-4, max_sweeps=0, thin=False, libm_pow=False):
     """Through the plan API of the C ABI (same code path as the one-shot entry
     points, plus max_sweeps for sweep-level parity)."""
     Nl, Nnu = cfg["nH"].size, cfg["E_eV"].size
@@ -43,6 +43,8 @@ def run_gpu(cfg, tol=1e-4, max_sweeps=0, thin=False):
     plan.set_problem(0, cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], cfg["E_eV"],
                      cfg["shape"], cfg["z"], cfg.get("Hz", 0.0))
     plan.upload()
+    if libm_pow:
+        plan.set_libm_pow(True)
     if thin:
         plan.thin()
         plan.sync()

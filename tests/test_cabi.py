@@ -27,6 +27,19 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.EXPORTS) == names        # the Python loader's list is the header's list
 
 
+def test_internal_symbols_are_not_in_the_public_header():
+    """Measurement / diagnostic entry points live in csrc/rb_internal.h (rbi_*), exported by
+    the library but not declared by the drop-in boundary."""
+    L = _lib.lib()
+    txt = open(os.path.join(ROOT, "rabacus_b200", "csrc", "rb_internal.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = sorted(set(re.findall(r"\b(rbi_[A-Za-z0-9_]+)\s*\(", txt)))
+    assert names == sorted(_lib.INTERNAL)
+    assert not [n for n in names if not hasattr(L, n)]
+    pub = open(os.path.join(ROOT, "include", "rabacus_b200.h")).read()
+    assert "rbi_" not in pub and "rb_diag" not in pub and "rb_microbench" not in pub
+
+
 def test_every_entry_cites_the_reference_interface():
     txt = open(os.path.join(ROOT, "include", "rabacus_b200.h")).read()
     for ref in ("sphere_bgnd.py:216-244", "sphere_stromgren.py:215-241", "slab_bgnd.py:198-220",
@@ -96,6 +109,6 @@ def test_host_helpers_match_oracle(orc):
 
 def test_struct_layouts_match_header():
     # rb_info: 2 ints, 8 doubles, 1 long long ; rb_plan_desc: 6 ints, 2 doubles, 3 ints
-    # (+ padding), 3 doubles
+    # (+ padding), 3 doubles, 1 int (+ padding)
     assert C.sizeof(_lib.rb_info) == 8 + 8 * 8 + 8
-    assert C.sizeof(_lib.rb_plan_desc) == 24 + 16 + 16 + 24
+    assert C.sizeof(_lib.rb_plan_desc) == 24 + 16 + 16 + 24 + 8

@@ -579,6 +579,55 @@ def test_graph_replay_equals_direct_launches(orc, spec128, monkeypatch):
         assert np.array_equal(a, b_)
 
 
+def _one_shot_iso(cfg, em):
+    from rabacus_b200 import rabacus_fc as fc
+    T = cfg["T"].copy()
+    Nl, Nnu = cfg["nH"].size, cfg["E_eV"].size
+    o = fc.sphere_bgnd.sphere_bgnd_solve(
+        cfg["Edges"].copy(), cfg["nH"].copy(), cfg["nHe"].copy(), T, cfg["Nmu"], cfg["E_eV"],
+        cfg["shape"], 4, 1.0, 1, 1, 0, 0, em[0], em[1], em[2], cfg["z"], 0.0, 1e-4, Nl, Nnu)
+    return dict(zip(("xH1", "xH2", "xHe1", "xHe2", "xHe3", "H1i_src", "He1i_src", "He2i_src",
+                     "H1i_rec", "He1i_rec", "He2i_rec", "H1h_src", "He1h_src", "He2h_src",
+                     "H1h_rec", "He1h_rec", "He2h_rec"), o)), dict(fc.last_info)["iters"]
+
+
+def test_one_shot_isotropic_rescans_em_fac_on_a_cached_plan(orc, spec128):
+    """Scanning em_*_fac on a fixed grid through the one-shot ABI re-arms one cached plan:
+    the captured sweep graphs bake the emission factors in (kernel arguments by value) and
+    must be re-captured, or sweeps >= 2 run with the previous call's factors.  Every call
+    must equal a fresh plan's result bit for bit, and the oracle's within tolerance."""
+    from rabacus_b200 import _lib
+    cfg = _small_sphere(64, 128, 8, False, nH0=1.0, spec=spec128)
+    cfg["i_rec_meth"] = 4
+    _lib.lib().rb_cache_clear()
+    for em in ((1.0, 1.0, 1.0), (0.3, 2.0, 0.5), (1.0, 1.0, 1.0), (0.0, 0.0, 0.0)):
+        got, iters = _one_shot_iso(cfg, em)          # cached plan from the 2nd call on
+        cfg["em_fac"] = em
+        fresh = run_gpu(cfg)                          # a new plan every time
+        assert iters == fresh["iters"], em
+        for n in CHECKED_REC:
+            if n != "T":
+                assert np.array_equal(got[n], fresh[n]), (em, n)
+        o = run_oracle(orc, cfg)
+        assert iters == o["iters"], em
+        worst, bad = compare(fresh, o, names=CHECKED_REC)
+        assert not bad, (em, bad)
+
+
+def test_explicit_zero_emission_factors_switch_the_emission_off(orc, spec128):
+    """sphere_base.f90:955 multiplies the emissivities by em_*_fac: zeros mean no
+    recombination emission (all *_rec rates exactly zero, case-A rates), not "unset"."""
+    cfg = _small_sphere(48, 128, 8, False, nH0=1.0, spec=spec128)
+    cfg["i_rec_meth"] = 4
+    got, _ = _one_shot_iso(cfg, (0.0, 0.0, 0.0))
+    for n in ("H1i_rec", "He1i_rec", "He2i_rec", "H1h_rec", "He1h_rec", "He2h_rec"):
+        assert np.all(got[n] == 0.0), n
+    fixedA = dict(cfg, i_rec_meth=1, fixed_fcA=1.0)
+    ref = run_gpu(fixedA)
+    for n in ("xH1", "xHe1", "xHe2", "H1i_src", "He1i_src", "He2i_src"):
+        assert np.array_equal(got[n], ref[n]), n
+
+
 @pytest.mark.parametrize("Nl,Nnu,Nmu", [(1, 16, 4), (2, 16, 1), (3, 1, 2), (33, 2, 3),
                                         (7500, 16, 4), (8192, 8, 2)])
 def test_sphere_bgnd_edge_sizes(orc, Nl, Nnu, Nmu):
@@ -658,19 +707,13 @@ def test_hg97_device_coefficients_match_oracle(orc):
 
 def test_solve_with_table_driven_powers_equals_libm_form(spec128):
     """A/B over whole find_Teq solves: the Hui & Gnedin fits through rb_fastpow.cuh vs through
-    libdevice's pow(): same sweep count, temperatures bit-identical, rates <= 1e-12,
-    fractions within the fraction policy."""
-    import ctypes as C
-    from rabacus_b200 import _lib
+    libdevice's pow() (a per-plan switch, csrc/rb_internal.h): same sweep count, temperatures
+    bit-identical, rates <= 1e-12, fractions within the fraction policy."""
     cfgs = [_small_sphere(96, 128, 8, True, nH0=1.0, spec=spec128),
             configs.c2_slab_plane(128, 128, True), configs.c3_slab_bgnd(128, 128, True)]
     for cfg in cfgs:
         fast = run_gpu(cfg)
-        assert _lib.lib().rb_diag_use_libm_pow(C.c_int(1)) == 0
-        try:
-            slow = run_gpu(cfg)
-        finally:
-            assert _lib.lib().rb_diag_use_libm_pow(C.c_int(0)) == 0
+        slow = run_gpu(cfg, libm_pow=True)
         assert fast["iters"] == slow["iters"]
         assert np.array_equal(fast["T"], slow["T"])
         worst, bad = compare(fast, slow)

@@ -85,18 +85,18 @@ def _diag_pow(x, y, on_device=0):
     from rabacus_b200 import _lib
     out = np.empty_like(x)
     P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
-    rc = _lib.lib().rb_diag_pow(P(x), P(y), C.c_int(x.size), P(out), C.c_int(on_device))
+    rc = _lib.lib().rbi_diag_pow(P(x), P(y), C.c_int(x.size), P(out), C.c_int(on_device))
     assert rc == 0
     return out
 
 
-def _diag_hg97(T, f1, f2, f3, on_device=0):
+def _diag_hg97(T, f1, f2, f3, on_device=0, libm=0):
     import ctypes as C
     from rabacus_b200 import _lib
     out = np.empty((16, T.size))
     P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
-    rc = _lib.lib().rb_diag_hg97(P(T), P(f1), P(f2), P(f3), C.c_int(T.size), P(out),
-                                 C.c_int(on_device))
+    rc = _lib.lib().rbi_diag_hg97(P(T), P(f1), P(f2), P(f3), C.c_int(T.size), P(out),
+                                  C.c_int(on_device), C.c_int(libm))
     assert rc == 0
     return out
 
@@ -158,20 +158,14 @@ def test_hg97_fast_evaluation_matches_the_libm_statement_form(orc):
 
 
 def test_hg97_libm_statement_form_is_bit_identical_to_the_oracle(orc):
-    """rb_diag_use_libm_pow(1) selects the statement-by-statement libm form of the fits; built
-    by the host compiler it calls the same glibc pow/exp/log10 as the oracle's C and must
-    agree with it bit for bit -- the two codings of chem_cool_rates.f90:45-204 pin each other."""
-    import ctypes as C
-    from rabacus_b200 import _lib
+    """libm=1 selects the statement-by-statement libm form of the fits; built by the host
+    compiler it calls the same glibc pow/exp/log10 as the oracle's C and must agree with
+    it bit for bit -- the two codings of chem_cool_rates.f90:45-204 pin each other."""
     rng = np.random.default_rng(3)
     n = 5000
     T = 10 ** rng.uniform(2.0, 9.0, n)
     f = [rng.choice([0.0, 1.0, 0.5], n) for _ in range(3)]
-    assert _lib.lib().rb_diag_use_libm_pow(C.c_int(1)) == 0
-    try:
-        out = _diag_hg97(T, *f)
-    finally:
-        assert _lib.lib().rb_diag_use_libm_pow(C.c_int(0)) == 0
+    out = _diag_hg97(T, *f, libm=1)
     ref = np.array(list(orc.get_kchem(T, *f)) + list(orc.get_kcool(T, *f)))
     assert np.array_equal(out, ref)
 
