@@ -225,6 +225,13 @@ int rb_plan_set_problem(rb_plan *plan, int b, const double *Edges,
                         const double *nH, const double *nHe, const double *T,
                         const double *E_eV, const double *shape, double z,
                         double Hz);
+/* the same for n problems b0 .. b0+n-1 in one call (parameter sweeps): row-major
+ * Edges[n][Nl+1], nH/nHe/T[n][Nl]; problem i uses spectrum spec_index[i] of the nspec
+ * rows E_eV/shape[nspec][Nnu]; z[n], Hz[n] (NULL: zeros) */
+int rb_plan_set_batch(rb_plan *plan, int b0, int n, const double *Edges,
+                      const double *nH, const double *nHe, const double *T, int nspec,
+                      const double *E_eV, const double *shape, const int *spec_index,
+                      const double *z, const double *Hz);
 /* H2D copy of everything staged; resets iteration state */
 int rb_plan_upload(rb_plan *plan);
 /* optically-thin initial state (sphere_bgnd.f90:379-499 and twins) */
@@ -281,6 +288,11 @@ int rb_plan_get_problem(rb_plan *plan, int b, double *T, double *xH1,
 int rb_plan_get_rec(rb_plan *plan, int b, double *H1i_rec, double *He1i_rec,
                     double *He2i_rec, double *H1h_rec, double *He1h_rec,
                     double *He2h_rec);
+/* D2H of ALL problems' results in one pass (parameter sweeps): out12 is
+ * [12][n_problems][Nl] = xH1,xH2,xHe1,xHe2,xHe3,T,H1i,He1i,He2i,H1h,He1h,He2h (source
+ * rates), rec6 (may be NULL) [6][n_problems][Nl] the recombination-photon rates, iters
+ * (may be NULL) [n_problems] the sweep counts; every problem in its input orientation. */
+int rb_plan_get_all(rb_plan *plan, double *out12, double *rec6, int *iters);
 /* device pointers for torch / NCCL interop: fields are [n_problems*Nl] float64.
  * 0..4 = xH1,xH2,xHe1,xHe2,xHe3 ; 5 = T ; 6..11 = H1i,He1i,He2i,H1h,He1h,He2h src */
 void *rb_plan_field_ptr(rb_plan *plan, int field);

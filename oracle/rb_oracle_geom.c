@@ -21,6 +21,27 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* bench.py sets the team size explicitly (torchrun exports OMP_NUM_THREADS=1) */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n >= 1) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
+/* wall time of the sweep loop of the last orc_sphere_bgnd_solve (thin start excluded):
+ * what bench.py's CPU legs report.  Not thread safe (test infrastructure). */
+static double g_sweep_seconds = 0.0;
+double orc_last_sweep_seconds(void) { return g_sweep_seconds; }
+static double wall_now(void) {
+#ifdef _OPENMP
+  return omp_get_wtime();
+#else
+  return 0.0;
+#endif
+}
+
 enum { SRC_BGND = 0, SRC_POINT = 1, SRC_PLANE = 2 };
 
 /* counters: 0 segment visits, 1 sqrt calls, 2 exp/e2xa calls, 3 cell solves */
@@ -605,9 +626,12 @@ int orc_sphere_bgnd_solve(
       conv_old[i] = xH2[i] * nH[i] + (xHe2[i] + 2.0 * xHe3[i]) * nHe[i];
     int iter = 0;
     int not_converged = 1;
+    const double t_sweeps0 = wall_now();
+    g_sweep_seconds = 0.0;
     while (not_converged) {
       rc = sphere_bgnd_sweep(&s, Edges, nH, nHe, T, Nmu, fcA, i_find_Teq, z, Hz,
                              tol, Nl, order, flavour, i_rec_meth, em_fac, &o, &cnt);
+      g_sweep_seconds = wall_now() - t_sweeps0;
       if (rc) break;
       if (iter > OUTER_MAX_ITER) { /* :284-287 */
         rc = ORC_ERR_MAX_ITER_OUTER;

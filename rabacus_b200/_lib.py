@@ -49,10 +49,10 @@ EXPORTS = (
     "rb_slab_plane_solve", "rb_set_column_vs_impact",
     "rb_get_kchem", "rb_get_kcool", "rb_solve_ce", "rb_solve_pce", "rb_solve_pcte",
     "rb_photo_sigma", "rb_photo_Eth", "rb_gauss_legendre",
-    "rb_plan_create", "rb_plan_destroy", "rb_plan_set_problem", "rb_plan_upload",
+    "rb_plan_create", "rb_plan_destroy", "rb_plan_set_problem", "rb_plan_set_batch", "rb_plan_upload",
     "rb_plan_thin", "rb_plan_sweep_local", "rb_plan_finish_sweep", "rb_plan_finish_sweep_async",
     "rb_plan_poll_sweep", "rb_plan_solve",
-    "rb_plan_get_problem", "rb_plan_get_rec", "rb_plan_field_ptr", "rb_plan_stream", "rb_plan_sync",
+    "rb_plan_get_problem", "rb_plan_get_rec", "rb_plan_get_all", "rb_plan_field_ptr", "rb_plan_stream", "rb_plan_sync",
     "rb_plan_evals_per_sweep", "rb_plan_last_info", "rb_plan_pack_cells",
     "rb_plan_unpack_cells",
     "rb_plan_peer_alloc", "rb_plan_peer_connect", "rb_plan_sweep_sharded", "rb_plan_solve_sharded",
@@ -61,7 +61,7 @@ EXPORTS = (
 # measurement / diagnostic symbols declared in rabacus_b200/csrc/rb_internal.h (not part of
 # the drop-in boundary)
 INTERNAL = ("rbi_diag_pow", "rbi_diag_hg97", "rbi_plan_set_libm_pow", "rbi_plan_bench_steps",
-            "rbi_microbench")
+            "rbi_microbench", "rbi_last_zone_kernel_ms")
 
 _lib = None
 
@@ -87,6 +87,7 @@ def lib():
         L.rb_plan_evals_per_sweep.restype = C.c_longlong
         L.rb_plan_evals_per_sweep.argtypes = [C.c_void_p]
         L.rb_plan_destroy.restype = None
+        L.rbi_last_zone_kernel_ms.restype = C.c_double
         L.rb_cache_clear.restype = None
         L.rb_plan_destroy.argtypes = [C.c_void_p]
         _lib = L

@@ -80,5 +80,49 @@ def c5_sweep(n_nH=32, n_R=16, n_z=16, Nl=512, Nnu=128, Nmu=32, find_Teq=False):
     return probs
 
 
+def c5_params(index, n_nH=32, n_R=16, n_z=16):
+    """(nH0, R_kpc, z, iz) of problems ``index`` of :func:`c5_sweep` (same ordering:
+    nH0 slowest, z fastest)."""
+    index = np.asarray(index)
+    nH0s = np.logspace(-1.0, 1.5, n_nH)
+    Rs = np.linspace(5.0, 50.0, n_R)
+    zs = np.linspace(0.0, 6.0, n_z)
+    iz = index % n_z
+    iR = (index // n_z) % n_R
+    iH = index // (n_z * n_R)
+    return nH0s[iH], Rs[iR], zs[iz], iz
+
+
+def c5_batch_arrays(index, Nl=512, Nnu=128, n_nH=32, n_R=16, n_z=16):
+    """The inputs of problems ``index`` of the C5 sweep as batch arrays, without per-problem
+    Python work: the 16 spectra and the 16 density profiles (one per radius) are built once
+    and the batch is assembled by broadcasting -- bit-identical to :func:`c4_sphere_bgnd`
+    per problem.  Returns dict(Edges [n, Nl+1], nH, nHe, T [n, Nl], E, shape [n_z, Nnu],
+    spec_index [n], z [n])."""
+    nH0, R_kpc, z, iz = c5_params(index, n_nH, n_R, n_z)
+    zs = np.linspace(0.0, 6.0, n_z)
+    spectra = [hm12_background(Nnu, float(zz)) for zz in zs]
+    Rs = np.linspace(5.0, 50.0, n_R)
+    iR = (np.asarray(index) // n_z) % n_R
+    edges_R = np.array([np.linspace(0.0, float(R) * KPC_CM, Nl + 1) for R in Rs])
+    r = 0.5 * (edges_R[:, 1:] + edges_R[:, :-1])
+    r0 = np.array([float(R) * KPC_CM / 100.0 for R in Rs])[:, None]
+    unit = np.where(r < r0, 1.0, (r / r0) ** -2.0)          # per radius
+    nH = nH0[:, None] * unit[iR]
+    return dict(Edges=edges_R[iR], nH=nH, nHe=nH * 0.25 * YP / (1.0 - YP),
+                T=np.full_like(nH, 1.0e4), E=np.array([s[0] for s in spectra]),
+                shape=np.array([s[1] for s in spectra]), spec_index=iz.astype(np.int32), z=z)
+
+
+def c5_stage(plan, index, n_nH=32, n_R=16, n_z=16, find_Teq=False):
+    """Stage problems ``index`` of the C5 sweep into ``plan`` (slots 0 .. len(index)-1) with
+    one ``rb_plan_set_batch`` call.  Returns a one-line description of the path taken."""
+    a = c5_batch_arrays(index, plan.Nl, plan.Nnu, n_nH, n_R, n_z)
+    plan.set_batch(0, a["Edges"], a["nH"], a["nHe"], a["T"], a["E"], a["shape"],
+                   a["spec_index"], a["z"])
+    return ("host: %d spectra + %d profiles built once (numpy), batch assembled by "
+            "broadcasting, one rb_plan_set_batch call" % (n_z, n_R))
+
+
 GEOM_IDS = {"sphere_bgnd": 0, "sphere_stromgren": 1, "slab_plane_1": 2, "slab_plane_2": 3,
             "slab_bgnd": 4}

@@ -138,6 +138,21 @@ extern "C" int rb_gauss_legendre(int n, double *x, double *w) {
   return RB_OK;
 }
 
+struct DevBuf {
+  double *d = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    n = count;
+    if (cudaMalloc((void **)&d, std::max<size_t>(1, count) * 8) != cudaSuccess) {
+      cudaGetLastError();
+      d = nullptr;
+      return RB_ERR_NOMEM;
+    }
+    return RB_OK;
+  }
+  ~DevBuf() { if (d) cudaFree(d); }
+};
+
 static int source_kind(int geom) {  // 0 background, 1 point, 2 plane
   switch (geom) {
     case RB_GEOM_SPHERE_BGND: case RB_GEOM_SLAB_BGND: return 0;
@@ -252,6 +267,7 @@ struct rb_plan {
     double thin[kThinStride];
   };
   std::vector<SpecEntry> spec_cache;
+  unsigned char *dreversed = nullptr;  // [B] input orientation was flipped (rb_plan_get_all)
   int *dflags = nullptr;    // active, notconv, iters, err : 4*B, then nactive
   unsigned long long *dresid = nullptr;
   // pinned host staging
@@ -298,7 +314,7 @@ extern "C" void rb_plan_destroy(rb_plan *p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   destroy_graphs(p);
   cudaFree(p->drec); cudaFree(p->drecbuf); cudaFree(p->drecI); cudaFree(p->diso_items);
-  cudaFree(p->dpart);
+  cudaFree(p->dpart); cudaFree(p->dreversed);
   if (p->dpeer) {
     for (int r = 0; r < kMaxPeers; ++r)
       if (p->peer_base[r] && p->peer_base[r] != p->dpeer) cudaIpcCloseMemHandle(p->peer_base[r]);
@@ -396,9 +412,10 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
     ALLOC(p->ditems, (size_t)((Nl + 31) / 32) * ((d.Nmu + 1) / 2) * 8 * sizeof(unsigned));
   cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev);
   ALLOC(p->dflags, (3 * B + kSlots) * sizeof(int)); ALLOC(p->dresid, B * 8);
+  ALLOC(p->dreversed, B);
   HALLOC(p->hEdges, B * (Nl + 1) * 8); HALLOC(p->hnH, NC * 8); HALLOC(p->hnHe, NC * 8);
   HALLOC(p->hT, NC * 8); HALLOC(p->hspec, B * Nnu * kSpecStride * 8);
-  HALLOC(p->hthin, B * kThinStride * 8); HALLOC(p->hzHz, B * 2 * 8); HALLOC(p->hout, 12 * NC * 8);
+  HALLOC(p->hthin, B * kThinStride * 8); HALLOC(p->hzHz, B * 2 * 8); HALLOC(p->hout, 12 * Nl * 8);
   HALLOC(p->hflags, (3 * B + kSlots) * sizeof(int));
 #undef ALLOC
 #undef HALLOC
@@ -531,6 +548,28 @@ extern "C" int rb_plan_set_problem(rb_plan *p, int b, const double *Edges, const
   return RB_OK;
 }
 
+// Stage n problems b0 .. b0+n-1 in one call (parameter sweeps: thousands of problems that
+// share a handful of spectra).  Row-major inputs; spec_index[i] selects problem i's
+// spectrum among the nspec rows of E_eV / shape.
+extern "C" int rb_plan_set_batch(rb_plan *p, int b0, int n, const double *Edges,
+                                 const double *nH, const double *nHe, const double *T,
+                                 int nspec, const double *E_eV, const double *shape,
+                                 const int *spec_index, const double *z, const double *Hz) {
+  if (!p || b0 < 0 || n < 0 || b0 + n > p->d.n_problems || nspec < 1 || !Edges || !nH || !nHe ||
+      !T || !E_eV || !shape || !spec_index || !z)
+    return RB_ERR_BAD_ARG;
+  const size_t Nl = p->d.Nl, Nnu = p->d.Nnu;
+  for (int i = 0; i < n; ++i) {
+    const int q = spec_index[i];
+    if (q < 0 || q >= nspec) return RB_ERR_BAD_ARG;
+    const int rc = rb_plan_set_problem(p, b0 + i, Edges + (size_t)i * (Nl + 1), nH + i * Nl,
+                                       nHe + i * Nl, T + i * Nl, E_eV + (size_t)q * Nnu,
+                                       shape + (size_t)q * Nnu, z[i], Hz ? Hz[i] : 0.0);
+    if (rc) return rc;
+  }
+  return RB_OK;
+}
+
 extern "C" int rb_plan_upload(rb_plan *p) {
   if (!p) return RB_ERR_BAD_ARG;
   PLAN_DEV(p);
@@ -543,6 +582,8 @@ extern "C" int rb_plan_upload(rb_plan *p) {
   CK(cudaMemcpyAsync(p->dspec, p->hspec, B * Nnu * kSpecStride * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(p->dthin, p->hthin, B * kThinStride * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(p->dzHz, p->hzHz, B * 2 * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->dreversed, p->reversed.data(), B, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));  // `reversed` is pageable
   for (size_t b = 0; b < B; ++b) {
     p->hflags[b] = 1; p->hflags[B + b] = 0; p->hflags[2 * B + b] = 0;
   }
@@ -1454,7 +1495,7 @@ extern "C" int rb_plan_get_rec(rb_plan *p, int b, double *H1i, double *He1i, dou
   if (!p || b < 0 || b >= p->d.n_problems) return RB_ERR_BAD_ARG;
   PLAN_DEV(p);
   const size_t B = p->d.n_problems, Nl = p->d.Nl, NC = B * Nl;
-  double *h = p->hout;  // 12*NC doubles of pinned staging; 6*Nl used
+  double *h = p->hout;  // 12*Nl doubles of pinned staging; 6*Nl used
   if (B == 1) {
     CK(cudaMemcpyAsync(h, p->drec, 6 * Nl * 8, cudaMemcpyDeviceToHost, p->stream));
   } else {
@@ -1469,6 +1510,27 @@ extern "C" int rb_plan_get_rec(rb_plan *p, int b, double *H1i, double *He1i, dou
     if (!outs[f]) continue;
     for (size_t i = 0; i < Nl; ++i) outs[f][i] = h[f * Nl + (rev ? Nl - 1 - i : i)];
   }
+  return RB_OK;
+}
+
+extern "C" int rb_plan_get_all(rb_plan *p, double *out12, double *rec6, int *iters) {
+  if (!p || !out12) return RB_ERR_BAD_ARG;
+  PLAN_DEV(p);
+  const size_t B = p->d.n_problems, Nl = p->d.Nl, NC = B * Nl;
+  const int nf = rec6 ? 18 : 12;
+  DevBuf tmp;
+  int rc = tmp.alloc((size_t)nf * NC);
+  if (rc) return rc;
+  dim3 g((unsigned)((Nl + 255) / 256), (unsigned)B, (unsigned)nf);
+  k_gather_outputs<<<g, 256, 0, p->stream>>>(p->P, p->dreversed, nf, tmp.d);
+  p->info.n_launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out12, tmp.d, 12 * NC * 8, cudaMemcpyDeviceToHost, p->stream));
+  if (rec6)
+    CK(cudaMemcpyAsync(rec6, tmp.d + 12 * NC, 6 * NC * 8, cudaMemcpyDeviceToHost, p->stream));
+  if (iters)
+    CK(cudaMemcpyAsync(iters, p->dflags + B, B * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
   return RB_OK;
 }
 
@@ -1683,20 +1745,25 @@ extern "C" int rb_slab_plane_solve(
 // ---------------------------------------------------------------------------
 // small device-buffer helper for the remaining entry points
 // ---------------------------------------------------------------------------
-struct DevBuf {
-  double *d = nullptr;
-  size_t n = 0;
-  int alloc(size_t count) {
-    n = count;
-    if (cudaMalloc((void **)&d, std::max<size_t>(1, count) * 8) != cudaSuccess) {
-      cudaGetLastError();
-      d = nullptr;
-      return RB_ERR_NOMEM;
-    }
-    return RB_OK;
+
+// device time of the last single-zone batch kernel of this thread (rbi_last_zone_kernel_ms)
+static thread_local double g_zone_kernel_ms = 0.0;
+struct ZoneTimer {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ZoneTimer() {
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
   }
-  ~DevBuf() { if (d) cudaFree(d); }
+  void stop() {
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) g_zone_kernel_ms = ms;
+    cudaGetLastError();
+  }
+  ~ZoneTimer() { cudaEventDestroy(e0); cudaEventDestroy(e1); }
 };
+extern "C" double rbi_last_zone_kernel_ms(void) { return g_zone_kernel_ms; }
 
 static int need_device() {
   if (rb_device_count() < 1) {
@@ -1942,7 +2009,9 @@ extern "C" int rb_solve_pce(const double *nH, const double *nHe, const double *r
     });
     if (rc) return rc;
   } else {
+    ZoneTimer zt;
     k_zone_pce<<<(nn + 127) / 128, 128>>>(in.d, nn, tol, out.d, derr, 0);
+    zt.stop();
   }
   CK(cudaGetLastError());
   double *o[5] = {xH1, xH2, xHe1, xHe2, xHe3};
@@ -1982,7 +2051,9 @@ extern "C" int rb_solve_pcte(const double *nH, const double *nHe, const double *
     });
     if (rc) return rc;
   } else {
+    ZoneTimer zt;
     k_zone_pcte<<<(nn + 127) / 128, 128>>>(in.d, nn, z, Hz, tol, out.d, derr);
+    zt.stop();
   }
   CK(cudaGetLastError());
   double *o[6] = {xH1, xH2, xHe1, xHe2, xHe3, T};

@@ -37,6 +37,10 @@ int rbi_plan_set_libm_pow(rb_plan *plan, int on);
 int rbi_plan_bench_steps(rb_plan *plan, int steps, size_t flush_bytes, int graphs,
                          double *ms_sum);
 
+/* device time [ms] of the kernel of this thread's last rb_solve_pce / rb_solve_pcte call
+ * (scalar mode), for the single-zone batch line of bench.py */
+double rbi_last_zone_kernel_ms(void);
+
 /* FP64 pipe micro-benchmarks used as roofline denominators (bench.py):
  * kind 0 = DFMA (64 FMAs per loop trip on 32 independent chains, >= 50 ms per repetition),
  * 1 = exp, 2 = sqrt, 3 = pow (CUDA library functions).  Returns operations / second. */

@@ -1259,6 +1259,19 @@ __global__ void k_unpack_cells(PlanDev P, int world, int n_local, const double *
   if (two_sided(P.geom)) dst[P.Nl - 1 - il] = v;  // mirrored half
 }
 
+// k_gather_outputs: all problems' results in INPUT orientation, field-major
+// out[f][b][i], f = xH1, xH2, xHe1, xHe2, xHe3, T, 6 source rates (, 6 recombination rates):
+// one device pass + one copy instead of 18 small copies per problem (rb_plan_get_all)
+__global__ void k_gather_outputs(PlanDev P, const unsigned char *__restrict__ reversed,
+                                 int nfields, double *__restrict__ out) {
+  const int b = blockIdx.y, f = blockIdx.z;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.Nl || f >= nfields) return;
+  const double *src = plan_field(P, f) + (size_t)b * P.Nl;
+  const int k = reversed[b] ? P.Nl - 1 - i : i;
+  out[((size_t)f * P.B + b) * P.Nl + i] = src[k];
+}
+
 // ---------------------------------------------------------------------------
 // lock-step ("_v") solvers, one block per problem, CPT cells per thread.
 // ---------------------------------------------------------------------------

@@ -64,6 +64,22 @@ class Plan(object):
         check(lib().rb_plan_set_problem(self._h, C.c_int(b), *[_p(a) for a in arrs],
                                         C.c_double(float(z)), C.c_double(float(Hz))))
 
+    def set_batch(self, b0, Edges, nH, nHe, T, E_eV, shape, spec_index, z, Hz=None):
+        """Stage ``n`` problems ``b0 .. b0+n-1`` in one call: ``Edges [n, Nl+1]``,
+        ``nH / nHe / T [n, Nl]``, spectra ``E_eV / shape [nspec, Nnu]`` shared through
+        ``spec_index [n]``, ``z [n]``, ``Hz [n]``."""
+        A = [np.ascontiguousarray(a, dtype=np.float64) for a in (Edges, nH, nHe, T, E_eV, shape)]
+        n = A[1].shape[0]
+        if A[0].shape != (n, self.Nl + 1) or A[1].shape != (n, self.Nl) or \
+                A[4].ndim != 2 or A[4].shape[1] != self.Nnu or A[5].shape != A[4].shape:
+            raise ValueError("array shapes do not match the plan")
+        si = np.ascontiguousarray(spec_index, dtype=np.int32)
+        zz = np.ascontiguousarray(z, dtype=np.float64)
+        hz = np.zeros(n) if Hz is None else np.ascontiguousarray(Hz, dtype=np.float64)
+        check(lib().rb_plan_set_batch(self._h, C.c_int(int(b0)), C.c_int(n), *[_p(a) for a in A[:4]],
+                                      C.c_int(A[4].shape[0]), _p(A[4]), _p(A[5]),
+                                      si.ctypes.data_as(C.POINTER(C.c_int)), _p(zz), _p(hz)))
+
     def upload(self):
         check(lib().rb_plan_upload(self._h))
 
@@ -133,6 +149,21 @@ class Plan(object):
         check(lib().rb_plan_get_rec(self._h, C.c_int(b), *[_p(rec[k]) for k in REC_FIELDS]))
         outs.update(rec)
         return outs
+
+    def get_all(self, with_rec=False):
+        """All problems' results in one device pass + copy: dict of [n_problems, Nl]
+        arrays (input orientation) and ``iters`` [n_problems]."""
+        B, Nl = self.n_problems, self.Nl
+        out = np.empty((12, B, Nl))
+        rec = np.empty((6, B, Nl)) if with_rec else None
+        iters = np.zeros(B, dtype=np.int32)
+        check(lib().rb_plan_get_all(self._h, _p(out), _p(rec) if with_rec else None,
+                                    iters.ctypes.data_as(C.POINTER(C.c_int))))
+        res = {k: out[i] for i, k in enumerate(FIELDS)}
+        if with_rec:
+            res.update({k: rec[i] for i, k in enumerate(REC_FIELDS)})
+        res["iters"] = iters
+        return res
 
     # ------------------------------------------------------------------ torch interop
     def field_tensor(self, field):
