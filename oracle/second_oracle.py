@@ -1,0 +1,314 @@
+"""Independent second derivation of the hot path -- TEST INFRASTRUCTURE ONLY.
+
+Written from the reference's Fortran (file:line cited per function), NOT from
+oracle/rb_oracle_*.c, in numpy with a selectable working precision ``F``
+(``np.float64``: same IEEE operations in the reference's own statement order, so the
+bisection paths can be compared step by step; ``np.longdouble``: 64-bit mantissa, the
+"truth" the float64 codings are measured against).  It keeps the reference's loop
+structure (per-segment ds_segment calls, six separate frequency integrals), so it is slow
+and only used at small sizes by tests/test_second_oracle.py to pin the C oracle:
+one Jacobi sweep of SphereBgnd, one sweep of Slab2Bgnd, solve_pce_s, solve_pcte_s.
+"""
+import numpy as np
+
+# rabacus/f2py/physical_constants.f90:7-21
+PI, KB, H_ERG, EV2ERG, ERG2EV = (3.141592653589793, 1.3806488e-16, 6.62606957e-27,
+                                 1.60217653e-12, 6.241509479607719e11)
+T_H1, T_He1, T_He2 = 1.57807e5, 2.85335e5, 6.31515e5      # hui_gnedin_97.f90:6-8
+TFLOOR, TMAX, MAX_ITER = 7.5e3, 1.0e5, 5000                # ion_solver.f90:13-15
+# rabacus/atomic/verner/photox/photo.dat:1-3  (Eth E0 sigma0 ya P yw y0 y1)
+V96 = ((13.60, 0.4298, 5.475e4, 32.88, 2.963, 0.0, 0.0, 0.0),
+       (24.59, 13.61, 949.2, 1.469, 3.188, 2.039, 0.4434, 2.136),
+       (54.42, 1.720, 1.369e4, 32.88, 2.963, 0.0, 0.0, 0.0))
+
+
+def sigma_v96(X, E, F):
+    """verner_96.f90:133-151"""
+    Eth, E0, s0, ya, P, yw, y0, y1 = (F(v) for v in V96[X])
+    E = np.asarray(E, dtype=F)
+    x = E / E0 - y0
+    y = np.sqrt(x * x + y1 * y1)
+    t1 = (x - F(1)) * (x - F(1)) + yw * yw
+    t2 = y ** (F(0.5) * P - F(5.5))
+    t3 = (F(1) + np.sqrt(y / ya)) ** (-P)
+    return np.where(E < Eth, F(0), (s0 * F(1.0e-18)) * (t1 * t2 * t3))
+
+
+def _ferland(lam, t1, t2, t3, t4, t5, F):      # hui_gnedin_97.f90:21-45 and twins
+    return F(t1) * lam ** F(t2) / (F(1) + (lam / F(t3)) ** F(t4)) ** F(t5)
+
+
+def _lotz(T, lam, t1, t2, t3, t4, t5, F):      # hui_gnedin_97.f90:106-150
+    return (F(t1) * T ** F(-1.5) * np.exp(-lam * F(0.5)) * lam ** F(t2)
+            / (F(1) + (lam / F(t3)) ** F(t4)) ** F(t5))
+
+
+def _mix(a, b, f, F):                          # chem_cool_rates.f90:67
+    return F(10) ** (np.log10(a) * f + np.log10(b) * (F(1) - f))
+
+
+def _di(T, F):                                 # hui_gnedin_97.f90:67-74
+    lam = F(2) * F(T_He2) / T
+    return (F(1.90e-3) * T ** F(-1.5) * np.exp(F(-0.75) * lam * F(0.5))
+            * (F(1) + F(0.3) * np.exp(F(-0.15) * lam * F(0.5))))
+
+
+def get_kchem(T, fc, F):
+    """chem_cool_rates.f90:45-88 -> (reH2, reHe2, reHe3, ciH1, ciHe1, ciHe2)"""
+    T, fc = F(T), [F(v) for v in fc]
+    l1, l2, l3 = F(2) * F(T_H1) / T, F(2) * F(T_He1) / T, F(2) * F(T_He2) / T
+    reH2 = _mix(_ferland(l1, 1.269e-13, 1.503, 0.522, 0.470, 1.923, F),
+                _ferland(l1, 2.753e-14, 1.500, 2.740, 0.407, 2.242, F), fc[0], F)
+    reHe2 = _mix(F(3.0e-14) * l2 ** F(0.654), F(1.26e-14) * l2 ** F(0.750), fc[1], F)
+    reHe2 = reHe2 + _di(T, F)
+    reHe3 = _mix(_ferland(l3, F(2) * F(1.269e-13), 1.503, 0.522, 0.470, 1.923, F),
+                 _ferland(l3, F(2) * F(2.753e-14), 1.500, 2.740, 0.407, 2.242, F), fc[2], F)
+    return (reH2, reHe2, reHe3, _lotz(T, l1, 21.11, -1.089, 0.354, 0.874, 1.101, F),
+            _lotz(T, l2, 32.38, -1.146, 0.416, 0.987, 1.056, F),
+            _lotz(T, l3, 19.95, -1.089, 0.553, 0.735, 1.275, F))
+
+
+def get_kcool(T, fc, F):
+    """chem_cool_rates.f90:147-204 with hui_gnedin_97.f90:162-322 ->
+    (recH2, recHe2, recHe3, cicH1, cicHe1, cicHe2, cecH1, cecHe2, bremss, compton)"""
+    T, fc = F(T), [F(v) for v in fc]
+    l1, l2, l3 = F(2) * F(T_H1) / T, F(2) * F(T_He1) / T, F(2) * F(T_He2) / T
+
+    def rec(lam, t1, t2, t3, t4, t5):
+        return t1 * T * lam ** F(t2) / (F(1) + (lam / F(t3)) ** F(t4)) ** F(t5)
+    recH2 = _mix(rec(l1, F(1.778e-29), 1.965, 0.541, 0.502, 2.697),
+                 rec(l1, F(3.435e-30), 1.970, 2.250, 0.376, 3.720), fc[0], F)
+    recHe2 = _mix(F(KB) * T * (F(3.0e-14) * l2 ** F(0.654)),
+                  F(KB) * T * (F(1.26e-14) * l2 ** F(0.750)), fc[1], F)
+    recHe2 = recHe2 + F(0.75) * F(KB) * F(T_He2) * _di(T, F)
+    recHe3 = _mix(rec(l3, F(8) * F(1.778e-29), 1.965, 0.541, 0.502, 2.697),
+                  rec(l3, F(8) * F(3.435e-30), 1.970, 2.250, 0.376, 3.720), fc[2], F)
+    cic = (F(KB) * F(T_H1) * _lotz(T, l1, 21.11, -1.089, 0.354, 0.874, 1.101, F),
+           F(KB) * F(T_He1) * _lotz(T, l2, 32.38, -1.146, 0.416, 0.987, 1.056, F),
+           F(KB) * F(T_He2) * _lotz(T, l3, 19.95, -1.089, 0.553, 0.735, 1.275, F))
+    den = F(1) + np.sqrt(T * F(1.0e-5))
+    cecH1 = F(7.5e-19) * np.exp(F(-0.75) * l1 * F(0.5)) / den
+    cecHe2 = F(5.54e-17) * (F(1) / T) ** F(0.397) * np.exp(F(-0.75) * l3 * F(0.5)) / den
+    gff = F(1.1) + F(0.34) * np.exp(-(F(5.5) - np.log10(T)) ** F(2.0) / F(3))
+    return (recH2, recHe2, recHe3) + cic + (cecH1, cecHe2,
+                                            F(1.43e-27) * np.sqrt(T) * gff, F(5.65e-36))
+
+
+def _fpc(x):                                   # ion_solver.f90:68-80
+    t = x[0] + x[1]
+    h = [x[0] / t, x[1] / t]
+    t = x[2] + x[3] + x[4]
+    return h + [x[2] / t, x[3] / t, x[4] / t]
+
+
+def _implicit(ne, k, H1i, He1i, He2i):         # ion_solver.f90:238-276
+    R2, CG1 = k[0] * ne, k[3] * ne + H1i
+    DH = R2 + CG1
+    x = [R2 / DH, CG1 / DH]
+    R2, R3 = k[1] * ne, k[2] * ne
+    CG1, CG2 = k[4] * ne + He1i, k[5] * ne + He2i
+    DHe = (R2 * R3) + (R3 * CG1) + (CG1 * CG2)
+    return _fpc(x + [R2 * R3 / DHe, R3 * CG1 / DHe, CG1 * CG2 / DHe])
+
+
+def solve_pce(nH, nHe, k, H1i, He1i, He2i, tol, F, path=None):
+    """ion_solver.f90:440-562; ``path`` collects the branch taken at :515-521."""
+    nH, nHe, k = F(nH), F(nHe), [F(v) for v in k]
+    H1i, He1i, He2i, tol = F(H1i), F(He1i), F(He2i), F(tol)
+    DD = k[0] + k[3]                                        # solve_ce_s :339-374
+    x = [k[0] / DD, k[3] / DD]
+    DD = k[1] * k[2] + k[2] * k[4] + k[4] * k[5]
+    x = _fpc(x + [k[1] * k[2] / DD, k[2] * k[4] / DD, k[4] * k[5] / DD])
+    ne_left = x[1] * nH + (x[3] + F(2) * x[4]) * nHe
+    ne_right = nH + F(2) * nHe
+    y = (x[3] + F(2) * x[4]) * nHe / nH
+    RR = (k[3] + k[0]) * nH                                 # analytic_H1_s :161-185
+    QQ = -(H1i + k[0] * nH + RR * (F(1) + y))
+    PP = k[0] * nH * (F(1) + y)
+    dd = QQ * QQ - F(4) * RR * PP
+    dd = dd if dd >= 0 else F(0)
+    x[0] = PP / (-F(0.5) * (QQ - np.sqrt(dd)))
+    x[1] = F(1) - x[0]
+    ne = x[1] * nH + (x[3] + F(2) * x[4]) * nHe
+    ne_old, o = ne, (x[0], x[2], x[4])
+    err, it = F(np.inf), 0
+    while err > tol:
+        x = _implicit(ne, k, H1i, He1i, He2i)
+        ne = x[1] * nH + (x[3] + F(2) * x[4]) * nHe
+        ratio_ne = ne / ne_old
+        err = abs(max(x[0] / o[0], x[2] / o[1], x[4] / o[2]) - F(1))
+        up = bool(ratio_ne > F(1))
+        if path is not None:
+            path.append(up)
+        if up:
+            ne, ne_left = (ne_old + ne_right) * F(0.5), ne_old
+        else:
+            ne, ne_right = (ne_left + ne_old) * F(0.5), ne_old
+        ne_old, o = ne, (x[0], x[2], x[4])
+        it += 1
+        assert it <= MAX_ITER
+    if nH <= 0:
+        x[0] = x[1] = F(0)
+    if nHe <= 0:
+        x[2] = x[3] = x[4] = F(0)
+    return x
+
+
+def _dudT(nH, nHe, T, p, z, Hz, fc, tol, F):
+    """get_dudT_s ion_solver.f90:1089-1134, get_heat/get_cool chem_cool_rates.f90:268-332"""
+    x = solve_pce(nH, nHe, get_kchem(T, fc, F), p[0], p[1], p[2], tol, F)
+    c = get_kcool(T, fc, F)
+    nH, nHe, z, Hz, T = F(nH), F(nHe), F(z), F(Hz), F(T)
+    heat = x[0] * nH * F(p[3]) + x[2] * nHe * F(p[4]) + x[3] * nHe * F(p[5])
+    ne = x[1] * nH + (x[3] + F(2) * x[4]) * nHe
+    cool = (c[0] * ne * x[1] * nH + c[1] * ne * x[3] * nHe + c[2] * ne * x[4] * nHe
+            + c[3] * ne * x[0] * nH + c[4] * ne * x[2] * nHe + c[5] * ne * x[3] * nHe
+            + c[6] * ne * x[0] * nH + c[7] * ne * x[3] * nHe)
+    zp = F(1) + z
+    cool = cool + c[9] * ((zp * zp) * (zp * zp)) * (T - F(2.725) * zp) * ne
+    cool = cool + c[8] * ne * (nH * x[1] + nHe * x[3] + F(4) * nHe * x[4])
+    cool = cool + F(3) * Hz * F(KB) * T * (nH + nHe + ne)
+    return heat - cool
+
+
+def solve_pcte(nH, nHe, p, z, Hz, fc, tol, F, path=None):
+    """ion_solver.f90:729-880; p = (H1i, He1i, He2i, H1h, He1h, He2h). -> (x[5], T)"""
+    Tl, Tr = F(TFLOOR), F(TMAX)
+    if _dudT(nH, nHe, Tl, p, z, Hz, fc, tol, F) < 0:
+        return solve_pce(nH, nHe, get_kchem(Tl, fc, F), p[0], p[1], p[2], tol, F), Tl
+    assert not _dudT(nH, nHe, Tr, p, z, Hz, fc, tol, F) > 0, "Teq not bracketed"
+    T = F(10) ** ((np.log10(Tl) + np.log10(Tr)) * F(0.5))
+    err, it = F(np.inf), 0
+    while err > F(tol):
+        neg = bool(_dudT(nH, nHe, T, p, z, Hz, fc, tol, F) < 0)
+        if path is not None:
+            path.append(neg)
+        Told = T
+        if neg:
+            Tr, T = T, (Tl + T) * F(0.5)
+        else:
+            Tl, T = T, (T + Tr) * F(0.5)
+        err = abs(F(1) - T / Told)
+        it += 1
+        assert it <= MAX_ITER
+    return solve_pce(nH, nHe, get_kchem(T, fc, F), p[0], p[1], p[2], tol, F), T
+
+
+def _ssum(a):
+    """Fortran sum() without reassociation: strictly left to right (np.sum is pairwise)."""
+    return np.cumsum(a)[-1] if a.size else a.dtype.type(0)
+
+
+def _trap(x, y):                               # utils.f90:11-21
+    return x.dtype.type(0.5) * _ssum((y[1:] + y[:-1]) * (x[1:] - x[:-1]))
+
+
+def _six_rates(E, shape, sig, att, F):
+    """source_background.f90:287-354 (+ :186-241 for att = 1): the six integrals, each
+    evaluated on its own as the reference does."""
+    Eth = [F(v[0]) for v in V96]
+    if E.size == 1:                             # :111-112, :302-304
+        yy = [F(4) * F(PI) * shape / E * F(ERG2EV) * s * att for s in sig]
+        return [y[0] for y in yy] + [(y * (E - t) * F(EV2ERG))[0] for y, t in zip(yy, Eth)]
+    base = F(4) * F(PI) * shape / (E * F(H_ERG))
+    ion = [_trap(E, base * s * att) for s in sig]
+    heat = [_trap(E, base * s * att * (E - t) * F(EV2ERG)) for s, t in zip(sig, Eth)]
+    return ion + heat
+
+
+def _ds_segment(E, il, mu, j, F):              # geometry.f90:90-168 (search repeated per call)
+    p = (E[il] + E[il + 1]) * F(0.5) * np.sqrt(F(1) - mu * mu)
+    m = next(i for i in range(1, E.size) if E[i] <= p) - 1
+    s = lambda i: np.sqrt(E[i] * E[i] - p * p)  # noqa: E731
+    if j == m:
+        return F(2) * s(j)
+    i1 = j if j < m else m - abs(m - j)
+    return abs(s(i1 + 1) - s(i1))
+
+
+def _cell_solve(nH, nHe, T, r6, fcA, find_Teq, z, Hz, tol_in, F):
+    if find_Teq:
+        return solve_pcte(nH, nHe, r6, z, Hz, (fcA,) * 3, tol_in, F)
+    return solve_pce(nH, nHe, get_kchem(T, (fcA,) * 3, F), r6[0], r6[1], r6[2], tol_in, F), F(T)
+
+
+def sphere_bgnd_jacobi_sweep(Edges, nH, nHe, T, x, src, mu, wmu, E_eV, shape, fcA, find_Teq,
+                             z, Hz, tol, F, cells=None):
+    """One sweep of sphere_bgnd.f90:578-918 in Jacobi order from state ``x`` [5][Nl] and
+    source rates ``src`` [6][Nl] (Edges decreasing).  Returns (x_new, T_new, src_new) for
+    ``cells`` (default all)."""
+    E = np.asarray(Edges, dtype=F)
+    Ev, sh = np.asarray(E_eV, dtype=F), np.asarray(shape, dtype=F)
+    nH_, nHe_ = np.asarray(nH, dtype=F), np.asarray(nHe, dtype=F)
+    x = np.asarray(x, dtype=F)
+    sig = [sigma_v96(X, Ev, F) for X in range(3)]
+    sth = [sigma_v96(X, np.array([V96[X][0]]), F)[0] for X in range(3)]   # :213-215
+    ra = [sig[X] / sth[X] for X in range(3)]
+    Nl = nH_.size
+    out = {}
+    for il in (range(Nl) if cells is None else cells):
+        acc = [F(v) for v in np.asarray(src)[:, il]]
+        for imu in range(len(mu)):
+            m_ = F(mu[imu])
+            p = (E[il] + E[il + 1]) * F(0.5) * np.sqrt(F(1) - m_ * m_)
+            m = next(i for i in range(1, Nl + 1) if E[i] <= p) - 1     # geometry.f90:61-71
+            j0 = il if m_ <= 0 else 2 * m - il                          # :769-773
+            N = [F(0), F(0), F(0)]
+            for j in range(j0, 2 * m + 1):
+                jnl = m - abs(m - j)
+                ds = _ds_segment(E, il, m_, j, F)
+                if j == j0:
+                    ds = ds * F(0.5)
+                N[0] = N[0] + ds * nH_[jnl] * x[0][jnl]
+                N[1] = N[1] + ds * nHe_[jnl] * x[2][jnl]
+                N[2] = N[2] + ds * nHe_[jnl] * x[3][jnl]
+            tau = sum((N[X] * sth[X]) * ra[X] for X in range(3))        # :794-800, s_b.f90:267
+            r6 = _six_rates(Ev, sh, sig, np.exp(-tau), F)
+            acc = [a + r * F(wmu[imu]) for a, r in zip(acc, r6)]        # :837-848
+        acc = [a * F(0.5) for a in acc]                                 # :850-856 (Q1)
+        xs, Tn = _cell_solve(nH_[il], nHe_[il], T[il], acc, fcA, find_Teq, z, Hz,
+                             F(tol) * F(1.0e-2), F)
+        out[il] = (xs, Tn, acc)
+    return out
+
+
+def _e2xa(t, F):                               # zhang_jin_f.f90:94-173
+    if t == 0:
+        e1 = F(1.0e300)
+    elif t <= 1:
+        e1 = (-np.log(t) + ((((F(1.07857e-3) * t - F(9.76004e-3)) * t + F(5.519968e-2)) * t
+                             - F(0.24991055)) * t + F(0.99999193)) * t - F(0.57721566))
+    else:
+        es1 = (((t + F(8.5733287401)) * t + F(18.059016973)) * t + F(8.6347608925)) * t \
+            + F(0.2677737343)
+        es2 = (((t + F(9.5733223454)) * t + F(25.6329561486)) * t + F(21.0996530827)) * t \
+            + F(3.9584969228)
+        e1 = np.exp(-t) / t * es1 / es2
+    return np.exp(-t) - t * e1
+
+
+def slab_bgnd_sweep(Edges, nH, nHe, T, x, E_eV, shape, fcA, find_Teq, z, Hz, tol, F,
+                    cells=None):
+    """One sweep of slab_bgnd.f90:532-883 (first half; the mirror is a copy) from state x."""
+    E = np.asarray(Edges, dtype=F)
+    Ev, sh = np.asarray(E_eV, dtype=F), np.asarray(shape, dtype=F)
+    nH_, nHe_, x = np.asarray(nH, dtype=F), np.asarray(nHe, dtype=F), np.asarray(x, dtype=F)
+    sig = [sigma_v96(X, Ev, F) for X in range(3)]
+    sth = [sigma_v96(X, np.array([V96[X][0]]), F)[0] for X in range(3)]
+    ra = [sig[X] / sth[X] for X in range(3)]
+    dl = E[1:] - E[:-1]                                                  # :612
+    dt = [dl * nH_ * x[0] * sth[0], dl * nHe_ * x[2] * sth[1], dl * nHe_ * x[3] * sth[2]]
+    Nl = nH_.size
+    out = {}
+    for i in (range(Nl // 2) if cells is None else cells):
+        r6 = [F(0)] * 6
+        for side in (0, 1):                                             # slab_base.f90:63-115
+            th = [(_ssum(d[:i]) if side == 0 else _ssum(d[i + 1:])) + F(0.5) * d[i] for d in dt]
+            tau = th[0] * ra[0] + th[1] * ra[1] + th[2] * ra[2]        # :701-713, s_b.f90:380
+            att = (np.ones_like(tau) if _ssum(tau) == 0                  # s_b.f90:380-383
+                   else np.array([_e2xa(t, F) for t in tau], dtype=F))
+            r6 = [a + r * F(0.5) for a, r in zip(r6, _six_rates(Ev, sh, sig, att, F))]
+        xs, Tn = _cell_solve(nH_[i], nHe_[i], T[i], r6, fcA, find_Teq, z, Hz,
+                             F(tol) * F(1.0e-2), F)
+        out[i] = (xs, Tn, r6)
+    return out

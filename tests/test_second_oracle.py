@@ -1,0 +1,133 @@
+"""The C oracle pinned by an independent second derivation (oracle/second_oracle.py: numpy,
+written from the Fortran, not from rb_oracle_*.c).  In float64 the two codings execute the
+reference's statements in the same order, so fractions, temperatures and the bisection
+paths must coincide; in longdouble (64-bit mantissa) the second derivation is the "truth"
+both float64 codings are measured against.  Bounds: rates <= 1e-13, float64 bisection
+results bit-identical (a 1-ulp difference between numpy's and C's pow() in a rate
+coefficient is allowed for: <= 1e-14 there)."""
+import numpy as np
+import pytest
+
+from oracle import second_oracle as so
+from rabacus_b200 import configs
+
+FR = ("xH1", "xH2", "xHe1", "xHe2", "xHe3")
+RT = ("H1i_src", "He1i_src", "He2i_src", "H1h_src", "He1h_src", "He2h_src")
+
+
+def _zones(n, seed):
+    rng = np.random.default_rng(seed)
+    T = 10 ** rng.uniform(3.9, 5.0, n)
+    nH = 10 ** rng.uniform(-5.0, 1.0, n)
+    H1i = 10 ** rng.uniform(-17.0, -11.0, n)
+    return T, nH, nH * 0.08, H1i, H1i * 0.6, H1i * 0.02
+
+
+def test_rate_coefficients_against_the_second_derivation(orc):
+    T = 10 ** np.linspace(3.0, 7.0, 60)
+    for fc in ((1.0, 1.0, 1.0), (0.0, 0.0, 0.0), (0.3, 0.77, 0.5)):
+        kc, kl = orc.get_kchem(T, *fc), orc.get_kcool(T, *fc)
+        for i, t in enumerate(T):
+            truth = so.get_kchem(t, fc, np.longdouble) + so.get_kcool(t, fc, np.longdouble)
+            f64 = so.get_kchem(t, fc, np.float64) + so.get_kcool(t, fc, np.float64)
+            for q, col in enumerate(list(kc) + list(kl)):
+                # vs 64-bit mantissa; exp(-lam/2) carries |lam/2| ulp of its argument (lam <= 570)
+                assert abs(col[i] / float(truth[q]) - 1.0) <= 5e-14, (t, q)
+                # vs the float64 twin: numpy's log10/pow differ from glibc's by <= 1 ulp, which the
+                # case A/B mixing 10**(f log10 a + ..) amplifies by |ln a| ~ 30
+                assert abs(col[i] / float(f64[q]) - 1.0) <= 2e-14, (t, q)
+
+
+def test_solve_pce_same_fractions_and_same_bisection_path(orc):
+    T, nH, nHe, H1i, He1i, He2i = _zones(60, 1)
+    k = orc.get_kchem(T, 1.0, 1.0, 1.0)
+    x = orc.solve_pce(nH, nHe, *k, H1i, He1i, He2i, 1e-6)
+    for i in range(T.size):
+        ki = [a[i] for a in k]
+        p64, pld = [], []
+        x64 = so.solve_pce(nH[i], nHe[i], ki, H1i[i], He1i[i], He2i[i], 1e-6, np.float64, p64)
+        xld = so.solve_pce(nH[i], nHe[i], ki, H1i[i], He1i[i], He2i[i], 1e-6, np.longdouble, pld)
+        assert all(x[q][i] == x64[q] for q in range(5)), i        # bit-identical
+        assert p64 == pld and len(p64) >= 1, i                    # same branches, same length
+        # float64 against 64-bit-mantissa arithmetic on the SAME path: the conditioning of the
+        # reference algorithm itself (analytic_H1's discriminant cancels, ion_solver.f90:172-183)
+        assert max(abs(float(xld[q]) / x[q][i] - 1.0) for q in range(5)) <= 1e-10
+
+
+def test_solve_pcte_same_temperature_and_fractions(orc):
+    T, nH, nHe, H1i, He1i, He2i = _zones(24, 2)
+    heat = (H1i * 5e-12, He1i * 8e-12, He2i * 2e-11)
+    o = orc.solve_pcte(nH, nHe, H1i, He1i, He2i, *heat, 3.0, 1e-18, 1.0, 0.5, 0.0, 1e-6)
+    for i in range(T.size):
+        p = (H1i[i], He1i[i], He2i[i], heat[0][i], heat[1][i], heat[2][i])
+        p64, pld = [], []
+        x64, T64 = so.solve_pcte(nH[i], nHe[i], p, 3.0, 1e-18, (1.0, 0.5, 0.0), 1e-6,
+                                 np.float64, p64)
+        xld, Tld = so.solve_pcte(nH[i], nHe[i], p, 3.0, 1e-18, (1.0, 0.5, 0.0), 1e-6,
+                                 np.longdouble, pld)
+        assert o[5][i] == T64 and p64 == pld, i                  # same T bisection path
+        assert abs(float(Tld) / o[5][i] - 1.0) <= 1e-15
+        for q in range(5):
+            assert abs(o[q][i] / x64[q] - 1.0) <= 1e-14, (i, q)
+            assert abs(o[q][i] / float(xld[q]) - 1.0) <= 1e-10, (i, q)
+
+
+def _sphere_cfg(kind, Nl, Nnu, Nmu, find_Teq):
+    cfg = configs.c4_sphere_bgnd(Nl, Nnu, Nmu, find_Teq, nH0=0.3)
+    if kind == "log_clumpy":      # log-spaced radii, lognormal clumps (2 dex), a void shell
+        rng = np.random.default_rng(5)
+        cfg["Edges"] = np.concatenate([[0.0], cfg["Edges"][-1] * 10 ** np.linspace(-3, 0, Nl)])
+        cfg["nH"] = cfg["nH"] * 10 ** rng.normal(0.0, 2.0, Nl)
+        cfg["nH"][Nl // 3] = 1e-12 * cfg["nH"].max()
+        cfg["nHe"] = cfg["nH"] * 0.08
+    return cfg
+
+
+@pytest.mark.parametrize("kind", ["uniform", "log_clumpy"])
+@pytest.mark.parametrize("find_Teq", [False, True])
+def test_one_jacobi_sweep_of_sphere_bgnd(orc, kind, find_Teq):
+    Nl, Nnu, Nmu = 28, 16, 5
+    cfg = _sphere_cfg(kind, Nl, Nnu, Nmu, find_Teq)
+    a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], Nmu, cfg["E_eV"], cfg["shape"])
+    kw = dict(i_find_Teq=int(find_Teq), z=3.0, order=orc.ORDER_JACOBI)
+    thin = orc.sphere_bgnd_solve(*a, i_thin=1, **kw)
+    one = orc.sphere_bgnd_solve(*a, max_sweeps=1, **kw)
+    mu, w = orc.p_quadrature_rule(Nmu)
+    rv = lambda v: np.asarray(v)[::-1].copy()  # noqa: E731  (the sweep runs outer shell first)
+    for F, rt_tol, x_tol in ((np.float64, 2e-15, 1e-13), (np.longdouble, 1e-13, 1e-10)):
+        out = so.sphere_bgnd_jacobi_sweep(
+            rv(cfg["Edges"]), rv(cfg["nH"]), rv(cfg["nHe"]), rv(thin["T"]),
+            [rv(thin[k]) for k in FR], [rv(thin[k]) for k in RT], mu, w, cfg["E_eV"],
+            cfg["shape"], 1.0, find_Teq, 3.0, 0.0, 1e-4, F)
+        for il, (xs, Tn, acc) in out.items():
+            io = Nl - 1 - il
+            for q, k in enumerate(RT):
+                assert abs(float(acc[q]) / one[k][io] - 1.0) <= rt_tol, (F, il, k)
+            for q, k in enumerate(FR):
+                assert abs(float(xs[q]) / one[k][io] - 1.0) <= x_tol, (F, il, k)
+            assert abs(float(Tn) / one["T"][io] - 1.0) <= 1e-15, (F, il)
+
+
+@pytest.mark.parametrize("find_Teq", [False, True])
+def test_one_sweep_of_slab_bgnd(orc, find_Teq):
+    Nl, Nnu = 26, 16
+    cfg = configs.c3_slab_bgnd(Nl, Nnu, find_Teq)
+    rng = np.random.default_rng(9)
+    cfg["nH"] = cfg["nH"] * 10 ** rng.normal(0.0, 1.0, Nl)      # asymmetric, clumpy
+    cfg["nHe"] = cfg["nH"] * 0.08
+    a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], cfg["E_eV"], cfg["shape"])
+    kw = dict(i_find_Teq=int(find_Teq), z=3.0)
+    thin = orc.slab_bgnd_solve(*a, i_thin=1, **kw)
+    one = orc.slab_bgnd_solve(*a, max_sweeps=1, **kw)
+    for F, rt_tol, x_tol in ((np.float64, 2e-15, 1e-13), (np.longdouble, 1e-13, 1e-10)):
+        out = so.slab_bgnd_sweep(cfg["Edges"], cfg["nH"], cfg["nHe"], thin["T"],
+                                 [thin[k] for k in FR], cfg["E_eV"], cfg["shape"], 1.0,
+                                 find_Teq, 3.0, 0.0, 1e-4, F)
+        assert sorted(out) == list(range(Nl // 2))
+        for i, (xs, Tn, acc) in out.items():
+            for q, k in enumerate(RT):
+                assert abs(float(acc[q]) / one[k][i] - 1.0) <= rt_tol, (F, i, k)
+                assert one[k][Nl - 1 - i] == one[k][i]             # the mirrored copy
+            for q, k in enumerate(FR):
+                assert abs(float(xs[q]) / one[k][i] - 1.0) <= x_tol, (F, i, k)
+            assert abs(float(Tn) / one["T"][i] - 1.0) <= 1e-15, (F, i)
