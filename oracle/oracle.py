@@ -97,6 +97,8 @@ def _load(path):
     L.orc_last_sweep_seconds.restype = C.c_double
     L.orc_set_num_threads.argtypes = [C.c_int]
     L.orc_set_num_threads.restype = None
+    L.orc_set_coefficient_hook.argtypes = [C.c_void_p]
+    L.orc_set_coefficient_hook.restype = None
     return L
 
 
@@ -159,6 +161,26 @@ def set_num_threads(n):
     """OpenMP team size of the active build (overrides OMP_NUM_THREADS; torchrun sets 1)."""
     lib().orc_set_num_threads(int(n))
     return lib().orc_num_threads()
+
+
+class coefficient_hook(object):
+    """``with oracle.coefficient_hook(fnptr):`` -- the oracle's solvers take the rate /
+    cooling coefficients of a temperature from the C function ``fnptr`` (signature
+    ``void(double T, double fA, double fB, double fC, double *out16)``) instead of its own
+    fits.  The GPU parity tests install the host build of the CUDA library's evaluation
+    (same bits as the device), which isolates the solvers from the <= 1-ulp difference
+    between two pow() implementations.  Applies to the active build only."""
+
+    def __init__(self, fnptr):
+        self.fn = C.cast(fnptr, C.c_void_p)
+
+    def __enter__(self):
+        lib().orc_set_coefficient_hook(self.fn)
+        return self
+
+    def __exit__(self, *exc):
+        lib().orc_set_coefficient_hook(C.c_void_p(0))
+        return False
 
 
 def last_sweep_seconds():

@@ -182,11 +182,26 @@ static double mixAB(double a, double b, double fcA) {
   return pow(10.0, log10(a) * fcA + log10(b) * (1.0 - fcA));
 }
 
+/* Coefficient hook (tests only): when set, the 6 + 10 rate / cooling coefficients of a
+ * temperature come from the caller's function instead of the fits below.  The parity tests
+ * install the host build of the CUDA library's own evaluation here, so that the SOLVERS of
+ * this oracle can be fed exactly the coefficients the device used (tests/helpers.py).
+ * out16 = reH2 reHe2 reHe3 ciH1 ciHe1 ciHe2 recH2 recHe2 recHe3 cicH1 cicHe1 cicHe2
+ *         cecH1 cecHe2 bremss compton.  NULL restores the fits.  Not thread safe to change. */
+static orc_coef_hook g_coef_hook = 0;
+void orc_set_coefficient_hook(orc_coef_hook fn) { g_coef_hook = fn; }
+
 /* chem_cool_rates.f90:45-88 (get_kchem_s); the _v twin :91-140 is the same
  * arithmetic element-wise */
 void orc_kchem1(double T, double fcA_H2, double fcA_He2, double fcA_He3,
                 double *reH2, double *reHe2, double *reHe3, double *ciH1,
                 double *ciHe1, double *ciHe2) {
+  if (g_coef_hook) {
+    double o[16];
+    g_coef_hook(T, fcA_H2, fcA_He2, fcA_He3, o);
+    *reH2 = o[0]; *reHe2 = o[1]; *reHe3 = o[2]; *ciH1 = o[3]; *ciHe1 = o[4]; *ciHe2 = o[5];
+    return;
+  }
   *reH2 = mixAB(hg97_reH2a(T), hg97_reH2b(T), fcA_H2);
   *reHe2 = mixAB(hg97_reHe2a(T), hg97_reHe2b(T), fcA_He2);
   *reHe2 = *reHe2 + hg97_reHe2di(T);
@@ -199,6 +214,14 @@ void orc_kchem1(double T, double fcA_H2, double fcA_He2, double fcA_He3,
 /* chem_cool_rates.f90:147-204 (get_kcool_s) */
 void orc_kcool1(double T, double fcA_H2, double fcA_He2, double fcA_He3,
                 orc_kcool *k) {
+  if (g_coef_hook) {
+    double o[16];
+    g_coef_hook(T, fcA_H2, fcA_He2, fcA_He3, o);
+    k->recH2 = o[6]; k->recHe2 = o[7]; k->recHe3 = o[8]; k->cicH1 = o[9]; k->cicHe1 = o[10];
+    k->cicHe2 = o[11]; k->cecH1 = o[12]; k->cecHe2 = o[13]; k->bremss = o[14];
+    k->compton = o[15];
+    return;
+  }
   k->recH2 = mixAB(hg97_recH2a(T), hg97_recH2b(T), fcA_H2);
   k->recHe2 = mixAB(hg97_recHe2a(T), hg97_recHe2b(T), fcA_He2);
   k->recHe2 = k->recHe2 + hg97_recHe2di(T);

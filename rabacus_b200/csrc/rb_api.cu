@@ -162,7 +162,7 @@ static int source_kind(int geom) {  // 0 background, 1 point, 2 plane
 }
 
 // Per-frequency table for one problem: [Nnu][9] = sigma_X/sigma_X,th (3),
-// W_ion,X (3), W_heat,X (3), plus thin[6] = sum_k W.
+// W_ion,X (3), W_heat,X (3), plus thin[9] = sum_k W (6), min_nu sigma ratio (3).
 //   y_ion,X(k)  = base_k * sigma_X(k)                  (source_background.f90:306-307)
 //   y_heat,X(k) = y_ion,X(k) * (E_k - E_th,X) * eV_2_erg   (:350)
 //   base_k = 4 pi I_k/(E_k h) | F_k/(E_k h) | L_k/(E_k h)   (s_bgnd:306, s_plane:296, s_point:348;
@@ -198,7 +198,8 @@ static void build_spec_table(int geom, const double *E, const double *shape, int
       row[6 + X] = yh * wk;
       thin[X] += row[3 + X];
       thin[3 + X] += row[6 + X];
-      thin[6 + X] = std::max(thin[6 + X], row[X]);  // max_nu sigma_X(nu)/sigma_X,th
+      // min_nu sigma_X(nu)/sigma_X,th: lower bound of a ray's optical depth (k_nu_rates)
+      thin[6 + X] = (k == 0) ? row[X] : std::min(thin[6 + X], row[X]);
     }
   }
 }
@@ -1888,6 +1889,20 @@ __global__ void k_diag_hg97(const double *T, const double *a, const double *b, c
                         kl.recH2, kl.recHe2, kl.recHe3, kl.cicH1, kl.cicHe1, kl.cicHe2,
                         kl.cecH1, kl.cecHe2, kl.bremss, kl.compton};
   for (int q = 0; q < 16; ++q) out[(size_t)q * n + i] = v[q];
+}
+
+// The device's rate-coefficient evaluation built by the host compiler: bit-identical to what
+// the kernels compute (IEEE operations and table reads only, -ffp-contract=off).  Signature
+// of the oracle's coefficient hook (oracle/rb_oracle.h: orc_set_coefficient_hook).
+extern "C" void rbi_host_coefficients(double T, double fcA_H2, double fcA_He2, double fcA_He3,
+                                      double *out16) {
+  rb_kchem_t kc;
+  rb_kcool_t kl;
+  get_kchem_kcool(T, fcA_H2, fcA_He2, fcA_He3, kc, kl, 0);
+  const double v[16] = {kc.reH2, kc.reHe2, kc.reHe3, kc.ciH1, kc.ciHe1, kc.ciHe2,
+                        kl.recH2, kl.recHe2, kl.recHe3, kl.cicH1, kl.cicHe1, kl.cicHe2,
+                        kl.cecH1, kl.cecHe2, kl.bremss, kl.compton};
+  for (int q = 0; q < 16; ++q) out16[q] = v[q];
 }
 
 extern "C" int rbi_plan_set_libm_pow(rb_plan *p, int on) {

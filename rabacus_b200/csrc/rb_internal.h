@@ -24,6 +24,11 @@ int rbi_diag_pow(const double *x, const double *y, int n, double *out, int on_de
  * statement, instead of the table-driven form. */
 int rbi_diag_hg97(const double *T, const double *fcA_H2, const double *fcA_He2,
                   const double *fcA_He3, int n, double *out16, int on_device, int libm);
+/* One temperature's 6 + 10 coefficients from the HOST build of the device code (same bits
+ * as the kernels): handed to the oracle as its coefficient hook by the parity tests, so
+ * that the oracle's solvers can be required to reproduce the device's fractions exactly. */
+void rbi_host_coefficients(double T, double fcA_H2, double fcA_He2, double fcA_He3,
+                           double *out16);
 /* Per-plan A/B switch: on != 0 makes every kernel of THIS plan evaluate the Hui & Gnedin
  * fits through libdevice pow() (no global state; other plans are unaffected). */
 int rbi_plan_set_libm_pow(rb_plan *plan, int on);

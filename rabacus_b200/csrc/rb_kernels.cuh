@@ -43,7 +43,7 @@ typedef RB_FLAG_T rb_flag_t;
 
 constexpr int kPackPad = 8;    // padding records after the Nl+1 shell records
 constexpr int kSpecStride = 9;  // per-frequency table: 3 sigma ratios, 3+3 weights
-constexpr int kThinStride = 9;  // per problem: 6 optically thin integrals, 3 max sigma ratios
+constexpr int kThinStride = 9;  // per problem: 6 optically thin integrals, 3 min sigma ratios
 
 // Everything a kernel needs, passed by value.
 struct PlanDev {
@@ -502,7 +502,10 @@ __device__ __forceinline__ double warp_incl_scan(double v) {
 // two-sided slabs).  The exclusive prefix is a block-wide shuffle scan over
 // per-thread sequential chunks; hi = total - lo - dtau_i.
 // ---------------------------------------------------------------------------
-// exclusive block scan of three running sums; `wsum` is [3][BLOCK/32] scratch
+// exclusive block scan of three running sums; `wsum` is [3][BLOCK/32] scratch.  The
+// exclusive value of a lane is the INCLUSIVE value of its left neighbour (shuffle), never
+// "inclusive minus own": one optically thick layer (own value 1e6 against a prefix of 1e-2)
+// would cancel 1e-16 x 1e6 into every thin layer behind it in the same warp / block.
 template <int BLOCK>
 __device__ __forceinline__ void block_excl_scan3(const double (&part)[3], double (&excl)[3],
                                                  double (*wsum)[BLOCK / 32]) {
@@ -511,7 +514,8 @@ __device__ __forceinline__ void block_excl_scan3(const double (&part)[3], double
 #pragma unroll
   for (int X = 0; X < 3; ++X) {
     const double inc = warp_incl_scan(part[X]);
-    inw[X] = inc - part[X];
+    const double left = __shfl_up_sync(0xffffffffu, inc, 1);
+    inw[X] = (lane == 0) ? 0.0 : left;
     if (lane == 31) wsum[X][wid] = inc;
   }
   __syncthreads();
@@ -520,7 +524,8 @@ __device__ __forceinline__ void block_excl_scan3(const double (&part)[3], double
     for (int X = 0; X < 3; ++X) {
       const double v = (lane < BLOCK / 32) ? wsum[X][lane] : 0.0;
       const double inc = warp_incl_scan(v);
-      if (lane < BLOCK / 32) wsum[X][lane] = inc - v;
+      const double left = __shfl_up_sync(0xffffffffu, inc, 1);
+      if (lane < BLOCK / 32) wsum[X][lane] = (lane == 0) ? 0.0 : left;
     }
   }
   __syncthreads();
@@ -694,8 +699,19 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int cpu) {
     __syncthreads();  // previous cell's rays / reduction scratch are no longer read
     {
       const double4 *g = P.col + col_index(P, b, il, 0);
-      for (int i = threadIdx.x; i < ndir_pad; i += BLOCK)
-        s_ray[i] = (i < ndir) ? g[i] : make_double4(0.0, 0.0, 0.0, 0.0);  // pad: weight 0
+      // A ray whose optical depth exceeds 708 at EVERY frequency (lower bound: each species'
+      // smallest cross-section ratio on the grid) contributes exp(-tau) < 3e-308 to every
+      // integral: a denormal or zero in the reference's libm.  exp_fast clamps its argument
+      // at -708 (3e-308 stands in), which is invisible next to any normal term but would be
+      // the whole answer behind a wall of neutral gas (monochromatic sources): such rays
+      // get weight 0, i.e. exactly the reference's zero.
+      const double *th = P.thin + (size_t)b * kThinStride;
+      const double m0 = th[6], m1 = th[7], m2 = th[8];
+      for (int i = threadIdx.x; i < ndir_pad; i += BLOCK) {
+        double4 r = (i < ndir) ? g[i] : make_double4(0.0, 0.0, 0.0, 0.0);  // pad: weight 0
+        if (!ATT_E2 && r.x * m0 + r.y * m1 + r.z * m2 > 708.0) r.w = 0.0;
+        s_ray[i] = r;
+      }
     }
     __syncthreads();
     double part[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};

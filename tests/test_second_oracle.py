@@ -72,6 +72,44 @@ def test_solve_pcte_same_temperature_and_fractions(orc):
             assert abs(o[q][i] / float(xld[q]) - 1.0) <= 1e-10, (i, q)
 
 
+def test_helium_free_zone_first_branch_is_decided_by_the_last_bit(orc):
+    """Why fractions cannot be held to 1e-10 end to end (helpers.solver_check).  Without helium
+    analytic_H1 (ion_solver.f90:172-183) is the exact fixed point of solve_pce, so the first
+    ratio_ne (:503) is 1 within a few ulp and the branch :515-521 is decided by rounding.
+    The scalar solver stops after that one step, but the lock-step `_v` twin (the optically
+    thin start, :565-696) keeps every zone bisecting until the slowest has converged: a
+    helium-free zone then returns from whichever bracket the noise chose.  Shown in the
+    oracle alone, no GPU involved: nudging H1i by ONE ulp moves xH1 of helium-free zones by
+    up to ~1e-7 (a good part of them by more than 1e-10), zones with helium by < 1e-14."""
+    rng = np.random.default_rng(4)
+    n, tol = 200, 1e-6
+    T = np.full(n, 1.0e4)
+    nH = 10 ** rng.uniform(-4.0, 0.0, n)
+    H1i = 10 ** rng.uniform(-14.0, -11.0, n)
+    nHe = nH * 0.08
+    nHe[::2] = 0.0
+    k = orc.get_kchem(T, 1.0, 1.0, 1.0)
+    # the first ratio_ne of a helium-free zone: one implicit step from the analytic start
+    for i in range(0, n, 2):
+        reH2, ciH1 = k[0][i], k[3][i]
+        RR = (ciH1 + reH2) * nH[i]
+        QQ = -(H1i[i] + reH2 * nH[i] + RR)
+        PP = reH2 * nH[i]
+        x1 = PP / (-0.5 * (QQ - np.sqrt(max(QQ * QQ - 4.0 * RR * PP, 0.0))))
+        ne0 = (1.0 - x1) * nH[i]
+        ne1 = (ciH1 * ne0 + H1i[i]) / (reH2 * ne0 + ciH1 * ne0 + H1i[i]) * nH[i]
+        assert abs(ne1 / ne0 - 1.0) <= 1e-11, i
+    args = (nH, nHe) + tuple(k)
+    base = orc.solve_pce(*args, H1i, H1i * 0.6, H1i * 0.02, tol, vector=True)
+    moved = np.zeros(n)
+    for h in (np.nextafter(H1i, np.inf), np.nextafter(H1i, 0.0)):
+        x = orc.solve_pce(*args, h, H1i * 0.6, H1i * 0.02, tol, vector=True)
+        moved = np.maximum(moved, np.abs(x[0] / base[0] - 1.0))
+    assert moved[1::2].max() <= 1e-14                   # zones with helium: well conditioned
+    assert (moved[::2] > 1e-10).sum() >= 10              # helium-free: decided by the last bit
+    assert 1e-9 < moved[::2].max() <= 100 * tol
+
+
 def _sphere_cfg(kind, Nl, Nnu, Nmu, find_Teq):
     cfg = configs.c4_sphere_bgnd(Nl, Nnu, Nmu, find_Teq, nH0=0.3)
     if kind == "log_clumpy":      # log-spaced radii, lognormal clumps (2 dex), a void shell
