@@ -221,6 +221,8 @@ struct rb_plan {
   double4 *dpack = nullptr;
   double *dspec = nullptr, *dthin = nullptr, *dmu = nullptr, *dzHz = nullptr;
   double4 *dcol = nullptr;
+  double4 *dfar = nullptr;      // far-field moment table [B][Nl+1][kFarNT] (SphereBgnd)
+  bool use_far = false;         // columns: far field from the table, near field walked
   unsigned *ditems = nullptr;   // column-kernel work list (LPT order), see build_items
   int *dwork = nullptr;         // [B] next-item counters of the column kernel
   // recombination-photon transfer (rec_meth != fixed)
@@ -245,7 +247,7 @@ struct rb_plan {
     RecConst K;
     RecDev R;
     PeerDev Q;
-    int rec_meth, live, spec_g, cols_chunks, sharded;
+    int rec_meth, live, spec_g, cols_chunks, sharded, use_far;
   };
   GraphKey gkey;
   bool gkey_valid = false;
@@ -260,6 +262,7 @@ struct rb_plan {
   long long peer_sweeps = 0;    // sharded sweeps enqueued since rb_plan_peer_connect
   int peer_world = 1;
   int n_items = 0, items_start = -1, items_stride = -1, items_chunks = 1, n_sm = 148;
+  bool items_far = false;
   double *dpart = nullptr;      // chunk partial sums of the column kernel (nchunk > 1)
   size_t part_bytes = 0;
   std::vector<double> items_edges;  // problem-0 edges the list was built from
@@ -315,7 +318,7 @@ extern "C" void rb_plan_destroy(rb_plan *p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   destroy_graphs(p);
   cudaFree(p->drec); cudaFree(p->drecbuf); cudaFree(p->drecI); cudaFree(p->diso_items);
-  cudaFree(p->dpart); cudaFree(p->dreversed);
+  cudaFree(p->dpart); cudaFree(p->dreversed); cudaFree(p->dfar);
   if (p->dpeer) {
     for (int r = 0; r < kMaxPeers; ++r)
       if (p->peer_base[r] && p->peer_base[r] != p->dpeer) cudaIpcCloseMemHandle(p->peer_base[r]);
@@ -411,6 +414,19 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   }
   if (d.geometry == RB_GEOM_SPHERE_BGND)
     ALLOC(p->ditems, (size_t)((Nl + 31) / 32) * ((d.Nmu + 1) / 2) * 8 * sizeof(unsigned));
+  if (d.geometry == RB_GEOM_SPHERE_BGND) {
+    // far-field moment table: where the shell records fit in shared memory (the column
+    // kernel that uses it) and the table stays below 32 GiB; RB_NO_FAR=1 disables it
+    const size_t far_bytes = B * (Nl + 1) * (size_t)kFarNT * sizeof(double4);
+    const size_t rec_smem = (size_t)(Nl + 1 + kPackPad) * sizeof(double4);
+    const int nseg = (int)((Nl + 1 + kFarSeg - 1) / kFarSeg);
+    const char *nf = getenv("RB_NO_FAR");
+    if (!(nf && atoi(nf) != 0) && rec_smem <= 227 * 1024 - 1024 && nseg <= 8 * 42 &&
+        far_bytes <= ((size_t)32 << 30)) {
+      if (cudaMalloc((void **)&p->dfar, far_bytes) == cudaSuccess) p->use_far = true;
+      else { cudaGetLastError(); p->dfar = nullptr; }
+    }
+  }
   cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev);
   ALLOC(p->dflags, (3 * B + kSlots) * sizeof(int)); ALLOC(p->dresid, B * 8);
   ALLOC(p->dreversed, B);
@@ -640,7 +656,8 @@ extern "C" int rb_plan_thin(rb_plan *p) {
 static int build_items(rb_plan *p, int cell_start, int cell_stride, int n_local, int nchunk) {
   const int Nl = p->d.Nl, Nmu = p->d.Nmu;
   const double *E = p->hEdges;  // solver orientation: non-increasing
-  if (p->items_start == cell_start && p->items_stride == cell_stride &&
+  const bool far = p->use_far;
+  if (p->items_start == cell_start && p->items_stride == cell_stride && p->items_far == far &&
       p->items_chunks == nchunk && p->items_edges.size() == (size_t)Nl + 1 &&
       memcmp(p->items_edges.data(), E, sizeof(double) * (Nl + 1)) == 0)
     return RB_OK;
@@ -662,8 +679,22 @@ static int build_items(rb_plan *p, int cell_start, int cell_stride, int n_local,
         if (E[mid] <= pr) hi = mid; else lo = mid + 1;
       }
       const int m = lo - 1;
+      int walked = m + 1;
+      if (far) {   // only the edges below RATIO p are walked (sphere_ray_pair)
+        const double rp = pr * RB_FAR_RATIO;
+        int kf = -1;
+        if (m >= 0 && E[0] >= rp) {
+          int a0 = 0, a1 = m;
+          while (a0 < a1) {
+            const int mid = (a0 + a1 + 1) >> 1;
+            if (E[mid] >= rp) a0 = mid; else a1 = mid - 1;
+          }
+          kf = a0;
+        }
+        walked = m - kf;
+      }
       for (int c = 0; c < nchunk; ++c) {  // shell edges c*Q .. (c+1)*Q-1, up to m
-        const int len = (nchunk == 1) ? m + 1 : std::min(m, (c + 1) * Q - 1) - c * Q + 1;
+        const int len = (nchunk == 1) ? walked : std::min(m, (c + 1) * Q - 1) - c * Q + 1;
         // (chunks that are empty for the whole block stay in the list: their lanes store the
         // zero partials the combine kernel reads)
         v.emplace_back(-std::max(len, 0), (unsigned)jb | ((unsigned)c << 12) | ((unsigned)ip << 16));
@@ -678,6 +709,7 @@ static int build_items(rb_plan *p, int cell_start, int cell_stride, int n_local,
                      cudaMemcpyHostToDevice, p->stream));
   CK(cudaStreamSynchronize(p->stream));  // `items` is pageable and dies here
   p->items_start = cell_start; p->items_stride = cell_stride; p->items_chunks = nchunk;
+  p->items_far = far;
   p->items_edges.assign(E, E + Nl + 1);
   return RB_OK;
 }
@@ -701,6 +733,36 @@ static int live_problems(const rb_plan *p) {
   int q = B;
   while (q / 4 >= p->active_hint && q / 4 >= 1) q /= 4;
   return q;
+}
+
+// far-field moment table of every problem (k_far_moments): one cluster per problem, as many
+// CTAs as it takes to give every (segment, absorber) a thread and -- for small batches --
+// to spread one problem's scan over several SMs
+static int launch_far_moments(rb_plan *p) {
+  const int Nl = p->d.Nl, B = p->d.n_problems;
+  const int nseg = (Nl + 1 + kFarSeg - 1) / kFarSeg;
+  int cs = 1;
+  while (cs < kMaxCluster && ((nseg + cs - 1) / cs > 42 || (long long)B * cs * 2 <= p->n_sm)) cs *= 2;
+  while (cs > 1 && nseg < cs) cs /= 2;
+  const int spc = (nseg + cs - 1) / cs;
+  if (3 * spc > 128) return RB_ERR_UNSUPPORTED;
+  const size_t smem = far_smem_bytes(spc);
+  int rc = set_smem(k_far_moments, smem);
+  if (rc) return rc;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)B * cs);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = p->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, k_far_moments, p->P, p->dfar, cs, spc));
+  p->info.n_launches += 1;
+  return RB_OK;
 }
 
 static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, int n_local) {
@@ -737,6 +799,7 @@ static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, in
       return (size_t)B * ((p->d.Nmu + 1) / 2) * n_local * nc * kPartStride * sizeof(double);
     };
     while (nchunk > 1 && part_bytes(nchunk) > ((size_t)2 << 30)) nchunk /= 2;
+    if (p->use_far) nchunk = 1;   // the walks are short: whole items balance well enough
   }
   int rc = build_items(p, cell_start, cell_stride, n_local, nchunk);
   if (rc) return rc;
@@ -753,6 +816,10 @@ static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, in
     }
   }
 
+  if (p->use_far) {
+    rc = launch_far_moments(p);
+    if (rc) return rc;
+  }
   const int waves = (B > 1) ? 4 : 1;  // batches: ~4 CTAs per resident slot (finer tail)
   const int live = live_problems(p);
   int per_problem = std::max(1, (waves * want + live - 1) / live);
@@ -767,7 +834,7 @@ static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, in
     if (rc) return rc;                                                                       \
     k_sphere_columns_smem<THREADS, 1, MINB><<<g, THREADS, smem, s>>>(                        \
         p->P, cell_start, cell_stride, n_local, p->ditems, p->n_items, p->dwork, nchunk,     \
-        p->dpart);                                                                           \
+        p->dpart, p->use_far ? p->dfar : nullptr);                                           \
   } while (0)
   // 16-18 warps per SM at ~100 registers beat 24 warps at 80 (1.035 vs 1.068 ms at C4,
   // profiles/r01_kernel_variants.md)
@@ -1165,6 +1232,7 @@ static int sweep_graph(rb_plan *p, bool sharded) {
   key.rec_meth = p->rec_meth;
   key.live = live_problems(p);
   key.sharded = sharded ? 1 : 0;
+  key.use_far = p->use_far ? 1 : 0;
   {
     const char *a = getenv("RB_SPEC_G"), *b = getenv("RB_COLS_CHUNKS");
     key.spec_g = a ? atoi(a) : 0;
@@ -1903,6 +1971,13 @@ extern "C" void rbi_host_coefficients(double T, double fcA_H2, double fcA_He2, d
                         kl.recH2, kl.recHe2, kl.recHe3, kl.cicH1, kl.cicHe1, kl.cicHe2,
                         kl.cecH1, kl.cecHe2, kl.bremss, kl.compton};
   for (int q = 0; q < 16; ++q) out16[q] = v[q];
+}
+
+extern "C" int rbi_plan_set_far_field(rb_plan *p, int on) {
+  if (!p) return RB_ERR_BAD_ARG;
+  if (on && !p->dfar) return RB_ERR_UNSUPPORTED;
+  p->use_far = on != 0;   // part of the graph key and of the work-list cache key
+  return RB_OK;
 }
 
 extern "C" int rbi_plan_set_libm_pow(rb_plan *p, int on) {

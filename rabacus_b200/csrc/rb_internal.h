@@ -42,6 +42,11 @@ int rbi_plan_set_libm_pow(rb_plan *plan, int on);
 int rbi_plan_bench_steps(rb_plan *plan, int steps, size_t flush_bytes, int graphs,
                          double *ms_sum);
 
+/* A/B switch of THIS plan: on = 0 makes the SphereBgnd column kernel walk every shell edge
+ * of every ray (the round-1 path) instead of taking the far field from the moment table
+ * (rb_kernels.cuh "Far-field evaluation"); RB_ERR_UNSUPPORTED if the plan has no table. */
+int rbi_plan_set_far_field(rb_plan *plan, int on);
+
 /* device time [ms] of the kernel of this thread's last rb_solve_pce / rb_solve_pcte call
  * (scalar mode), for the single-zone batch line of bench.py */
 double rbi_last_zone_kernel_ms(void);

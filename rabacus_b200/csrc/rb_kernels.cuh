@@ -29,6 +29,7 @@
 #pragma once
 #include <cooperative_groups.h>
 
+#include "rb_far_coeffs.h"
 #include "rb_ion.cuh"
 
 namespace rb {
@@ -203,6 +204,181 @@ __device__ __forceinline__ double sqrt_pos(double x) {
   return fma(ge, q, g0);
 }
 
+// ---------------------------------------------------------------------------
+// Far-field evaluation of the column sums.
+//
+// A ray pair with impact parameter p adds s_k D_k, s_k = sqrt(E_k^2 - p^2), over ALL shell
+// edges above its tangent point -- 0.68 Nl edges on average, most of them far from the
+// tangent point, where s_k is a smooth function of u_k = (p/E_k)^2:
+//     s_k = E_k sqrt(1 - u_k) = E_k sum_n b_n u_k^n          (u_k <= 1/RATIO^2 = 0.64)
+// (b_n: Chebyshev interpolant of degree NT-1, error 5e-18, rb_far_coeffs.h).  Summed over the
+// edges k <= K that are far for this ray (E_k >= RATIO p) the p-dependence factors out:
+//     sum_{k<=K} s_k D_k = E_K sum_n b_n u_K^n Mt_n[K],   Mt_n[K] = sum_{k<=K} D_k (E_K/E_k)^(2n-1)
+// and the moments Mt_n obey  Mt_n[K] = Mt_n[K-1] (E_K/E_{K-1})^(2n-1) + D_K : one pass over
+// the edges per sweep (k_far_moments), after which every ray pair gets its whole far field
+// from ONE table row with NT fused multiply-adds per absorber -- and walks only the edges
+// with p < E_k < RATIO p (11 % of the edge visits at C4).  The normalisation by E_K keeps
+// every factor in (0, 1]: no overflow for any radial dynamic range.  Rounding: measured
+// <= 2e-14 of a column for random 1e6 density jumps (scratch/farfield_proto.py), i.e. the
+// same order as the summed-by-parts walk itself; the result depends on (cell, mu) only, not
+// on how cells are dealt to warps or GPUs.
+// ---------------------------------------------------------------------------
+constexpr int kFarNT = RB_FAR_NT;
+constexpr int kFarSeg = 32;           // edges per scan segment (fixed: part of the rounding)
+__constant__ double kFarB[kFarNT] = {RB_FAR_COEFFS};
+
+// g_K = E_K / E_{K-1} (0 for K = 0 and wherever an edge is 0: the row then restarts at D_K)
+__device__ __forceinline__ double far_g(const double *E, int K) {
+  if (K == 0) return 0.0;
+  const double a = E[K - 1];
+  return a > 0.0 ? E[K] / a : 0.0;
+}
+
+// one step of the NT recurrences, f_n = g^(2n-1) generated as two interleaved chains
+// (even n from 1/g, odd n from g, both stepped by g^4)
+__device__ __forceinline__ void far_step(double (&M)[kFarNT], double g, double D) {
+  const double g2 = g * g, g4 = g2 * g2;
+  double fe = g > 0.0 ? 1.0 / g : 0.0, fo = g;
+#pragma unroll
+  for (int n = 0; n < kFarNT; n += 2) {
+    M[n] = fma(M[n], fe, D);
+    fe = fe * g4;
+    if (n + 1 < kFarNT) {
+      M[n + 1] = fma(M[n + 1], fo, D);
+      fo = fo * g4;
+    }
+  }
+}
+
+// k_far_moments: one thread-block cluster of `csize` CTAs per problem; CTA `crank` owns the
+// contiguous scan segments [seg0, seg1) of kFarSeg edges; thread <-> (segment, absorber).
+//   pass 1   segment-local recurrences from zero -> B_s[X][n]; A_s[n] = prod g^(2n-1)
+//   CTA composite (A, B) over its segments; exchanged through distributed shared memory
+//   carry-in of the CTA from the CTAs before it, of the segment from the segments before it
+//   pass 2   the recurrences again from the carry-in, rows stored as b_n Mt_n[K]
+// far: [B][Nl+1][NT] double4 {HI, HeI, HeII, 0}.
+struct FarSmem {
+  double4 *rec;     // [spc * kFarSeg] {g, D0, D1, D2}
+  double *sA;       // [spc][NT]
+  double *sB;       // [spc][3][NT]
+  double *cA;       // [NT]      CTA composite
+  double *cB;       // [3][NT]
+  double *cin;      // [3][NT]   CTA carry-in
+};
+__host__ __device__ inline size_t far_smem_bytes(int spc) {
+  return (size_t)spc * kFarSeg * sizeof(double4) +
+         ((size_t)spc * kFarNT * 4 + 7 * kFarNT) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(128) k_far_moments(PlanDev P, double4 *__restrict__ far,
+                                                     int csize, int spc) {
+  namespace cg = cooperative_groups;
+  extern __shared__ double4 s_far4[];
+  const int b = blockIdx.x / csize, crank = blockIdx.x % csize;
+  const int Nl = P.Nl, nedge = Nl + 1;
+  const int nseg = (nedge + kFarSeg - 1) / kFarSeg;
+  const int seg0 = min(nseg, crank * spc), seg1 = min(nseg, seg0 + spc);
+  const int nmine = seg1 - seg0;
+  FarSmem S;
+  S.rec = s_far4;
+  S.sA = reinterpret_cast<double *>(s_far4 + (size_t)spc * kFarSeg);
+  S.sB = S.sA + (size_t)spc * kFarNT;
+  S.cA = S.sB + (size_t)spc * 3 * kFarNT;
+  S.cB = S.cA + kFarNT;
+  S.cin = S.cB + 3 * kFarNT;
+  const bool live = P.active[b] != 0;   // uniform over the cluster
+  const double *E = P.Edges + (size_t)b * nedge;
+  if (live) {
+    const int k0 = seg0 * kFarSeg, k1 = min(nedge, seg1 * kFarSeg);
+    for (int k = k0 + (int)threadIdx.x; k < k1; k += blockDim.x) {
+      const double4 r = shell_record(P, b, k);
+      S.rec[k - k0] = make_double4(far_g(E, k), r.y, r.z, r.w);
+    }
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  const int sl = t / 3, X = t - 3 * sl;          // my segment (local index) and absorber
+  const bool mine = live && sl < nmine;
+  const int kb = (seg0 + sl) * kFarSeg, ke = min(nedge, kb + kFarSeg);   // [kb, ke)
+  if (mine) {
+    double M[kFarNT];
+#pragma unroll
+    for (int n = 0; n < kFarNT; ++n) M[n] = 0.0;
+    double G = 1.0;
+    for (int k = kb; k < ke; ++k) {
+      const double4 r = S.rec[k - seg0 * kFarSeg];
+      const double D = X == 0 ? r.y : (X == 1 ? r.z : r.w);
+      far_step(M, r.x, D);
+      G = G * r.x;
+    }
+#pragma unroll
+    for (int n = 0; n < kFarNT; ++n) S.sB[(sl * 3 + X) * kFarNT + n] = M[n];
+    if (X == 0) {   // A_s[n] = G^(2n-1)
+      const double G2 = G * G;
+      double f = G > 0.0 ? 1.0 / G : 0.0;
+#pragma unroll
+      for (int n = 0; n < kFarNT; ++n) { S.sA[sl * kFarNT + n] = f; f = f * G2; }
+    }
+  }
+  __syncthreads();
+  if (t < 3 * kFarNT) {   // CTA composite over its segments
+    const int X2 = t / kFarNT, n = t - X2 * kFarNT;
+    double ca = 1.0, cb = 0.0;
+    for (int j = 0; j < nmine; ++j) {
+      const double a = S.sA[j * kFarNT + n];
+      cb = fma(cb, a, S.sB[(j * 3 + X2) * kFarNT + n]);
+      ca = ca * a;
+    }
+    S.cB[X2 * kFarNT + n] = cb;
+    if (X2 == 0) S.cA[n] = ca;
+  }
+  if (csize > 1) cg::this_cluster().sync(); else __syncthreads();
+  if (t < 3 * kFarNT) {   // carry into this CTA from the CTAs before it
+    const int X2 = t / kFarNT, n = t - X2 * kFarNT;
+    double ci = 0.0;
+    for (int c = 0; c < crank; ++c) {
+      const double *rA = cg::this_cluster().map_shared_rank(S.cA, c);
+      const double *rB = cg::this_cluster().map_shared_rank(S.cB, c);
+      ci = fma(ci, rA[n], rB[X2 * kFarNT + n]);
+    }
+    S.cin[X2 * kFarNT + n] = ci;
+  }
+  __syncthreads();
+  if (mine) {
+    double M[kFarNT];
+#pragma unroll
+    for (int n = 0; n < kFarNT; ++n) M[n] = S.cin[X * kFarNT + n];
+    for (int j = 0; j < sl; ++j) {
+#pragma unroll
+      for (int n = 0; n < kFarNT; ++n)
+        M[n] = fma(M[n], S.sA[j * kFarNT + n], S.sB[(j * 3 + X) * kFarNT + n]);
+    }
+    double *out = reinterpret_cast<double *>(far + ((size_t)b * nedge) * kFarNT) + X;
+    for (int k = kb; k < ke; ++k) {
+      const double4 r = S.rec[k - seg0 * kFarSeg];
+      const double D = X == 0 ? r.y : (X == 1 ? r.z : r.w);
+      far_step(M, r.x, D);
+#pragma unroll
+      for (int n = 0; n < kFarNT; ++n) out[((size_t)k * kFarNT + n) * 4] = kFarB[n] * M[n];
+    }
+  }
+  if (csize > 1) cg::this_cluster().sync();   // peers may still read cA / cB
+}
+
+// sum_{k<=K} s_k D_k for the three absorbers from table row K (E_K >= RATIO p)
+__device__ __forceinline__ void far_eval(const double4 *__restrict__ row, double u, double EK,
+                                         double (&out)[3]) {
+  double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+#pragma unroll
+  for (int n = kFarNT - 1; n >= 0; --n) {
+    const double4 c = row[n];
+    h0 = fma(h0, u, c.x);
+    h1 = fma(h1, u, c.y);
+    h2 = fma(h2, u, c.z);
+  }
+  out[0] = EK * h0; out[1] = EK * h1; out[2] = EK * h2;
+}
+
 struct ColAcc {
   double P0, P1, P2;     // running sum of s_k D_k (HI, HeI, HeII)
   double A0, A1, A2;     // its value before the own shell's edge (P_{il-1})
@@ -255,6 +431,14 @@ __device__ __forceinline__ void col_advance(ColAcc &a, const double4 *__restrict
 
 // the walk over shell edges kb .. ke of one ray pair (see sphere_ray_pair); [kA, kB] is
 // the warp-uniform window of edges that can be a lane's own-shell edge
+template <int U, bool SAFE>
+__device__ __forceinline__ void col_walk_from(ColAcc &a, const double4 *__restrict__ pk, int kb,
+                                              int ke, int kA, int kB, int il, double p2) {
+  col_advance<false, U, SAFE>(a, pk, kb, min(ke, kA - 1), il, p2);
+  col_advance<true, U, SAFE>(a, pk, max(kb, kA), min(ke, kB), il, p2);
+  col_advance<false, U, SAFE>(a, pk, max(kb, kB + 1), ke, il, p2);
+}
+
 template <int U, bool SAFE>
 __device__ __forceinline__ void col_walk(ColAcc &a, const double4 *__restrict__ pk, int kb, int ke,
                                          int kA, int kB, int il, double p2) {
@@ -317,7 +501,8 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
                                                 int cell_stride, int ip,
                                                 const double4 *__restrict__ pk, bool store,
                                                 int nchunk = 1, int chunk = 0,
-                                                double *part = nullptr) {
+                                                double *part = nullptr,
+                                                const double4 *__restrict__ far = nullptr) {
   const int Nl = P.Nl;
   const double *E = P.Edges + (size_t)b * (Nl + 1);
 
@@ -328,9 +513,11 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
 
   // m_for_ray (geometry.f90:61-71): smallest i >= 1 with E_i <= p, m = i-1.
   // E is non-increasing, so a bisection finds the same i as the linear search.
-  if (E[Nl] > p_ray) {  // reference would use an undefined m
+  const bool hollow = E[Nl] > p_ray;  // reference would use an undefined m
+  if (hollow) {
     atomicMax(&P.err[b], RB_ERR_RAY_GEOMETRY);
-    return;
+    if (far == nullptr) return;
+    store = false;   // (the far path is warp-collective: the lane stays, with an empty walk)
   }
   int lo = il + 1, hi = Nl;  // E_il >= r_ray >= p: the answer is > il
   if (E[il] <= p_ray) lo = 1;  // degenerate (zero-width shells): full search
@@ -338,7 +525,53 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
     const int mid = (lo + hi) >> 1;
     if (E[mid] <= p_ray) hi = mid; else lo = mid + 1;
   }
-  const int m = lo - 1;
+  const int m = hollow ? -1 : lo - 1;
+
+  if (far != nullptr) {
+    // ---- far field from the moment table, near field (p < E_k < RATIO p) walked.
+    // Kf = last edge k <= m with E_k >= RATIO p (-1: none).  Called by all 32 lanes.
+    const double rp = p_ray * RB_FAR_RATIO;
+    int Kf = -1;
+    if (m >= 0 && E[0] >= rp) {
+      int a0 = 0, a1 = m;
+      while (a0 < a1) {
+        const int mid = (a0 + a1 + 1) >> 1;
+        if (E[mid] >= rp) a0 = mid; else a1 = mid - 1;
+      }
+      Kf = a0;
+    }
+    const double4 *tab = far + (size_t)b * (Nl + 1) * kFarNT;
+    ColAcc a;
+    a.P0 = a.P1 = a.P2 = 0.0;
+    a.A0 = a.A1 = a.A2 = 0.0;
+    a.s_il = a.s_il1 = 0.0;
+    if (Kf >= 0) {
+      double f[3];
+      far_eval(tab + (size_t)Kf * kFarNT, p2 / pk[Kf].x, E[Kf], f);
+      a.P0 = f[0]; a.P1 = f[1]; a.P2 = f[2];
+      if (il <= Kf) {   // the own shell lies in the far zone: its snapshot from the table
+        a.s_il = sqrt_pos<true>(pk[il].x - p2);
+        if (il + 1 <= Kf) a.s_il1 = sqrt_pos<true>(pk[il + 1].x - p2);
+        if (il >= 1) {
+          far_eval(tab + (size_t)(il - 1) * kFarNT, p2 / pk[il - 1].x, E[il - 1], f);
+          a.A0 = f[0]; a.A1 = f[1]; a.A2 = f[2];
+        }
+      }
+    }
+    // lanes start at different edges: the warp walks from the smallest start with the
+    // others masked until their own (a short ragged zone), then all lanes together
+    const int kmin = __reduce_min_sync(0xffffffffu, Kf), kmax = __reduce_max_sync(0xffffffffu, Kf);
+    for (int k = kmin + 1; k <= kmax; ++k) {
+      const double4 rec = pk[k];
+      if (k > Kf && k <= m) col_close<true>(a, rec, sqrt_pos<true>(rec.x - p2), k, il);
+    }
+    const int kA2 = il_w0, kB2 = il_w0 + 31 * cell_stride + 1;
+    col_walk_from<U, false>(a, pk, kmax + 1, m, kA2, kB2, il, p2);
+    if (!store) return;
+    const double Pm2[3] = {a.P0, a.P1, a.P2}, Pa2[3] = {a.A0, a.A1, a.A2};
+    store_ray_pair(P, b, il, ip, m, mu, Pm2, Pa2, a.s_il, a.s_il1);
+    return;
+  }
 
   // shell edges of this call: k = kb .. ke, all of 0 .. m without chunks
   int kb = 0, ke = m;
@@ -407,7 +640,7 @@ template <int THREADS, int U, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_sphere_columns_smem(PlanDev P, int cell_start, int cell_stride, int n_local,
                       const unsigned *__restrict__ items, int n_items, int *work, int nchunk,
-                      double *__restrict__ part) {
+                      double *__restrict__ part, const double4 *__restrict__ far) {
   const int b = blockIdx.y;
   if (!P.active[b]) return;
   extern __shared__ double4 s_pk[];
@@ -434,7 +667,7 @@ k_sphere_columns_smem(PlanDev P, int cell_start, int cell_stride, int n_local,
       pp = part + ((((size_t)b * ((P.Nmu + 1) / 2) + ip) * n_local + (valid ? j : 0)) * nchunk +
                    chunk) * kPartStride;
     sphere_ray_pair<U>(P, b, il, cell_start + jw * cell_stride, cell_stride, ip, s_pk, valid,
-                       nchunk, chunk, pp);
+                       nchunk, chunk, pp, far);
     it = __shfl_sync(0xffffffffu, nxt, 0);
   }
 }

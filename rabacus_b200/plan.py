@@ -122,6 +122,11 @@ class Plan(object):
                                          C.c_int(1 if graphs else 0), C.byref(ms)))
         return ms.value
 
+    def set_far_field(self, on):
+        """Diagnostic A/B switch of THIS plan: SphereBgnd columns with (default) / without
+        the far-field moment table."""
+        check(lib().rbi_plan_set_far_field(self._h, C.c_int(1 if on else 0)))
+
     def set_libm_pow(self, on):
         """Diagnostic A/B switch of THIS plan: rate fits through libdevice pow()."""
         check(lib().rbi_plan_set_libm_pow(self._h, C.c_int(1 if on else 0)))

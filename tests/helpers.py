@@ -35,7 +35,7 @@ def run_oracle(orc, cfg, tol=1e-4, max_sweeps=0, order=None, thin=False, flavour
     return res
 
 
-def run_gpu(cfg, tol=1e-4, max_sweeps=0, thin=False, libm_pow=False):
+def run_gpu(cfg, tol=1e-4, max_sweeps=0, thin=False, libm_pow=False, far_field=None):
     """Through the plan API of the C ABI (same code path as the one-shot entry
     points, plus max_sweeps for sweep-level parity)."""
     Nl, Nnu = cfg["nH"].size, cfg["E_eV"].size
@@ -48,6 +48,8 @@ def run_gpu(cfg, tol=1e-4, max_sweeps=0, thin=False, libm_pow=False):
     plan.upload()
     if libm_pow:
         plan.set_libm_pow(True)
+    if far_field is not None:
+        plan.set_far_field(far_field)
     if thin:
         plan.thin()
         plan.sync()

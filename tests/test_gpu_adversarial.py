@@ -131,3 +131,33 @@ def test_shells_without_gas(orc):
     assert e.value.code == 2                       # RB_ERR_MAX_ITER_OUTER
     with pytest.raises(orc.OracleError):
         run_oracle(orc, cfg)
+
+
+@pytest.mark.parametrize("kind", ("uniform",) + KINDS)
+@pytest.mark.parametrize("shape", [(72, 48, 8), (300, 32, 33), (40, 16, 2), (1024, 32, 16)])
+def test_far_field_columns_equal_the_full_walk(orc, kind, shape):
+    """The far-field moment table (rb_kernels.cuh: k_far_moments, far_eval) against the walk
+    over every shell edge (the round-1 column kernel, per-plan switch in rb_internal.h): the
+    same sums, associated differently.  Ray optical depths feed exp(-tau): the rates after
+    sweeps 1 and 3 must agree to 1e-12, and each arm separately with the oracle."""
+    Nl, Nnu, Nmu = shape
+    cfg = base_config("sphere_bgnd", Nl=Nl, Nnu=Nnu, Nmu=Nmu)
+    if kind != "uniform":
+        cfg = adversarial(cfg, kind, seed=Nl)
+    for sweeps in (1, 3):
+        a = run_gpu(cfg, max_sweeps=sweeps, far_field=True)
+        b = run_gpu(cfg, max_sweeps=sweeps, far_field=False)
+        worst = 0.0
+        for n in CHECKED:
+            if n.endswith("_src"):
+                with np.errstate(all="ignore"):
+                    r = np.where(a[n] == b[n], 0.0, np.abs(a[n] - b[n]) / np.abs(b[n]))
+                worst = max(worst, float(np.nanmax(r)))
+        _report("far vs full walk %s %dx%dx%d %d sweeps" % (kind, Nl, Nnu, Nmu, sweeps),
+                dict({k: 0.0 for k in CHECKED}, H1i_src=worst))
+        assert worst <= 1e-12, (kind, shape, sweeps, worst)
+    if Nl <= 300:
+        o = run_oracle(orc, cfg, max_sweeps=3)
+        for arm in (a, b):
+            w, bad = compare(arm, o)
+            assert not bad, bad
