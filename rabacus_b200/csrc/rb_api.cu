@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <vector>
 
 #include "rb_rec.cuh"
@@ -205,9 +207,84 @@ static void build_spec_table(int geom, const double *E, const double *shape, int
 }
 
 // ---------------------------------------------------------------------------
+// Memo tables of the temperature bisection (TeqTab, rb_ion.cuh): one per (device, case-A
+// fraction, libm flag, depth), shared by every plan and single-zone call of the process;
+// built on first use (k_teq_table, 2^depth + 1 evaluations of the rate fits) and kept --
+// the four most recently used ones -- until rb_cache_clear().
+// Depth: RB_TEQ_DEPTH (0 disables the memo, default 18: 32 MiB, L2-resident hot levels).
+// ---------------------------------------------------------------------------
+struct TeqTable {
+  int dev = 0, depth = 0, libm = 0;
+  double fcA = 0.0;
+  double *rows = nullptr;
+  ~TeqTable() {
+    if (rows) {
+      int prev = -1;
+      cudaGetDevice(&prev);
+      cudaSetDevice(dev);
+      cudaFree(rows);
+      if (prev >= 0) cudaSetDevice(prev);
+      cudaGetLastError();
+    }
+  }
+};
+static std::mutex g_teq_mu;
+static std::vector<std::shared_ptr<TeqTable>> g_teq;   // most recently used last
+
+static int teq_depth_wanted() {
+  const char *e = getenv("RB_TEQ_DEPTH");
+  int d = e ? atoi(e) : 18;
+  return std::max(0, std::min(d, 24));
+}
+
+// the table of (current device, fcA, libm); nullptr when disabled or out of memory (the
+// solvers then evaluate the fits at every probe, with identical results)
+static std::shared_ptr<TeqTable> teq_table_get(double fcA, int libm) {
+  const int depth = teq_depth_wanted();
+  if (depth < 1) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  std::lock_guard<std::mutex> lk(g_teq_mu);
+  for (size_t i = 0; i < g_teq.size(); ++i) {
+    const auto &t = g_teq[i];
+    if (t->dev == dev && t->depth == depth && t->libm == (libm != 0) &&
+        memcmp(&t->fcA, &fcA, sizeof(double)) == 0) {
+      auto hit = t;
+      g_teq.erase(g_teq.begin() + i);
+      g_teq.push_back(hit);
+      return hit;
+    }
+  }
+  auto t = std::make_shared<TeqTable>();
+  t->dev = dev; t->depth = depth; t->libm = libm != 0; t->fcA = fcA;
+  const size_t nrows = ((size_t)1 << depth) + 1;
+  if (cudaMalloc((void **)&t->rows, nrows * kTeqStride * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    t->rows = nullptr;
+    return nullptr;
+  }
+  k_teq_table<<<(unsigned)((nrows + 127) / 128), 128>>>(t->rows, depth, fcA, t->libm);
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  g_teq.push_back(t);
+  if (g_teq.size() > 4) g_teq.erase(g_teq.begin());
+  return t;
+}
+static TeqTab teq_tab_of(const std::shared_ptr<TeqTable> &t) {
+  TeqTab tb;
+  tb.rows = t ? t->rows : nullptr;
+  tb.depth = t ? t->depth : 0;
+  tb.pad_ = 0;
+  return tb;
+}
+
+// ---------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------
 struct rb_plan {
+  std::shared_ptr<TeqTable> teq;   // find_Teq: memo of the rate fits (bound by plan_bind_teq)
   rb_plan_desc d;
   int dev = 0;   // CUDA device the plan lives on (every entry point switches to it)
   int Ndir;
@@ -290,6 +367,17 @@ struct rb_plan {
 };
 
 static size_t cells(const rb_plan *p) { return (size_t)p->d.n_problems * p->d.Nl; }
+
+// find_Teq plans: point P.teq at the memo table of the plan's current (fcA, libm flag).
+// Called at the start of every solve (rb_plan_thin): both can change on a cached plan.
+// P is part of the graph key, so captured sweeps follow.
+static void plan_bind_teq(rb_plan *p) {
+  if (!p->d.i_find_Teq) { p->teq.reset(); p->P.teq = teq_tab_of(nullptr); return; }
+  if (p->teq && p->teq->libm == (p->P.libm_pow != 0) && p->teq->depth == teq_depth_wanted() &&
+      memcmp(&p->teq->fcA, &p->P.fcA, sizeof(double)) == 0) return;
+  p->teq = teq_table_get(p->P.fcA, p->P.libm_pow);
+  p->P.teq = teq_tab_of(p->teq);
+}
 
 // Every plan entry point runs on the plan's device and leaves the caller's current device
 // as it found it (a process may hold plans on several GPUs, or share the thread with torch).
@@ -592,6 +680,7 @@ extern "C" int rb_plan_upload(rb_plan *p) {
   PLAN_DEV(p);
   const size_t B = p->d.n_problems, Nl = p->d.Nl, Nnu = p->d.Nnu, NC = B * Nl;
   cudaStream_t s = p->stream;
+  plan_bind_teq(p);
   CK(cudaMemcpyAsync(p->dEdges, p->hEdges, B * (Nl + 1) * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(p->dnH, p->hnH, NC * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(p->dnHe, p->hnHe, NC * 8, cudaMemcpyHostToDevice, s));
@@ -620,6 +709,7 @@ extern "C" int rb_plan_thin(rb_plan *p) {
   if (!p) return RB_ERR_BAD_ARG;
   PLAN_DEV(p);
   const int Nl = p->d.Nl, B = p->d.n_problems;
+  plan_bind_teq(p);
   // one cell per thread over a cluster of up to 8 CTAs of 512 threads; two cells per
   // thread beyond 4096 cells
   int cs = 1;
@@ -1696,6 +1786,8 @@ extern "C" void rb_cache_clear(void) {
     all.swap(g_cache);
   }
   for (rb_plan *p : all) rb_plan_destroy(p);
+  std::lock_guard<std::mutex> lk(g_teq_mu);
+  g_teq.clear();   // tables still bound to live plans stay alive through their shared_ptr
 }
 
 static int solve_one(int geom, const double *Edges, const double *nH, const double *nHe,
@@ -1973,6 +2065,19 @@ extern "C" void rbi_host_coefficients(double T, double fcA_H2, double fcA_He2, d
   for (int q = 0; q < 16; ++q) out16[q] = v[q];
 }
 
+extern "C" int rbi_teq_table_fetch(double fcA, int row0, int n, double *out16, int *depth) {
+  if (!out16 || !depth || row0 < 0 || n < 1) return RB_ERR_BAD_ARG;
+  int rc = need_device();
+  if (rc) return rc;
+  std::shared_ptr<TeqTable> t = teq_table_get(fcA, 0);
+  if (!t) return RB_ERR_UNSUPPORTED;
+  *depth = t->depth;
+  if ((long long)row0 + n > ((long long)1 << t->depth) + 1) return RB_ERR_BAD_ARG;
+  CK(cudaMemcpy(out16, t->rows + (size_t)row0 * kTeqStride, (size_t)n * kTeqStride * 8,
+                cudaMemcpyDeviceToHost));
+  return RB_OK;
+}
+
 extern "C" int rbi_plan_set_far_field(rb_plan *p, int on) {
   if (!p) return RB_ERR_BAD_ARG;
   if (on && !p->dfar) return RB_ERR_UNSUPPORTED;
@@ -2092,9 +2197,9 @@ extern "C" int rb_solve_pce(const double *nH, const double *nHe, const double *r
   if (lockstep) {
     rc = launch_lockstep(nn, [&](int cpt, int threads) {
       switch (cpt) {
-        case 1: k_zone_lockstep<1><<<1, threads>>>(in.d, nn, 0, 0, tol, out.d, derr, 0); break;
-        case 4: k_zone_lockstep<4><<<1, threads>>>(in.d, nn, 0, 0, tol, out.d, derr, 0); break;
-        default: k_zone_lockstep<16><<<1, threads>>>(in.d, nn, 0, 0, tol, out.d, derr, 0);
+        case 1: k_zone_lockstep<1><<<1, threads>>>(in.d, nn, 0, 0, tol, out.d, derr, 0, TeqTab{nullptr, 0, 0}); break;
+        case 4: k_zone_lockstep<4><<<1, threads>>>(in.d, nn, 0, 0, tol, out.d, derr, 0, TeqTab{nullptr, 0, 0}); break;
+        default: k_zone_lockstep<16><<<1, threads>>>(in.d, nn, 0, 0, tol, out.d, derr, 0, TeqTab{nullptr, 0, 0});
       }
     });
     if (rc) return rc;
@@ -2119,11 +2224,16 @@ extern "C" int rb_solve_pcte(const double *nH, const double *nHe, const double *
   if (nn < 1) return RB_ERR_BAD_ARG;
   int rc = need_device();
   if (rc) return rc;
-  if (lockstep) {  // the lock-step kernel carries one case-A triple for the batch
-    for (int i = 1; i < nn; ++i)
-      if (fcA_H2[i] != fcA_H2[0] || fcA_He2[i] != fcA_He2[0] || fcA_He3[i] != fcA_He3[0])
-        return RB_ERR_UNSUPPORTED;
-  }
+  bool uniform = true;
+  for (int i = 1; i < nn && uniform; ++i)
+    uniform = fcA_H2[i] == fcA_H2[0] && fcA_He2[i] == fcA_He2[0] && fcA_He3[i] == fcA_He3[0];
+  // the lock-step kernel carries one case-A triple for the batch
+  if (lockstep && !uniform) return RB_ERR_UNSUPPORTED;
+  // one case-A fraction for all zones and ions (the usual call): the memo of the rate fits
+  // over the temperature bisection tree applies (rb_ion.cuh: TeqTab)
+  std::shared_ptr<TeqTable> tq;
+  if (uniform && fcA_He2[0] == fcA_H2[0] && fcA_He3[0] == fcA_H2[0]) tq = teq_table_get(fcA_H2[0], 0);
+  const TeqTab tb = teq_tab_of(tq);
   DevBuf in, out;
   const double *f[11] = {nH, nHe, H1i, He1i, He2i, H1h, He1h, He2h, fcA_H2, fcA_He2, fcA_He3};
   if ((rc = upload_fields(in, f, 11, nn))) return rc;
@@ -2134,15 +2244,15 @@ extern "C" int rb_solve_pcte(const double *nH, const double *nHe, const double *
   if (lockstep) {
     rc = launch_lockstep(nn, [&](int cpt, int threads) {
       switch (cpt) {
-        case 1: k_zone_lockstep<1><<<1, threads>>>(in.d, nn, z, Hz, tol, out.d, derr, 1); break;
-        case 4: k_zone_lockstep<4><<<1, threads>>>(in.d, nn, z, Hz, tol, out.d, derr, 1); break;
-        default: k_zone_lockstep<16><<<1, threads>>>(in.d, nn, z, Hz, tol, out.d, derr, 1);
+        case 1: k_zone_lockstep<1><<<1, threads>>>(in.d, nn, z, Hz, tol, out.d, derr, 1, tb); break;
+        case 4: k_zone_lockstep<4><<<1, threads>>>(in.d, nn, z, Hz, tol, out.d, derr, 1, tb); break;
+        default: k_zone_lockstep<16><<<1, threads>>>(in.d, nn, z, Hz, tol, out.d, derr, 1, tb);
       }
     });
     if (rc) return rc;
   } else {
     ZoneTimer zt;
-    k_zone_pcte<<<(nn + 127) / 128, 128>>>(in.d, nn, z, Hz, tol, out.d, derr);
+    k_zone_pcte<<<(nn + 127) / 128, 128>>>(in.d, nn, z, Hz, tol, out.d, derr, tb);
     zt.stop();
   }
   CK(cudaGetLastError());

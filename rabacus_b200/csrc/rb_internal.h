@@ -47,6 +47,12 @@ int rbi_plan_bench_steps(rb_plan *plan, int steps, size_t flush_bytes, int graph
  * (rb_kernels.cuh "Far-field evaluation"); RB_ERR_UNSUPPORTED if the plan has no table. */
 int rbi_plan_set_far_field(rb_plan *plan, int on);
 
+/* Rows [row0, row0 + n) of the memo table of the rate fits over the temperature bisection
+ * tree (rb_ion.cuh: TeqTab) for case-A fraction fcA on the current device, built on demand:
+ * out16[n][16] = {6 kchem, 8 kcool, bremss, T}; *depth = the table's depth (row 2^depth is
+ * TMAX).  RB_ERR_UNSUPPORTED when the memo is disabled (RB_TEQ_DEPTH=0). */
+int rbi_teq_table_fetch(double fcA, int row0, int n, double *out16, int *depth);
+
 /* device time [ms] of the kernel of this thread's last rb_solve_pce / rb_solve_pcte call
  * (scalar mode), for the single-zone batch line of bench.py */
 double rbi_last_zone_kernel_ms(void);

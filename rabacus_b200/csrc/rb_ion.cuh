@@ -165,11 +165,106 @@ RB_HDN int solve_pce(double nH, double nHe, const rb_kchem_t &k, double H1i,
   return ION_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// Memo of the rate coefficients over the temperatures solve_pcte can probe.
+//
+// solve_pcte_s (ion_solver.f90:796-850) always probes TFLOOR and TMAX, starts its bisection
+// at 10^((log10 TFLOOR + log10 TMAX)/2) and halves: whatever the cell, the d-th probe
+// temperature is one of 2^(d-1) fixed doubles -- the nodes of one binary tree (heap index:
+// root = 1, child of n = 2n after a negative dudT, 2n + 1 otherwise).  For the first
+// `depth` levels the 16 coefficients of get_kchem_s + get_kcool_s (they depend on T and the
+// plan's case-A fractions only) are evaluated ONCE per (fcA, libm flag) by k_teq_table with
+// the very device function the solvers call, so a hit returns the bits the solver would have
+// computed; the row's key is the temperature itself, compared bit for bit, so a row can never
+// be used for another temperature (a miss evaluates the fits as before).
+// rows: [2^depth + 1][16] = {6 kchem, 8 kcool (recH2 .. cecHe2), bremss, T};
+// row 0 = TFLOOR, rows 1 .. 2^depth - 1 = tree nodes, row 2^depth = TMAX.
+// ---------------------------------------------------------------------------
+constexpr int kTeqStride = 16;
+struct TeqTab {
+  const double *rows;   // nullptr: no table (host code, single-zone API with per-zone fcA)
+  int depth, pad_;
+};
+RB_HD int teq_rows(const TeqTab &tb) { return tb.rows ? (1 << tb.depth) : 0; }   // = row of TMAX
+// heap index of the next probe (-1 once the path leaves the table)
+RB_HD int teq_child(const TeqTab &tb, int node, bool neg) {
+  if (node <= 0 || node >= (1 << 29)) return -1;
+  const int c = 2 * node + (neg ? 0 : 1);
+  return c < teq_rows(tb) ? c : -1;
+}
+RB_HD bool teq_hit(const TeqTab &tb, int row, double T, const double *&r) {
+  if (row < 0 || tb.rows == nullptr || row > teq_rows(tb)) return false;
+  r = tb.rows + (size_t)row * kTeqStride;
+#ifdef __CUDA_ARCH__
+  return __ldg(r + 15) == T;
+#else
+  return r[15] == T;
+#endif
+}
+RB_HD void teq_load_chem(const double *r, rb_kchem_t &kc) {
+#ifdef __CUDA_ARCH__
+  const double2 a = __ldg(reinterpret_cast<const double2 *>(r));
+  const double2 b = __ldg(reinterpret_cast<const double2 *>(r) + 1);
+  const double2 c = __ldg(reinterpret_cast<const double2 *>(r) + 2);
+  kc.reH2 = a.x; kc.reHe2 = a.y; kc.reHe3 = b.x; kc.ciH1 = b.y; kc.ciHe1 = c.x; kc.ciHe2 = c.y;
+#else
+  kc.reH2 = r[0]; kc.reHe2 = r[1]; kc.reHe3 = r[2]; kc.ciH1 = r[3]; kc.ciHe1 = r[4]; kc.ciHe2 = r[5];
+#endif
+}
+RB_HD void teq_load_cool(const double *r, rb_kcool_t &kl) {
+#ifdef __CUDA_ARCH__
+  const double2 a = __ldg(reinterpret_cast<const double2 *>(r) + 3);
+  const double2 b = __ldg(reinterpret_cast<const double2 *>(r) + 4);
+  const double2 c = __ldg(reinterpret_cast<const double2 *>(r) + 5);
+  const double2 d = __ldg(reinterpret_cast<const double2 *>(r) + 6);
+  const double e = __ldg(r + 14);
+  kl.recH2 = a.x; kl.recHe2 = a.y; kl.recHe3 = b.x; kl.cicH1 = b.y; kl.cicHe1 = c.x;
+  kl.cicHe2 = c.y; kl.cecH1 = d.x; kl.cecHe2 = d.y; kl.bremss = e;
+#else
+  kl.recH2 = r[6]; kl.recHe2 = r[7]; kl.recHe3 = r[8]; kl.cicH1 = r[9]; kl.cicHe1 = r[10];
+  kl.cicHe2 = r[11]; kl.cecH1 = r[12]; kl.cecHe2 = r[13]; kl.bremss = r[14];
+#endif
+  kl.compton = 5.65e-36;   // chem_cool_rates.f90:200 (a constant)
+}
+RB_HD void teq_store(double *r, double T, const rb_kchem_t &kc, const rb_kcool_t &kl) {
+  r[0] = kc.reH2; r[1] = kc.reHe2; r[2] = kc.reHe3; r[3] = kc.ciH1; r[4] = kc.ciHe1; r[5] = kc.ciHe2;
+  r[6] = kl.recH2; r[7] = kl.recHe2; r[8] = kl.recHe3; r[9] = kl.cicH1; r[10] = kl.cicHe1;
+  r[11] = kl.cicHe2; r[12] = kl.cecH1; r[13] = kl.cecHe2; r[14] = kl.bremss; r[15] = T;
+}
+// get_kchem_s + get_kcool_s / get_kchem_s / get_kcool_s at T, from row `row` when its key is T
+RB_HD void kchem_kcool_memo(const TeqTab &tb, int row, double T, const CaseA &fc,
+                            rb_kchem_t &kc, rb_kcool_t &kl) {
+  const double *r;
+  if (teq_hit(tb, row, T, r)) { teq_load_chem(r, kc); teq_load_cool(r, kl); return; }
+  get_kchem_kcool(T, fc.H2, fc.He2, fc.He3, kc, kl, fc.libm);
+}
+RB_HD rb_kchem_t kchem_memo(const TeqTab &tb, int row, double T, const CaseA &fc) {
+  const double *r;
+  rb_kchem_t kc;
+  if (teq_hit(tb, row, T, r)) { teq_load_chem(r, kc); return kc; }
+  return get_kchem(T, fc.H2, fc.He2, fc.He3, fc.libm);
+}
+RB_HD rb_kcool_t kcool_memo(const TeqTab &tb, int row, double T, const CaseA &fc) {
+  const double *r;
+  rb_kcool_t kl;
+  if (teq_hit(tb, row, T, r)) { teq_load_cool(r, kl); return kl; }
+  return get_kcool(T, fc.H2, fc.He2, fc.He3, fc.libm);
+}
+// the bisection's first temperature (ion_solver.f90:814-815); one function, so that the
+// solvers and the table builder hold the same bits
+RB_HDN double teq_root_T() {
+  double T = (log10(RB_TFLOOR) + log10(RB_TMAX)) * 0.5;
+  T = pow(10.0, T);
+  return T;
+}
+
 RB_HDN int get_dudT(double nH, double nHe, double T, const PhotoRates &p,
-                   double z, double Hz, const CaseA &fc, double tol, double &dudT) {
+                   double z, double Hz, const CaseA &fc, double tol, double &dudT,
+                   const TeqTab &tb, int row) {
   rb_kchem_t kc;
   rb_kcool_t kl;
-  get_kchem_kcool(T, fc.H2, fc.He2, fc.He3, kc, kl, fc.libm);
+  kchem_kcool_memo(tb, row, T, fc, kc, kl);
   rb_frac_t x;
   const int rc = solve_pce(nH, nHe, kc, p.H1i, p.He1i, p.He2i, tol, x);
   if (rc) return rc;
@@ -184,10 +279,11 @@ RB_HDN int get_dudT(double nH, double nHe, double T, const PhotoRates &p,
 // bisection stops at a temperature that has been probed, these ARE the final
 // fractions (solve_pcte's last statement re-solves at that same T).
 RB_HDN int probe_T(double nH, double nHe, double T, const PhotoRates &p, double z,
-                   double Hz, const CaseA &fc, double tol, double &dudT, rb_frac_t &x) {
+                   double Hz, const CaseA &fc, double tol, double &dudT, rb_frac_t &x,
+                   const TeqTab &tb, int row) {
   rb_kchem_t kc;
   rb_kcool_t kl;
-  get_kchem_kcool(T, fc.H2, fc.He2, fc.He3, kc, kl, fc.libm);
+  kchem_kcool_memo(tb, row, T, fc, kc, kl);
   const int rc = solve_pce(nH, nHe, kc, p.H1i, p.He1i, p.He2i, tol, x);
   if (rc) return rc;
   const double heat =
@@ -215,27 +311,27 @@ RB_HD void tbisect_step(TBisect &s, bool neg) {
 
 RB_HDN int solve_pcte(double nH, double nHe, const PhotoRates &p, double z,
                      double Hz, const CaseA &fc, double tol, rb_frac_t &x,
-                     double &Tout) {
+                     double &Tout, const TeqTab &tb) {
   double Tleft = RB_TFLOOR, Tright = RB_TMAX;
   double dudT, dudTmin, dudTmax;
-  int rc = get_dudT(nH, nHe, Tleft, p, z, Hz, fc, tol, dudTmin);
+  int rc = get_dudT(nH, nHe, Tleft, p, z, Hz, fc, tol, dudTmin, tb, 0);
   if (rc) return rc;
   if (dudTmin < 0.0) {  // :782-794: equilibrium below the floor
-    const rb_kchem_t kc = get_kchem(Tleft, fc.H2, fc.He2, fc.He3, fc.libm);
+    const rb_kchem_t kc = kchem_memo(tb, 0, Tleft, fc);
     rc = solve_pce(nH, nHe, kc, p.H1i, p.He1i, p.He2i, tol, x);
     Tout = Tleft;
     return rc;
   }
-  rc = get_dudT(nH, nHe, Tright, p, z, Hz, fc, tol, dudTmax);
+  rc = get_dudT(nH, nHe, Tright, p, z, Hz, fc, tol, dudTmax, tb, teq_rows(tb));
   if (rc) return rc;
   if (dudTmin < 0.0 || dudTmax > 0.0) return ION_ERR_T_NOT_BRACKETED;
 
-  double T = (log10(Tleft) + log10(Tright)) * 0.5;
-  T = pow(10.0, T);
+  double T = teq_root_T();   // :814-815
+  int node = tb.rows ? 1 : -1;   // heap index of T in the bisection tree (memo row)
   double err = 1.7976931348623157e308;
   int iter = 0;
   while (err > tol) {
-    rc = get_dudT(nH, nHe, T, p, z, Hz, fc, tol, dudT);
+    rc = get_dudT(nH, nHe, T, p, z, Hz, fc, tol, dudT, tb, node);
     if (rc) return rc;
     const double Told = T;
     if (dudT < 0.0) {
@@ -245,11 +341,12 @@ RB_HDN int solve_pcte(double nH, double nHe, const PhotoRates &p, double z,
       Tleft = T;
       T = (T + Tright) * 0.5;
     }
+    node = teq_child(tb, node, dudT < 0.0);
     err = fabs(1.0 - T / Told);
     iter = iter + 1;
     if (iter > RB_ION_MAX_ITER) return ION_ERR_MAX_ITER_PCTE;
   }
-  const rb_kchem_t kc = get_kchem(T, fc.H2, fc.He2, fc.He3, fc.libm);
+  const rb_kchem_t kc = kchem_memo(tb, node, T, fc);
   rc = solve_pce(nH, nHe, kc, p.H1i, p.He1i, p.He2i, tol, x);
   if (rc) return rc;
   zero_absent_species(nH, nHe, x);

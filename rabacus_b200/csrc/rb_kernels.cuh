@@ -74,6 +74,8 @@ struct PlanDev {
   int *active, *iters, *err;            // [B]
   unsigned long long *resid_bits;       // [B]
   int *nactive;                         // [kSlots] active-problem count per sweep slot
+  TeqTab teq;              // find_Teq: memo of the rate coefficients over the temperature
+                           // bisection tree (rb_ion.cuh), shared by every cell and sweep
 };
 
 // Cell-sharded multi-GPU exchange over peer memory (NVLink / NVSwitch), SURVEY 8e.
@@ -1048,7 +1050,7 @@ k_cell_solve(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_local)
   int rc;
   if (P.find_Teq) {
     const CaseA fc = {P.fcA, P.fcA, P.fcA, P.libm_pow};
-    rc = solve_pcte(nH, nHe, p, P.zHz[2 * b], P.zHz[2 * b + 1], fc, P.tol_inner, x, T);
+    rc = solve_pcte(nH, nHe, p, P.zHz[2 * b], P.zHz[2 * b + 1], fc, P.tol_inner, x, T, P.teq);
   } else {
     // get_kchem(T) of sphere_bgnd.f90:897-899: T is fixed, the coefficients were stored
     // by k_thin_state
@@ -1231,9 +1233,10 @@ k_cell_solve_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_l
 
   TBisect root;
   root.Tl = RB_TFLOOR; root.Tr = RB_TMAX;
-  root.T = (log10(root.Tl) + log10(root.Tr)) * 0.5;   // :814-815
-  root.T = pow(10.0, root.T);
+  root.T = teq_root_T();   // :814-815
   root.err = 1.7976931348623157e308;
+  const TeqTab tb = P.teq;
+  int groot = tb.rows ? 1 : -1;   // heap index of root.T in the whole bisection tree (memo row)
   int rc = 0, iter = 0, src = 0;   // src: lane of the group holding the answer
   bool done = false;
   rb_frac_t x;
@@ -1251,7 +1254,15 @@ k_cell_solve_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_l
       for (int i = depth - 1; i >= 0; --i) tbisect_step(mine, ((node >> i) & 1) == 0);
     }
     const double myT = (first && sub == 0) ? root.Tl : (first && sub == 1) ? root.Tr : mine.T;
-    int prc = probe_T(nH, nHe, myT, p, z, Hz, fc, tol, dudT, x);
+    int row = -1;   // memo row of myT: the bracket rows, or my node below the round's root
+    if (first && sub < 2) {
+      row = sub == 0 ? 0 : teq_rows(tb);
+    } else if (groot > 0) {
+      const int depth = 31 - __clz(node);
+      const long long gl = ((long long)groot << depth) | (long long)(node - (1 << depth));
+      if (gl < (long long)teq_rows(tb)) row = (int)gl;
+    }
+    int prc = probe_T(nH, nHe, myT, p, z, Hz, fc, tol, dudT, x, tb, row);
     // ---- brackets (round 0): :771-812
     if (first) {
       const double dmin = __shfl_sync(mask, dudT, gbase + 0);
@@ -1276,6 +1287,7 @@ k_cell_solve_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_l
       if (r) { rc = r; done = true; break; }
       const bool neg = d < 0.0;
       tbisect_step(root, neg);
+      groot = teq_child(tb, groot, neg);
       n = 2 * n + (neg ? 0 : 1);
       iter = iter + 1;
       if (iter > RB_ION_MAX_ITER) { rc = ION_ERR_MAX_ITER_PCTE; done = true; }
@@ -1598,17 +1610,18 @@ template <int CPT, class ANY>
 __host__ __device__ int dudT_lockstep(const double (&nH)[CPT], const double (&nHe)[CPT],
                              const double (&T)[CPT], const PhotoRates (&p)[CPT],
                              const rb_flag_t (&valid)[CPT], double z, double Hz,
-                             const CaseA &fc, double tol, double (&dudT)[CPT], ANY &block_any) {
+                             const CaseA &fc, double tol, double (&dudT)[CPT], ANY &block_any,
+                             const TeqTab &tb, const int (&row)[CPT]) {
   rb_kchem_t kc[CPT];
   rb_frac_t x[CPT];
 RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i)
-    if (valid[i]) kc[i] = get_kchem(T[i], fc.H2, fc.He2, fc.He3, fc.libm);
+    if (valid[i]) kc[i] = kchem_memo(tb, row[i], T[i], fc);
   const int rc = pce_lockstep<CPT>(nH, nHe, kc, p, valid, tol, x, block_any);
 RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) {
     if (valid[i]) {
-      const rb_kcool_t kl = get_kcool(T[i], fc.H2, fc.He2, fc.He3, fc.libm);
+      const rb_kcool_t kl = kcool_memo(tb, row[i], T[i], fc);
       const double heat = get_heat(nH[i], nHe[i], p[i].H1h, p[i].He1h, p[i].He2h,
                                    x[i].xH1, x[i].xHe1, x[i].xHe2);
       const double cool = get_cool(nH[i], nHe[i], T[i], kl, x[i], z, Hz);
@@ -1625,26 +1638,31 @@ template <int CPT, class ANY>
 __host__ __device__ int pcte_lockstep(const double (&nH)[CPT], const double (&nHe)[CPT],
                              const PhotoRates (&p)[CPT], const rb_flag_t (&valid)[CPT],
                              double z, double Hz, const CaseA &fc, double tol,
-                             rb_frac_t (&x)[CPT], double (&T)[CPT], ANY &block_any) {
+                             rb_frac_t (&x)[CPT], double (&T)[CPT], ANY &block_any,
+                             const TeqTab &tb) {
   double Tleft[CPT], Tright[CPT], dudT[CPT], err[CPT];
   rb_flag_t floor_[CPT];
+  int node[CPT];   // memo row of the temperature in flight (rb_ion.cuh: TeqTab)
   int rc = 0, r;
 RB_LS_UNROLL
-  for (int i = 0; i < CPT; ++i) { Tleft[i] = RB_TFLOOR; Tright[i] = RB_TMAX; }
-  r = dudT_lockstep<CPT>(nH, nHe, Tleft, p, valid, z, Hz, fc, tol, dudT, block_any);
+  for (int i = 0; i < CPT; ++i) { Tleft[i] = RB_TFLOOR; Tright[i] = RB_TMAX; node[i] = 0; }
+  r = dudT_lockstep<CPT>(nH, nHe, Tleft, p, valid, z, Hz, fc, tol, dudT, block_any, tb, node);
   if (r) rc = r;
 RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) floor_[i] = valid[i] && (dudT[i] < 0.0);
-  r = dudT_lockstep<CPT>(nH, nHe, Tright, p, valid, z, Hz, fc, tol, dudT, block_any);
+RB_LS_UNROLL
+  for (int i = 0; i < CPT; ++i) node[i] = teq_rows(tb);
+  r = dudT_lockstep<CPT>(nH, nHe, Tright, p, valid, z, Hz, fc, tol, dudT, block_any, tb, node);
   if (r) rc = r;
 RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i) {
     if (valid[i] && !floor_[i] && dudT[i] > 0.0) rc = ION_ERR_T_NOT_BRACKETED;
     if (floor_[i]) {
       T[i] = Tleft[i];
+      node[i] = 0;
     } else {
-      T[i] = (log10(Tleft[i]) + log10(Tright[i])) * 0.5;
-      T[i] = pow(10.0, T[i]);
+      T[i] = teq_root_T();   // ion_solver.f90:978-979
+      node[i] = tb.rows ? 1 : -1;
     }
     err[i] = 1.7976931348623157e308;
   }
@@ -1655,7 +1673,7 @@ RB_LS_UNROLL
     for (int i = 0; i < CPT; ++i)
       if (valid[i] && err[i] > tol) any = 1;
     if (!block_any(any)) break;  // ion_solver.f90:988
-    r = dudT_lockstep<CPT>(nH, nHe, T, p, valid, z, Hz, fc, tol, dudT, block_any);
+    r = dudT_lockstep<CPT>(nH, nHe, T, p, valid, z, Hz, fc, tol, dudT, block_any, tb, node);
     if (r) rc = r;
 RB_LS_UNROLL
     for (int i = 0; i < CPT; ++i) {
@@ -1663,9 +1681,11 @@ RB_LS_UNROLL
       if (dudT[i] < 0.0 && !floor_[i]) {
         Tright[i] = T[i];
         T[i] = (Tleft[i] + T[i]) * 0.5;
+        node[i] = teq_child(tb, node[i], true);
       } else if (dudT[i] > 0.0 && !floor_[i]) {
         Tleft[i] = T[i];
         T[i] = (T[i] + Tright[i]) * 0.5;
+        node[i] = teq_child(tb, node[i], false);
       }
       err[i] = fabs(1.0 - T[i] / Told);
     }
@@ -1675,7 +1695,7 @@ RB_LS_UNROLL
   rb_kchem_t kc[CPT];
 RB_LS_UNROLL
   for (int i = 0; i < CPT; ++i)
-    if (valid[i]) kc[i] = get_kchem(T[i], fc.H2, fc.He2, fc.He3, fc.libm);
+    if (valid[i]) kc[i] = kchem_memo(tb, node[i], T[i], fc);
   r = pce_lockstep<CPT>(nH, nHe, kc, p, valid, tol, x, block_any);
   if (r) rc = r;
   return rc;
@@ -1720,7 +1740,7 @@ RB_LS_UNROLL
   const CaseA fc = {P.fcA, P.fcA, P.fcA, P.libm_pow};
   if (P.find_Teq) {
     rc = pcte_lockstep<CPT>(nH, nHe, p, valid, P.zHz[2 * b], P.zHz[2 * b + 1], fc,
-                            P.tol_inner, x, T, any_fn);
+                            P.tol_inner, x, T, any_fn, P.teq);
   } else {
     rb_kchem_t k[CPT];
 RB_LS_UNROLL
@@ -1848,7 +1868,7 @@ __global__ void k_zone_pce(const double *in, int nn, double tol, double *out, in
 
 // in: [11][nn] = nH,nHe,H1i,He1i,He2i,H1h,He1h,He2h,fcA_H2,fcA_He2,fcA_He3 ; out [6][nn]
 __global__ void k_zone_pcte(const double *in, int nn, double z, double Hz, double tol,
-                            double *out, int *err) {
+                            double *out, int *err, TeqTab tb) {
   pow_tables_to_smem();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nn) return;
@@ -1858,17 +1878,43 @@ __global__ void k_zone_pcte(const double *in, int nn, double z, double Hz, doubl
   const CaseA fc = {in[8 * n + i], in[9 * n + i], in[10 * n + i]};
   rb_frac_t x;
   double T = 0.0;
-  const int rc = solve_pcte(in[0 * n + i], in[1 * n + i], p, z, Hz, fc, tol, x, T);
+  const int rc = solve_pcte(in[0 * n + i], in[1 * n + i], p, z, Hz, fc, tol, x, T, tb);
   if (rc) atomicMax(err, rc);
   out[0 * n + i] = x.xH1; out[1 * n + i] = x.xH2; out[2 * n + i] = x.xHe1;
   out[3 * n + i] = x.xHe2; out[4 * n + i] = x.xHe3; out[5 * n + i] = T;
+}
+
+// k_teq_table: the memo rows of TeqTab (rb_ion.cuh) -- one thread per row replays the
+// bisection's mid-point arithmetic down to its node and evaluates the 16 coefficients with
+// the solvers' own get_kchem_kcool.
+__global__ void __launch_bounds__(128) k_teq_table(double *rows, int depth, double fcA, int libm) {
+  pow_tables_to_smem();
+  const int last = 1 << depth;   // row of TMAX
+  const int r = blockIdx.x * 128 + threadIdx.x;
+  if (r > last) return;
+  double T;
+  if (r == 0) {
+    T = RB_TFLOOR;
+  } else if (r == last) {
+    T = RB_TMAX;
+  } else {
+    TBisect s;
+    s.Tl = RB_TFLOOR; s.Tr = RB_TMAX; s.T = teq_root_T(); s.err = 0.0;
+    const int d = 31 - __clz(r);
+    for (int i = d - 1; i >= 0; --i) tbisect_step(s, ((r >> i) & 1) == 0);
+    T = s.T;
+  }
+  rb_kchem_t kc;
+  rb_kcool_t kl;
+  get_kchem_kcool(T, fcA, fcA, fcA, kc, kl, libm);
+  teq_store(rows + (size_t)r * kTeqStride, T, kc, kl);
 }
 
 // lock-step single-zone solvers: ONE block, CPT zones per thread (nn <= 512*CPT)
 template <int CPT>
 __global__ void __launch_bounds__(512)
 k_zone_lockstep(const double *in, int nn, double z, double Hz, double tol, double *out,
-                int *err, int pcte) {
+                int *err, int pcte, TeqTab tb) {
   pow_tables_to_smem();
   const size_t n = (size_t)nn;
   double nH[CPT], nHe[CPT], T[CPT];
@@ -1898,7 +1944,7 @@ RB_LS_UNROLL
   }
   int rc;
   BlockAny any_fn;
-  if (pcte) rc = pcte_lockstep<CPT>(nH, nHe, p, valid, z, Hz, fc, tol, x, T, any_fn);
+  if (pcte) rc = pcte_lockstep<CPT>(nH, nHe, p, valid, z, Hz, fc, tol, x, T, any_fn, tb);
   else rc = pce_lockstep<CPT>(nH, nHe, k, p, valid, tol, x, any_fn);
   if (rc) atomicMax(err, rc);
 RB_LS_UNROLL
