@@ -232,10 +232,45 @@ int rb_plan_set_batch(rb_plan *plan, int b0, int n, const double *Edges,
                       const double *nH, const double *nHe, const double *T, int nspec,
                       const double *E_eV, const double *shape, const int *spec_index,
                       const double *z, const double *Hz);
-/* H2D copy of everything staged; resets iteration state */
+/* Photon-energy grid of rabacus/rad_src/source.py:178-259 (segmented=True): Nnu
+ * log-spaced samples between q_min and q_max (units of 13.6 eV) with the samples nearest
+ * the H I / He I / He II thresholds snapped onto them; E_eV [Nnu].  Host-side helper.
+ * RB_ERR_BAD_ARG where the reference raises (q_min > 1, q_max < 54.42/13.6, Nnu < 2). */
+int rb_photon_energies(double q_min, double q_max, int Nnu, double *E_eV);
+/* Device-side input producers for parameter sweeps of SphereBgnd problems (replaces the
+ * per-problem Python work of rabacus/rad_src/source.py:178-259 -- segmented photon-energy
+ * grid --, rabacus/uv_bgnd/hm12.py:239-303 -- HM12 spectrum at redshift z: linear in z,
+ * log-log in wavelength --, rabacus/f2py/verner_96.f90:108-154 -- cross sections -- and
+ * of the density profile of doc/guide_bgnd_sphere_examples.rst:126-146).  Every problem b
+ * of the plan is described by three numbers: Edges = linspace(0, R_cm[b], Nl+1),
+ * nH = nH0[b] * (r < r0 ? 1 : (r/r0)^-slope) at the shell centres with r0 = R/core_div,
+ * nHe = nH * nHe_over_nH, T = T0, spectrum = HM12 at z[b] on the Nnu-point grid
+ * q_min..q_max (in units of 13.6 eV).  The HM12 table is passed as log10(lambda/cm)
+ * [nlam] non-decreasing, z_tab [nzt] ascending and log10 I_nu [nlam][nzt].  rb_plan_upload then
+ * generates all inputs ON THE DEVICE (k_family_profiles, k_family_spectra); only these
+ * arguments cross PCIe.  E_eV_out (may be NULL) receives the energy grid.  Results come
+ * back centre-first, like a call with increasing Edges. */
+int rb_plan_set_sphere_family(rb_plan *plan, const double *nH0, const double *R_cm,
+                              const double *z, const double *Hz, double core_div,
+                              double slope, double nHe_over_nH, double T0, double q_min,
+                              double q_max, int nlam, int nzt, const double *log_lam_cm,
+                              const double *z_tab, const double *logInu, double *E_eV_out);
+/* H2D copy of everything staged (or, after rb_plan_set_sphere_family, generation of the
+ * inputs on the device); resets iteration state */
 int rb_plan_upload(rb_plan *plan);
 /* optically-thin initial state (sphere_bgnd.f90:379-499 and twins) */
 int rb_plan_thin(rb_plan *plan);
+/* Sweep order of SphereBgnd plans.  RB_ORDER_JACOBI (default): every cell's rays see the
+ * pre-sweep state -- the order of the reference's other three drivers, and the one that
+ * shards.  RB_ORDER_GAUSS_SEIDEL: rabacus/f2py/sphere_bgnd.f90:753-913 as it runs with
+ * OMP_NUM_THREADS=1 (its only deterministic order): cells outermost first, each seeing the
+ * cells before it already updated.  Serial in the cells (4-5 launches per cell): one GPU
+ * only, no cell shards; meant for checks against the reference's iterates, not for speed.
+ * The one-shot entry rb_sphere_bgnd_solve takes the order from the environment variable
+ * RB_SPHERE_BGND_ORDER ("gs" | "jacobi"). */
+#define RB_ORDER_JACOBI 0
+#define RB_ORDER_GAUSS_SEIDEL 1
+int rb_plan_set_sweep_order(rb_plan *plan, int order);
 /* one Jacobi sweep over the local cells il = cell_start + j*cell_stride:
  * columns -> frequency/angle integrals -> cell solve.  Does NOT test
  * convergence. */

@@ -48,8 +48,9 @@ EXPORTS = (
     "rb_sphere_bgnd_solve", "rb_sphere_stromgren_solve", "rb_slab_bgnd_solve",
     "rb_slab_plane_solve", "rb_set_column_vs_impact",
     "rb_get_kchem", "rb_get_kcool", "rb_solve_ce", "rb_solve_pce", "rb_solve_pcte",
-    "rb_photo_sigma", "rb_photo_Eth", "rb_gauss_legendre",
-    "rb_plan_create", "rb_plan_destroy", "rb_plan_set_problem", "rb_plan_set_batch", "rb_plan_upload",
+    "rb_photo_sigma", "rb_photo_Eth", "rb_gauss_legendre", "rb_photon_energies",
+    "rb_plan_create", "rb_plan_destroy", "rb_plan_set_problem", "rb_plan_set_batch",
+    "rb_plan_set_sphere_family", "rb_plan_set_sweep_order", "rb_plan_upload",
     "rb_plan_thin", "rb_plan_sweep_local", "rb_plan_finish_sweep", "rb_plan_finish_sweep_async",
     "rb_plan_poll_sweep", "rb_plan_solve",
     "rb_plan_get_problem", "rb_plan_get_rec", "rb_plan_get_all", "rb_plan_field_ptr", "rb_plan_stream", "rb_plan_sync",
@@ -61,7 +62,7 @@ EXPORTS = (
 # measurement / diagnostic symbols declared in rabacus_b200/csrc/rb_internal.h (not part of
 # the drop-in boundary)
 INTERNAL = ("rbi_diag_pow", "rbi_diag_hg97", "rbi_host_coefficients", "rbi_plan_set_libm_pow", "rbi_plan_set_far_field", "rbi_plan_bench_steps",
-            "rbi_microbench", "rbi_last_zone_kernel_ms", "rbi_teq_table_fetch")
+            "rbi_microbench", "rbi_last_zone_kernel_ms", "rbi_teq_table_fetch", "rbi_plan_fetch_inputs")
 
 _lib = None
 

@@ -124,5 +124,18 @@ def c5_stage(plan, index, n_nH=32, n_R=16, n_z=16, find_Teq=False):
             "broadcasting, one rb_plan_set_batch call" % (n_z, n_R))
 
 
+def c5_stage_device(plan, index, n_nH=32, n_R=16, n_z=16, find_Teq=False):
+    """Stage problems ``index`` of the C5 sweep as a device-side family: only (nH0, R, z) per
+    problem, the HM12 table and the energy grid go to the GPU; edges, density profiles,
+    spectra, cross sections and per-frequency weights are produced there by
+    ``plan.upload()`` (``rb_plan_set_sphere_family``).  Same problems as :func:`c5_stage`
+    to the last few ulp (device ``pow`` / ``log10`` instead of numpy's)."""
+    nH0, R_kpc, z, _ = c5_params(index, n_nH, n_R, n_z)
+    plan.set_sphere_family(nH0, R_kpc * KPC_CM, z, core_div=100.0, slope=2.0,
+                           nHe_over_nH=0.25 * YP / (1.0 - YP), T0=1.0e4, q_min=1.0, q_max=400.0)
+    return ("device: (nH0, R, z) per problem + HM12 table uploaded, edges / profiles / spectra / "
+            "cross sections / weights generated by k_family_profiles + k_family_spectra")
+
+
 GEOM_IDS = {"sphere_bgnd": 0, "sphere_stromgren": 1, "slab_plane_1": 2, "slab_plane_2": 3,
             "slab_bgnd": 4}

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "rb_rec.cuh"
+#include "rb_inputs.cuh"
 #include "rb_internal.h"
 
 using namespace rb;
@@ -298,7 +299,8 @@ struct rb_plan {
   double4 *dpack = nullptr;
   double *dspec = nullptr, *dthin = nullptr, *dmu = nullptr, *dzHz = nullptr;
   double4 *dcol = nullptr;
-  double4 *dfar = nullptr;      // far-field moment table [B][Nl+1][kFarNT] (SphereBgnd)
+  double *dfar = nullptr;       // kept far-field moment rows [B][Nl/S + 1][NT][3] (SphereBgnd)
+  int far_slog = 3;             // S = 2^far_slog: every S-th row is kept (far_row_slog)
   bool use_far = false;         // columns: far field from the table, near field walked
   unsigned *ditems = nullptr;   // column-kernel work list (LPT order), see build_items
   int *dwork = nullptr;         // [B] next-item counters of the column kernel
@@ -324,7 +326,7 @@ struct rb_plan {
     RecConst K;
     RecDev R;
     PeerDev Q;
-    int rec_meth, live, spec_g, cols_chunks, sharded, use_far;
+    int rec_meth, live, spec_g, cols_chunks, sharded, use_far, order;
   };
   GraphKey gkey;
   bool gkey_valid = false;
@@ -348,6 +350,14 @@ struct rb_plan {
     double thin[kThinStride];
   };
   std::vector<SpecEntry> spec_cache;
+  // device-side input producers (rb_plan_set_sphere_family): parameters of every problem,
+  // the shared energy grid and the HM12 table live on the device; rb_plan_upload then
+  // regenerates the inputs there instead of copying host staging
+  int sweep_order = RB_ORDER_JACOBI;   // SphereBgnd: RB_ORDER_GAUSS_SEIDEL = the reference's
+                                       // single-thread order (rb_plan_set_sweep_order)
+  bool family = false;
+  double *dfam = nullptr;       // nH0, R, z, Hz [4][B] | E [Nnu] | log_lam, z_tab, logI
+  FamilyDev F;
   unsigned char *dreversed = nullptr;  // [B] input orientation was flipped (rb_plan_get_all)
   int *dflags = nullptr;    // active, notconv, iters, err : 4*B, then nactive
   unsigned long long *dresid = nullptr;
@@ -406,7 +416,7 @@ extern "C" void rb_plan_destroy(rb_plan *p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   destroy_graphs(p);
   cudaFree(p->drec); cudaFree(p->drecbuf); cudaFree(p->drecI); cudaFree(p->diso_items);
-  cudaFree(p->dpart); cudaFree(p->dreversed); cudaFree(p->dfar);
+  cudaFree(p->dpart); cudaFree(p->dreversed); cudaFree(p->dfar); cudaFree(p->dfam);
   if (p->dpeer) {
     for (int r = 0; r < kMaxPeers; ++r)
       if (p->peer_base[r] && p->peer_base[r] != p->dpeer) cudaIpcCloseMemHandle(p->peer_base[r]);
@@ -503,14 +513,14 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   if (d.geometry == RB_GEOM_SPHERE_BGND)
     ALLOC(p->ditems, (size_t)((Nl + 31) / 32) * ((d.Nmu + 1) / 2) * 8 * sizeof(unsigned));
   if (d.geometry == RB_GEOM_SPHERE_BGND) {
-    // far-field moment table: where the shell records fit in shared memory (the column
-    // kernel that uses it) and the table stays below 32 GiB; RB_NO_FAR=1 disables it
-    const size_t far_bytes = B * (Nl + 1) * (size_t)kFarNT * sizeof(double4);
-    const size_t rec_smem = (size_t)(Nl + 1 + kPackPad) * sizeof(double4);
+    // far-field moment rows: where shell records + kept rows fit in shared memory (the
+    // column kernel that uses them); RB_NO_FAR=1 disables the far field
+    p->far_slog = far_row_slog((int)Nl);
+    const size_t far_bytes = B * (size_t)far_rows((int)Nl, p->far_slog) * kFarRow * sizeof(double);
     const int nseg = (int)((Nl + 1 + kFarSeg - 1) / kFarSeg);
     const char *nf = getenv("RB_NO_FAR");
-    if (!(nf && atoi(nf) != 0) && rec_smem <= 227 * 1024 - 1024 && nseg <= 8 * 42 &&
-        far_bytes <= ((size_t)32 << 30)) {
+    if (!(nf && atoi(nf) != 0) && far_cols_smem((int)Nl, p->far_slog) <= (size_t)226 * 1024 &&
+        nseg <= 8 * 42) {
       if (cudaMalloc((void **)&p->dfar, far_bytes) == cudaSuccess) p->use_far = true;
       else { cudaGetLastError(); p->dfar = nullptr; }
     }
@@ -605,6 +615,7 @@ extern "C" int rb_plan_set_problem(rb_plan *p, int b, const double *Edges, const
                                    const double *shape, double z, double Hz) {
   if (!p || b < 0 || b >= p->d.n_problems) return RB_ERR_BAD_ARG;
   const int Nl = p->d.Nl, Nnu = p->d.Nnu, g = p->d.geometry;
+  p->family = false;   // host staging takes over again
   // orientation: SphereBgnd wants decreasing Edges (sphere_bgnd.f90:182-202),
   // SphereStromgren increasing (sphere_stromgren.f90:186-204); slabs as given.
   bool rev = false;
@@ -675,21 +686,141 @@ extern "C" int rb_plan_set_batch(rb_plan *p, int b0, int n, const double *Edges,
   return RB_OK;
 }
 
+// Photon-energy grid of rad_src/source.py:178-259 (segmented): Nnu log-spaced samples of
+// q = E / 13.6 eV between q_min and q_max, the samples nearest the three ionisation
+// thresholds snapped onto them.  numpy.linspace semantics (start + k*step, exact end point).
+static int photon_energies(double q_min, double q_max, int Nnu, std::vector<double> &E) {
+  if (Nnu < 2 || !(q_min > 0.0) || !(q_max > q_min)) return RB_ERR_BAD_ARG;
+  const double Eth[3] = {v96_row(0).Eth, v96_row(1).Eth, v96_row(2).Eth};
+  const double a = log10(q_min), b = log10(q_max);
+  const double step = (b - a) / (double)(Nnu - 1);
+  std::vector<double> lq(Nnu), q(Nnu);
+  for (int k = 0; k < Nnu; ++k) lq[k] = (k == Nnu - 1) ? b : (double)k * step + a;
+  for (int k = 0; k < Nnu; ++k) q[k] = pow(10.0, lq[k]);
+  double qmin = q[0], qmax = q[0];
+  for (int k = 1; k < Nnu; ++k) { qmin = std::min(qmin, q[k]); qmax = std::max(qmax, q[k]); }
+  const double qt[3] = {1.0, Eth[1] / Eth[0], Eth[2] / Eth[0]};
+  if (qmin > 1.0 || qmax < qt[2]) return RB_ERR_BAD_ARG;   // source.py:205-212
+  for (int X = 0; X < 3; ++X) {
+    const double t = log10(qt[X]);
+    int best = 0;
+    for (int k = 1; k < Nnu; ++k)
+      if (fabs(lq[k] - t) < fabs(lq[best] - t)) best = k;
+    q[best] = qt[X];
+  }
+  E.resize(Nnu);
+  for (int k = 0; k < Nnu; ++k) E[k] = q[k] * Eth[0];
+  return RB_OK;
+}
+
+extern "C" int rb_photon_energies(double q_min, double q_max, int Nnu, double *E_eV) {
+  if (!E_eV) return RB_ERR_BAD_ARG;
+  std::vector<double> E;
+  const int rc = photon_energies(q_min, q_max, Nnu, E);
+  if (rc) return rc;
+  memcpy(E_eV, E.data(), (size_t)Nnu * 8);
+  return RB_OK;
+}
+
+extern "C" int rb_plan_set_sphere_family(rb_plan *p, const double *nH0, const double *R_cm,
+                                         const double *z, const double *Hz, double core_div,
+                                         double slope, double nHe_over_nH, double T0,
+                                         double q_min, double q_max, int nlam, int nzt,
+                                         const double *log_lam_cm, const double *z_tab,
+                                         const double *logInu, double *E_eV_out) {
+  if (!p || !nH0 || !R_cm || !z || !log_lam_cm || !z_tab || !logInu || nlam < 2 || nzt < 2 ||
+      !(core_div > 0.0))
+    return RB_ERR_BAD_ARG;
+  if (p->d.geometry != RB_GEOM_SPHERE_BGND) return RB_ERR_UNSUPPORTED;
+  PLAN_DEV(p);
+  const size_t B = p->d.n_problems, Nl = p->d.Nl, Nnu = p->d.Nnu;
+  for (size_t b = 0; b < B; ++b)
+    if (!(R_cm[b] > 0.0) || !(nH0[b] >= 0.0)) return RB_ERR_BAD_ARG;
+  for (int i = 1; i < nlam; ++i)
+    if (!(log_lam_cm[i] >= log_lam_cm[i - 1])) return RB_ERR_BAD_ARG;   // repeated nodes allowed
+  for (int i = 1; i < nzt; ++i)
+    if (!(z_tab[i] > z_tab[i - 1])) return RB_ERR_BAD_ARG;
+  std::vector<double> E;
+  int rc = photon_energies(q_min, q_max, (int)Nnu, E);
+  if (rc) return rc;
+  if (E_eV_out) memcpy(E_eV_out, E.data(), Nnu * 8);
+  const size_t n = 4 * B + Nnu + (size_t)nlam + (size_t)nzt + (size_t)nlam * nzt;
+  std::vector<double> h(n);
+  double *q = h.data();
+  memcpy(q, nH0, B * 8); memcpy(q + B, R_cm, B * 8); memcpy(q + 2 * B, z, B * 8);
+  for (size_t b = 0; b < B; ++b) q[3 * B + b] = Hz ? Hz[b] : 0.0;
+  q += 4 * B;
+  memcpy(q, E.data(), Nnu * 8); q += Nnu;
+  memcpy(q, log_lam_cm, (size_t)nlam * 8); q += nlam;
+  memcpy(q, z_tab, (size_t)nzt * 8); q += nzt;
+  memcpy(q, logInu, (size_t)nlam * nzt * 8);
+  cudaFree(p->dfam);
+  p->dfam = nullptr;
+  if (cudaMalloc((void **)&p->dfam, n * 8) != cudaSuccess) { cudaGetLastError(); return RB_ERR_NOMEM; }
+  CK(cudaMemcpyAsync(p->dfam, h.data(), n * 8, cudaMemcpyHostToDevice, p->stream));
+  CK(cudaStreamSynchronize(p->stream));   // `h` is pageable
+  FamilyDev &F = p->F;
+  memset(&F, 0, sizeof(F));
+  F.B = (int)B; F.Nl = (int)Nl; F.Nnu = (int)Nnu;
+  F.nH0 = p->dfam; F.R = p->dfam + B; F.z = p->dfam + 2 * B; F.Hz = p->dfam + 3 * B;
+  F.E = p->dfam + 4 * B;
+  F.core_div = core_div; F.slope = slope; F.he_ratio = nHe_over_nH; F.T0 = T0;
+  F.hm.nlam = nlam; F.hm.nz = nzt;
+  F.hm.log_lam = F.E + Nnu; F.hm.z = F.hm.log_lam + nlam; F.hm.logI = F.hm.z + nzt;
+  F.Edges = p->dEdges; F.nH = p->dnH; F.nHe = p->dnHe; F.T = p->dT; F.spec = p->dspec;
+  F.thin = p->dthin; F.zHz = p->dzHz; F.reversed = p->dreversed;
+  // host mirrors that the launch logic reads: problem 0's edges (work-list order of the
+  // column kernel), the orientation flags (results go back centre-first)
+  for (size_t i = 0; i <= Nl; ++i) {
+    const size_t k = Nl - i;
+    p->hEdges[i] = (k == Nl) ? R_cm[0] : (double)k * (R_cm[0] / (double)Nl);
+  }
+  std::fill(p->reversed.begin(), p->reversed.end(), (char)1);
+  p->family = true;
+  return RB_OK;
+}
+
+extern "C" int rbi_plan_fetch_inputs(rb_plan *p, int b, double *Edges, double *nH, double *nHe,
+                                     double *T, double *spec, double *thin) {
+  if (!p || b < 0 || b >= p->d.n_problems) return RB_ERR_BAD_ARG;
+  PLAN_DEV(p);
+  const size_t Nl = p->d.Nl, Nnu = p->d.Nnu;
+  CK(cudaStreamSynchronize(p->stream));
+  if (Edges) CK(cudaMemcpy(Edges, p->dEdges + b * (Nl + 1), (Nl + 1) * 8, cudaMemcpyDeviceToHost));
+  if (nH) CK(cudaMemcpy(nH, p->dnH + b * Nl, Nl * 8, cudaMemcpyDeviceToHost));
+  if (nHe) CK(cudaMemcpy(nHe, p->dnHe + b * Nl, Nl * 8, cudaMemcpyDeviceToHost));
+  if (T) CK(cudaMemcpy(T, p->dT + b * Nl, Nl * 8, cudaMemcpyDeviceToHost));
+  if (spec) CK(cudaMemcpy(spec, p->dspec + b * Nnu * kSpecStride, Nnu * kSpecStride * 8,
+                          cudaMemcpyDeviceToHost));
+  if (thin) CK(cudaMemcpy(thin, p->dthin + b * kThinStride, kThinStride * 8, cudaMemcpyDeviceToHost));
+  return RB_OK;
+}
+
 extern "C" int rb_plan_upload(rb_plan *p) {
   if (!p) return RB_ERR_BAD_ARG;
   PLAN_DEV(p);
   const size_t B = p->d.n_problems, Nl = p->d.Nl, Nnu = p->d.Nnu, NC = B * Nl;
   cudaStream_t s = p->stream;
   plan_bind_teq(p);
-  CK(cudaMemcpyAsync(p->dEdges, p->hEdges, B * (Nl + 1) * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(p->dnH, p->hnH, NC * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(p->dnHe, p->hnHe, NC * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(p->dT, p->hT, NC * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(p->dspec, p->hspec, B * Nnu * kSpecStride * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(p->dthin, p->hthin, B * kThinStride * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(p->dzHz, p->hzHz, B * 2 * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(p->dreversed, p->reversed.data(), B, cudaMemcpyHostToDevice, s));
-  CK(cudaStreamSynchronize(s));  // `reversed` is pageable
+  if (p->family) {
+    // inputs produced on the device from (nH0, R, z) per problem (rb_inputs.cuh)
+    dim3 gp((unsigned)((Nl + 1 + 127) / 128), (unsigned)B);
+    k_family_profiles<<<gp, 128, 0, s>>>(p->F);
+    k_family_spectra<<<(unsigned)B, 128, 0, s>>>(p->F, p->sigma_th[0], p->sigma_th[1],
+                                                 p->sigma_th[2]);
+    p->info.n_launches += 2;
+    CK(cudaGetLastError());
+  } else {
+    CK(cudaMemcpyAsync(p->dEdges, p->hEdges, B * (Nl + 1) * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->dnH, p->hnH, NC * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->dnHe, p->hnHe, NC * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->dT, p->hT, NC * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->dspec, p->hspec, B * Nnu * kSpecStride * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->dthin, p->hthin, B * kThinStride * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->dzHz, p->hzHz, B * 2 * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->dreversed, p->reversed.data(), B, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));  // `reversed` is pageable
+  }
   for (size_t b = 0; b < B; ++b) {
     p->hflags[b] = 1; p->hflags[B + b] = 0; p->hflags[2 * B + b] = 0;
   }
@@ -747,7 +878,11 @@ static int build_items(rb_plan *p, int cell_start, int cell_stride, int n_local,
   const int Nl = p->d.Nl, Nmu = p->d.Nmu;
   const double *E = p->hEdges;  // solver orientation: non-increasing
   const bool far = p->use_far;
-  if (p->items_start == cell_start && p->items_stride == cell_stride && p->items_far == far &&
+  // single-cell launches (the Gauss-Seidel order) all use the same list -- one 32-cell block,
+  // every |mu| pair (x chunk): its order is only a scheduling heuristic, so it is built once
+  // and kept for every cell (no host copy inside a captured sweep)
+  const int cell_key = (n_local == 1) ? -2 : cell_start;
+  if (p->items_start == cell_key && p->items_stride == cell_stride && p->items_far == far &&
       p->items_chunks == nchunk && p->items_edges.size() == (size_t)Nl + 1 &&
       memcmp(p->items_edges.data(), E, sizeof(double) * (Nl + 1)) == 0)
     return RB_OK;
@@ -781,7 +916,7 @@ static int build_items(rb_plan *p, int cell_start, int cell_stride, int n_local,
           }
           kf = a0;
         }
-        walked = m - kf;
+        walked = m - (kf >= 0 ? (kf & ~((1 << p->far_slog) - 1)) : -1);
       }
       for (int c = 0; c < nchunk; ++c) {  // shell edges c*Q .. (c+1)*Q-1, up to m
         const int len = (nchunk == 1) ? walked : std::min(m, (c + 1) * Q - 1) - c * Q + 1;
@@ -798,7 +933,7 @@ static int build_items(rb_plan *p, int cell_start, int cell_stride, int n_local,
   CK(cudaMemcpyAsync(p->ditems, items.data(), items.size() * sizeof(unsigned),
                      cudaMemcpyHostToDevice, p->stream));
   CK(cudaStreamSynchronize(p->stream));  // `items` is pageable and dies here
-  p->items_start = cell_start; p->items_stride = cell_stride; p->items_chunks = nchunk;
+  p->items_start = cell_key; p->items_stride = cell_stride; p->items_chunks = nchunk;
   p->items_far = far;
   p->items_edges.assign(E, E + Nl + 1);
   return RB_OK;
@@ -850,7 +985,7 @@ static int launch_far_moments(rb_plan *p) {
   at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, k_far_moments, p->P, p->dfar, cs, spc));
+  CK(cudaLaunchKernelEx(&cfg, k_far_moments, p->P, p->dfar, cs, spc, p->far_slog));
   p->info.n_launches += 1;
   return RB_OK;
 }
@@ -858,7 +993,8 @@ static int launch_far_moments(rb_plan *p) {
 static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, int n_local) {
   const int Nl = p->d.Nl, B = p->d.n_problems;
   cudaStream_t s = p->stream;
-  const size_t smem = (size_t)(Nl + 1 + kPackPad) * sizeof(double4);
+  const size_t rec_smem = (size_t)(Nl + 1 + kPackPad) * sizeof(double4);
+  const size_t smem = p->use_far ? far_cols_smem(Nl, p->far_slog) : rec_smem;
   const size_t kMaxSmem = 227 * 1024 - 1024;
   if (smem > kMaxSmem) {  // records do not fit in shared memory: global-memory fallback
     dim3 gp((Nl + 1 + kPackPad + 255) / 256, B);
@@ -924,7 +1060,7 @@ static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, in
     if (rc) return rc;                                                                       \
     k_sphere_columns_smem<THREADS, 1, MINB><<<g, THREADS, smem, s>>>(                        \
         p->P, cell_start, cell_stride, n_local, p->ditems, p->n_items, p->dwork, nchunk,     \
-        p->dpart, p->use_far ? p->dfar : nullptr);                                           \
+        p->dpart, p->use_far ? p->dfar : nullptr, p->far_slog);                              \
   } while (0)
   // 16-18 warps per SM at ~100 registers beat 24 warps at 80 (1.035 vs 1.068 ms at C4,
   // profiles/r01_kernel_variants.md)
@@ -1114,9 +1250,82 @@ static int cell_group_size(const rb_plan *p, int n_local) {
   return G < 4 ? 1 : G;
 }
 
+// G lanes per cell run the bisection (on T with find_Teq: k_cell_solve_spec, on n_e at
+// fixed T: k_cell_solve_pce_spec) speculatively; G is the largest group that keeps the
+// launch within ~one wave of resident threads, larger batches run one thread per cell.
+static void launch_cell_solve(rb_plan *p, const PeerDev &Q, int cell_start, int cell_stride,
+                              int n_local) {
+  const int B = p->d.n_problems;
+  cudaStream_t s = p->stream;
+  const int G = cell_group_size(p, n_local);
+  if (G == 1) {
+    dim3 gs3((n_local + 127) / 128, B);
+    k_cell_solve<<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local);
+  } else {
+    dim3 gs3(((long long)n_local * G + 127) / 128, B);
+#define CELL(KERN)                                                                           \
+  switch (G) {                                                                               \
+    case 32: KERN<32><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local); break; \
+    case 16: KERN<16><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local); break; \
+    case 8: KERN<8><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local); break;   \
+    default: KERN<4><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local);         \
+  }
+    if (p->d.i_find_Teq) { CELL(k_cell_solve_spec) } else { CELL(k_cell_solve_pce_spec) }
+#undef CELL
+  }
+}
+
+// One sweep of SphereBgnd in the reference's sequential order (sphere_bgnd.f90:753-913 with
+// OMP_NUM_THREADS=1): the recombination-photon rates once from the pre-sweep state
+// (:694-735), then the cells outermost first, each one seeing the fractions and temperatures
+// of the cells before it ALREADY UPDATED -- Gauss-Seidel.  The three stages run per cell
+// (columns of its rays from the current state -> frequency / angle integrals -> cell solve):
+// 4-5 small launches per cell, strictly serial.  This is the reference's only deterministic
+// order; it is a non-default switch because it cannot use the GPU (or shard), see DESIGN.md.
+static int sweep_gauss_seidel(rb_plan *p) {
+  const int Nl = p->d.Nl;
+  cudaStream_t s = p->stream;
+  cudaEvent_t *sev = p->sev[p->sweeps_issued % kSlots];
+  const bool timed = !p->capturing;
+  p->slot_timed[p->sweeps_issued % kSlots] = timed;
+  if (timed) cudaEventRecord(p->rev[p->sweeps_issued % kSlots], s);
+  int rc = RB_OK;
+  if (p->rec_meth != 1) {
+    RecCells L = {0, 1, Nl, Nl};
+    rc = launch_rec(p, L);
+    if (rc) return rc;
+  }
+  if (timed) cudaEventRecord(sev[0], s);
+  PeerDev Q = p->Q;
+  Q.world = 1;
+  // one cell per launch: the far-field table would be rebuilt for every cell -- walk instead
+  const bool far_saved = p->use_far;
+  p->use_far = false;
+  for (int il = 0; il < Nl && !rc; ++il) {
+    rc = launch_sphere_columns(p, il, Nl, 1);
+    if (!rc) rc = launch_nu_rates(p, il, Nl, 1);
+    if (!rc) {
+      launch_cell_solve(p, Q, il, Nl, 1);
+      p->info.n_launches += 1;
+    }
+  }
+  p->use_far = far_saved;
+  if (rc) return rc;
+  if (timed) {   // the stages interleave: the whole cell loop is booked as "columns"
+    cudaEventRecord(sev[1], s); cudaEventRecord(sev[2], s); cudaEventRecord(sev[3], s);
+    CK(cudaGetLastError());
+  }
+  return RB_OK;
+}
+
 static int sweep_impl(rb_plan *p, int cell_start, int cell_stride, bool scatter) {
   if (!p || cell_start < 0 || cell_stride < 1) return RB_ERR_BAD_ARG;
   PLAN_DEV(p);
+  if (p->sweep_order == RB_ORDER_GAUSS_SEIDEL && p->d.geometry == RB_GEOM_SPHERE_BGND) {
+    // sequential in the cells: no cell shards (replicas only in this mode)
+    if (scatter || cell_start != 0 || cell_stride != 1) return RB_ERR_UNSUPPORTED;
+    return sweep_gauss_seidel(p);
+  }
   PeerDev Q = p->Q;
   if (!scatter) Q.world = 1;
   const int Nl = p->d.Nl, B = p->d.n_problems, g = p->d.geometry;
@@ -1153,31 +1362,21 @@ static int sweep_impl(rb_plan *p, int cell_start, int cell_stride, bool scatter)
     rc = launch_nu_rates(p, cell_start, cell_stride, n_local);
     if (rc) return rc;
     if (timed) cudaEventRecord(sev[2], s);
-    // G lanes per cell run the bisection (on T with find_Teq: k_cell_solve_spec, on n_e at
-    // fixed T: k_cell_solve_pce_spec) speculatively; G is the largest group that keeps the
-    // launch within ~one wave of resident threads, larger batches run one thread per cell.
-    const int G = cell_group_size(p, n_local);
-    if (G == 1) {
-      dim3 gs3((n_local + 127) / 128, B);
-      k_cell_solve<<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local);
-    } else {
-      dim3 gs3(((long long)n_local * G + 127) / 128, B);
-#define CELL(KERN)                                                                           \
-  switch (G) {                                                                               \
-    case 32: KERN<32><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local); break; \
-    case 16: KERN<16><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local); break; \
-    case 8: KERN<8><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local); break;   \
-    default: KERN<4><<<gs3, 128, 0, s>>>(p->P, Q, cell_start, cell_stride, n_local);         \
-  }
-      if (p->d.i_find_Teq) { CELL(k_cell_solve_spec) } else { CELL(k_cell_solve_pce_spec) }
-#undef CELL
-    }
+    launch_cell_solve(p, Q, cell_start, cell_stride, n_local);
     p->info.n_launches += 1;
   } else {
     if (timed) cudaEventRecord(sev[2], s);
   }
   if (timed) cudaEventRecord(sev[3], s);
   if (timed) CK(cudaGetLastError());
+  return RB_OK;
+}
+
+extern "C" int rb_plan_set_sweep_order(rb_plan *p, int order) {
+  if (!p || (order != RB_ORDER_JACOBI && order != RB_ORDER_GAUSS_SEIDEL)) return RB_ERR_BAD_ARG;
+  if (order == RB_ORDER_GAUSS_SEIDEL && p->d.geometry != RB_GEOM_SPHERE_BGND)
+    return RB_ERR_UNSUPPORTED;   // the other three drivers ARE Jacobi in the reference
+  p->sweep_order = order;        // part of the graph key
   return RB_OK;
 }
 
@@ -1323,6 +1522,7 @@ static int sweep_graph(rb_plan *p, bool sharded) {
   key.live = live_problems(p);
   key.sharded = sharded ? 1 : 0;
   key.use_far = p->use_far ? 1 : 0;
+  key.order = p->sweep_order;
   {
     const char *a = getenv("RB_SPEC_G"), *b = getenv("RB_COLS_CHUNKS");
     key.spec_g = a ? atoi(a) : 0;
@@ -1807,6 +2007,13 @@ static int solve_one(int geom, const double *Edges, const double *nH, const doub
   int rc = plan_acquire(&p, d);
   if (rc) return rc;
   PLAN_DEV(p);
+  {
+    // sweep order of the one-shot SphereBgnd entry: RB_SPHERE_BGND_ORDER=gs selects the
+    // reference's sequential order (rb_plan_set_sweep_order); cached plans are re-armed
+    const char *o = getenv("RB_SPHERE_BGND_ORDER");
+    const bool gs = geom == RB_GEOM_SPHERE_BGND && o && (o[0] == 'g' || o[0] == 'G');
+    p->sweep_order = gs ? RB_ORDER_GAUSS_SEIDEL : RB_ORDER_JACOBI;
+  }
   rc = rb_plan_set_problem(p, 0, Edges, nH, nHe, T, E_eV, shape, z, Hz);
   if (!rc) rc = rb_plan_upload(p);
   if (!rc) {

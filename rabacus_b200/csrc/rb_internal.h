@@ -53,6 +53,12 @@ int rbi_plan_set_far_field(rb_plan *plan, int on);
  * TMAX).  RB_ERR_UNSUPPORTED when the memo is disabled (RB_TEQ_DEPTH=0). */
 int rbi_teq_table_fetch(double fcA, int row0, int n, double *out16, int *depth);
 
+/* D2H of problem b's staged INPUTS as the kernels see them (solver orientation): Edges
+ * [Nl+1], nH / nHe / T [Nl], the per-frequency table [Nnu][9] and the thin integrals [9];
+ * any pointer may be NULL.  For the tests of the device-side input producers. */
+int rbi_plan_fetch_inputs(rb_plan *plan, int b, double *Edges, double *nH, double *nHe,
+                          double *T, double *spec, double *thin);
+
 /* device time [ms] of the kernel of this thread's last rb_solve_pce / rb_solve_pcte call
  * (scalar mode), for the single-zone batch line of bench.py */
 double rbi_last_zone_kernel_ms(void);

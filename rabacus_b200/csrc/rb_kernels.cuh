@@ -224,10 +224,32 @@ __device__ __forceinline__ double sqrt_pos(double x) {
 // <= 2e-14 of a column for random 1e6 density jumps (scratch/farfield_proto.py), i.e. the
 // same order as the summed-by-parts walk itself; the result depends on (cell, mu) only, not
 // on how cells are dealt to warps or GPUs.
+//
+// Only every S-th row is kept (S = 2^slog, far_row_stride()): a ray pair takes the last kept
+// row K' = Kf - Kf mod S at or above its far limit Kf and walks S/2 more edges on average.
+// The kept rows -- (Nl/S + 1) x 3 NT doubles -- fit in SHARED memory next to the shell
+// records, so the far field costs no memory traffic at all (with one row per edge in global
+// memory a batch of 8192 problems moved 107 GB of rows through L2 per sweep, and that --
+// not the arithmetic -- was the column stage: 1.81 ms per 1024 problems).
 // ---------------------------------------------------------------------------
 constexpr int kFarNT = RB_FAR_NT;
 constexpr int kFarSeg = 32;           // edges per scan segment (fixed: part of the rounding)
+constexpr int kFarRow = 3 * kFarNT;   // doubles per kept row: [NT][3 absorbers]
 __constant__ double kFarB[kFarNT] = {RB_FAR_COEFFS};
+
+// kept rows / row stride for a grid of Nl shells: the smallest power of two S >= 8 for which
+// shell records + kept rows fit the shared memory of one CTA (three CTAs per SM where S = 8
+// allows it)
+__host__ __device__ inline int far_rows(int Nl, int slog) { return (Nl >> slog) + 1; }
+__host__ __device__ inline size_t far_cols_smem(int Nl, int slog) {
+  return (size_t)(Nl + 1 + kPackPad) * sizeof(double4) +
+         (size_t)far_rows(Nl, slog) * kFarRow * sizeof(double);
+}
+__host__ inline int far_row_slog(int Nl) {
+  int slog = 3;
+  while (slog < 12 && far_cols_smem(Nl, slog) > (size_t)226 * 1024) ++slog;
+  return slog;
+}
 
 // g_K = E_K / E_{K-1} (0 for K = 0 and wherever an edge is 0: the row then restarts at D_K)
 __device__ __forceinline__ double far_g(const double *E, int K) {
@@ -257,8 +279,8 @@ __device__ __forceinline__ void far_step(double (&M)[kFarNT], double g, double D
 //   pass 1   segment-local recurrences from zero -> B_s[X][n]; A_s[n] = prod g^(2n-1)
 //   CTA composite (A, B) over its segments; exchanged through distributed shared memory
 //   carry-in of the CTA from the CTAs before it, of the segment from the segments before it
-//   pass 2   the recurrences again from the carry-in, rows stored as b_n Mt_n[K]
-// far: [B][Nl+1][NT] double4 {HI, HeI, HeII, 0}.
+//   pass 2   the recurrences again from the carry-in, every S-th row stored as b_n Mt_n[K]
+// far: [B][Nl/S + 1][NT][3] doubles {HI, HeI, HeII}.
 struct FarSmem {
   double4 *rec;     // [spc * kFarSeg] {g, D0, D1, D2}
   double *sA;       // [spc][NT]
@@ -272,8 +294,8 @@ __host__ __device__ inline size_t far_smem_bytes(int spc) {
          ((size_t)spc * kFarNT * 4 + 7 * kFarNT) * sizeof(double);
 }
 
-__global__ void __launch_bounds__(128) k_far_moments(PlanDev P, double4 *__restrict__ far,
-                                                     int csize, int spc) {
+__global__ void __launch_bounds__(128) k_far_moments(PlanDev P, double *__restrict__ far,
+                                                     int csize, int spc, int slog) {
   namespace cg = cooperative_groups;
   extern __shared__ double4 s_far4[];
   const int b = blockIdx.x / csize, crank = blockIdx.x % csize;
@@ -355,28 +377,30 @@ __global__ void __launch_bounds__(128) k_far_moments(PlanDev P, double4 *__restr
       for (int n = 0; n < kFarNT; ++n)
         M[n] = fma(M[n], S.sA[j * kFarNT + n], S.sB[(j * 3 + X) * kFarNT + n]);
     }
-    double *out = reinterpret_cast<double *>(far + ((size_t)b * nedge) * kFarNT) + X;
+    double *out = far + (size_t)b * far_rows(Nl, slog) * kFarRow + X;
     for (int k = kb; k < ke; ++k) {
       const double4 r = S.rec[k - seg0 * kFarSeg];
       const double D = X == 0 ? r.y : (X == 1 ? r.z : r.w);
       far_step(M, r.x, D);
+      if ((k & ((1 << slog) - 1)) == 0) {
+        double *row = out + (size_t)(k >> slog) * kFarRow;
 #pragma unroll
-      for (int n = 0; n < kFarNT; ++n) out[((size_t)k * kFarNT + n) * 4] = kFarB[n] * M[n];
+        for (int n = 0; n < kFarNT; ++n) row[3 * n] = kFarB[n] * M[n];
+      }
     }
   }
   if (csize > 1) cg::this_cluster().sync();   // peers may still read cA / cB
 }
 
 // sum_{k<=K} s_k D_k for the three absorbers from table row K (E_K >= RATIO p)
-__device__ __forceinline__ void far_eval(const double4 *__restrict__ row, double u, double EK,
+__device__ __forceinline__ void far_eval(const double *__restrict__ row, double u, double EK,
                                          double (&out)[3]) {
   double h0 = 0.0, h1 = 0.0, h2 = 0.0;
 #pragma unroll
   for (int n = kFarNT - 1; n >= 0; --n) {
-    const double4 c = row[n];
-    h0 = fma(h0, u, c.x);
-    h1 = fma(h1, u, c.y);
-    h2 = fma(h2, u, c.z);
+    h0 = fma(h0, u, row[3 * n]);
+    h1 = fma(h1, u, row[3 * n + 1]);
+    h2 = fma(h2, u, row[3 * n + 2]);
   }
   out[0] = EK * h0; out[1] = EK * h1; out[2] = EK * h2;
 }
@@ -504,7 +528,8 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
                                                 const double4 *__restrict__ pk, bool store,
                                                 int nchunk = 1, int chunk = 0,
                                                 double *part = nullptr,
-                                                const double4 *__restrict__ far = nullptr) {
+                                                const double *__restrict__ far = nullptr,
+                                                int slog = 0) {
   const int Nl = P.Nl;
   const double *E = P.Edges + (size_t)b * (Nl + 1);
 
@@ -530,8 +555,9 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
   const int m = hollow ? -1 : lo - 1;
 
   if (far != nullptr) {
-    // ---- far field from the moment table, near field (p < E_k < RATIO p) walked.
-    // Kf = last edge k <= m with E_k >= RATIO p (-1: none).  Called by all 32 lanes.
+    // ---- far field from the kept moment rows (shared memory), the rest walked.
+    // Kf = last edge k <= m with E_k >= RATIO p (-1: none); Kc = last KEPT row at or above
+    // it.  Called by all 32 lanes.
     const double rp = p_ray * RB_FAR_RATIO;
     int Kf = -1;
     if (m >= 0 && E[0] >= rp) {
@@ -542,30 +568,41 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
       }
       Kf = a0;
     }
-    const double4 *tab = far + (size_t)b * (Nl + 1) * kFarNT;
+    const int smask = (1 << slog) - 1;
+    const int Kc = Kf >= 0 ? (Kf & ~smask) : -1;
     ColAcc a;
     a.P0 = a.P1 = a.P2 = 0.0;
     a.A0 = a.A1 = a.A2 = 0.0;
     a.s_il = a.s_il1 = 0.0;
-    if (Kf >= 0) {
+    if (Kc >= 0) {
       double f[3];
-      far_eval(tab + (size_t)Kf * kFarNT, p2 / pk[Kf].x, E[Kf], f);
+      far_eval(far + (size_t)(Kc >> slog) * kFarRow, p2 / pk[Kc].x, E[Kc], f);
       a.P0 = f[0]; a.P1 = f[1]; a.P2 = f[2];
-      if (il <= Kf) {   // the own shell lies in the far zone: its snapshot from the table
+      if (il <= Kc) {
+        // the own shell lies above the walk: its two roots directly, and the sum before it
+        // from the kept row at or above edge il-1 plus the (< S) edges down to il-1
         a.s_il = sqrt_pos<true>(pk[il].x - p2);
-        if (il + 1 <= Kf) a.s_il1 = sqrt_pos<true>(pk[il + 1].x - p2);
+        if (il + 1 <= Kc) a.s_il1 = sqrt_pos<true>(pk[il + 1].x - p2);
         if (il >= 1) {
-          far_eval(tab + (size_t)(il - 1) * kFarNT, p2 / pk[il - 1].x, E[il - 1], f);
+          const int Ks = (il - 1) & ~smask;
+          far_eval(far + (size_t)(Ks >> slog) * kFarRow, p2 / pk[Ks].x, E[Ks], f);
+          for (int k = Ks + 1; k <= il - 1; ++k) {
+            const double4 rec = pk[k];
+            const double sq = sqrt_pos<true>(rec.x - p2);
+            f[0] = fma(sq, rec.y, f[0]);
+            f[1] = fma(sq, rec.z, f[1]);
+            f[2] = fma(sq, rec.w, f[2]);
+          }
           a.A0 = f[0]; a.A1 = f[1]; a.A2 = f[2];
         }
       }
     }
     // lanes start at different edges: the warp walks from the smallest start with the
     // others masked until their own (a short ragged zone), then all lanes together
-    const int kmin = __reduce_min_sync(0xffffffffu, Kf), kmax = __reduce_max_sync(0xffffffffu, Kf);
+    const int kmin = __reduce_min_sync(0xffffffffu, Kc), kmax = __reduce_max_sync(0xffffffffu, Kc);
     for (int k = kmin + 1; k <= kmax; ++k) {
       const double4 rec = pk[k];
-      if (k > Kf && k <= m) col_close<true>(a, rec, sqrt_pos<true>(rec.x - p2), k, il);
+      if (k > Kc && k <= m) col_close<true>(a, rec, sqrt_pos<true>(rec.x - p2), k, il);
     }
     const int kA2 = il_w0, kB2 = il_w0 + 31 * cell_stride + 1;
     col_walk_from<U, false>(a, pk, kmax + 1, m, kA2, kB2, il, p2);
@@ -642,12 +679,20 @@ template <int THREADS, int U, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_sphere_columns_smem(PlanDev P, int cell_start, int cell_stride, int n_local,
                       const unsigned *__restrict__ items, int n_items, int *work, int nchunk,
-                      double *__restrict__ part, const double4 *__restrict__ far) {
+                      double *__restrict__ part, const double *__restrict__ far, int slog) {
   const int b = blockIdx.y;
   if (!P.active[b]) return;
   extern __shared__ double4 s_pk[];
   const int nrec = P.Nl + 1 + kPackPad;
   for (int k = threadIdx.x; k < nrec; k += THREADS) s_pk[k] = shell_record(P, b, k);
+  // kept far-field rows of this problem (k_far_moments), behind the shell records
+  double *s_far = nullptr;
+  if (far != nullptr) {
+    s_far = reinterpret_cast<double *>(s_pk + nrec);
+    const int nd = far_rows(P.Nl, slog) * kFarRow;
+    const double *g = far + (size_t)b * nd;
+    for (int i = threadIdx.x; i < nd; i += THREADS) s_far[i] = g[i];
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   // items are handed out by a per-problem counter (zeroed before the launch):
@@ -669,7 +714,7 @@ k_sphere_columns_smem(PlanDev P, int cell_start, int cell_stride, int n_local,
       pp = part + ((((size_t)b * ((P.Nmu + 1) / 2) + ip) * n_local + (valid ? j : 0)) * nchunk +
                    chunk) * kPartStride;
     sphere_ray_pair<U>(P, b, il, cell_start + jw * cell_stride, cell_stride, ip, s_pk, valid,
-                       nchunk, chunk, pp, far);
+                       nchunk, chunk, pp, s_far, slog);
     it = __shfl_sync(0xffffffffu, nxt, 0);
   }
 }

@@ -80,6 +80,46 @@ class Plan(object):
                                       C.c_int(A[4].shape[0]), _p(A[4]), _p(A[5]),
                                       si.ctypes.data_as(C.POINTER(C.c_int)), _p(zz), _p(hz)))
 
+    def set_sphere_family(self, nH0, R_cm, z, Hz=None, core_div=100.0, slope=2.0,
+                          nHe_over_nH=None, T0=1.0e4, q_min=1.0, q_max=400.0, hm12=None):
+        """Describe EVERY problem of a SphereBgnd plan by (nH0, R, z): linspace edges, a flat
+        core + power-law envelope, HM12 spectrum at z.  ``upload`` then produces all solver
+        inputs on the device (``rb_plan_set_sphere_family``).  Returns the
+        photon-energy grid [eV]."""
+        from . import rad_src
+        n = self.n_problems
+        A = [np.ascontiguousarray(a, dtype=np.float64) for a in (nH0, R_cm, z)]
+        if any(a.shape != (n,) for a in A):
+            raise ValueError("nH0, R_cm, z must have one entry per problem of the plan")
+        hz = None if Hz is None else np.ascontiguousarray(Hz, dtype=np.float64)
+        if nHe_over_nH is None:
+            nHe_over_nH = 0.25 * 0.24 / (1.0 - 0.24)
+        tab = hm12 if hm12 is not None else rad_src.HM12Table()
+        lam = np.ascontiguousarray(tab.log_lam_cm, dtype=np.float64)
+        zt = np.ascontiguousarray(tab.z, dtype=np.float64)
+        logI = np.ascontiguousarray(tab.logInu, dtype=np.float64)
+        E = np.empty(self.Nnu)
+        check(lib().rb_plan_set_sphere_family(
+            self._h, _p(A[0]), _p(A[1]), _p(A[2]), _p(hz) if hz is not None else None,
+            C.c_double(core_div), C.c_double(slope), C.c_double(nHe_over_nH), C.c_double(T0),
+            C.c_double(q_min), C.c_double(q_max), C.c_int(lam.size), C.c_int(zt.size),
+            _p(lam), _p(zt), _p(logI), _p(E)))
+        return E
+
+    def fetch_inputs(self, b):
+        """Problem ``b``'s staged inputs as the kernels see them (solver orientation)."""
+        out = dict(Edges=np.empty(self.Nl + 1), nH=np.empty(self.Nl), nHe=np.empty(self.Nl),
+                   T=np.empty(self.Nl), spec=np.empty((self.Nnu, 9)), thin=np.empty(9))
+        check(lib().rbi_plan_fetch_inputs(self._h, C.c_int(int(b)), *[_p(out[k]) for k in
+                                          ("Edges", "nH", "nHe", "T", "spec", "thin")]))
+        return out
+
+    def set_sweep_order(self, order):
+        """SphereBgnd: ``"jacobi"`` (default) or ``"gs"`` -- the reference's sequential
+        Gauss-Seidel order (``sphere_bgnd.f90:753-913`` with one OpenMP thread)."""
+        code = {"jacobi": 0, "gs": 1, "gauss-seidel": 1, 0: 0, 1: 1}[order]
+        check(lib().rb_plan_set_sweep_order(self._h, C.c_int(code)))
+
     def upload(self):
         check(lib().rb_plan_upload(self._h))
 

@@ -120,8 +120,12 @@ class SphereBgnd(_SphereBase):
     def __init__(self, Edges, T, nH, nHe, rad_src, rec_meth="fixed", fixed_fcA=1.0,
                  atomic_fit_name="hg97", find_Teq=False, z=None, Hz=None, em_H1_fac=1.0,
                  em_He1_fac=1.0, em_He2_fac=1.0, verbose=False, tol=1.0e-4, thin=False,
-                 Nmu=32):
+                 Nmu=32, sweep_order=None):
+        """``sweep_order`` (not in the reference): ``None`` / ``"jacobi"`` -- every cell sees the
+        pre-sweep state --, or ``"gs"`` -- the reference's own sequential order
+        (``sphere_bgnd.f90:753-913`` with one OpenMP thread; slow on a GPU)."""
         self.Nmu = Nmu
+        self.sweep_order = sweep_order
         self.em_H1_fac, self.em_He1_fac, self.em_He2_fac = em_H1_fac, em_He1_fac, em_He2_fac
         self._setup(Edges, T, nH, nHe, rad_src, rec_meth, fixed_fcA, atomic_fit_name,
                     find_Teq, z, Hz, verbose, tol, thin)
@@ -129,6 +133,20 @@ class SphereBgnd(_SphereBase):
         self._post()
 
     def call_fortran_solver(self):
+        import os
+        old = os.environ.get("RB_SPHERE_BGND_ORDER")
+        if self.sweep_order is not None:
+            os.environ["RB_SPHERE_BGND_ORDER"] = "gs" if str(self.sweep_order).lower().startswith("g") else "jacobi"
+        try:
+            self._call()
+        finally:
+            if self.sweep_order is not None:
+                if old is None:
+                    os.environ.pop("RB_SPHERE_BGND_ORDER", None)
+                else:
+                    os.environ["RB_SPHERE_BGND_ORDER"] = old
+
+    def _call(self):
         out = rabacus_fc.sphere_bgnd.sphere_bgnd_solve(
             self.Edges, self.nH, self.nHe, self.T, self.Nmu, self.E_eV, self.shape,
             self.i_rec_meth, self.fixed_fcA, self.i_photo_fit, self.i_rate_fit,

@@ -35,7 +35,7 @@ def run_oracle(orc, cfg, tol=1e-4, max_sweeps=0, order=None, thin=False, flavour
     return res
 
 
-def run_gpu(cfg, tol=1e-4, max_sweeps=0, thin=False, libm_pow=False, far_field=None):
+def run_gpu(cfg, tol=1e-4, max_sweeps=0, thin=False, libm_pow=False, far_field=None, order=None):
     """Through the plan API of the C ABI (same code path as the one-shot entry
     points, plus max_sweeps for sweep-level parity)."""
     Nl, Nnu = cfg["nH"].size, cfg["E_eV"].size
@@ -50,6 +50,8 @@ def run_gpu(cfg, tol=1e-4, max_sweeps=0, thin=False, libm_pow=False, far_field=N
         plan.set_libm_pow(True)
     if far_field is not None:
         plan.set_far_field(far_field)
+    if order is not None:
+        plan.set_sweep_order(order)
     if thin:
         plan.thin()
         plan.sync()

@@ -112,3 +112,25 @@ def test_struct_layouts_match_header():
     # (+ padding), 3 doubles, 1 int (+ padding)
     assert C.sizeof(_lib.rb_info) == 8 + 8 * 8 + 8
     assert C.sizeof(_lib.rb_plan_desc) == 24 + 16 + 16 + 24 + 8
+
+
+def test_photon_energies_match_the_host_producer():
+    """rb_photon_energies = rad_src.photon_energies (rad_src/source.py:178-259): numpy's
+    linspace / power / argmin statement by statement; pinned to the reference's 128-point
+    fixture through tests/test_oracle_pins.py's check of rad_src."""
+    from rabacus_b200 import rad_src
+    L = _lib.lib()
+    for Nnu in (8, 64, 128, 512):
+        for q_max in (10.0, 400.0):
+            ref, idx = rad_src.photon_energies(1.0, q_max, Nnu)
+            E = np.empty(Nnu)
+            assert L.rb_photon_energies(C.c_double(1.0), C.c_double(q_max), C.c_int(Nnu),
+                                        E.ctypes.data_as(C.POINTER(C.c_double))) == 0
+            assert np.max(np.abs(E / ref - 1.0)) <= 4.5e-16           # libm pow vs numpy's: <= 2 ulp
+            for name, Eth in (("H1", 13.60), ("He1", 24.59), ("He2", 54.42)):
+                assert E[idx[name]] == ref[idx[name]]                   # thresholds snapped exactly
+                assert abs(E[idx[name]] - Eth) < 1e-13
+    E = np.empty(16)
+    for bad in ((2.0, 400.0, 16), (1.0, 3.0, 16), (1.0, 400.0, 1)):     # the reference raises here
+        assert L.rb_photon_energies(C.c_double(bad[0]), C.c_double(bad[1]), C.c_int(bad[2]),
+                                    E.ctypes.data_as(C.POINTER(C.c_double))) == 8

@@ -120,10 +120,11 @@ def test_single_zone_api_memo(lockstep):
     rng = np.random.default_rng(7)
     nH = 10.0 ** rng.uniform(-6.0, 1.0, n)
     nHe = nH * 0.079
-    ion = [8.0e-13 * 10.0 ** rng.uniform(-4, 1, n), 5.0e-13 * 10.0 ** rng.uniform(-4, 1, n),
-           6.0e-15 * 10.0 ** rng.uniform(-4, 1, n)]
-    heat = [5.0e-24 * 10.0 ** rng.uniform(-4, 1, n), 6.0e-24 * 10.0 ** rng.uniform(-4, 1, n),
-            2.0e-25 * 10.0 ** rng.uniform(-4, 1, n)]
+    # HM12-like photo-rates scaled by a common attenuation per zone (heating per ionisation
+    # stays physical, so that the equilibrium is bracketed by [7.5e3, 1e5] K or at the floor)
+    att = 10.0 ** rng.uniform(-4.0, 0.5, n)
+    ion = [8.0e-13 * att, 5.0e-13 * att, 6.0e-15 * att]
+    heat = [5.0e-24 * att, 6.0e-24 * att, 2.0e-25 * att]
     f = fc.solve_pcte_v if lockstep else None
 
     def call(fcA):
