@@ -165,6 +165,47 @@ def segments_per_sweep(cfg, Nmu):
     return total
 
 
+FAR_RATIO, FAR_NT = 1.25, 25      # csrc/rb_far_coeffs.h
+
+
+def far_row_slog(Nl):
+    """csrc/rb_kernels.cuh far_row_slog(): every 2^slog-th far-field row is kept"""
+    slog = 3
+    while slog < 12 and (Nl + 1 + 8) * 32 + ((Nl >> slog) + 1) * 3 * FAR_NT * 8 > 226 * 1024:
+        slog += 1
+    return slog
+
+
+def column_work_executed(cfg, Nmu):
+    """What the far-field column kernel EXECUTES per sweep (csrc/rb_kernels.cuh
+    sphere_ray_pair): shell edges walked with one sqrt each (those below the last kept
+    far-field row at or above 1.25 p, plus the few edges between a kept row and the own
+    shell), and far-field series evaluations (3 x 25 fused multiply-adds each)."""
+    import numpy as np
+    from rabacus_b200 import rabacus_fc
+    E = cfg["Edges"][::-1].copy()  # decreasing, outermost first
+    Nl = E.size - 1
+    asc = E[::-1]
+    r = 0.5 * (E[:-1] + E[1:])
+    il = np.arange(Nl)
+    mu, _ = rabacus_fc.p_quadrature_rule(Nmu)
+    S = 1 << far_row_slog(Nl)
+    walked = evals = 0
+    for ip in range((Nmu + 1) // 2):
+        p = r * np.sqrt(1.0 - mu[ip] * mu[ip])
+        m = (E.size - np.searchsorted(asc, p, side="right")) - 1          # last edge > p
+        kf = (E.size - np.searchsorted(asc, p * FAR_RATIO, side="left")) - 1   # last edge >= 1.25 p
+        kf = np.minimum(kf, m)
+        kc = np.where(kf >= 0, kf - kf % S, -1)
+        walked += int(np.sum(m - kc))
+        evals += int(np.sum(kc >= 0))
+        own_far = (kc >= 0) & (il <= kc) & (il >= 1)      # own shell above the walk
+        ks = (il - 1) - (il - 1) % S
+        walked += int(np.sum(np.where(own_far, (il - 1) - ks + 2, 0)))   # + the two own roots
+        evals += int(np.sum(own_far))
+    return walked, evals
+
+
 # ------------------------------------------------------------------------------ CPU legs
 def cpu_sweep_seconds(cfg, sweeps=1, flavour=0):
     """`sweeps` Jacobi sweeps of cfg on the host cores with the oracle's timing build (the C
@@ -308,7 +349,10 @@ def c5_leg(args, rank, world, local_rank, dist, find_Teq):
     plan = Plan(configs.GEOM_IDS["sphere_bgnd"], len(idx), 512, 128, 32, find_Teq=find_Teq,
                 fixed_fcA=1.0, tol=1e-4, device=local_rank)
     t1 = time.perf_counter()
-    stage = configs.c5_stage(plan, idx, n_nH=n_nH, find_Teq=find_Teq)
+    # inputs: produced on the device from (nH0, R, z) per problem, or
+    # --c5-staging host: built with numpy on the host and copied
+    stager = configs.c5_stage_device if args.c5_staging == "device" else configs.c5_stage
+    stage = stager(plan, idx, n_nH=n_nH, find_Teq=find_Teq)
     plan.upload()
     plan.sync()
     t2 = time.perf_counter()
@@ -403,6 +447,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the c4_find_Teq / c5 / zones legs (quick runs, profiling)")
     ap.add_argument("--c5-problems", type=int, default=8192)
+    ap.add_argument("--c5-staging", default="device", choices=["device", "host"],
+                    help="C5 inputs: generated on the GPU from (nH0, R, z), or numpy + H2D copy")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the updated fractions reach the other ranks each sweep")
     args = ap.parse_args()
@@ -658,6 +704,14 @@ def main():
         k["tflops"] = 2.0 * k["alg_ops"] / (k["ms"] * 1e-3) / 1e12 if k["ms"] > 0 else 0.0
         k["frac"] = k["tflops"] / peak_tflops if peak_tflops > 0 else 0.0
         k["frac_arch"] = k["tflops"] / peak_arch_tflops
+    # the column kernel takes the far part of every ray from a moment table: what it executes
+    walked, far_evals = column_work_executed(cfg, args.Nmu)
+    exec_ops_cols = (walked * OPS_PER_SEGMENT + far_evals * 3 * FAR_NT) / world
+    kern["k_sphere_columns"]["exec_ops"] = exec_ops_cols
+    kern["k_nu_rates"]["exec_ops"] = kern["k_nu_rates"]["alg_ops"]
+    for k in kern.values():
+        k["frac_executed"] = (2.0 * k["exec_ops"] / (k["ms"] * 1e-3) / 1e12 / peak_tflops
+                              if k["ms"] > 0 and peak_tflops > 0 else 0.0)
     dom = max(kern, key=lambda n: kern[n]["ms"])
     traffic = None  # DRAM bytes per launch of that kernel from the committed ncu capture
     try:
@@ -673,6 +727,7 @@ def main():
     t_roof = (n_exp / peak["exp"] + n_sqrt / peak["sqrt"] + n_fma / peak["dfma"]
               + (args.Nl / world) * c_cell / peak["dfma"])
     step_ops = ev_local * OPS_PER_EVAL + n_seg_local * OPS_PER_SEGMENT
+    step_ops_exec = ev_local * OPS_PER_EVAL + exec_ops_cols
     roofline = {
         "bound": "fp64", "kernel": dom, "achieved": kern[dom]["tflops"], "peak": peak_tflops,
         "unit": "TFLOP/s", "frac": kern[dom]["frac"],
@@ -689,7 +744,10 @@ def main():
                 "the kernels do not call those functions (sqrt is a MUFU seed + one correction, "
                 "5 FP64 instead of ~14; exp a table + degree-4 polynomial, 8 instead of ~20), so "
                 "the library rates are not bounds for this implementation -- the DFMA issue "
-                "rate is",
+                "rate is.  k_sphere_columns: its `frac` counts the reference algorithm's work "
+                "(every shell edge above a ray's tangent point) and exceeds 1 because the kernel "
+                "takes the far part of every ray from a per-sweep moment table (DESIGN.md 4); "
+                "`frac_executed` counts the edges it walks and its series evaluations",
         "traffic": traffic,
         "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + "
                           "dram__bytes_write.sum per launch; the 33.5 MB ray buffer stays in L2)",
@@ -697,11 +755,15 @@ def main():
                        "loop trip on 32 chains, >= 50 ms), MEASURED_PEAKS.json has no FP64 figure",
         "ms_per_launch": kern[dom]["ms"], "stage_times_from": stages["source"],
         "kernels": {n: {"ms": round(v["ms"], 4), "tflops": round(v["tflops"], 3),
-                        "frac": round(v["frac"], 4), "frac_arch": round(v["frac_arch"], 4)}
+                        "frac": round(v["frac"], 4), "frac_arch": round(v["frac_arch"], 4),
+                        "frac_executed": round(v["frac_executed"], 4)}
                     for n, v in kern.items()},
         "ms_cell_solve": round(stages["ms_cell"], 4), "ms_finish": round(stages["ms_finish"], 4),
         "step_frac_of_fp64_peak": (2.0 * step_ops / (ms / K * 1e-3) / 1e12) / peak_tflops,
         "step_frac_architectural": (2.0 * step_ops / (ms / K * 1e-3) / 1e12) / peak_arch_tflops,
+        "step_frac_executed": (2.0 * step_ops_exec / (ms / K * 1e-3) / 1e12) / peak_tflops,
+        "columns_executed": {"edges_walked": walked, "far_series_evaluations": far_evals,
+                             "edges_of_the_reference_algorithm": n_seg},
         "microbench_ops_per_s": peak, "segments_per_sweep": n_seg,
     }
 

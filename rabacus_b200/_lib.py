@@ -8,7 +8,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librabacus_b200.so")
+# RB_LIBRARY selects another build of the same sources (the checked build
+# librabacus_b200_checked.so of build.py --checked: device assertions + buffer guards)
+LIB_PATH = os.environ.get("RB_LIBRARY") or os.path.join(_HERE, "librabacus_b200.so")
 
 
 class RabacusB200Error(RuntimeError):
@@ -62,7 +64,7 @@ EXPORTS = (
 # measurement / diagnostic symbols declared in rabacus_b200/csrc/rb_internal.h (not part of
 # the drop-in boundary)
 INTERNAL = ("rbi_diag_pow", "rbi_diag_hg97", "rbi_host_coefficients", "rbi_plan_set_libm_pow", "rbi_plan_set_far_field", "rbi_plan_bench_steps",
-            "rbi_microbench", "rbi_last_zone_kernel_ms", "rbi_teq_table_fetch", "rbi_plan_fetch_inputs")
+            "rbi_microbench", "rbi_last_zone_kernel_ms", "rbi_teq_table_fetch", "rbi_plan_fetch_inputs", "rbi_plan_check_guards")
 
 _lib = None
 

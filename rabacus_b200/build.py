@@ -28,6 +28,20 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
+OUT_CHECKED = os.path.join(HERE, "librabacus_b200_checked.so")
+
+
+def build_checked(verbose=False):
+    """The checked build: -DRB_DEBUG_CHECKS turns on the device-side assertions (RB_ASSERT)
+    and the guard words behind every plan buffer.  Not built by default."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    flags = [f for f in NVCC_FLAGS if f != "-O3"] + ["-O2", "-DRB_DEBUG_CHECKS"]
+    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT_CHECKED, SRC]
+    print("[rabacus_b200] " + " ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+    return OUT_CHECKED
+
+
 def build(force=False, verbose=False):
     if up_to_date() and not force:
         return OUT
@@ -41,4 +55,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    if "--checked" in sys.argv:
+        build_checked(verbose="-v" in sys.argv)
+    else:
+        build(force="--force" in sys.argv, verbose="-v" in sys.argv)

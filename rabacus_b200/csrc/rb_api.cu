@@ -141,6 +141,9 @@ extern "C" int rb_gauss_legendre(int n, double *x, double *w) {
   return RB_OK;
 }
 
+#ifdef RB_DEBUG_CHECKS
+constexpr size_t kGuardBytes = 256;
+#endif
 struct DevBuf {
   double *d = nullptr;
   size_t n = 0;
@@ -353,6 +356,7 @@ struct rb_plan {
   // device-side input producers (rb_plan_set_sphere_family): parameters of every problem,
   // the shared energy grid and the HM12 table live on the device; rb_plan_upload then
   // regenerates the inputs there instead of copying host staging
+  std::vector<std::pair<const unsigned char *, const char *>> guards;   // checked build only
   int sweep_order = RB_ORDER_JACOBI;   // SphereBgnd: RB_ORDER_GAUSS_SEIDEL = the reference's
                                        // single-thread order (rb_plan_set_sweep_order)
   bool family = false;
@@ -475,6 +479,20 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
   }
   for (int X = 0; X < 3; ++X) p->sigma_th[X] = v96_sigma(X, v96_row(X).Eth);
   const size_t B = d.n_problems, Nl = d.Nl, Nnu = d.Nnu, NC = B * Nl;
+#ifdef RB_DEBUG_CHECKS
+  // checked build: kGuardBytes of 0xA5 behind every device buffer (rbi_plan_check_guards)
+#define ALLOC(ptr, n)                                                          \
+  do {                                                                         \
+    const size_t n_ = ((size_t)(n) + 15) / 16 * 16;                            \
+    if (cudaMalloc((void **)&(ptr), n_ + kGuardBytes) != cudaSuccess) {        \
+      cudaGetLastError();                                                      \
+      rb_plan_destroy(p);                                                      \
+      return RB_ERR_NOMEM;                                                     \
+    }                                                                          \
+    cudaMemset((char *)(ptr) + n_, 0xA5, kGuardBytes);                         \
+    p->guards.emplace_back((const unsigned char *)(ptr) + n_, #ptr);           \
+  } while (0)
+#else
 #define ALLOC(ptr, n)                                                          \
   do {                                                                         \
     if (cudaMalloc((void **)&(ptr), (n)) != cudaSuccess) {                     \
@@ -483,6 +501,7 @@ extern "C" int rb_plan_create(rb_plan **out, const rb_plan_desc *desc) {
       return RB_ERR_NOMEM;                                                     \
     }                                                                          \
   } while (0)
+#endif
 #define HALLOC(ptr, n)                                                         \
   do {                                                                         \
     if (cudaMallocHost((void **)&(ptr), (n)) != cudaSuccess) {                 \
@@ -2270,6 +2289,29 @@ extern "C" void rbi_host_coefficients(double T, double fcA_H2, double fcA_He2, d
                         kl.recH2, kl.recHe2, kl.recHe3, kl.cicH1, kl.cicHe1, kl.cicHe2,
                         kl.cecH1, kl.cecHe2, kl.bremss, kl.compton};
   for (int q = 0; q < 16; ++q) out16[q] = v[q];
+}
+
+// checked build: number of guard bytes behind the plan's device buffers that no longer hold
+// the fill pattern (0 = no kernel wrote past the end of a buffer); -1 in the release build
+extern "C" int rbi_plan_check_guards(rb_plan *p, char *where, size_t wherelen) {
+  if (!p) return -2;
+#ifdef RB_DEBUG_CHECKS
+  PLAN_DEV(p);
+  cudaStreamSynchronize(p->stream);
+  int bad = 0;
+  std::vector<unsigned char> h(kGuardBytes);
+  for (const auto &g : p->guards) {
+    if (cudaMemcpy(h.data(), g.first, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    int n = 0;
+    for (unsigned char v : h) n += (v != 0xA5);
+    if (n && where && wherelen && bad == 0) snprintf(where, wherelen, "%s", g.second);
+    bad += n;
+  }
+  return bad;
+#else
+  (void)where; (void)wherelen;
+  return -1;
+#endif
 }
 
 extern "C" int rbi_teq_table_fetch(double fcA, int row0, int n, double *out16, int *depth) {

@@ -30,6 +30,19 @@
 // slab_bgnd.f90:153-155,278-282: silent stop after 200 sweeps
 #define RB_SLAB_BGND_MAX_SWEEPS 200
 
+// Checked build (rabacus_b200/build.py --checked -> librabacus_b200_checked.so): device-side
+// assertions on every computed index of the hot kernels (shared-memory records, far-field
+// rows, table offsets, work items, memo rows, peer staging) and guard words behind every
+// device buffer of a plan (rbi_plan_check_guards).  compute-sanitizer is closed on the GPU
+// pool this was developed on; scratch/sanitize_small.py runs every kernel family on small
+// grids under this build instead (profiles/r02_sanitizer.txt).
+#ifdef RB_DEBUG_CHECKS
+#include <assert.h>
+#define RB_ASSERT(c) assert(c)
+#else
+#define RB_ASSERT(c) ((void)0)
+#endif
+
 #define RB_HD __host__ __device__ __forceinline__
 // heavy bodies (dozens of pow/exp): real calls keep code size and compile time sane
 #define RB_HDN static __host__ __device__ __noinline__

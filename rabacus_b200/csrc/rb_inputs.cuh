@@ -91,6 +91,7 @@ __device__ __forceinline__ double hm12_logI(const Hm12Dev &H, int i_lo, int i_hi
   }
   if (x == H.log_lam[lo]) return f(lo);   // numpy.interp: exact at a node (the table holds
                                           // repeated wavelengths at the spectral edges)
+  RB_ASSERT(lo >= 0 && lo + 1 < n && H.log_lam[lo] <= x && x < H.log_lam[lo + 1]);
   const double f0 = f(lo), f1 = f(lo + 1);
   const double slope = (f1 - f0) / (H.log_lam[lo + 1] - H.log_lam[lo]);
   return slope * (x - H.log_lam[lo]) + f0;
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(128) k_family_spectra(FamilyDev F, double s_th
   if (H.z[i_lo] < z) { i_hi = i_lo + 1; } else { i_hi = i_lo; i_lo = i_lo - 1; }
   if (i_lo < 0) { i_lo = 0; i_hi = 1; }
   if (i_hi > H.nz - 1) { i_hi = H.nz - 1; i_lo = i_hi - 1; }
+  RB_ASSERT(i_lo >= 0 && i_hi == i_lo + 1 && i_hi < H.nz);
   const double z_frac = (z - H.z[i_lo]) / (H.z[i_hi] - H.z[i_lo]);
   const double sth[3] = {s_th0, s_th1, s_th2};
   double *tab = F.spec + (size_t)b * Nnu * kSpecStride;

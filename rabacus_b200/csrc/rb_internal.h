@@ -59,6 +59,11 @@ int rbi_teq_table_fetch(double fcA, int row0, int n, double *out16, int *depth);
 int rbi_plan_fetch_inputs(rb_plan *plan, int b, double *Edges, double *nH, double *nHe,
                           double *T, double *spec, double *thin);
 
+/* Checked build (-DRB_DEBUG_CHECKS, librabacus_b200_checked.so): how many of the guard bytes
+ * behind this plan's device buffers were overwritten (0 = none); `where` receives the name of
+ * the first damaged buffer.  Returns -1 in the release build (no guards). */
+int rbi_plan_check_guards(rb_plan *plan, char *where, size_t wherelen);
+
 /* device time [ms] of the kernel of this thread's last rb_solve_pce / rb_solve_pcte call
  * (scalar mode), for the single-zone batch line of bench.py */
 double rbi_last_zone_kernel_ms(void);

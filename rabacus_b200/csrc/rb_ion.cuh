@@ -195,6 +195,7 @@ RB_HD int teq_child(const TeqTab &tb, int node, bool neg) {
 }
 RB_HD bool teq_hit(const TeqTab &tb, int row, double T, const double *&r) {
   if (row < 0 || tb.rows == nullptr || row > teq_rows(tb)) return false;
+  RB_ASSERT(row <= (1 << tb.depth));
   r = tb.rows + (size_t)row * kTeqStride;
 #ifdef __CUDA_ARCH__
   return __ldg(r + 15) == T;

@@ -111,6 +111,7 @@ __device__ __forceinline__ void peer_scatter(const PeerDev &Q, int j, const rb_f
                                              double T) {
   const size_t n = (size_t)Q.n_local;
   const int parity = (int)(peer_sweep_id(Q) & 1ull);
+  RB_ASSERT(j >= 0 && j < Q.n_local && Q.rank < Q.world && Q.world <= kMaxPeers);
   const size_t off = ((size_t)(parity * Q.world + Q.rank) * kPeerFields) * n + j;
   for (int r = 0; r < Q.world; ++r) {
     double *d = Q.stage[r] + off;
@@ -383,6 +384,7 @@ __global__ void __launch_bounds__(128) k_far_moments(PlanDev P, double *__restri
       const double D = X == 0 ? r.y : (X == 1 ? r.z : r.w);
       far_step(M, r.x, D);
       if ((k & ((1 << slog) - 1)) == 0) {
+        RB_ASSERT((k >> slog) < far_rows(Nl, slog));
         double *row = out + (size_t)(k >> slog) * kFarRow;
 #pragma unroll
         for (int n = 0; n < kFarNT; ++n) row[3 * n] = kFarB[n] * M[n];
@@ -433,6 +435,7 @@ template <bool SNAP, int U, bool SAFE>
 __device__ __forceinline__ void col_advance(ColAcc &a, const double4 *__restrict__ pk, int kb,
                                             int ke, int il, double p2) {
   if (kb > ke) return;
+  RB_ASSERT(kb >= 0);
   int k = kb;
   double4 n[U];
 #pragma unroll
@@ -553,6 +556,7 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
     if (E[mid] <= p_ray) hi = mid; else lo = mid + 1;
   }
   const int m = hollow ? -1 : lo - 1;
+  RB_ASSERT(m >= -1 && m < Nl && (hollow || m >= il) && il >= 0 && il < Nl);
 
   if (far != nullptr) {
     // ---- far field from the kept moment rows (shared memory), the rest walked.
@@ -570,6 +574,8 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
     }
     const int smask = (1 << slog) - 1;
     const int Kc = Kf >= 0 ? (Kf & ~smask) : -1;
+    RB_ASSERT(Kf <= m && Kc <= Kf && (Kc < 0 || (Kc >> slog) < far_rows(Nl, slog)));
+    RB_ASSERT(Kc < 0 || E[Kc] >= rp);   // the series is only valid for u <= 1 / RATIO^2
     ColAcc a;
     a.P0 = a.P1 = a.P2 = 0.0;
     a.A0 = a.A1 = a.A2 = 0.0;
@@ -585,6 +591,7 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
         if (il + 1 <= Kc) a.s_il1 = sqrt_pos<true>(pk[il + 1].x - p2);
         if (il >= 1) {
           const int Ks = (il - 1) & ~smask;
+          RB_ASSERT(Ks >= 0 && Ks <= il - 1 && E[Ks] >= rp);
           far_eval(far + (size_t)(Ks >> slog) * kFarRow, p2 / pk[Ks].x, E[Ks], f);
           for (int k = Ks + 1; k <= il - 1; ++k) {
             const double4 rec = pk[k];
@@ -707,6 +714,7 @@ k_sphere_columns_smem(PlanDev P, int cell_start, int cell_stride, int n_local,
     const int chunk = (int)((item >> 12) & 0xfu);
     const int ip = (int)(item >> 16);
     const int j = jw + lane;
+    RB_ASSERT(jw < n_local && ip < (P.Nmu + 1) / 2 && chunk < nchunk);
     const bool valid = j < n_local;
     const int il = cell_start + (valid ? j : n_local - 1) * cell_stride;
     double *pp = nullptr;
@@ -908,6 +916,7 @@ __device__ __forceinline__ double exp_fast(double x, const double *s_tab, unsign
   const double r2 = r * r;
   const double pl = fma(r2, q, r);
   const unsigned off = ((unsigned)(n << 7) & (unsigned)(((1 << L) - 1) << 7)) | lane_off;
+  RB_ASSERT(off + 8u <= (unsigned)((1 << L) * kExpTabCopies * 8) && x <= 0.0 && x >= -708.5);
   const double T = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(s_tab) + off);
   const double v = fma(T, pl, T);
   // exponent: hi += (n >> L) << 20 = (n & ~(2^L - 1)) * 2^(20-L), kept as lop3 + one imad
@@ -975,6 +984,7 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int cpu) {
     if (j >= n_local || !P.active[b]) continue;
     const double *spec = P.spec + (size_t)b * Nnu * kSpecStride;
     const int il = cell_start + j * cell_stride;
+    RB_ASSERT(il >= 0 && il < Nl && b < P.B);
     const size_t c = (size_t)b * Nl + il;
     __syncthreads();  // previous cell's rays / reduction scratch are no longer read
     {

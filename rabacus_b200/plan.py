@@ -44,10 +44,20 @@ class Plan(object):
         self.geometry = geometry
         self.device = device
 
+    def check_guards(self):
+        """Checked build (``RB_LIBRARY=.../librabacus_b200_checked.so``): number of guard bytes
+        behind the plan's device buffers that a kernel overwrote; -1 in the release build."""
+        where = C.create_string_buffer(64)
+        n = lib().rbi_plan_check_guards(self._h, where, C.c_size_t(64))
+        return n, where.value.decode()
+
     def close(self):
         if self._h:
+            n, where = self.check_guards()
             lib().rb_plan_destroy(self._h)
             self._h = C.c_void_p()
+            if n > 0:
+                raise RuntimeError("checked build: %d guard bytes overwritten behind %s" % (n, where))
 
     def __del__(self):
         try:

@@ -41,12 +41,23 @@ def test_device_inputs_match_host_producers(Nl, Nnu):
         h, d = host.fetch_inputs(b), dev.fetch_inputs(b)
         assert np.array_equal(d["Edges"], h["Edges"]), "linspace edges are bit-identical"
         assert np.array_equal(d["T"], h["T"])
-        for k in ("nH", "nHe", "spec", "thin"):
+        for k in ("nH", "nHe", "thin"):
             worst[k] = max(worst.get(k, 0.0), _rel(d[k], h[k]))
-    # measured on B200: nH / nHe <= 4e-16 (device pow), table and thin integrals <= 2e-14
-    # (one ulp of log10 I_nu ~ -21 is 8e-15 of I_nu)
+        # per-frequency table: entries that matter (>= 1e-12 of their column's largest) and
+        # the rest.  Inside the He II absorption trough of the z = 6 spectrum (I_nu ~ 1e-55,
+        # 40 dex below the peak) the HM12 table is so steep that the 1-ulp difference between
+        # libm's and numpy's 10**x in the energy grid moves log10 I_nu by 3e-11.
+        big = np.abs(h["spec"]) >= 1e-12 * np.abs(h["spec"]).max(axis=0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            r = np.where(d["spec"] == h["spec"], 0.0, np.abs(d["spec"] - h["spec"]) / np.abs(h["spec"]))
+        worst["spec"] = max(worst.get("spec", 0.0), float(r[big].max()))
+        worst["spec_negligible"] = max(worst.get("spec_negligible", 0.0),
+                                       float(r[~big].max()) if (~big).any() else 0.0)
+    # measured on B200: nH / nHe 4e-16 (device pow), table 1.1e-14 and thin integrals 2e-15
+    # (one ulp of log10 I_nu ~ -21 is 8e-15 of I_nu); negligible entries 6.7e-11
     assert worst["nH"] <= 1e-15 and worst["nHe"] <= 1e-15, worst
     assert worst["spec"] <= 1e-13 and worst["thin"] <= 1e-13, worst
+    assert worst["spec_negligible"] <= 1e-9, worst
     print("device inputs vs host producers:", worst)
     host.close()
     dev.close()
