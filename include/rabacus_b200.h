@@ -289,6 +289,16 @@ int rb_plan_poll_sweep(rb_plan *plan, int *n_active);
  * Device pointers; enqueued on the plan's stream. */
 int rb_plan_pack_cells(rb_plan *plan, int cell_start, int cell_stride, double *dev_send);
 int rb_plan_unpack_cells(rb_plan *plan, int world, const double *dev_recv);
+/* The deal of a shard's cells is a (start, stride) pair everywhere in this interface:
+ * stride > 0: cyclic, il = start + j*stride; stride < 0: blocks of 32 consecutive cells
+ * dealt cyclically over W = -stride ranks, il = ((j/32) W + start) 32 + j%32 (needs the
+ * number of swept cells to be a multiple of 32 W).  rb_plan_unpack_cells takes the same code
+ * as `world`.  Peer-connected plans use the block deal where the grid allows it (the 32
+ * lanes of a ray-walk warp then hold consecutive shells); rb_plan_peer_deal returns the code
+ * to pass to rb_plan_pack_cells / rb_plan_unpack_cells for the final gather. */
+int rb_plan_peer_deal(const rb_plan *plan);
+/* local cell index j of the deal (start, stride) -> cell (host-side helper, no GPU) */
+int rb_cell_of(int j, int start, int stride);
 /* Cell sharding over peer memory (NVLink/NVSwitch), one process per GPU, no
  * collective library on the per-sweep path.  Rank `rank` of `world` (<= 8) sweeps
  * the cells il = rank + j*world of a single-problem plan.

@@ -58,7 +58,7 @@ EXPORTS = (
     "rb_plan_get_problem", "rb_plan_get_rec", "rb_plan_get_all", "rb_plan_field_ptr", "rb_plan_stream", "rb_plan_sync",
     "rb_plan_evals_per_sweep", "rb_plan_last_info", "rb_plan_pack_cells",
     "rb_plan_unpack_cells",
-    "rb_plan_peer_alloc", "rb_plan_peer_connect", "rb_plan_sweep_sharded", "rb_plan_solve_sharded",
+    "rb_plan_peer_alloc", "rb_plan_peer_connect", "rb_plan_peer_deal", "rb_cell_of", "rb_plan_sweep_sharded", "rb_plan_solve_sharded",
 )
 
 # measurement / diagnostic symbols declared in rabacus_b200/csrc/rb_internal.h (not part of

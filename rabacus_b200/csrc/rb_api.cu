@@ -382,6 +382,16 @@ struct rb_plan {
 
 static size_t cells(const rb_plan *p) { return (size_t)p->d.n_problems * p->d.Nl; }
 
+// number of local cells of the deal (start, stride) over ncell swept cells (cell_of(),
+// rb_common.cuh); -1: not a valid deal
+static int deal_n_local(int ncell, int start, int stride) {
+  if (start < 0 || stride == 0) return -1;
+  if (stride > 0) return start < ncell ? (ncell - start + stride - 1) / stride : 0;
+  const int W = -stride;
+  if (start >= W || ncell % (32 * W) != 0) return -1;
+  return ncell / W;
+}
+
 // find_Teq plans: point P.teq at the memo table of the plan's current (fcA, libm flag).
 // Called at the start of every solve (rb_plan_thin): both can change on a cached plan.
 // P is part of the graph key, so captured sweeps follow.
@@ -915,7 +925,7 @@ static int build_items(rb_plan *p, int cell_start, int cell_stride, int n_local,
     const double st = sqrt(1.0 - mu * mu);
     for (int jb = 0; jb < nblk; ++jb) {
       const int j = std::min(n_local - 1, jb * 32 + 31);
-      const int il = cell_start + j * cell_stride;
+      const int il = cell_of(j, cell_start, cell_stride);
       const double pr = 0.5 * (E[il] + E[il + 1]) * st;
       int lo = 1, hi = Nl;  // smallest i >= 1 with E_i <= p
       while (lo < hi) {
@@ -989,14 +999,14 @@ static int launch_far_moments(rb_plan *p) {
   while (cs < kMaxCluster && ((nseg + cs - 1) / cs > 42 || (long long)B * cs * 2 <= p->n_sm)) cs *= 2;
   while (cs > 1 && nseg < cs) cs /= 2;
   const int spc = (nseg + cs - 1) / cs;
-  if (3 * spc > 128) return RB_ERR_UNSUPPORTED;
+  if (3 * spc > kFarThreads) return RB_ERR_UNSUPPORTED;
   const size_t smem = far_smem_bytes(spc);
   int rc = set_smem(k_far_moments, smem);
   if (rc) return rc;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)B * cs);
-  cfg.blockDim = dim3(128);
+  cfg.blockDim = dim3(kFarThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = p->stream;
   cudaLaunchAttribute at[1];
@@ -1067,25 +1077,32 @@ static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, in
   }
   const int waves = (B > 1) ? 4 : 1;  // batches: ~4 CTAs per resident slot (finer tail)
   const int live = live_problems(p);
+  // A launch with fewer than ~3 items per warp (cell shards over 4-8 GPUs) is bound by the
+  // latency of ONE warp's walk, not by throughput: there the variant with four independent
+  // square roots per trip and half the warps runs (same operations in the same order:
+  // results are bit-identical).
+  const bool sparse = p->use_far && nchunk == 1 && cps == 1 &&
+                      (long long)p->n_items * live < (long long)3 * p->n_sm * warps;
+  const int warps_cta = sparse ? 8 : warps;
   int per_problem = std::max(1, (waves * want + live - 1) / live);
-  per_problem = std::min(per_problem, (p->n_items + warps - 1) / warps);
+  per_problem = std::min(per_problem, (p->n_items + warps_cta - 1) / warps_cta);
   // the grid spans all B problems (converged ones return at once): bound it
   per_problem = std::min(per_problem, std::max(1, (1 << 17) / B));
   dim3 g(per_problem, B);
   CK(cudaMemsetAsync(p->dwork, 0, B * sizeof(int), s));
-#define COLS(THREADS, MINB)                                                                  \
+#define COLS(THREADS, U, MINB)                                                               \
   do {                                                                                       \
-    rc = set_smem(k_sphere_columns_smem<THREADS, 1, MINB>, smem);                            \
+    rc = set_smem(k_sphere_columns_smem<THREADS, U, MINB>, smem);                            \
     if (rc) return rc;                                                                       \
-    k_sphere_columns_smem<THREADS, 1, MINB><<<g, THREADS, smem, s>>>(                        \
+    k_sphere_columns_smem<THREADS, U, MINB><<<g, THREADS, smem, s>>>(                        \
         p->P, cell_start, cell_stride, n_local, p->ditems, p->n_items, p->dwork, nchunk,     \
         p->dpart, p->use_far ? p->dfar : nullptr, p->far_slog);                              \
   } while (0)
   // 16-18 warps per SM at ~100 registers beat 24 warps at 80 (1.035 vs 1.068 ms at C4,
   // profiles/r01_kernel_variants.md)
-  if (cps == 1) COLS(512, 1);
-  else if (cps == 2) COLS(256, 2);
-  else COLS(192, 3);
+  if (cps == 1) { if (sparse) COLS(256, 4, 1); else COLS(512, 1, 1); }
+  else if (cps == 2) COLS(256, 1, 2);
+  else COLS(192, 1, 3);
 #undef COLS
   p->info.n_launches += 1;
   if (nchunk > 1) {
@@ -1338,7 +1355,7 @@ static int sweep_gauss_seidel(rb_plan *p) {
 }
 
 static int sweep_impl(rb_plan *p, int cell_start, int cell_stride, bool scatter) {
-  if (!p || cell_start < 0 || cell_stride < 1) return RB_ERR_BAD_ARG;
+  if (!p) return RB_ERR_BAD_ARG;
   PLAN_DEV(p);
   if (p->sweep_order == RB_ORDER_GAUSS_SEIDEL && p->d.geometry == RB_GEOM_SPHERE_BGND) {
     // sequential in the cells: no cell shards (replicas only in this mode)
@@ -1350,7 +1367,8 @@ static int sweep_impl(rb_plan *p, int cell_start, int cell_stride, bool scatter)
   const int Nl = p->d.Nl, B = p->d.n_problems, g = p->d.geometry;
   const bool two = (g == RB_GEOM_SLAB_PLANE_2 || g == RB_GEOM_SLAB_BGND);
   const int ncell = two ? Nl / 2 : Nl;  // slab_bgnd.f90:686 (Nl2 = Nl/2)
-  const int n_local = (cell_start < ncell) ? (ncell - cell_start + cell_stride - 1) / cell_stride : 0;
+  const int n_local = deal_n_local(ncell, cell_start, cell_stride);
+  if (n_local < 0) return RB_ERR_BAD_ARG;
   cudaStream_t s = p->stream;
   cudaEvent_t *sev = p->sev[p->sweeps_issued % kSlots];
   int rc = RB_OK;
@@ -1438,6 +1456,11 @@ extern "C" int rb_plan_peer_alloc(rb_plan *p, int rank, int world, unsigned char
   memcpy(handle, &h, 64);
   p->Q.world = 1;  // not usable until rb_plan_peer_connect
   p->Q.rank = rank; p->Q.n_local = n_local;
+  // 32-cell blocks dealt over the ranks where the grid allows it (compact ray walks per
+  // warp, see cell_of()); RB_PEER_DEAL=cyclic keeps single cells
+  const char *de = getenv("RB_PEER_DEAL");
+  const bool cyc = (de && (de[0] == 'c' || de[0] == 'C')) || ncell % (32 * world) != 0;
+  p->Q.deal = cyc ? world : -world;
   p->peer_world = world;
   p->peer_base[rank] = p->dpeer;
   return RB_OK;
@@ -1481,7 +1504,7 @@ extern "C" int rb_plan_sweep_sharded(rb_plan *p) {
   if (!p || p->Q.world < 2) return RB_ERR_BAD_ARG;
   if (p->sweeps_issued - p->sweeps_polled >= kSlots - 1) return RB_ERR_BAD_ARG;  // poll first
   PLAN_DEV(p);
-  int rc = sweep_impl(p, p->Q.rank, p->Q.world, true);
+  int rc = sweep_impl(p, p->Q.rank, p->Q.deal, true);
   if (rc) return rc;
   const int slot = (int)(p->sweeps_issued % kSlots);
   PeerDev Q = p->Q;
@@ -1562,7 +1585,7 @@ static int sweep_graph(rb_plan *p, bool sharded) {
     p->capturing = true;
     int rc;
     if (sharded) {
-      rc = sweep_impl(p, p->Q.rank, p->Q.world, true);
+      rc = sweep_impl(p, p->Q.rank, p->Q.deal, true);
       if (!rc) rc = exchange_body(p, p->Q, slot);
     } else {
       rc = sweep_impl(p, 0, 1, false);
@@ -1635,11 +1658,11 @@ static int plan_sweep_cells(const rb_plan *p) {
 }
 
 extern "C" int rb_plan_pack_cells(rb_plan *p, int cell_start, int cell_stride, double *dev_send) {
-  if (!p || !dev_send || cell_start < 0 || cell_stride < 1 || p->d.n_problems != 1)
-    return RB_ERR_BAD_ARG;
+  if (!p || !dev_send || p->d.n_problems != 1) return RB_ERR_BAD_ARG;
   PLAN_DEV(p);
   const int ncell = plan_sweep_cells(p);
-  const int n_local = (cell_start < ncell) ? (ncell - cell_start + cell_stride - 1) / cell_stride : 0;
+  const int n_local = deal_n_local(ncell, cell_start, cell_stride);
+  if (n_local < 0) return RB_ERR_BAD_ARG;
   if (n_local > 0) {
     dim3 g((n_local + 127) / 128, kExchangeFields);
     k_pack_cells<<<g, 128, 0, p->stream>>>(p->P, cell_start, cell_stride, n_local, dev_send);
@@ -1650,16 +1673,26 @@ extern "C" int rb_plan_pack_cells(rb_plan *p, int cell_start, int cell_stride, d
 }
 
 extern "C" int rb_plan_unpack_cells(rb_plan *p, int world, const double *dev_recv) {
-  if (!p || !dev_recv || world < 1 || p->d.n_problems != 1) return RB_ERR_BAD_ARG;
+  // world > 0: cyclic deal il = j*world + g; world < 0: 32-cell blocks over -world ranks
+  if (!p || !dev_recv || world == 0 || p->d.n_problems != 1) return RB_ERR_BAD_ARG;
   PLAN_DEV(p);
   const int ncell = plan_sweep_cells(p);
-  if (ncell % world != 0) return RB_ERR_BAD_ARG;
-  const int n_local = ncell / world;
-  dim3 g((n_local + 127) / 128, kExchangeFields, world);
+  const int W = world > 0 ? world : -world;
+  if (ncell % W != 0 || deal_n_local(ncell, 0, world) < 0) return RB_ERR_BAD_ARG;
+  const int n_local = ncell / W;
+  dim3 g((n_local + 127) / 128, kExchangeFields, W);
   k_unpack_cells<<<g, 128, 0, p->stream>>>(p->P, world, n_local, dev_recv);
   p->info.n_launches += 1;
   CK(cudaGetLastError());
   return RB_OK;
+}
+
+// the deal of a peer-connected plan's cells (cell_of() stride code: +world cyclic, -world
+// 32-cell blocks), for rb_plan_pack_cells / rb_plan_unpack_cells; 1 when not connected
+extern "C" int rb_cell_of(int j, int start, int stride) { return cell_of(j, start, stride); }
+
+extern "C" int rb_plan_peer_deal(const rb_plan *p) {
+  return (p && p->dpeer) ? p->Q.deal : 1;
 }
 
 extern "C" long long rb_plan_evals_per_sweep(const rb_plan *p) {

@@ -44,6 +44,23 @@
 #endif
 
 #define RB_HD __host__ __device__ __forceinline__
+
+// Local cell index j of a rank -> cell il.  Two deals of the swept cells over ranks:
+//   stride > 0  cyclic: il = start + j * stride (start = rank, stride = world)
+//   stride < 0  32-cell BLOCKS dealt cyclically over W = -stride ranks (start = rank):
+//               il = ((j / 32) W + rank) 32 + j % 32 -- the 32 lanes of a column-kernel warp
+//               then hold 32 CONSECUTIVE shells whatever the world size, so a shard's ray
+//               walks are as compact as a single GPU's (cyclic cells at W = 8 spread a warp
+//               over 256 shells and cost 2.5x the instructions per ray); the ray cost still
+//               balances over the ranks because the blocks interleave.  Needs
+//               (cells to sweep) % (32 W) == 0.
+static __host__ __device__ __forceinline__ int cell_of(int j, int start, int stride) {
+  return stride > 0 ? start + j * stride : ((((j >> 5) * (-stride)) + start) << 5) + (j & 31);
+}
+// distance in cells between neighbouring lanes of a warp
+static __host__ __device__ __forceinline__ int lane_stride_of(int stride) {
+  return stride > 0 ? stride : 1;
+}
 // heavy bodies (dozens of pow/exp): real calls keep code size and compile time sane
 #define RB_HDN static __host__ __device__ __noinline__
 

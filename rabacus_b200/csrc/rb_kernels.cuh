@@ -94,7 +94,9 @@ constexpr int kMaxPeers = 8;
 constexpr int kPeerCtl = 16;
 constexpr unsigned long long kPeerPoison = ~0ull;   // flag value: "a rank gave up, abort"
 struct PeerDev {
-  int world, rank, n_local, pad_;
+  int world, rank, n_local;
+  int deal;                               // cell_of() stride code of the shard: +world cyclic,
+                                          // -world 32-cell blocks
   unsigned long long timeout_ns;          // barrier timeout (RB_ERR_PEER_TIMEOUT)
   unsigned long long *ctl;                // this rank's control words (own buffer + kPeerCtl)
   double *stage[kMaxPeers];               // rank r's staging [2][world][6][n_local]
@@ -235,6 +237,7 @@ __device__ __forceinline__ double sqrt_pos(double x) {
 // ---------------------------------------------------------------------------
 constexpr int kFarNT = RB_FAR_NT;
 constexpr int kFarSeg = 32;           // edges per scan segment (fixed: part of the rounding)
+constexpr int kMaxClusterFar = 8;     // CTAs per cluster of k_far_moments (= kMaxCluster)
 constexpr int kFarRow = 3 * kFarNT;   // doubles per kept row: [NT][3 absorbers]
 __constant__ double kFarB[kFarNT] = {RB_FAR_COEFFS};
 
@@ -261,9 +264,9 @@ __device__ __forceinline__ double far_g(const double *E, int K) {
 
 // one step of the NT recurrences, f_n = g^(2n-1) generated as two interleaved chains
 // (even n from 1/g, odd n from g, both stepped by g^4)
-__device__ __forceinline__ void far_step(double (&M)[kFarNT], double g, double D) {
+__device__ __forceinline__ void far_step(double (&M)[kFarNT], double g, double ginv, double D) {
   const double g2 = g * g, g4 = g2 * g2;
-  double fe = g > 0.0 ? 1.0 / g : 0.0, fo = g;
+  double fe = ginv, fo = g;   // ginv = 1/g (0 where g = 0), formed once per edge by the fill
 #pragma unroll
   for (int n = 0; n < kFarNT; n += 2) {
     M[n] = fma(M[n], fe, D);
@@ -284,6 +287,7 @@ __device__ __forceinline__ void far_step(double (&M)[kFarNT], double g, double D
 // far: [B][Nl/S + 1][NT][3] doubles {HI, HeI, HeII}.
 struct FarSmem {
   double4 *rec;     // [spc * kFarSeg] {g, D0, D1, D2}
+  double *ginv;     // [spc * kFarSeg] 1/g
   double *sA;       // [spc][NT]
   double *sB;       // [spc][3][NT]
   double *cA;       // [NT]      CTA composite
@@ -291,11 +295,12 @@ struct FarSmem {
   double *cin;      // [3][NT]   CTA carry-in
 };
 __host__ __device__ inline size_t far_smem_bytes(int spc) {
-  return (size_t)spc * kFarSeg * sizeof(double4) +
+  return (size_t)spc * kFarSeg * (sizeof(double4) + sizeof(double)) +
          ((size_t)spc * kFarNT * 4 + 7 * kFarNT) * sizeof(double);
 }
 
-__global__ void __launch_bounds__(128) k_far_moments(PlanDev P, double *__restrict__ far,
+constexpr int kFarThreads = 256;   // 3 * segments-per-CTA of them scan, all of them fill
+__global__ void __launch_bounds__(kFarThreads) k_far_moments(PlanDev P, double *__restrict__ far,
                                                      int csize, int spc, int slog) {
   namespace cg = cooperative_groups;
   extern __shared__ double4 s_far4[];
@@ -306,7 +311,8 @@ __global__ void __launch_bounds__(128) k_far_moments(PlanDev P, double *__restri
   const int nmine = seg1 - seg0;
   FarSmem S;
   S.rec = s_far4;
-  S.sA = reinterpret_cast<double *>(s_far4 + (size_t)spc * kFarSeg);
+  S.ginv = reinterpret_cast<double *>(s_far4 + (size_t)spc * kFarSeg);
+  S.sA = S.ginv + (size_t)spc * kFarSeg;
   S.sB = S.sA + (size_t)spc * kFarNT;
   S.cA = S.sB + (size_t)spc * 3 * kFarNT;
   S.cB = S.cA + kFarNT;
@@ -317,8 +323,17 @@ __global__ void __launch_bounds__(128) k_far_moments(PlanDev P, double *__restri
     const int k0 = seg0 * kFarSeg, k1 = min(nedge, seg1 * kFarSeg);
     for (int k = k0 + (int)threadIdx.x; k < k1; k += blockDim.x) {
       const double4 r = shell_record(P, b, k);
-      S.rec[k - k0] = make_double4(far_g(E, k), r.y, r.z, r.w);
+      const double g = far_g(E, k);
+      S.rec[k - k0] = make_double4(g, r.y, r.z, r.w);
+      S.ginv[k - k0] = g > 0.0 ? 1.0 / g : 0.0;
+      // by-product: the shell records of the sweep in global memory, so that the column
+      // kernel's CTAs copy them (16-byte loads) instead of each rebuilding all Nl + 1 of
+      // them from six state arrays -- 148 CTAs x 4097 records x 11 loads at C4
+      P.pack[(size_t)b * (nedge + kPackPad) + k] = r;
     }
+    if (crank == csize - 1 && threadIdx.x < kPackPad)
+      P.pack[(size_t)b * (nedge + kPackPad) + nedge + threadIdx.x] =
+          make_double4(0.0, 0.0, 0.0, 0.0);
   }
   __syncthreads();
   const int t = threadIdx.x;
@@ -333,7 +348,7 @@ __global__ void __launch_bounds__(128) k_far_moments(PlanDev P, double *__restri
     for (int k = kb; k < ke; ++k) {
       const double4 r = S.rec[k - seg0 * kFarSeg];
       const double D = X == 0 ? r.y : (X == 1 ? r.z : r.w);
-      far_step(M, r.x, D);
+      far_step(M, r.x, S.ginv[k - seg0 * kFarSeg], D);
       G = G * r.x;
     }
 #pragma unroll
@@ -360,12 +375,20 @@ __global__ void __launch_bounds__(128) k_far_moments(PlanDev P, double *__restri
   if (csize > 1) cg::this_cluster().sync(); else __syncthreads();
   if (t < 3 * kFarNT) {   // carry into this CTA from the CTAs before it
     const int X2 = t / kFarNT, n = t - X2 * kFarNT;
-    double ci = 0.0;
-    for (int c = 0; c < crank; ++c) {
-      const double *rA = cg::this_cluster().map_shared_rank(S.cA, c);
-      const double *rB = cg::this_cluster().map_shared_rank(S.cB, c);
-      ci = fma(ci, rA[n], rB[X2 * kFarNT + n]);
+    // (the remote reads of all earlier CTAs are issued before the dependent chain starts)
+    double ra[kMaxClusterFar], rb_[kMaxClusterFar];
+#pragma unroll
+    for (int c = 0; c < kMaxClusterFar; ++c) {
+      ra[c] = 1.0; rb_[c] = 0.0;
+      if (c < crank) {
+        ra[c] = cg::this_cluster().map_shared_rank(S.cA, c)[n];
+        rb_[c] = cg::this_cluster().map_shared_rank(S.cB, c)[X2 * kFarNT + n];
+      }
     }
+    double ci = 0.0;
+#pragma unroll
+    for (int c = 0; c < kMaxClusterFar; ++c)
+      if (c < crank) ci = fma(ci, ra[c], rb_[c]);
     S.cin[X2 * kFarNT + n] = ci;
   }
   __syncthreads();
@@ -382,7 +405,7 @@ __global__ void __launch_bounds__(128) k_far_moments(PlanDev P, double *__restri
     for (int k = kb; k < ke; ++k) {
       const double4 r = S.rec[k - seg0 * kFarSeg];
       const double D = X == 0 ? r.y : (X == 1 ? r.z : r.w);
-      far_step(M, r.x, D);
+      far_step(M, r.x, S.ginv[k - seg0 * kFarSeg], D);
       if ((k & ((1 << slog) - 1)) == 0) {
         RB_ASSERT((k >> slog) < far_rows(Nl, slog));
         double *row = out + (size_t)(k >> slog) * kFarRow;
@@ -607,9 +630,23 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
     // lanes start at different edges: the warp walks from the smallest start with the
     // others masked until their own (a short ragged zone), then all lanes together
     const int kmin = __reduce_min_sync(0xffffffffu, Kc), kmax = __reduce_max_sync(0xffffffffu, Kc);
-    for (int k = kmin + 1; k <= kmax; ++k) {
-      const double4 rec = pk[k];
-      if (k > Kc && k <= m) col_close<true>(a, rec, sqrt_pos<true>(rec.x - p2), k, il);
+    {
+      int k = kmin + 1;
+      for (; k + U - 1 <= kmax; k += U) {   // U independent roots per trip, closed in edge order
+        double4 rec[U];
+        double sq[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) rec[u] = pk[k + u];
+#pragma unroll
+        for (int u = 0; u < U; ++u) sq[u] = sqrt_pos<true>(rec[u].x - p2);   // (k > m: unused)
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (k + u > Kc && k + u <= m) col_close<true>(a, rec[u], sq[u], k + u, il);
+      }
+      for (; k <= kmax; ++k) {
+        const double4 rec = pk[k];
+        if (k > Kc && k <= m) col_close<true>(a, rec, sqrt_pos<true>(rec.x - p2), k, il);
+      }
     }
     const int kA2 = il_w0, kB2 = il_w0 + 31 * cell_stride + 1;
     col_walk_from<U, false>(a, pk, kmax + 1, m, kA2, kB2, il, p2);
@@ -661,9 +698,10 @@ k_sphere_columns(PlanDev P, int cell_start, int cell_stride, int n_local) {
   if (!P.active[b]) return;
   const int j = blockIdx.x * BLOCK + threadIdx.x;
   if (j >= n_local) return;
-  const int il = cell_start + j * cell_stride;
+  const int il = cell_of(j, cell_start, cell_stride);
   const int lane = threadIdx.x & 31;
-  sphere_ray_pair<U>(P, b, il, il - lane * cell_stride, cell_stride, blockIdx.y,
+  const int ls = lane_stride_of(cell_stride);
+  sphere_ray_pair<U>(P, b, il, il - lane * ls, ls, blockIdx.y,
                      P.pack + (size_t)b * (P.Nl + 1 + kPackPad), true);
 }
 
@@ -691,7 +729,12 @@ k_sphere_columns_smem(PlanDev P, int cell_start, int cell_stride, int n_local,
   if (!P.active[b]) return;
   extern __shared__ double4 s_pk[];
   const int nrec = P.Nl + 1 + kPackPad;
-  for (int k = threadIdx.x; k < nrec; k += THREADS) s_pk[k] = shell_record(P, b, k);
+  if (far != nullptr) {   // records of this sweep as left by k_far_moments
+    const double4 *g = P.pack + (size_t)b * nrec;
+    for (int k = threadIdx.x; k < nrec; k += THREADS) s_pk[k] = g[k];
+  } else {
+    for (int k = threadIdx.x; k < nrec; k += THREADS) s_pk[k] = shell_record(P, b, k);
+  }
   // kept far-field rows of this problem (k_far_moments), behind the shell records
   double *s_far = nullptr;
   if (far != nullptr) {
@@ -716,12 +759,13 @@ k_sphere_columns_smem(PlanDev P, int cell_start, int cell_stride, int n_local,
     const int j = jw + lane;
     RB_ASSERT(jw < n_local && ip < (P.Nmu + 1) / 2 && chunk < nchunk);
     const bool valid = j < n_local;
-    const int il = cell_start + (valid ? j : n_local - 1) * cell_stride;
+    const int il = cell_of(valid ? j : n_local - 1, cell_start, cell_stride);
     double *pp = nullptr;
     if (nchunk > 1)
       pp = part + ((((size_t)b * ((P.Nmu + 1) / 2) + ip) * n_local + (valid ? j : 0)) * nchunk +
                    chunk) * kPartStride;
-    sphere_ray_pair<U>(P, b, il, cell_start + jw * cell_stride, cell_stride, ip, s_pk, valid,
+    sphere_ray_pair<U>(P, b, il, cell_of(jw, cell_start, cell_stride),
+                       lane_stride_of(cell_stride), ip, s_pk, valid,
                        nchunk, chunk, pp, s_far, slog);
     it = __shfl_sync(0xffffffffu, nxt, 0);
   }
@@ -737,7 +781,7 @@ __global__ void k_columns_combine(PlanDev P, int cell_start, int cell_stride, in
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int ip = blockIdx.y;
   if (j >= n_local) return;
-  const int il = cell_start + j * cell_stride;
+  const int il = cell_of(j, cell_start, cell_stride);
   const int Nl = P.Nl;
   const double *E = P.Edges + (size_t)b * (Nl + 1);
   const double mu = P.mu[ip];
@@ -983,7 +1027,7 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int cpu) {
     const int b = u / upp, j = (u % upp) * cpu + q;
     if (j >= n_local || !P.active[b]) continue;
     const double *spec = P.spec + (size_t)b * Nnu * kSpecStride;
-    const int il = cell_start + j * cell_stride;
+    const int il = cell_of(j, cell_start, cell_stride);
     RB_ASSERT(il >= 0 && il < Nl && b < P.B);
     const size_t c = (size_t)b * Nl + il;
     __syncthreads();  // previous cell's rays / reduction scratch are no longer read
@@ -1093,7 +1137,7 @@ k_cell_solve(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_local)
   if (!P.active[b]) return;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_local) return;
-  const int il = cell_start + j * cell_stride;
+  const int il = cell_of(j, cell_start, cell_stride);
   const size_t c = (size_t)b * P.Nl + il;
   PhotoRates p;  // total = source + recombination photons (sphere_bgnd.f90:861-881)
   p.H1i = P.src[0][c] + P.rec[0][c]; p.He1i = P.src[1][c] + P.rec[1][c];
@@ -1171,7 +1215,7 @@ k_cell_solve_pce_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int
   const int t = blockIdx.x * 128 + threadIdx.x;
   const int j = t / G, sub = t % G;
   const bool valid = j < n_local;
-  const int il = cell_start + (valid ? j : n_local - 1) * cell_stride;
+  const int il = cell_of(valid ? j : n_local - 1, cell_start, cell_stride);
   const int lane = threadIdx.x & 31, gbase = lane & ~(G - 1);
   const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
   const size_t c = (size_t)b * P.Nl + il;
@@ -1273,7 +1317,7 @@ k_cell_solve_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int n_l
   const int t = blockIdx.x * 128 + threadIdx.x;
   const int j = t / G, sub = t % G;
   const bool valid = j < n_local;
-  const int il = cell_start + (valid ? j : n_local - 1) * cell_stride;
+  const int il = cell_of(valid ? j : n_local - 1, cell_start, cell_stride);
   const int lane = threadIdx.x & 31, gbase = lane & ~(G - 1);
   const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
   const size_t c = (size_t)b * P.Nl + il;
@@ -1506,7 +1550,7 @@ __global__ void __launch_bounds__(BLOCK) k_exchange_finish(PlanDev P, PeerDev Q,
     const bool two = two_sided(P.geom);
     for (int i = blockIdx.x * BLOCK + threadIdx.x; i < ncell; i += gridDim.x * BLOCK) {
       const int g = i / Q.n_local, j = i - g * Q.n_local;
-      const int il = j * Q.world + g;
+      const int il = cell_of(j, g, Q.deal);
 #pragma unroll
       for (int f = 0; f < kPeerFields; ++f) {
         const double v = __ldcv(st + ((size_t)g * kPeerFields + f) * n + j);
@@ -1561,14 +1605,14 @@ __global__ void k_pack_cells(PlanDev P, int cell_start, int cell_stride, int n_l
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y;
   if (j >= n_local) return;
-  send[(size_t)f * n_local + j] = plan_field(P, f)[cell_start + j * cell_stride];
+  send[(size_t)f * n_local + j] = plan_field(P, f)[cell_of(j, cell_start, cell_stride)];
 }
 
-__global__ void k_unpack_cells(PlanDev P, int world, int n_local, const double *recv) {
+__global__ void k_unpack_cells(PlanDev P, int deal, int n_local, const double *recv) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y, g = blockIdx.z;
   if (j >= n_local) return;
-  const int il = j * world + g;
+  const int il = cell_of(j, g, deal);
   const double v = recv[((size_t)g * gridDim.y + f) * n_local + j];
   double *dst = plan_field(P, f);
   dst[il] = v;

@@ -53,7 +53,7 @@ __device__ __forceinline__ bool plan_outer_first(int geom) { return geom == RB_G
 struct RecCells {
   int start, stride, n_local, n_total;
   __device__ __forceinline__ int cell(int j, int Nl) const {
-    return j < n_local ? start + j * stride : Nl / 2;
+    return j < n_local ? cell_of(j, start, stride) : Nl / 2;
   }
 };
 

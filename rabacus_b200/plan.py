@@ -295,10 +295,14 @@ class Plan(object):
         import torch.distributed as dist
         send, recv = self.shard_buffers(world)
         ext = torch.cuda.ExternalStream(self.stream_ptr)
+        # the deal of a peer-connected plan (cyclic cells, or 32-cell blocks: cell_of() in
+        # csrc/rb_common.cuh) decides which cells this rank packs and where they land
+        deal = lib().rb_plan_peer_deal(self._h) if getattr(self, "_peer", None) else world
+        deal = deal if abs(deal) == world else world
         with torch.cuda.stream(ext):
-            self.pack_cells(rank, world, send.data_ptr())
+            self.pack_cells(rank, deal, send.data_ptr())
             dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
-            self.unpack_cells(world, recv.data_ptr())
+            self.unpack_cells(deal, recv.data_ptr())
         self.sync()
 
     def enqueue_sharded_sweep(self, rank, world, send, recv, group=None):

@@ -31,7 +31,7 @@ def _fake_sweep(fields, cells, sweep):
     return out
 
 
-def _worker(rank, world, port, Nl, mirror, q):
+def _worker(rank, world, port, Nl, mirror, q, deal=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -42,11 +42,11 @@ def _worker(rank, world, port, Nl, mirror, q):
         fields[:, Nl - ncell:] = fields[:, :ncell][:, ::-1]
     nloc = ncell // world
     for sweep in range(3):
-        new = _fake_sweep(fields, sharding.local_cells(rank, world, ncell), sweep)
-        send = torch.from_numpy(sharding.pack_cells(new, rank, world, ncell))
+        new = _fake_sweep(fields, sharding.local_cells(rank, world, ncell, deal), sweep)
+        send = torch.from_numpy(sharding.pack_cells(new, rank, world, ncell, deal))
         recv = torch.empty((world, 12, nloc), dtype=torch.float64)
         dist.all_gather_into_tensor(recv.view(-1), send.view(-1))
-        sharding.unpack_cells(recv.numpy(), fields, world, ncell, mirror=mirror)
+        sharding.unpack_cells(recv.numpy(), fields, world, ncell, mirror=mirror, deal=deal)
     # every rank must now hold the same full state
     t = torch.from_numpy(fields.copy())
     ref = t.clone()
@@ -60,13 +60,16 @@ def _worker(rank, world, port, Nl, mirror, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mirror", [False, True])
-def test_cell_sharded_exchange_equals_single_rank(mirror):
-    Nl, world = 24, 2
+@pytest.mark.parametrize("mirror,Nl,deal", [(False, 24, None), (True, 24, None),
+                                            (False, 128, -2), (True, 256, -2)])
+def test_cell_sharded_exchange_equals_single_rank(mirror, Nl, deal):
+    """cyclic deal (NCCL path) and the 32-cell block deal of the peer path"""
+    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, Nl, mirror, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, Nl, mirror, q, deal))
+             for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(world)]
@@ -86,6 +89,28 @@ def test_cell_sharded_exchange_equals_single_rank(mirror):
         if mirror:
             f[:, Nl - ncell:] = new[:, :ncell][:, ::-1]
     assert np.array_equal(got, f)
+
+
+def test_block_deal_matches_the_library():
+    """sharding.cell_of is the twin of csrc/rb_common.cuh cell_of (exported as rb_cell_of);
+    both deals are permutations of the swept cells, and a block-dealt warp of 32 local cells
+    holds 32 consecutive shells."""
+    import ctypes as C
+    from rabacus_b200 import _lib
+    L = _lib.lib()
+    for world, ncell in ((2, 128), (4, 4096), (8, 4096), (8, 256)):
+        assert sharding.peer_deal(world, ncell) == -world
+        seen = []
+        for g in range(world):
+            for stride in (world, -world):
+                idx = sharding.local_cells(g, world, ncell, stride)
+                got = [L.rb_cell_of(C.c_int(j), C.c_int(g), C.c_int(stride)) for j in range(idx.size)]
+                assert list(idx) == got
+            blk = sharding.local_cells(g, world, ncell, -world)
+            assert np.all(np.diff(blk.reshape(-1, 32), axis=1) == 1)
+            seen.append(blk)
+        assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(ncell))
+    assert sharding.peer_deal(8, 4000) == 8 and sharding.peer_deal(2, 33) == 2   # falls back
 
 
 def test_index_conventions():
