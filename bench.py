@@ -713,12 +713,15 @@ def main():
         k["frac_executed"] = (2.0 * k["exec_ops"] / (k["ms"] * 1e-3) / 1e12 / peak_tflops
                               if k["ms"] > 0 and peak_tflops > 0 else 0.0)
     dom = max(kern, key=lambda n: kern[n]["ms"])
-    traffic = None  # DRAM bytes per launch of that kernel from the committed ncu capture
+    traffic = traffic_pipe = None  # DRAM bytes per launch of that kernel from the committed ncu captures
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f)["bytes_per_launch"].get(dom) if world == 1 else None
+            tj = json.load(f)
+        if world == 1:
+            traffic = tj["bytes_per_launch"].get(dom)
+            traffic_pipe = tj.get("bytes_per_launch_in_pipeline", {}).get(dom)
     except Exception:
-        traffic = None
+        traffic = traffic_pipe = None
     # SURVEY 8(d)'s formula with the LIBRARY rates measured in this run:
     #   T_roof = N_exp/R_exp + N_sqrt/R_sqrt + (N_fma,nu + N_fma,ray)/R_fma + N_cell c_cell/R_fma
     c_cell = 1.5e5 if args.find_Teq else 1.0e3
@@ -748,9 +751,14 @@ def main():
                 "(every shell edge above a ray's tangent point) and exceeds 1 because the kernel "
                 "takes the far part of every ray from a per-sweep moment table (DESIGN.md 4); "
                 "`frac_executed` counts the edges it walks and its series evaluations",
-        "traffic": traffic,
-        "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + "
-                          "dram__bytes_write.sum per launch; the 33.5 MB ray buffer stays in L2)",
+        "traffic": traffic, "traffic_in_pipeline": traffic_pipe,
+        "traffic_source": "profiles/ncu_traffic.json: ncu --set full, dram__bytes_read.sum + "
+                          "dram__bytes_write.sum per launch.  `traffic` is ncu's default (L2 "
+                          "flushed before every replay: the kernel re-reads the 33.5 MB ray-record "
+                          "buffer from DRAM); `traffic_in_pipeline` is the same capture with "
+                          "--cache-control none, i.e. what the sweep sees: the buffer the column "
+                          "kernel just wrote is read back from L2.  Algorithmic bytes per launch: "
+                          "33.5 MB of ray records + < 1 MB of state",
         "peak_source": "measured in this run: DFMA micro-benchmark (rbi_microbench: 64 FMAs per "
                        "loop trip on 32 chains, >= 50 ms), MEASURED_PEAKS.json has no FP64 figure",
         "ms_per_launch": kern[dom]["ms"], "stage_times_from": stages["source"],

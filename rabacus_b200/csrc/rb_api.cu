@@ -1118,46 +1118,50 @@ static int launch_nu_rates(rb_plan *p, int cell_start, int cell_stride, int n_lo
   const int B = p->d.n_problems, Nnu = p->d.Nnu, g = p->d.geometry;
   cudaStream_t s = p->stream;
   int rc = RB_OK;
-#define NU(ATT, KU, RU, BLOCK, MINB, LTAB)                                                   \
+#define NU(ATT, KU, RU, BLOCK, MINB, LTAB, CPB)                                              \
   do {                                                                                       \
     const int ndir_pad = (p->Ndir + RU - 1) / RU * RU;                                       \
-    const size_t smem = (size_t)ndir_pad * sizeof(double4);                                  \
-    rc = set_smem(k_nu_rates<ATT, KU, RU, BLOCK, MINB, LTAB>, smem);                         \
+    const size_t smem = (size_t)ndir_pad * sizeof(double4) * CPB;                            \
+    rc = set_smem(k_nu_rates<ATT, KU, RU, BLOCK, MINB, LTAB, CPB>, smem);                    \
     if (rc) return rc;                                                                       \
     int occ = 1;                                                                             \
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                           \
-        &occ, k_nu_rates<ATT, KU, RU, BLOCK, MINB, LTAB>, BLOCK, smem);                      \
+        &occ, k_nu_rates<ATT, KU, RU, BLOCK, MINB, LTAB, CPB>, BLOCK, smem);                 \
     /* 4 CTAs per resident slot: the hardware scheduler evens out the tail (+3 %) */       \
     const long long want = (long long)p->n_sm * std::max(1, occ) * 4;                        \
     /* cells per work unit: 16 in a full batch (a CTA re-reads one problem's frequency   */ \
-    /* table from L1), fewer when few problems are left (>= 2 units per resident CTA),   */ \
-    /* bounded below so that the flat unit list stays under 2^20 entries                 */ \
+    /* table from L1), fewer when few problems are left (>= 2 units per resident cell    */ \
+    /* slot), bounded below so that the flat unit list stays under 2^20 entries          */ \
     int cpu = 1;                                                                             \
     if (B > 1) {                                                                             \
-      const long long slots = (long long)p->n_sm * std::max(1, occ);                         \
+      const long long slots = (long long)p->n_sm * std::max(1, occ) * CPB;                   \
       const long long fit = (long long)live_problems(p) * n_local / (2 * slots);             \
       cpu = (int)std::min<long long>(16, std::max<long long>(1, fit));                       \
       while (cpu < 16 && (long long)B * ((n_local + cpu - 1) / cpu) > (1ll << 20)) cpu *= 2; \
       cpu = std::min(cpu, n_local);                                                          \
     }                                                                                        \
     const long long units = (long long)((n_local + cpu - 1) / cpu) * B;                      \
-    dim3 gn((unsigned)std::min<long long>(want, units));                                     \
-    k_nu_rates<ATT, KU, RU, BLOCK, MINB, LTAB><<<gn, BLOCK, smem, s>>>(                      \
+    dim3 gn((unsigned)std::min<long long>(want, (units + CPB - 1) / CPB));                   \
+    k_nu_rates<ATT, KU, RU, BLOCK, MINB, LTAB, CPB><<<gn, BLOCK, smem, s>>>(                 \
         p->P, cell_start, cell_stride, n_local, cpu);                                        \
   } while (0)
   // thread <-> 4 frequencies, 2 rays in flight: 8 independent exp chains per thread
   if (g == RB_GEOM_SLAB_BGND) {
-    if (Nnu <= 32) NU(1, 1, 1, 32, 8, 0);
-    else if (Nnu <= 64) NU(1, 1, 1, 64, 4, 0);
-    else NU(1, 1, 1, 128, 3, 0);
+    if (Nnu <= 32) NU(1, 1, 1, 32, 8, 0, 1);
+    else if (Nnu <= 64) NU(1, 1, 1, 64, 4, 0, 1);
+    else NU(1, 1, 1, 128, 3, 0, 1);
   } else {
-    // timed on B200 (profiles/r01_kernel_variants.md): 4 frequencies x 2 rays in flight
-    // for wide grids; one warp per cell, 4 frequencies x 1 ray, 16 warps/SM for Nnu <= 128.
-    // exp table: 256 entries (degree-4 polynomial) where one CTA serves 128 threads,
-    // 64 entries (degree 5) for the small CTAs
-    if (Nnu <= 128) NU(0, 4, 1, 32, 16, 6);
-    else if (Nnu <= 256) NU(0, 4, 2, 64, 6, 6);
-    else NU(0, 4, 2, 128, 4, 8);
+    // timed on B200 (profiles/r01_kernel_variants.md, r02_kernel_variants.md): 4 frequencies
+    // x 2 rays in flight for wide grids; one warp per cell, 4 frequencies x 1 ray, 16 warps
+    // per SM for Nnu <= 128.  exp table: 1024 entries x 4 copies + cubic (11 FP64 per
+    // evaluation) where 128 threads share it -- one cell per CTA on wide grids, four cells
+    // (one per warp) on narrow ones; RB_NU_LTAB=8 / 6 select the round-1 tables (256
+    // entries, degree 4 / 64 entries, degree 5, one 32-thread CTA per cell) for A/B runs
+    const char *le = getenv("RB_NU_LTAB");
+    const int lt = le ? atoi(le) : 10;
+    if (Nnu <= 128) { if (lt == 10) NU(0, 4, 1, 128, 4, 10, 4); else NU(0, 4, 1, 32, 16, 6, 1); }
+    else if (Nnu <= 256) NU(0, 4, 2, 64, 6, 6, 1);
+    else { if (lt == 10) NU(0, 4, 2, 128, 4, 10, 1); else NU(0, 4, 2, 128, 4, 8, 1); }
   }
 #undef NU
   p->info.n_launches += 1;

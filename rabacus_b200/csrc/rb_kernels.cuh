@@ -916,6 +916,12 @@ __global__ void __launch_bounds__(BLOCK) k_column_taus(PlanDev P) {
 // exp() of the hot loops.
 // ---------------------------------------------------------------------------
 constexpr int kExpTabCopies = 16;
+// copies of the 2^L-entry table: 16 (a half-warp's lookups never conflict) up to L = 8;
+// the 1024-entry table is kept 4 times (32 KB, ~2-way conflicts) -- see exp_fast
+template <int L> struct ExpTab {
+  static constexpr int copies = (L >= 10) ? 4 : kExpTabCopies;
+  static constexpr int shift = (L >= 10) ? 5 : 7;   // byte offset of entry j: j * copies * 8
+};
 
 // exp(x) for -708 <= x <= 0 with a 2^L-entry table (L = 6: degree-5 polynomial,
 // L = 8: degree 4), 8 / 7 FP64 instructions + 6 integer / load instructions:
@@ -936,6 +942,12 @@ __constant__ double kExpF6[7] = {92.33248261689366,          // 64/ln2
                                  -1.0830424696249145e-02,    // -ln2/64
                                  8.3333333333333332e-03, 4.1666666666666664e-02,
                                  1.6666666666666666e-01, 0.5, 6755399441055744.0};
+// L = 10: |r| <= ln2/2048 = 3.4e-4, cubic 1 + r + r^2 (c2 + r/6) with c2 = 1/2 + (sqrt2 - 1)/12 a^2
+// (equal-ripple against the dropped r^4/24: max error 9.4e-17), one FP64 instruction less
+__constant__ double kExpF10[7] = {1477.3197218702985,        // 1024/ln2
+                                  -0.0006769015435155716,    // -ln2/1024
+                                  0.0, 0.0, 1.6666666666666666e-01, 0.5000000039539765,
+                                  6755399441055744.0};
 __constant__ double kExpF8[7] = {369.32993046757463,         // 256/ln2
                                  -2.7076061740622863e-03,    // -ln2/256
                                  0.0, 4.1666666666666664e-02,
@@ -943,14 +955,16 @@ __constant__ double kExpF8[7] = {369.32993046757463,         // 256/ln2
 
 template <int L>
 __device__ __forceinline__ double exp_fast(double x, const double *s_tab, unsigned lane_off) {
-  const double *C = (L >= 8) ? kExpF8 : kExpF6;
+  const double *C = (L >= 10) ? kExpF10 : ((L >= 8) ? kExpF8 : kExpF6);
   x = __hiloint2double((int)min((unsigned)__double2hiint(x), 0xC0862000u), __double2loint(x));
   const double t = fma(x, C[0], C[6]);
   const int n = __double2loint(t);
   const double nd = t - C[6];
   const double r = fma(nd, C[1], x);
   double q;
-  if (L >= 8) {
+  if (L >= 10) {
+    q = C[4];
+  } else if (L >= 8) {
     q = fma(r, C[3], C[4]);
   } else {
     q = fma(r, C[2], C[3]);
@@ -959,8 +973,9 @@ __device__ __forceinline__ double exp_fast(double x, const double *s_tab, unsign
   q = fma(r, q, C[5]);
   const double r2 = r * r;
   const double pl = fma(r2, q, r);
-  const unsigned off = ((unsigned)(n << 7) & (unsigned)(((1 << L) - 1) << 7)) | lane_off;
-  RB_ASSERT(off + 8u <= (unsigned)((1 << L) * kExpTabCopies * 8) && x <= 0.0 && x >= -708.5);
+  constexpr int SH = ExpTab<L>::shift;
+  const unsigned off = ((unsigned)(n << SH) & (unsigned)(((1 << L) - 1) << SH)) | lane_off;
+  RB_ASSERT(off + 8u <= (unsigned)((1 << L) * ExpTab<L>::copies * 8) && x <= 0.0 && x >= -708.5);
   const double T = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(s_tab) + off);
   const double v = fma(T, pl, T);
   // exponent: hi += (n >> L) << 20 = (n & ~(2^L - 1)) * 2^(20-L), kept as lop3 + one imad
@@ -976,7 +991,7 @@ __device__ __forceinline__ void fill_exp_table_L(double *s_exp) {
   for (int j = threadIdx.x; j < (1 << L); j += blockDim.x) {
     const double v = exp2((double)j * (1.0 / (double)(1 << L)));
 #pragma unroll
-    for (int c = 0; c < kExpTabCopies; ++c) s_exp[j * kExpTabCopies + c] = v;
+    for (int c = 0; c < ExpTab<L>::copies; ++c) s_exp[j * ExpTab<L>::copies + c] = v;
   }
 }
 
@@ -1002,19 +1017,27 @@ __device__ __forceinline__ void fill_exp_table_L(double *s_exp) {
 // Algorithmic FP64 work per (ray, nu): 3 + 10 + 1 = 14 instructions.
 // grid = a few waves of CTAs striding over the flat list of (problem, unit of cells).
 // ---------------------------------------------------------------------------
-template <int ATT_E2, int KU, int RU, int BLOCK, int MINB, int LTAB>
+// CPB = 1: the whole CTA works on one cell.  CPB > 1 (narrow frequency grids): every WARP of
+// the CTA works on its own cell (BLOCK = 32 CPB) -- the warps only share the exp table, so a
+// 1024-entry table serves 4 cells and the CTA count per SM stays low.
+template <int ATT_E2, int KU, int RU, int BLOCK, int MINB, int LTAB, int CPB = 1>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int cpu) {
+  static_assert(CPB == 1 || BLOCK == 32 * CPB, "one warp per cell");
+  constexpr int CT = (CPB > 1) ? 32 : BLOCK;   // threads working on one cell
   extern __shared__ double4 s_dyn4[];
-  double4 *s_ray = s_dyn4;                                     // [ndir_pad]
   const int Nnu = P.Nnu, Nl = P.Nl, ndir = P.Ndir;
   const int ndir_pad = (ndir + RU - 1) / RU * RU;
-  __shared__ double s_exp[ATT_E2 ? 1 : (1 << LTAB) * kExpTabCopies];   // [2^LTAB][16]
-  __shared__ double s_red[6][BLOCK / 32];
+  __shared__ double s_exp[ATT_E2 ? 1 : (1 << LTAB) * ExpTab<LTAB>::copies];   // [2^LTAB][copies]
+  __shared__ double s_red[6][CT / 32];
   if (!ATT_E2) fill_exp_table_L<LTAB>(s_exp);
-  const unsigned lane_off = (threadIdx.x & (kExpTabCopies - 1)) << 3;
+  if (CPB > 1) __syncthreads();   // (CPB = 1: the first barrier of the cell loop covers it)
+  const unsigned lane_off = (threadIdx.x & (ExpTab<LTAB>::copies - 1)) << 3;
 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tid = (CPB > 1) ? lane : (int)threadIdx.x;        // thread index within the cell
+  double4 *s_ray = s_dyn4 + ((CPB > 1) ? wid * ndir_pad : 0);   // [ndir_pad] per cell in flight
+  auto cell_sync = [&]() { if (CPB > 1) __syncwarp(); else __syncthreads(); };
 
   // the grid is one wave of CTAs striding over the flat list of (problem, local cell):
   // balanced to one cell whatever the batch size, also while problems drop out
@@ -1022,7 +1045,7 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int cpu) {
   // re-reads one problem's frequency table from L1 instead of a new one from L2 per cell)
   const int upp = (n_local + cpu - 1) / cpu;   // units per problem
   const int n_units = P.B * upp;
-  for (int u = blockIdx.x; u < n_units; u += gridDim.x)
+  for (int u = blockIdx.x * CPB + ((CPB > 1) ? wid : 0); u < n_units; u += gridDim.x * CPB)
   for (int q = 0; q < cpu; ++q) {
     const int b = u / upp, j = (u % upp) * cpu + q;
     if (j >= n_local || !P.active[b]) continue;
@@ -1030,7 +1053,7 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int cpu) {
     const int il = cell_of(j, cell_start, cell_stride);
     RB_ASSERT(il >= 0 && il < Nl && b < P.B);
     const size_t c = (size_t)b * Nl + il;
-    __syncthreads();  // previous cell's rays / reduction scratch are no longer read
+    cell_sync();  // previous cell's rays / reduction scratch are no longer read
     {
       const double4 *g = P.col + col_index(P, b, il, 0);
       // A ray whose optical depth exceeds 708 at EVERY frequency (lower bound: each species'
@@ -1041,19 +1064,19 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int cpu) {
       // get weight 0, i.e. exactly the reference's zero.
       const double *th = P.thin + (size_t)b * kThinStride;
       const double m0 = th[6], m1 = th[7], m2 = th[8];
-      for (int i = threadIdx.x; i < ndir_pad; i += BLOCK) {
+      for (int i = tid; i < ndir_pad; i += CT) {
         double4 r = (i < ndir) ? g[i] : make_double4(0.0, 0.0, 0.0, 0.0);  // pad: weight 0
         if (!ATT_E2 && r.x * m0 + r.y * m1 + r.z * m2 > 708.0) r.w = 0.0;
         s_ray[i] = r;
       }
     }
-    __syncthreads();
+    cell_sync();
     double part[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int k0 = 0; k0 < Nnu; k0 += BLOCK * KU) {
+    for (int k0 = 0; k0 < Nnu; k0 += CT * KU) {
       double n0[KU], n1[KU], n2[KU], A[KU];
 #pragma unroll
       for (int u = 0; u < KU; ++u) {
-        const int k = k0 + u * BLOCK + threadIdx.x;
+        const int k = k0 + u * CT + tid;
         const bool has = k < Nnu;
         const double *row = spec + (size_t)(has ? k : 0) * kSpecStride;
         n0[u] = has ? -row[0] : 0.0;  // -ra_X: the loop forms -tau
@@ -1078,7 +1101,7 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int cpu) {
       }
 #pragma unroll
       for (int u = 0; u < KU; ++u) {
-        const int k = k0 + u * BLOCK + threadIdx.x;
+        const int k = k0 + u * CT + tid;
         if (k < Nnu) {
           const double *row = spec + (size_t)k * kSpecStride;
 #pragma unroll
@@ -1094,13 +1117,13 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int cpu) {
       for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
       part[q] = v;
     }
-    if (BLOCK > 32) {
+    if (CT > 32) {
       if (lane == 0)
 #pragma unroll
         for (int q = 0; q < 6; ++q) s_red[q][wid] = part[q];
       __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       double scale = 1.0;
       if (P.geom == RB_GEOM_SPHERE_STROMGREN) {
         // point source dilution 1/(4 pi r_c^2): source_point.f90:348
@@ -1111,9 +1134,9 @@ k_nu_rates(PlanDev P, int cell_start, int cell_stride, int n_local, int cpu) {
 #pragma unroll
       for (int q = 0; q < 6; ++q) {
         double v = part[q];
-        if (BLOCK > 32) {
+        if (CT > 32) {
           v = 0.0;
-          for (int w = 0; w < BLOCK / 32; ++w) v += s_red[q][w];
+          for (int w = 0; w < CT / 32; ++w) v += s_red[q][w];
         }
         v *= scale;
         if (P.geom == RB_GEOM_SPHERE_BGND) v = (P.src[q][c] + v) * 0.5;
