@@ -44,12 +44,12 @@ METRIC = "SphereBgnd cell*ray*freq evals/s"
 UNIT = "evals/s"
 
 # algorithmic FP64-pipe operations of THIS implementation (DESIGN.md "Roofline"):
-#   frequency kernel, per (cell, ray, nu): 3 (tau = sum_X tau_X ra_X) + 8 (exp: scale,
-#   round, reduce, 4 polynomial, table merge) + 1 (A(nu) += w_ray a); the six rate
+#   frequency kernel, per (cell, ray, nu): 3 (tau = sum_X tau_X ra_X) + 7 (exp: scale,
+#   round, reduce, 3 polynomial, table merge) + 1 (A(nu) += w_ray a); the six rate
 #   accumulations are per (cell, nu), 1/Nmu of that, and are not counted
 #   column kernel, per shell edge of a ray pair: 1 (E^2 - p^2) + 5 (sqrt: MUFU seed + one
 #   third-order correction) + 3 (column FMAs, summed by parts: P += s_k (c_k - c_{k-1}))
-OPS_PER_EVAL = 12
+OPS_PER_EVAL = 11    # 3 (tau) + 7 (exp: 1024-entry table + cubic) + 1 (A += w a)
 OPS_PER_SEGMENT = 9
 
 
@@ -739,13 +739,13 @@ def main():
         "survey_model": {"T_roof_ms": t_roof * 1e3, "T_measured_ms": ms / K, "N_exp": n_exp,
                          "N_sqrt": n_sqrt, "N_fma": n_fma, "c_cell": c_cell,
                          "R_exp": peak["exp"], "R_sqrt": peak["sqrt"], "R_fma": peak["dfma"]},
-        "note": "frac = this implementation's own FP64 instruction recipe (9 per shell edge, 12 "
+        "note": "frac = this implementation's own FP64 instruction recipe (9 per shell edge, 11 "
                 "per evaluation, x2 flop) / the kernel's launch time, against the DFMA rate "
                 "measured in this run; frac_architectural uses 64 DFMA/clk/SM x SMs x max clock. "
                 "frac_survey_model = T_roof / T_measured with SURVEY 8(d)'s formula and the "
                 "measured rates of CUDA's exp()/sqrt() LIBRARY functions: it exceeds 1 because "
                 "the kernels do not call those functions (sqrt is a MUFU seed + one correction, "
-                "5 FP64 instead of ~14; exp a table + degree-4 polynomial, 8 instead of ~20), so "
+                "5 FP64 instead of ~14; exp a 1024-entry table + cubic, 7 instead of ~20), so "
                 "the library rates are not bounds for this implementation -- the DFMA issue "
                 "rate is.  k_sphere_columns: its `frac` counts the reference algorithm's work "
                 "(every shell edge above a ray's tangent point) and exceeds 1 because the kernel "

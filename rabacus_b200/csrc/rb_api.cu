@@ -968,9 +968,16 @@ static int build_items(rb_plan *p, int cell_start, int cell_stride, int n_local,
   return RB_OK;
 }
 
+// opt in to more than 48 KB of shared memory per CTA (static + dynamic) where a launch needs it
 template <typename K>
 static int set_smem(K kern, size_t smem) {
-  if (smem > 48 * 1024)
+  size_t stat = 0;
+  if (smem > 0 && smem <= 48 * 1024) {
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, kern));
+    stat = fa.sharedSizeBytes;
+  }
+  if (smem + stat > 48 * 1024)
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return RB_OK;
 }
