@@ -12,15 +12,19 @@ sphere: ray-segment columns -> fused tau/exp/quadrature -> per-cell equilibrium
 solve -> convergence test.
 
 * ``value``: K sweeps with the problem resident in HBM, every sweep bracketed by CUDA
-  events on the stream the kernels run on.  N > 1: the cells are dealt cyclically over
-  the ranks, the new fractions travel as remote stores over NVLink peer memory and one
+  events on the stream the kernels run on.  N > 1: the cells are dealt over the ranks in
+  32-cell blocks (cyclically), the new fractions travel as remote stores over NVLink peer memory and one
   flag barrier ends the sweep (no collective; ``--exchange nccl`` selects an all-gather
   instead); strong scaling: total work fixed, time = max over ranks.  At N > 1 the timed
   sweeps are replayed as CUDA graphs, as rb_plan_solve does.
 * ``e2e``: the same metric through the reference-facing C-ABI entry point
   ``rb_sphere_bgnd_solve`` with HOST buffers: upload, optically-thin start, sweeps to
   convergence (tol 1e-4), download; evaluations of the whole solve / wall time of the call.
-* ``roofline``: the dominant kernel against the FP64 pipe, two ways (see ``note`` there).
+* ``roofline``: the dominant kernel against the FP64 pipe: the implementation's FP64
+  recipe against the DFMA rate measured in this run and against the architectural peak,
+  the work it executes (the column kernel takes the far part of every ray from a moment
+  table), SURVEY 8(d)'s library-rate model, and DRAM traffic from the committed ncu
+  captures (see ``note`` / ``traffic_source`` there).
 * ``cpu_baseline``: the C restatement of the reference (oracle/, "port": the Fortran
   cannot be built here), -O3 -mtune=native build, on this box's host cores.
   ``--impl reference`` times that arm alone, with all host threads.
@@ -790,12 +794,13 @@ def main():
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": bench_config(args),
-        "parallelism": "cells dealt cyclically over %d GPU(s)%s"
-                       % (world, "" if world == 1 else
-                          (", fractions exchanged by remote stores over NVLink peer memory + flag "
-                           "barrier (no collective per sweep), sweeps replayed as CUDA graphs"
-                           if args.exchange == "peer" else
-                           ", NCCL all-gather of 18 state fields per sweep")),
+        "parallelism": ("all cells on one GPU" if world == 1 else
+                        ("cells dealt over %d GPUs in 32-cell blocks, fractions exchanged by remote "
+                         "stores over NVLink peer memory + flag barrier (no collective per sweep), "
+                         "sweeps replayed as CUDA graphs" % world
+                         if args.exchange == "peer" else
+                         "cells dealt cyclically over %d GPUs, NCCL all-gather of 18 state fields "
+                         "per sweep" % world)),
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "clocks": sampler.summary() if sampler else None,
         "solve": {"sweeps_to_converge": iters, "wall_ms": solve_ms},

@@ -508,14 +508,14 @@ __device__ __forceinline__ void col_walk(ColAcc &a, const double4 *__restrict__ 
 __device__ __forceinline__ void store_ray_pair(const PlanDev &P, int b, int il, int ip, int m,
                                                double mu, const double (&Pm)[3],
                                                const double (&Pa)[3], double s_il,
-                                               double s_il1) {
+                                               double s_il1, const double3 &c0,
+                                               const double3 &c1) {
   const int imu_in = ip, imu_out = P.Nmu - 1 - ip;
   double Nout[3], Nin[3];
   if (il == m) {
 #pragma unroll
     for (int X = 0; X < 3; ++X) Nout[X] = Nin[X] = Pm[X];
   } else {
-    const double3 c0 = shell_dens(P, b, il - 1), c1 = shell_dens(P, b, il);
     const double cm[3] = {c0.x, c0.y, c0.z}, cc[3] = {c1.x, c1.y, c1.z};
     const double ds = s_il - s_il1;
 #pragma unroll
@@ -547,6 +547,51 @@ __device__ __forceinline__ void store_ray_pair(const PlanDev &P, int b, int il, 
 // chunk `chunk` only, leaving its partial sums {P, P before the own shell, the two
 // own-shell roots, flags} in `part` for k_columns_combine -- finer work items for
 // launches with few rays.
+// The two searches of a ray pair on the monotone (non-increasing) edges.  They run on the
+// squared edges of the shell records -- shared memory -- and are then VERIFIED on the edges
+// themselves with two independent loads (rounding is monotone, so E_i <= p implies
+// fl(E_i^2) <= fl(p^2), but two edges within an ulp of p can square to the same double); a
+// failed check repeats the search on the edges.  Result: the reference's index, always, with
+// 2 instead of ~12 dependent global loads per search (only ~20 KB of L1 remain beside the
+// kernel's shared memory, so those loads mostly went to L2: the latency floor of a launch
+// with few rays per warp).
+// smallest i in [lo0, Nl] with E_i <= p, given E_Nl <= p (m_for_ray, geometry.f90:61-71)
+__device__ __forceinline__ int first_edge_le(const double *__restrict__ E,
+                                             const double4 *__restrict__ pk, int lo0, int Nl,
+                                             double p, double p2) {
+  int lo = lo0, hi = Nl;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (pk[mid].x <= p2) hi = mid; else lo = mid + 1;
+  }
+  const double e1 = E[lo], e0 = E[lo > lo0 ? lo - 1 : lo0];
+  if ((lo == Nl || e1 <= p) && (lo == lo0 || e0 > p)) return lo;
+  lo = lo0; hi = Nl;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (E[mid] <= p) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+// largest a in [0, m] with E_a >= rp, given E_0 >= rp
+__device__ __forceinline__ int last_edge_ge(const double *__restrict__ E,
+                                            const double4 *__restrict__ pk, int m, double rp,
+                                            double rp2) {
+  int a0 = 0, a1 = m;
+  while (a0 < a1) {
+    const int mid = (a0 + a1 + 1) >> 1;
+    if (pk[mid].x >= rp2) a0 = mid; else a1 = mid - 1;
+  }
+  const double e0 = E[a0], e1 = E[a0 < m ? a0 + 1 : m];
+  if (e0 >= rp && (a0 == m || e1 < rp)) return a0;
+  a0 = 0; a1 = m;
+  while (a0 < a1) {
+    const int mid = (a0 + a1 + 1) >> 1;
+    if (E[mid] >= rp) a0 = mid; else a1 = mid - 1;
+  }
+  return a0;
+}
+
 constexpr int kPartStride = 9;
 template <int U>
 __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il, int il_w0,
@@ -572,12 +617,11 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
     if (far == nullptr) return;
     store = false;   // (the far path is warp-collective: the lane stays, with an empty walk)
   }
-  int lo = il + 1, hi = Nl;  // E_il >= r_ray >= p: the answer is > il
+  // the own shell's absorber densities (store_ray_pair): loaded now, used after the walk
+  const double3 c_prev = shell_dens(P, b, il - 1), c_own = shell_dens(P, b, il);
+  int lo = il + 1;  // E_il >= r_ray >= p: the answer is > il
   if (E[il] <= p_ray) lo = 1;  // degenerate (zero-width shells): full search
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (E[mid] <= p_ray) hi = mid; else lo = mid + 1;
-  }
+  lo = first_edge_le(E, pk, lo, Nl, p_ray, p2);
   const int m = hollow ? -1 : lo - 1;
   RB_ASSERT(m >= -1 && m < Nl && (hollow || m >= il) && il >= 0 && il < Nl);
 
@@ -587,14 +631,7 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
     // it.  Called by all 32 lanes.
     const double rp = p_ray * RB_FAR_RATIO;
     int Kf = -1;
-    if (m >= 0 && E[0] >= rp) {
-      int a0 = 0, a1 = m;
-      while (a0 < a1) {
-        const int mid = (a0 + a1 + 1) >> 1;
-        if (E[mid] >= rp) a0 = mid; else a1 = mid - 1;
-      }
-      Kf = a0;
-    }
+    if (m >= 0 && E[0] >= rp) Kf = last_edge_ge(E, pk, m, rp, rp * rp);
     const int smask = (1 << slog) - 1;
     const int Kc = Kf >= 0 ? (Kf & ~smask) : -1;
     RB_ASSERT(Kf <= m && Kc <= Kf && (Kc < 0 || (Kc >> slog) < far_rows(Nl, slog)));
@@ -652,7 +689,7 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
     col_walk_from<U, false>(a, pk, kmax + 1, m, kA2, kB2, il, p2);
     if (!store) return;
     const double Pm2[3] = {a.P0, a.P1, a.P2}, Pa2[3] = {a.A0, a.A1, a.A2};
-    store_ray_pair(P, b, il, ip, m, mu, Pm2, Pa2, a.s_il, a.s_il1);
+    store_ray_pair(P, b, il, ip, m, mu, Pm2, Pa2, a.s_il, a.s_il1, c_prev, c_own);
     return;
   }
 
@@ -677,7 +714,7 @@ __device__ __forceinline__ void sphere_ray_pair(const PlanDev &P, int b, int il,
   if (!store) return;
   const double Pm[3] = {a.P0, a.P1, a.P2}, Pa[3] = {a.A0, a.A1, a.A2};
   if (nchunk == 1) {
-    store_ray_pair(P, b, il, ip, m, mu, Pm, Pa, a.s_il, a.s_il1);
+    store_ray_pair(P, b, il, ip, m, mu, Pm, Pa, a.s_il, a.s_il1, c_prev, c_own);
     return;
   }
   // chunk partials: the chunk sum, and what the own shell's edges left in this chunk
@@ -810,7 +847,8 @@ __global__ void k_columns_combine(PlanDev P, int cell_start, int cell_stride, in
 #pragma unroll
     for (int X = 0; X < 3; ++X) Pm[X] = Pm[X] + q[X];
   }
-  store_ray_pair(P, b, il, ip, m, mu, Pm, Pa, s_il, s_il1);
+  store_ray_pair(P, b, il, ip, m, mu, Pm, Pa, s_il, s_il1, shell_dens(P, b, il - 1),
+                 shell_dens(P, b, il));
 }
 
 // ---------------------------------------------------------------------------
