@@ -7,7 +7,9 @@ bisection paths can be compared step by step; ``np.longdouble``: 64-bit mantissa
 "truth" the float64 codings are measured against).  It keeps the reference's loop
 structure (per-segment ds_segment calls, six separate frequency integrals), so it is slow
 and only used at small sizes by tests/test_second_oracle.py to pin the C oracle:
-one Jacobi sweep of SphereBgnd, one sweep of Slab2Bgnd, solve_pce_s, solve_pcte_s.
+one sweep of every geometry -- SphereBgnd (Jacobi order and the reference's sequential
+Gauss-Seidel order), Slab2Bgnd, SlabPln, Slab2Pln, SphereStromgren (monochromatic and
+polychromatic point source) -- and the single-zone solvers solve_pce_s, solve_pcte_s.
 """
 import numpy as np
 
@@ -233,14 +235,17 @@ def _cell_solve(nH, nHe, T, r6, fcA, find_Teq, z, Hz, tol_in, F):
 
 
 def sphere_bgnd_jacobi_sweep(Edges, nH, nHe, T, x, src, mu, wmu, E_eV, shape, fcA, find_Teq,
-                             z, Hz, tol, F, cells=None):
-    """One sweep of sphere_bgnd.f90:578-918 in Jacobi order from state ``x`` [5][Nl] and
-    source rates ``src`` [6][Nl] (Edges decreasing).  Returns (x_new, T_new, src_new) for
-    ``cells`` (default all)."""
+                             z, Hz, tol, F, cells=None, gauss_seidel=False):
+    """One sweep of sphere_bgnd.f90:578-918 from state ``x`` [5][Nl] and source rates ``src``
+    [6][Nl] (Edges decreasing).  Returns (x_new, T_new, src_new) for ``cells`` (default all).
+    Jacobi order by default; ``gauss_seidel``: the loop exactly as the reference runs it with
+    one thread (:753-913) -- every cell's new fractions and temperature are stored back before
+    the next (inner) cell is traced."""
     E = np.asarray(Edges, dtype=F)
     Ev, sh = np.asarray(E_eV, dtype=F), np.asarray(shape, dtype=F)
     nH_, nHe_ = np.asarray(nH, dtype=F), np.asarray(nHe, dtype=F)
-    x = np.asarray(x, dtype=F)
+    x = np.array(x, dtype=F)
+    T = np.array(T, dtype=F)
     sig = [sigma_v96(X, Ev, F) for X in range(3)]
     sth = [sigma_v96(X, np.array([V96[X][0]]), F)[0] for X in range(3)]   # :213-215
     ra = [sig[X] / sth[X] for X in range(3)]
@@ -269,6 +274,10 @@ def sphere_bgnd_jacobi_sweep(Edges, nH, nHe, T, x, src, mu, wmu, E_eV, shape, fc
         xs, Tn = _cell_solve(nH_[il], nHe_[il], T[il], acc, fcA, find_Teq, z, Hz,
                              F(tol) * F(1.0e-2), F)
         out[il] = (xs, Tn, acc)
+        if gauss_seidel:                                                # :886-907 in place
+            for q in range(5):
+                x[q][il] = xs[q]
+            T[il] = Tn
     return out
 
 
@@ -308,6 +317,66 @@ def slab_bgnd_sweep(Edges, nH, nHe, T, x, E_eV, shape, fcA, find_Teq, z, Hz, tol
             att = (np.ones_like(tau) if _ssum(tau) == 0                  # s_b.f90:380-383
                    else np.array([_e2xa(t, F) for t in tau], dtype=F))
             r6 = [a + r * F(0.5) for a, r in zip(r6, _six_rates(Ev, sh, sig, att, F))]
+        xs, Tn = _cell_solve(nH_[i], nHe_[i], T[i], r6, fcA, find_Teq, z, Hz,
+                             F(tol) * F(1.0e-2), F)
+        out[i] = (xs, Tn, r6)
+    return out
+
+
+def _src_rates(kind, E, shape, sig, att, F, r=None):
+    """The six integrals of a plane ('plane': source_plane.f90:178-342) or point ('point':
+    source_point.f90:226-395) source seen through attenuation ``att``, each evaluated on its
+    own as the reference does; ``r``: shell-centre radius (point source dilution)."""
+    Eth = [F(v[0]) for v in V96]
+    four, pi = F(4.0), F(PI)
+    if E.size == 1:                             # monochromatic branches (nn == 1)
+        Fn = shape[0] / E[0] * F(ERG2EV)        # s_plane.f90:101 / s_point.f90:104
+        if kind == "point":
+            Fn = Fn / (four * pi * r * r)       # s_point.f90:149-158
+        ion = [Fn * s[0] * att[0] for s in sig]
+        heat = [Fn * s[0] * (E[0] - t) * F(EV2ERG) * att[0] for s, t in zip(sig, Eth)]
+        return ion + heat
+    if kind == "point":
+        base = shape / (E * F(H_ERG) * four * pi * r * r)   # s_point.f90:346
+    else:
+        base = shape / (E * F(H_ERG))                       # s_plane.f90:296
+    ion = [_trap(E, base * s * att) for s in sig]
+    heat = [_trap(E, base * s * att * (E - t) * F(EV2ERG)) for s, t in zip(sig, Eth)]
+    return ion + heat
+
+
+def column_sweep(geom, Edges, nH, nHe, T, x, E_eV, shape, fcA, find_Teq, z, Hz, tol, F,
+                 cells=None):
+    """One (Jacobi) sweep of the three column geometries from state ``x`` [5][Nl]:
+    'slab_plane_1' (slab_plane.f90:551-830, source at the z = 0 face), 'slab_plane_2'
+    (:832-1164: half of the flux from either side; only the first half is solved, the rest
+    is the mirrored copy) and 'sphere_stromgren' (sphere_stromgren.f90:595-878, increasing
+    Edges, source at the centre).  Optical depths to a layer: the layers below (slab_base.f90:
+    63-115 / sphere_base.f90:1232-1367, plain left-to-right sums) plus half of its own."""
+    E = np.asarray(Edges, dtype=F)
+    Ev, sh = np.asarray(E_eV, dtype=F), np.asarray(shape, dtype=F)
+    nH_, nHe_, x = np.asarray(nH, dtype=F), np.asarray(nHe, dtype=F), np.asarray(x, dtype=F)
+    sig = [sigma_v96(X, Ev, F) for X in range(3)]
+    sth = [sigma_v96(X, np.array([V96[X][0]]), F)[0] for X in range(3)]
+    ra = [sig[X] / sth[X] for X in range(3)]
+    Nl = nH_.size
+    point = geom == "sphere_stromgren"
+    dl = np.abs(E[:-1] - E[1:]) if point else E[1:] - E[:-1]     # sphere_base.f90:1535 / :403
+    r_c = (E[:-1] + E[1:]) * F(0.5)
+    dt = [dl * nH_ * x[0] * sth[0], dl * nHe_ * x[2] * sth[1], dl * nHe_ * x[3] * sth[2]]
+    two = geom == "slab_plane_2"
+    out = {}
+    for i in (range(Nl // 2 if two else Nl) if cells is None else cells):
+        def att_from(side):
+            th = [(_ssum(d[:i]) if side == 0 else _ssum(d[i + 1:])) + F(0.5) * d[i] for d in dt]
+            return np.exp(-(th[0] * ra[0] + th[1] * ra[1] + th[2] * ra[2]))
+        kind = "point" if point else "plane"
+        if two:                                                   # slab_plane.f90:1011-1048
+            lo = _src_rates(kind, Ev, sh, sig, att_from(0), F)
+            hi = _src_rates(kind, Ev, sh, sig, att_from(1), F)
+            r6 = [a * F(0.5) + b * F(0.5) for a, b in zip(lo, hi)]
+        else:
+            r6 = _src_rates(kind, Ev, sh, sig, att_from(0), F, r=r_c[i] if point else None)
         xs, Tn = _cell_solve(nH_[i], nHe_[i], T[i], r6, fcA, find_Teq, z, Hz,
                              F(tol) * F(1.0e-2), F)
         out[i] = (xs, Tn, r6)

@@ -169,3 +169,82 @@ def test_one_sweep_of_slab_bgnd(orc, find_Teq):
             for q, k in enumerate(FR):
                 assert abs(float(xs[q]) / one[k][i] - 1.0) <= x_tol, (F, i, k)
             assert abs(float(Tn) / one["T"][i] - 1.0) <= 1e-15, (F, i)
+
+
+@pytest.mark.parametrize("geom,find_Teq", [("slab_plane_1", False), ("slab_plane_1", True),
+                                           ("slab_plane_2", True), ("sphere_stromgren", False),
+                                           ("sphere_stromgren_hm12", True)])
+def test_one_sweep_of_the_column_geometries(orc, geom, find_Teq):
+    """SlabPln, Slab2Pln and SphereStromgren (monochromatic Iliev source and a polychromatic
+    one): thin start by the C oracle, then one sweep by both derivations."""
+    Nl, Nnu = 24, 16
+    rng = np.random.default_rng(13)
+    if geom.startswith("slab"):
+        cfg = configs.c2_slab_plane(Nl, Nnu, find_Teq, two_sided=(geom == "slab_plane_2"))
+        cfg["nH"] = cfg["nH"] * 10 ** rng.normal(0.0, 1.0, Nl)       # clumpy, asymmetric
+        cfg["nHe"] = cfg["nH"] * 0.08
+        a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], cfg["E_eV"], cfg["shape"])
+        kw = dict(i_find_Teq=int(find_Teq), z=3.0, i_2side=int(geom == "slab_plane_2"))
+        solve = orc.slab_plane_solve
+        g = geom
+    else:
+        cfg = configs.c1_iliev_stromgren(Nl)
+        if geom.endswith("hm12"):                                    # polychromatic point source
+            from rabacus_b200 import rad_src
+            src = rad_src.PointSource(1.0, 400.0, "hm12", Nnu=Nnu, z=3.0)
+            src.normalize_Ln(5.0e48)
+            cfg["E_eV"], cfg["shape"] = src.E.copy(), src.shape.copy()
+            cfg["nHe"] = cfg["nH"] * 0.08
+        cfg["nH"] = cfg["nH"] * 10 ** rng.normal(0.0, 0.5, Nl)
+        a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], 1, cfg["E_eV"], cfg["shape"])
+        kw = dict(i_find_Teq=int(find_Teq), z=3.0, fixed_fcA=cfg["fixed_fcA"])
+        solve = orc.sphere_stromgren_solve
+        g = "sphere_stromgren"
+    thin = solve(*a, i_thin=1, **kw)
+    one = solve(*a, max_sweeps=1, **kw)
+    fcA = cfg["fixed_fcA"]
+    ncell = Nl // 2 if g == "slab_plane_2" else Nl
+    # float64: same statements, same bisection path; longdouble: the "truth" -- a minority
+    # fraction carries the n_e bisection's own stopping noise (tol_inner = 1e-6 on successive
+    # iterates), measured up to 1.6e-10 here
+    for F, rt_tol, x_tol in ((np.float64, 4e-15, 1e-13), (np.longdouble, 1e-13, 1e-9)):
+        out = so.column_sweep(g, cfg["Edges"], cfg["nH"], cfg["nHe"], thin["T"],
+                              [thin[k] for k in FR], cfg["E_eV"], cfg["shape"], fcA, find_Teq,
+                              3.0, 0.0, 1e-4, F)
+        assert sorted(out) == list(range(ncell))
+        for i, (xs, Tn, acc) in out.items():
+            for q, k in enumerate(RT):
+                ref = one[k][i]
+                assert (ref == 0.0 and float(acc[q]) == 0.0) or \
+                    abs(float(acc[q]) / ref - 1.0) <= rt_tol, (F, i, k, float(acc[q]), ref)
+            for q, k in enumerate(FR):
+                assert abs(float(xs[q]) / one[k][i] - 1.0) <= x_tol, (F, i, k)
+            assert abs(float(Tn) / one["T"][i] - 1.0) <= 1e-15, (F, i)
+
+
+@pytest.mark.parametrize("find_Teq", [False, True])
+def test_one_gauss_seidel_sweep_of_sphere_bgnd(orc, find_Teq):
+    """the reference's own (single-thread) order, sphere_bgnd.f90:753-913: the oracle's
+    order=gs against the second derivation run the same way"""
+    Nl, Nnu, Nmu = 24, 16, 4
+    cfg = _sphere_cfg("uniform", Nl, Nnu, Nmu, find_Teq)
+    a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], Nmu, cfg["E_eV"], cfg["shape"])
+    kw = dict(i_find_Teq=int(find_Teq), z=3.0, order=orc.ORDER_GS)
+    thin = orc.sphere_bgnd_solve(*a, i_thin=1, **kw)
+    one = orc.sphere_bgnd_solve(*a, max_sweeps=1, **kw)
+    jac = orc.sphere_bgnd_solve(*a, max_sweeps=1, i_find_Teq=int(find_Teq), z=3.0,
+                                order=orc.ORDER_JACOBI)
+    assert np.max(np.abs(jac["xH1"] / one["xH1"] - 1.0)) > 1e-9      # the orders do differ
+    mu, w = orc.p_quadrature_rule(Nmu)
+    rv = lambda v: np.asarray(v)[::-1].copy()  # noqa: E731
+    out = so.sphere_bgnd_jacobi_sweep(
+        rv(cfg["Edges"]), rv(cfg["nH"]), rv(cfg["nHe"]), rv(thin["T"]),
+        [rv(thin[k]) for k in FR], [rv(thin[k]) for k in RT], mu, w, cfg["E_eV"],
+        cfg["shape"], 1.0, find_Teq, 3.0, 0.0, 1e-4, np.float64, gauss_seidel=True)
+    for il, (xs, Tn, acc) in out.items():
+        io = Nl - 1 - il
+        for q, k in enumerate(RT):
+            assert abs(float(acc[q]) / one[k][io] - 1.0) <= 4e-15, (il, k)
+        for q, k in enumerate(FR):
+            assert abs(float(xs[q]) / one[k][io] - 1.0) <= 1e-13, (il, k)
+        assert abs(float(Tn) / one["T"][io] - 1.0) <= 1e-15, il
