@@ -271,8 +271,9 @@ int rb_plan_thin(rb_plan *plan);
 #define RB_ORDER_JACOBI 0
 #define RB_ORDER_GAUSS_SEIDEL 1
 int rb_plan_set_sweep_order(rb_plan *plan, int order);
-/* one Jacobi sweep over the local cells il = cell_start + j*cell_stride:
- * columns -> frequency/angle integrals -> cell solve.  Does NOT test
+/* one Jacobi sweep over the local cells of the deal (cell_start, cell_stride) -- stride > 0:
+ * il = cell_start + j*cell_stride; stride < 0: 32-cell blocks over -stride ranks (see
+ * rb_plan_peer_deal) --: columns -> frequency/angle integrals -> cell solve.  Does NOT test
  * convergence. */
 int rb_plan_sweep_local(rb_plan *plan, int cell_start, int cell_stride);
 /* convergence test on n_e over all cells + iteration bookkeeping
