@@ -64,7 +64,7 @@ EXPORTS = (
 # measurement / diagnostic symbols declared in rabacus_b200/csrc/rb_internal.h (not part of
 # the drop-in boundary)
 INTERNAL = ("rbi_diag_pow", "rbi_diag_hg97", "rbi_host_coefficients", "rbi_plan_set_libm_pow", "rbi_plan_set_far_field", "rbi_plan_bench_steps",
-            "rbi_microbench", "rbi_last_zone_kernel_ms", "rbi_teq_table_fetch", "rbi_plan_fetch_inputs", "rbi_plan_check_guards")
+            "rbi_microbench", "rbi_last_zone_kernel_ms", "rbi_teq_table_fetch", "rbi_plan_fetch_inputs", "rbi_plan_check_guards", "rbi_diag_ratio_err")
 
 _lib = None
 

@@ -2371,6 +2371,34 @@ extern "C" int rbi_teq_table_fetch(double fcA, int row0, int n, double *out16, i
   return RB_OK;
 }
 
+// decisions of rb_ion.cuh ratio_err_exceeds (reciprocal-based, certified) and of the IEEE
+// divisions it stands for, for n triples of quotients: out[i] = fast | exact << 1
+__global__ void k_diag_ratio_err(const double *a, const double *b, int n, double tol, int *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a1 = a[3 * i], a2 = a[3 * i + 1], a3 = a[3 * i + 2];
+  const double b1 = b[3 * i], b2 = b[3 * i + 1], b3 = b[3 * i + 2];
+  const int fast = ratio_err_exceeds(a1, b1, a2, b2, a3, b3, tol) ? 1 : 0;
+  const int exact = (fabs(fmax(fmax(a1 / b1, a2 / b2), a3 / b3) - 1.0) > tol) ? 1 : 0;
+  const int up = (a1 > b1) ? 1 : 0, up_div = ((a1 / b1) > 1.0) ? 1 : 0;
+  const int dn = (a1 < b1) ? 1 : 0, dn_div = ((a1 / b1) < 1.0) ? 1 : 0;
+  out[i] = fast | (exact << 1) | (up << 2) | (up_div << 3) | (dn << 4) | (dn_div << 5);
+}
+extern "C" int rbi_diag_ratio_err(const double *a, const double *b, int n, double tol, int *out) {
+  if (!a || !b || !out || n < 1) return RB_ERR_BAD_ARG;
+  int rc = need_device();
+  if (rc) return rc;
+  DevBuf da, db, dout;
+  if ((rc = da.alloc((size_t)3 * n)) || (rc = db.alloc((size_t)3 * n)) || (rc = dout.alloc((size_t)n)))
+    return rc;
+  CK(cudaMemcpy(da.d, a, (size_t)3 * n * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db.d, b, (size_t)3 * n * 8, cudaMemcpyHostToDevice));
+  k_diag_ratio_err<<<(n + 255) / 256, 256>>>(da.d, db.d, n, tol, (int *)dout.d);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, dout.d, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  return RB_OK;
+}
+
 extern "C" int rbi_plan_set_far_field(rb_plan *p, int on) {
   if (!p) return RB_ERR_BAD_ARG;
   if (on && !p->dfar) return RB_ERR_UNSUPPORTED;

@@ -64,6 +64,12 @@ int rbi_plan_fetch_inputs(rb_plan *plan, int b, double *Edges, double *nH, doubl
  * the first damaged buffer.  Returns -1 in the release build (no guards). */
 int rbi_plan_check_guards(rb_plan *plan, char *where, size_t wherelen);
 
+/* The two decisions of a solve_pce step as the kernels take them (csrc/rb_ion.cuh: comparison
+ * instead of ratio_ne, reciprocal-based certified error test) next to the IEEE divisions of
+ * the reference, for n triples a[3n] / b[3n]: out[i] bit 0 = certified err > tol, bit 1 = by
+ * division; bits 2/3 = a1 > b1 vs a1/b1 > 1; bits 4/5 = a1 < b1 vs a1/b1 < 1. */
+int rbi_diag_ratio_err(const double *a, const double *b, int n, double tol, int *out);
+
 /* device time [ms] of the kernel of this thread's last rb_solve_pce / rb_solve_pcte call
  * (scalar mode), for the single-zone batch line of bench.py */
 double rbi_last_zone_kernel_ms(void);

@@ -90,8 +90,45 @@ RB_HD double ne_of(double nH, double nHe, const rb_frac_t &x) {
   return x.xH2 * nH + (x.xHe2 + 2.0 * x.xHe3) * nHe;
 }
 
+// ---------------------------------------------------------------------------
+// The two DECISIONS of a solve_pce step without their divisions.
+//
+// A step of the n_e bisection (ion_solver.f90:497-528) uses four quotients only to decide:
+//   ratio_ne = ne / ne_old  ->  ratio_ne > 1 (< 1)         which bracket moves
+//   err = |max(xH1/xH1_old, xHe1/xHe1_old, xHe3/xHe3_old) - 1|  ->  err > tol   loop test
+// The iterates themselves (mid-points of the bracket) never see the quotients.  So the
+// reference's path is kept bit for bit as long as the two DECISIONS are the reference's:
+//  * RN(a/b) > 1  <=>  a > b  and  RN(a/b) < 1  <=>  a < b  for IEEE doubles (a > b gives
+//    a/b >= 1 + ulp(b)/b > 1 + 2^-53, which rounds to >= 1 + 2^-52; a < b gives a/b <=
+//    1 - 2^-53, representable; zeros / NaN: both sides false): the comparison IS the decision.
+//  * err > tol is decided from quotients formed with a refined reciprocal (relative error
+//    < 1e-11) whenever the outcome is certain -- |max - 1| further than 2e-10 from tol --
+//    and from the IEEE divisions otherwise (also for any non-finite intermediate).
+// An IEEE double division is ~25 instructions on this GPU, and with the rate coefficients of
+// a probe memoised the divisions were what was left of a temperature probe: 14 -> 10 per step.
+// ---------------------------------------------------------------------------
+RB_HD bool ratio_err_exceeds(double a1, double b1, double a2, double b2, double a3, double b3,
+                             double tol) {
+#ifdef __CUDA_ARCH__
+  double r1, r2, r3;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r1) : "d"(b1));
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r2) : "d"(b2));
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r3) : "d"(b3));
+  r1 = fma(fma(-b1, r1, 1.0), r1, r1);   // one Newton step: 2^-20 -> 2^-40
+  r2 = fma(fma(-b2, r2, 1.0), r2, r2);
+  r3 = fma(fma(-b3, r3, 1.0), r3, r3);
+  const double m = fmax(fmax(a1 * r1, a2 * r2), a3 * r3);
+  const double d = fabs(m - 1.0);
+  const double slack = 2.0e-10 * (1.0 + d);
+  if (d > tol + slack) return true;     // (false for NaN / inf: those take the exact path)
+  if (d < tol - slack) return false;
+#endif
+  return fabs(fmax(fmax(a1 / b1, a2 / b2), a3 / b3) - 1.0) > tol;   // :507-512
+}
+
 // State of one solve_pce bisection, so that the scalar loop below and the
-// lock-step (vector) kernels share the step.
+// lock-step (vector) kernels share the step.  `err` carries only what the loop tests read
+// from it: huge while the step's error exceeds the tolerance, 0 once it does not.
 struct PceState {
   double ne, ne_old, ne_left, ne_right, xH1_old, xHe1_old, xHe3_old, err;
 };
@@ -118,17 +155,16 @@ RB_HD int pce_init(double nH, double nHe, const rb_kchem_t &k, double H1i,
 // treatment of ratio_ne == 1 (:640-652): ne is then left at the fresh value.
 RB_HD void pce_step(double nH, double nHe, const rb_kchem_t &k, double H1i,
                     double He1i, double He2i, rb_frac_t &x, PceState &s,
-                    bool vector_rule) {
+                    bool vector_rule, double tol) {
   implicit_ionfracs(s.ne, k, H1i, He1i, He2i, x);
   s.ne = ne_of(nH, nHe, x);
-  const double ratio_ne = s.ne / s.ne_old;
-  const double ratio_x = fmax(fmax(x.xH1 / s.xH1_old, x.xHe1 / s.xHe1_old),
-                              x.xHe3 / s.xHe3_old);
-  s.err = fabs(ratio_x - 1.0);
-  if (ratio_ne > 1.0) {
+  const bool up = s.ne > s.ne_old, down = s.ne < s.ne_old;   // ratio_ne > 1, < 1 (:503)
+  s.err = ratio_err_exceeds(x.xH1, s.xH1_old, x.xHe1, s.xHe1_old, x.xHe3, s.xHe3_old, tol)
+              ? 1.7976931348623157e308 : 0.0;
+  if (up) {
     s.ne = (s.ne_old + s.ne_right) * 0.5;
     s.ne_left = s.ne_old;
-  } else if (!vector_rule || ratio_ne < 1.0) {
+  } else if (!vector_rule || down) {
     s.ne = (s.ne_left + s.ne_old) * 0.5;
     s.ne_right = s.ne_old;
   }
@@ -157,7 +193,7 @@ RB_HDN int solve_pce(double nH, double nHe, const rb_kchem_t &k, double H1i,
   if (rc) return rc;
   int iter = 0;
   while (s.err > tol) {
-    pce_step(nH, nHe, k, H1i, He1i, He2i, x, s, false);
+    pce_step(nH, nHe, k, H1i, He1i, He2i, x, s, false, tol);
     iter = iter + 1;
     if (iter > RB_ION_MAX_ITER) return ION_ERR_MAX_ITER_PCE;
   }

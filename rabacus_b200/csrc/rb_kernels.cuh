@@ -1306,7 +1306,7 @@ k_cell_solve_pce_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int
     rb_frac_t x;
     implicit_ionfracs(mine.ne, k, H1i, He1i, He2i, x);
     const double ne_new = ne_of(nH, nHe, x);
-    const bool up = (ne_new / mine.ne) > 1.0;   // ratio_ne of :503
+    const bool up = ne_new > mine.ne;   // ratio_ne = ne_new / ne > 1 of :503 (rb_ion.cuh)
     const unsigned ups = __ballot_sync(mask, up) >> gbase;
     // ---- walk
     int n = 1, last = -1;
@@ -1315,7 +1315,8 @@ k_cell_solve_pce_spec(PlanDev P, PeerDev Q, int cell_start, int cell_stride, int
       const double a1 = __shfl_sync(mask, x.xH1, gbase + n);
       const double a2 = __shfl_sync(mask, x.xHe1, gbase + n);
       const double a3 = __shfl_sync(mask, x.xHe3, gbase + n);
-      err = fabs(fmax(fmax(a1 / o1, a2 / o2), a3 / o3) - 1.0);   // :507-512
+      err = ratio_err_exceeds(a1, o1, a2, o2, a3, o3, P.tol_inner)   // :507-512
+                ? 1.7976931348623157e308 : 0.0;
       o1 = a1; o2 = a2; o3 = a3;
       const bool u = (ups >> n) & 1u;
       nebisect_step(root, u);
@@ -1756,7 +1757,7 @@ RB_LS_UNROLL
     if (!block_any(any)) break;  // ion_solver.f90:620
 RB_LS_UNROLL
     for (int i = 0; i < CPT; ++i)
-      if (ok[i]) pce_step(nH[i], nHe[i], k[i], p[i].H1i, p[i].He1i, p[i].He2i, x[i], s[i], true);
+      if (ok[i]) pce_step(nH[i], nHe[i], k[i], p[i].H1i, p[i].He1i, p[i].He2i, x[i], s[i], true, tol);
     iter = iter + 1;
     if (iter > RB_ION_MAX_ITER) { rc = ION_ERR_MAX_ITER_PCE; break; }
   }

@@ -1,0 +1,4 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r02v_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r02v_pytest_gpu.log
