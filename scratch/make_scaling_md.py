@@ -1,0 +1,45 @@
+"""profiles/r02_scaling.md from the bench lines profiles/<tag>_bench_n{1,2,4,8}.json (+ _b)."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02w"
+def L(f): return json.load(open(os.path.join(ROOT, "profiles", f)))
+rows = [(1, L("%s_bench_n1.json" % tag), None)] + [(n, L("%s_bench_n%d.json" % (tag, n)), L("%s_bench_n%d_b.json" % (tag, n))) for n in (2, 4, 8)]
+out = ["# Round 2 (final build): scaling over the 8 B200s of one box (bench.py --gpus N under torchrun, one rank per GPU)", "",
+"All numbers: CUDA events on the launching stream, max over ranks, L2 flushed between timed steps, clocks 1965 MHz without throttle reasons.",
+"Records: `%s_bench_n{1,2,4,8}.json` (`_b`: an immediate second run of the C4 part).  Earlier builds of this round: `r02t_*` (before the" % tag,
+"division-free solver decisions), `r02n_bench_n1.json`, `r02_bench_n2.json`, `r02o_bench_n{4,8}.json` (256-entry exp table; N = 2 with single cells dealt cyclically).", "",
+"## C4: one SphereBgnd problem (4096 x 512 x 256), cells sharded over peer memory in 32-cell blocks -- STRONG scaling of a 0.75 ms sweep", "",
+"| N | ms / sweep (second run) | evals/s | speed-up | efficiency | converged solve (45 sweeps, host pointers) | parity_vs_n1 |", "|---|---|---|---|---|---|---|"]
+t1 = rows[0][1]["ms_per_step"]
+for n, d, b in rows:
+    ms = d["ms_per_step"]; ms2 = (" (%.3f)" % b["ms_per_step"]) if b else ""
+    par = d.get("parity_vs_n1"); ps = ("bit-identical, %d = %d sweeps" % (par["sweeps_sharded"], par["sweeps_n1"])) if par else "-"
+    out.append("| %d | %.3f%s | %.3e | %.2f | %.0f %% | %.1f ms | %s |" % (n, ms, ms2, d["value"], t1 / ms, 100 * t1 / ms / n, d["solve"]["wall_ms"], ps))
+out += ["", "Stage times (ms; N > 1: from the direct-launch warm-up steps, the timed steps are CUDA graphs; the exchange column includes the wait for the slowest rank):", "",
+"| N | columns (moments + walk) | frequency integrals | cell solve | exchange + convergence |", "|---|---|---|---|---|"]
+for n, d, b in rows:
+    k = d["roofline"]["kernels"]; r = d["roofline"]
+    out.append("| %d | %.3f | %.3f | %.3f | %.3f |" % (n, k["k_sphere_columns"]["ms"], k["k_nu_rates"]["ms"], r["ms_cell_solve"], r["ms_finish"]))
+out += ["", "One rank's share alone on a GPU (`scratch/rank_share2.py`, no barrier skew), total ms per sweep: 0.747 / 0.437 / 0.290 / 0.217 at N = 1 / 2 / 4 / 8",
+"(single cells dealt cyclically instead of 32-cell blocks, earlier build: 0.805 / 0.476 / 0.326 / 0.266).", "",
+"Why one sweep does not scale further (DESIGN.md 6): the far-field moment scan (0.024 ms) is needed in full by every rank; ~0.05 ms of the column",
+"kernel is per-CTA shared-memory fill and the latency of one warp's walk (with 2048 work items on 148 SMs every warp has one or two); 512 cells on 148",
+"SMs leave the frequency kernel's slowest SM with 4 cells against 3.46 on average; cell solve + finish are 0.035 ms of latency; the flag barrier adds",
+"the skew between the ranks (0.03-0.05 ms).  Round 1 measured 0.382 ms per sweep at N = 8 (from a 1.63 ms single-GPU sweep); now 0.25-0.27 ms from 0.75 ms,",
+"and a converged C4 solve on eight GPUs takes 11.2 ms (round 1: 17 ms).", "",
+"C4 with find_Teq (ms / sweep): " + ", ".join("N=%d %.3f" % (n, d["c4_find_Teq"]["ms_per_step"]) for n, d, b in rows), "",
+"## C5: 8192 independent SphereBgnd solves (512 x 128 x 32), problems dealt over the ranks, no exchange", "",
+"| N | fixed T: wall s (staging / solve / read-back) | speed-up (solve) | find_Teq: wall s (solve) | speed-up (solve) |", "|---|---|---|---|---|"]
+w1 = rows[0][1]["c5"]["wall_s"]; s1 = rows[0][1]["c5"]["solve_s"]; w1t = rows[0][1]["c5_find_Teq"]["wall_s"]; s1t = rows[0][1]["c5_find_Teq"]["solve_s"]
+for n, d, b in rows:
+    c = d["c5"]; t = d["c5_find_Teq"]
+    out.append("| %d | %.3f (%.4f / %.3f / %.3f) | %.2f (%.2f) | %.3f (%.3f) | %.2f (%.2f) |" % (n, c["wall_s"], c["staging_s"], c["solve_s"], c["readback_s"], w1 / c["wall_s"], s1 / c["solve_s"], t["wall_s"], t["solve_s"], w1t / t["wall_s"], s1t / t["solve_s"]))
+out += ["", "Staging = generation of every input on the device from (nH0, R, z) per problem (round 1: 0.07-0.39 s of numpy + H2D copies).  Round 1: 1.92 s / 5.25 s at N = 1.",
+"Read-back = 403 MB of results into pageable numpy arrays (0.10 s at N = 1; single runs show host hiccups of 0.1-0.5 s there).", "",
+"## Correctness at N > 1", "",
+"`%s_check_n{2,4,8}.log`: `tests/multigpu/check_cell_sharding.py`, 11 cases, peer and NCCL paths bit-identical to one GPU." % tag,
+"`%s_soak_n{2,4,8}.log`: `tests/multigpu/soak_peer.py`, 1044 sweeps through the exchange, every solve bit-identical to one GPU." % tag,
+"`r02_dead_peer_n2.log`: a rank that stops sweeping -> RB_ERR_PEER_TIMEOUT on its peer after 1.6 s.",
+"Every bench line at N > 1 carries `parity_vs_n1.bit_identical = true`."]
+open(os.path.join(ROOT, "profiles", "r02_scaling.md"), "w").write("\n".join(out) + "\n")
+print("\n".join(out[6:14]))
