@@ -104,3 +104,23 @@ def test_family_rejects_bad_arguments():
     with pytest.raises(RabacusB200Error):
         slab.set_sphere_family([1.0], [1e22], [3.0])
     slab.close()
+
+
+def test_large_readback_of_a_batch():
+    """rb_plan_get_all on a 59 MB batch (one device gather pass + one copy): every problem must
+    come back as rb_plan_get_problem returns it.  (A chunked read-back through pinned bounce
+    buffers was tried for the 403 MB of C5: no gain -- the 0.10 s are first-touch page faults
+    of the freshly allocated numpy arrays, not the PCIe copy.)"""
+    B, Nl, Nnu, Nmu = 800, 512, 16, 2
+    idx = np.arange(B) * 10
+    plan = Plan(0, B, Nl, Nnu, Nmu, max_sweeps=1)
+    configs.c5_stage_device(plan, idx)
+    plan.upload()
+    plan.solve()
+    allr = plan.get_all(with_rec=True)
+    for b in (0, 1, 399, 798, 799):
+        one = plan.get_problem(b)
+        for k in CHECK:
+            assert np.array_equal(allr[k][b], one[k]), (b, k)
+    assert np.all(allr["H1i_rec"] == 0.0) and allr["iters"].shape == (B,)
+    plan.close()
