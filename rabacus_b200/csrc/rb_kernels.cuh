@@ -1014,20 +1014,26 @@ __device__ __forceinline__ double exp_fast(double x, const double *s_tab, unsign
   constexpr int SH = ExpTab<L>::shift;
   const unsigned off = ((unsigned)(n << SH) & (unsigned)(((1 << L) - 1) << SH)) | lane_off;
   RB_ASSERT(off + 8u <= (unsigned)((1 << L) * ExpTab<L>::copies * 8) && x <= 0.0 && x >= -708.5);
-  const double T = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(s_tab) + off);
-  const double v = fma(T, pl, T);
-  // exponent: hi += (n >> L) << 20 = (n & ~(2^L - 1)) * 2^(20-L), kept as lop3 + one imad
+  // The table holds 2^(j/2^L) with j 2^(20-L) SUBTRACTED from its high word, so that adding
+  // n 2^(20-L) = (e << 20) + j 2^(20-L) (one imad, no mask) leaves the entry scaled by 2^e;
+  // the scaling is applied BEFORE the last fma -- exact, x >= -708 keeps 2^e 2^(j/2^L) normal --
+  // so the result is the bits of 2^e fma(T, pl, T), and nothing but that fma follows the
+  // polynomial on the dependent chain (the lop3 + imad on the RESULT's high word that this
+  // replaces cost 9 % of the frequency kernel: 0.499 -> 0.454 ms at C4).
+  const double Ts = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(s_tab) + off);
   int hi;
   asm("mad.lo.s32 %0, %1, %2, %3;"
       : "=r"(hi)
-      : "r"(n & ~((1 << L) - 1)), "n"(1 << (20 - L)), "r"(__double2hiint(v)));
-  return __hiloint2double(hi, __double2loint(v));
+      : "r"(n), "n"(1 << (20 - L)), "r"(__double2hiint(Ts)));
+  const double T = __hiloint2double(hi, __double2loint(Ts));
+  return fma(T, pl, T);
 }
 
 template <int L>
 __device__ __forceinline__ void fill_exp_table_L(double *s_exp) {
   for (int j = threadIdx.x; j < (1 << L); j += blockDim.x) {
-    const double v = exp2((double)j * (1.0 / (double)(1 << L)));
+    double v = exp2((double)j * (1.0 / (double)(1 << L)));
+    v = __hiloint2double(__double2hiint(v) - (j << (20 - L)), __double2loint(v));   // see exp_fast
 #pragma unroll
     for (int c = 0; c < ExpTab<L>::copies; ++c) s_exp[j * ExpTab<L>::copies + c] = v;
   }
