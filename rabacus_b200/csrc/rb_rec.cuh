@@ -423,11 +423,13 @@ __device__ __forceinline__ double exp_small(double x, const double *s_tab, unsig
   const double r2 = r * r;
   const double pl = fma(r2, q, r);
   const unsigned off = ((unsigned)(n << 4) & (31u << 4)) | lane_off;
-  const double T = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(s_tab) + off);
-  const double v = fma(T, pl, T);
+  // (entries carry -j 2^15 in their high word: one imad on the entry, before the last fma --
+  // see exp_fast in rb_kernels.cuh)
+  const double Ts = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(s_tab) + off);
   int hi;
-  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(hi) : "r"(n & ~31), "n"(1 << 15), "r"(__double2hiint(v)));
-  return __hiloint2double(hi, __double2loint(v));
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(hi) : "r"(n), "n"(1 << 15), "r"(__double2hiint(Ts)));
+  const double T = __hiloint2double(hi, __double2loint(Ts));
+  return fma(T, pl, T);
 }
 
 __device__ __forceinline__ void iso_step_s(IsoAcc &a, double ds, const IsoSmem &S, int k,
@@ -468,7 +470,11 @@ k_rec_iso_rays_smem(PlanDev P, RecDev R, int Nmu, const unsigned *__restrict__ i
   __syncthreads();
   const IsoSmem S = {sE2, sK, sM};
   __shared__ double s_tab[64];   // [32 entries][2 copies]
-  if (threadIdx.x < 64) s_tab[threadIdx.x] = exp2((double)(threadIdx.x >> 1) * (1.0 / 32.0));
+  if (threadIdx.x < 64) {
+    const int j = threadIdx.x >> 1;
+    const double v = exp2((double)j * (1.0 / 32.0));
+    s_tab[threadIdx.x] = __hiloint2double(__double2hiint(v) - (j << 15), __double2loint(v));
+  }
   __syncthreads();
   const unsigned lane_off = (threadIdx.x & 1) << 3;
   const int lane = threadIdx.x & 31;
