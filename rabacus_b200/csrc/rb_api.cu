@@ -9,6 +9,9 @@
 #include <mutex>
 #include <vector>
 
+#include <sys/mman.h>
+#include <unistd.h>
+
 #include "rb_rec.cuh"
 #include "rb_inputs.cuh"
 #include "rb_internal.h"
@@ -1935,11 +1938,28 @@ extern "C" int rb_plan_get_rec(rb_plan *p, int b, double *H1i, double *He1i, dou
   return RB_OK;
 }
 
+// A large, freshly allocated host buffer is about to be written for the first time (the
+// results of a parameter sweep: 403 MB at C5): ask for huge pages, so that the first touch
+// costs one fault per 2 MB instead of one per 4 KB (0.1 s, with outliers of 0.5-0.8 s, of page
+// faults inside the D2H copy otherwise).  Advisory: ignored where transparent huge pages are off.
+static void advise_huge(void *ptr, size_t bytes) {
+#ifdef MADV_HUGEPAGE
+  if (bytes < ((size_t)16 << 20)) return;
+  const size_t pg = (size_t)2 << 20;
+  const uintptr_t a = ((uintptr_t)ptr + pg - 1) / pg * pg, e = ((uintptr_t)ptr + bytes) / pg * pg;
+  if (e > a) madvise((void *)a, e - a, MADV_HUGEPAGE);
+#else
+  (void)ptr; (void)bytes;
+#endif
+}
+
 extern "C" int rb_plan_get_all(rb_plan *p, double *out12, double *rec6, int *iters) {
   if (!p || !out12) return RB_ERR_BAD_ARG;
   PLAN_DEV(p);
   const size_t B = p->d.n_problems, Nl = p->d.Nl, NC = B * Nl;
   const int nf = rec6 ? 18 : 12;
+  advise_huge(out12, 12 * NC * 8);
+  if (rec6) advise_huge(rec6, 6 * NC * 8);
   DevBuf tmp;
   int rc = tmp.alloc((size_t)nf * NC);
   if (rc) return rc;
