@@ -339,6 +339,14 @@ int rb_plan_get_rec(rb_plan *plan, int b, double *H1i_rec, double *He1i_rec,
  * rates), rec6 (may be NULL) [6][n_problems][Nl] the recombination-photon rates, iters
  * (may be NULL) [n_problems] the sweep counts; every problem in its input orientation. */
 int rb_plan_get_all(rb_plan *plan, double *out12, double *rec6, int *iters);
+/* The same results in a PINNED host buffer owned by the plan (no caller allocation, no
+ * first-touch page faults inside the copy: the read-back of a large parameter sweep runs at
+ * PCIe speed).  rb_plan_reserve_results allocates the buffer ahead of time (18 fields x
+ * n_problems x Nl doubles); rb_plan_get_all_pinned fills it and returns pointers into it,
+ * valid until the next call or rb_plan_destroy (any of the three may be NULL). */
+int rb_plan_reserve_results(rb_plan *plan);
+int rb_plan_get_all_pinned(rb_plan *plan, const double **out12, const double **rec6,
+                           const int **iters);
 /* device pointers for torch / NCCL interop: fields are [n_problems*Nl] float64.
  * 0..4 = xH1,xH2,xHe1,xHe2,xHe3 ; 5 = T ; 6..11 = H1i,He1i,He2i,H1h,He1h,He2h src */
 void *rb_plan_field_ptr(rb_plan *plan, int field);

@@ -55,7 +55,7 @@ EXPORTS = (
     "rb_plan_set_sphere_family", "rb_plan_set_sweep_order", "rb_plan_upload",
     "rb_plan_thin", "rb_plan_sweep_local", "rb_plan_finish_sweep", "rb_plan_finish_sweep_async",
     "rb_plan_poll_sweep", "rb_plan_solve",
-    "rb_plan_get_problem", "rb_plan_get_rec", "rb_plan_get_all", "rb_plan_field_ptr", "rb_plan_stream", "rb_plan_sync",
+    "rb_plan_get_problem", "rb_plan_get_rec", "rb_plan_get_all", "rb_plan_reserve_results", "rb_plan_get_all_pinned", "rb_plan_field_ptr", "rb_plan_stream", "rb_plan_sync",
     "rb_plan_evals_per_sweep", "rb_plan_last_info", "rb_plan_pack_cells",
     "rb_plan_unpack_cells",
     "rb_plan_peer_alloc", "rb_plan_peer_connect", "rb_plan_peer_deal", "rb_cell_of", "rb_plan_sweep_sharded", "rb_plan_solve_sharded",

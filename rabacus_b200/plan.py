@@ -205,10 +205,30 @@ class Plan(object):
         outs.update(rec)
         return outs
 
-    def get_all(self, with_rec=False):
+    def reserve_results(self):
+        """Allocate the plan's pinned host result buffer now (``get_all(pinned=True)`` would do
+        it on first use): 18 x n_problems x Nl doubles."""
+        check(lib().rb_plan_reserve_results(self._h))
+
+    def get_all(self, with_rec=False, pinned=False):
         """All problems' results in one device pass + copy: dict of [n_problems, Nl]
-        arrays (input orientation) and ``iters`` [n_problems]."""
+        arrays (input orientation) and ``iters`` [n_problems].  ``pinned``: the arrays are
+        read-only VIEWS of a pinned host buffer owned by the plan (no allocation, copy at PCIe
+        speed) -- valid until the next ``get_all`` or ``close``."""
         B, Nl = self.n_problems, self.Nl
+        if pinned:
+            po, pr, pi = _DP(), _DP(), C.POINTER(C.c_int)()
+            check(lib().rb_plan_get_all_pinned(self._h, C.byref(po),
+                                               C.byref(pr) if with_rec else None, C.byref(pi)))
+            out = np.ctypeslib.as_array(po, shape=(12, B, Nl))
+            res = {k: out[i] for i, k in enumerate(FIELDS)}
+            if with_rec:
+                rec = np.ctypeslib.as_array(pr, shape=(6, B, Nl))
+                res.update({k: rec[i] for i, k in enumerate(REC_FIELDS)})
+            res["iters"] = np.ctypeslib.as_array(pi, shape=(B,))
+            for v in res.values():
+                v.flags.writeable = False
+            return res
         out = np.empty((12, B, Nl))
         rec = np.empty((6, B, Nl)) if with_rec else None
         iters = np.zeros(B, dtype=np.int32)

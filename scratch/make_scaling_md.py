@@ -1,14 +1,14 @@
 """profiles/r02_scaling.md from the bench lines profiles/<tag>_bench_n{1,2,4,8}.json (+ _b)."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r02w"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02x"
 def L(f): return json.load(open(os.path.join(ROOT, "profiles", f)))
 rows = [(1, L("%s_bench_n1.json" % tag), None)] + [(n, L("%s_bench_n%d.json" % (tag, n)), L("%s_bench_n%d_b.json" % (tag, n))) for n in (2, 4, 8)]
 out = ["# Round 2 (final build): scaling over the 8 B200s of one box (bench.py --gpus N under torchrun, one rank per GPU)", "",
 "All numbers: CUDA events on the launching stream, max over ranks, L2 flushed between timed steps, clocks 1965 MHz without throttle reasons.",
-"Records: `%s_bench_n{1,2,4,8}.json` (`_b`: an immediate second run of the C4 part).  Earlier builds of this round: `r02t_*` (before the" % tag,
+"Records: `%s_bench_n{1,2,4,8}.json` (`_b`: an immediate second run of the C4 part).  Earlier builds of this round: `r02w_*`, `r02t_*` (before the last exp change / the" % tag,
 "division-free solver decisions), `r02n_bench_n1.json`, `r02_bench_n2.json`, `r02o_bench_n{4,8}.json` (256-entry exp table; N = 2 with single cells dealt cyclically).", "",
-"## C4: one SphereBgnd problem (4096 x 512 x 256), cells sharded over peer memory in 32-cell blocks -- STRONG scaling of a 0.75 ms sweep", "",
+"## C4: one SphereBgnd problem (4096 x 512 x 256), cells sharded over peer memory in 32-cell blocks -- STRONG scaling of a 0.72 ms sweep", "",
 "| N | ms / sweep (second run) | evals/s | speed-up | efficiency | converged solve (45 sweeps, host pointers) | parity_vs_n1 |", "|---|---|---|---|---|---|---|"]
 t1 = rows[0][1]["ms_per_step"]
 for n, d, b in rows:
@@ -25,7 +25,7 @@ out += ["", "One rank's share alone on a GPU (`scratch/rank_share2.py`, no barri
 "Why one sweep does not scale further (DESIGN.md 6): the far-field moment scan (0.024 ms) is needed in full by every rank; ~0.05 ms of the column",
 "kernel is per-CTA shared-memory fill and the latency of one warp's walk (with 2048 work items on 148 SMs every warp has one or two); 512 cells on 148",
 "SMs leave the frequency kernel's slowest SM with 4 cells against 3.46 on average; cell solve + finish are 0.035 ms of latency; the flag barrier adds",
-"the skew between the ranks (0.03-0.05 ms).  Round 1 measured 0.382 ms per sweep at N = 8 (from a 1.63 ms single-GPU sweep); now 0.25-0.27 ms from 0.75 ms,",
+"the skew between the ranks (0.03-0.05 ms).  Round 1 measured 0.382 ms per sweep at N = 8 (from a 1.63 ms single-GPU sweep); now 0.26 ms from 0.72 ms,",
 "and a converged C4 solve on eight GPUs takes 11.2 ms (round 1: 17 ms).", "",
 "C4 with find_Teq (ms / sweep): " + ", ".join("N=%d %.3f" % (n, d["c4_find_Teq"]["ms_per_step"]) for n, d, b in rows), "",
 "## C5: 8192 independent SphereBgnd solves (512 x 128 x 32), problems dealt over the ranks, no exchange", "",

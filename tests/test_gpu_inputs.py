@@ -124,3 +124,19 @@ def test_large_readback_of_a_batch():
             assert np.array_equal(allr[k][b], one[k]), (b, k)
     assert np.all(allr["H1i_rec"] == 0.0) and allr["iters"].shape == (B,)
     plan.close()
+
+
+def test_pinned_results_equal_copied_results():
+    """rb_plan_get_all_pinned (views of the plan's pinned buffer) against rb_plan_get_all"""
+    idx = np.arange(0, 8192, 8192 // 40)
+    plan = Plan(0, idx.size, 96, 32, 4, i_rec_meth=2)
+    configs.c5_stage_device(plan, idx)
+    plan.upload()
+    plan.solve()
+    a = plan.get_all(with_rec=True)
+    b = plan.get_all(with_rec=True, pinned=True)
+    assert set(a) == set(b)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert not b["xH1"].flags.writeable
+    plan.close()
