@@ -1,13 +1,18 @@
 """profiles/r02_scaling.md from the bench lines profiles/<tag>_bench_n{1,2,4,8}.json (+ _b)."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r02x"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02y"
+# per-N tags (a later session may have re-measured only some N): N=tag pairs after the default
+tags = {1: tag, 2: tag, 4: tag, 8: tag}
+for a in sys.argv[2:]:
+    n, t = a.split("=")
+    tags[int(n)] = t
 def L(f): return json.load(open(os.path.join(ROOT, "profiles", f)))
-rows = [(1, L("%s_bench_n1.json" % tag), None)] + [(n, L("%s_bench_n%d.json" % (tag, n)), L("%s_bench_n%d_b.json" % (tag, n))) for n in (2, 4, 8)]
+rows = [(1, L("%s_bench_n1.json" % tags[1]), None)] + [(n, L("%s_bench_n%d.json" % (tags[n], n)), L("%s_bench_n%d_b.json" % (tags[n], n))) for n in (2, 4, 8)]
 out = ["# Round 2 (final build): scaling over the 8 B200s of one box (bench.py --gpus N under torchrun, one rank per GPU)", "",
 "All numbers: CUDA events on the launching stream, max over ranks, L2 flushed between timed steps, clocks 1965 MHz without throttle reasons.",
-"Records: `%s_bench_n{1,2,4,8}.json` (`_b`: an immediate second run of the C4 part).  Earlier builds of this round: `r02w_*`, `r02t_*` (before the last exp change / the" % tag,
-"division-free solver decisions), `r02n_bench_n1.json`, `r02_bench_n2.json`, `r02o_bench_n{4,8}.json` (256-entry exp table; N = 2 with single cells dealt cyclically).", "",
+"Records: " + ", ".join("`%s_bench_n%d.json`" % (tags[n], n) for n in (1, 2, 4, 8)) + " (`_b`: an immediate second run of the C4 part; `r02x` = the same kernels",
+"before the results of a batch were read back into the plan's pinned buffer, which only changes the C5 read-back column).", "",
 "## C4: one SphereBgnd problem (4096 x 512 x 256), cells sharded over peer memory in 32-cell blocks -- STRONG scaling of a 0.72 ms sweep", "",
 "| N | ms / sweep (second run) | evals/s | speed-up | efficiency | converged solve (45 sweeps, host pointers) | parity_vs_n1 |", "|---|---|---|---|---|---|---|"]
 t1 = rows[0][1]["ms_per_step"]
