@@ -332,7 +332,7 @@ struct rb_plan {
     RecConst K;
     RecDev R;
     PeerDev Q;
-    int rec_meth, live, spec_g, cols_chunks, sharded, use_far, order;
+    int rec_meth, live, spec_g, cols_chunks, sharded, use_far, order, nu_ltab;
   };
   GraphKey gkey;
   bool gkey_valid = false;
@@ -1585,9 +1585,10 @@ static int sweep_graph(rb_plan *p, bool sharded) {
   key.use_far = p->use_far ? 1 : 0;
   key.order = p->sweep_order;
   {
-    const char *a = getenv("RB_SPEC_G"), *b = getenv("RB_COLS_CHUNKS");
+    const char *a = getenv("RB_SPEC_G"), *b = getenv("RB_COLS_CHUNKS"), *c = getenv("RB_NU_LTAB");
     key.spec_g = a ? atoi(a) : 0;
     key.cols_chunks = b ? atoi(b) : 0;
+    key.nu_ltab = c ? atoi(c) : 0;
   }
   if (!p->gkey_valid || memcmp(&p->gkey, &key, sizeof(key)) != 0) {
     destroy_graphs(p);
