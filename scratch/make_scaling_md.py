@@ -40,10 +40,11 @@ for n, d, b in rows:
     c = d["c5"]; t = d["c5_find_Teq"]
     out.append("| %d | %.3f (%.4f / %.3f / %.3f) | %.2f (%.2f) | %.3f (%.3f) | %.2f (%.2f) |" % (n, c["wall_s"], c["staging_s"], c["solve_s"], c["readback_s"], w1 / c["wall_s"], s1 / c["solve_s"], t["wall_s"], t["solve_s"], w1t / t["wall_s"], s1t / t["solve_s"]))
 out += ["", "Staging = generation of every input on the device from (nH0, R, z) per problem (round 1: 0.07-0.39 s of numpy + H2D copies).  Round 1: 1.92 s / 5.25 s at N = 1.",
-"Read-back = 403 MB of results into pageable numpy arrays (0.10 s at N = 1; single runs show host hiccups of 0.1-0.5 s there).", "",
+"Read-back: into the plan's pinned host buffer (`r02y` records: 10 ms for the 403 MB at N = 1); the `r02x` records read into freshly allocated",
+"pageable numpy arrays (0.02-0.1 s, with host hiccups up to 0.8 s).", "",
 "## Correctness at N > 1", "",
-"`%s_check_n{2,4,8}.log`: `tests/multigpu/check_cell_sharding.py`, 11 cases, peer and NCCL paths bit-identical to one GPU." % tag,
-"`%s_soak_n{2,4,8}.log`: `tests/multigpu/soak_peer.py`, 1044 sweeps through the exchange, every solve bit-identical to one GPU." % tag,
+", ".join("`%s_check_n%d.log`" % (tags[n], n) for n in (2, 4, 8)) + ": `tests/multigpu/check_cell_sharding.py`, 11 cases, peer and NCCL paths bit-identical to one GPU.",
+", ".join("`%s_soak_n%d.log`" % (tags[n], n) for n in (2, 4, 8)) + ": `tests/multigpu/soak_peer.py`, 1044 sweeps through the exchange, every solve bit-identical to one GPU.",
 "`r02_dead_peer_n2.log`: a rank that stops sweeping -> RB_ERR_PEER_TIMEOUT on its peer after 1.6 s.",
 "Every bench line at N > 1 carries `parity_vs_n1.bit_identical = true`."]
 open(os.path.join(ROOT, "profiles", "r02_scaling.md"), "w").write("\n".join(out) + "\n")
