@@ -381,3 +381,55 @@ def column_sweep(geom, Edges, nH, nHe, T, x, E_eV, shape, fcA, find_Teq, z, Hz, 
                              F(tol) * F(1.0e-2), F)
         out[i] = (xs, Tn, r6)
     return out
+
+
+def recomb_outward(Edges, nH, nHe, T, x, F):
+    """set_recomb_photons_outward (sphere_base.f90:79-346): recombination photons of every
+    shell stream radially outward; rates of the six channels in every solve layer.  ``Edges``
+    decreasing (outermost shell first), ``x`` [5][Nl].  Returns (H1i, He1i, He2i, H1h, He1h,
+    He2h) -- including the routine's quirks (He1h without the excess-energy factor, He2h = 0)."""
+    E = np.asarray(Edges, dtype=F)
+    nH_, nHe_, T_ = (np.asarray(a, dtype=F) for a in (nH, nHe, T))
+    x = np.asarray(x, dtype=F)
+    Nl = nH_.size
+    half, four, pi = F(0.5), F(4.0), F(PI)
+    Eth = [F(v[0]) for v in V96]
+    dr = np.abs(E[:-1] - E[1:])                                     # :1535
+    r_c = (E[:-1] + E[1:]) * half
+    sth = [sigma_v96(X, np.array([V96[X][0]]), F)[0] for X in range(3)]
+    dt = [dr * nH_ * x[0] * sth[0], dr * nHe_ * x[2] * sth[1], dr * nHe_ * x[3] * sth[2]]
+    area = four * pi * r_c * r_c
+    vol = np.abs(four / F(3.0) * pi * (E[:-1] ** 3 - E[1:] ** 3))
+    s_H1 = [sth[0], sigma_v96(0, np.array([Eth[1]]), F)[0], sigma_v96(0, np.array([Eth[2]]), F)[0]]
+    s_He1 = [None, sth[1], sigma_v96(1, np.array([Eth[2]]), F)[0]]
+    kA = [get_kchem(T_[i], (F(1),) * 3, F) for i in range(Nl)]
+    kB = [get_kchem(T_[i], (F(0),) * 3, F) for i in range(Nl)]
+    re1 = np.array([[kA[i][q] - kB[i][q] for i in range(Nl)] for q in range(3)], dtype=F)
+    ne = x[1] * nH_ + (x[3] + F(2) * x[4]) * nHe_
+    em = [(re1[0] * nH_ * x[1] * ne) / (four * pi), (re1[1] * nHe_ * x[3] * ne) / (four * pi),
+          (re1[2] * nHe_ * x[4] * ne) / (four * pi)]
+    F0 = [e * four * pi * vol / area for e in em]
+    Fl = np.zeros((3, Nl), dtype=F)
+    for isl in range(Nl):
+        tau = [F(0), F(0), F(0)]
+        for irl in range(isl, Nl):
+            for X in range(3):
+                if irl == isl or irl == isl + 1:
+                    tau[X] = tau[X] + dt[X][irl] * half
+                else:
+                    tau[X] = tau[X] + dt[X][irl - 1] * half
+                    tau[X] = tau[X] + dt[X][irl] * half
+            geo = (r_c[irl] / r_c[isl]) * (r_c[irl] / r_c[isl])
+            t0 = tau[0] * (s_H1[0] / sth[0])
+            Fl[0, isl] = Fl[0, isl] + F0[0][irl] * geo * np.exp(-t0)
+            t1 = tau[0] * (s_H1[1] / sth[0]) + tau[1] * (s_He1[1] / sth[1])
+            Fl[1, isl] = Fl[1, isl] + F0[1][irl] * geo * np.exp(-t1)
+            t2 = tau[0] * (s_H1[2] / sth[0]) + tau[1] * (s_He1[2] / sth[1]) + tau[2] * (sth[2] / sth[2])
+            Fl[2, isl] = Fl[2, isl] + F0[2][irl] * geo * np.exp(-t2)
+    H1i = Fl[0] * s_H1[0] + Fl[1] * s_H1[1] + Fl[2] * s_H1[2]
+    He1i = Fl[1] * s_He1[1] + Fl[2] * s_He1[2]
+    He2i = Fl[2] * sth[2]
+    H1h = (Fl[1] * (Eth[1] - Eth[0]) * s_H1[1] + Fl[2] * (Eth[2] - Eth[0]) * s_H1[2]) * F(EV2ERG)
+    He1h = (Fl[1] * s_He1[1] + Fl[2] * s_He1[2]) * F(EV2ERG)
+    He2h = np.zeros(Nl, dtype=F)
+    return H1i, He1i, He2i, H1h, He1h, He2h

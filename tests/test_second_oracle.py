@@ -248,3 +248,27 @@ def test_one_gauss_seidel_sweep_of_sphere_bgnd(orc, find_Teq):
         for q, k in enumerate(FR):
             assert abs(float(xs[q]) / one[k][io] - 1.0) <= 1e-13, (il, k)
         assert abs(float(Tn) / one["T"][io] - 1.0) <= 1e-15, il
+
+
+def test_outward_recombination_photon_closure(orc):
+    """set_recomb_photons_outward (sphere_base.f90:79-346): the closure the first sweep of a
+    rec_meth = outward solve evaluates on the thin state, against the second derivation."""
+    Nl, Nnu, Nmu = 20, 16, 4
+    cfg = _sphere_cfg("log_clumpy", Nl, Nnu, Nmu, False)
+    a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], Nmu, cfg["E_eV"], cfg["shape"])
+    kw = dict(z=3.0, order=orc.ORDER_JACOBI, i_rec_meth=2)
+    thin = orc.sphere_bgnd_solve(*a, i_thin=1, **kw)
+    one = orc.sphere_bgnd_solve(*a, max_sweeps=1, **kw)
+    rv = lambda v: np.asarray(v)[::-1].copy()  # noqa: E731
+    names = ("H1i_rec", "He1i_rec", "He2i_rec", "H1h_rec", "He1h_rec", "He2h_rec")
+    for F, tol in ((np.float64, 1e-13), (np.longdouble, 1e-12)):
+        got = so.recomb_outward(rv(cfg["Edges"]), rv(cfg["nH"]), rv(cfg["nHe"]), rv(thin["T"]),
+                                [rv(thin[k]) for k in FR], F)
+        for g, k in zip(got, names):
+            ref = rv(one[k])
+            g = np.asarray(g, dtype=np.float64)
+            assert np.all((ref == 0.0) == (g == 0.0)), k
+            nz = ref != 0.0
+            if nz.any():
+                assert np.max(np.abs(g[nz] / ref[nz] - 1.0)) <= tol, (F, k, np.max(np.abs(g[nz] / ref[nz] - 1.0)))
+    assert np.any(one["H1i_rec"] > 0.0) and np.all(one["He2h_rec"] == 0.0)
