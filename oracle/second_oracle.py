@@ -281,19 +281,21 @@ def sphere_bgnd_jacobi_sweep(Edges, nH, nHe, T, x, src, mu, wmu, E_eV, shape, fc
     return out
 
 
-def _e2xa(t, F):                               # zhang_jin_f.f90:94-173
+def _e1xa(t, F):                               # zhang_jin_f.f90:15-91
     if t == 0:
-        e1 = F(1.0e300)
-    elif t <= 1:
-        e1 = (-np.log(t) + ((((F(1.07857e-3) * t - F(9.76004e-3)) * t + F(5.519968e-2)) * t
-                             - F(0.24991055)) * t + F(0.99999193)) * t - F(0.57721566))
-    else:
-        es1 = (((t + F(8.5733287401)) * t + F(18.059016973)) * t + F(8.6347608925)) * t \
-            + F(0.2677737343)
-        es2 = (((t + F(9.5733223454)) * t + F(25.6329561486)) * t + F(21.0996530827)) * t \
-            + F(3.9584969228)
-        e1 = np.exp(-t) / t * es1 / es2
-    return np.exp(-t) - t * e1
+        return F(1.0e300)
+    if t <= 1:
+        return (-np.log(t) + ((((F(1.07857e-3) * t - F(9.76004e-3)) * t + F(5.519968e-2)) * t
+                               - F(0.24991055)) * t + F(0.99999193)) * t - F(0.57721566))
+    es1 = (((t + F(8.5733287401)) * t + F(18.059016973)) * t + F(8.6347608925)) * t \
+        + F(0.2677737343)
+    es2 = (((t + F(9.5733223454)) * t + F(25.6329561486)) * t + F(21.0996530827)) * t \
+        + F(3.9584969228)
+    return np.exp(-t) / t * es1 / es2
+
+
+def _e2xa(t, F):                               # zhang_jin_f.f90:94-173 (E1 inlined there)
+    return np.exp(-t) - t * _e1xa(t, F)
 
 
 def slab_bgnd_sweep(Edges, nH, nHe, T, x, E_eV, shape, fcA, find_Teq, z, Hz, tol, F,
@@ -383,53 +385,194 @@ def column_sweep(geom, Edges, nH, nHe, T, x, E_eV, shape, fcA, find_Teq, z, Hz, 
     return out
 
 
-def recomb_outward(Edges, nH, nHe, T, x, F):
-    """set_recomb_photons_outward (sphere_base.f90:79-346): recombination photons of every
-    shell stream radially outward; rates of the six channels in every solve layer.  ``Edges``
-    decreasing (outermost shell first), ``x`` [5][Nl].  Returns (H1i, He1i, He2i, H1h, He1h,
-    He2h) -- including the routine's quirks (He1h without the excess-energy factor, He2h = 0)."""
+def _rec_setup(Edges, nH, nHe, T, x, F):
+    """The part the three sphere closures share (sphere_base.f90:170-246, :483-547, :890-957):
+    threshold cross sections, recombinations to the ground level (case A minus case B) and the
+    emission coefficients [photons / (s cm^3 sr)]."""
     E = np.asarray(Edges, dtype=F)
     nH_, nHe_, T_ = (np.asarray(a, dtype=F) for a in (nH, nHe, T))
     x = np.asarray(x, dtype=F)
     Nl = nH_.size
-    half, four, pi = F(0.5), F(4.0), F(PI)
     Eth = [F(v[0]) for v in V96]
-    dr = np.abs(E[:-1] - E[1:])                                     # :1535
-    r_c = (E[:-1] + E[1:]) * half
     sth = [sigma_v96(X, np.array([V96[X][0]]), F)[0] for X in range(3)]
-    dt = [dr * nH_ * x[0] * sth[0], dr * nHe_ * x[2] * sth[1], dr * nHe_ * x[3] * sth[2]]
-    area = four * pi * r_c * r_c
-    vol = np.abs(four / F(3.0) * pi * (E[:-1] ** 3 - E[1:] ** 3))
     s_H1 = [sth[0], sigma_v96(0, np.array([Eth[1]]), F)[0], sigma_v96(0, np.array([Eth[2]]), F)[0]]
     s_He1 = [None, sth[1], sigma_v96(1, np.array([Eth[2]]), F)[0]]
     kA = [get_kchem(T_[i], (F(1),) * 3, F) for i in range(Nl)]
     kB = [get_kchem(T_[i], (F(0),) * 3, F) for i in range(Nl)]
     re1 = np.array([[kA[i][q] - kB[i][q] for i in range(Nl)] for q in range(3)], dtype=F)
     ne = x[1] * nH_ + (x[3] + F(2) * x[4]) * nHe_
-    em = [(re1[0] * nH_ * x[1] * ne) / (four * pi), (re1[1] * nHe_ * x[3] * ne) / (four * pi),
-          (re1[2] * nHe_ * x[4] * ne) / (four * pi)]
-    F0 = [e * four * pi * vol / area for e in em]
+    fp = F(4.0) * F(PI)
+    em = [(re1[0] * nH_ * x[1] * ne) / fp, (re1[1] * nHe_ * x[3] * ne) / fp,
+          (re1[2] * nHe_ * x[4] * ne) / fp]
+    return E, nH_, nHe_, x, Nl, Eth, sth, s_H1, s_He1, em
+
+
+def _rec_rates(Fl, Eth, sth, s_H1, s_He1, scale, F):
+    """Fluxes (or 4 pi J) at the three thresholds -> the six rates (sphere_base.f90:319-342,
+    :712-733, :1046-1067), quirks included: He1h carries no excess-energy factor, He2h = 0."""
+    H1i = (Fl[0] * s_H1[0] + Fl[1] * s_H1[1] + Fl[2] * s_H1[2]) * scale
+    He1i = (Fl[1] * s_He1[1] + Fl[2] * s_He1[2]) * scale
+    He2i = (Fl[2] * sth[2]) * scale
+    H1h = (Fl[1] * (Eth[1] - Eth[0]) * s_H1[1] + Fl[2] * (Eth[2] - Eth[0]) * s_H1[2]) * scale * F(EV2ERG)
+    He1h = (Fl[1] * s_He1[1] + Fl[2] * s_He1[2]) * scale * F(EV2ERG)
+    return H1i, He1i, He2i, H1h, He1h, np.zeros(Fl.shape[1], dtype=F)
+
+
+def _rec_shells(E, nH_, nHe_, x, sth, em, F):
+    """dtau at the thresholds per shell, mid radii, flux leaving each shell (:166-246)."""
+    half, fp = F(0.5), F(4.0) * F(PI)
+    dr = np.abs(E[:-1] - E[1:])
+    r_c = (E[:-1] + E[1:]) * half
+    dt = [dr * nH_ * x[0] * sth[0], dr * nHe_ * x[2] * sth[1], dr * nHe_ * x[3] * sth[2]]
+    area = fp * r_c * r_c
+    vol = np.abs(F(4.0) / F(3.0) * F(PI) * (E[:-1] ** 3 - E[1:] ** 3))
+    F0 = [e * fp * vol / area for e in em]
+    return r_c, dt, F0
+
+
+def _rec_add(Fl, isl, irl, tau, r_c, F0, sth, s_H1, s_He1, w):
+    geo = (r_c[irl] / r_c[isl]) * (r_c[irl] / r_c[isl])
+    t0 = tau[0] * (s_H1[0] / sth[0])
+    Fl[0, isl] = Fl[0, isl] + w * F0[0][irl] * geo * np.exp(-t0)
+    t1 = tau[0] * (s_H1[1] / sth[0]) + tau[1] * (s_He1[1] / sth[1])
+    Fl[1, isl] = Fl[1, isl] + w * F0[1][irl] * geo * np.exp(-t1)
+    t2 = tau[0] * (s_H1[2] / sth[0]) + tau[1] * (s_He1[2] / sth[1]) + tau[2] * (sth[2] / sth[2])
+    Fl[2, isl] = Fl[2, isl] + w * F0[2][irl] * geo * np.exp(-t2)
+
+
+def recomb_outward(Edges, nH, nHe, T, x, F):
+    """set_recomb_photons_outward (sphere_base.f90:79-346): recombination photons of every
+    shell stream radially outward.  ``Edges`` decreasing (outermost shell first), ``x``
+    [5][Nl].  Returns (H1i, He1i, He2i, H1h, He1h, He2h) per solve layer."""
+    E, nH_, nHe_, x, Nl, Eth, sth, s_H1, s_He1, em = _rec_setup(Edges, nH, nHe, T, x, F)
+    r_c, dt, F0 = _rec_shells(E, nH_, nHe_, x, sth, em, F)
+    half = F(0.5)
     Fl = np.zeros((3, Nl), dtype=F)
     for isl in range(Nl):
         tau = [F(0), F(0), F(0)]
-        for irl in range(isl, Nl):
+        for irl in range(isl, Nl):                                  # :262-312
             for X in range(3):
                 if irl == isl or irl == isl + 1:
                     tau[X] = tau[X] + dt[X][irl] * half
                 else:
                     tau[X] = tau[X] + dt[X][irl - 1] * half
                     tau[X] = tau[X] + dt[X][irl] * half
-            geo = (r_c[irl] / r_c[isl]) * (r_c[irl] / r_c[isl])
-            t0 = tau[0] * (s_H1[0] / sth[0])
-            Fl[0, isl] = Fl[0, isl] + F0[0][irl] * geo * np.exp(-t0)
-            t1 = tau[0] * (s_H1[1] / sth[0]) + tau[1] * (s_He1[1] / sth[1])
-            Fl[1, isl] = Fl[1, isl] + F0[1][irl] * geo * np.exp(-t1)
-            t2 = tau[0] * (s_H1[2] / sth[0]) + tau[1] * (s_He1[2] / sth[1]) + tau[2] * (sth[2] / sth[2])
-            Fl[2, isl] = Fl[2, isl] + F0[2][irl] * geo * np.exp(-t2)
-    H1i = Fl[0] * s_H1[0] + Fl[1] * s_H1[1] + Fl[2] * s_H1[2]
-    He1i = Fl[1] * s_He1[1] + Fl[2] * s_He1[2]
-    He2i = Fl[2] * sth[2]
-    H1h = (Fl[1] * (Eth[1] - Eth[0]) * s_H1[1] + Fl[2] * (Eth[2] - Eth[0]) * s_H1[2]) * F(EV2ERG)
-    He1h = (Fl[1] * s_He1[1] + Fl[2] * s_He1[2]) * F(EV2ERG)
-    He2h = np.zeros(Nl, dtype=F)
-    return H1i, He1i, He2i, H1h, He1h, He2h
+            _rec_add(Fl, isl, irl, tau, r_c, F0, sth, s_H1, s_He1, F(1))
+    return _rec_rates(Fl, Eth, sth, s_H1, s_He1, F(1), F)
+
+
+def recomb_radial(Edges, nH, nHe, T, x, F):
+    """set_recomb_photons_radial (sphere_base.f90:392-750): half of every shell's photons go
+    radially inward (through the centre and out the other side), half outward.  ``Edges``
+    INCREASING here (the routine's own orientation, 1-based layers in the Fortran).  The far
+    side of the inward walk (layers beyond the solve layer) adds no optical depth -- the
+    routine's own statement (:575-590) -- and is reproduced."""
+    E, nH_, nHe_, x, Nl, Eth, sth, s_H1, s_He1, em = _rec_setup(Edges, nH, nHe, T, x, F)
+    r_c, dt, F0 = _rec_shells(E, nH_, nHe_, x, sth, em, F)
+    half = F(0.5)
+    Fl = np.zeros((3, Nl), dtype=F)
+    for isl in range(1, Nl + 1):                                    # 1-based as in the Fortran
+        tau = [F(0), F(0), F(0)]
+        for il in range(isl, -Nl - 1, -1):                          # :567-632
+            if il == 0:
+                continue
+            irl = abs(il)
+            for X in range(3):
+                if irl == isl or irl == isl - 1:
+                    tau[X] = tau[X] + dt[X][irl - 1] * half
+                elif irl < isl - 1:
+                    tau[X] = tau[X] + dt[X][irl] * half
+                    tau[X] = tau[X] + dt[X][irl - 1] * half
+            _rec_add(Fl, isl - 1, irl - 1, tau, r_c, F0, sth, s_H1, s_He1, half)
+        tau = [F(0), F(0), F(0)]
+        for irl in range(isl, Nl + 1):                              # :640-703
+            for X in range(3):
+                if irl == isl or irl == isl + 1:
+                    tau[X] = tau[X] + dt[X][irl - 1] * half
+                else:
+                    tau[X] = tau[X] + dt[X][irl - 1] * half
+                    tau[X] = tau[X] + dt[X][irl - 2] * half
+            _rec_add(Fl, isl - 1, irl - 1, tau, r_c, F0, sth, s_H1, s_He1, half)
+    return _rec_rates(Fl, Eth, sth, s_H1, s_He1, F(1), F)
+
+
+def recomb_isotropic(Edges, nH, nHe, T, x, mu, wmu, em_fac, F):
+    """set_recomb_photons_isotropic (sphere_base.f90:800-1083): formal solution along the
+    ``Nmu`` rays of every solve layer at the three thresholds, then the angle average.
+    ``Edges`` decreasing; ``mu``, ``wmu`` the Gauss-Legendre rule (:963)."""
+    E, nH_, nHe_, x, Nl, Eth, sth, s_H1, s_He1, em = _rec_setup(Edges, nH, nHe, T, x, F)
+    half = F(0.5)
+    em = [e * F(f) for e, f in zip(em, em_fac)]                     # :955-957
+    dk = [nH_ * x[0] * s_H1[0],
+          nH_ * x[0] * s_H1[1] + nHe_ * x[2] * s_He1[1],
+          nH_ * x[0] * s_H1[2] + nHe_ * x[2] * s_He1[2] + nHe_ * x[3] * sth[2]]   # :906-918
+    J = np.zeros((3, Nl), dtype=F)
+    for il in range(Nl):
+        I = np.zeros((3, len(mu)), dtype=F)
+        for imu in range(len(mu)):
+            m_ = F(mu[imu])
+            p = (E[il] + E[il + 1]) * half * np.sqrt(F(1) - m_ * m_)
+            m = next(i for i in range(1, Nl + 1) if E[i] <= p) - 1
+            j0 = il if m_ <= 0 else 2 * m - il
+            tau = [F(0), F(0), F(0)]
+            for j in range(j0, 2 * m + 1):                          # :1003-1023
+                jnl = m - abs(m - j)
+                ds = _ds_segment(E, il, m_, j, F)
+                if j == j0:
+                    ds = ds * half
+                for q in range(3):
+                    tau[q] = tau[q] + ds * dk[q][jnl]
+                    I[q, imu] = I[q, imu] + em[q][jnl] * ds * np.exp(-tau[q])
+        for q in range(3):
+            J[q, il] = _ssum(I[q] * np.asarray(wmu, dtype=F))       # :1029-1031
+    J = J * half
+    return _rec_rates(J, Eth, sth, s_H1, s_He1, F(4.0) * F(PI), F)
+
+
+def recomb_slab(Edges, nH, nHe, T, x, F):
+    """set_recomb_photons of the slabs (slab_base.f90:163-560): plane-parallel diffuse field,
+    J at the centre of every layer from the emission on the edges seen through E1 of the
+    optical depth, trapezoid in z below and above, plus the layer's own contribution."""
+    E, nH_, nHe_, x, Nl, Eth, sth, s_H1, s_He1, em = _rec_setup(Edges, nH, nHe, T, x, F)
+    half = F(0.5)
+    dl = E[1:] - E[:-1]
+    dt = [dl * nH_ * x[0] * sth[0], dl * nHe_ * x[2] * sth[1], dl * nHe_ * x[3] * sth[2]]
+    ra = [(F(1),), (s_H1[1] / s_H1[0], F(1)), (s_H1[2] / s_H1[0], s_He1[2] / s_He1[1], F(1))]
+    J = np.zeros((3, Nl), dtype=F)
+    for q in range(3):
+        lo = np.zeros(Nl + 1, dtype=F)                               # :333-351
+        for k in range(1, Nl + 1):
+            acc = lo[k - 1]
+            for X in range(q + 1):
+                acc = acc + dt[X][k - 1] * ra[q][X]
+            lo[k] = acc
+        e = np.zeros(Nl + 1, dtype=F)                                # :367-384
+        e[0], e[Nl] = em[q][0] * half, em[q][Nl - 1] * half
+        e[1:Nl] = (em[q][:-1] + em[q][1:]) * half
+        for k in range(Nl):                                          # :393-512
+            tau = (lo[k + 1] - lo[k]) * half
+            J_lo = dl[k] * em[q][k] * _e1xa(tau, F) * half
+            J_hi = J_lo
+            g = np.zeros(Nl + 1, dtype=F)
+            if k != 0:
+                tau = (lo[k + 1] - lo[k]) * half
+                g[k] = e[k] * _e1xa(tau, F)
+                for i in range(k - 1, -1, -1):
+                    tau = tau + (lo[i + 1] - lo[i])
+                    g[i] = e[i] * _e1xa(tau, F)
+                J_lo = J_lo + _trap(E[:k + 1], g[:k + 1])
+            if k != Nl - 1:
+                tau = (lo[k + 1] - lo[k]) * half
+                g[k + 1] = e[k + 1] * _e1xa(tau, F)
+                for i in range(k + 1, Nl):
+                    tau = tau + (lo[i + 1] - lo[i])
+                    g[i + 1] = e[i + 1] * _e1xa(tau, F)
+                J_hi = J_hi + _trap(E[k + 1:], g[k + 1:])
+            J[q, k] = (J_lo + J_hi) * F(4.0) * F(PI) * half          # :523-532
+    ev = F(EV2ERG)
+    H1i = J[2] * s_H1[2] + J[1] * s_H1[1] + J[0] * s_H1[0]           # :538-556, as written there:
+    He1i = J[2] * s_He1[2] + J[1] * s_He1[1]                         # He1h uses E_He2 - E_H1
+    He2i = J[2] * sth[2]
+    H1h = J[2] * (Eth[2] - Eth[0]) * s_H1[2] * ev + J[1] * (Eth[1] - Eth[0]) * s_H1[1] * ev
+    He1h = J[2] * (Eth[2] - Eth[0]) * s_He1[2] * ev
+    return H1i, He1i, He2i, H1h, He1h, np.zeros(Nl, dtype=F)

@@ -250,25 +250,74 @@ def test_one_gauss_seidel_sweep_of_sphere_bgnd(orc, find_Teq):
         assert abs(float(Tn) / one["T"][io] - 1.0) <= 1e-15, il
 
 
-def test_outward_recombination_photon_closure(orc):
-    """set_recomb_photons_outward (sphere_base.f90:79-346): the closure the first sweep of a
-    rec_meth = outward solve evaluates on the thin state, against the second derivation."""
+@pytest.mark.parametrize("meth", ["outward", "radial", "isotropic"])
+def test_sphere_recombination_photon_closures(orc, meth):
+    """set_recomb_photons_outward / _radial / _isotropic (sphere_base.f90:79-1083): the closure
+    the first sweep of a rec_meth solve evaluates on the thin state, against the second
+    derivation (float64: same statements; longdouble: the truth)."""
     Nl, Nnu, Nmu = 20, 16, 4
     cfg = _sphere_cfg("log_clumpy", Nl, Nnu, Nmu, False)
     a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], Nmu, cfg["E_eV"], cfg["shape"])
-    kw = dict(z=3.0, order=orc.ORDER_JACOBI, i_rec_meth=2)
+    em_fac = (1.0, 0.8, 1.25) if meth == "isotropic" else (1.0, 1.0, 1.0)
+    kw = dict(z=3.0, order=orc.ORDER_JACOBI, i_rec_meth={"outward": 2, "radial": 3, "isotropic": 4}[meth],
+              em_fac=em_fac)
     thin = orc.sphere_bgnd_solve(*a, i_thin=1, **kw)
     one = orc.sphere_bgnd_solve(*a, max_sweeps=1, **kw)
+    assert cfg["Edges"][1] > cfg["Edges"][0]
     rv = lambda v: np.asarray(v)[::-1].copy()  # noqa: E731
     names = ("H1i_rec", "He1i_rec", "He2i_rec", "H1h_rec", "He1h_rec", "He2h_rec")
+    mu, w = orc.p_quadrature_rule(Nmu)
     for F, tol in ((np.float64, 1e-13), (np.longdouble, 1e-12)):
-        got = so.recomb_outward(rv(cfg["Edges"]), rv(cfg["nH"]), rv(cfg["nHe"]), rv(thin["T"]),
-                                [rv(thin[k]) for k in FR], F)
+        if meth == "radial":                    # the routine's own orientation: increasing edges
+            got = so.recomb_radial(cfg["Edges"], cfg["nH"], cfg["nHe"], thin["T"],
+                                   [thin[k] for k in FR], F)
+            got = [rv(g) for g in got]
+        else:
+            args = (rv(cfg["Edges"]), rv(cfg["nH"]), rv(cfg["nHe"]), rv(thin["T"]),
+                    [rv(thin[k]) for k in FR])
+            got = (so.recomb_outward(*args, F) if meth == "outward"
+                   else so.recomb_isotropic(*args, mu, w, em_fac, F))
         for g, k in zip(got, names):
             ref = rv(one[k])
             g = np.asarray(g, dtype=np.float64)
             assert np.all((ref == 0.0) == (g == 0.0)), k
             nz = ref != 0.0
             if nz.any():
-                assert np.max(np.abs(g[nz] / ref[nz] - 1.0)) <= tol, (F, k, np.max(np.abs(g[nz] / ref[nz] - 1.0)))
+                err = np.max(np.abs(g[nz] / ref[nz] - 1.0))
+                assert err <= tol, (F, k, err)
+    assert np.any(one["H1i_rec"] > 0.0) and np.all(one["He2h_rec"] == 0.0)
+
+
+@pytest.mark.parametrize("geom", ["slab_plane_1", "slab_plane_2", "slab_bgnd"])
+def test_slab_recombination_photon_closure(orc, geom):
+    """set_recomb_photons (slab_base.f90:163-560), rec_meth = ray, on the thin state."""
+    Nl, Nnu = 24, 16
+    rng = np.random.default_rng(17)
+    if geom == "slab_bgnd":
+        cfg = configs.c3_slab_bgnd(Nl, Nnu, False)
+        solve, kw = orc.slab_bgnd_solve, dict(z=3.0, i_rec_meth=2)
+    else:
+        cfg = configs.c2_slab_plane(Nl, Nnu, False, two_sided=(geom == "slab_plane_2"))
+        solve, kw = orc.slab_plane_solve, dict(z=3.0, i_rec_meth=2, i_2side=int(geom == "slab_plane_2"))
+    cfg["nH"] = cfg["nH"] * 10 ** rng.normal(0.0, 1.0, Nl)
+    cfg["nHe"] = cfg["nH"] * 0.08
+    a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], cfg["E_eV"], cfg["shape"])
+    thin = solve(*a, i_thin=1, **kw)
+    one = solve(*a, max_sweeps=1, **kw)
+    ncell = Nl if geom == "slab_plane_1" else Nl // 2
+    names = ("H1i_rec", "He1i_rec", "He2i_rec", "H1h_rec", "He1h_rec", "He2h_rec")
+    # longdouble: the routine recovers each layer's optical depth as a DIFFERENCE of the running
+    # sums tau_lo(k+1) - tau_lo(k) (:400-427), which in float64 carries eps * tau_lo / dtau
+    for F, tol in ((np.float64, 1e-13), (np.longdouble, 1e-10)):
+        got = so.recomb_slab(cfg["Edges"], cfg["nH"], cfg["nHe"], thin["T"], [thin[k] for k in FR], F)
+        for g, k in zip(got, names):
+            ref = np.asarray(one[k])[:ncell]
+            g = np.asarray(g, dtype=np.float64)[:ncell]
+            if ncell < Nl:                      # slab_bgnd.f90:842-865: rates reflected too
+                assert np.array_equal(np.asarray(one[k])[::-1][:ncell], ref), k
+            assert np.all((ref == 0.0) == (g == 0.0)), k
+            nz = ref != 0.0
+            if nz.any():
+                err = np.max(np.abs(g[nz] / ref[nz] - 1.0))
+                assert err <= tol, (F, k, err)
     assert np.any(one["H1i_rec"] > 0.0) and np.all(one["He2h_rec"] == 0.0)
