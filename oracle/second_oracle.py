@@ -9,7 +9,8 @@ structure (per-segment ds_segment calls, six separate frequency integrals), so i
 and only used at small sizes by tests/test_second_oracle.py to pin the C oracle:
 one sweep of every geometry -- SphereBgnd (Jacobi order and the reference's sequential
 Gauss-Seidel order), Slab2Bgnd, SlabPln, Slab2Pln, SphereStromgren (monochromatic and
-polychromatic point source) -- and the single-zone solvers solve_pce_s, solve_pcte_s.
+polychromatic point source) --, the single-zone solvers solve_pce_s, solve_pcte_s and the
+recombination-photon closures (outward, radial, isotropic; slab).
 """
 import numpy as np
 
