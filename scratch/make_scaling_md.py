@@ -7,12 +7,16 @@ tags = {1: tag, 2: tag, 4: tag, 8: tag}
 for a in sys.argv[2:]:
     n, t = a.split("=")
     tags[int(n)] = t
-def L(f): return json.load(open(os.path.join(ROOT, "profiles", f)))
+def L(f):
+    f = os.path.join(ROOT, "profiles", f)
+    return json.load(open(f)) if os.path.exists(f) else None
 rows = [(1, L("%s_bench_n1.json" % tags[1]), None)] + [(n, L("%s_bench_n%d.json" % (tags[n], n)), L("%s_bench_n%d_b.json" % (tags[n], n))) for n in (2, 4, 8)]
 out = ["# Round 2 (final build): scaling over the 8 B200s of one box (bench.py --gpus N under torchrun, one rank per GPU)", "",
 "All numbers: CUDA events on the launching stream, max over ranks, L2 flushed between timed steps, clocks 1965 MHz without throttle reasons.",
-"Records: " + ", ".join("`%s_bench_n%d.json`" % (tags[n], n) for n in (1, 2, 4, 8)) + " (`_b`: an immediate second run of the C4 part; `r02x` = the same kernels",
-"before the results of a batch were read back into the plan's pinned buffer, which only changes the C5 read-back column).", "",
+"Records: " + ", ".join("`%s_bench_n%d.json`" % (tags[n], n) for n in (1, 2, 4, 8)) + " (`_b`: an immediate second run of the C4 part).  The `r02x` records at N = 4 and 8",
+"are an earlier measurement (before the exp-table exponent trick of the frequency kernel and the pinned result buffer) on another box: C4 sweep" + "".join(
+    " N=%d %.3f / %.3f ms," % (n, L("r02x_bench_n%d.json" % n)["ms_per_step"], L("r02x_bench_n%d_b.json" % n)["ms_per_step"]) for n in (4, 8)) + " i.e. the",
+"run-to-run spread at N >= 4 (barrier skew between the ranks) is ~0.02 ms and larger than the kernel gain there.", "",
 "## C4: one SphereBgnd problem (4096 x 512 x 256), cells sharded over peer memory in 32-cell blocks -- STRONG scaling of a 0.72 ms sweep", "",
 "| N | ms / sweep (second run) | evals/s | speed-up | efficiency | converged solve (45 sweeps, host pointers) | parity_vs_n1 |", "|---|---|---|---|---|---|---|"]
 t1 = rows[0][1]["ms_per_step"]
@@ -30,8 +34,8 @@ out += ["", "One rank's share alone on a GPU (`scratch/rank_share2.py`, no barri
 "Why one sweep does not scale further (DESIGN.md 6): the far-field moment scan (0.024 ms) is needed in full by every rank; ~0.05 ms of the column",
 "kernel is per-CTA shared-memory fill and the latency of one warp's walk (with 2048 work items on 148 SMs every warp has one or two); 512 cells on 148",
 "SMs leave the frequency kernel's slowest SM with 4 cells against 3.46 on average; cell solve + finish are 0.035 ms of latency; the flag barrier adds",
-"the skew between the ranks (0.03-0.05 ms).  Round 1 measured 0.382 ms per sweep at N = 8 (from a 1.63 ms single-GPU sweep); now 0.26 ms from 0.72 ms,",
-"and a converged C4 solve on eight GPUs takes 11.2 ms (round 1: 17 ms).", "",
+"the skew between the ranks (0.03-0.05 ms).  Round 1 measured 0.382 ms per sweep at N = 8 (from a 1.63 ms single-GPU sweep); now 0.26-0.27 ms from 0.72 ms,",
+"and a converged C4 solve on eight GPUs takes 10.9 ms (round 1: 17 ms).", "",
 "C4 with find_Teq (ms / sweep): " + ", ".join("N=%d %.3f" % (n, d["c4_find_Teq"]["ms_per_step"]) for n, d, b in rows), "",
 "## C5: 8192 independent SphereBgnd solves (512 x 128 x 32), problems dealt over the ranks, no exchange", "",
 "| N | fixed T: wall s (staging / solve / read-back) | speed-up (solve) | find_Teq: wall s (solve) | speed-up (solve) |", "|---|---|---|---|---|"]
