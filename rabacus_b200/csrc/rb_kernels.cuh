@@ -29,7 +29,11 @@
 #pragma once
 #include <cooperative_groups.h>
 
+#ifdef RB_FAR_COEFFS_H   // another (RATIO, NT) pair: -DRB_FAR_COEFFS_H='"path"' (gen_far_coeffs.py)
+#include RB_FAR_COEFFS_H
+#else
 #include "rb_far_coeffs.h"
+#endif
 #include "rb_ion.cuh"
 
 namespace rb {
