@@ -332,7 +332,7 @@ struct rb_plan {
     RecConst K;
     RecDev R;
     PeerDev Q;
-    int rec_meth, live, spec_g, cols_chunks, sharded, use_far, order, nu_ltab;
+    int rec_meth, live, spec_g, cols_chunks, sharded, use_far, order, nu_ltab, far_split, pad_;
   };
   GraphKey gkey;
   bool gkey_valid = false;
@@ -1007,6 +1007,11 @@ static int live_problems(const rb_plan *p) {
 // far-field moment table of every problem (k_far_moments): one cluster per problem, as many
 // CTAs as it takes to give every (segment, absorber) a thread and -- for small batches --
 // to spread one problem's scan over several SMs
+static bool far_split_wanted() {   // testing knob, part of the graph key
+  const char *e = getenv("RB_FAR_SPLIT");
+  return !(e && atoi(e) == 0);
+}
+
 static int launch_far_moments(rb_plan *p) {
   const int Nl = p->d.Nl, B = p->d.n_problems;
   const int nseg = (Nl + 1 + kFarSeg - 1) / kFarSeg;
@@ -1015,8 +1020,14 @@ static int launch_far_moments(rb_plan *p) {
   while (cs > 1 && nseg < cs) cs /= 2;
   const int spc = (nseg + cs - 1) / cs;
   if (3 * spc > kFarThreads) return RB_ERR_UNSUPPORTED;
-  const size_t smem = far_smem_bytes(spc);
-  int rc = set_smem(k_far_moments, smem);
+  // the moments of a (segment, absorber) dealt over kFarParts threads: for launches that are
+  // bound by the latency of one CTA's scan (few problems), where the factor table fits in
+  // shared memory (grids up to ~6500 shells).  Large batches keep one thread per (segment,
+  // absorber): six CTAs per SM instead of one.  RB_FAR_SPLIT=0: never split.
+  const bool split = far_split_wanted() && (long long)B * cs <= 2LL * p->n_sm &&
+                     far_split_smem_bytes(spc) <= (size_t)226 * 1024;
+  const size_t smem = split ? far_split_smem_bytes(spc) : far_smem_bytes(spc);
+  int rc = split ? set_smem(k_far_moments_split, smem) : set_smem(k_far_moments, smem);
   if (rc) return rc;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -1029,7 +1040,8 @@ static int launch_far_moments(rb_plan *p) {
   at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, k_far_moments, p->P, p->dfar, cs, spc, p->far_slog));
+  if (split) CK(cudaLaunchKernelEx(&cfg, k_far_moments_split, p->P, p->dfar, cs, spc, p->far_slog));
+  else CK(cudaLaunchKernelEx(&cfg, k_far_moments, p->P, p->dfar, cs, spc, p->far_slog));
   p->info.n_launches += 1;
   return RB_OK;
 }
@@ -1589,6 +1601,7 @@ static int sweep_graph(rb_plan *p, bool sharded) {
     key.spec_g = a ? atoi(a) : 0;
     key.cols_chunks = b ? atoi(b) : 0;
     key.nu_ltab = c ? atoi(c) : 0;
+    key.far_split = far_split_wanted() ? 1 : 0;
   }
   if (!p->gkey_valid || memcmp(&p->gkey, &key, sizeof(key)) != 0) {
     destroy_graphs(p);

@@ -421,6 +421,167 @@ __global__ void __launch_bounds__(kFarThreads) k_far_moments(PlanDev P, double *
   if (csize > 1) cg::this_cluster().sync();   // peers may still read cA / cB
 }
 
+// k_far_moments_split: the same scan with the NT moments of a (segment, absorber) dealt over
+// kFarParts threads.  In k_far_moments one thread carries all NT recurrences of its segment and
+// absorber and regenerates the factors g^(2n-1) at every edge: 2 NT FP64 instructions per edge
+// on 3 x segments threads -- two warps per CTA, 11 of the kernel's 24 us at C4 (ncu source
+// page, profiles/r02z_far_moments_ncu.txt).  Here the fill forms the factors of every edge
+// ONCE (the same two multiplication chains as far_step, so the same bits) into shared memory
+// and thread (segment, absorber, part) advances NT / kFarParts recurrences by one fma each.
+// Every M_n sees the same operations in the same order as in k_far_moments: the rows are
+// bit-identical (tests/test_gpu_far_field.py compares the two kernels).
+constexpr int kFarParts = 5;
+constexpr int kFarPer = (kFarNT + kFarParts - 1) / kFarParts;   // moments per thread
+constexpr int kFarFStride = kFarSeg * kFarNT + 2;   // doubles per segment of the factor table
+__host__ __device__ inline size_t far_split_smem_bytes(int spc) {
+  return far_smem_bytes(spc) + (size_t)spc * kFarFStride * sizeof(double);
+}
+
+__global__ void __launch_bounds__(kFarThreads) k_far_moments_split(PlanDev P,
+                                                                  double *__restrict__ far,
+                                                                  int csize, int spc, int slog) {
+  namespace cg = cooperative_groups;
+  extern __shared__ double4 s_far4[];
+  const int b = blockIdx.x / csize, crank = blockIdx.x % csize;
+  const int Nl = P.Nl, nedge = Nl + 1;
+  const int nseg = (nedge + kFarSeg - 1) / kFarSeg;
+  const int seg0 = min(nseg, crank * spc), seg1 = min(nseg, seg0 + spc);
+  const int nmine = seg1 - seg0;
+  FarSmem S;
+  S.rec = s_far4;
+  S.ginv = reinterpret_cast<double *>(s_far4 + (size_t)spc * kFarSeg);
+  S.sA = S.ginv + (size_t)spc * kFarSeg;
+  S.sB = S.sA + (size_t)spc * kFarNT;
+  S.cA = S.sB + (size_t)spc * 3 * kFarNT;
+  S.cB = S.cA + kFarNT;
+  S.cin = S.cB + 3 * kFarNT;
+  double *fT = S.cin + 3 * kFarNT;      // [spc][kFarSeg][NT] (+2 per segment: banks)
+  const bool live = P.active[b] != 0;   // uniform over the cluster
+  const double *E = P.Edges + (size_t)b * nedge;
+  if (live) {
+    const int k0 = seg0 * kFarSeg, k1 = min(nedge, seg1 * kFarSeg);
+    for (int k = k0 + (int)threadIdx.x; k < k1; k += blockDim.x) {
+      const double4 r = shell_record(P, b, k);
+      const double g = far_g(E, k);
+      const double ginv = g > 0.0 ? 1.0 / g : 0.0;
+      S.rec[k - k0] = make_double4(g, r.y, r.z, r.w);
+      P.pack[(size_t)b * (nedge + kPackPad) + k] = r;
+      // the factors of far_step, generated by the same two chains
+      double *f = fT + (size_t)((k - k0) / kFarSeg) * kFarFStride + ((k - k0) % kFarSeg) * kFarNT;
+      const double g2 = g * g, g4 = g2 * g2;
+      double fe = ginv, fo = g;
+#pragma unroll
+      for (int n = 0; n < kFarNT; n += 2) {
+        f[n] = fe;
+        fe = fe * g4;
+        if (n + 1 < kFarNT) {
+          f[n + 1] = fo;
+          fo = fo * g4;
+        }
+      }
+    }
+    if (crank == csize - 1 && threadIdx.x < kPackPad)
+      P.pack[(size_t)b * (nedge + kPackPad) + nedge + threadIdx.x] =
+          make_double4(0.0, 0.0, 0.0, 0.0);
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  const int nunit = live ? nmine * 3 * kFarParts : 0;   // (segment, absorber, part)
+  for (int u = t; u < nunit; u += blockDim.x) {
+    const int sl = u / (3 * kFarParts), rem = u - sl * 3 * kFarParts;
+    const int X = rem / kFarParts, n0 = (rem - X * kFarParts) * kFarPer;
+    const int kb = (seg0 + sl) * kFarSeg, ke = min(nedge, kb + kFarSeg);
+    double M[kFarPer];
+#pragma unroll
+    for (int i = 0; i < kFarPer; ++i) M[i] = 0.0;
+    const double *f = fT + (size_t)sl * kFarFStride + n0;
+    for (int k = kb; k < ke; ++k, f += kFarNT) {
+      const double4 r = S.rec[k - seg0 * kFarSeg];
+      const double D = X == 0 ? r.y : (X == 1 ? r.z : r.w);
+#pragma unroll
+      for (int i = 0; i < kFarPer; ++i)
+        if (n0 + i < kFarNT) M[i] = fma(M[i], f[i], D);
+    }
+#pragma unroll
+    for (int i = 0; i < kFarPer; ++i)
+      if (n0 + i < kFarNT) S.sB[(sl * 3 + X) * kFarNT + n0 + i] = M[i];
+    if (X == 0 && n0 == 0) {   // A_s[n] = G^(2n-1)
+      double G = 1.0;
+      for (int k = kb; k < ke; ++k) G = G * S.rec[k - seg0 * kFarSeg].x;
+      const double G2 = G * G;
+      double a = G > 0.0 ? 1.0 / G : 0.0;
+#pragma unroll
+      for (int n = 0; n < kFarNT; ++n) { S.sA[sl * kFarNT + n] = a; a = a * G2; }
+    }
+  }
+  __syncthreads();
+  if (t < 3 * kFarNT) {   // CTA composite over its segments
+    const int X2 = t / kFarNT, n = t - X2 * kFarNT;
+    double ca = 1.0, cb = 0.0;
+    for (int j = 0; j < nmine; ++j) {
+      const double a = S.sA[j * kFarNT + n];
+      cb = fma(cb, a, S.sB[(j * 3 + X2) * kFarNT + n]);
+      ca = ca * a;
+    }
+    S.cB[X2 * kFarNT + n] = cb;
+    if (X2 == 0) S.cA[n] = ca;
+  }
+  if (csize > 1) cg::this_cluster().sync(); else __syncthreads();
+  if (t < 3 * kFarNT) {   // carry into this CTA from the CTAs before it
+    const int X2 = t / kFarNT, n = t - X2 * kFarNT;
+    double ra[kMaxClusterFar], rb_[kMaxClusterFar];
+#pragma unroll
+    for (int c = 0; c < kMaxClusterFar; ++c) {
+      ra[c] = 1.0; rb_[c] = 0.0;
+      if (c < crank) {
+        ra[c] = cg::this_cluster().map_shared_rank(S.cA, c)[n];
+        rb_[c] = cg::this_cluster().map_shared_rank(S.cB, c)[X2 * kFarNT + n];
+      }
+    }
+    double ci = 0.0;
+#pragma unroll
+    for (int c = 0; c < kMaxClusterFar; ++c)
+      if (c < crank) ci = fma(ci, ra[c], rb_[c]);
+    S.cin[X2 * kFarNT + n] = ci;
+  }
+  __syncthreads();
+  for (int u = t; u < nunit; u += blockDim.x) {
+    const int sl = u / (3 * kFarParts), rem = u - sl * 3 * kFarParts;
+    const int X = rem / kFarParts, n0 = (rem - X * kFarParts) * kFarPer;
+    const int kb = (seg0 + sl) * kFarSeg, ke = min(nedge, kb + kFarSeg);
+    double M[kFarPer], bn[kFarPer];
+#pragma unroll
+    for (int i = 0; i < kFarPer; ++i) {
+      const bool on = n0 + i < kFarNT;
+      M[i] = on ? S.cin[X * kFarNT + n0 + i] : 0.0;
+      bn[i] = on ? kFarB[n0 + i] : 0.0;
+    }
+    for (int j = 0; j < sl; ++j) {
+#pragma unroll
+      for (int i = 0; i < kFarPer; ++i)
+        if (n0 + i < kFarNT)
+          M[i] = fma(M[i], S.sA[j * kFarNT + n0 + i], S.sB[(j * 3 + X) * kFarNT + n0 + i]);
+    }
+    double *out = far + (size_t)b * far_rows(Nl, slog) * kFarRow + X;
+    const double *f = fT + (size_t)sl * kFarFStride + n0;
+    for (int k = kb; k < ke; ++k, f += kFarNT) {
+      const double4 r = S.rec[k - seg0 * kFarSeg];
+      const double D = X == 0 ? r.y : (X == 1 ? r.z : r.w);
+#pragma unroll
+      for (int i = 0; i < kFarPer; ++i)
+        if (n0 + i < kFarNT) M[i] = fma(M[i], f[i], D);
+      if ((k & ((1 << slog) - 1)) == 0) {
+        RB_ASSERT((k >> slog) < far_rows(Nl, slog));
+        double *row = out + (size_t)(k >> slog) * kFarRow;
+#pragma unroll
+        for (int i = 0; i < kFarPer; ++i)
+          if (n0 + i < kFarNT) row[3 * (n0 + i)] = bn[i] * M[i];
+      }
+    }
+  }
+  if (csize > 1) cg::this_cluster().sync();   // peers may still read cA / cB
+}
+
 // sum_{k<=K} s_k D_k for the three absorbers from table row K (E_K >= RATIO p)
 __device__ __forceinline__ void far_eval(const double *__restrict__ row, double u, double EK,
                                          double (&out)[3]) {
