@@ -332,7 +332,7 @@ struct rb_plan {
     RecConst K;
     RecDev R;
     PeerDev Q;
-    int rec_meth, live, spec_g, cols_chunks, sharded, use_far, order, nu_ltab, far_split, pad_;
+    int rec_meth, live, spec_g, cols_chunks, sharded, use_far, order, nu_ltab, far_split, cols_variant;
   };
   GraphKey gkey;
   bool gkey_valid = false;
@@ -1104,13 +1104,25 @@ static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, in
   }
   const int waves = (B > 1) ? 4 : 1;  // batches: ~4 CTAs per resident slot (finer tail)
   const int live = live_problems(p);
-  // A launch with fewer than ~3 items per warp (cell shards over 4-8 GPUs) is bound by the
-  // latency of ONE warp's walk, not by throughput: there the variant with four independent
-  // square roots per trip and half the warps runs (same operations in the same order:
-  // results are bit-identical).
-  const bool sparse = p->use_far && nchunk == 1 && cps == 1 &&
-                      (long long)p->n_items * live < (long long)3 * p->n_sm * warps;
-  const int warps_cta = sparse ? 8 : warps;
+  // Launch shape where the records allow one CTA per SM (the same operations in the same
+  // order in every shape: results are bit-identical).  A full launch (C4 on one GPU: 110 ray-pair
+  // items per SM) is throughput-bound and runs 16 warps per SM.  Cell shards have fewer, and
+  // the launch is then bound by the latency of the warps that hold the long walks: fewer warps
+  // per SM run them faster -- one rank's share of the C4 column stage on 2 / 4 / 8 GPUs:
+  // 0.130 / 0.107 / 0.096 ms with 512 threads, 0.125 / 0.093 / 0.084 with 384, 0.138 / 0.090 /
+  // 0.077 with 256 (profiles/r02_kernel_variants.md).  RB_COLS_VARIANT (testing knob): 1 = 256
+  // threads x 4 roots per trip, 6 = 384 x 1, 7 = 512 x 1, 9 = 256 x 1.
+  int variant = 7;
+  if (p->use_far && nchunk == 1 && cps == 1) {
+    const long long items = (long long)p->n_items * live, full = (long long)p->n_sm * 16;
+    if (2 * items < 5 * full) variant = 9;
+    else if (items < 5 * full) variant = 6;
+  }
+  if (const char *se = getenv("RB_COLS_VARIANT")) {
+    const int v = atoi(se);
+    if (v == 1 || v == 6 || v == 7 || v == 9) variant = v;
+  }
+  const int warps_cta = cps != 1 ? warps : (variant == 7 ? 16 : (variant == 6 ? 12 : 8));
   int per_problem = std::max(1, (waves * want + live - 1) / live);
   per_problem = std::min(per_problem, (p->n_items + warps_cta - 1) / warps_cta);
   // the grid spans all B problems (converged ones return at once): bound it
@@ -1127,7 +1139,14 @@ static int launch_sphere_columns(rb_plan *p, int cell_start, int cell_stride, in
   } while (0)
   // 16-18 warps per SM at ~100 registers beat 24 warps at 80 (1.035 vs 1.068 ms at C4,
   // profiles/r01_kernel_variants.md)
-  if (cps == 1) { if (sparse) COLS(256, 4, 1); else COLS(512, 1, 1); }
+  if (cps == 1) {
+    switch (variant) {
+      case 1: COLS(256, 4, 1); break;
+      case 6: COLS(384, 1, 1); break;
+      case 9: COLS(256, 1, 1); break;
+      default: COLS(512, 1, 1); break;
+    }
+  }
   else if (cps == 2) COLS(256, 1, 2);
   else COLS(192, 1, 3);
 #undef COLS
@@ -1602,6 +1621,8 @@ static int sweep_graph(rb_plan *p, bool sharded) {
     key.cols_chunks = b ? atoi(b) : 0;
     key.nu_ltab = c ? atoi(c) : 0;
     key.far_split = far_split_wanted() ? 1 : 0;
+    const char *cv = getenv("RB_COLS_VARIANT");
+    key.cols_variant = cv ? atoi(cv) : 0;
   }
   if (!p->gkey_valid || memcmp(&p->gkey, &key, sizeof(key)) != 0) {
     destroy_graphs(p);

@@ -29,8 +29,9 @@ out += ["", "Stage times (ms; N > 1: from the direct-launch warm-up steps, the t
 for n, d, b in rows:
     k = d["roofline"]["kernels"]; r = d["roofline"]
     out.append("| %d | %.3f | %.3f | %.3f | %.3f |" % (n, k["k_sphere_columns"]["ms"], k["k_nu_rates"]["ms"], r["ms_cell_solve"], r["ms_finish"]))
-out += ["", "One rank's share alone on a GPU (`scratch/rank_share2.py`, no barrier skew), total ms per sweep: 0.747 / 0.437 / 0.290 / 0.217 at N = 1 / 2 / 4 / 8",
-"(single cells dealt cyclically instead of 32-cell blocks, earlier build: 0.805 / 0.476 / 0.326 / 0.266).", "",
+out += ["", "One rank's share alone on a GPU (`scratch/rank_share2.py`, no barrier skew), total ms per sweep: 0.694 / 0.400 / 0.252 / 0.190 at N = 1 / 2 / 4 / 8 with the",
+"launch-shape rule of the column kernel added after the N = 4 / 8 records above were taken (`r02z3_rank_share.log`; with the build of those records:",
+"0.696 / 0.402 / 0.270 / 0.205; single cells dealt cyclically instead of 32-cell blocks, earlier build: 0.805 / 0.476 / 0.326 / 0.266).", "",
 "Why one sweep does not scale further (DESIGN.md 6): the far-field moment scan (0.024 ms) is needed in full by every rank; ~0.05 ms of the column",
 "kernel is per-CTA shared-memory fill and the latency of one warp's walk (with 2048 work items on 148 SMs every warp has one or two); 512 cells on 148",
 "SMs leave the frequency kernel's slowest SM with 4 cells against 3.46 on average; cell solve + finish are 0.035 ms of latency; the flag barrier adds",

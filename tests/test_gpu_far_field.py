@@ -66,3 +66,28 @@ def test_split_moment_scan_batch_is_bit_identical():
     b = _with_split(False, run)
     for k in a:
         assert np.array_equal(a[k], b[k]), k
+
+
+def _with_env(name, value, fn):
+    old = os.environ.get(name)
+    os.environ[name] = str(value)
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ[name]
+        else:
+            os.environ[name] = old
+
+
+@pytest.mark.parametrize("variant", [1, 6, 9])
+def test_column_launch_shapes_are_bit_identical(variant):
+    """k_sphere_columns_smem<THREADS, U, 1>: the launch shape is chosen from the number of
+    ray-pair items per SM (full launches 512 threads, cell shards 384 / 256; rb_api.cu
+    launch_sphere_columns) -- same operations in the same order, so every output of a solve
+    must be the same bits whatever the shape."""
+    cfg = configs.c4_sphere_bgnd(4096, 16, 16, False)
+    a = _with_env("RB_COLS_VARIANT", 7, lambda: run_gpu(cfg, max_sweeps=2))
+    b = _with_env("RB_COLS_VARIANT", variant, lambda: run_gpu(cfg, max_sweeps=2))
+    for n in FIELDS:
+        assert np.array_equal(a[n], b[n]), (variant, n)
