@@ -9,8 +9,9 @@ structure (per-segment ds_segment calls, six separate frequency integrals), so i
 and only used at small sizes by tests/test_second_oracle.py to pin the C oracle:
 one sweep of every geometry -- SphereBgnd (Jacobi order and the reference's sequential
 Gauss-Seidel order), Slab2Bgnd, SlabPln, Slab2Pln, SphereStromgren (monochromatic and
-polychromatic point source) --, the single-zone solvers solve_pce_s, solve_pcte_s and the
-recombination-photon closures (outward, radial, isotropic; slab).
+polychromatic point source) --, the single-zone solvers solve_pce_s, solve_pcte_s, the
+lock-step solve_pce_v / solve_pcte_v behind the optically thin start, the recombination-photon
+closures (outward, radial, isotropic; slab) and set_column_vs_impact.
 """
 import numpy as np
 
@@ -577,3 +578,153 @@ def recomb_slab(Edges, nH, nHe, T, x, F):
     H1h = J[2] * (Eth[2] - Eth[0]) * s_H1[2] * ev + J[1] * (Eth[1] - Eth[0]) * s_H1[1] * ev
     He1h = J[2] * (Eth[2] - Eth[0]) * s_He1[2] * ev
     return H1i, He1i, He2i, H1h, He1h, np.zeros(Nl, dtype=F)
+
+
+def column_vs_impact(Edges, nH, nHe, x, F):
+    """set_column_vs_impact (sphere_base.f90:1115-1205): total and absorber columns along the
+    full chord (mu = 0, j = 0 .. 2m) through the centre radius of every shell.  ``Edges``
+    decreasing.  Returns (NH, NHe, NH1, NHe1, NHe2)."""
+    E = np.asarray(Edges, dtype=F)
+    nH_, nHe_, x = np.asarray(nH, dtype=F), np.asarray(nHe, dtype=F), np.asarray(x, dtype=F)
+    Nl = nH_.size
+    out = np.zeros((5, Nl), dtype=F)
+    for il in range(Nl):
+        p = (E[il] + E[il + 1]) * F(0.5) * np.sqrt(F(1) - F(0) * F(0))
+        m = next(i for i in range(1, Nl + 1) if E[i] <= p) - 1
+        for j in range(0, 2 * m + 1):
+            jnl = m - abs(m - j)
+            ds = _ds_segment(E, il, F(0), j, F)
+            out[0, il] = out[0, il] + ds * nH_[jnl]
+            out[1, il] = out[1, il] + ds * nHe_[jnl]
+            out[2, il] = out[2, il] + ds * nH_[jnl] * x[0][jnl]
+            out[3, il] = out[3, il] + ds * nHe_[jnl] * x[2][jnl]
+            out[4, il] = out[4, il] + ds * nHe_[jnl] * x[3][jnl]
+    return tuple(out)
+
+
+def _ce(k, F):                                  # solve_ce ion_solver.f90:339-374 / :377-412
+    DD = k[0] + k[3]
+    x = [k[0] / DD, k[3] / DD]
+    DD = k[1] * k[2] + k[2] * k[4] + k[4] * k[5]
+    return _fpc(x + [k[1] * k[2] / DD, k[2] * k[4] / DD, k[4] * k[5] / DD])
+
+
+def solve_pce_v(nH, nHe, k, H1i, He1i, He2i, tol, F):
+    """solve_pce_v (ion_solver.f90:565-696): the lock-step form -- every zone keeps bisecting
+    until ALL zones meet the tolerance, a zone with ratio_ne == 1 keeps its newly computed n_e
+    (neither `where` fires).  ``k``: per zone the six coefficients.  Returns per zone x[5]."""
+    n = len(nH)
+    nH, nHe = [F(v) for v in nH], [F(v) for v in nHe]
+    k = [[F(v) for v in kk] for kk in k]
+    G = [[F(H1i[i]), F(He1i[i]), F(He2i[i])] for i in range(n)]
+    tol = F(tol)
+    x = [_ce(k[i], F) for i in range(n)]
+    left = [x[i][1] * nH[i] + (x[i][3] + F(2) * x[i][4]) * nHe[i] for i in range(n)]
+    right = [nH[i] + F(2) * nHe[i] for i in range(n)]
+    ne = [None] * n
+    with np.errstate(all="ignore"):
+        for i in range(n):                                      # analytic_H1_v :186-210
+            y = (x[i][3] + F(2) * x[i][4]) * nHe[i] / nH[i]
+            RR = (k[i][3] + k[i][0]) * nH[i]
+            QQ = -(G[i][0] + k[i][0] * nH[i] + RR * (F(1) + y))
+            PP = k[i][0] * nH[i] * (F(1) + y)
+            dd = QQ * QQ - F(4) * RR * PP
+            dd = F(0) if dd < 0 else dd
+            x[i][0] = PP / (-F(0.5) * (QQ - np.sqrt(dd)))
+            x[i][1] = F(1) - x[i][0]
+            ne[i] = x[i][1] * nH[i] + (x[i][3] + F(2) * x[i][4]) * nHe[i]
+        ne_old = list(ne)
+        old = [(x[i][0], x[i][2], x[i][4]) for i in range(n)]
+        err = [F(np.inf)] * n
+        it = 0
+        while any(e > tol for e in err):
+            for i in range(n):
+                x[i] = _implicit(ne[i], k[i], *G[i])
+                ne[i] = x[i][1] * nH[i] + (x[i][3] + F(2) * x[i][4]) * nHe[i]
+                ratio = ne[i] / ne_old[i]
+                err[i] = abs(max(x[i][0] / old[i][0], x[i][2] / old[i][1], x[i][4] / old[i][2]) - F(1))
+                if ratio > F(1):
+                    ne[i], left[i] = (ne_old[i] + right[i]) * F(0.5), ne_old[i]
+                elif ratio < F(1):
+                    ne[i], right[i] = (left[i] + ne_old[i]) * F(0.5), ne_old[i]
+                ne_old[i], old[i] = ne[i], (x[i][0], x[i][2], x[i][4])
+            it += 1
+            assert it <= MAX_ITER
+    for i in range(n):
+        if nH[i] <= 0:
+            x[i][0] = x[i][1] = F(0)
+        if nHe[i] <= 0:
+            x[i][2] = x[i][3] = x[i][4] = F(0)
+    return x
+
+
+def _dudT_v(nH, nHe, T, p, z, Hz, fc, tol, F):
+    """get_dudT_v (ion_solver.f90:1136-1185): lock-step solve_pce_v inside."""
+    n = len(nH)
+    x = solve_pce_v(nH, nHe, [get_kchem(T[i], fc, F) for i in range(n)],
+                    [p[i][0] for i in range(n)], [p[i][1] for i in range(n)],
+                    [p[i][2] for i in range(n)], tol, F)
+    out = []
+    for i in range(n):
+        c = get_kcool(T[i], fc, F)
+        nh, nhe, zz, hz, t = F(nH[i]), F(nHe[i]), F(z), F(Hz), F(T[i])
+        xi = x[i]
+        heat = xi[0] * nh * F(p[i][3]) + xi[2] * nhe * F(p[i][4]) + xi[3] * nhe * F(p[i][5])
+        ne = xi[1] * nh + (xi[3] + F(2) * xi[4]) * nhe
+        cool = (c[0] * ne * xi[1] * nh + c[1] * ne * xi[3] * nhe + c[2] * ne * xi[4] * nhe
+                + c[3] * ne * xi[0] * nh + c[4] * ne * xi[2] * nhe + c[5] * ne * xi[3] * nhe
+                + c[6] * ne * xi[0] * nh + c[7] * ne * xi[3] * nhe)
+        zp = F(1) + zz
+        cool = cool + c[9] * ((zp * zp) * (zp * zp)) * (t - F(2.725) * zp) * ne
+        cool = cool + c[8] * ne * (nh * xi[1] + nhe * xi[3] + F(4) * nhe * xi[4])
+        cool = cool + F(3) * hz * F(KB) * t * (nh + nhe + ne)
+        out.append(heat - cool)
+    return out
+
+
+def solve_pcte_v(nH, nHe, p, z, Hz, fc, tol, F):
+    """solve_pcte_v (ion_solver.f90:884-1056): lock-step temperature bisection; zones whose
+    balance is negative at the floor stay there.  ``p``: per zone the six rates.
+    Returns (per zone x[5], per zone T)."""
+    n = len(nH)
+    Tl, Tr = [F(TFLOOR)] * n, [F(TMAX)] * n
+    dmin = _dudT_v(nH, nHe, Tl, p, z, Hz, fc, tol, F)
+    floor = [d < 0 for d in dmin]
+    dmax = _dudT_v(nH, nHe, Tr, p, z, Hz, fc, tol, F)
+    assert not any(d > 0 and not f for d, f in zip(dmax, floor)), "Teq not bracketed"
+    T = [Tl[i] if floor[i] else F(10) ** ((np.log10(Tl[i]) + np.log10(Tr[i])) * F(0.5))
+         for i in range(n)]
+    err, it = [F(np.inf)] * n, 0
+    while any(e > F(tol) for e in err):
+        d = _dudT_v(nH, nHe, T, p, z, Hz, fc, tol, F)
+        Told = list(T)
+        for i in range(n):
+            if floor[i]:
+                pass
+            elif d[i] < 0:
+                Tr[i], T[i] = T[i], (Tl[i] + T[i]) * F(0.5)
+            elif d[i] > 0:
+                Tl[i], T[i] = T[i], (T[i] + Tr[i]) * F(0.5)
+            err[i] = abs(F(1) - T[i] / Told[i])
+        it += 1
+        assert it <= MAX_ITER
+    x = solve_pce_v(nH, nHe, [get_kchem(T[i], fc, F) for i in range(n)], [q[0] for q in p],
+                    [q[1] for q in p], [q[2] for q in p], tol, F)
+    return x, T
+
+
+def sphere_bgnd_thin(nH, nHe, T, E_eV, shape, fcA, find_Teq, z, Hz, tol, F):
+    """sphere_bgnd_optically_thin (sphere_bgnd.f90:379-499): tau = 0 rates in every shell, then
+    the lock-step solvers at tol * TOL_FRAC.  Returns (per shell x[5], T, the six rates)."""
+    Ev, sh = np.asarray(E_eV, dtype=F), np.asarray(shape, dtype=F)
+    sig = [sigma_v96(X, Ev, F) for X in range(3)]
+    r6 = _six_rates(Ev, sh, sig, np.ones_like(Ev), F)
+    n = len(nH)
+    tin = F(tol) * F(1.0e-2)
+    if find_Teq:
+        x, Tn = solve_pcte_v(nH, nHe, [r6] * n, z, Hz, (fcA,) * 3, tin, F)
+    else:
+        x = solve_pce_v(nH, nHe, [get_kchem(T[i], (fcA,) * 3, F) for i in range(n)],
+                        [r6[0]] * n, [r6[1]] * n, [r6[2]] * n, tin, F)
+        Tn = [F(t) for t in T]
+    return x, Tn, r6

@@ -321,3 +321,55 @@ def test_slab_recombination_photon_closure(orc, geom):
                 err = np.max(np.abs(g[nz] / ref[nz] - 1.0))
                 assert err <= tol, (F, k, err)
     assert np.any(one["H1i_rec"] > 0.0) and np.all(one["He2h_rec"] == 0.0)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "log_clumpy"])
+def test_column_vs_impact(orc, kind):
+    """set_column_vs_impact (sphere_base.f90:1115-1205) on a thin state, increasing and
+    decreasing edges (the routine reverses and restores)."""
+    Nl, Nnu, Nmu = 30, 16, 4
+    cfg = _sphere_cfg(kind, Nl, Nnu, Nmu, False)
+    a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], Nmu, cfg["E_eV"], cfg["shape"])
+    thin = orc.sphere_bgnd_solve(*a, i_thin=1, z=3.0, order=orc.ORDER_JACOBI)
+    x = [thin[k] for k in FR]
+    ref = orc.set_column_vs_impact(*x, cfg["Edges"], cfg["nH"], cfg["nHe"], thin["T"])
+    rv = lambda v: np.asarray(v)[::-1].copy()  # noqa: E731
+    ref_dec = orc.set_column_vs_impact(*[rv(v) for v in x], rv(cfg["Edges"]), rv(cfg["nH"]),
+                                       rv(cfg["nHe"]), rv(thin["T"]))
+    for r, d in zip(ref, ref_dec):
+        assert np.array_equal(r, rv(d))
+    for F, tol in ((np.float64, 0.0), (np.longdouble, 1e-13)):
+        got = so.column_vs_impact(rv(cfg["Edges"]), rv(cfg["nH"]), rv(cfg["nHe"]), [rv(v) for v in x], F)
+        for g, r in zip(got, ref):
+            g = rv(np.asarray(g, dtype=np.float64))
+            assert np.all(r > 0.0)
+            assert np.max(np.abs(g / r - 1.0)) <= tol, (F, np.max(np.abs(g / r - 1.0)))
+
+
+@pytest.mark.parametrize("find_Teq", [False, True])
+def test_thin_start_with_the_lock_step_solvers(orc, find_Teq):
+    """sphere_bgnd_optically_thin (sphere_bgnd.f90:379-499) with solve_pce_v / solve_pcte_v
+    (ion_solver.f90:565-696, 884-1056): every zone iterates until ALL have converged, so a
+    zone's result depends on its neighbours' iteration counts."""
+    Nl, Nnu, Nmu = 18, 16, 4
+    cfg = _sphere_cfg("log_clumpy", Nl, Nnu, Nmu, find_Teq)
+    a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], Nmu, cfg["E_eV"], cfg["shape"])
+    thin = orc.sphere_bgnd_solve(*a, i_thin=1, i_find_Teq=int(find_Teq), z=3.0,
+                                 order=orc.ORDER_JACOBI)
+    for F, x_tol in ((np.float64, 1e-13), (np.longdouble, 1e-9)):
+        x, T, r6 = so.sphere_bgnd_thin(cfg["nH"], cfg["nHe"], cfg["T"], cfg["E_eV"], cfg["shape"],
+                                       1.0, find_Teq, 3.0, 0.0, 1e-4, F)
+        for q, kname in enumerate(RT):
+            assert np.max(np.abs(float(r6[q]) / thin[kname] - 1.0)) <= 4e-15, (F, kname)
+        for i in range(Nl):
+            for q, kname in enumerate(FR):
+                assert abs(float(x[i][q]) / thin[kname][i] - 1.0) <= x_tol, (F, i, kname)
+            assert abs(float(T[i]) / thin["T"][i] - 1.0) <= 1e-15, (F, i)
+    # the lock-step result is NOT the scalar solver's: at least one zone differs in its last bits
+    if not find_Teq:
+        k = [so.get_kchem(cfg["T"][i], (1.0,) * 3, np.float64) for i in range(Nl)]
+        diff = 0
+        for i in range(Nl):
+            xs = so.solve_pce(cfg["nH"][i], cfg["nHe"][i], k[i], r6[0], r6[1], r6[2], 1e-6, np.float64)
+            diff += int(any(float(xs[q]) != thin[kname][i] for q, kname in enumerate(FR)))
+        assert diff > 0
