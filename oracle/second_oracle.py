@@ -11,7 +11,8 @@ one sweep of every geometry -- SphereBgnd (Jacobi order and the reference's sequ
 Gauss-Seidel order), Slab2Bgnd, SlabPln, Slab2Pln, SphereStromgren (monochromatic and
 polychromatic point source) --, the single-zone solvers solve_pce_s, solve_pcte_s, the
 lock-step solve_pce_v / solve_pcte_v behind the optically thin start, the recombination-photon
-closures (outward, radial, isotropic; slab) and set_column_vs_impact.
+closures (outward, radial, isotropic; slab), set_column_vs_impact, and the drivers of all
+five solvers from the thin start to convergence (equal sweep counts).
 """
 import numpy as np
 
@@ -728,3 +729,91 @@ def sphere_bgnd_thin(nH, nHe, T, E_eV, shape, fcA, find_Teq, z, Hz, tol, F):
                         [r6[0]] * n, [r6[1]] * n, [r6[2]] * n, tin, F)
         Tn = [F(t) for t in T]
     return x, Tn, r6
+
+
+def sphere_bgnd_solve(Edges, nH, nHe, T, mu, wmu, E_eV, shape, fcA, find_Teq, z, Hz, tol, F,
+                      gauss_seidel=False, max_iter=500):
+    """sphere_bgnd_solve (sphere_bgnd.f90:107-314): thin start, then sweeps until
+    all(|ne_new / ne_old - 1| < tol) (:284-296; the limit is tested before the increment).
+    ``Edges`` decreasing.  Returns (x [5][Nl], T, src [6][Nl], sweeps)."""
+    Nl = len(nH)
+    xs, Tn, r6 = sphere_bgnd_thin(nH, nHe, T, E_eV, shape, fcA, find_Teq, z, Hz, tol, F)
+    x = np.array([[xs[i][q] for i in range(Nl)] for q in range(5)], dtype=F)
+    T = np.array(Tn, dtype=F)
+    src = np.array([[r6[q]] * Nl for q in range(6)], dtype=F)
+    nH_, nHe_ = np.asarray(nH, dtype=F), np.asarray(nHe, dtype=F)
+    ne_old = x[1] * nH_ + (x[3] + F(2) * x[4]) * nHe_
+    it = 0
+    while True:
+        out = sphere_bgnd_jacobi_sweep(Edges, nH, nHe, T, x, src, mu, wmu, E_eV, shape, fcA,
+                                       find_Teq, z, Hz, tol, F, gauss_seidel=gauss_seidel)
+        for il, (xc, Tc, acc) in out.items():
+            for q in range(5):
+                x[q][il] = xc[q]
+            T[il] = Tc
+            for q in range(6):
+                src[q][il] = acc[q]
+        assert it <= max_iter
+        it += 1
+        ne = x[1] * nH_ + (x[3] + F(2) * x[4]) * nHe_
+        done = bool(np.all(np.abs(ne / ne_old - F(1)) < F(tol)))
+        ne_old = ne
+        if done:
+            return x, T, src, it
+
+
+def solve_column_geometry(geom, Edges, nH, nHe, T, E_eV, shape, fcA, find_Teq, z, Hz, tol, F):
+    """The drivers of the other four geometries from the thin start to convergence:
+    'slab_plane_1' / 'slab_plane_2' (slab_plane.f90:105-345), 'sphere_stromgren'
+    (sphere_stromgren.f90:111-383, increasing Edges) and 'slab_bgnd' (slab_bgnd.f90:97-289: no
+    error at the sweep limit, it stops after 200).  Thin start: tau = 0 rates (per shell for the
+    point source) and the lock-step solvers over all layers; every sweep is Jacobi; the
+    two-sided slabs solve the first half and mirror fractions, temperature and rates.
+    Returns (x [5][Nl], T, src [6][Nl], sweeps)."""
+    E = np.asarray(Edges, dtype=F)
+    Ev, sh = np.asarray(E_eV, dtype=F), np.asarray(shape, dtype=F)
+    sig = [sigma_v96(X, Ev, F) for X in range(3)]
+    Nl = len(nH)
+    one = np.ones_like(Ev)
+    r_c = (E[:-1] + E[1:]) * F(0.5)
+    if geom == "slab_bgnd":
+        p = [_six_rates(Ev, sh, sig, one, F)] * Nl
+    elif geom == "sphere_stromgren":
+        p = [_src_rates("point", Ev, sh, sig, one, F, r=r_c[i]) for i in range(Nl)]
+    else:
+        p = [_src_rates("plane", Ev, sh, sig, one, F)] * Nl
+    tin = F(tol) * F(1.0e-2)
+    if find_Teq:
+        xs, Tn = solve_pcte_v(nH, nHe, p, z, Hz, (fcA,) * 3, tin, F)
+    else:
+        xs = solve_pce_v(nH, nHe, [get_kchem(T[i], (fcA,) * 3, F) for i in range(Nl)],
+                         [q[0] for q in p], [q[1] for q in p], [q[2] for q in p], tin, F)
+        Tn = T
+    x = np.array([[xs[i][q] for i in range(Nl)] for q in range(5)], dtype=F)
+    T = np.array(Tn, dtype=F)
+    src = np.array([[p[i][q] for i in range(Nl)] for q in range(6)], dtype=F)
+    nH_, nHe_ = np.asarray(nH, dtype=F), np.asarray(nHe, dtype=F)
+    ne_old = x[1] * nH_ + (x[3] + F(2) * x[4]) * nHe_
+    mirror = geom in ("slab_bgnd", "slab_plane_2")
+    it = 0
+    while True:
+        if geom == "slab_bgnd":
+            out = slab_bgnd_sweep(Edges, nH, nHe, T, x, E_eV, shape, fcA, find_Teq, z, Hz, tol, F)
+        else:
+            out = column_sweep(geom, Edges, nH, nHe, T, x, E_eV, shape, fcA, find_Teq, z, Hz,
+                               tol, F)
+        for il, (xc, Tc, acc) in out.items():
+            for j in ((il, Nl - 1 - il) if mirror else (il,)):
+                for q in range(5):
+                    x[q][j] = xc[q]
+                T[j] = Tc
+                for q in range(6):
+                    src[q][j] = acc[q]
+        if geom != "slab_bgnd":
+            assert it <= 500                    # tested before the increment
+        it += 1
+        ne = x[1] * nH_ + (x[3] + F(2) * x[4]) * nHe_
+        done = bool(np.all(np.abs(ne / ne_old - F(1)) < F(tol)))
+        ne_old = ne
+        if done or (geom == "slab_bgnd" and it >= 200):
+            return x, T, src, it

@@ -373,3 +373,66 @@ def test_thin_start_with_the_lock_step_solvers(orc, find_Teq):
             xs = so.solve_pce(cfg["nH"][i], cfg["nHe"][i], k[i], r6[0], r6[1], r6[2], 1e-6, np.float64)
             diff += int(any(float(xs[q]) != thin[kname][i] for q, kname in enumerate(FR)))
         assert diff > 0
+
+
+@pytest.mark.parametrize("order,find_Teq", [("jacobi", False), ("jacobi", True), ("gs", False)])
+def test_whole_sphere_bgnd_solve(orc, order, find_Teq):
+    """sphere_bgnd_solve (sphere_bgnd.f90:107-314): thin start, the 1/2 (old + sum) recurrence of
+    the rates across sweeps (Q1), the n_e convergence test -- the same sweep count and the same
+    converged state from both derivations, in the Jacobi order and in the reference's own
+    sequential order."""
+    Nl, Nnu, Nmu = 12, 12, 2
+    cfg = _sphere_cfg("uniform", Nl, Nnu, Nmu, find_Teq)
+    a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], Nmu, cfg["E_eV"], cfg["shape"])
+    ref = orc.sphere_bgnd_solve(*a, i_find_Teq=int(find_Teq), z=3.0,
+                                order=orc.ORDER_JACOBI if order == "jacobi" else orc.ORDER_GS)
+    rv = lambda v: np.asarray(v)[::-1].copy()  # noqa: E731
+    mu, w = orc.p_quadrature_rule(Nmu)
+    x, T, src, sweeps = so.sphere_bgnd_solve(rv(cfg["Edges"]), rv(cfg["nH"]), rv(cfg["nHe"]),
+                                             rv(cfg["T"]), mu, w, cfg["E_eV"], cfg["shape"], 1.0,
+                                             find_Teq, 3.0, 0.0, 1e-4, np.float64,
+                                             gauss_seidel=(order == "gs"))
+    assert sweeps == ref["iters"] and sweeps > 5
+    for q, k in enumerate(RT):
+        assert np.max(np.abs(rv(src[q]).astype(np.float64) / ref[k] - 1.0)) <= 1e-12, k
+    for q, k in enumerate(FR):
+        assert np.max(np.abs(rv(x[q]).astype(np.float64) / ref[k] - 1.0)) <= 1e-11, k
+    assert np.max(np.abs(rv(T).astype(np.float64) / ref["T"] - 1.0)) <= 1e-13
+
+
+@pytest.mark.parametrize("geom,find_Teq", [("slab_plane_1", False), ("slab_plane_1", True),
+                                           ("slab_plane_2", False), ("slab_bgnd", False),
+                                           ("slab_bgnd", True), ("sphere_stromgren", False)])
+def test_whole_solves_of_the_column_geometries(orc, geom, find_Teq):
+    """Drivers of SlabPln, Slab2Pln, Slab2Bgnd and SphereStromgren from the thin start (lock-step
+    solvers over all layers) to convergence: the same sweep count and state from both
+    derivations."""
+    Nl, Nnu = 16, 12
+    kw = dict(i_find_Teq=int(find_Teq), z=3.0)
+    if geom == "slab_bgnd":
+        cfg = configs.c3_slab_bgnd(Nl, Nnu, find_Teq)
+        a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], cfg["E_eV"], cfg["shape"])
+        ref = orc.slab_bgnd_solve(*a, **kw)
+    elif geom.startswith("slab"):
+        cfg = configs.c2_slab_plane(Nl, Nnu, find_Teq, two_sided=(geom == "slab_plane_2"))
+        a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], cfg["E_eV"], cfg["shape"])
+        ref = orc.slab_plane_solve(*a, i_2side=int(geom == "slab_plane_2"), **kw)
+    else:
+        cfg = configs.c1_iliev_stromgren(Nl)
+        a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], 1, cfg["E_eV"], cfg["shape"])
+        ref = orc.sphere_stromgren_solve(*a, fixed_fcA=cfg["fixed_fcA"], **kw)
+    x, T, src, sweeps = so.solve_column_geometry(geom, cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"],
+                                                 cfg["E_eV"], cfg["shape"], cfg["fixed_fcA"],
+                                                 find_Teq, 3.0, 0.0, 1e-4, np.float64)
+    assert sweeps == ref["iters"] and sweeps > 2, (sweeps, ref["iters"])
+    for q, k in enumerate(RT):
+        r = np.asarray(ref[k])
+        g = np.asarray(src[q], dtype=np.float64)
+        nz = r != 0.0
+        assert np.all(g[~nz] == 0.0)
+        if nz.any():
+            assert np.max(np.abs(g[nz] / r[nz] - 1.0)) <= 1e-12, k
+    assert np.all(np.asarray(ref["H1i_src"]) > 0.0)
+    for q, k in enumerate(FR):
+        assert np.max(np.abs(np.asarray(x[q], dtype=np.float64) / ref[k] - 1.0)) <= 1e-11, k
+    assert np.max(np.abs(np.asarray(T, dtype=np.float64) / ref["T"] - 1.0)) <= 1e-13
