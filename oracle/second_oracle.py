@@ -237,8 +237,13 @@ def _cell_solve(nH, nHe, T, r6, fcA, find_Teq, z, Hz, tol_in, F):
     return solve_pce(nH, nHe, get_kchem(T, (fcA,) * 3, F), r6[0], r6[1], r6[2], tol_in, F), F(T)
 
 
+def _plus(r6, rec, i, F):
+    """total rates of cell i: source + recombination photons (sphere_bgnd.f90:858-884)"""
+    return list(r6) if rec is None else [a + F(rec[q][i]) for q, a in enumerate(r6)]
+
+
 def sphere_bgnd_jacobi_sweep(Edges, nH, nHe, T, x, src, mu, wmu, E_eV, shape, fcA, find_Teq,
-                             z, Hz, tol, F, cells=None, gauss_seidel=False):
+                             z, Hz, tol, F, cells=None, gauss_seidel=False, rec=None):
     """One sweep of sphere_bgnd.f90:578-918 from state ``x`` [5][Nl] and source rates ``src``
     [6][Nl] (Edges decreasing).  Returns (x_new, T_new, src_new) for ``cells`` (default all).
     Jacobi order by default; ``gauss_seidel``: the loop exactly as the reference runs it with
@@ -274,8 +279,8 @@ def sphere_bgnd_jacobi_sweep(Edges, nH, nHe, T, x, src, mu, wmu, E_eV, shape, fc
             r6 = _six_rates(Ev, sh, sig, np.exp(-tau), F)
             acc = [a + r * F(wmu[imu]) for a, r in zip(acc, r6)]        # :837-848
         acc = [a * F(0.5) for a in acc]                                 # :850-856 (Q1)
-        xs, Tn = _cell_solve(nH_[il], nHe_[il], T[il], acc, fcA, find_Teq, z, Hz,
-                             F(tol) * F(1.0e-2), F)
+        xs, Tn = _cell_solve(nH_[il], nHe_[il], T[il], _plus(acc, rec, il, F), fcA, find_Teq, z,
+                             Hz, F(tol) * F(1.0e-2), F)
         out[il] = (xs, Tn, acc)
         if gauss_seidel:                                                # :886-907 in place
             for q in range(5):
@@ -302,7 +307,7 @@ def _e2xa(t, F):                               # zhang_jin_f.f90:94-173 (E1 inli
 
 
 def slab_bgnd_sweep(Edges, nH, nHe, T, x, E_eV, shape, fcA, find_Teq, z, Hz, tol, F,
-                    cells=None):
+                    cells=None, rec=None):
     """One sweep of slab_bgnd.f90:532-883 (first half; the mirror is a copy) from state x."""
     E = np.asarray(Edges, dtype=F)
     Ev, sh = np.asarray(E_eV, dtype=F), np.asarray(shape, dtype=F)
@@ -322,7 +327,7 @@ def slab_bgnd_sweep(Edges, nH, nHe, T, x, E_eV, shape, fcA, find_Teq, z, Hz, tol
             att = (np.ones_like(tau) if _ssum(tau) == 0                  # s_b.f90:380-383
                    else np.array([_e2xa(t, F) for t in tau], dtype=F))
             r6 = [a + r * F(0.5) for a, r in zip(r6, _six_rates(Ev, sh, sig, att, F))]
-        xs, Tn = _cell_solve(nH_[i], nHe_[i], T[i], r6, fcA, find_Teq, z, Hz,
+        xs, Tn = _cell_solve(nH_[i], nHe_[i], T[i], _plus(r6, rec, i, F), fcA, find_Teq, z, Hz,
                              F(tol) * F(1.0e-2), F)
         out[i] = (xs, Tn, r6)
     return out
@@ -351,7 +356,7 @@ def _src_rates(kind, E, shape, sig, att, F, r=None):
 
 
 def column_sweep(geom, Edges, nH, nHe, T, x, E_eV, shape, fcA, find_Teq, z, Hz, tol, F,
-                 cells=None):
+                 cells=None, rec=None):
     """One (Jacobi) sweep of the three column geometries from state ``x`` [5][Nl]:
     'slab_plane_1' (slab_plane.f90:551-830, source at the z = 0 face), 'slab_plane_2'
     (:832-1164: half of the flux from either side; only the first half is solved, the rest
@@ -382,7 +387,7 @@ def column_sweep(geom, Edges, nH, nHe, T, x, E_eV, shape, fcA, find_Teq, z, Hz, 
             r6 = [a * F(0.5) + b * F(0.5) for a, b in zip(lo, hi)]
         else:
             r6 = _src_rates(kind, Ev, sh, sig, att_from(0), F, r=r_c[i] if point else None)
-        xs, Tn = _cell_solve(nH_[i], nHe_[i], T[i], r6, fcA, find_Teq, z, Hz,
+        xs, Tn = _cell_solve(nH_[i], nHe_[i], T[i], _plus(r6, rec, i, F), fcA, find_Teq, z, Hz,
                              F(tol) * F(1.0e-2), F)
         out[i] = (xs, Tn, r6)
     return out
@@ -731,13 +736,28 @@ def sphere_bgnd_thin(nH, nHe, T, E_eV, shape, fcA, find_Teq, z, Hz, tol, F):
     return x, Tn, r6
 
 
+def sphere_rec(meth, Edges, nH, nHe, T, x, mu, wmu, em_fac, F):
+    """The closure ``meth`` ('outward', 'radial', 'isotropic') on a state given with
+    DECREASING edges: [6][Nl] rates (radial: the routine's own orientation is increasing)."""
+    if meth == "radial":
+        rv = lambda a: np.asarray(a)[::-1]  # noqa: E731
+        out = recomb_radial(rv(Edges), rv(nH), rv(nHe), rv(T), [rv(v) for v in x], F)
+        return [rv(o) for o in out]
+    if meth == "outward":
+        return list(recomb_outward(Edges, nH, nHe, T, x, F))
+    return list(recomb_isotropic(Edges, nH, nHe, T, x, mu, wmu, em_fac, F))
+
+
 def sphere_bgnd_solve(Edges, nH, nHe, T, mu, wmu, E_eV, shape, fcA, find_Teq, z, Hz, tol, F,
-                      gauss_seidel=False, max_iter=500):
+                      gauss_seidel=False, max_iter=500, rec_meth=None, em_fac=(1.0, 1.0, 1.0)):
     """sphere_bgnd_solve (sphere_bgnd.f90:107-314): thin start, then sweeps until
     all(|ne_new / ne_old - 1| < tol) (:284-296; the limit is tested before the increment).
-    ``Edges`` decreasing.  Returns (x [5][Nl], T, src [6][Nl], sweeps)."""
+    ``Edges`` decreasing.  ``rec_meth``: the recombination-photon closure evaluated at the top
+    of every sweep on the pre-sweep state (:676-745), its rates added to the source rates of
+    every cell.  Returns (x [5][Nl], T, src [6][Nl], sweeps[, rec [6][Nl]])."""
     Nl = len(nH)
     xs, Tn, r6 = sphere_bgnd_thin(nH, nHe, T, E_eV, shape, fcA, find_Teq, z, Hz, tol, F)
+    rec = None
     x = np.array([[xs[i][q] for i in range(Nl)] for q in range(5)], dtype=F)
     T = np.array(Tn, dtype=F)
     src = np.array([[r6[q]] * Nl for q in range(6)], dtype=F)
@@ -745,8 +765,11 @@ def sphere_bgnd_solve(Edges, nH, nHe, T, mu, wmu, E_eV, shape, fcA, find_Teq, z,
     ne_old = x[1] * nH_ + (x[3] + F(2) * x[4]) * nHe_
     it = 0
     while True:
+        if rec_meth:
+            rec = sphere_rec(rec_meth, Edges, nH, nHe, T, x, mu, wmu, em_fac, F)
         out = sphere_bgnd_jacobi_sweep(Edges, nH, nHe, T, x, src, mu, wmu, E_eV, shape, fcA,
-                                       find_Teq, z, Hz, tol, F, gauss_seidel=gauss_seidel)
+                                       find_Teq, z, Hz, tol, F, gauss_seidel=gauss_seidel,
+                                       rec=rec)
         for il, (xc, Tc, acc) in out.items():
             for q in range(5):
                 x[q][il] = xc[q]
@@ -759,10 +782,11 @@ def sphere_bgnd_solve(Edges, nH, nHe, T, mu, wmu, E_eV, shape, fcA, find_Teq, z,
         done = bool(np.all(np.abs(ne / ne_old - F(1)) < F(tol)))
         ne_old = ne
         if done:
-            return x, T, src, it
+            return (x, T, src, it) if rec is None else (x, T, src, it, np.array(rec, dtype=F))
 
 
-def solve_column_geometry(geom, Edges, nH, nHe, T, E_eV, shape, fcA, find_Teq, z, Hz, tol, F):
+def solve_column_geometry(geom, Edges, nH, nHe, T, E_eV, shape, fcA, find_Teq, z, Hz, tol, F,
+                          rec_meth=None):
     """The drivers of the other four geometries from the thin start to convergence:
     'slab_plane_1' / 'slab_plane_2' (slab_plane.f90:105-345), 'sphere_stromgren'
     (sphere_stromgren.f90:111-383, increasing Edges) and 'slab_bgnd' (slab_bgnd.f90:97-289: no
@@ -796,12 +820,24 @@ def solve_column_geometry(geom, Edges, nH, nHe, T, E_eV, shape, fcA, find_Teq, z
     ne_old = x[1] * nH_ + (x[3] + F(2) * x[4]) * nHe_
     mirror = geom in ("slab_bgnd", "slab_plane_2")
     it = 0
+    rec = None
     while True:
+        if rec_meth == "ray":                   # slabs: slab_base.f90:163-560, pre-sweep state
+            rec = [np.array(r, dtype=F) for r in recomb_slab(Edges, nH, nHe, T, x, F)]
+        elif rec_meth:                          # Stromgren sphere: increasing edges
+            rv = lambda a: np.asarray(a)[::-1]  # noqa: E731
+            rec = [rv(r) for r in sphere_rec(rec_meth, rv(Edges), rv(nH), rv(nHe), rv(T),
+                                             [rv(v) for v in x], None, None, (1.0,) * 3, F)]
         if geom == "slab_bgnd":
-            out = slab_bgnd_sweep(Edges, nH, nHe, T, x, E_eV, shape, fcA, find_Teq, z, Hz, tol, F)
+            out = slab_bgnd_sweep(Edges, nH, nHe, T, x, E_eV, shape, fcA, find_Teq, z, Hz, tol, F,
+                                  rec=rec)
         else:
             out = column_sweep(geom, Edges, nH, nHe, T, x, E_eV, shape, fcA, find_Teq, z, Hz,
-                               tol, F)
+                               tol, F, rec=rec)
+        if rec is not None and mirror:          # slab_bgnd.f90:842-865: rates reflected too
+            for r in rec:
+                for il in out:
+                    r[Nl - 1 - il] = r[il]
         for il, (xc, Tc, acc) in out.items():
             for j in ((il, Nl - 1 - il) if mirror else (il,)):
                 for q in range(5):
@@ -816,4 +852,4 @@ def solve_column_geometry(geom, Edges, nH, nHe, T, E_eV, shape, fcA, find_Teq, z
         done = bool(np.all(np.abs(ne / ne_old - F(1)) < F(tol)))
         ne_old = ne
         if done or (geom == "slab_bgnd" and it >= 200):
-            return x, T, src, it
+            return (x, T, src, it) if rec is None else (x, T, src, it, np.array(rec, dtype=F))

@@ -436,3 +436,57 @@ def test_whole_solves_of_the_column_geometries(orc, geom, find_Teq):
     for q, k in enumerate(FR):
         assert np.max(np.abs(np.asarray(x[q], dtype=np.float64) / ref[k] - 1.0)) <= 1e-11, k
     assert np.max(np.abs(np.asarray(T, dtype=np.float64) / ref["T"] - 1.0)) <= 1e-13
+
+
+RC = ("H1i_rec", "He1i_rec", "He2i_rec", "H1h_rec", "He1h_rec", "He2h_rec")
+
+
+@pytest.mark.parametrize("geom,meth", [("sphere_bgnd", "outward"), ("sphere_bgnd", "radial"),
+                                       ("sphere_bgnd", "isotropic"), ("slab_plane_1", "ray"),
+                                       ("slab_plane_2", "ray"), ("slab_bgnd", "ray"),
+                                       ("sphere_stromgren", "outward")])
+def test_whole_solves_with_recombination_photons(orc, geom, meth):
+    """rec_meth != fixed from the thin start to convergence: the closure at the top of every
+    sweep on the pre-sweep state, case-A coefficients, total = source + recombination rates."""
+    irec = {"outward": 2, "radial": 3, "isotropic": 4, "ray": 2}[meth]
+    kw = dict(z=3.0, i_rec_meth=irec)
+    if geom == "sphere_bgnd":
+        Nl, Nnu, Nmu = 12, 12, 2
+        cfg = _sphere_cfg("uniform", Nl, Nnu, Nmu, False)
+        a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], Nmu, cfg["E_eV"], cfg["shape"])
+        ref = orc.sphere_bgnd_solve(*a, order=orc.ORDER_JACOBI, em_fac=(1.0, 0.9, 1.1), **kw)
+        rv = lambda v: np.asarray(v)[::-1].copy()  # noqa: E731
+        mu, w = orc.p_quadrature_rule(Nmu)
+        x, T, src, sweeps, rec = so.sphere_bgnd_solve(
+            rv(cfg["Edges"]), rv(cfg["nH"]), rv(cfg["nHe"]), rv(cfg["T"]), mu, w, cfg["E_eV"],
+            cfg["shape"], 1.0, False, 3.0, 0.0, 1e-4, np.float64, rec_meth=meth,
+            em_fac=(1.0, 0.9, 1.1))
+        x, src, rec, T = [rv(v) for v in x], [rv(v) for v in src], [rv(v) for v in rec], rv(T)
+    else:
+        Nl, Nnu = 16, 12
+        if geom == "slab_bgnd":
+            cfg = configs.c3_slab_bgnd(Nl, Nnu, False)
+            a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], cfg["E_eV"], cfg["shape"])
+            ref = orc.slab_bgnd_solve(*a, **kw)
+        elif geom.startswith("slab"):
+            cfg = configs.c2_slab_plane(Nl, Nnu, False, two_sided=(geom == "slab_plane_2"))
+            a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], cfg["E_eV"], cfg["shape"])
+            ref = orc.slab_plane_solve(*a, i_2side=int(geom == "slab_plane_2"), **kw)
+        else:
+            cfg = configs.c1_iliev_stromgren(Nl)
+            cfg["nHe"] = cfg["nH"] * 0.08
+            a = (cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], 1, cfg["E_eV"], cfg["shape"])
+            ref = orc.sphere_stromgren_solve(*a, fixed_fcA=1.0, **kw)
+        x, T, src, sweeps, rec = so.solve_column_geometry(
+            geom, cfg["Edges"], cfg["nH"], cfg["nHe"], cfg["T"], cfg["E_eV"], cfg["shape"], 1.0,
+            False, 3.0, 0.0, 1e-4, np.float64, rec_meth=meth)
+    assert sweeps == ref["iters"] and sweeps > 2, (sweeps, ref["iters"])
+    for names, arr, tol in ((RT, src, 1e-11), (RC, rec, 1e-10), (FR, x, 1e-10)):
+        for q, k in enumerate(names):
+            r = np.asarray(ref[k])
+            g = np.asarray(arr[q], dtype=np.float64)
+            nz = r != 0.0
+            assert np.all(g[~nz] == 0.0), k
+            if nz.any():
+                assert np.max(np.abs(g[nz] / r[nz] - 1.0)) <= tol, (k, np.max(np.abs(g[nz] / r[nz] - 1.0)))
+    assert np.any(np.asarray(ref["H1i_rec"]) > 0.0)
