@@ -166,3 +166,38 @@ def compare(res_gpu, res_orc, names=CHECKED, rtol=1e-10, tol=1e-4):
     if solver_level:
         bad.update(solver_check(orc, res_gpu))
     return worst, bad
+
+
+def load_second_oracle_golden():
+    """tests/golden/second_oracle_solves.npz (made by make_second_oracle_golden.py from the
+    independent numpy derivation) -> {case: dict of inputs and outputs}"""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                             "second_oracle_solves.npz"))
+    cases = {}
+    for key in z.files:
+        name, field = key.split("/")
+        v = z[key]
+        cases.setdefault(name, {})[field] = v.item() if v.ndim == 0 else v
+    return cases
+
+
+def golden_cfg(g):
+    """the config dict run_gpu / run_oracle take, from a golden case"""
+    return dict(geometry=str(g["geometry"]), Edges=g["Edges"].copy(), nH=g["nH"].copy(),
+                nHe=g["nHe"].copy(), T=g["T0"].copy(), E_eV=g["E_eV"].copy(),
+                shape=g["shape"].copy(), fixed_fcA=float(g["fixed_fcA"]),
+                find_Teq=bool(g["find_Teq"]), z=float(g["z"]), Nmu=int(g["Nmu"]),
+                i_rec_meth=int(g["i_rec_meth"]), em_fac=tuple(float(v) for v in g["em_fac"]))
+
+
+def golden_diff(res, g, names):
+    """worst relative difference over ``names`` (exact zeros must match as zeros)"""
+    worst = 0.0
+    for k in names:
+        a, b = np.asarray(res[k], dtype=np.float64), np.asarray(g[k], dtype=np.float64)
+        nz = b != 0.0
+        assert np.all(a[~nz] == 0.0), k
+        if nz.any():
+            worst = max(worst, float(np.max(np.abs(a[nz] / b[nz] - 1.0))))
+    return worst

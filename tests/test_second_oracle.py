@@ -490,3 +490,19 @@ def test_whole_solves_with_recombination_photons(orc, geom, meth):
             if nz.any():
                 assert np.max(np.abs(g[nz] / r[nz] - 1.0)) <= tol, (k, np.max(np.abs(g[nz] / r[nz] - 1.0)))
     assert np.any(np.asarray(ref["H1i_rec"]) > 0.0)
+
+
+def test_committed_golden_solves_match_the_c_oracle(orc):
+    """tests/golden/second_oracle_solves.npz (whole solves by the numpy derivation, float64):
+    the C oracle on the stored inputs gives the same sweep counts and states -- the fixture the
+    GPU tests compare the CUDA path with (test_zz_gpu_second_oracle_golden.py)."""
+    from helpers import golden_cfg, golden_diff, load_second_oracle_golden, run_oracle
+    cases = load_second_oracle_golden()
+    assert len(cases) == 9
+    for name, g in cases.items():
+        ref = run_oracle(orc, golden_cfg(g))
+        assert ref["iters"] == int(g["iters"]), name
+        assert golden_diff(ref, g, RT) <= 1e-11, name
+        assert golden_diff(ref, g, RC) <= 1e-10, name
+        assert golden_diff(ref, g, FR) <= 1e-10, name
+        assert golden_diff(ref, g, ("T",)) <= 1e-13, name
