@@ -32,7 +32,7 @@ for n, d, b in rows:
 out += ["", "One rank's share alone on a GPU (`scratch/rank_share2.py`, no barrier skew), total ms per sweep: 0.694 / 0.400 / 0.252 / 0.190 at N = 1 / 2 / 4 / 8 with the",
 "launch-shape rule of the column kernel added after the N = 4 / 8 records above were taken (`r02z3_rank_share.log`; with the build of those records:",
 "0.696 / 0.402 / 0.270 / 0.205; single cells dealt cyclically instead of 32-cell blocks, earlier build: 0.805 / 0.476 / 0.326 / 0.266).", "",
-"Why one sweep does not scale further (DESIGN.md 6): the far-field moment scan (0.024 ms) is needed in full by every rank; ~0.05 ms of the column",
+"Why one sweep does not scale further (DESIGN.md 6): the far-field moment scan (0.018 ms) is needed in full by every rank; ~0.05 ms of the column",
 "kernel is per-CTA shared-memory fill and the latency of one warp's walk (with 2048 work items on 148 SMs every warp has one or two); 512 cells on 148",
 "SMs leave the frequency kernel's slowest SM with 4 cells against 3.46 on average; cell solve + finish are 0.035 ms of latency; the flag barrier adds",
 "the skew between the ranks (0.03-0.05 ms).  Round 1 measured 0.382 ms per sweep at N = 8 (from a 1.63 ms single-GPU sweep); now 0.26-0.27 ms from 0.72 ms,",
