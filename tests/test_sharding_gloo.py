@@ -129,3 +129,39 @@ def test_index_conventions():
     assert all(np.unique(d % 16).size == 16 for d in deals)
     assert np.array_equal(np.sort(np.concatenate(deals)), np.arange(8192))
     assert [sharding.deal_problems(10, r, 4).size for r in range(4)] == [3, 3, 2, 2]
+
+
+def test_deals_are_partitions_for_any_size():
+    """property test (hypothesis): for every world size and grid the cyclic deal, the block deal
+    where the peer path selects it, and the shuffled problem deal are partitions -- every cell /
+    problem is owned by exactly one rank -- and pack / unpack is the identity."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 8), st.integers(1, 700), st.booleans())
+    def check(world, ncell, mirror):
+        deal = sharding.peer_deal(world, ncell)
+        assert deal == (-world if ncell % (32 * world) == 0 else world)
+        for d in {world, deal}:
+            if d > 0 and ncell < world:
+                continue
+            own = [sharding.local_cells(g, world, ncell, d) for g in range(world)]
+            assert np.array_equal(np.sort(np.concatenate(own)), np.arange(ncell))
+            if d < 0 or ncell % world == 0:      # the exchange needs equal shares
+                Nl = 2 * ncell if mirror else ncell
+                f = np.arange(3 * Nl, dtype=float).reshape(3, Nl)
+                if mirror:
+                    f[:, ncell:] = f[:, :ncell][:, ::-1]
+                recv = np.stack([sharding.pack_cells(f, g, world, ncell, d) for g in range(world)])
+                out = sharding.unpack_cells(recv, np.zeros_like(f), world, ncell, mirror=mirror,
+                                            deal=d)
+                assert np.array_equal(out, f)
+        n = ncell * 3 + 1
+        parts = [sharding.deal_problems(n, r, world) for r in range(world)]
+        assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(n))
+        assert max(p.size for p in parts) - min(p.size for p in parts) <= 1
+        blocks = [sharding.shard_problems(n, r, world) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+
+    check()
